@@ -1,0 +1,194 @@
+/* sndvae.h -- C ABI of the B200-native SND-VAE train / generate step.
+ *
+ * The reference (xguo7/SND-VAE, TensorFlow 1.x) has no FFI: its only runtime
+ * boundary is `sess.run(fetches, feed_dict)` on the graph built by
+ * `SGCNModelVAE.__init__` (model.py:22, model_joint.py:14) and
+ * `OptimizerVAE.__init__` (optimizer.py:124).  This header is the C surface a
+ * drop-in for that boundary binds; each entry point
+ * cites the reference call it replaces.
+ *
+ * Conventions: every function returns 0 on success or a negative SNDVAE_E_*
+ * code; `sndvae_last_error(h)` gives the message.  No C++ exceptions cross the
+ * ABI.  Pointers are DEVICE pointers unless the name ends in `_host`.  The
+ * caller owns input/output buffers; the library owns parameters, gradients,
+ * Adam state and workspace.  All work is issued on the stream given at create
+ * time.  One handle per device, one host thread per handle (the reference has
+ * one driver thread, main.py:310-349).  There is no CPU fallback: create fails
+ * with SNDVAE_E_CUDA when no sm_100 device is present.
+ */
+#ifndef SNDVAE_H_
+#define SNDVAE_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNDVAE_OK          0
+#define SNDVAE_E_ARG      -1   /* bad argument / shape (TF: InvalidArgumentError) */
+#define SNDVAE_E_CUDA     -2   /* CUDA / cuBLAS failure, or no usable device */
+#define SNDVAE_E_DENSE    -3   /* a sampled adjacency row set exceeded the edge capacity */
+#define SNDVAE_E_STATE    -4   /* call sequence error */
+
+#define SNDVAE_MODEL_DISENTANGLED 0   /* model.py       (z_s, z_sg, z_g) */
+#define SNDVAE_MODEL_BASE         1   /* model_joint.py (z_sg only, S = 1) */
+
+/* Hyper-parameters = the reference's flags (main.py:42-103, synthetic2 block
+ * main.py:181-209).  Layer counts are those of the reference (2 graph conv, 3
+ * spatial conv, 2 SGC, 2 node deconv, 3 spatial deconv, 2 e2e); kernel size 5. */
+typedef struct sndvae_config {
+  int32_t model_type;        /* SNDVAE_MODEL_*                       main.py:72 */
+  int32_t num_nodes;         /* N                                     main.py:243 */
+  int32_t num_feature;       /* F  = FLAGS.num_feature                main.py:83 */
+  int32_t spatial_dim;       /* D  = FLAGS.spatial_dim                main.py:84 */
+  int32_t sampling_num;      /* S  = FLAGS.sampling_num (base: 1)     main.py:100 */
+  int32_t node_h_size;       /* H                                     main.py:209 */
+  int32_t s_channel[3];      /* spatial conv1d channels               main.py:183 */
+  int32_t s_hidden_size, s_latent_size;
+  int32_t g_conv_hidden[2];  /* graph conv channels                   main.py:190 */
+  int32_t g_hidden_size, g_latent_size;
+  int32_t sg_conv_hidden[2][3];                                    /* main.py:195 */
+  int32_t sg_hidden_size, sg_latent_size;
+  int32_t s_d_channel[3];    /* spatial deconv channels               main.py:200 */
+  int32_t n_d_channel[2];    /* node deconv channels                  main.py:205 */
+  int32_t e_d_hidden[2];     /* e2e channels                          main.py:209 */
+  int32_t batch_size;        /* B graphs per step = FLAGS.batch_size  main.py:213 */
+  int32_t chunk_graphs;      /* graphs per device micro-batch for the N^2 stages (0 = auto) */
+  int32_t edge_capacity;     /* per-sample nnz capacity of `adj` (0 = 4N) */
+  int32_t use_tensor_cores;  /* 1: tcgen05 bf16x3 e2e GEMMs; 0: fp32 SIMT reference kernels */
+  float   learning_rate;     /* FLAGS.learning_rate                   main.py:211 */
+  float   beta;              /* KL weight                             main.py:515 */
+  float   adam_beta1, adam_beta2, adam_eps;   /* tf.train.AdamOptimizer defaults */
+} sndvae_config;
+
+/* The eight feeds of construct_feed_dict_train (preprocessing.py:32-42) with
+ * the static shapes of main.py:253-264.  fp32, C-contiguous.  `spatial` and
+ * `rel_truth` are accepted and unused on this path. */
+typedef struct sndvae_inputs {
+  const float* features;       /* [B*S, N, F] */
+  const float* spatial;        /* [B*S, N, D]   (unused; may be NULL) */
+  const float* adj;            /* [B*S, N, N]   row b*S+s = sample s of graph b */
+  const float* rel;            /* [B*S, N, N, 1] */
+  const float* adj_truth;      /* [B, N, N] */
+  const float* feature_truth;  /* [B, N, F] */
+  const float* spatial_truth;  /* [B, N, D] */
+  const float* rel_truth;      /* [B, N, N, 1]  (unused; may be NULL) */
+} sndvae_inputs;
+
+/* The tf.random.normal draws of get_z / get_random_z (model.py:153-169) made
+ * explicit so that results are reproducible against the oracle. */
+typedef struct sndvae_noise {
+  const float* eps_s;          /* [B, Ls]     (NULL for base) */
+  const float* eps_sg;         /* [B*S, Lsg] */
+  const float* eps_g;          /* [B, Lg]     (NULL for base) */
+} sndvae_noise;
+
+/* Model attributes a caller fetches (model.py:78-80,114-151).  Any pointer may
+ * be NULL = not fetched. */
+typedef struct sndvae_outputs {
+  float* z_mean_s;  float* z_std_s;   float* z_s;     /* [B, Ls]    */
+  float* z_mean_g;  float* z_std_g;   float* z_g;     /* [B, Lg]    */
+  float* z_mean_sg; float* z_std_sg;  float* z_sg;    /* [B*S, Lsg] */
+  int64_t* generated_adj;         /* [B, N, N]    tf.argmax -> int64 (model.py:208) */
+  float* generated_adj_prob;      /* [B, N, N, 2] masked logits   (model.py:207) */
+  float* generated_spatial;       /* [B, N, D] */
+  float* generated_node_feat;     /* [B, N, F] */
+} sndvae_outputs;
+
+typedef struct sndvae_handle sndvae_t;
+
+/* One parameter of tf.trainable_variables() (model.py:92-94): TF variable
+ * name, offset (in floats) into the flat arenas, shape. */
+typedef struct sndvae_param_info {
+  char    name[64];
+  int64_t offset;
+  int64_t size;
+  int32_t rank;
+  int32_t shape[4];
+} sndvae_param_info;
+
+/* Fill a config with the synthetic2 defaults (main.py:181-215). */
+int sndvae_default_config(sndvae_config* cfg_host);
+
+/* Replaces SGCNModelVAE(...) + OptimizerVAE(...) + tf.Session() +
+ * global_variables_initializer (model.py:22, optimizer.py:124, main.py:301-302).
+ * `stream` is a cudaStream_t (NULL = default stream).  Parameters start at
+ * zero; load them with sndvae_set_params. */
+int sndvae_create(const sndvae_config* cfg_host, void* stream, sndvae_t** out);
+int sndvae_destroy(sndvae_t* h);
+const char* sndvae_last_error(const sndvae_t* h);
+
+/* tf.trainable_variables() in creation order. */
+int64_t sndvae_param_count(const sndvae_t* h);        /* padded arena length in floats */
+int32_t sndvae_num_params(const sndvae_t* h);
+int sndvae_param_table(const sndvae_t* h, sndvae_param_info* table_host, int32_t capacity);
+
+/* tf.train.Saver save/restore of variables and Adam slots (main.py:299,351-352).
+ * Host buffers of sndvae_param_count floats. */
+int sndvae_get_params(sndvae_t* h, float* params_host);
+int sndvae_set_params(sndvae_t* h, const float* params_host);
+int sndvae_get_adam(sndvae_t* h, float* m_host, float* v_host, float* beta_pows_host /*[2]*/);
+int sndvae_set_adam(sndvae_t* h, const float* m_host, const float* v_host, const float* beta_pows_host);
+
+/* Device pointers of the library-owned arenas (for NCCL all-reduce of the
+ * gradient arena and zero-copy views from the host language). */
+float* sndvae_params_device(sndvae_t* h);
+float* sndvae_grads_device(sndvae_t* h);
+
+/* sess.run([model.z_*, model.generated_*], feed) with FLAGS.type in
+ * {'train','test_reconstruct'} (main.py:368-371): encoder, get_z, decoder.
+ * losses_host (may be NULL) receives optimizer.overall_loss (optimizer.py:200-203):
+ * [cost, spatial, adj, node, kl_g, kl_s, kl_sg] (base: 5 entries, last = kl_sg). */
+int sndvae_forward(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* noise,
+                   sndvae_outputs* out, float* losses_host);
+
+/* optimizer.compute_gradients(cost) (optimizer.py:198): forward + backward
+ * into the gradient arena, no update.  The arena holds LOCAL-shard sums scaled
+ * by 1/(global batch): with `global_batch` = world * B the all-reduced arena is
+ * the full-batch gradient.  global_batch <= 0 means B. */
+int sndvae_grads(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* noise,
+                 sndvae_outputs* out, float* losses_host, int64_t global_batch);
+
+/* The apply half of AdamOptimizer.minimize (optimizer.py:197): TF1 ApplyAdam on
+ * the whole arena using the current gradient arena. */
+int sndvae_apply_adam(sndvae_t* h);
+
+/* sess.run([opt.opt_op, opt.overall_loss, model.generated_adj], feed)
+ * (main.py:331): forward, backward and Adam on one device. */
+int sndvae_train_step(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* noise,
+                      sndvae_outputs* out, float* losses_host);
+
+/* model.sample(z) with FLAGS.type == 'test_generation' (model.py:83-85,
+ * 163-169,227-229): decoder only, from caller-provided latents. */
+int sndvae_generate(sndvae_t* h, const float* z_s, const float* z_sg, const float* z_g,
+                    sndvae_outputs* out);
+
+/* Same call as sndvae_train_step but with HOST buffers in and out, like the
+ * reference's feed_dict (numpy in, numpy out; main.py:327-331): copies the
+ * feeds host->device, runs the step, copies losses and generated_adj back. */
+int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in_host, const sndvae_noise* noise_host,
+                           int64_t* generated_adj_host, float* losses_host);
+
+/* Number of library kernels launched since create (bench.py's gpu_launches). */
+int64_t sndvae_launch_count(const sndvae_t* h);
+
+/* Average duration (ms) and launch count of the e2e layer-1 GEMM launches
+ * (forward + dgrad + wgrad) since the last reset, measured with CUDA events on
+ * the handle's stream; used for bench.py's roofline block. */
+int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms_host, int64_t* launches_host,
+                       double* flops_host);
+
+/* argmax(softmax([l0,l1])) of model.py:208 on caller logits [n,2] -> int64 [n];
+ * exposed so the thresholding rule can be checked bit-exactly on its own. */
+int sndvae_threshold_logits(sndvae_t* h, const float* logits, int64_t n, int64_t* out);
+
+/* Read a named intermediate buffer of the last chunk (debug / parity tests).
+ * Returns the number of floats written, or a negative error. */
+int64_t sndvae_debug_read(sndvae_t* h, const char* name, float* dst_host, int64_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNDVAE_H_ */

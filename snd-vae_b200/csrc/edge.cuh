@@ -1,0 +1,380 @@
+// edge.cuh -- the N x N edge-logit decoder (model.py:196-208, layers.py:431-450)
+// and its backward, in the exact collapsed form of SURVEY Appendix C.2 / C.3 / F.
+//
+//   a_i = relu(BN_e0[:Ch](v_i)),  c_j = relu(BN_e0[Ch:](v_j))            (never tiled to N x N)
+//   E1[i,j] = a_i WSa[j] + c_j WSc[i] + Rc[j] + Sa[i] + 2 b0             (e2e layer 0, collapsed)
+//   Y = relu(BN_e1(E1))
+//   O[i,j]  = sum_{j'} Y[i,j'] w1[j'-j+p] + sum_{i'} Y[i',j] w1[i'-i+p] + 2 b1   (e2e layer 1: the hot GEMM)
+//   logits  = relu(BN_decadj(O)) Me + be, diagonal mask, argmax(softmax), 2-class CE
+//
+// Staging formats between kernels ("stacked" = direction 0 row-major [b,i,j,c],
+// direction 1 transposed [b,j,i,c], so that both e2e directions are one GEMM):
+//   fp32 mode (SIMT reference path): Y2 / dO2 are float, channel stride C1 / C2
+//   bf16 mode (tcgen05 path): Y2 / dO2 are bf16 hi + lo planes, channel stride CP / OP (zero padded)
+#pragma once
+#include "common.cuh"
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// ---- e2e layer 0: per-step weight sums  WS[pos][o][ch] = sum_{t valid(pos)} w0[t][coff+ch][o] -----
+// valid(pos): 0 <= pos + t - p < N  (zero padding of the width-N SAME conv, layers.py:436,443)
+__global__ void e2e_l0_prep_k(const float* __restrict__ w0, float* __restrict__ WS, int N, int Ctot, int coff,
+                              int Ch, int C1) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * C1 * Ch) return;
+  int ch = idx % Ch; int o = (idx / Ch) % C1; int pos = idx / ((long long)Ch * C1);
+  int p = (N - 1) / 2;
+  int tlo = max(0, p - pos), thi = min(N - 1, N - 1 + p - pos);
+  float acc = 0.f;
+  for (int t = tlo; t <= thi; ++t) acc += w0[((size_t)t * Ctot + coff + ch) * C1 + o];
+  WS[idx] = acc;
+}
+
+// dw0[t][coff+ch][o] += sum_{pos valid(t)} dWS[pos][o][ch]
+__global__ void e2e_l0_prep_bwd_k(const float* __restrict__ dWS, float* __restrict__ dw0, int N, int Ctot, int coff,
+                                  int Ch, int C1) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Ch * C1) return;
+  int o = idx % C1; int ch = (idx / C1) % Ch; int t = idx / ((long long)C1 * Ch);
+  int p = (N - 1) / 2;
+  int lo = max(0, p - t), hi = min(N - 1, N - 1 + p - t);
+  float acc = 0.f;
+  for (int pos = lo; pos <= hi; ++pos) acc += dWS[((size_t)pos * C1 + o) * Ch + ch];
+  dw0[((size_t)t * Ctot + coff + ch) * C1 + o] += acc;
+}
+
+// ---- Toeplitz row-vector products (the Rc / Sa terms of layer 0), fp32 SIMT -----------------------
+// out[b,pos,o] = sum_{pos'} sum_ch in[b,pos',ch] w[pos'-pos+p][coff+ch][o]
+__global__ void toep_vec_fwd_k(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                               long long B, int N, int Ctot, int coff, int Ch, int C1) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N * C1) return;
+  int o = idx % C1; int pos = (idx / C1) % N; long long b = idx / ((long long)C1 * N);
+  int p = (N - 1) / 2;
+  const float* x = in + b * N * Ch;
+  float acc = 0.f;
+  int lo = max(0, pos - p), hi = min(N - 1, pos + N - 1 - p);
+  for (int q = lo; q <= hi; ++q) {
+    const float* wr = w + ((size_t)(q - pos + p) * Ctot + coff) * C1 + o;
+    const float* xr = x + q * Ch;
+    for (int ch = 0; ch < Ch; ++ch) acc = fmaf(xr[ch], wr[ch * C1], acc);
+  }
+  out[idx] = acc;
+}
+
+// din[b,pos',ch] += sum_pos sum_o dout[b,pos,o] w[pos'-pos+p][coff+ch][o]
+__global__ void toep_vec_bwd_in_k(const float* __restrict__ dout, const float* __restrict__ w, float* __restrict__ din,
+                                  long long B, int N, int Ctot, int coff, int Ch, int C1) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N * Ch) return;
+  int ch = idx % Ch; int q = (idx / Ch) % N; long long b = idx / ((long long)Ch * N);
+  int p = (N - 1) / 2;
+  const float* d = dout + b * N * C1;
+  float acc = 0.f;
+  int lo = max(0, q + p - (N - 1)), hi = min(N - 1, q + p);
+  for (int pos = lo; pos <= hi; ++pos) {
+    const float* wr = w + ((size_t)(q - pos + p) * Ctot + coff + ch) * C1;
+    const float* dr = d + pos * C1;
+    for (int o = 0; o < C1; ++o) acc = fmaf(dr[o], wr[o], acc);
+  }
+  din[idx] += acc;
+}
+
+// dw[t][coff+ch][o] += sum_b sum_pos in[b,pos+t-p,ch] dout[b,pos,o];  grid.y splits the batch
+#define TOEP_BG 8
+__global__ void toep_vec_bwd_w_k(const float* __restrict__ in, const float* __restrict__ dout, float* __restrict__ dw,
+                                 long long B, int N, int Ctot, int coff, int Ch, int C1) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * Ch * C1) return;
+  int o = idx % C1; int ch = (idx / C1) % Ch; int t = idx / ((long long)C1 * Ch);
+  int p = (N - 1) / 2;
+  long long b0 = (long long)blockIdx.y * TOEP_BG, b1 = b0 + TOEP_BG; if (b1 > B) b1 = B;
+  int lo = max(0, p - t), hi = min(N - 1, N - 1 + p - t);
+  float acc = 0.f;
+  for (long long b = b0; b < b1; ++b) {
+    const float* x = in + b * N * Ch; const float* d = dout + b * N * C1;
+    for (int pos = lo; pos <= hi; ++pos) acc = fmaf(x[(pos + t - p) * Ch + ch], d[pos * C1 + o], acc);
+  }
+  atomicAdd(dw + ((size_t)t * Ctot + coff + ch) * C1 + o, acc);
+}
+
+// ---- Y producer: E1 (fp32, kept for the BN_e1 backward) and Y = relu(BN_e1(E1)) ------------------
+// one CTA per (graph, i); threads loop over (j, o).
+struct YOut {
+  float* E1;              // [Bc, N, N, C1]
+  float* Yf;              // fp32 mode: [2][Bc*N][N*C1]
+  __nv_bfloat16* Yhi;     // bf16 mode: [2][Bc*N][N*CP]
+  __nv_bfloat16* Ylo;
+  int CP;
+  int bf16;
+};
+__global__ void __launch_bounds__(256) y_producer_k(const float* __restrict__ a, const float* __restrict__ c,
+                                                    const float* __restrict__ WSa, const float* __restrict__ WSc,
+                                                    const float* __restrict__ Rc, const float* __restrict__ Sa,
+                                                    const float* __restrict__ b0, const float* __restrict__ gam1,
+                                                    const float* __restrict__ bet1, YOut Y, int Bc, int N, int Ch, int C1) {
+  extern __shared__ float sm[];
+  float* sa = sm;                 // [Ch]  a_i
+  float* ssa = sm + Ch;           // [C1]  Sa_i + 2 b0
+  long long row = blockIdx.x;     // local (b, i)
+  int i = (int)(row % N); long long b = row / N;
+  for (int t = threadIdx.x; t < Ch; t += blockDim.x) sa[t] = a[row * Ch + t];
+  for (int t = threadIdx.x; t < C1; t += blockDim.x) ssa[t] = Sa[row * C1 + t] + 2.f * b0[t];
+  __syncthreads();
+  const float* wci = WSc + (size_t)i * C1 * Ch;     // WSc[i][o][ch]
+  long long plane = (long long)Bc * N * N;           // elements per direction / channel stride
+  for (int idx = threadIdx.x; idx < N * C1; idx += blockDim.x) {
+    int j = idx / C1, o = idx - j * C1;
+    const float* wa = WSa + ((size_t)j * C1 + o) * Ch;
+    const float* wc = wci + (size_t)o * Ch;
+    const float* cj = c + (b * N + j) * Ch;
+    float acc = ssa[o] + Rc[(b * N + j) * C1 + o];
+    for (int ch = 0; ch < Ch; ++ch) { acc = fmaf(sa[ch], wa[ch], acc); acc = fmaf(cj[ch], wc[ch], acc); }
+    Y.E1[row * N * C1 + idx] = acc;
+    float y = fmaxf(fmaf(acc, gam1[o] * BN_RS, bet1[o]), 0.f);
+    long long e0 = (b * N + i) * N + j, e1 = (b * N + j) * N + i;     // [b,i,j] and [b,j,i]
+    if (Y.bf16) {
+      __nv_bfloat16 hi, lo; split_bf16(y, hi, lo);
+      Y.Yhi[e0 * Y.CP + o] = hi; Y.Ylo[e0 * Y.CP + o] = lo;
+      Y.Yhi[(plane + e1) * Y.CP + o] = hi; Y.Ylo[(plane + e1) * Y.CP + o] = lo;
+    } else {
+      Y.Yf[e0 * C1 + o] = y; Y.Yf[(plane + e1) * C1 + o] = y;
+    }
+  }
+}
+
+// ---- e2e layer 1, fp32 SIMT reference kernels (stacked operands, one "row" = (dir, b, r)) --------
+// out[row, s, q] = sum_{s'} sum_o Yf[row, s', o] w1[s'-s+p][o][q]
+__global__ void e2e_l1_simt_fwd_k(const float* __restrict__ Yf, const float* __restrict__ w1, float* __restrict__ out,
+                                  long long rows, int N, int C1, int C2) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * N * C2) return;
+  int q = idx % C2; int s = (idx / C2) % N; long long row = idx / ((long long)C2 * N);
+  int p = (N - 1) / 2;
+  const float* y = Yf + row * N * C1;
+  float acc = 0.f;
+  int lo = max(0, s - p), hi = min(N - 1, s + N - 1 - p);
+  for (int sp = lo; sp <= hi; ++sp) {
+    const float* wr = w1 + (size_t)(sp - s + p) * C1 * C2 + q;
+    const float* yr = y + sp * C1;
+    for (int o = 0; o < C1; ++o) acc = fmaf(yr[o], wr[o * C2], acc);
+  }
+  out[idx] = acc;
+}
+// dY[row, s', o] = sum_s sum_q dO[row, s, q] w1[s'-s+p][o][q]
+__global__ void e2e_l1_simt_dgrad_k(const float* __restrict__ dOf, const float* __restrict__ w1, float* __restrict__ dY,
+                                    long long rows, int N, int C1, int C2) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * N * C1) return;
+  int o = idx % C1; int sp = (idx / C1) % N; long long row = idx / ((long long)C1 * N);
+  int p = (N - 1) / 2;
+  const float* d = dOf + row * N * C2;
+  float acc = 0.f;
+  int lo = max(0, sp + p - (N - 1)), hi = min(N - 1, sp + p);
+  for (int s = lo; s <= hi; ++s) {
+    const float* wr = w1 + ((size_t)(sp - s + p) * C1 + o) * C2;
+    const float* dr = d + s * C2;
+    for (int q = 0; q < C2; ++q) acc = fmaf(dr[q], wr[q], acc);
+  }
+  dY[idx] = acc;
+}
+// dw1[t][o][q] += sum_rows sum_s Yf[row, s+t-p, o] dO[row, s, q];  grid.y splits the rows
+#define WGRAD_RG 64
+__global__ void e2e_l1_simt_wgrad_k(const float* __restrict__ Yf, const float* __restrict__ dOf, float* __restrict__ dw1,
+                                    long long rows, int N, int C1, int C2) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * C1 * C2) return;
+  int q = idx % C2; int o = (idx / C2) % C1; int t = idx / ((long long)C2 * C1);
+  int p = (N - 1) / 2;
+  long long r0 = (long long)blockIdx.y * WGRAD_RG, r1 = r0 + WGRAD_RG; if (r1 > rows) r1 = rows;
+  int lo = max(0, p - t), hi = min(N - 1, N - 1 + p - t);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float* y = Yf + r * N * C1; const float* d = dOf + r * N * C2;
+    for (int s = lo; s <= hi; ++s) acc = fmaf(y[(s + t - p) * C1 + o], d[s * C2 + q], acc);
+  }
+  atomicAdd(dw1 + idx, acc);
+}
+
+// ---- edge epilogue: logits, mask, threshold, CE loss, and dO (fused forward tail + backward head) -
+// TF semantics (model.py:203-208, optimizer.py:142-144): softmax in fp32 as exp(x-max)/sum, first
+// index wins ties.  CE = logsumexp - label logit; d/dl1 = softmax1 - A = -d/dl0; diagonal masked.
+struct EpiParams {
+  const float* O12;       // [2][Bc*N][N*C2]: dir 0 [b,i,j,q], dir 1 [b,j,i,q]
+  const float* b1;        // e1 biases [C2]
+  const float* gd; const float* bd;   // decoder_adj BN (NULL for base)
+  const float* Me; const float* be;   // d_e_lin2 [C2,2], [2]
+  const float* At;        // adj_truth chunk [Bc,N,N] (NULL: no loss / no backward)
+  long long* gen_adj;     // [Bc,N,N] or NULL
+  float* logits;          // [Bc,N,N,2] or NULL
+  float* dOf;             // fp32 mode [2][Bc*N][N*C2]
+  __nv_bfloat16* dOhi; __nv_bfloat16* dOlo;   // bf16 mode [2][Bc*N][N*OP]
+  int OP; int bf16; int backward;
+  float* loss_sum;        // CE sum
+  float* g_b1; float* g_gd; float* g_bd; float* g_Me; float* g_be;   // gradient slots
+  float gscale;           // 1 / (B_global N^2)
+};
+#define EPI_C2 20
+#define EPI_EPT 4
+__global__ void __launch_bounds__(128) edge_epilogue_k(EpiParams P, int Bc, int N) {
+  const int C2 = EPI_C2;
+  long long total = (long long)Bc * N * N;
+  long long plane = total;
+  float wme0[EPI_C2], wme1[EPI_C2], gsc[EPI_C2], gsh[EPI_C2], bb[EPI_C2];
+#pragma unroll
+  for (int q = 0; q < C2; ++q) {
+    wme0[q] = P.Me[q * 2]; wme1[q] = P.Me[q * 2 + 1];
+    gsc[q] = P.gd ? P.gd[q] * BN_RS : 1.f; gsh[q] = P.bd ? P.bd[q] : 0.f;
+    bb[q] = 2.f * P.b1[q];
+  }
+  float be0 = P.be[0], be1 = P.be[1];
+  float acc_dO[EPI_C2], acc_gg[EPI_C2], acc_gb[EPI_C2], acc_m0[EPI_C2];
+#pragma unroll
+  for (int q = 0; q < C2; ++q) { acc_dO[q] = 0.f; acc_gg[q] = 0.f; acc_gb[q] = 0.f; acc_m0[q] = 0.f; }
+  float acc_l1 = 0.f, loss = 0.f;
+  long long base = ((long long)blockIdx.x * blockDim.x) * EPI_EPT + threadIdx.x;
+  for (int it = 0; it < EPI_EPT; ++it) {
+    long long e = base + (long long)it * blockDim.x;
+    if (e >= total) break;
+    int j = (int)(e % N); int i = (int)((e / N) % N); long long b = e / ((long long)N * N);
+    long long et = (b * N + j) * N + i;
+    const float4* o1 = reinterpret_cast<const float4*>(P.O12 + e * C2);
+    const float4* o2 = reinterpret_cast<const float4*>(P.O12 + (plane + et) * C2);
+    float O[EPI_C2];
+#pragma unroll
+    for (int v = 0; v < C2 / 4; ++v) {
+      float4 x = o1[v], y = o2[v];
+      O[4 * v] = x.x + y.x + bb[4 * v]; O[4 * v + 1] = x.y + y.y + bb[4 * v + 1];
+      O[4 * v + 2] = x.z + y.z + bb[4 * v + 2]; O[4 * v + 3] = x.w + y.w + bb[4 * v + 3];
+    }
+    float l0 = be0, l1 = be1;
+    float Z[EPI_C2];
+#pragma unroll
+    for (int q = 0; q < C2; ++q) {
+      float z = fmaxf(fmaf(O[q], gsc[q], gsh[q]), 0.f);
+      Z[q] = z; l0 = fmaf(z, wme0[q], l0); l1 = fmaf(z, wme1[q], l1);
+    }
+    float m = (i == j) ? 0.f : 1.f;
+    float p0 = m * l0 + (1.f - m), p1 = m * l1;           // model.py:205-206
+    if (P.logits) { P.logits[e * 2] = p0; P.logits[e * 2 + 1] = p1; }
+    float mx = fmaxf(p0, p1);
+    float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
+    float s = e0 + e1;
+    float s0 = e0 / s, s1 = e1 / s;
+    if (P.gen_adj) P.gen_adj[e] = (s1 > s0) ? 1 : 0;      // tf.argmax: first index on ties
+    if (P.At) {
+      float A = P.At[e];
+      float lse = mx + logf(s);
+      loss += lse - ((1.f - A) * p0 + A * p1);
+      if (P.backward) {
+        float d1 = m * (s1 - A) * P.gscale;               // dL/dl1 = -dL/dl0
+        acc_l1 += d1;
+        float dOv[EPI_C2];
+#pragma unroll
+        for (int q = 0; q < C2; ++q) {
+          acc_m0[q] = fmaf(Z[q], d1, acc_m0[q]);          // dMe[q,1] = +, dMe[q,0] = -
+          float dz = d1 * (wme1[q] - wme0[q]);
+          float dd = Z[q] > 0.f ? dz : 0.f;
+          acc_gg[q] = fmaf(dd, O[q], acc_gg[q]); acc_gb[q] += dd;
+          float d = dd * gsc[q];
+          dOv[q] = d; acc_dO[q] += d;
+        }
+        if (P.bf16) {
+          __nv_bfloat16 hi[EPI_C2], lo[EPI_C2];
+#pragma unroll
+          for (int q = 0; q < C2; ++q) split_bf16(dOv[q], hi[q], lo[q]);
+          __nv_bfloat16* h0 = P.dOhi + e * P.OP; __nv_bfloat16* l0p = P.dOlo + e * P.OP;
+          __nv_bfloat16* h1 = P.dOhi + (plane + et) * P.OP; __nv_bfloat16* l1p = P.dOlo + (plane + et) * P.OP;
+#pragma unroll
+          for (int q = 0; q < C2; ++q) { h0[q] = hi[q]; l0p[q] = lo[q]; h1[q] = hi[q]; l1p[q] = lo[q]; }
+        } else {
+          float* f0 = P.dOf + e * C2; float* f1 = P.dOf + (plane + et) * C2;
+#pragma unroll
+          for (int q = 0; q < C2; ++q) { f0[q] = dOv[q]; f1[q] = dOv[q]; }
+        }
+      }
+    }
+  }
+  // reductions: warp shuffle, then one atomic per warp and value
+  int lane = threadIdx.x & 31;
+  loss = warp_sum(loss);
+  if (lane == 0 && P.loss_sum && P.At) atomicAdd(P.loss_sum, loss);
+  if (P.backward && P.At) {
+    acc_l1 = warp_sum(acc_l1);
+    if (lane == 0) { atomicAdd(P.g_be + 1, acc_l1); atomicAdd(P.g_be, -acc_l1); }
+#pragma unroll
+    for (int q = 0; q < C2; ++q) {
+      float v0 = warp_sum(acc_m0[q]), v1 = warp_sum(acc_gg[q]), v2 = warp_sum(acc_gb[q]), v3 = warp_sum(acc_dO[q]);
+      if (lane == 0) {
+        atomicAdd(P.g_Me + q * 2 + 1, v0); atomicAdd(P.g_Me + q * 2, -v0);
+        if (P.g_gd) { atomicAdd(P.g_gd + q, v1 * BN_RS); atomicAdd(P.g_bd + q, v2); }
+        atomicAdd(P.g_b1 + q, 2.f * v3);                  // bias added twice (layers.py:438,446)
+      }
+    }
+  }
+}
+
+// standalone thresholding rule of model.py:208 on caller logits
+__global__ void threshold_logits_k(const float* __restrict__ lg, long long n, long long* __restrict__ out) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  float p0 = lg[idx * 2], p1 = lg[idx * 2 + 1];
+  float mx = fmaxf(p0, p1);
+  float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
+  float s = e0 + e1;
+  out[idx] = (e1 / s > e0 / s) ? 1 : 0;
+}
+
+// ---- combine the two dgrad directions, go back through relu / BN_e1 --------------------------------
+// dY = dY12[0][b,i,j,:] + dY12[1][b,j,i,:];  dE1 = dY * 1[BN(E1) > 0] * g1, written IN PLACE to both
+// layouts (each CTA touches exactly the locations it reads).  One CTA per (b, i), blockDim = 5 * C1.
+__global__ void l0_combine_k(float* __restrict__ dY12, const float* __restrict__ E1, const float* __restrict__ gam1,
+                             const float* __restrict__ bet1, float* __restrict__ g_gam1, float* __restrict__ g_bet1,
+                             float* __restrict__ g_b0, int Bc, int N, int C1) {
+  extern __shared__ float sm[];           // [3][blockDim]
+  long long row = blockIdx.x;
+  int i = (int)(row % N); long long b = row / N;
+  long long plane = (long long)Bc * N * N * C1;
+  int o = threadIdx.x % C1;
+  float g = gam1[o] * BN_RS, bt = bet1[o];
+  float sg = 0.f, sb = 0.f, s0 = 0.f;
+  for (int idx = threadIdx.x; idx < N * C1; idx += blockDim.x) {
+    int j = idx / C1;
+    long long a0 = row * N * C1 + idx;
+    long long a1 = plane + ((b * N + j) * N + i) * C1 + o;
+    float dy = dY12[a0] + dY12[a1];
+    float e = E1[a0];
+    float dd = fmaf(e, g, bt) > 0.f ? dy : 0.f;
+    sg = fmaf(dd, e, sg); sb += dd;
+    float de = dd * g;
+    s0 += de;
+    dY12[a0] = de; dY12[a1] = de;
+  }
+  float* r0 = sm; float* r1 = sm + blockDim.x; float* r2 = sm + 2 * blockDim.x;
+  r0[threadIdx.x] = sg; r1[threadIdx.x] = sb; r2[threadIdx.x] = s0;
+  __syncthreads();
+  if (threadIdx.x < C1) {
+    float a = 0.f, bq = 0.f, cq = 0.f;
+    for (int t = threadIdx.x; t < blockDim.x; t += C1) { a += r0[t]; bq += r1[t]; cq += r2[t]; }
+    atomicAdd(g_gam1 + o, a * BN_RS); atomicAdd(g_bet1 + o, bq); atomicAdd(g_b0 + o, 2.f * cq);
+  }
+}
+
+// out[row, o] (+)= sum_s in[row, s, o]   (dSa from dE1, dRc from dE1^T); one CTA per row, blockDim = k*C
+__global__ void rowsum_k(const float* __restrict__ in, float* __restrict__ out, int N, int C) {
+  extern __shared__ float sm[];
+  long long row = blockIdx.x;
+  int o = threadIdx.x % C;
+  float s = 0.f;
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) s += in[row * N * C + idx];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f;
+    for (int t = threadIdx.x; t < blockDim.x; t += C) a += sm[t];
+    out[row * C + o] = a;
+  }
+}

@@ -1,0 +1,279 @@
+// layers.cuh -- node-level layers of the SND-VAE encoders / decoders (fp32 SIMT).
+// These stages are O(N * C^2) per graph and together well under 1% of a train
+// step at N=256; they are written for clarity and coalescing, the
+// heavy N^2 stages live in sgc.cuh / edge.cuh / e2e_tc.cuh.
+// All activations are row-major [rows, C] with rows = (graph, node).
+#pragma once
+#include "common.cuh"
+
+// ---- per-node linear:  out[r, co] = act(bias[co] + sum_ci in[r, ci] W[ci, co]) ---------
+// (layers.py:566-576 `linear` on [B*N, C] rows; GraphConvolution's x.w, layers.py:121)
+__global__ void rowlin_fwd_k(const float* __restrict__ in, int ldi, const float* __restrict__ W,
+                             const float* __restrict__ bias, float* __restrict__ out, int ldo,
+                             long long rows, int Ci, int Co, int act) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Co) return;
+  long long r = idx / Co; int co = (int)(idx - r * Co);
+  float acc = bias ? bias[co] : 0.f;
+  const float* x = in + r * ldi;
+  for (int ci = 0; ci < Ci; ++ci) acc = fmaf(x[ci], W[ci * Co + co], acc);
+  out[r * ldo + co] = act_f(act, acc);
+}
+
+// din[r, ci] (+)= sum_co dout[r, co] W[ci, co]
+__global__ void rowlin_bwd_in_k(const float* __restrict__ dout, int ldd, const float* __restrict__ W,
+                                float* __restrict__ din, int ldi, long long rows, int Ci, int Co, int accumulate) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Ci) return;
+  long long r = idx / Ci; int ci = (int)(idx - r * Ci);
+  const float* d = dout + r * ldd;
+  float acc = 0.f;
+  for (int co = 0; co < Co; ++co) acc = fmaf(d[co], W[ci * Co + co], acc);
+  if (accumulate) din[r * ldi + ci] += acc; else din[r * ldi + ci] = acc;
+}
+
+// ---- conv1d over the node axis, k taps, SAME zero padding (model.py:122,191,216) -------
+// out[b, n, co] = bias[co] + sum_t sum_ci in[b, n + t - pb, ci] K[t, ci, co],  pb = (k-1)/2
+__global__ void conv1d_fwd_k(const float* __restrict__ in, const float* __restrict__ K,
+                             const float* __restrict__ bias, float* __restrict__ out,
+                             long long rows, int N, int Ci, int Co, int ktaps) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Co) return;
+  long long r = idx / Co; int co = (int)(idx - r * Co);
+  int n = (int)(r % N);
+  int pb = (ktaps - 1) / 2;
+  float acc = bias[co];
+  for (int t = 0; t < ktaps; ++t) {
+    int nn = n + t - pb;
+    if (nn < 0 || nn >= N) continue;
+    const float* x = in + (r + t - pb) * Ci;
+    const float* w = K + (size_t)t * Ci * Co + co;
+    for (int ci = 0; ci < Ci; ++ci) acc = fmaf(x[ci], w[ci * Co], acc);
+  }
+  out[idx] = acc;
+}
+
+// din[b, n', ci] = sum_t sum_co dout[b, n' - t + pb, co] K[t, ci, co]
+__global__ void conv1d_bwd_in_k(const float* __restrict__ dout, const float* __restrict__ K,
+                                float* __restrict__ din, long long rows, int N, int Ci, int Co, int ktaps) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Ci) return;
+  long long r = idx / Ci; int ci = (int)(idx - r * Ci);
+  int n = (int)(r % N);
+  int pb = (ktaps - 1) / 2;
+  float acc = 0.f;
+  for (int t = 0; t < ktaps; ++t) {
+    int nn = n - t + pb;
+    if (nn < 0 || nn >= N) continue;
+    const float* d = dout + (r - t + pb) * Co;
+    const float* w = K + ((size_t)t * Ci + ci) * Co;
+    for (int co = 0; co < Co; ++co) acc = fmaf(d[co], w[co], acc);
+  }
+  din[idx] = acc;
+}
+
+// ---- weight gradients:  dW[t, ci, co] += sum_r X[r + t - pb, ci] dY[r, co]  ------------
+// (ktaps = 1: plain X^T dY for `linear` / graph-conv weights).  Each block owns a
+// slab of rows, each thread a strided set of (t, ci, co); one atomicAdd per
+// (block, parameter).
+#define XTDY_SLAB 512
+__global__ void xtdy_k(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
+                       float* __restrict__ dW, long long rows, int N, int Ci, int Co, int ktaps) {
+  long long r0 = (long long)blockIdx.x * XTDY_SLAB;
+  long long r1 = r0 + XTDY_SLAB; if (r1 > rows) r1 = rows;
+  int pb = (ktaps - 1) / 2;
+  int np = ktaps * Ci * Co;
+  for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    int co = p % Co; int q = p / Co; int ci = q % Ci; int t = q / Ci;
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      int nn = (int)(r % N) + t - pb;
+      if (nn < 0 || nn >= N) continue;
+      acc = fmaf(X[(r + t - pb) * ldx + ci], dY[r * ldy + co], acc);
+    }
+    atomicAdd(dW + p, acc);
+  }
+}
+
+// db[c] += sum_r dY[r, c]
+__global__ void colsum_k(const float* __restrict__ dY, int ldy, float* __restrict__ db, long long rows, int C) {
+  long long r0 = (long long)blockIdx.x * XTDY_SLAB;
+  long long r1 = r0 + XTDY_SLAB; if (r1 > rows) r1 = rows;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (long long r = r0; r < r1; ++r) acc += dY[r * ldy + c];
+    atomicAdd(db + c, acc);
+  }
+}
+
+// ---- Keras BN (inference affine, SURVEY finding 3) fused with an activation ------------
+// order 0: out = act(bn(in))   (model.py:122-123,146: relu/lrelu after BN)
+// order 1: out = bn(act(in))   (model.py:107: BN of GraphConvolution's lrelu output)
+__global__ void bn_act_fwd_k(const float* __restrict__ in, int ldi, const float* __restrict__ gamma,
+                             const float* __restrict__ beta, float* __restrict__ out, int ldo,
+                             long long rows, int C, int act, int order) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  long long r = idx / C; int c = (int)(idx - r * C);
+  float x = in[r * ldi + c];
+  float g = gamma ? gamma[c] * BN_RS : 1.f, b = beta ? beta[c] : 0.f;
+  float y = order == 0 ? act_f(act, fmaf(x, g, b)) : fmaf(act_f(act, x), g, b);
+  out[r * ldo + c] = y;
+}
+
+// backward of the above.  din may alias dout.  dgamma/dbeta accumulate (atomics).
+#define BN_SLAB 256
+__global__ void bn_act_bwd_k(const float* __restrict__ dout, int ldd, const float* __restrict__ in, int ldi,
+                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                             float* din, int ldn, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                             long long rows, int C, int act, int order) {
+  long long r0 = (long long)blockIdx.x * BN_SLAB;
+  long long r1 = r0 + BN_SLAB; if (r1 > rows) r1 = rows;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float g = gamma ? gamma[c] * BN_RS : 1.f, b = beta ? beta[c] : 0.f;
+    float sg = 0.f, sb = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      float x = in[r * ldi + c];
+      float d = dout[r * ldd + c];
+      float dx;
+      if (order == 0) {
+        float pre = fmaf(x, g, b);
+        float dd = d * act_g(act, pre);
+        sg += dd * x; sb += dd; dx = dd * g;
+      } else {
+        sg += d * act_f(act, x); sb += d; dx = d * g * act_g(act, x);
+      }
+      if (din) din[r * ldn + c] = dx;
+    }
+    if (dgamma) { atomicAdd(dgamma + c, sg * BN_RS); atomicAdd(dbeta + c, sb); }
+  }
+}
+
+// copy a column block:  out[r, oc + c] = in[r, ic + c]  (concat / split)
+__global__ void copy_cols_k(const float* __restrict__ in, int ldi, int ic, float* __restrict__ out, int ldo, int oc,
+                            long long rows, int C, int accumulate) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  long long r = idx / C; int c = (int)(idx - r * C);
+  float v = in[r * ldi + ic + c];
+  if (accumulate) out[r * ldo + oc + c] += v; else out[r * ldo + oc + c] = v;
+}
+
+// ---- GraphConvolution propagate (layers.py:122): c[b,i,h] = sum_j A[b,i,j] t[b,j,h] ----
+// one warp per (graph,row); lanes stride over j (coalesced A reads), zeros skipped.
+template <int HMAX>
+__global__ void graph_prop_fwd_k(const float* __restrict__ A, const float* __restrict__ t,
+                                 float* __restrict__ c, long long rows, int N, int H) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long b = row / N;
+  const float* a = A + row * N;
+  const float* tb = t + b * N * H;
+  float acc[HMAX];
+#pragma unroll
+  for (int h = 0; h < HMAX; ++h) acc[h] = 0.f;
+  for (int j = lane; j < N; j += 32) {
+    float av = a[j];
+    if (av != 0.f) {
+      const float* tj = tb + (size_t)j * H;
+#pragma unroll
+      for (int h = 0; h < HMAX; ++h) if (h < H) acc[h] = fmaf(av, tj[h], acc[h]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < HMAX; ++h) {
+    if (h < H) {
+      float v = warp_sum(acc[h]);
+      if (lane == 0) c[row * H + h] = v;
+    }
+  }
+}
+
+// dt[b,j,h] += sum_i A[b,i,j] dc[b,i,h]   (dt must be zeroed by the caller)
+__global__ void graph_prop_bwd_k(const float* __restrict__ A, const float* __restrict__ dc,
+                                 float* __restrict__ dt, long long rows, int N, int H) {
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long b = row / N;
+  const float* a = A + row * N;
+  const float* d = dc + row * H;
+  float* tb = dt + b * N * H;
+  for (int j = lane; j < N; j += 32) {
+    float av = a[j];
+    if (av != 0.f) {
+      for (int h = 0; h < H; ++h) atomicAdd(tb + (size_t)j * H + h, av * d[h]);
+    }
+  }
+}
+
+// ---- reparameterisation + KL (model.py:153-161, optimizer.py:160-162) -----------------
+// z = mu + eps * exp(ls);  kl_sum += -0.5 * sum(1 + 2 ls - mu^2 - exp(ls)^2)
+__global__ void reparam_kl_k(const float* __restrict__ mu, const float* __restrict__ ls,
+                             const float* __restrict__ eps, float* __restrict__ z,
+                             float* __restrict__ kl_sum, long long n) {
+  __shared__ float red[32];
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float k = 0.f;
+  if (idx < n) {
+    float m = mu[idx], l = ls[idx];
+    float e = expf(l);
+    z[idx] = fmaf(eps[idx], e, m);
+    k = -0.5f * (1.f + 2.f * l - m * m - e * e);
+  }
+  k = block_sum(k, red);
+  if (threadIdx.x == 0) atomicAdd(kl_sum, k);
+}
+
+// dmu = dz + w*mu;  dls = dz*eps*exp(ls) + w*(exp(2 ls) - 1),  w = beta/(rows_global*L)
+// dz_rep > 1: dz row index = row / dz_rep and scaled by 1/dz_rep (the S-mean, model.py:180)
+__global__ void reparam_kl_bwd_k(const float* __restrict__ mu, const float* __restrict__ ls,
+                                 const float* __restrict__ eps, const float* __restrict__ dz,
+                                 float* __restrict__ dmu, float* __restrict__ dls,
+                                 long long rows, int L, int dz_rep, float w) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * L) return;
+  long long r = idx / L; int c = (int)(idx - r * L);
+  float g = dz[(r / dz_rep) * L + c] / (float)dz_rep;
+  float m = mu[idx], l = ls[idx];
+  float e = expf(l);
+  dmu[idx] = g + w * m;
+  dls[idx] = g * eps[idx] * e + w * (e * e - 1.f);
+}
+
+// zbar[b, c] = mean_s z[b*S + s, c]   (S-mean hoisted before d_sg_lin1; exact, linear)
+__global__ void smean_k(const float* __restrict__ z, float* __restrict__ zbar, long long B, int S, int L) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * L) return;
+  long long b = idx / L; int c = (int)(idx - b * L);
+  float acc = 0.f;
+  for (int s = 0; s < S; ++s) acc += z[(b * S + s) * L + c];
+  zbar[idx] = acc / (float)S;
+}
+
+// ---- sigmoid + MSE head (model.py:193,218; optimizer.py:149,153) -----------------------
+// pred = sigmoid(pre); loss_sum += sum (target - pred)^2; dpre = 2 (pred - target) pred (1 - pred) * scale
+__global__ void sigmoid_mse_k(const float* __restrict__ pre, const float* __restrict__ target,
+                              float* __restrict__ pred, float* __restrict__ dpre,
+                              float* __restrict__ loss_sum, long long n, float scale) {
+  __shared__ float red[32];
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (idx < n) {
+    float p = 1.f / (1.f + expf(-pre[idx]));
+    pred[idx] = p;
+    if (target) {
+      float d = p - target[idx];
+      l = d * d;
+      if (dpre) dpre[idx] = 2.f * d * p * (1.f - p) * scale;
+    }
+  }
+  l = block_sum(l, red);
+  if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, l);
+}
+
+__global__ void add_inplace_k(float* __restrict__ a, const float* __restrict__ b, long long n) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) a[idx] += b[idx];
+}

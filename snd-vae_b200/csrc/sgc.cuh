@@ -1,0 +1,347 @@
+// sgc.cuh -- SpatialGraphConvolution (layers.py:143-198) in its exact factored
+// form, on per-sample edge lists.
+//
+//   m3s_ij = A_ij [ deg_j (P_i + Q_j + phi(r_ij) w4 + b1) + (A Rm)_j + s_j w5 + G_ij w6 ]
+//   m2s_i  = deg_i (U_i + b2) + (A V)_i + s_i M2c + (sum_j A_ij phi(m3s_ij)) M2d
+//   out_i  = phi([x_i || m2s_i]) M3 + b3
+// with P,Q,Rm = phi(x) M1[0:C],[C:2C],[2C:3C]; U,V = phi(x) M2[0:C],[C:2C];
+// deg_j = sum_k A_jk, s_j = sum_k A_jk phi(r_jk), G_ij = sum_k A_jk phi(r_ik).
+// Every term is multiplied by A_ij, so only stored (non-zero) entries of the
+// sampled adjacency matter; the samples are spanning forests
+// (input_data.py:18-38: nnz <= 2(N-1)).  sgc_build_edges_k streams `adj` once
+// (the HBM-bound stage of the encoder) and gathers the few `rel` entries needed.
+#pragma once
+#include "common.cuh"
+
+struct SgcEdges {        // per-sample edge storage, capacity `cap` entries per sample
+  int*   rowstart;       // [samples, N]
+  int*   rowcnt;         // [samples, N]
+  int*   erow;           // [samples, cap]
+  int*   ecol;           // [samples, cap]
+  float* ea;             // [samples, cap]  A_ij
+  float* epr;            // [samples, cap]  phi(r_ij)
+  float* eG;             // [samples, cap]  G_ij
+  float* deg;            // [samples, N]
+  float* ssum;           // [samples, N]
+  int*   nedges;         // [samples]
+  int    cap;
+};
+
+// One CTA per sample.  Pass A per row: count non-zeros (streams the adjacency
+// row, 128-bit loads when N % 4 == 0); allocate a contiguous slot range; pass B
+// re-reads the row (L1-hot) and writes (col, a, phi(rel)).  Then G per edge.
+__global__ void __launch_bounds__(256) sgc_build_edges_k(const float* __restrict__ adj, const float* __restrict__ rel,
+                                                         SgcEdges E, int N, int* __restrict__ err) {
+  __shared__ int s_count;
+  long long smp = blockIdx.x;
+  const float* A = adj + smp * N * N;
+  const float* R = rel + smp * N * N;
+  int* rowstart = E.rowstart + smp * N;
+  int* rowcnt = E.rowcnt + smp * N;
+  int* erow = E.erow + smp * E.cap;
+  int* ecol = E.ecol + smp * E.cap;
+  float* ea = E.ea + smp * E.cap;
+  float* epr = E.epr + smp * E.cap;
+  float* eG = E.eG + smp * E.cap;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bool vec = (N % 4) == 0;
+  for (int i = warp; i < N; i += nw) {
+    const float* a = A + (size_t)i * N;
+    int cnt = 0;
+    if (vec) {
+      const float4* a4 = reinterpret_cast<const float4*>(a);
+      for (int q = lane; q < N / 4; q += 32) {
+        float4 v = __ldg(a4 + q);
+        cnt += (v.x != 0.f) + (v.y != 0.f) + (v.z != 0.f) + (v.w != 0.f);
+      }
+    } else {
+      for (int j = lane; j < N; j += 32) cnt += (__ldg(a + j) != 0.f);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_count, cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane == 0) { rowstart[i] = base; rowcnt[i] = (base + cnt <= E.cap) ? cnt : 0; }
+    float dsum = 0.f, ss = 0.f;
+    if (base + cnt <= E.cap) {
+      int pos = base;
+      for (int j0 = 0; j0 < N; j0 += 32) {
+        int j = j0 + lane;
+        float av = j < N ? a[j] : 0.f;
+        unsigned m = __ballot_sync(0xffffffffu, av != 0.f);
+        if (av != 0.f) {
+          int p = pos + __popc(m & ((1u << lane) - 1u));
+          float pr = lrelu_f(__ldg(R + (size_t)i * N + j));
+          erow[p] = i; ecol[p] = j; ea[p] = av; epr[p] = pr;
+          dsum += av; ss += av * pr;
+        }
+        pos += __popc(m);
+      }
+    }
+    dsum = warp_sum(dsum); ss = warp_sum(ss);
+    if (lane == 0) { E.deg[smp * N + i] = dsum; E.ssum[smp * N + i] = ss; }
+  }
+  __syncthreads();
+  int ne = s_count;
+  if (ne > E.cap) { if (threadIdx.x == 0) { atomicExch(err, 1); E.nedges[smp] = 0; } return; }
+  if (threadIdx.x == 0) E.nedges[smp] = ne;
+  // G_ij = sum_{k in nbr(j)} A_jk phi(r_ik)
+  for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+    int i = erow[e], j = ecol[e];
+    int s0 = rowstart[j], c0 = rowcnt[j];
+    float g = 0.f;
+    for (int q = s0; q < s0 + c0; ++q) g = fmaf(ea[q], lrelu_f(__ldg(R + (size_t)i * N + ecol[q])), g);
+    eG[e] = g;
+  }
+}
+
+struct SgcW {            // parameter (or gradient) pointers of one SGC layer
+  float *M1, *b1, *M2, *b2, *M3, *b3;
+  int C, h0, h1, h2;
+};
+
+struct SgcScratch {      // per-sample activations of one layer (global memory)
+  float* apx;            // [samples, N, C]   sum_k A_jk phi(x_k)
+  float* T;              // [samples, N, h0]
+  float* m2s;            // [samples, N, h1]
+  float* y;              // [samples, N, h2]  layer output before BN
+  // backward
+  float* dm2s;           // [samples, N, h1]
+  float* dT;             // [samples, N, h0]
+  float* ee;             // [samples, cap, h0]
+  float* dpx;            // [samples, N, C]
+  float* dapx;           // [samples, N, C]
+};
+
+// bracket of m3s for edge (i,j), channel h (without the leading A_ij)
+__device__ __forceinline__ float sgc_bracket(const SgcW& W, const float* __restrict__ x, const float* __restrict__ apx,
+                                             int i, int j, int h, float degj, float sj, float pr, float G) {
+  const int C = W.C, h0 = W.h0;
+  float pq = 0.f, ar = 0.f;
+  for (int c = 0; c < C; ++c) {
+    pq = fmaf(lrelu_f(x[i * C + c]), W.M1[c * h0 + h], pq);
+    pq = fmaf(lrelu_f(x[j * C + c]), W.M1[(C + c) * h0 + h], pq);
+    ar = fmaf(apx[j * C + c], W.M1[(2 * C + c) * h0 + h], ar);
+  }
+  return degj * (pq + pr * W.M1[(3 * C) * h0 + h] + W.b1[h]) + ar + sj * W.M1[(3 * C + 1) * h0 + h] +
+         G * W.M1[(3 * C + 2) * h0 + h];
+}
+
+// forward of one SGC layer; one CTA per sample (sample index = blockIdx.x + s_off)
+__global__ void __launch_bounds__(256) sgc_layer_fwd_k(const float* __restrict__ xin, SgcEdges E, SgcW W, SgcScratch Sx,
+                                                       int N, long long e_off) {
+  long long ls = blockIdx.x;             // local sample (scratch / x index)
+  long long gs = ls + e_off;             // global sample (edge storage index)
+  const int C = W.C, h0 = W.h0, h1 = W.h1, h2 = W.h2;
+  const float* x = xin + ls * N * C;
+  const int* rowstart = E.rowstart + gs * N; const int* rowcnt = E.rowcnt + gs * N;
+  const int* ecol = E.ecol + gs * E.cap;
+  const float* ea = E.ea + gs * E.cap; const float* epr = E.epr + gs * E.cap; const float* eG = E.eG + gs * E.cap;
+  const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
+  float* apx = Sx.apx + ls * N * C; float* T = Sx.T + ls * N * h0;
+  float* m2s = Sx.m2s + ls * N * h1; float* y = Sx.y + ls * N * h2;
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+    int i = idx / C, c = idx - i * C;
+    float acc = 0.f;
+    for (int q = rowstart[i]; q < rowstart[i] + rowcnt[i]; ++q) acc = fmaf(ea[q], lrelu_f(x[ecol[q] * C + c]), acc);
+    apx[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * h0; idx += blockDim.x) {
+    int i = idx / h0, h = idx - i * h0;
+    float acc = 0.f;
+    for (int q = rowstart[i]; q < rowstart[i] + rowcnt[i]; ++q) {
+      int j = ecol[q];
+      float br = sgc_bracket(W, x, apx, i, j, h, deg[j], ssum[j], epr[q], eG[q]);
+      acc = fmaf(ea[q], lrelu_f(ea[q] * br), acc);
+    }
+    T[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * h1; idx += blockDim.x) {
+    int i = idx / h1, h = idx - i * h1;
+    float u = W.b2[h], av = 0.f;
+    for (int c = 0; c < C; ++c) {
+      u = fmaf(lrelu_f(x[i * C + c]), W.M2[c * h1 + h], u);
+      av = fmaf(apx[i * C + c], W.M2[(C + c) * h1 + h], av);
+    }
+    float acc = deg[i] * u + av + ssum[i] * W.M2[(2 * C) * h1 + h];
+    for (int k = 0; k < h0; ++k) acc = fmaf(T[i * h0 + k], W.M2[(2 * C + 1 + k) * h1 + h], acc);
+    m2s[idx] = acc;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * h2; idx += blockDim.x) {
+    int i = idx / h2, h = idx - i * h2;
+    float acc = W.b3[h];
+    for (int c = 0; c < C; ++c) acc = fmaf(lrelu_f(x[i * C + c]), W.M3[c * h2 + h], acc);
+    for (int k = 0; k < h1; ++k) acc = fmaf(lrelu_f(m2s[i * h1 + k]), W.M3[(C + k) * h2 + h], acc);
+    y[idx] = acc;
+  }
+}
+
+// backward of one SGC layer w.r.t. activations; one CTA per sample.
+// dy: [samples, N, h2].  dx (optional): [samples, N, C] gradient w.r.t. the layer input.
+// Leaves dm2s / ee in scratch for sgc_param_grad_k.
+__global__ void __launch_bounds__(256) sgc_layer_bwd_k(const float* __restrict__ xin, const float* __restrict__ dyin,
+                                                       float* __restrict__ dxout, SgcEdges E, SgcW W, SgcScratch Sx,
+                                                       int N, long long e_off) {
+  long long ls = blockIdx.x, gs = ls + e_off;
+  const int C = W.C, h0 = W.h0, h1 = W.h1, h2 = W.h2;
+  const float* x = xin + ls * N * C;
+  const float* dy = dyin + ls * N * h2;
+  const int* rowstart = E.rowstart + gs * N; const int* rowcnt = E.rowcnt + gs * N;
+  const int* erow = E.erow + gs * E.cap; const int* ecol = E.ecol + gs * E.cap;
+  const float* ea = E.ea + gs * E.cap; const float* epr = E.epr + gs * E.cap; const float* eG = E.eG + gs * E.cap;
+  const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
+  const int ne = E.nedges[gs];
+  const float* apx = Sx.apx + ls * N * C; const float* m2s = Sx.m2s + ls * N * h1;
+  float* dm2s = Sx.dm2s + ls * N * h1; float* dT = Sx.dT + ls * N * h0;
+  float* ee = Sx.ee + ls * (long long)E.cap * h0;
+  float* dpx = Sx.dpx + ls * N * C; float* dapx = Sx.dapx + ls * N * C;
+  float* dx = dxout ? dxout + ls * N * C : nullptr;
+  // (a) through M3 and the lrelu of the concat [x || m2s]
+  int qlo = dx ? 0 : C;
+  for (int idx = threadIdx.x; idx < N * (C + h1 - qlo); idx += blockDim.x) {
+    int i = idx / (C + h1 - qlo), q = qlo + idx - i * (C + h1 - qlo);
+    float cv = q < C ? x[i * C + q] : m2s[i * h1 + q - C];
+    float acc = 0.f;
+    for (int k = 0; k < h2; ++k) acc = fmaf(dy[i * h2 + k], W.M3[q * h2 + k], acc);
+    acc *= lrelu_g(cv);
+    if (q < C) dx[i * C + q] = acc; else dm2s[i * h1 + q - C] = acc;
+  }
+  __syncthreads();
+  // (b) through M2
+  for (int idx = threadIdx.x; idx < N * h0; idx += blockDim.x) {
+    int i = idx / h0, k = idx - i * h0;
+    float acc = 0.f;
+    for (int h = 0; h < h1; ++h) acc = fmaf(dm2s[i * h1 + h], W.M2[(2 * C + 1 + k) * h1 + h], acc);
+    dT[idx] = acc;
+  }
+  if (dx) {
+    for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+      int i = idx / C, c = idx - i * C;
+      float a0 = 0.f, a1 = 0.f;
+      for (int h = 0; h < h1; ++h) {
+        float d = dm2s[i * h1 + h];
+        a0 = fmaf(d, W.M2[c * h1 + h], a0);
+        a1 = fmaf(d, W.M2[(C + c) * h1 + h], a1);
+      }
+      dpx[idx] = deg[i] * a0; dapx[idx] = a1;
+    }
+  }
+  __syncthreads();
+  // (c) per (edge, channel): gradient w.r.t. the bracket
+  for (int idx = threadIdx.x; idx < ne * h0; idx += blockDim.x) {
+    int e = idx / h0, h = idx - e * h0;
+    int i = erow[e], j = ecol[e];
+    float a = ea[e];
+    float br = sgc_bracket(W, x, apx, i, j, h, deg[j], ssum[j], epr[e], eG[e]);
+    ee[idx] = a * a * dT[i * h0 + h] * lrelu_g(a * br);
+  }
+  __syncthreads();
+  if (!dx) return;
+  // (d) edge contributions to d phi(x) and d apx
+  for (int idx = threadIdx.x; idx < ne * C; idx += blockDim.x) {
+    int e = idx / C, c = idx - e * C;
+    int i = erow[e], j = ecol[e];
+    float dj = deg[j];
+    float si = 0.f, sj = 0.f, sa = 0.f;
+    for (int h = 0; h < h0; ++h) {
+      float v = ee[e * h0 + h];
+      si = fmaf(v, W.M1[c * h0 + h], si);
+      sj = fmaf(v, W.M1[(C + c) * h0 + h], sj);
+      sa = fmaf(v, W.M1[(2 * C + c) * h0 + h], sa);
+    }
+    atomicAdd(dpx + i * C + c, dj * si);
+    atomicAdd(dpx + j * C + c, dj * sj);
+    atomicAdd(dapx + j * C + c, sa);
+  }
+  __syncthreads();
+  // (e) apx_j = sum_k A_jk phi(x_k):  d phi(x_k) += A_jk d apx_j
+  for (int idx = threadIdx.x; idx < ne * C; idx += blockDim.x) {
+    int e = idx / C, c = idx - e * C;
+    atomicAdd(dpx + ecol[e] * C + c, ea[e] * dapx[erow[e] * C + c]);
+  }
+  __syncthreads();
+  // (f) dx = dx_direct + dphi(x) * phi'(x)
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) dx[idx] += dpx[idx] * lrelu_g(x[idx]);
+}
+
+// parameter gradients of one SGC layer.  grid = (ceil(nparams/256), sample groups);
+// each thread owns one parameter entry, loops over SGC_PG samples, one atomicAdd.
+#define SGC_PG 16
+__global__ void __launch_bounds__(256) sgc_param_grad_k(const float* __restrict__ xin, const float* __restrict__ dyin,
+                                                        SgcEdges E, SgcW W, SgcW G, SgcScratch Sx, int N,
+                                                        long long nsamples, long long e_off) {
+  const int C = W.C, h0 = W.h0, h1 = W.h1, h2 = W.h2;
+  const int n1 = (3 * C + 4) * h0;          // M1 rows + bias1
+  const int n2 = (2 * C + 2 + h0) * h1;     // M2 rows + bias2
+  const int n3 = (C + h1 + 1) * h2;         // M3 rows + bias3
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n1 + n2 + n3) return;
+  long long s0 = (long long)blockIdx.y * SGC_PG, s1 = s0 + SGC_PG;
+  if (s1 > nsamples) s1 = nsamples;
+  float acc = 0.f;
+  float* dst;
+  if (p < n1) {
+    int row = p / h0, h = p - row * h0;
+    dst = row < 3 * C + 3 ? G.M1 + row * h0 + h : G.b1 + h;
+    for (long long ls = s0; ls < s1; ++ls) {
+      long long gs = ls + e_off;
+      const float* x = xin + ls * N * C; const float* apx = Sx.apx + ls * N * C;
+      const float* ee = Sx.ee + ls * (long long)E.cap * h0;
+      const int* erow = E.erow + gs * E.cap; const int* ecol = E.ecol + gs * E.cap;
+      const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
+      const float* epr = E.epr + gs * E.cap; const float* eG = E.eG + gs * E.cap;
+      int ne = E.nedges[gs];
+      for (int e = 0; e < ne; ++e) {
+        int i = erow[e], j = ecol[e];
+        float coef;
+        if (row < C) coef = deg[j] * lrelu_f(x[i * C + row]);
+        else if (row < 2 * C) coef = deg[j] * lrelu_f(x[j * C + row - C]);
+        else if (row < 3 * C) coef = apx[j * C + row - 2 * C];
+        else if (row == 3 * C) coef = deg[j] * epr[e];
+        else if (row == 3 * C + 1) coef = ssum[j];
+        else if (row == 3 * C + 2) coef = eG[e];
+        else coef = deg[j];
+        acc = fmaf(coef, ee[e * h0 + h], acc);
+      }
+    }
+  } else if (p < n1 + n2) {
+    int q = p - n1; int row = q / h1, h = q - row * h1;
+    dst = row < 2 * C + 1 + h0 ? G.M2 + row * h1 + h : G.b2 + h;
+    for (long long ls = s0; ls < s1; ++ls) {
+      long long gs = ls + e_off;
+      const float* x = xin + ls * N * C; const float* apx = Sx.apx + ls * N * C;
+      const float* T = Sx.T + ls * N * h0; const float* dm2s = Sx.dm2s + ls * N * h1;
+      const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
+      for (int i = 0; i < N; ++i) {
+        float coef;
+        if (row < C) coef = deg[i] * lrelu_f(x[i * C + row]);
+        else if (row < 2 * C) coef = apx[i * C + row - C];
+        else if (row == 2 * C) coef = ssum[i];
+        else if (row < 2 * C + 1 + h0) coef = T[i * h0 + row - 2 * C - 1];
+        else coef = deg[i];
+        acc = fmaf(coef, dm2s[i * h1 + h], acc);
+      }
+    }
+  } else {
+    int q = p - n1 - n2; int row = q / h2, h = q - row * h2;
+    dst = row < C + h1 ? G.M3 + row * h2 + h : G.b3 + h;
+    for (long long ls = s0; ls < s1; ++ls) {
+      const float* x = xin + ls * N * C; const float* m2s = Sx.m2s + ls * N * h1;
+      const float* dy = dyin + ls * N * h2;
+      for (int i = 0; i < N; ++i) {
+        float coef;
+        if (row < C) coef = lrelu_f(x[i * C + row]);
+        else if (row < C + h1) coef = lrelu_f(m2s[i * h1 + row - C]);
+        else coef = 1.f;
+        acc = fmaf(coef, dy[i * h2 + h], acc);
+      }
+    }
+  }
+  atomicAdd(dst, acc);
+}

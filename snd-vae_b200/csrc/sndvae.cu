@@ -1,0 +1,947 @@
+// sndvae.cu -- handle, parameter table, orchestration and the C ABI (include/sndvae.h)
+// of the B200-native SND-VAE train / generate step.
+//
+// Path replaced (reference file:line): model.py:98-222 (encoder/get_z/decoder),
+// model_joint.py:72-182, layers.py:112-125,143-198,431-450,566-576,
+// optimizer.py:126-164,192-204 (ELBO + Adam), driven as main.py:331.
+#include "../../include/sndvae.h"
+#include "common.cuh"
+#include "layers.cuh"
+#include "sgc.cuh"
+#include "edge.cuh"
+#include "adam.cuh"
+#include "e2e_tc.cuh"
+#include <cublas_v2.h>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdarg>
+#include <cmath>
+
+#define KS 5   /* conv1d kernel size (main.py:184,201,206) */
+
+struct PT {   // parameter offsets (floats) into the flat arenas; -1 = absent
+  long gg_w[2], gg_bng[2], gg_bnb[2], encg_g, encg_b, g_lin[3][2];
+  long gs_k[3], gs_b[3], gs_bng[3], gs_bnb[3], encs_g, encs_b, s_lin[3][2];
+  long sg_M1[2], sg_b1[2], sg_M2[2], sg_b2[2], sg_M3[2], sg_b3[2], sg_bng[2], sg_bnb[2], encsg_g, encsg_b, sg_lin[3][2];
+  long d_sg_lin1[2], d_s_lin1[2], d_g_lin1[2];
+  long n_k[2], n_b[2], n_bng[2], n_bnb[2], decnode_g, decnode_b, d_n_lin2[2];
+  long e_bng[2], e_bnb[2], e_w[2], e_b[2], decadj_g, decadj_b, d_e_lin2[2];
+  long s_k[3], s_b[3], s_bng[3], s_bnb[3], d_s_lin2[2];
+};
+
+struct EvPair { cudaEvent_t a, b; double flops; };
+
+struct sndvae_handle {
+  sndvae_config cfg;
+  cudaStream_t stream;
+  cublasHandle_t blas;
+  std::string err;
+  std::vector<sndvae_param_info> table;
+  PT pt;
+  long long nparam;          // padded arena length
+  float *P, *G, *M, *V;      // params, grads, Adam slots
+  float b1p, b2p;            // running beta powers (fp32, as TF's beta1_power / beta2_power)
+  std::vector<void*> allocs;
+  long long launches;
+  // derived sizes
+  int dis, N, F, D, S, H, Chv, C1, C2, Bc, SC;
+  long long B, BS, Rn;
+  // buffers (see alloc_buffers)
+  float *t0, *c0, *g1, *t1, *c1, *g2, *fg, *hg, *mu_g, *ls_g;
+  float *h1p, *h1, *h2p, *h2, *h3p, *h3, *fs, *hs, *mu_s, *ls_s;
+  float *fsg, *hsg, *mu_sg, *ls_sg, *dfsg;
+  float *x1, *x2, *dxa, *dxb;          // SGC chunk activations / grads
+  SgcEdges E; SgcScratch S0, S1;
+  float *z_s, *z_g, *z_sg, *zbar, *dz_s, *dz_g, *dzbar;
+  float *dmu, *dls, *dh;               // head backward temporaries (sized for BS rows)
+  float *n_sg, *n_s, *n_g, *dn_sg, *dn_s, *dn_g;
+  float *v, *sp0, *q1p, *q1, *q2p, *q2, *q3, *xpre, *xhat, *dxpre;
+  float *s1p, *s1, *s2p, *s2, *s3p, *s3, *ppre, *phat, *dppre;
+  float *a, *c, *Rc, *Sa, *WSa, *WSc, *da, *dc, *dRc, *dSa, *dWSa, *dWSc, *dv, *dsp0;
+  float *gA, *gB, *gC;                 // generic [Rn, 64] backward temporaries
+  float *E1, *O12, *dY12, *Yf, *dOf;   // chunk buffers (fp32)
+  __nv_bfloat16 *Yhi, *Ylo, *dOhi, *dOlo;
+  TcState tc;
+  float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg
+  int* errflag;
+  float* pinned_loss;
+  // host-feed staging (sndvae_train_step_host)
+  float *hf_features, *hf_adj, *hf_rel, *hf_adj_truth, *hf_feature_truth, *hf_spatial_truth, *hf_eps_s, *hf_eps_sg, *hf_eps_g;
+  long long* hf_gen_adj;
+  // gemm timing
+  std::vector<EvPair> ev; size_t ev_used;
+};
+
+static int fail(sndvae_t* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define CKB(call) do { cublasStatus_t s_ = (call); if (s_ != CUBLAS_STATUS_SUCCESS) return fail(h, SNDVAE_E_CUDA, "%s: cublas status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); } while (0)
+#define LAUNCH(k, grid, block, smem, ...) do { k<<<(grid), (block), (smem), h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
+#define LEW(k, n, ...) LAUNCH(k, cdiv((n), 256), 256, 0, __VA_ARGS__)   /* elementwise launch */
+
+// ------------------------------------------------------------------------------------------
+// parameter table: tf.trainable_variables() in creation order
+// ------------------------------------------------------------------------------------------
+static long add_param(sndvae_t* h, const char* name, int rank, int s0, int s1 = 1, int s2 = 1, int s3 = 1) {
+  sndvae_param_info pi; memset(&pi, 0, sizeof pi);
+  snprintf(pi.name, sizeof pi.name, "%s", name);
+  pi.rank = rank; pi.shape[0] = s0; pi.shape[1] = s1; pi.shape[2] = s2; pi.shape[3] = s3;
+  pi.size = (int64_t)s0 * s1 * s2 * s3;
+  pi.offset = h->nparam;
+  h->nparam += (pi.size + 3) / 4 * 4;     // 16-byte aligned entries
+  h->table.push_back(pi);
+  return (long)pi.offset;
+}
+static void add_bn(sndvae_t* h, const char* name, int c, long* g, long* b) {
+  char buf[96];
+  snprintf(buf, sizeof buf, "%s/gamma", name); *g = add_param(h, buf, 1, c);
+  snprintf(buf, sizeof buf, "%s/beta", name);  *b = add_param(h, buf, 1, c);
+}
+static void add_lin(sndvae_t* h, const char* name, int i, int o, long* mb) {
+  char buf[96];
+  snprintf(buf, sizeof buf, "%s/Matrix", name); mb[0] = add_param(h, buf, 2, i, o);
+  snprintf(buf, sizeof buf, "%s/bias", name);   mb[1] = add_param(h, buf, 1, o);
+}
+static void add_conv(sndvae_t* h, const char* name, int ci, int co, long* k, long* b) {
+  char buf[96];
+  snprintf(buf, sizeof buf, "%s/kernel", name); *k = add_param(h, buf, 3, KS, ci, co);
+  snprintf(buf, sizeof buf, "%s/bias", name);   *b = add_param(h, buf, 1, co);
+}
+
+static void build_table(sndvae_t* h) {
+  const sndvae_config& c = h->cfg;
+  PT& p = h->pt;
+  memset(&p, 0xff, sizeof p);
+  h->nparam = 0;
+  const int N = c.num_nodes, F = c.num_feature, D = c.spatial_dim, H = c.node_h_size;
+  char nm[96];
+  if (h->dis) {
+    int ci = F;
+    for (int i = 0; i < 2; ++i) {
+      snprintf(nm, sizeof nm, "encoder/g_g%d_conv/w", i); p.gg_w[i] = add_param(h, nm, 2, ci, c.g_conv_hidden[i]);
+      snprintf(nm, sizeof nm, "encoder/g_bn_g%d", i); add_bn(h, nm, c.g_conv_hidden[i], &p.gg_bng[i], &p.gg_bnb[i]);
+      ci = c.g_conv_hidden[i] + F;
+    }
+    add_bn(h, "encoder/encoder_g", ci, &p.encg_g, &p.encg_b);
+    add_lin(h, "encoder/g_g1_lin", N * ci, c.g_hidden_size, p.g_lin[0]);
+    add_lin(h, "encoder/g_g2_lin", c.g_hidden_size, c.g_latent_size, p.g_lin[1]);
+    add_lin(h, "encoder/g_g3_lin", c.g_hidden_size, c.g_latent_size, p.g_lin[2]);
+    ci = D;
+    for (int i = 0; i < 3; ++i) {
+      snprintf(nm, sizeof nm, "encoder/g_s%d_conv", i + 1); add_conv(h, nm, ci, c.s_channel[i], &p.gs_k[i], &p.gs_b[i]);
+      snprintf(nm, sizeof nm, "encoder/g_bn_s%d", i); add_bn(h, nm, c.s_channel[i], &p.gs_bng[i], &p.gs_bnb[i]);
+      ci = c.s_channel[i];
+    }
+    add_bn(h, "encoder/encoder_s", ci, &p.encs_g, &p.encs_b);
+    add_lin(h, "encoder/g_s1_lin", N * ci, c.s_hidden_size, p.s_lin[0]);
+    add_lin(h, "encoder/g_s2_lin", c.s_hidden_size, c.s_latent_size, p.s_lin[1]);
+    add_lin(h, "encoder/g_s3_lin", c.s_hidden_size, c.s_latent_size, p.s_lin[2]);
+  }
+  int ci = F;
+  for (int i = 0; i < 2; ++i) {
+    const int* hs = c.sg_conv_hidden[i];
+    snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/Matrix1", i); p.sg_M1[i] = add_param(h, nm, 2, 3 * ci + 3, hs[0]);
+    snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/bias1", i);   p.sg_b1[i] = add_param(h, nm, 1, hs[0]);
+    snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/Matrix2", i); p.sg_M2[i] = add_param(h, nm, 2, 2 * ci + hs[0] + 1, hs[1]);
+    snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/bias2", i);   p.sg_b2[i] = add_param(h, nm, 1, hs[1]);
+    snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/Matrix3", i); p.sg_M3[i] = add_param(h, nm, 2, ci + hs[1], hs[2]);
+    snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/bias3", i);   p.sg_b3[i] = add_param(h, nm, 1, hs[2]);
+    snprintf(nm, sizeof nm, "encoder/g_bn_sg%d", i); add_bn(h, nm, hs[2], &p.sg_bng[i], &p.sg_bnb[i]);
+    ci = hs[2];
+  }
+  if (h->dis) add_bn(h, "encoder/encoder_sg", ci, &p.encsg_g, &p.encsg_b);
+  add_lin(h, "encoder/g_sg1_lin", N * ci, c.sg_hidden_size, p.sg_lin[0]);
+  add_lin(h, "encoder/g_sg2_lin", c.sg_hidden_size, c.sg_latent_size, p.sg_lin[1]);
+  add_lin(h, "encoder/g_sg3_lin", c.sg_hidden_size, c.sg_latent_size, p.sg_lin[2]);
+  add_lin(h, "decoder/d_sg_lin1", c.sg_latent_size, N * H, p.d_sg_lin1);
+  if (h->dis) {
+    add_lin(h, "decoder/d_s_lin1", c.s_latent_size, N * H, p.d_s_lin1);
+    add_lin(h, "decoder/d_g_lin1", c.g_latent_size, N * H, p.d_g_lin1);
+  }
+  const int cin0 = h->dis ? 2 * H : H;
+  auto spatial_dec = [&]() {
+    int cc = cin0;
+    for (int i = 0; i < 3; ++i) {
+      snprintf(nm, sizeof nm, "decoder/s%d_deconv", i + 1); add_conv(h, nm, cc, c.s_d_channel[i], &p.s_k[i], &p.s_b[i]);
+      snprintf(nm, sizeof nm, "decoder/d_bn_s%d", i); add_bn(h, nm, c.s_d_channel[i], &p.s_bng[i], &p.s_bnb[i]);
+      cc = c.s_d_channel[i];
+    }
+    add_lin(h, "decoder/d_s_lin2", cc, D, p.d_s_lin2);
+  };
+  if (!h->dis) spatial_dec();       // model_joint.py builds the spatial decoder first (113-121)
+  int cc = cin0;
+  for (int i = 0; i < 2; ++i) {
+    snprintf(nm, sizeof nm, "decoder/n%d_deconv", i); add_conv(h, nm, cc, c.n_d_channel[i], &p.n_k[i], &p.n_b[i]);
+    snprintf(nm, sizeof nm, "decoder/d_bn_n%d", i); add_bn(h, nm, c.n_d_channel[i], &p.n_bng[i], &p.n_bnb[i]);
+    cc = c.n_d_channel[i];
+  }
+  if (h->dis) add_bn(h, "decoder/decoder_node", cc, &p.decnode_g, &p.decnode_b);
+  add_lin(h, "decoder/d_n_lin2", cc, F, p.d_n_lin2);
+  cc = 2 * cin0;
+  for (int i = 0; i < 2; ++i) {
+    snprintf(nm, sizeof nm, "decoder/d_bn_e%d", i); add_bn(h, nm, cc, &p.e_bng[i], &p.e_bnb[i]);
+    snprintf(nm, sizeof nm, "decoder/e%d_deconv/w1", i); p.e_w[i] = add_param(h, nm, 4, 1, N, cc, c.e_d_hidden[i]);
+    snprintf(nm, sizeof nm, "decoder/e%d_deconv/biases1", i); p.e_b[i] = add_param(h, nm, 1, c.e_d_hidden[i]);
+    cc = c.e_d_hidden[i];
+  }
+  if (h->dis) add_bn(h, "decoder/decoder_adj", cc, &p.decadj_g, &p.decadj_b);
+  add_lin(h, "decoder/d_e_lin2", cc, 2, p.d_e_lin2);
+  if (h->dis) spatial_dec();
+}
+
+// ------------------------------------------------------------------------------------------
+// memory
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int dalloc(sndvae_t* h, T** p, long long n) {
+  if (n <= 0) n = 1;
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, (size_t)n * sizeof(T));
+  if (e != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMalloc(%lld bytes): %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
+  cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), h->stream);
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+#define DA(ptr, n) do { int r_ = dalloc(h, &(ptr), (long long)(n)); if (r_) return r_; } while (0)
+
+static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long long samples, int N, int cap) {
+  DA(s.apx, samples * N * C); DA(s.T, samples * N * hs[0]); DA(s.m2s, samples * N * hs[1]); DA(s.y, samples * N * hs[2]);
+  DA(s.dm2s, samples * N * hs[1]); DA(s.dT, samples * N * hs[0]); DA(s.ee, samples * cap * hs[0]);
+  DA(s.dpx, samples * N * C); DA(s.dapx, samples * N * C);
+  return 0;
+}
+
+static int alloc_buffers(sndvae_t* h) {
+  const sndvae_config& c = h->cfg;
+  const long long B = h->B, BS = h->BS, Rn = h->Rn;
+  const int N = h->N, F = h->F, D = h->D, H = h->H, Chv = h->Chv, C1 = h->C1, C2 = h->C2;
+  DA(h->P, h->nparam); DA(h->G, h->nparam); DA(h->M, h->nparam); DA(h->V, h->nparam);
+  if (h->dis) {
+    int g0 = c.g_conv_hidden[0], g1c = c.g_conv_hidden[1];
+    DA(h->t0, Rn * g0); DA(h->c0, Rn * g0); DA(h->g1, Rn * (g0 + F)); DA(h->t1, Rn * g1c); DA(h->c1, Rn * g1c);
+    DA(h->g2, Rn * (g1c + F)); DA(h->fg, Rn * (g1c + F));
+    DA(h->hg, B * c.g_hidden_size); DA(h->mu_g, B * c.g_latent_size); DA(h->ls_g, B * c.g_latent_size);
+    DA(h->h1p, Rn * c.s_channel[0]); DA(h->h1, Rn * c.s_channel[0]); DA(h->h2p, Rn * c.s_channel[1]); DA(h->h2, Rn * c.s_channel[1]);
+    DA(h->h3p, Rn * c.s_channel[2]); DA(h->h3, Rn * c.s_channel[2]); DA(h->fs, Rn * c.s_channel[2]);
+    DA(h->hs, B * c.s_hidden_size); DA(h->mu_s, B * c.s_latent_size); DA(h->ls_s, B * c.s_latent_size);
+    DA(h->z_s, B * c.s_latent_size); DA(h->z_g, B * c.g_latent_size); DA(h->dz_s, B * c.s_latent_size); DA(h->dz_g, B * c.g_latent_size);
+    DA(h->n_s, Rn * H); DA(h->n_g, Rn * H); DA(h->dn_s, Rn * H); DA(h->dn_g, Rn * H);
+  }
+  const int hl = c.sg_conv_hidden[1][2];
+  DA(h->fsg, BS * N * hl); DA(h->dfsg, BS * N * hl);
+  DA(h->hsg, BS * c.sg_hidden_size); DA(h->mu_sg, BS * c.sg_latent_size); DA(h->ls_sg, BS * c.sg_latent_size);
+  // edge storage for all samples, SGC activations for one chunk of SC samples
+  SgcEdges& E = h->E; E.cap = c.edge_capacity;
+  DA(E.rowstart, BS * N); DA(E.rowcnt, BS * N); DA(E.erow, BS * E.cap); DA(E.ecol, BS * E.cap);
+  DA(E.ea, BS * E.cap); DA(E.epr, BS * E.cap); DA(E.eG, BS * E.cap); DA(E.deg, BS * N); DA(E.ssum, BS * N); DA(E.nedges, BS);
+  const long long SC = h->SC;
+  int r;
+  if ((r = alloc_scratch(h, h->S0, F, c.sg_conv_hidden[0], SC, N, E.cap))) return r;
+  if ((r = alloc_scratch(h, h->S1, c.sg_conv_hidden[0][2], c.sg_conv_hidden[1], SC, N, E.cap))) return r;
+  DA(h->x1, SC * N * c.sg_conv_hidden[0][2]); DA(h->x2, SC * N * hl); DA(h->dxa, SC * N * hl); DA(h->dxb, SC * N * hl);
+  DA(h->z_sg, BS * c.sg_latent_size); DA(h->zbar, B * c.sg_latent_size); DA(h->dzbar, B * c.sg_latent_size);
+  long long maxL = c.sg_latent_size > c.sg_hidden_size ? c.sg_latent_size : c.sg_hidden_size;
+  if (h->dis) { int m2 = c.s_latent_size > c.g_latent_size ? c.s_latent_size : c.g_latent_size; if (m2 > maxL) maxL = m2;
+                if (c.s_hidden_size > maxL) maxL = c.s_hidden_size; if (c.g_hidden_size > maxL) maxL = c.g_hidden_size; }
+  DA(h->dmu, BS * maxL); DA(h->dls, BS * maxL); DA(h->dh, BS * maxL);
+  DA(h->n_sg, Rn * H); DA(h->dn_sg, Rn * H);
+  DA(h->v, Rn * Chv);
+  if (h->dis) DA(h->sp0, Rn * Chv); else h->sp0 = h->v;
+  DA(h->q1p, Rn * c.n_d_channel[0]); DA(h->q1, Rn * c.n_d_channel[0]); DA(h->q2p, Rn * c.n_d_channel[1]); DA(h->q2, Rn * c.n_d_channel[1]);
+  if (h->dis) DA(h->q3, Rn * c.n_d_channel[1]); else h->q3 = h->q2;
+  DA(h->xpre, Rn * F); DA(h->xhat, Rn * F); DA(h->dxpre, Rn * F);
+  DA(h->s1p, Rn * c.s_d_channel[0]); DA(h->s1, Rn * c.s_d_channel[0]); DA(h->s2p, Rn * c.s_d_channel[1]); DA(h->s2, Rn * c.s_d_channel[1]);
+  DA(h->s3p, Rn * c.s_d_channel[2]); DA(h->s3, Rn * c.s_d_channel[2]); DA(h->ppre, Rn * D); DA(h->phat, Rn * D); DA(h->dppre, Rn * D);
+  DA(h->a, Rn * Chv); DA(h->c, Rn * Chv); DA(h->Rc, Rn * C1); DA(h->Sa, Rn * C1);
+  DA(h->WSa, (long long)N * C1 * Chv); DA(h->WSc, (long long)N * C1 * Chv);
+  DA(h->da, Rn * Chv); DA(h->dc, Rn * Chv); DA(h->dRc, Rn * C1); DA(h->dSa, Rn * C1);
+  DA(h->dWSa, (long long)N * C1 * Chv); DA(h->dWSc, (long long)N * C1 * Chv);
+  DA(h->dv, Rn * Chv); DA(h->dsp0, Rn * Chv);
+  DA(h->gA, Rn * 64); DA(h->gB, Rn * 64); DA(h->gC, Rn * 64);
+  const long long cells = (long long)h->Bc * N * N;
+  DA(h->E1, cells * C1); DA(h->O12, 2 * cells * C2); DA(h->dY12, 2 * cells * C1);
+  if (c.use_tensor_cores) {
+    DA(h->Yhi, 2 * cells * TC_CP); DA(h->Ylo, 2 * cells * TC_CP); DA(h->dOhi, 2 * cells * TC_OP); DA(h->dOlo, 2 * cells * TC_OP);
+    h->Yf = nullptr; h->dOf = nullptr;
+  } else {
+    DA(h->Yf, 2 * cells * C1); DA(h->dOf, 2 * cells * C2);
+    h->Yhi = h->Ylo = h->dOhi = h->dOlo = nullptr;
+  }
+  DA(h->loss, 8); DA(h->errflag, 1);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// small host helpers
+// ------------------------------------------------------------------------------------------
+// row-major C[M,N] = alpha op(A) op(B) + beta C
+static cublasStatus_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
+                              const float* B, int ldb, float beta, float* C, int ldc) {
+  h->launches++;
+  return cublasSgemm(h->blas, tB ? CUBLAS_OP_T : CUBLAS_OP_N, tA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda,
+                     &beta, C, ldc);
+}
+__global__ void bias_rows_k(float* __restrict__ C, const float* __restrict__ bias, long long rows, int cols) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rows * cols) C[idx] = bias[idx % cols];
+}
+// Y[rows, o] = X[rows, i] W[i, o] + bias   (layers.py:566-576 on flattened features)
+static int lin_fwd(sndvae_t* h, const float* X, const long* mb, float* Y, long long rows, int i, int o) {
+  LEW(bias_rows_k, rows * o, Y, h->P + mb[1], rows, o);
+  CKB(gemm_rm(h, false, false, (int)rows, o, i, 1.f, X, i, h->P + mb[0], o, 1.f, Y, o));
+  return 0;
+}
+// dW += X^T dY; db += colsum(dY); dX = dY W^T (optional)
+static int lin_bwd(sndvae_t* h, const float* X, const long* mb, const float* dY, float* dX, long long rows, int i, int o) {
+  CKB(gemm_rm(h, true, false, i, o, (int)rows, 1.f, X, i, dY, o, 1.f, h->G + mb[0], o));
+  LAUNCH(colsum_k, cdiv(rows, XTDY_SLAB), 128, 0, dY, o, h->G + mb[1], rows, o);
+  if (dX) CKB(gemm_rm(h, false, true, (int)rows, i, o, 1.f, dY, o, h->P + mb[0], o, 0.f, dX, i));
+  return 0;
+}
+static void bn_fwd(sndvae_t* h, const float* in, int ldi, long g, long b, float* out, int ldo, long long rows, int C, int act, int order) {
+  LEW(bn_act_fwd_k, rows * C, in, ldi, g >= 0 ? h->P + g : nullptr, b >= 0 ? h->P + b : nullptr, out, ldo, rows, C, act, order);
+}
+static void bn_bwd(sndvae_t* h, const float* dout, int ldd, const float* in, int ldi, long g, long b, float* din, int ldn,
+                   long long rows, int C, int act, int order) {
+  LAUNCH(bn_act_bwd_k, cdiv(rows, BN_SLAB), 64, 0, dout, ldd, in, ldi, g >= 0 ? h->P + g : nullptr, b >= 0 ? h->P + b : nullptr,
+         din, ldn, g >= 0 ? h->G + g : nullptr, b >= 0 ? h->G + b : nullptr, rows, C, act, order);
+}
+static void conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, long long rows, int Ci, int Co) {
+  LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS);
+}
+// weight/bias grads + optional input grad of a conv1d layer
+static void conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
+  LAUNCH(xtdy_k, cdiv(rows, XTDY_SLAB), 256, 0, in, Ci, dout, Co, h->G + k, rows, h->N, Ci, Co, KS);
+  LAUNCH(colsum_k, cdiv(rows, XTDY_SLAB), 64, 0, dout, Co, h->G + b, rows, Co);
+  if (din) LEW(conv1d_bwd_in_k, rows * Ci, dout, h->P + k, din, rows, h->N, Ci, Co, KS);
+}
+static SgcW sgc_w(sndvae_t* h, float* base, int l) {
+  const sndvae_config& c = h->cfg; const PT& p = h->pt;
+  SgcW w; w.M1 = base + p.sg_M1[l]; w.b1 = base + p.sg_b1[l]; w.M2 = base + p.sg_M2[l]; w.b2 = base + p.sg_b2[l];
+  w.M3 = base + p.sg_M3[l]; w.b3 = base + p.sg_b3[l];
+  w.C = l == 0 ? c.num_feature : c.sg_conv_hidden[0][2];
+  w.h0 = c.sg_conv_hidden[l][0]; w.h1 = c.sg_conv_hidden[l][1]; w.h2 = c.sg_conv_hidden[l][2];
+  return w;
+}
+static void ev_begin(sndvae_t* h, double flops) {
+  if (h->ev_used < h->ev.size()) { h->ev[h->ev_used].flops = flops; cudaEventRecord(h->ev[h->ev_used].a, h->stream); }
+}
+static void ev_end(sndvae_t* h) {
+  if (h->ev_used < h->ev.size()) { cudaEventRecord(h->ev[h->ev_used].b, h->stream); h->ev_used++; }
+}
+
+// ------------------------------------------------------------------------------------------
+// encoder  (model.py:98-151 / model_joint.py:72-85)
+// ------------------------------------------------------------------------------------------
+// SGC forward for samples [s0, s0+ns); writes fsg rows s0.. ; leaves the chunk's activations in scratch
+static int sgc_chunk_fwd(sndvae_t* h, const sndvae_inputs* in, long long s0, long long ns) {
+  const sndvae_config& c = h->cfg; const PT& p = h->pt; const int N = h->N, F = h->F;
+  const int h02 = c.sg_conv_hidden[0][2], h12 = c.sg_conv_hidden[1][2];
+  const float* x0 = in->features + s0 * N * F;
+  LAUNCH(sgc_layer_fwd_k, (unsigned)ns, 256, 0, x0, h->E, sgc_w(h, h->P, 0), h->S0, N, s0);
+  bn_fwd(h, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->x1, h02, ns * N, h02, ACT_LRELU, 0);
+  LAUNCH(sgc_layer_fwd_k, (unsigned)ns, 256, 0, h->x1, h->E, sgc_w(h, h->P, 1), h->S1, N, s0);
+  bn_fwd(h, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->x2, h12, ns * N, h12, ACT_LRELU, 0);
+  // encoder_sg BN (model.py:148; absent in model_joint.py:83)
+  bn_fwd(h, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->fsg + s0 * N * h12, h12, ns * N, h12, ACT_NONE, 0);
+  return 0;
+}
+
+static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
+  const sndvae_config& c = h->cfg; const PT& p = h->pt;
+  const int N = h->N, F = h->F, D = h->D; const long long B = h->B, BS = h->BS, Rn = h->Rn;
+  if (h->dis) {
+    // graph encoder (model.py:104-115): g <- BN(lrelu(A (g w))); g <- [g || X]
+    int g0 = c.g_conv_hidden[0], g1c = c.g_conv_hidden[1];
+    LEW(rowlin_fwd_k, Rn * g0, in->feature_truth, F, h->P + p.gg_w[0], (const float*)nullptr, h->t0, g0, Rn, F, g0, ACT_NONE);
+    LAUNCH(graph_prop_fwd_k<32>, cdiv(Rn * 32, 256), 256, 0, in->adj_truth, h->t0, h->c0, Rn, N, g0);
+    bn_fwd(h, h->c0, g0, p.gg_bng[0], p.gg_bnb[0], h->g1, g0 + F, Rn, g0, ACT_LRELU, 1);
+    LEW(copy_cols_k, Rn * F, in->feature_truth, F, 0, h->g1, g0 + F, g0, Rn, F, 0);
+    LEW(rowlin_fwd_k, Rn * g1c, h->g1, g0 + F, h->P + p.gg_w[1], (const float*)nullptr, h->t1, g1c, Rn, g0 + F, g1c, ACT_NONE);
+    LAUNCH(graph_prop_fwd_k<32>, cdiv(Rn * 32, 256), 256, 0, in->adj_truth, h->t1, h->c1, Rn, N, g1c);
+    bn_fwd(h, h->c1, g1c, p.gg_bng[1], p.gg_bnb[1], h->g2, g1c + F, Rn, g1c, ACT_LRELU, 1);
+    LEW(copy_cols_k, Rn * F, in->feature_truth, F, 0, h->g2, g1c + F, g1c, Rn, F, 0);
+    bn_fwd(h, h->g2, g1c + F, p.encg_g, p.encg_b, h->fg, g1c + F, Rn, g1c + F, ACT_NONE, 0);
+    int r;
+    if ((r = lin_fwd(h, h->fg, p.g_lin[0], h->hg, B, N * (g1c + F), c.g_hidden_size))) return r;
+    if ((r = lin_fwd(h, h->hg, p.g_lin[1], h->mu_g, B, c.g_hidden_size, c.g_latent_size))) return r;
+    if ((r = lin_fwd(h, h->hg, p.g_lin[2], h->ls_g, B, c.g_hidden_size, c.g_latent_size))) return r;
+    // spatial encoder (model.py:119-129): relu(BN(conv1d k5 SAME)) x3
+    const int* sc = c.s_channel;
+    conv_fwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->h1p, Rn, D, sc[0]);
+    bn_fwd(h, h->h1p, sc[0], p.gs_bng[0], p.gs_bnb[0], h->h1, sc[0], Rn, sc[0], ACT_RELU, 0);
+    conv_fwd(h, h->h1, p.gs_k[1], p.gs_b[1], h->h2p, Rn, sc[0], sc[1]);
+    bn_fwd(h, h->h2p, sc[1], p.gs_bng[1], p.gs_bnb[1], h->h2, sc[1], Rn, sc[1], ACT_RELU, 0);
+    conv_fwd(h, h->h2, p.gs_k[2], p.gs_b[2], h->h3p, Rn, sc[1], sc[2]);
+    bn_fwd(h, h->h3p, sc[2], p.gs_bng[2], p.gs_bnb[2], h->h3, sc[2], Rn, sc[2], ACT_RELU, 0);
+    bn_fwd(h, h->h3, sc[2], p.encs_g, p.encs_b, h->fs, sc[2], Rn, sc[2], ACT_NONE, 0);
+    if ((r = lin_fwd(h, h->fs, p.s_lin[0], h->hs, B, N * sc[2], c.s_hidden_size))) return r;
+    if ((r = lin_fwd(h, h->hs, p.s_lin[1], h->mu_s, B, c.s_hidden_size, c.s_latent_size))) return r;
+    if ((r = lin_fwd(h, h->hs, p.s_lin[2], h->ls_s, B, c.s_hidden_size, c.s_latent_size))) return r;
+  }
+  // joint encoder (model.py:134-151): edge lists once per step, SGC x2 in sample chunks
+  LAUNCH(sgc_build_edges_k, (unsigned)BS, 256, 0, in->adj, in->rel, h->E, N, h->errflag);
+  for (long long s0 = 0; s0 < BS; s0 += h->SC) {
+    long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
+    int r = sgc_chunk_fwd(h, in, s0, ns); if (r) return r;
+  }
+  const int h12 = c.sg_conv_hidden[1][2];
+  int r;
+  if ((r = lin_fwd(h, h->fsg, p.sg_lin[0], h->hsg, BS, N * h12, c.sg_hidden_size))) return r;
+  if ((r = lin_fwd(h, h->hsg, p.sg_lin[1], h->mu_sg, BS, c.sg_hidden_size, c.sg_latent_size))) return r;
+  if ((r = lin_fwd(h, h->hsg, p.sg_lin[2], h->ls_sg, BS, c.sg_hidden_size, c.sg_latent_size))) return r;
+  return 0;
+}
+
+// get_z (model.py:153-161) + KL sums (optimizer.py:160-162)
+static int reparam_fwd(sndvae_t* h, const sndvae_noise* nz) {
+  const sndvae_config& c = h->cfg;
+  if (h->dis) {
+    LEW(reparam_kl_k, h->B * c.s_latent_size, h->mu_s, h->ls_s, nz->eps_s, h->z_s, h->loss + 3, h->B * c.s_latent_size);
+    LEW(reparam_kl_k, h->B * c.g_latent_size, h->mu_g, h->ls_g, nz->eps_g, h->z_g, h->loss + 4, h->B * c.g_latent_size);
+  }
+  LEW(reparam_kl_k, h->BS * c.sg_latent_size, h->mu_sg, h->ls_sg, nz->eps_sg, h->z_sg, h->loss + 5, h->BS * c.sg_latent_size);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// decoder  (model.py:172-222 / model_joint.py:94-182)
+// ------------------------------------------------------------------------------------------
+static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out, bool backward, float gB) {
+  const sndvae_config& c = h->cfg; const PT& p = h->pt;
+  const int N = h->N, F = h->F, D = h->D, H = h->H, Chv = h->Chv, C1 = h->C1, C2 = h->C2, S = h->S;
+  const long long B = h->B, Rn = h->Rn;
+  const int dact = h->dis ? ACT_NONE : ACT_LRELU;      // model_joint.py:116,139 lrelu after BN
+  int r;
+  // latent -> node features; the S-mean (model.py:180) is hoisted before the linear map
+  LEW(smean_k, B * c.sg_latent_size, h->z_sg, h->zbar, B, S, c.sg_latent_size);
+  if ((r = lin_fwd(h, h->zbar, p.d_sg_lin1, h->n_sg, B, c.sg_latent_size, N * H))) return r;
+  if (h->dis) {
+    if ((r = lin_fwd(h, h->z_s, p.d_s_lin1, h->n_s, B, c.s_latent_size, N * H))) return r;
+    if ((r = lin_fwd(h, h->z_g, p.d_g_lin1, h->n_g, B, c.g_latent_size, N * H))) return r;
+    LEW(copy_cols_k, Rn * H, h->n_sg, H, 0, h->v, Chv, 0, Rn, H, 0);
+    LEW(copy_cols_k, Rn * H, h->n_g, H, 0, h->v, Chv, H, Rn, H, 0);
+    LEW(copy_cols_k, Rn * H, h->n_sg, H, 0, h->sp0, Chv, 0, Rn, H, 0);
+    LEW(copy_cols_k, Rn * H, h->n_s, H, 0, h->sp0, Chv, H, Rn, H, 0);
+  } else {
+    LEW(copy_cols_k, Rn * H, h->n_sg, H, 0, h->v, Chv, 0, Rn, H, 0);
+  }
+  // node-feature decoder (model.py:186-194)
+  const int* nc = c.n_d_channel;
+  conv_fwd(h, h->v, p.n_k[0], p.n_b[0], h->q1p, Rn, Chv, nc[0]);
+  bn_fwd(h, h->q1p, nc[0], p.n_bng[0], p.n_bnb[0], h->q1, nc[0], Rn, nc[0], dact, 0);
+  conv_fwd(h, h->q1, p.n_k[1], p.n_b[1], h->q2p, Rn, nc[0], nc[1]);
+  bn_fwd(h, h->q2p, nc[1], p.n_bng[1], p.n_bnb[1], h->q2, nc[1], Rn, nc[1], dact, 0);
+  if (h->dis) bn_fwd(h, h->q2, nc[1], p.decnode_g, p.decnode_b, h->q3, nc[1], Rn, nc[1], ACT_NONE, 0);
+  LEW(rowlin_fwd_k, Rn * F, h->q3, nc[1], h->P + p.d_n_lin2[0], h->P + p.d_n_lin2[1], h->xpre, F, Rn, nc[1], F, ACT_NONE);
+  LEW(sigmoid_mse_k, Rn * F, h->xpre, in ? in->feature_truth : nullptr, h->xhat, backward ? h->dxpre : nullptr, h->loss + 1,
+         Rn * F, 1.f / (gB * N * F));
+  // spatial decoder (model.py:213-219)
+  const int* sc = c.s_d_channel;
+  conv_fwd(h, h->sp0, p.s_k[0], p.s_b[0], h->s1p, Rn, Chv, sc[0]);
+  bn_fwd(h, h->s1p, sc[0], p.s_bng[0], p.s_bnb[0], h->s1, sc[0], Rn, sc[0], dact, 0);
+  conv_fwd(h, h->s1, p.s_k[1], p.s_b[1], h->s2p, Rn, sc[0], sc[1]);
+  bn_fwd(h, h->s2p, sc[1], p.s_bng[1], p.s_bnb[1], h->s2, sc[1], Rn, sc[1], dact, 0);
+  conv_fwd(h, h->s2, p.s_k[2], p.s_b[2], h->s3p, Rn, sc[1], sc[2]);
+  bn_fwd(h, h->s3p, sc[2], p.s_bng[2], p.s_bnb[2], h->s3, sc[2], Rn, sc[2], dact, 0);
+  LEW(rowlin_fwd_k, Rn * D, h->s3, sc[2], h->P + p.d_s_lin2[0], h->P + p.d_s_lin2[1], h->ppre, D, Rn, sc[2], D, ACT_NONE);
+  LEW(sigmoid_mse_k, Rn * D, h->ppre, in ? in->spatial_truth : nullptr, h->phat, backward ? h->dppre : nullptr, h->loss + 2,
+         Rn * D, 1.f / (gB * N * D));
+  if (out && out->generated_node_feat) CK(cudaMemcpyAsync(out->generated_node_feat, h->xhat, sizeof(float) * Rn * F, cudaMemcpyDeviceToDevice, h->stream));
+  if (out && out->generated_spatial) CK(cudaMemcpyAsync(out->generated_spatial, h->phat, sizeof(float) * Rn * D, cudaMemcpyDeviceToDevice, h->stream));
+
+  // ---- edge decoder (model.py:196-208) -------------------------------------------------
+  const int Ctot = 2 * Chv;
+  const float* w0 = h->P + p.e_w[0];
+  bn_fwd(h, h->v, Chv, p.e_bng[0], p.e_bnb[0], h->a, Chv, Rn, Chv, ACT_RELU, 0);
+  bn_fwd(h, h->v, Chv, p.e_bng[0] + Chv, p.e_bnb[0] + Chv, h->c, Chv, Rn, Chv, ACT_RELU, 0);
+  LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSa, N, Ctot, 0, Chv, C1);
+  LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSc, N, Ctot, Chv, Chv, C1);
+  LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
+  LEW(toep_vec_fwd_k, Rn * C1, h->a, w0, h->Sa, B, N, Ctot, 0, Chv, C1);
+  const bool tc = c.use_tensor_cores != 0;
+  if (tc) { if ((r = tc_prepare_weights(h->tc, h->P + p.e_w[1], N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_prepare_weights failed: %s", tc_last_error()); h->launches += 1; }
+  if (backward) {
+    CK(cudaMemsetAsync(h->dWSa, 0, sizeof(float) * N * C1 * Chv, h->stream));
+    CK(cudaMemsetAsync(h->dWSc, 0, sizeof(float) * N * C1 * Chv, h->stream));
+  }
+  const double f1 = 2.0 * 2.0 * N * ((double)N * N - (double)((N - 1) / 2) * ((N - 1) / 2 + 1) / 2.0 -
+                                     (double)(N - 1 - (N - 1) / 2) * (N - (N - 1) / 2) / 2.0) * C1 * C2;
+  for (long long b0 = 0; b0 < B; b0 += h->Bc) {
+    const int bc = (int)(B - b0 < h->Bc ? B - b0 : h->Bc);
+    const long long rows = (long long)bc * N, cells = rows * N;
+    YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = TC_CP; Y.bf16 = tc;
+    LAUNCH(y_producer_k, (unsigned)rows, 256, sizeof(float) * (Chv + C1), h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc,
+           h->Rc + b0 * N * C1, h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, Chv, C1);
+    ev_begin(h, f1 * bc);
+    if (tc) { if ((r = tc_fwd(h->tc, h->Yhi, h->Ylo, h->O12, 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_fwd: %s", tc_last_error()); h->launches++; }
+    else LEW(e2e_l1_simt_fwd_k, 2 * cells * C2, h->Yf, h->P + p.e_w[1], h->O12, 2 * rows, N, C1, C2);
+    ev_end(h);
+    EpiParams ep; memset(&ep, 0, sizeof ep);
+    ep.O12 = h->O12; ep.b1 = h->P + p.e_b[1];
+    ep.gd = h->dis ? h->P + p.decadj_g : nullptr; ep.bd = h->dis ? h->P + p.decadj_b : nullptr;
+    ep.Me = h->P + p.d_e_lin2[0]; ep.be = h->P + p.d_e_lin2[1];
+    ep.At = in ? in->adj_truth + b0 * N * N : nullptr;
+    ep.gen_adj = (out && out->generated_adj) ? (long long*)out->generated_adj + b0 * N * N : nullptr;
+    ep.logits = (out && out->generated_adj_prob) ? out->generated_adj_prob + b0 * N * N * 2 : nullptr;
+    ep.dOf = h->dOf; ep.dOhi = h->dOhi; ep.dOlo = h->dOlo; ep.OP = TC_OP; ep.bf16 = tc; ep.backward = backward;
+    ep.loss_sum = h->loss + 0;
+    ep.g_b1 = h->G + p.e_b[1]; ep.g_gd = h->dis ? h->G + p.decadj_g : nullptr; ep.g_bd = h->dis ? h->G + p.decadj_b : nullptr;
+    ep.g_Me = h->G + p.d_e_lin2[0]; ep.g_be = h->G + p.d_e_lin2[1];
+    ep.gscale = 1.f / (gB * N * N);
+    LAUNCH(edge_epilogue_k, cdiv(cells, 128 * EPI_EPT), 128, 0, ep, bc, N);
+    if (!backward) continue;
+    // backward of e2e layer 1: dgrad + wgrad
+    ev_begin(h, f1 * bc);
+    if (tc) { if ((r = tc_dgrad(h->tc, h->dOhi, h->dOlo, h->dY12, 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_dgrad: %s", tc_last_error()); h->launches++; }
+    else LEW(e2e_l1_simt_dgrad_k, 2 * cells * C1, h->dOf, h->P + p.e_w[1], h->dY12, 2 * rows, N, C1, C2);
+    ev_end(h);
+    ev_begin(h, f1 * bc);
+    if (tc) { if ((r = tc_wgrad(h->tc, h->Yhi, h->Ylo, h->dOhi, h->dOlo, h->G + p.e_w[1], 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_wgrad: %s", tc_last_error()); h->launches++; }
+    else { dim3 g(cdiv((long long)N * C1 * C2, 256), cdiv(2 * rows, WGRAD_RG));
+           LAUNCH(e2e_l1_simt_wgrad_k, g, 256, 0, h->Yf, h->dOf, h->G + p.e_w[1], 2 * rows, N, C1, C2); }
+    ev_end(h);
+    // back through relu/BN_e1 to dE1 (both layouts), then the layer-0 contractions
+    LAUNCH(l0_combine_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
+           h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], bc, N, C1);
+    const float* dE1 = h->dY12; const float* dE1t = h->dY12 + cells * C1;
+    LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1, h->dSa + b0 * N * C1, N, C1);
+    LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1t, h->dRc + b0 * N * C1, N, C1);
+    // da[i,:] = sum_{(j,o)} dE1[i,(j,o)] WSa[(j,o),:];  dc[j,:] = sum_{(i,o)} dE1t[j,(i,o)] WSc[(i,o),:]
+    CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1, N * C1, h->WSa, Chv, 0.f, h->da + b0 * N * Chv, Chv));
+    CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1t, N * C1, h->WSc, Chv, 0.f, h->dc + b0 * N * Chv, Chv));
+    // dWSa[(j,o),:] += sum_rows dE1[row,(j,o)] a[row,:]
+    CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1, N * C1, h->a + b0 * N * Chv, Chv, 1.f, h->dWSa, Chv));
+    CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1t, N * C1, h->c + b0 * N * Chv, Chv, 1.f, h->dWSc, Chv));
+  }
+  return 0;
+}
+
+// backward of everything except the per-chunk N^2 stages (already done inside decoder_fwd)
+static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, float gB) {
+  const sndvae_config& c = h->cfg; const PT& p = h->pt;
+  const int N = h->N, F = h->F, D = h->D, H = h->H, Chv = h->Chv, C1 = h->C1, S = h->S;
+  const long long B = h->B, BS = h->BS, Rn = h->Rn;
+  const int Ctot = 2 * Chv;
+  const int dact = h->dis ? ACT_NONE : ACT_LRELU;
+  const float* w0 = h->P + p.e_w[0];
+  int r;
+  // ---- e2e layer 0 vector terms and weight sums ----
+  LEW(toep_vec_bwd_in_k, Rn * Chv, h->dRc, w0, h->dc, B, N, Ctot, Chv, Chv, C1);
+  LEW(toep_vec_bwd_in_k, Rn * Chv, h->dSa, w0, h->da, B, N, Ctot, 0, Chv, C1);
+  { dim3 g(cdiv((long long)N * Chv * C1, 256), cdiv(B, TOEP_BG));
+    LAUNCH(toep_vec_bwd_w_k, g, 256, 0, h->c, h->dRc, h->G + p.e_w[0], B, N, Ctot, Chv, Chv, C1);
+    LAUNCH(toep_vec_bwd_w_k, g, 256, 0, h->a, h->dSa, h->G + p.e_w[0], B, N, Ctot, 0, Chv, C1); }
+  LEW(e2e_l0_prep_bwd_k, (long long)N * Chv * C1, h->dWSa, h->G + p.e_w[0], N, Ctot, 0, Chv, C1);
+  LEW(e2e_l0_prep_bwd_k, (long long)N * Chv * C1, h->dWSc, h->G + p.e_w[0], N, Ctot, Chv, Chv, C1);
+  // a = relu(BN_e0[:Ch](v)), c = relu(BN_e0[Ch:](v))
+  bn_bwd(h, h->da, Chv, h->v, Chv, p.e_bng[0], p.e_bnb[0], h->dv, Chv, Rn, Chv, ACT_RELU, 0);
+  bn_bwd(h, h->dc, Chv, h->v, Chv, p.e_bng[0] + Chv, p.e_bnb[0] + Chv, h->gA, Chv, Rn, Chv, ACT_RELU, 0);
+  LEW(add_inplace_k, Rn * Chv, h->dv, h->gA, Rn * Chv);
+  // ---- node-feature decoder ----
+  const int* nc = c.n_d_channel;
+  LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, h->q3, nc[1], h->dxpre, F, h->G + p.d_n_lin2[0], Rn, N, nc[1], F, 1);
+  LAUNCH(colsum_k, cdiv(Rn, XTDY_SLAB), 32, 0, h->dxpre, F, h->G + p.d_n_lin2[1], Rn, F);
+  LEW(rowlin_bwd_in_k, Rn * nc[1], h->dxpre, F, h->P + p.d_n_lin2[0], h->gA, nc[1], Rn, nc[1], F, 0);      // dq3
+  if (h->dis) bn_bwd(h, h->gA, nc[1], h->q2, nc[1], p.decnode_g, p.decnode_b, h->gA, nc[1], Rn, nc[1], ACT_NONE, 0);  // dq2
+  bn_bwd(h, h->gA, nc[1], h->q2p, nc[1], p.n_bng[1], p.n_bnb[1], h->gA, nc[1], Rn, nc[1], dact, 0);                   // dq2p
+  conv_bwd(h, h->q1, p.n_k[1], p.n_b[1], h->gA, h->gB, Rn, nc[0], nc[1]);                                            // dq1
+  bn_bwd(h, h->gB, nc[0], h->q1p, nc[0], p.n_bng[0], p.n_bnb[0], h->gB, nc[0], Rn, nc[0], dact, 0);                   // dq1p
+  conv_bwd(h, h->v, p.n_k[0], p.n_b[0], h->gB, h->gA, Rn, Chv, nc[0]);                                               // dv (node)
+  LEW(add_inplace_k, Rn * Chv, h->dv, h->gA, Rn * Chv);
+  // ---- spatial decoder ----
+  const int* sc = c.s_d_channel;
+  LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, h->s3, sc[2], h->dppre, D, h->G + p.d_s_lin2[0], Rn, N, sc[2], D, 1);
+  LAUNCH(colsum_k, cdiv(Rn, XTDY_SLAB), 32, 0, h->dppre, D, h->G + p.d_s_lin2[1], Rn, D);
+  LEW(rowlin_bwd_in_k, Rn * sc[2], h->dppre, D, h->P + p.d_s_lin2[0], h->gA, sc[2], Rn, sc[2], D, 0);      // ds3
+  bn_bwd(h, h->gA, sc[2], h->s3p, sc[2], p.s_bng[2], p.s_bnb[2], h->gA, sc[2], Rn, sc[2], dact, 0);                   // ds3p
+  conv_bwd(h, h->s2, p.s_k[2], p.s_b[2], h->gA, h->gB, Rn, sc[1], sc[2]);                                            // ds2
+  bn_bwd(h, h->gB, sc[1], h->s2p, sc[1], p.s_bng[1], p.s_bnb[1], h->gB, sc[1], Rn, sc[1], dact, 0);
+  conv_bwd(h, h->s1, p.s_k[1], p.s_b[1], h->gB, h->gA, Rn, sc[0], sc[1]);                                            // ds1
+  bn_bwd(h, h->gA, sc[0], h->s1p, sc[0], p.s_bng[0], p.s_bnb[0], h->gA, sc[0], Rn, sc[0], dact, 0);
+  conv_bwd(h, h->sp0, p.s_k[0], p.s_b[0], h->gA, h->dsp0, Rn, Chv, sc[0]);                                           // dsp0
+  // ---- split back into n_sg / n_s / n_g and through the z -> [N,H] linears ----
+  if (h->dis) {
+    LEW(copy_cols_k, Rn * H, h->dv, Chv, 0, h->dn_sg, H, 0, Rn, H, 0);
+    LEW(copy_cols_k, Rn * H, h->dsp0, Chv, 0, h->dn_sg, H, 0, Rn, H, 1);
+    LEW(copy_cols_k, Rn * H, h->dv, Chv, H, h->dn_g, H, 0, Rn, H, 0);
+    LEW(copy_cols_k, Rn * H, h->dsp0, Chv, H, h->dn_s, H, 0, Rn, H, 0);
+    if ((r = lin_bwd(h, h->z_s, p.d_s_lin1, h->dn_s, h->dz_s, B, c.s_latent_size, N * H))) return r;
+    if ((r = lin_bwd(h, h->z_g, p.d_g_lin1, h->dn_g, h->dz_g, B, c.g_latent_size, N * H))) return r;
+  } else {
+    LEW(copy_cols_k, Rn * H, h->dv, Chv, 0, h->dn_sg, H, 0, Rn, H, 0);
+    LEW(copy_cols_k, Rn * H, h->dsp0, Chv, 0, h->dn_sg, H, 0, Rn, H, 1);
+  }
+  if ((r = lin_bwd(h, h->zbar, p.d_sg_lin1, h->dn_sg, h->dzbar, B, c.sg_latent_size, N * H))) return r;
+  // ---- reparameterisation + KL, heads, encoders ----
+  const float beta = c.beta;
+  if (h->dis) {
+    // graph head
+    int L = c.g_latent_size, Hh = c.g_hidden_size;
+    int g0 = c.g_conv_hidden[0], g1c = c.g_conv_hidden[1];
+    LEW(reparam_kl_bwd_k, B * L, h->mu_g, h->ls_g, nz->eps_g, h->dz_g, h->dmu, h->dls, B, L, 1, beta / (gB * L));
+    if ((r = lin_bwd(h, h->hg, p.g_lin[1], h->dmu, h->dh, B, Hh, L))) return r;
+    if ((r = lin_bwd(h, h->hg, p.g_lin[2], h->dls, h->gC, B, Hh, L))) return r;
+    LEW(add_inplace_k, B * Hh, h->dh, h->gC, B * Hh);
+    if ((r = lin_bwd(h, h->fg, p.g_lin[0], h->dh, h->gA, B, N * (g1c + F), Hh))) return r;                          // dfg [Rn, g1c+F]
+    bn_bwd(h, h->gA, g1c + F, h->g2, g1c + F, p.encg_g, p.encg_b, h->gA, g1c + F, Rn, g1c + F, ACT_NONE, 0);        // dg2
+    bn_bwd(h, h->gA, g1c + F, h->c1, g1c, p.gg_bng[1], p.gg_bnb[1], h->gB, g1c, Rn, g1c, ACT_LRELU, 1);             // dc1
+    CK(cudaMemsetAsync(h->gC, 0, sizeof(float) * Rn * g1c, h->stream));
+    LAUNCH(graph_prop_bwd_k, cdiv(Rn * 32, 256), 256, 0, in->adj_truth, h->gB, h->gC, Rn, N, g1c);                  // dt1
+    LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 256, 0, h->g1, g0 + F, h->gC, g1c, h->G + p.gg_w[1], Rn, N, g0 + F, g1c, 1);
+    LEW(rowlin_bwd_in_k, Rn * (g0 + F), h->gC, g1c, h->P + p.gg_w[1], h->gA, g0 + F, Rn, g0 + F, g1c, 0);  // dg1
+    bn_bwd(h, h->gA, g0 + F, h->c0, g0, p.gg_bng[0], p.gg_bnb[0], h->gB, g0, Rn, g0, ACT_LRELU, 1);                 // dc0
+    CK(cudaMemsetAsync(h->gC, 0, sizeof(float) * Rn * g0, h->stream));
+    LAUNCH(graph_prop_bwd_k, cdiv(Rn * 32, 256), 256, 0, in->adj_truth, h->gB, h->gC, Rn, N, g0);                   // dt0
+    LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, in->feature_truth, F, h->gC, g0, h->G + p.gg_w[0], Rn, N, F, g0, 1);
+    // spatial head
+    L = c.s_latent_size; Hh = c.s_hidden_size;
+    const int* ec = c.s_channel;
+    LEW(reparam_kl_bwd_k, B * L, h->mu_s, h->ls_s, nz->eps_s, h->dz_s, h->dmu, h->dls, B, L, 1, beta / (gB * L));
+    if ((r = lin_bwd(h, h->hs, p.s_lin[1], h->dmu, h->dh, B, Hh, L))) return r;
+    if ((r = lin_bwd(h, h->hs, p.s_lin[2], h->dls, h->gC, B, Hh, L))) return r;
+    LEW(add_inplace_k, B * Hh, h->dh, h->gC, B * Hh);
+    if ((r = lin_bwd(h, h->fs, p.s_lin[0], h->dh, h->gA, B, N * ec[2], Hh))) return r;                              // dfs
+    bn_bwd(h, h->gA, ec[2], h->h3, ec[2], p.encs_g, p.encs_b, h->gA, ec[2], Rn, ec[2], ACT_NONE, 0);                // dh3
+    bn_bwd(h, h->gA, ec[2], h->h3p, ec[2], p.gs_bng[2], p.gs_bnb[2], h->gA, ec[2], Rn, ec[2], ACT_RELU, 0);         // dh3p
+    conv_bwd(h, h->h2, p.gs_k[2], p.gs_b[2], h->gA, h->gB, Rn, ec[1], ec[2]);
+    bn_bwd(h, h->gB, ec[1], h->h2p, ec[1], p.gs_bng[1], p.gs_bnb[1], h->gB, ec[1], Rn, ec[1], ACT_RELU, 0);
+    conv_bwd(h, h->h1, p.gs_k[1], p.gs_b[1], h->gB, h->gA, Rn, ec[0], ec[1]);
+    bn_bwd(h, h->gA, ec[0], h->h1p, ec[0], p.gs_bng[0], p.gs_bnb[0], h->gA, ec[0], Rn, ec[0], ACT_RELU, 0);
+    conv_bwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->gA, nullptr, Rn, D, ec[0]);
+  }
+  // joint head (z_sg rows are graph-major: row b*S+s; the S-mean gives dz = dzbar[b]/S)
+  {
+    int L = c.sg_latent_size, Hh = c.sg_hidden_size;
+    const int h02 = c.sg_conv_hidden[0][2], h12 = c.sg_conv_hidden[1][2];
+    LEW(reparam_kl_bwd_k, BS * L, h->mu_sg, h->ls_sg, nz->eps_sg, h->dzbar, h->dmu, h->dls, BS, L, S, beta / (gB * S * L));
+    if ((r = lin_bwd(h, h->hsg, p.sg_lin[1], h->dmu, h->dh, BS, Hh, L))) return r;
+    float* tmp = h->dmu;   // reuse: dmu is consumed
+    if ((r = lin_bwd(h, h->hsg, p.sg_lin[2], h->dls, tmp, BS, Hh, L))) return r;
+    LEW(add_inplace_k, BS * Hh, h->dh, tmp, BS * Hh);
+    if ((r = lin_bwd(h, h->fsg, p.sg_lin[0], h->dh, h->dfsg, BS, N * h12, Hh))) return r;
+    for (long long s0 = 0; s0 < BS; s0 += h->SC) {
+      long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
+      if (BS > h->SC || true) { if ((r = sgc_chunk_fwd(h, in, s0, ns))) return r; }     // recompute the chunk's activations
+      const float* x0 = in->features + s0 * N * F;
+      // fsg = BN_encsg(x2); x2 = lrelu(BN_sg1(y1))
+      bn_bwd(h, h->dfsg + s0 * N * h12, h12, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h12, ns * N, h12, ACT_NONE, 0);
+      bn_bwd(h, h->dxa, h12, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->dxa, h12, ns * N, h12, ACT_LRELU, 0);      // dy1
+      LAUNCH(sgc_layer_bwd_k, (unsigned)ns, 256, 0, h->x1, h->dxa, h->dxb, h->E, sgc_w(h, h->P, 1), h->S1, N, s0);  // dx1
+      { SgcW w = sgc_w(h, h->P, 1); int np = (3 * w.C + 4) * w.h0 + (2 * w.C + 2 + w.h0) * w.h1 + (w.C + w.h1 + 1) * w.h2;
+        dim3 g(cdiv(np, 256), cdiv(ns, SGC_PG));
+        LAUNCH(sgc_param_grad_k, g, 256, 0, h->x1, h->dxa, h->E, w, sgc_w(h, h->G, 1), h->S1, N, ns, s0); }
+      bn_bwd(h, h->dxb, h02, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->dxb, h02, ns * N, h02, ACT_LRELU, 0);      // dy0
+      LAUNCH(sgc_layer_bwd_k, (unsigned)ns, 256, 0, x0, h->dxb, (float*)nullptr, h->E, sgc_w(h, h->P, 0), h->S0, N, s0);
+      { SgcW w = sgc_w(h, h->P, 0); int np = (3 * w.C + 4) * w.h0 + (2 * w.C + 2 + w.h0) * w.h1 + (w.C + w.h1 + 1) * w.h2;
+        dim3 g(cdiv(np, 256), cdiv(ns, SGC_PG));
+        LAUNCH(sgc_param_grad_k, g, 256, 0, x0, h->dxb, h->E, w, sgc_w(h, h->G, 0), h->S0, N, ns, s0); }
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// step drivers
+// ------------------------------------------------------------------------------------------
+static int check_inputs(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz) {
+  if (!in || !nz) return fail(h, SNDVAE_E_ARG, "inputs / noise struct is NULL");
+  if (!in->features || !in->adj || !in->rel || !in->adj_truth || !in->feature_truth || !in->spatial_truth)
+    return fail(h, SNDVAE_E_ARG, "a required feed (features, adj, rel, adj_truth, feature_truth, spatial_truth) is NULL");
+  if (!nz->eps_sg || (h->dis && (!nz->eps_s || !nz->eps_g))) return fail(h, SNDVAE_E_ARG, "a required noise tensor is NULL");
+  return 0;
+}
+
+static int copy_latents(sndvae_t* h, sndvae_outputs* out) {
+  if (!out) return 0;
+  const sndvae_config& c = h->cfg;
+#define CP_(dst, src, n) if (out->dst && (src)) CK(cudaMemcpyAsync(out->dst, (src), sizeof(float) * (n), cudaMemcpyDeviceToDevice, h->stream))
+  if (h->dis) {
+    CP_(z_mean_s, h->mu_s, h->B * c.s_latent_size); CP_(z_std_s, h->ls_s, h->B * c.s_latent_size); CP_(z_s, h->z_s, h->B * c.s_latent_size);
+    CP_(z_mean_g, h->mu_g, h->B * c.g_latent_size); CP_(z_std_g, h->ls_g, h->B * c.g_latent_size); CP_(z_g, h->z_g, h->B * c.g_latent_size);
+  }
+  CP_(z_mean_sg, h->mu_sg, h->BS * c.sg_latent_size); CP_(z_std_sg, h->ls_sg, h->BS * c.sg_latent_size); CP_(z_sg, h->z_sg, h->BS * c.sg_latent_size);
+#undef CP_
+  return 0;
+}
+
+// losses_host <- optimizer.overall_loss (optimizer.py:200-203)
+static int fetch_losses(sndvae_t* h, float* losses_host) {
+  CK(cudaMemcpyAsync(h->pinned_loss, h->loss, sizeof(float) * 8, cudaMemcpyDeviceToHost, h->stream));
+  int ef = 0;
+  CK(cudaMemcpyAsync(&ef, h->errflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (ef) { cudaMemsetAsync(h->errflag, 0, sizeof(int), h->stream);
+            return fail(h, SNDVAE_E_DENSE, "a sampled adjacency has more than edge_capacity=%d non-zeros; the joint encoder expects spanning-forest samples (input_data.py:18-38)", h->cfg.edge_capacity); }
+  if (!losses_host) return 0;
+  const sndvae_config& c = h->cfg; const float* L = h->pinned_loss;
+  const double B = (double)h->B, N = h->N;
+  float adj = (float)(L[0] / (B * N * N)), node = (float)(L[1] / (B * N * h->F)), sp = (float)(L[2] / (B * N * h->D));
+  float kl_sg = (float)(L[5] / ((double)h->BS * c.sg_latent_size));
+  if (h->dis) {
+    float kl_s = (float)(L[3] / (B * c.s_latent_size)), kl_g = (float)(L[4] / (B * c.g_latent_size));
+    losses_host[0] = adj + node + sp + c.beta * (kl_sg + kl_s + kl_g);
+    losses_host[1] = sp; losses_host[2] = adj; losses_host[3] = node; losses_host[4] = kl_g; losses_host[5] = kl_s; losses_host[6] = kl_sg;
+  } else {
+    losses_host[0] = adj + node + sp + c.beta * kl_sg;
+    losses_host[1] = sp; losses_host[2] = adj; losses_host[3] = node; losses_host[4] = kl_sg;
+  }
+  return 0;
+}
+
+static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host,
+               bool backward, long long global_batch) {
+  int r = check_inputs(h, in, nz); if (r) return r;
+  const float gB = (float)(global_batch > 0 ? global_batch : h->B);
+  CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * 8, h->stream));
+  if (backward) CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
+  if ((r = encoder_fwd(h, in))) return r;
+  if ((r = reparam_fwd(h, nz))) return r;
+  if ((r = copy_latents(h, out))) return r;
+  if ((r = decoder_fwd(h, in, out, backward, gB))) return r;
+  if (backward && (r = backward_rest(h, in, nz, gB))) return r;
+  CK(cudaGetLastError());
+  return fetch_losses(h, losses_host);
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int sndvae_default_config(sndvae_config* c) {
+  if (!c) return SNDVAE_E_ARG;
+  memset(c, 0, sizeof *c);
+  c->model_type = SNDVAE_MODEL_DISENTANGLED; c->num_nodes = 25; c->num_feature = 1; c->spatial_dim = 2; c->sampling_num = 10;
+  c->node_h_size = 20;
+  c->s_channel[0] = 10; c->s_channel[1] = 10; c->s_channel[2] = 20; c->s_hidden_size = 100; c->s_latent_size = 100;
+  c->g_conv_hidden[0] = 10; c->g_conv_hidden[1] = 20; c->g_hidden_size = 100; c->g_latent_size = 100;
+  for (int k = 0; k < 3; ++k) { c->sg_conv_hidden[0][k] = 20; c->sg_conv_hidden[1][k] = 50; }
+  c->sg_hidden_size = 100; c->sg_latent_size = 100;
+  c->s_d_channel[0] = 50; c->s_d_channel[1] = 20; c->s_d_channel[2] = 10;
+  c->n_d_channel[0] = 50; c->n_d_channel[1] = 20; c->e_d_hidden[0] = 50; c->e_d_hidden[1] = 20;
+  c->batch_size = 10; c->chunk_graphs = 0; c->edge_capacity = 0; c->use_tensor_cores = 1;
+  c->learning_rate = 0.0008f; c->beta = 1.f; c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f; c->adam_eps = 1e-8f;
+  return 0;
+}
+
+int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
+  if (!cfg || !out) return SNDVAE_E_ARG;
+  *out = nullptr;
+  sndvae_t* h = new sndvae_handle();
+  *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
+  h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
+  h->hf_features = nullptr;
+  sndvae_config& c = h->cfg;
+  if (c.num_nodes < 2 || c.batch_size < 1 || c.num_feature < 1 || c.spatial_dim < 1 || c.node_h_size < 1)
+    return fail(h, SNDVAE_E_ARG, "bad config: num_nodes=%d batch_size=%d", c.num_nodes, c.batch_size);
+  if (c.model_type != SNDVAE_MODEL_DISENTANGLED && c.model_type != SNDVAE_MODEL_BASE) return fail(h, SNDVAE_E_ARG, "bad model_type %d", c.model_type);
+  h->dis = c.model_type == SNDVAE_MODEL_DISENTANGLED;
+  if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
+  if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
+  if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);
+  if (c.g_conv_hidden[0] > 32 || c.g_conv_hidden[1] > 32) return fail(h, SNDVAE_E_ARG, "g_conv_hidden must be <= 32");
+  h->N = c.num_nodes; h->F = c.num_feature; h->D = c.spatial_dim; h->S = c.sampling_num; h->H = c.node_h_size;
+  h->Chv = h->dis ? 2 * h->H : h->H; h->C1 = c.e_d_hidden[0]; h->C2 = c.e_d_hidden[1];
+  h->B = c.batch_size; h->BS = h->B * h->S; h->Rn = h->B * h->N;
+  if (c.edge_capacity <= 0) c.edge_capacity = 4 * h->N;
+  if (c.use_tensor_cores && (h->C1 != TC_C1 || h->C2 != TC_C2))
+    return fail(h, SNDVAE_E_ARG, "tensor-core e2e path requires e_d_hidden = (%d, %d)", TC_C1, TC_C2);
+  if (c.chunk_graphs <= 0) {
+    // bound the N^2 staging buffers to ~24 GB: ~320 B per (i,j) cell
+    long long per_graph = (long long)h->N * h->N * 340;
+    long long bc = (24LL << 30) / per_graph; if (bc < 1) bc = 1; if (bc > h->B) bc = h->B; if (bc > 512) bc = 512;
+    c.chunk_graphs = (int)bc;
+  }
+  if (c.chunk_graphs > h->B) c.chunk_graphs = (int)h->B;
+  h->Bc = c.chunk_graphs;
+  { long long per_sample = (long long)h->N * 700 * 4 + (long long)c.edge_capacity * 75 * 4;
+    long long sc = (4LL << 30) / per_sample; if (sc < 1) sc = 1; if (sc > h->BS) sc = h->BS; h->SC = (int)sc; }
+  if ((long long)2 * h->Bc * h->N * h->N * h->C1 > 2000000000LL) return fail(h, SNDVAE_E_ARG, "chunk too large for 32-bit GEMM dims");
+  build_table(h);      // host-only: the table is valid even when no device is present (checked by the CPU tests)
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, SNDVAE_E_CUDA, "no CUDA device: the SND-VAE hot path has no CPU fallback");
+  cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
+  if (prop.major < 10) return fail(h, SNDVAE_E_CUDA, "device sm_%d%d is not sm_100: this library is built for B200 only", prop.major, prop.minor);
+  if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(h, SNDVAE_E_CUDA, "cublasCreate failed");
+  cublasSetStream(h->blas, h->stream);
+  cublasSetMathMode(h->blas, CUBLAS_PEDANTIC_MATH);       // plain fp32 library GEMMs, no TF32
+  int r = alloc_buffers(h); if (r) return r;
+  if (cudaMallocHost((void**)&h->pinned_loss, 64) != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMallocHost failed");
+  h->b1p = c.adam_beta1; h->b2p = c.adam_beta2;
+  h->ev.resize(4096);
+  for (auto& e : h->ev) { cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.flops = 0; }
+  if (c.use_tensor_cores) {
+    if ((r = tc_init(h->tc, h->N, 2LL * h->Bc * h->N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sndvae_destroy(sndvae_t* h) {
+  if (!h) return 0;
+  cudaStreamSynchronize(h->stream);
+  tc_destroy(h->tc);
+  for (void* p : h->allocs) cudaFree(p);
+  for (auto& e : h->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (h->pinned_loss) cudaFreeHost(h->pinned_loss);
+  if (h->blas) cublasDestroy(h->blas);
+  delete h;
+  return 0;
+}
+
+const char* sndvae_last_error(const sndvae_t* h) { return h ? h->err.c_str() : "null handle"; }
+int64_t sndvae_param_count(const sndvae_t* h) { return h ? h->nparam : 0; }
+int32_t sndvae_num_params(const sndvae_t* h) { return h ? (int32_t)h->table.size() : 0; }
+int sndvae_param_table(const sndvae_t* h, sndvae_param_info* t, int32_t cap) {
+  if (!h || !t) return SNDVAE_E_ARG;
+  if (cap < (int32_t)h->table.size()) return SNDVAE_E_ARG;
+  memcpy(t, h->table.data(), sizeof(sndvae_param_info) * h->table.size());
+  return 0;
+}
+int sndvae_get_params(sndvae_t* h, float* dst) {
+  if (!h || !dst) return SNDVAE_E_ARG;
+  CK(cudaMemcpyAsync(dst, h->P, sizeof(float) * h->nparam, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream)); return 0;
+}
+int sndvae_set_params(sndvae_t* h, const float* src) {
+  if (!h || !src) return SNDVAE_E_ARG;
+  CK(cudaMemcpyAsync(h->P, src, sizeof(float) * h->nparam, cudaMemcpyHostToDevice, h->stream)); CK(cudaStreamSynchronize(h->stream)); return 0;
+}
+int sndvae_get_adam(sndvae_t* h, float* m, float* v, float* bp) {
+  if (!h) return SNDVAE_E_ARG;
+  if (m) CK(cudaMemcpyAsync(m, h->M, sizeof(float) * h->nparam, cudaMemcpyDeviceToHost, h->stream));
+  if (v) CK(cudaMemcpyAsync(v, h->V, sizeof(float) * h->nparam, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (bp) { bp[0] = h->b1p; bp[1] = h->b2p; }
+  return 0;
+}
+int sndvae_set_adam(sndvae_t* h, const float* m, const float* v, const float* bp) {
+  if (!h) return SNDVAE_E_ARG;
+  if (m) CK(cudaMemcpyAsync(h->M, m, sizeof(float) * h->nparam, cudaMemcpyHostToDevice, h->stream));
+  if (v) CK(cudaMemcpyAsync(h->V, v, sizeof(float) * h->nparam, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (bp) { h->b1p = bp[0]; h->b2p = bp[1]; }
+  return 0;
+}
+float* sndvae_params_device(sndvae_t* h) { return h ? h->P : nullptr; }
+float* sndvae_grads_device(sndvae_t* h) { return h ? h->G : nullptr; }
+
+int sndvae_forward(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host) {
+  if (!h) return SNDVAE_E_ARG;
+  return run(h, in, nz, out, losses_host, false, 0);
+}
+int sndvae_grads(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host, int64_t gb) {
+  if (!h) return SNDVAE_E_ARG;
+  return run(h, in, nz, out, losses_host, true, gb);
+}
+int sndvae_apply_adam(sndvae_t* h) {
+  if (!h) return SNDVAE_E_ARG;
+  const sndvae_config& c = h->cfg;
+  // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) with fp32 running powers (TF ApplyAdam)
+  float alpha = c.learning_rate * sqrtf(1.f - h->b2p) / (1.f - h->b1p);
+  long long n4 = h->nparam / 4;
+  unsigned grid = cdiv(n4, 256); if (grid > 148 * 8) grid = 148 * 8;
+  LAUNCH(tf_adam_k, grid, 256, 0, (float4*)h->P, (const float4*)h->G, (float4*)h->M, (float4*)h->V, n4, alpha, 1.f - c.adam_beta1,
+         1.f - c.adam_beta2, c.adam_eps);
+  h->b1p *= c.adam_beta1; h->b2p *= c.adam_beta2;
+  CK(cudaGetLastError());
+  return 0;
+}
+int sndvae_train_step(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host) {
+  if (!h) return SNDVAE_E_ARG;
+  int r = run(h, in, nz, out, losses_host, true, 0); if (r) return r;
+  return sndvae_apply_adam(h);
+}
+
+int sndvae_generate(sndvae_t* h, const float* z_s, const float* z_sg, const float* z_g, sndvae_outputs* out) {
+  if (!h || !z_sg || !out) return SNDVAE_E_ARG;
+  if (h->dis && (!z_s || !z_g)) return fail(h, SNDVAE_E_ARG, "z_s / z_g required for the disentangled model");
+  const sndvae_config& c = h->cfg;
+  CK(cudaMemcpyAsync(h->z_sg, z_sg, sizeof(float) * h->BS * c.sg_latent_size, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->dis) {
+    CK(cudaMemcpyAsync(h->z_s, z_s, sizeof(float) * h->B * c.s_latent_size, cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->z_g, z_g, sizeof(float) * h->B * c.g_latent_size, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  int r = decoder_fwd(h, nullptr, out, false, (float)h->B); if (r) return r;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, int64_t* gen_adj_host, float* losses_host) {
+  if (!h) return SNDVAE_E_ARG;
+  int r = check_inputs(h, in, nz); if (r) return r;
+  const sndvae_config& c = h->cfg; const int N = h->N; const long long B = h->B, BS = h->BS;
+  if (!h->hf_features) {
+    DA(h->hf_features, BS * N * h->F); DA(h->hf_adj, BS * N * N); DA(h->hf_rel, BS * N * N); DA(h->hf_adj_truth, B * N * N);
+    DA(h->hf_feature_truth, B * N * h->F); DA(h->hf_spatial_truth, B * N * h->D);
+    DA(h->hf_eps_s, B * c.s_latent_size); DA(h->hf_eps_sg, BS * c.sg_latent_size); DA(h->hf_eps_g, B * c.g_latent_size);
+    DA(h->hf_gen_adj, B * N * N);
+  }
+#define H2D(dst, src, n) CK(cudaMemcpyAsync(dst, src, sizeof(float) * (n), cudaMemcpyHostToDevice, h->stream))
+  H2D(h->hf_features, in->features, BS * N * h->F); H2D(h->hf_adj, in->adj, BS * N * N); H2D(h->hf_rel, in->rel, BS * N * N);
+  H2D(h->hf_adj_truth, in->adj_truth, B * N * N); H2D(h->hf_feature_truth, in->feature_truth, B * N * h->F);
+  H2D(h->hf_spatial_truth, in->spatial_truth, B * N * h->D);
+  H2D(h->hf_eps_sg, nz->eps_sg, BS * c.sg_latent_size);
+  if (h->dis) { H2D(h->hf_eps_s, nz->eps_s, B * c.s_latent_size); H2D(h->hf_eps_g, nz->eps_g, B * c.g_latent_size); }
+#undef H2D
+  sndvae_inputs din; memset(&din, 0, sizeof din);
+  din.features = h->hf_features; din.adj = h->hf_adj; din.rel = h->hf_rel; din.adj_truth = h->hf_adj_truth;
+  din.feature_truth = h->hf_feature_truth; din.spatial_truth = h->hf_spatial_truth;
+  sndvae_noise dnz; dnz.eps_s = h->hf_eps_s; dnz.eps_sg = h->hf_eps_sg; dnz.eps_g = h->hf_eps_g;
+  sndvae_outputs o; memset(&o, 0, sizeof o); o.generated_adj = gen_adj_host ? (int64_t*)h->hf_gen_adj : nullptr;
+  r = sndvae_train_step(h, &din, &dnz, &o, losses_host); if (r) return r;
+  if (gen_adj_host) { CK(cudaMemcpyAsync(gen_adj_host, h->hf_gen_adj, sizeof(int64_t) * B * N * N, cudaMemcpyDeviceToHost, h->stream)); }
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t sndvae_launch_count(const sndvae_t* h) { return h ? h->launches : 0; }
+
+int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms, int64_t* launches, double* flops) {
+  if (!h) return SNDVAE_E_ARG;
+  CK(cudaStreamSynchronize(h->stream));
+  double ms = 0, fl = 0;
+  for (size_t i = 0; i < h->ev_used; ++i) { float t = 0; cudaEventElapsedTime(&t, h->ev[i].a, h->ev[i].b); ms += t; fl += h->ev[i].flops; }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (int64_t)h->ev_used;
+  if (flops) *flops = fl;
+  if (reset) h->ev_used = 0;
+  return 0;
+}
+
+int sndvae_threshold_logits(sndvae_t* h, const float* logits, int64_t n, int64_t* out) {
+  if (!h || !logits || !out) return SNDVAE_E_ARG;
+  LEW(threshold_logits_k, n, logits, (long long)n, (long long*)out);
+  CK(cudaGetLastError()); CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int64_t sndvae_debug_read(sndvae_t* h, const char* name, float* dst, int64_t cap) {
+  if (!h || !name || !dst) return SNDVAE_E_ARG;
+  const sndvae_config& c = h->cfg;
+  struct { const char* n; const float* p; long long len; } tab[] = {
+    {"fg", h->fg, h->dis ? h->Rn * (c.g_conv_hidden[1] + h->F) : 0}, {"fs", h->fs, h->dis ? h->Rn * c.s_channel[2] : 0},
+    {"fsg", h->fsg, h->BS * h->N * c.sg_conv_hidden[1][2]}, {"n_sg", h->n_sg, h->Rn * h->H}, {"v", h->v, h->Rn * h->Chv},
+    {"a", h->a, h->Rn * h->Chv}, {"c", h->c, h->Rn * h->Chv}, {"Rc", h->Rc, h->Rn * h->C1}, {"Sa", h->Sa, h->Rn * h->C1},
+    {"E1", h->E1, (long long)h->Bc * h->N * h->N * h->C1}, {"O12", h->O12, 2LL * h->Bc * h->N * h->N * h->C2},
+    {"dY12", h->dY12, 2LL * h->Bc * h->N * h->N * h->C1}, {"da", h->da, h->Rn * h->Chv}, {"dc", h->dc, h->Rn * h->Chv},
+    {"dv", h->dv, h->Rn * h->Chv}, {"dfsg", h->dfsg, h->BS * h->N * c.sg_conv_hidden[1][2]}, {"loss", h->loss, 8},
+  };
+  for (auto& t : tab) if (!strcmp(t.n, name)) {
+    long long n = t.len < cap ? t.len : cap;
+    if (n <= 0 || !t.p) return 0;
+    CK(cudaMemcpyAsync(dst, t.p, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream)); CK(cudaStreamSynchronize(h->stream));
+    return n;
+  }
+  return fail(h, SNDVAE_E_ARG, "unknown debug buffer '%s'", name);
+}
+
+}  // extern "C"

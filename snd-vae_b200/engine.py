@@ -1,0 +1,282 @@
+"""Engine: the device-side state behind the reference-facing shims.
+
+Thin host layer over the C ABI: owns a handle, moves feeds, returns torch
+tensors.  PyTorch is used for device memory, streams and torch.distributed only;
+all arithmetic runs in libsndvae.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+FEED_KEYS = ("features", "spatial", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth", "rel_truth")
+NOISE_KEYS = ("eps_s", "eps_sg", "eps_g")
+
+
+class SndvaeError(RuntimeError):
+    """Raised where TensorFlow would raise InvalidArgumentError / a runtime error."""
+
+
+class _ArenaView:
+    """Zero-copy torch view of a library-owned device arena (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def make_config(num_nodes: int, batch_size: int, model_type: str = "disentangled", **kw) -> _lib.Config:
+    lib = _lib.load()
+    cfg = _lib.Config()
+    lib.sndvae_default_config(C.byref(cfg))
+    cfg.num_nodes, cfg.batch_size = num_nodes, batch_size
+    cfg.model_type = 1 if model_type == "base" else 0
+    for k, v in kw.items():
+        cur = getattr(cfg, k)
+        if hasattr(cur, "__len__"):
+            if k == "sg_conv_hidden":
+                for i in range(2):
+                    for j in range(3):
+                        cur[i][j] = int(v[i][j])
+            else:
+                for i, x in enumerate(v):
+                    cur[i] = int(x)
+        else:
+            setattr(cfg, k, v)
+    if cfg.model_type == 1:
+        cfg.sampling_num = 1
+    return cfg
+
+
+class Engine:
+    def __init__(self, cfg: _lib.Config, device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise SndvaeError("no CUDA device: the SND-VAE hot path is hand-written CUDA for sm_100a and has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.sndvae_create(C.byref(cfg), C.c_void_p(stream), C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.sndvae_last_error(self._h).decode() if self._h else "create failed"
+            if self._h:
+                self.lib.sndvae_destroy(self._h)
+            self._h = C.c_void_p()
+            raise SndvaeError(f"sndvae_create: {msg} (code {rc})")
+        self.dis = cfg.model_type == 0
+        self.N, self.F, self.D = cfg.num_nodes, cfg.num_feature, cfg.spatial_dim
+        self.S, self.B = cfg.sampling_num, cfg.batch_size
+        self.nparam = int(self.lib.sndvae_param_count(self._h))
+        n = int(self.lib.sndvae_num_params(self._h))
+        tab = (_lib.ParamInfo * n)()
+        self._check(self.lib.sndvae_param_table(self._h, tab, n))
+        self.table = [(t.name.decode(), int(t.offset), tuple(int(t.shape[i]) for i in range(t.rank))) for t in tab]
+        self._keep = None
+
+    # -- plumbing -----------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise SndvaeError(f"{self.lib.sndvae_last_error(self._h).decode()} (code {rc})")
+
+    def close(self):
+        if self._h:
+            self.lib.sndvae_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape_of(self, key):
+        B, S, N, F, D = self.B, self.S, self.N, self.F, self.D
+        c = self.cfg
+        return {
+            "features": (B * S, N, F), "spatial": (B * S, N, D), "adj": (B * S, N, N), "rel": (B * S, N, N, 1),
+            "adj_truth": (B, N, N), "feature_truth": (B, N, F), "spatial_truth": (B, N, D), "rel_truth": (B, N, N, 1),
+            "eps_s": (B, c.s_latent_size), "eps_sg": (B * S, c.sg_latent_size), "eps_g": (B, c.g_latent_size),
+            "z_mean_s": (B, c.s_latent_size), "z_std_s": (B, c.s_latent_size), "z_s": (B, c.s_latent_size),
+            "z_mean_g": (B, c.g_latent_size), "z_std_g": (B, c.g_latent_size), "z_g": (B, c.g_latent_size),
+            "z_mean_sg": (B * S, c.sg_latent_size), "z_std_sg": (B * S, c.sg_latent_size), "z_sg": (B * S, c.sg_latent_size),
+            "generated_adj": (B, N, N), "generated_adj_prob": (B, N, N, 2),
+            "generated_spatial": (B, N, D), "generated_node_feat": (B, N, F),
+        }[key]
+
+    def _dev(self, key, t):
+        """Validate one feed: static shape as in main.py:253-264 (TF raises on mismatch)."""
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(np.asarray(t))
+        want = self._shape_of(key)
+        if tuple(t.shape) != want and not (key in ("rel", "rel_truth") and tuple(t.shape) == want[:-1]):
+            raise SndvaeError(f"feed '{key}' has shape {tuple(t.shape)}, expected {want}")
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _pack(self, feeds, noise):
+        keep = []
+        inp = _lib.Inputs()
+        for k in FEED_KEYS:
+            t = self._dev(k, feeds.get(k))
+            if t is not None:
+                keep.append(t)
+                setattr(inp, k, t.data_ptr())
+        nz = _lib.Noise()
+        for k in NOISE_KEYS:
+            t = self._dev(k, noise.get(k)) if (self.dis or k == "eps_sg") else None
+            if t is not None:
+                keep.append(t)
+                setattr(nz, k, t.data_ptr())
+        return inp, nz, keep
+
+    def _outs(self, fetch):
+        out = _lib.Outputs()
+        res = {}
+        for k in fetch:
+            if k not in _lib.OUTPUT_FIELDS:
+                raise SndvaeError(f"unknown fetch '{k}'")
+            if not self.dis and k in ("z_mean_s", "z_std_s", "z_s", "z_mean_g", "z_std_g", "z_g"):
+                continue
+            dt = torch.int64 if k == "generated_adj" else torch.float32
+            res[k] = torch.empty(self._shape_of(k), dtype=dt, device=self.device)
+            setattr(out, k, res[k].data_ptr())
+        return out, res
+
+    @property
+    def n_losses(self):
+        return 7 if self.dis else 5
+
+    # -- parameters ---------------------------------------------------------------------
+    def set_params(self, params: Dict[str, torch.Tensor]):
+        flat = np.zeros(self.nparam, dtype=np.float32)
+        for name, off, shape in self.table:
+            v = params[name].detach().cpu().to(torch.float32).numpy()
+            if tuple(v.shape) != shape:
+                raise SndvaeError(f"param '{name}' has shape {tuple(v.shape)}, expected {shape}")
+            flat[off:off + v.size] = v.reshape(-1)
+        self._check(self.lib.sndvae_set_params(self._h, flat.ctypes.data))
+
+    def _unflatten(self, flat):
+        return {name: torch.from_numpy(flat[off:off + int(np.prod(shape))].reshape(shape).copy())
+                for name, off, shape in self.table}
+
+    def get_params(self) -> Dict[str, torch.Tensor]:
+        flat = np.empty(self.nparam, dtype=np.float32)
+        self._check(self.lib.sndvae_get_params(self._h, flat.ctypes.data))
+        return self._unflatten(flat)
+
+    def get_adam(self):
+        m = np.empty(self.nparam, dtype=np.float32)
+        v = np.empty(self.nparam, dtype=np.float32)
+        bp = np.empty(2, dtype=np.float32)
+        self._check(self.lib.sndvae_get_adam(self._h, m.ctypes.data, v.ctypes.data, bp.ctypes.data))
+        return self._unflatten(m), self._unflatten(v), bp
+
+    def set_adam(self, m, v, bp):
+        fm = np.zeros(self.nparam, dtype=np.float32)
+        fv = np.zeros(self.nparam, dtype=np.float32)
+        for name, off, shape in self.table:
+            a = m[name].detach().cpu().numpy().reshape(-1); fm[off:off + a.size] = a
+            b = v[name].detach().cpu().numpy().reshape(-1); fv[off:off + b.size] = b
+        bp = np.asarray(bp, dtype=np.float32)
+        self._check(self.lib.sndvae_set_adam(self._h, fm.ctypes.data, fv.ctypes.data, bp.ctypes.data))
+
+    def grads_tensor(self) -> torch.Tensor:
+        """Zero-copy view of the gradient arena (for torch.distributed.all_reduce)."""
+        ptr = self.lib.sndvae_grads_device(self._h)
+        return torch.as_tensor(_ArenaView(ptr, self.nparam), device=self.device)
+
+    def params_tensor(self) -> torch.Tensor:
+        ptr = self.lib.sndvae_params_device(self._h)
+        return torch.as_tensor(_ArenaView(ptr, self.nparam), device=self.device)
+
+    def get_grads(self) -> Dict[str, torch.Tensor]:
+        return self._unflatten(self.grads_tensor().cpu().numpy())
+
+    # -- the step -----------------------------------------------------------------------
+    def forward(self, feeds, noise, fetch=_lib.OUTPUT_FIELDS):
+        inp, nz, keep = self._pack(feeds, noise)
+        out, res = self._outs(fetch)
+        losses = np.zeros(8, dtype=np.float32)
+        self._check(self.lib.sndvae_forward(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data))
+        res["overall_loss"] = losses[:self.n_losses].copy()
+        return res
+
+    def grads(self, feeds, noise, fetch=("generated_adj",), global_batch=0):
+        inp, nz, keep = self._pack(feeds, noise)
+        out, res = self._outs(fetch)
+        losses = np.zeros(8, dtype=np.float32)
+        self._check(self.lib.sndvae_grads(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data, global_batch))
+        res["overall_loss"] = losses[:self.n_losses].copy()
+        return res
+
+    def apply_adam(self):
+        self._check(self.lib.sndvae_apply_adam(self._h))
+
+    def train_step(self, feeds, noise, fetch=("generated_adj",)):
+        inp, nz, keep = self._pack(feeds, noise)
+        out, res = self._outs(fetch)
+        losses = np.zeros(8, dtype=np.float32)
+        self._check(self.lib.sndvae_train_step(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data))
+        res["overall_loss"] = losses[:self.n_losses].copy()
+        return res
+
+    def train_step_packed(self, inp, nz, out, losses):
+        """Bench path: pre-packed structs, device-resident feeds."""
+        self._check(self.lib.sndvae_train_step(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data))
+
+    def grads_packed(self, inp, nz, out, losses, global_batch):
+        self._check(self.lib.sndvae_grads(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data, global_batch))
+
+    def train_step_host(self, feeds_np, noise_np, gen_adj_np, losses_np):
+        """The reference-facing call: host (pinned) numpy in, host numpy out (main.py:327-331)."""
+        inp = _lib.Inputs()
+        for k in FEED_KEYS:
+            a = feeds_np.get(k)
+            if a is not None:
+                setattr(inp, k, a.ctypes.data)
+        nz = _lib.Noise()
+        for k in NOISE_KEYS:
+            a = noise_np.get(k)
+            if a is not None:
+                setattr(nz, k, a.ctypes.data)
+        self._check(self.lib.sndvae_train_step_host(self._h, C.byref(inp), C.byref(nz), gen_adj_np.ctypes.data,
+                                                    losses_np.ctypes.data))
+
+    def generate(self, z_s, z_sg, z_g, fetch=("generated_adj", "generated_adj_prob", "generated_spatial", "generated_node_feat")):
+        zs = self._dev("z_s", z_s) if self.dis else None
+        zg = self._dev("z_g", z_g) if self.dis else None
+        zsg = self._dev("z_sg", z_sg)
+        out, res = self._outs(fetch)
+        self._check(self.lib.sndvae_generate(self._h, zs.data_ptr() if zs is not None else None, zsg.data_ptr(),
+                                             zg.data_ptr() if zg is not None else None, C.byref(out)))
+        return res
+
+    def threshold_logits(self, logits: torch.Tensor) -> torch.Tensor:
+        lg = logits.to(device=self.device, dtype=torch.float32).contiguous()
+        n = lg.numel() // 2
+        out = torch.empty(lg.shape[:-1], dtype=torch.int64, device=self.device)
+        self._check(self.lib.sndvae_threshold_logits(self._h, lg.data_ptr(), n, out.data_ptr()))
+        return out
+
+    def debug_read(self, name: str, n: int) -> np.ndarray:
+        buf = np.empty(n, dtype=np.float32)
+        got = self.lib.sndvae_debug_read(self._h, name.encode(), buf.ctypes.data, n)
+        if got < 0:
+            self._check(int(got))
+        return buf[:got]
+
+    def launch_count(self) -> int:
+        return int(self.lib.sndvae_launch_count(self._h))
+
+    def gemm_timing(self, reset=True):
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        self._check(self.lib.sndvae_gemm_timing(self._h, 1 if reset else 0, C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
