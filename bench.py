@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- train graphs/sec (fwd + bwd + Adam) of the SND-VAE step at N=256.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU, NCCL gradient all-reduce)
+
+A "step" is one pass of the hot path over one batch of synthetic spatial graphs:
+encoder + reparameterisation + decoder + ELBO + backward + TF-Adam for
+`--batch` graphs per GPU (weak scaling).  Workload = BASELINE.json configs[2]:
+the 3-latent model (model.py) at N=256, 4096 graphs per step per GPU, S=10
+spanning-tree samples per graph, fp32 arithmetic (e2e layer 1 as 3-pass split-bf16
+on tcgen05 with fp32 accumulation).
+
+`value`   : device-resident inputs (CUDA events around K steps, max over ranks).
+`e2e`     : the same step through the host-buffer entry point
+            (sndvae_train_step_host: pinned numpy feeds in, losses + int64
+            adjacency out), host<->device copies inside the timed region.
+`roofline`: the e2e layer-1 GEMM launches (fwd, dgrad, wgrad), timed live with CUDA
+            events on the launching stream; algorithmic FLOPs (SURVEY 8d F1 per
+            graph per GEMM) over measured bf16 peak.  Executed MMA FLOPs are 3x.
+`cpu_baseline` / `--impl reference`: TensorFlow is not installable here, so the
+            reference arm is the oracle's CPU restatement of the reference
+            (kind "port"), timed on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "train_graphs_per_sec"
+UNIT = "graphs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=4096, help="graphs per step per GPU")
+    ap.add_argument("--sampling", type=int, default=10)
+    ap.add_argument("--model", default="disentangled", choices=["disentangled", "base"])
+    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic graphs generated on the host, tiled to --batch")
+    ap.add_argument("--tc", type=int, default=1)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=2, help="graphs in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def f1_flops(N, C1=50, C2=20):
+    p = (N - 1) // 2
+    q = N - 1 - p
+    V = N * N - p * (p + 1) // 2 - q * (q + 1) // 2
+    return 2.0 * 2.0 * N * V * C1 * C2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop, self.th = index, [], threading.Event(), None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle's restatement of the reference, timed on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_reference(args, steps, warmup):
+    """fwd + bwd (autograd) + TF-Adam of the factored CPU restatement on `cpu_sample`
+    graphs of the same workload (N, S, model).  The literal, as-written form needs 4.2 GB
+    per sample at N=256 (layers.py:174-177) and is infeasible."""
+    import torch
+    from oracle import sndvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.Config(num_nodes=args.nodes, model_type=args.model, sampling_num=args.sampling)
+    Bs = args.cpu_sample
+    P = O.init_params(cfg, 7, torch.float32)
+    inp = O.synthetic_inputs(cfg, Bs, 1234, torch.float32)
+    noise = O.synthetic_noise(cfg, Bs, 4321, torch.float32)
+    adam = O.TFAdam(P, cfg.learning_rate)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, _, L, g = O.loss_and_grads(P, inp, noise, cfg, "factored")
+        adam.step(P, g)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times[warmup:])) if steps > 0 else float("nan")
+    return {"value": Bs / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{Bs} graphs x S={cfg.S} of the N={args.nodes} workload per step, factored PyTorch-CPU fp32 restatement "
+                      f"(oracle/sndvae_oracle.py), autograd backward + TF-Adam; TensorFlow unavailable",
+            "ms_per_step": t * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb = cpu_reference(args, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SND-VAE {args.model} model train step, N={args.nodes}, S={args.sampling}, batch {args.batch}/GPU "
+                               f"(reference arm: bounded sample of {args.cpu_sample} graphs per step)"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sndvae_b200 as sv
+    from importlib import import_module
+    data = import_module("snd-vae_b200.data")
+    params = import_module("snd-vae_b200.params")
+    C = import_module("ctypes")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, B, S = args.nodes, args.batch, (args.sampling if args.model != "base" else 1)
+
+    cfg = sv.make_config(N, B, args.model, sampling_num=S, use_tensor_cores=args.tc, chunk_graphs=args.chunk)
+    eng = sv.Engine(cfg, dev)
+    P = params.init_params(eng.table, seed=7)                   # identical on every rank
+    eng.set_params({k: torch.from_numpy(v) for k, v in P.items()})
+
+    pool_n = min(args.pool, B)
+    pool = data.synthetic_graphs(N, pool_n, S, seed=1234 + rank)
+    feeds_np = data.tile_pool(pool, B, pool_n, S)
+    g = torch.Generator().manual_seed(4321 + rank)
+    noise_np = {"eps_s": torch.randn(B, cfg.s_latent_size, generator=g).numpy(),
+                "eps_sg": torch.randn(B * S, cfg.sg_latent_size, generator=g).numpy(),
+                "eps_g": torch.randn(B, cfg.g_latent_size, generator=g).numpy()}
+    used = ("features", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth")
+    feeds_dev = {k: torch.from_numpy(np.ascontiguousarray(feeds_np[k])).to(dev) for k in used}
+    noise_dev = {k: torch.from_numpy(v).to(dev) for k, v in noise_np.items()}
+    inp, nz, keep = eng._pack(feeds_dev, noise_dev)
+    out, res = eng._outs(("generated_adj",))
+    losses = np.zeros(8, dtype=np.float32)
+    gview = eng.grads_tensor() if world > 1 else None
+
+    def step():
+        if world == 1:
+            eng.train_step_packed(inp, nz, out, losses)
+        else:
+            eng.grads_packed(inp, nz, out, losses, world * B)    # local sums / global batch
+            dist.all_reduce(gview)                               # NCCL sum over NVLink
+            eng.apply_adam()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    eng.gemm_timing(reset=True)
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as cs:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = eng.launch_count() - l0
+    gemm_ms, gemm_n, gemm_flops = eng.gemm_timing(reset=True)
+    ms_step = ms / args.steps
+    value = world * B / (ms_step * 1e-3)
+    final_loss = float(losses[0])
+
+    # ---- end to end through the host-buffer entry point (rank-local, then max over ranks) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+            hf = {k: pin(feeds_np[k]) for k in used}
+            hn = {k: pin(v) for k, v in noise_np.items()}
+            gen = torch.empty((B, N, N), dtype=torch.int64).pin_memory().numpy()
+            hl = np.zeros(8, dtype=np.float32)
+            del feeds_dev, keep
+            torch.cuda.empty_cache()
+            eng.train_step_host(hf, hn, gen, hl)                # warm (allocates the staging buffers)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                eng.train_step_host(hf, hn, gen, hl)
+                if world > 1:
+                    pass
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / args.e2e_steps
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            h2d = sum(v.nbytes for v in hf.values()) + sum(v.nbytes for v in hn.values())
+            e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(gen.nbytes + 32),
+                   "note": "sndvae_train_step_host: pinned host feeds -> device, step, losses + int64 generated_adj -> host"
+                           + ("; per-rank local step without all-reduce" if world > 1 else "")}
+        except Exception as ex:            # e.g. not enough pinnable host memory on the box
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    roofline = {
+        "bound": "tensor", "kernel": "toep_gemm_k<240> (fwd, dgrad) + wgrad_gemm_k: e2e layer-1 block-Toeplitz GEMMs",
+        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+        "traffic": None, "peak_source": peak_src,
+        "executed_mma_tflops": (3.0 * achieved * (56 / 50)) if achieved else None,
+        "note": "achieved = algorithmic FLOPs (F1 = 2*2*N*V(N)*50*20 per graph per GEMM, SURVEY 8d) / CUDA-event time of the GEMM launches; "
+                "the 3-pass split-bf16 product executes >= 3x those FLOPs on the tensor pipe",
+        "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+        "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+    }
+    cpu = None
+    if not args.no_cpu_baseline:
+        cb = cpu_reference(args, 2, 1)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": f"synthetic (random-geometric spatial graphs + spanning-tree samples; {pool_n} distinct graphs per rank tiled to the batch; "
+                f"inputs {sum(feeds_np[k].nbytes for k in used) / 1e9:.1f} GB per rank >> L2)",
+        "config": {"workload": f"SND-VAE {args.model} model (model.py) train step fwd+bwd+Adam, N={N}, S={S}, {B} graphs/step/GPU, "
+                               f"global batch {world * B}", "num_nodes": N, "batch_per_gpu": B, "sampling_num": S,
+                   "parallelism": f"dp{world}", "chunk_graphs": int(eng.cfg.chunk_graphs), "tensor_cores": bool(args.tc),
+                   "l2": "inputs larger than L2 (no flush needed)"},
+        "clocks": cs.summary(), "gpu_launches": int(launches), "final_loss": final_loss,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ struct PT {   // parameter offsets (floats) into the flat arenas; -1 = absent
 };
 
 struct EvPair { cudaEvent_t a, b; double flops; };
+struct StageTimer { std::vector<cudaEvent_t> ev; std::vector<const char*> name; size_t used; int on; };
 
 struct sndvae_handle {
   sndvae_config cfg;
@@ -71,7 +72,31 @@ struct sndvae_handle {
   long long* hf_gen_adj;
   // gemm timing
   std::vector<EvPair> ev; size_t ev_used;
+  StageTimer stt;
 };
+// optional per-stage timing (env SNDVAE_STAGE_TIMING=1): mark(h, "name") closes the previous stage
+static void mark(sndvae_handle* h, const char* name) {
+  StageTimer& t = h->stt;
+  if (!t.on) return;
+  if (t.used == t.ev.size()) { cudaEvent_t e; cudaEventCreate(&e); t.ev.push_back(e); t.name.push_back(name); }
+  t.name[t.used] = name;
+  cudaEventRecord(t.ev[t.used++], h->stream);
+}
+static void report_stages(sndvae_handle* h) {
+  StageTimer& t = h->stt;
+  if (!t.on || t.used < 2) { t.used = 0; return; }
+  std::vector<std::pair<std::string, double>> acc;
+  for (size_t i = 0; i + 1 < t.used; ++i) {
+    float ms = 0; cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]);
+    bool found = false;
+    for (auto& a : acc) if (a.first == t.name[i]) { a.second += ms; found = true; break; }
+    if (!found) acc.push_back({t.name[i], ms});
+  }
+  fprintf(stderr, "[sndvae stages]");
+  for (auto& a : acc) fprintf(stderr, " %s=%.2fms", a.first.c_str(), a.second);
+  fprintf(stderr, "\n");
+  t.used = 0;
+}
 
 static int fail(sndvae_t* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -419,6 +444,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   const long long B = h->B, Rn = h->Rn;
   const int dact = h->dis ? ACT_NONE : ACT_LRELU;      // model_joint.py:116,139 lrelu after BN
   int r;
+  mark(h, "dec_nodes");
   // latent -> node features; the S-mean (model.py:180) is hoisted before the linear map
   LEW(smean_k, B * c.sg_latent_size, h->z_sg, h->zbar, B, S, c.sg_latent_size);
   if ((r = lin_fwd(h, h->zbar, p.d_sg_lin1, h->n_sg, B, c.sg_latent_size, N * H))) return r;
@@ -457,6 +483,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   if (out && out->generated_spatial) CK(cudaMemcpyAsync(out->generated_spatial, h->phat, sizeof(float) * Rn * D, cudaMemcpyDeviceToDevice, h->stream));
 
   // ---- edge decoder (model.py:196-208) -------------------------------------------------
+  mark(h, "l0_vec");
   const int Ctot = 2 * Chv;
   const float* w0 = h->P + p.e_w[0];
   bn_fwd(h, h->v, Chv, p.e_bng[0], p.e_bnb[0], h->a, Chv, Rn, Chv, ACT_RELU, 0);
@@ -476,13 +503,16 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   for (long long b0 = 0; b0 < B; b0 += h->Bc) {
     const int bc = (int)(B - b0 < h->Bc ? B - b0 : h->Bc);
     const long long rows = (long long)bc * N, cells = rows * N;
+    mark(h, "y_producer");
     YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = TC_CP; Y.bf16 = tc;
     LAUNCH(y_producer_k, (unsigned)rows, 256, sizeof(float) * (Chv + C1), h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc,
            h->Rc + b0 * N * C1, h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, Chv, C1);
+    mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
     if (tc) { if ((r = tc_fwd(h->tc, h->Yhi, h->Ylo, h->O12, 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_fwd: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_fwd_k, 2 * cells * C2, h->Yf, h->P + p.e_w[1], h->O12, 2 * rows, N, C1, C2);
     ev_end(h);
+    mark(h, "epilogue");
     EpiParams ep; memset(&ep, 0, sizeof ep);
     ep.O12 = h->O12; ep.b1 = h->P + p.e_b[1];
     ep.gd = h->dis ? h->P + p.decadj_g : nullptr; ep.bd = h->dis ? h->P + p.decadj_b : nullptr;
@@ -498,21 +528,25 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     LAUNCH(edge_epilogue_k, cdiv(cells, 128 * EPI_EPT), 128, 0, ep, bc, N);
     if (!backward) continue;
     // backward of e2e layer 1: dgrad + wgrad
+    mark(h, "gemm_dgrad");
     ev_begin(h, f1 * bc);
     if (tc) { if ((r = tc_dgrad(h->tc, h->dOhi, h->dOlo, h->dY12, 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_dgrad: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_dgrad_k, 2 * cells * C1, h->dOf, h->P + p.e_w[1], h->dY12, 2 * rows, N, C1, C2);
     ev_end(h);
+    mark(h, "gemm_wgrad");
     ev_begin(h, f1 * bc);
     if (tc) { if ((r = tc_wgrad(h->tc, h->Yhi, h->Ylo, h->dOhi, h->dOlo, h->G + p.e_w[1], 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_wgrad: %s", tc_last_error()); h->launches++; }
     else { dim3 g(cdiv((long long)N * C1 * C2, 256), cdiv(2 * rows, WGRAD_RG));
            LAUNCH(e2e_l1_simt_wgrad_k, g, 256, 0, h->Yf, h->dOf, h->G + p.e_w[1], 2 * rows, N, C1, C2); }
     ev_end(h);
+    mark(h, "combine");
     // back through relu/BN_e1 to dE1 (both layouts), then the layer-0 contractions
     LAUNCH(l0_combine_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
            h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], bc, N, C1);
     const float* dE1 = h->dY12; const float* dE1t = h->dY12 + cells * C1;
     LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1, h->dSa + b0 * N * C1, N, C1);
     LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1t, h->dRc + b0 * N * C1, N, C1);
+    mark(h, "l0_gemms");
     // da[i,:] = sum_{(j,o)} dE1[i,(j,o)] WSa[(j,o),:];  dc[j,:] = sum_{(i,o)} dE1t[j,(i,o)] WSc[(i,o),:]
     CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1, N * C1, h->WSa, Chv, 0.f, h->da + b0 * N * Chv, Chv));
     CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1t, N * C1, h->WSc, Chv, 0.f, h->dc + b0 * N * Chv, Chv));
@@ -532,6 +566,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   const int dact = h->dis ? ACT_NONE : ACT_LRELU;
   const float* w0 = h->P + p.e_w[0];
   int r;
+  mark(h, "l0_vec_bwd");
   // ---- e2e layer 0 vector terms and weight sums ----
   LEW(toep_vec_bwd_in_k, Rn * Chv, h->dRc, w0, h->dc, B, N, Ctot, Chv, Chv, C1);
   LEW(toep_vec_bwd_in_k, Rn * Chv, h->dSa, w0, h->da, B, N, Ctot, 0, Chv, C1);
@@ -540,6 +575,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     LAUNCH(toep_vec_bwd_w_k, g, 256, 0, h->a, h->dSa, h->G + p.e_w[0], B, N, Ctot, 0, Chv, C1); }
   LEW(e2e_l0_prep_bwd_k, (long long)N * Chv * C1, h->dWSa, h->G + p.e_w[0], N, Ctot, 0, Chv, C1);
   LEW(e2e_l0_prep_bwd_k, (long long)N * Chv * C1, h->dWSc, h->G + p.e_w[0], N, Ctot, Chv, Chv, C1);
+  mark(h, "dec_nodes_bwd");
   // a = relu(BN_e0[:Ch](v)), c = relu(BN_e0[Ch:](v))
   bn_bwd(h, h->da, Chv, h->v, Chv, p.e_bng[0], p.e_bnb[0], h->dv, Chv, Rn, Chv, ACT_RELU, 0);
   bn_bwd(h, h->dc, Chv, h->v, Chv, p.e_bng[0] + Chv, p.e_bnb[0] + Chv, h->gA, Chv, Rn, Chv, ACT_RELU, 0);
@@ -579,6 +615,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     LEW(copy_cols_k, Rn * H, h->dsp0, Chv, 0, h->dn_sg, H, 0, Rn, H, 1);
   }
   if ((r = lin_bwd(h, h->zbar, p.d_sg_lin1, h->dn_sg, h->dzbar, B, c.sg_latent_size, N * H))) return r;
+  mark(h, "enc_bwd_small");
   // ---- reparameterisation + KL, heads, encoders ----
   const float beta = c.beta;
   if (h->dis) {
@@ -616,6 +653,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     bn_bwd(h, h->gA, ec[0], h->h1p, ec[0], p.gs_bng[0], p.gs_bnb[0], h->gA, ec[0], Rn, ec[0], ACT_RELU, 0);
     conv_bwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->gA, nullptr, Rn, D, ec[0]);
   }
+  mark(h, "enc_bwd_sgc");
   // joint head (z_sg rows are graph-major: row b*S+s; the S-mean gives dz = dzbar[b]/S)
   {
     int L = c.sg_latent_size, Hh = c.sg_hidden_size;
@@ -628,7 +666,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     if ((r = lin_bwd(h, h->fsg, p.sg_lin[0], h->dh, h->dfsg, BS, N * h12, Hh))) return r;
     for (long long s0 = 0; s0 < BS; s0 += h->SC) {
       long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
-      if (BS > h->SC || true) { if ((r = sgc_chunk_fwd(h, in, s0, ns))) return r; }     // recompute the chunk's activations
+      if ((r = sgc_chunk_fwd(h, in, s0, ns))) return r;     // recompute the chunk's activations (cheap; bounds scratch to one chunk)
       const float* x0 = in->features + s0 * N * F;
       // fsg = BN_encsg(x2); x2 = lrelu(BN_sg1(y1))
       bn_bwd(h, h->dfsg + s0 * N * h12, h12, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h12, ns * N, h12, ACT_NONE, 0);
@@ -701,13 +739,17 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
   const float gB = (float)(global_batch > 0 ? global_batch : h->B);
   CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * 8, h->stream));
   if (backward) CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
+  mark(h, "encoder");
   if ((r = encoder_fwd(h, in))) return r;
   if ((r = reparam_fwd(h, nz))) return r;
   if ((r = copy_latents(h, out))) return r;
   if ((r = decoder_fwd(h, in, out, backward, gB))) return r;
   if (backward && (r = backward_rest(h, in, nz, gB))) return r;
+  mark(h, "end");
   CK(cudaGetLastError());
-  return fetch_losses(h, losses_host);
+  r = fetch_losses(h, losses_host);
+  report_stages(h);
+  return r;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -738,6 +780,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
   h->hf_features = nullptr;
+  h->stt.used = 0; h->stt.on = getenv("SNDVAE_STAGE_TIMING") != nullptr;
   sndvae_config& c = h->cfg;
   if (c.num_nodes < 2 || c.batch_size < 1 || c.num_feature < 1 || c.spatial_dim < 1 || c.node_h_size < 1)
     return fail(h, SNDVAE_E_ARG, "bad config: num_nodes=%d batch_size=%d", c.num_nodes, c.batch_size);
@@ -754,8 +797,8 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (c.use_tensor_cores && (h->C1 != TC_C1 || h->C2 != TC_C2))
     return fail(h, SNDVAE_E_ARG, "tensor-core e2e path requires e_d_hidden = (%d, %d)", TC_C1, TC_C2);
   if (c.chunk_graphs <= 0) {
-    // bound the N^2 staging buffers to ~24 GB: ~320 B per (i,j) cell
-    long long per_graph = (long long)h->N * h->N * 340;
+    // bound the N^2 staging buffers to ~24 GB: E1 200 + O12 160 + dY12 400 + Y planes 448 + dO planes 192 B per (i,j) cell
+    long long per_graph = (long long)h->N * h->N * 1400;
     long long bc = (24LL << 30) / per_graph; if (bc < 1) bc = 1; if (bc > h->B) bc = h->B; if (bc > 512) bc = 512;
     c.chunk_graphs = (int)bc;
   }

@@ -1,0 +1,32 @@
+"""`OptimizerVAE` with the reference's constructor signature (optimizer.py:124) and
+attribute names (optimizer.py:144-203).  The ELBO, its backward pass and the TF1 Adam
+update run inside the engine; this object only exposes the fetch handles.  `pos_weight`,
+`norm`, `labels_rel` and `global_iter` are accepted and unused, as in the reference's
+'disentangled' / base branches."""
+from .flags import FLAGS
+from .session import Fetch
+
+
+class OptimizerVAE(object):
+    def __init__(self, preds_edge, preds_node, preds_spatial, labels_edge, labels_node, labels_spatial, labels_rel, model,
+                 num_nodes, pos_weight, norm, beta, global_iter):
+        if FLAGS.model_type not in ("disentangled", "base"):
+            raise ValueError(f"model_type '{FLAGS.model_type}' is outside the hot path (SURVEY section 2 row 8)")
+        self.model = model
+        model.optimizer = self
+        model.engine.cfg.beta = float(beta)
+        if float(beta) != 1.0:
+            raise ValueError("beta is fixed at engine creation; construct the model with FLAGS beta=1 (main.py:515)")
+        for name in ("opt_op", "cost", "adj_cost", "node_cost", "spatial_cost", "kl_sg", "kl_s", "kl_g"):
+            setattr(self, name, Fetch(self, name))
+        if model.engine.dis:
+            self.overall_loss = [self.cost, self.spatial_cost, self.adj_cost, self.node_cost, self.kl_g, self.kl_s, self.kl_sg]
+        else:
+            self.overall_loss = [self.cost, self.spatial_cost, self.adj_cost, self.node_cost, self.kl_sg]
+
+    @property
+    def grads_vars(self):
+        """optimizer.compute_gradients(cost) (optimizer.py:198): (gradient, variable-name) pairs of
+        the last backward pass, as views of the flat gradient arena."""
+        g = self.model.engine.get_grads()
+        return [(g[name], name) for name, _, _ in self.model.engine.table]

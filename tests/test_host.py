@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic: synthetic data generator, reference initialisers,
+flag defaults, feed-dict helpers, and the data-parallel gradient protocol over gloo
+(world_size 2) with the oracle standing in for the device step."""
+import os
+import socket
+from importlib import import_module
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sndvae_oracle as O
+
+data = import_module("snd-vae_b200.data")
+params = import_module("snd-vae_b200.params")
+flags = import_module("snd-vae_b200.flags")
+prep = import_module("snd-vae_b200.preprocessing")
+session = import_module("snd-vae_b200.session")
+
+
+def test_synthetic_graphs_properties():
+    N, B, S = 30, 5, 4
+    d = data.synthetic_graphs(N, B, S, seed=3)
+    A, As = d["adj_truth"], d["adj"].reshape(B, S, N, N)
+    assert A.shape == (B, N, N) and d["rel"].shape == (B * S, N, N, 1) and d["features"].shape == (B * S, N, 1)
+    assert np.array_equal(A, A.transpose(0, 2, 1)) and (A[:, np.arange(N), np.arange(N)] == 0).all()    # input_data.py:65-67
+    for b in range(B):
+        for s in range(S):
+            T = As[b, s]
+            assert np.array_equal(T, T.T) and (T <= A[b]).all()               # spanning forest of the truth graph
+            assert T.sum() <= 2 * (N - 1)
+    # aligned tiling: row b*S+s carries graph b's features / rel (SURVEY quirk Q6 fixed)
+    assert np.array_equal(d["features"].reshape(B, S, N, 1)[:, 0], d["feature_truth"])
+    assert np.array_equal(d["rel"].reshape(B, S, N, N)[:, 2], d["rel_truth"][..., 0])
+    t = data.tile_pool(d, 12, B, S)
+    assert t["adj"].shape[0] == 12 * S and t["adj_truth"].shape[0] == 12
+    assert np.array_equal(t["adj_truth"][5], d["adj_truth"][0])
+
+
+def test_reference_initialisers():
+    cfg = O.Config(num_nodes=25)
+    table = []
+    off = 0
+    for name, shape, _ in O.param_table(cfg):
+        table.append((name, off, tuple(shape))); off += int(np.prod(shape))
+    P = params.init_params(table, seed=7)
+    assert set(P) == {n for n, _, _ in table}
+    assert (P["encoder/g_bn_g0/gamma"] == 1).all() and (P["encoder/g_bn_g0/beta"] == 0).all()
+    assert (P["decoder/e1_deconv/biases1"] == 0).all()
+    w = P["decoder/e1_deconv/w1"]
+    assert w.shape == (1, 25, 50, 20) and np.abs(w).max() <= 0.04 + 1e-9 and 0.015 < w.std() < 0.02   # truncated at 2 sigma
+    m = P["encoder/g_sg1_lin/Matrix"]
+    assert abs(m.std() - 0.02) < 1e-3 and np.abs(m).max() > 0.05
+    k = P["decoder/n0_deconv/kernel"]
+    lim = np.sqrt(6.0 / (5 * 40 + 5 * 50))
+    assert np.abs(k).max() <= lim and np.abs(k).max() > 0.9 * lim
+
+
+def test_flags_defaults_and_overrides():
+    F = flags.FLAGS
+    F.reset()
+    assert F.sg_hidden_size == 200 and F.learning_rate == 0.001 and F.batch_size == 2 and F.sampling_num == 10   # main.py:42-103
+    F.apply_dataset("synthetic2")
+    assert (F.sg_hidden_size, F.sg_latent_size, F.node_h_size, F.batch_size) == (100, 100, 20, 10)              # main.py:181-217
+    assert F.learning_rate == 0.0008 and F.num_edge_feature == 2
+    F.apply_dataset("synthetic1")
+    assert (F.sg_hidden_size, F.node_h_size, F.learning_rate) == (500, 50, 0.001)
+    with pytest.raises(ValueError):
+        F.apply_dataset("protein")
+    F.reset()
+
+
+def test_feed_dict_helpers():
+    ph = session.make_placeholders(2, 3, 5, 1, 2)
+    assert ph["adj"].shape == (6, 5, 5) and ph["rel_truth"].shape == (2, 5, 5, 1)            # main.py:253-264
+    arrs = [np.zeros(1) for _ in range(8)]
+    fd = prep.construct_feed_dict_train(*arrs, ph)
+    assert set(k.name for k in fd) == {"features", "adj", "spatial", "rel", "adj_truth", "feature_truth", "spatial_truth",
+                                       "rel_truth"}
+    fd2 = prep.construct_feed_dict(*arrs[:4], ph)
+    assert len(fd2) == 4
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    cfg = O.Config(num_nodes=6, sampling_num=2)
+    P = O.init_params(cfg, 7, torch.float64)
+    Bg = 4; Bl = Bg // world; S = cfg.S
+    inp = O.synthetic_inputs(cfg, Bg, 5, torch.float64)
+    noise = O.synthetic_noise(cfg, Bg, 9, torch.float64)
+    sl = slice(rank * Bl, (rank + 1) * Bl); sls = slice(rank * Bl * S, (rank + 1) * Bl * S)
+    si = {k: (v[sls] if k in ("adj", "features", "spatial", "rel") else v[sl]) for k, v in inp.items()}
+    sn = {"eps_s": noise["eps_s"][sl], "eps_g": noise["eps_g"][sl], "eps_sg": noise["eps_sg"][sls]}
+    # the device step produces LOCAL sums scaled by 1/global_batch (sndvae_grads' contract):
+    # a shard-mean gradient times Bl/Bg
+    g = O.loss_and_grads(P, si, sn, cfg)[4]
+    names = [n for n, _, _ in O.param_table(cfg)]
+    arena = torch.cat([g[n].reshape(-1) for n in names]) * (Bl / Bg)
+    dist.all_reduce(arena)                                   # the one collective of the path
+    if rank == 0:
+        full = O.loss_and_grads(P, inp, noise, cfg)[4]
+        ref = torch.cat([full[n].reshape(-1) for n in names])
+        q.put(float((arena - ref).abs().max()))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_allreduce_gloo_world2():
+    """Shard the graphs over 2 ranks, all-reduce the flat gradient arena (gloo on CPU): the
+    result equals the full-batch gradient (exact: no cross-graph op besides the loss means)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) < 1e-13

@@ -1,0 +1,169 @@
+"""CPU tests that pin the oracle: literal == factored restatement,
+autograd == finite differences, invariants, TF-Adam formula, golden vectors.
+The oracle is a restatement of the TensorFlow reference, not TensorFlow itself
+(parity unpinned at that boundary)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sndvae_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _setup(N, B, S, model, seed=1, perturb=0.05, dtype=torch.float64):
+    cfg = O.Config(num_nodes=N, model_type=model, sampling_num=S)
+    P = O.init_params(cfg, 7, dtype)
+    g = torch.Generator().manual_seed(seed)
+    for k in P:
+        P[k] = P[k] + perturb * torch.randn(P[k].shape, generator=g, dtype=dtype)
+    return cfg, P, O.synthetic_inputs(cfg, B, 5, dtype), O.synthetic_noise(cfg, B, 9, dtype)
+
+
+@pytest.mark.parametrize("model", ["disentangled", "base"])
+@pytest.mark.parametrize("N", [6, 7])
+def test_literal_equals_factored(model, N):
+    cfg, P, inp, noise = _setup(N, 2, 3, model)
+    e1, z1, d1, L1, g1 = O.loss_and_grads(P, inp, noise, cfg, "literal")
+    e2, z2, d2, L2, g2 = O.loss_and_grads(P, inp, noise, cfg, "factored")
+    for k in e1:
+        assert (e1[k] - e2[k]).abs().max() < 1e-12
+    assert (d1["generated_adj_prob"] - d2["generated_adj_prob"]).abs().max() < 1e-12
+    assert torch.equal(d1["generated_adj"], d2["generated_adj"])
+    for k in g1:
+        assert (g1[k] - g2[k]).abs().max() < 1e-12, k
+
+
+def test_sgc_factorisation_general_adjacency():
+    """Appendix C.1 holds for arbitrary real A and arbitrary-sign rel, not only 0/1 trees."""
+    torch.manual_seed(0)
+    Bn, N, C = 3, 6, 4
+    P = {"s/Matrix1": torch.randn(3 * C + 3, 5, dtype=torch.float64), "s/bias1": torch.randn(5, dtype=torch.float64),
+         "s/Matrix2": torch.randn(2 * C + 5 + 1, 7, dtype=torch.float64), "s/bias2": torch.randn(7, dtype=torch.float64),
+         "s/Matrix3": torch.randn(C + 7, 3, dtype=torch.float64), "s/bias3": torch.randn(3, dtype=torch.float64)}
+    A = torch.randn(Bn, N, N, dtype=torch.float64)
+    x = torch.randn(Bn, N, C, dtype=torch.float64)
+    rel = torch.randn(Bn, N, N, 1, dtype=torch.float64)
+    assert (O.sgc_literal(A, x, rel, P, "s") - O.sgc_factored(A, x, rel, P, "s")).abs().max() < 1e-11
+
+
+def test_e2e_forms_agree():
+    torch.manual_seed(1)
+    for N in (5, 8):
+        x = torch.randn(2, N, N, 6, dtype=torch.float64)
+        w = torch.randn(1, N, 6, 4, dtype=torch.float64)
+        b = torch.randn(4, dtype=torch.float64)
+        assert (O.e2e_literal(x, w, b) - O.e2e_toeplitz(x, w, b)).abs().max() < 1e-12
+        # density of the block-Toeplitz matrix = V(N) / N^2
+        p = (N - 1) // 2; q = N - 1 - p
+        V = N * N - p * (p + 1) // 2 - q * (q + 1) // 2
+        T = O.toeplitz_matrix(torch.ones(1, N, 1, 1, dtype=torch.float64))
+        assert int(T.sum().item()) == V
+
+
+def test_autograd_matches_finite_differences():
+    cfg, P, inp, noise = _setup(6, 2, 2, "disentangled")
+    _, _, _, L, g = O.loss_and_grads(P, inp, noise, cfg, "factored")
+    rng = np.random.default_rng(0)
+    eps = 1e-6
+    for name in ["encoder/g_sg1_conv/Matrix1", "encoder/g_g1_conv/w", "decoder/e1_deconv/w1", "decoder/e0_deconv/w1",
+                 "decoder/d_bn_e1/gamma", "encoder/g_s2_conv/kernel", "decoder/decoder_adj/beta", "decoder/d_sg_lin1/Matrix"]:
+        flat = P[name].reshape(-1)
+        for idx in rng.choice(flat.numel(), size=3, replace=False):
+            old = flat[idx].item()
+            flat[idx] = old + eps
+            lp = O.forward(P, inp, noise, cfg)[3]["cost"].item()
+            flat[idx] = old - eps
+            lm = O.forward(P, inp, noise, cfg)[3]["cost"].item()
+            flat[idx] = old
+            fd = (lp - lm) / (2 * eps)
+            an = g[name].reshape(-1)[idx].item()
+            assert abs(fd - an) < 1e-7 + 1e-5 * abs(an), (name, idx, fd, an)
+
+
+def test_shard_sum_equals_full_batch_gradient():
+    """Every graph's forward is independent of the rest of the batch (SURVEY finding 3), so the
+    data-parallel sum of shard gradients scaled by 1/world equals the full-batch gradient."""
+    cfg, P, inp, noise = _setup(6, 4, 2, "disentangled")
+    _, _, _, L, g = O.loss_and_grads(P, inp, noise, cfg)
+    S = cfg.S
+    acc = {k: torch.zeros_like(v) for k, v in P.items()}
+    for r in range(2):
+        sl = slice(2 * r, 2 * r + 2); sls = slice(2 * r * S, (2 * r + 2) * S)
+        si = {k: (v[sls] if k in ("adj", "features", "spatial", "rel") else v[sl]) for k, v in inp.items()}
+        sn = {"eps_s": noise["eps_s"][sl], "eps_g": noise["eps_g"][sl], "eps_sg": noise["eps_sg"][sls]}
+        gs = O.loss_and_grads(P, si, sn, cfg)[4]
+        for k in acc:
+            acc[k] += gs[k] / 2
+    for k in g:
+        assert (acc[k] - g[k]).abs().max() < 1e-13, k
+
+
+def test_batch_permutation_and_diagonal():
+    cfg, P, inp, noise = _setup(7, 3, 2, "disentangled")
+    enc, z, dec, L = O.forward(P, inp, noise, cfg)
+    perm = torch.tensor([2, 0, 1]); S = cfg.S
+    perms = (perm[:, None] * S + torch.arange(S)[None]).reshape(-1)
+    pi = {k: (v[perms] if k in ("adj", "features", "spatial", "rel") else v[perm]) for k, v in inp.items()}
+    pn = {"eps_s": noise["eps_s"][perm], "eps_g": noise["eps_g"][perm], "eps_sg": noise["eps_sg"][perms]}
+    enc2, z2, dec2, L2 = O.forward(P, pi, pn, cfg)
+    assert (dec2["generated_adj_prob"] - dec["generated_adj_prob"][perm]).abs().max() < 1e-12
+    assert abs(L2["cost"].item() - L["cost"].item()) < 1e-12
+    N = cfg.N
+    d = torch.arange(N)
+    assert (dec["generated_adj"][:, d, d] == 0).all()                      # diag logits are (1, 0)
+    assert (dec["generated_adj_prob"][:, d, d, 0] == 1).all() and (dec["generated_adj_prob"][:, d, d, 1] == 0).all()
+
+
+def test_step0_anchors():
+    """with the reference initialisers adj_cost ~ (ln2 (N-1) + ln(1+1/e))/N etc."""
+    cfg = O.Config(num_nodes=25)
+    P = O.init_params(cfg, 7, torch.float64)
+    inp = O.synthetic_inputs(cfg, 4, 5, torch.float64)
+    noise = O.synthetic_noise(cfg, 4, 9, torch.float64)
+    L = O.forward(P, inp, noise, cfg)[3]
+    N = 25
+    assert abs(L["adj_cost"].item() - (math.log(2) * (N - 1) + math.log(1 + math.exp(-1))) / N) < 5e-3
+    assert abs(L["node_cost"].item() - 1 / 12) < 2e-2 and abs(L["spatial_cost"].item() - 1 / 12) < 2e-2
+    assert L["kl_sg"].item() < 1e-2
+
+
+def test_tf_adam_formula():
+    """TF1 ApplyAdam against a hand-rolled scalar recurrence; differs from torch Adam."""
+    P = {"w": torch.tensor([0.5, -1.0], dtype=torch.float64)}
+    opt = O.TFAdam(P, 0.01)
+    m = v = np.zeros(2); th = np.array([0.5, -1.0]); b1p, b2p = 0.9, 0.999
+    for t in range(1, 4):
+        g = np.array([0.1 * t, -1e-7])
+        opt.step(P, {"w": torch.tensor(g)})
+        alpha = 0.01 * math.sqrt(1 - b2p) / (1 - b1p)
+        m = m + (g - m) * 0.1; v = v + (g * g - v) * 0.001
+        th = th - m * alpha / (np.sqrt(v) + 1e-8)
+        b1p *= 0.9; b2p *= 0.999
+    assert np.allclose(P["w"].numpy(), th, rtol=1e-6, atol=0)
+
+
+def test_param_counts():
+    n = lambda c: sum(int(np.prod(s)) for _, s, _ in O.param_table(c))
+    assert n(O.Config(num_nodes=25)) == 611587
+    assert n(O.Config(num_nodes=256)) == 5268547
+    assert n(O.Config(num_nodes=256, model_type="base")) == 2619755
+
+
+@pytest.mark.parametrize("name", ["dis_n8", "base_n8", "dis_n25"])
+def test_golden_vectors(name):
+    """The committed fixtures (tests/golden/make_golden.py) are reproduced by the oracle."""
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    model = "base" if name.startswith("base") else "disentangled"
+    N, B, S = int(z["N"]), int(z["B"]), int(z["S"])
+    cfg, P, inp, noise = _setup(N, B, S, model)
+    enc, zz, dec, L, g = O.loss_and_grads(P, inp, noise, cfg)
+    assert np.allclose(np.array([x.item() for x in L["overall_loss"]]), z["overall_loss"], rtol=1e-10)
+    assert np.allclose(dec["generated_adj_prob"].detach().numpy(), z["generated_adj_prob"], rtol=0, atol=1e-10)
+    assert np.array_equal(dec["generated_adj"].numpy(), z["generated_adj"])
+    for k in g:
+        d = z["gradsum/" + k]
+        assert np.allclose([g[k].sum().item(), g[k].abs().sum().item()], d, rtol=1e-7, atol=1e-12), k
