@@ -423,6 +423,19 @@ def mask_and_threshold(lg):
     return torch.argmax(torch.softmax(prob, dim=-1), dim=-1), prob
 
 
+def threshold_rule_fp32(lg):
+    """argmax(softmax([l0,l1])) evaluated with correctly rounded fp32 operations (numpy fp32
+    add / divide are correctly rounded; exp is taken in fp64 and rounded once), first index on
+    ties -- the arithmetic tf.nn.softmax + tf.argmax specify (model.py:208).  lg: [...,2] fp32."""
+    a = np.asarray(lg, dtype=np.float32)
+    p0, p1 = a[..., 0], a[..., 1]
+    mx = np.maximum(p0, p1)
+    e0 = np.exp((p0 - mx).astype(np.float64)).astype(np.float32)
+    e1 = np.exp((p1 - mx).astype(np.float64)).astype(np.float32)
+    s = e0 + e1
+    return (e1 / s > e0 / s).astype(np.int64)
+
+
 def decoder(P, z, cfg: Config, mode="factored"):
     """model.py:172-222 (disentangled) / model_joint.py:94-182 (base)."""
     N, H, S = cfg.N, cfg.node_h_size, cfg.S

@@ -16,8 +16,8 @@
 // contiguous slice  Wp[ch][x + jr*CS : +64]  (jr = N-1-j, CS = padded channel stride), i.e. a
 // 3-D tensor map (x, jr, ch) whose jr-stride (CS elements) is smaller than the x extent.
 //
-// Kernels: one CTA (192 threads) per 128 x BN output tile; warp 0 = TMA producer, warp 1 =
-// TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (tcgen05.ld).
+// Kernels: one CTA (320 threads) per 128 x BN output tile; warp 0 = TMA producer, warp 1 =
+// TMEM allocator + single-thread tcgen05.mma issuer, warps 2..9 = accumulate/epilogue (tcgen05.ld).
 // smem ring of 2 stages (K chunk 64, SWIZZLE_128B), mbarrier full/empty pipeline.
 #pragma once
 #include "common.cuh"
@@ -90,6 +90,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -124,19 +133,30 @@ struct ToepArgs {
   int n_jtiles;        // ceil(N / JT)
   int pad_rows;        // zero rows in front of the padded weights (N-1-p fwd, p dgrad)
   int KA;              // K extent = N*CS
+  int accumulate;      // out += result instead of out = result
 };
 
+// Two-level accumulation.  tcgen05.mma adds into its fp32 TMEM accumulator with truncation
+// (measured here: a systematic shrink of ~1.7e-8 per accumulate, -4.5e-5 over the 2688 accumulates
+// of one N=256 output), so the K loop is cut into groups of TC_GROUP chunks: each group accumulates
+// into one of two TMEM slots, and the epilogue warps drain the finished slot into round-to-nearest
+// fp32 registers while the tensor pipe fills the other slot.
+#define TC_GROUP 8
+#define TC_EPI_WARPS 8
+#define TC_THREADS (64 + 32 * TC_EPI_WARPS)
 template <int BN>
-__global__ void __launch_bounds__(192, 1) toep_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                                                      const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                                                      ToepArgs P) {
+__global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                                                             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                                                             ToepArgs P) {
   constexpr int A_BYTES = TC_BM * TC_KC * 2;       // 16 KB
   constexpr int B_BYTES = BN * TC_KC * 2;          // 30 KB at BN = 240
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  constexpr uint32_t TMEM_COLS = 512;              // two accumulator slots of 256 columns
+  constexpr int HC = BN / 2;                       // columns per epilogue warp (two warps per lane quarter)
+  static_assert(BN <= 256 && HC % 8 == 0, "tile shape");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], done_bar;
+  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,10 +173,11 @@ __global__ void __launch_bounds__(192, 1) toep_gemm_k(const __grid_constant__ CU
   const int kc_lo = (int)(xlo / TC_KC);
   const int kc_hi = (int)((xhi + TC_KC - 1) / TC_KC);
   const int nk = kc_hi > kc_lo ? kc_hi - kc_lo : 0;
+  const int ngroups = (nk + TC_GROUP - 1) / TC_GROUP;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&done_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -183,10 +204,13 @@ __global__ void __launch_bounds__(192, 1) toep_gemm_k(const __grid_constant__ CU
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(TC_BM, BN, 0, 0);
       for (int it = 0; it < nk; ++it) {
+        const int g = it / TC_GROUP, gi = it - g * TC_GROUP, slot = g & 1;
+        if (gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }   // slot drained by the epilogue
         const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t td = tmem_d + slot * 256;
 #pragma unroll
         for (int k = 0; k < TC_KC / 16; ++k) {
           // K-major SWIZZLE_128B: 8-row groups 1024 B apart; +32 B per 16-element K step
@@ -194,35 +218,47 @@ __global__ void __launch_bounds__(192, 1) toep_gemm_k(const __grid_constant__ CU
           const uint64_t al = umma_desc_sw128(sa + A_BYTES + k * 32, 16, 1024);
           const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES + k * 32, 16, 1024);
           const uint64_t bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES + k * 32, 16, 1024);
-          umma_bf16(tmem_d, ah, bh, idesc, (it | k) ? 1u : 0u);
-          umma_bf16(tmem_d, ah, bl, idesc, 1u);
-          umma_bf16(tmem_d, al, bh, idesc, 1u);
+          umma_bf16(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
+          umma_bf16(td, ah, bl, idesc, 1u);
+          umma_bf16(td, al, bh, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);          // smem slot free once these MMAs retire
+        if (gi == TC_GROUP - 1 || it == nk - 1) umma_commit(&acc_full[slot]);   // group complete
       }
-      umma_commit(&done_bar);                // accumulator complete
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
-    if (nk > 0) { mbar_wait(&done_bar, 0); tc_fence_after(); }
-    const int q = warp & 3;
-    const long long row = (long long)m0 + q * 32 + lane;
-    float* orow = P.out + row * (long long)P.N * P.Cout;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      if (nk > 0) tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
-      else {
+    // epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32); two warps share a quarter, HC columns each
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float acc[HC];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = 0u;
+    for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+    for (int g = 0; g < ngroups; ++g) {
+      const int slot = g & 1;
+      mbar_wait(&acc_full[slot], (g >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_d + slot * 256 + ((uint32_t)(q * 32) << 16) + half * HC;
+#pragma unroll
+      for (int c0 = 0; c0 < HC; c0 += 8) {
+        uint32_t r[8];
+        tmem_ld8(ta + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(r[i]);
       }
-      if (row < P.rows) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+    }
+    const long long row = (long long)m0 + q * 32 + lane;
+    if (row < P.rows) {
+      float* orow = P.out + row * (long long)P.N * P.Cout;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = c0 + i;
-          const int chl = n / P.JT, jr = jr0 + n - chl * P.JT;
-          const int j = P.N - 1 - jr;
-          if (j >= 0) orow[(long long)j * P.Cout + ch0 + chl] = __uint_as_float(r[i]);
+      for (int i = 0; i < HC; ++i) {
+        const int n = half * HC + i;
+        const int chl = n / P.JT, jr = jr0 + n - chl * P.JT;
+        const int j = P.N - 1 - jr;
+        if (j >= 0) {
+          float* dst = orow + (long long)j * P.Cout + ch0 + chl;
+          *dst = P.accumulate ? *dst + acc[i] : acc[i];
         }
       }
     }
@@ -237,23 +273,27 @@ __global__ void __launch_bounds__(192, 1) toep_gemm_k(const __grid_constant__ CU
 // block diagonals:  dw1[t, c, q] += dT[(j',c),(j,q)],  t = j'-j+p  
 // ------------------------------------------------------------------------------------------
 struct WgradArgs {
-  float* dw1;          // [N, C1, C2] gradient slot (atomicAdd)
+  float* dw;           // [N, Ctot, Cout] gradient slot (atomicAdd); this product owns channels [coff, coff+Cin)
   long long rows;
   int N;
-  int n_ntiles;        // ceil(N*OP / 256)
+  int CSi, Cin;        // channel stride / count of the M-side planes
+  int CSo, Cout;       // channel stride / count of the N-side planes
+  int Ctot, coff;
+  int n_ntiles;        // ceil(N*CSo / 256)
   int ksplit;          // CTAs per output tile along K
 };
 #define TC_WN 256
-__global__ void __launch_bounds__(192, 1) wgrad_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                                                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                                                       WgradArgs P) {
+__global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                                                              const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                                                              WgradArgs P) {
   constexpr int A_BYTES = TC_KC * TC_BM * 2;       // [2 x (64 k-rows x 128 B)] = 16 KB
   constexpr int B_BYTES = TC_KC * TC_WN * 2;       // [4 x (64 k-rows x 128 B)] = 32 KB
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
   constexpr int BLK = TC_KC * 128;                 // one 64(mn) x 64(k) box = 8 KB
+  constexpr int HC = TC_WN / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], done_bar;
+  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / P.ksplit, ks = blockIdx.x % P.ksplit;
@@ -261,8 +301,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_k(const __grid_constant__ C
   const int m0 = mt * TC_BM, n0 = nt * TC_WN;
   const int p = (P.N - 1) / 2;
   // band test: does any (j', j) in this tile have 0 <= j'-j+p < N ?
-  const int jp_lo = m0 / TC_CP, jp_hi = min(P.N - 1, (m0 + TC_BM - 1) / TC_CP);
-  const int j_lo = n0 / TC_OP, j_hi = min(P.N - 1, (n0 + TC_WN - 1) / TC_OP);
+  const int jp_lo = m0 / P.CSi, jp_hi = min(P.N - 1, (m0 + TC_BM - 1) / P.CSi);
+  const int j_lo = n0 / P.CSo, j_hi = min(P.N - 1, (n0 + TC_WN - 1) / P.CSo);
   if (jp_lo > P.N - 1 || j_lo > P.N - 1) return;
   if (jp_hi - j_lo + p < 0 || jp_lo - j_hi + p > P.N - 1) return;
   const long long kchunks = (P.rows + TC_KC - 1) / TC_KC;
@@ -271,13 +311,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_k(const __grid_constant__ C
   long long kc_hi = kc_lo + per; if (kc_hi > kchunks) kc_hi = kchunks;
   const int nk = kc_hi > kc_lo ? (int)(kc_hi - kc_lo) : 0;
   if (nk == 0) return;
+  const int ngroups = (nk + TC_GROUP - 1) / TC_GROUP;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&done_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -307,10 +348,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_k(const __grid_constant__ C
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(TC_BM, TC_WN, 1, 1);
       for (int it = 0; it < nk; ++it) {
+        const int g = it / TC_GROUP, gi = it - g * TC_GROUP, slot = g & 1;
+        if (gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
         const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t td = tmem_d + slot * 256;
 #pragma unroll
         for (int k = 0; k < TC_KC / 16; ++k) {
           // MN-major SWIZZLE_128B: 64-element MN blocks BLK bytes apart (LBO), 8-row K groups
@@ -319,217 +363,252 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_k(const __grid_constant__ C
           const uint64_t al = umma_desc_sw128(sa + A_BYTES + k * 2048, BLK, 1024);
           const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES + k * 2048, BLK, 1024);
           const uint64_t bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES + k * 2048, BLK, 1024);
-          umma_bf16(tmem_d, ah, bh, idesc, (it | k) ? 1u : 0u);
-          umma_bf16(tmem_d, ah, bl, idesc, 1u);
-          umma_bf16(tmem_d, al, bh, idesc, 1u);
+          umma_bf16(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
+          umma_bf16(td, ah, bl, idesc, 1u);
+          umma_bf16(td, al, bh, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);
+        if (gi == TC_GROUP - 1 || it == nk - 1) umma_commit(&acc_full[slot]);
       }
-      umma_commit(&done_bar);
     }
   } else {
-    mbar_wait(&done_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
-    const int jp = m / TC_CP, c = m - jp * TC_CP;
-    const bool mok = jp < P.N && c < TC_C1;
-#pragma unroll 1
-    for (int c0 = 0; c0 < TC_WN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
-      if (mok) {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float acc[HC];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + c0 + i;
-          const int j = n / TC_OP, qq = n - j * TC_OP;
-          const int t = jp - j + p;
-          if (j < P.N && qq < TC_C2 && t >= 0 && t < P.N)
-            atomicAdd(P.dw1 + ((size_t)t * TC_C1 + c) * TC_C2 + qq, __uint_as_float(r[i]));
-        }
+    for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+    for (int g = 0; g < ngroups; ++g) {
+      const int slot = g & 1;
+      mbar_wait(&acc_full[slot], (g >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_d + slot * 256 + ((uint32_t)(q * 32) << 16) + half * HC;
+#pragma unroll
+      for (int c0 = 0; c0 < HC; c0 += 8) {
+        uint32_t r[8];
+        tmem_ld8(ta + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+    }
+    const int m = m0 + q * 32 + lane;
+    const int jp = m / P.CSi, c = m - jp * P.CSi;
+    if (jp < P.N && c < P.Cin) {
+#pragma unroll
+      for (int i = 0; i < HC; ++i) {
+        const int n = n0 + half * HC + i;
+        const int j = n / P.CSo, qq = n - j * P.CSo;
+        const int t = jp - j + p;
+        if (j < P.N && qq < P.Cout && t >= 0 && t < P.N)
+          atomicAdd(P.dw + ((size_t)t * P.Ctot + P.coff + c) * P.Cout + qq, acc[i]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 512); }
 }
 
 // ------------------------------------------------------------------------------------------
-// per-step weight staging: zero-padded, channel-major, bf16 hi/lo copies of w1 [N, C1, C2]
-//   Wf[q][rho*CP + c] = w1[rho - (N-1-p), c, q]      rho in [0, 2N-1)   (forward B operand)
-//   Wd[c][rho*OP + q] = w1[N-1+p - rho,  c, q]                           (dgrad  B operand)
+// per-step weight staging: zero-padded, channel-major, bf16 hi/lo copies of w[N, Ctot, Cout]
+// (channels [coff, coff+Cin) of the input side):
+//   Wf[q][rho*CSi + c] = w[rho - (N-1-p), coff + c, q]      rho in [0, 2N-1)   (forward B operand)
+//   Wd[c][rho*CSo + q] = w[N-1+p - rho,  coff + c, q]                           (dgrad  B operand)
 // ------------------------------------------------------------------------------------------
-__global__ void tc_stage_weights_k(const float* __restrict__ w1, __nv_bfloat16* __restrict__ Wfh, __nv_bfloat16* __restrict__ Wfl,
-                                   __nv_bfloat16* __restrict__ Wdh, __nv_bfloat16* __restrict__ Wdl, int N) {
+__global__ void tc_stage_weights_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ Wfh, __nv_bfloat16* __restrict__ Wfl,
+                                   __nv_bfloat16* __restrict__ Wdh, __nv_bfloat16* __restrict__ Wdl, int N, int Ctot, int coff,
+                                   int Cin, int Cout, int CSi, int CSo) {
   const int p = (N - 1) / 2;
-  const long long LF = (long long)(2 * N - 1) * TC_CP, LD = (long long)(2 * N - 1) * TC_OP;
-  const long long nf = (long long)TC_C2 * LF, nd = (long long)TC_C1 * LD;
+  const long long LF = (long long)(2 * N - 1) * CSi, LD = (long long)(2 * N - 1) * CSo;
+  const long long nf = (long long)Cout * LF, nd = (long long)Cin * LD;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < nf) {
-    int q = (int)(idx / LF); long long x = idx - q * LF; int rho = (int)(x / TC_CP), c = (int)(x - (long long)rho * TC_CP);
+    int q = (int)(idx / LF); long long x = idx - q * LF; int rho = (int)(x / CSi), c = (int)(x - (long long)rho * CSi);
     int t = rho - (N - 1 - p);
-    float v = (c < TC_C1 && t >= 0 && t < N) ? w1[((size_t)t * TC_C1 + c) * TC_C2 + q] : 0.f;
+    float v = (c < Cin && t >= 0 && t < N) ? w[((size_t)t * Ctot + coff + c) * Cout + q] : 0.f;
     __nv_bfloat16 hi = __float2bfloat16_rn(v);
     Wfh[idx] = hi; Wfl[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
   } else if (idx < nf + nd) {
     idx -= nf;
-    int c = (int)(idx / LD); long long x = idx - c * LD; int rho = (int)(x / TC_OP), q = (int)(x - (long long)rho * TC_OP);
+    int c = (int)(idx / LD); long long x = idx - c * LD; int rho = (int)(x / CSo), q = (int)(x - (long long)rho * CSo);
     int t = N - 1 + p - rho;
-    float v = (q < TC_C2 && t >= 0 && t < N) ? w1[((size_t)t * TC_C1 + c) * TC_C2 + q] : 0.f;
+    float v = (q < Cout && t >= 0 && t < N) ? w[((size_t)t * Ctot + coff + c) * Cout + q] : 0.f;
     __nv_bfloat16 hi = __float2bfloat16_rn(v);
     Wdh[idx] = hi; Wdl[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
 }
 
+// fp32 rows [rows, C] -> bf16 hi / lo planes [rows, CS] (pad channels stay zero from allocation)
+__global__ void tc_split_planes_k(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                  long long rows, int C, int CS) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * C) return;
+  long long r = idx / C; int c = (int)(idx - r * C);
+  float v = src[idx];
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[r * CS + c] = h; lo[r * CS + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
 // ------------------------------------------------------------------------------------------
-// host side
+// host side: one ToepPlan per weight block  w[N, Ctot, Cout] restricted to Cin input channels
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_tc_encode = nullptr;
 
-struct TcState {
+struct ToepPlan {
+  int ready, N, Cin, Cout, CSi, CSo;
+  int fCT, fJT, dCT, dJT;                  // tile shapes (channels x positions, product 240)
+  __nv_bfloat16 *Wfh, *Wfl, *Wdh, *Wdl;    // staged weights
+  CUtensorMap fB_h, fB_l, dB_h, dB_l;      // window views of the staged weights
+};
+struct TcState {                           // all tensor-core products of the edge decoder
   int ready;
-  int N;
-  long long max_rows;
-  __nv_bfloat16 *Wfh, *Wfl, *Wdh, *Wdl;
-  PFN_encodeTiled encode;
-  // tensor maps over the weights are fixed; maps over Y / dO planes are rebuilt when pointers change
-  const void *yh, *yl, *dh, *dl;
-  const void *wyh, *wdh; long long wrows;
-  CUtensorMap fA_h, fA_l, fB_h, fB_l;      // forward: A = Y planes (K-major), B = Wf window view
-  CUtensorMap dA_h, dA_l, dB_h, dB_l;      // dgrad:   A = dO planes,          B = Wd window view
-  CUtensorMap wA_h, wA_l, wB_h, wB_l;      // wgrad:   A = Y planes (MN-major boxes), B = dO planes
+  ToepPlan l1;                             // e2e layer 1:  50 -> 20
+  ToepPlan l0a, l0c;                       // e2e layer 0 vector terms: a-half / c-half of w0 (Ch -> 50)
+  __nv_bfloat16 *ah, *al, *ch, *cl;        // a / c planes      [B, N*CSi]
+  __nv_bfloat16 *dsh, *dsl, *drh, *drl;    // dSa / dRc planes  [B, N*CSo]
 };
 
-static int tc_encode(TcState& s, CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b,
-                     const cuuint32_t* box) {
+static int tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b, const cuuint32_t* box) {
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = s.encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_tc_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled failed: %d (rank %d)", (int)r, rank); return -1; }
   return 0;
 }
-
-static int tc_init(TcState& s, int N, long long max_rows, cudaStream_t st) {
-  memset(&s, 0, sizeof s);
-  s.N = N; s.max_rows = max_rows;
+static int tc_encode_rows(CUtensorMap* tm, const void* base, long long width, long long rows, int box0, int box1) {
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)width * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
+  return tc_encode(tm, base, 2, dims, str, box);
+}
+static int tc_global_init() {
+  if (g_tc_encode) return 0;
   void* fn = nullptr; cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
     snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled entry point not found"); return -1;
   }
-  s.encode = (PFN_encodeTiled)fn;
-  const long long LF = (long long)(2 * N - 1) * TC_CP, LD = (long long)(2 * N - 1) * TC_OP;
-  // + one K chunk of slack so that window reads past the last row stay inside the allocation
-  size_t nf = (size_t)TC_C2 * LF + 2 * TC_KC, nd = (size_t)TC_C1 * LD + 2 * TC_KC;
-  if (cudaMalloc(&s.Wfh, nf * 2) || cudaMalloc(&s.Wfl, nf * 2) || cudaMalloc(&s.Wdh, nd * 2) || cudaMalloc(&s.Wdl, nd * 2)) {
-    snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of staged weights failed"); return -1;
-  }
-  cudaMemsetAsync(s.Wfh, 0, nf * 2, st); cudaMemsetAsync(s.Wfl, 0, nf * 2, st);
-  cudaMemsetAsync(s.Wdh, 0, nd * 2, st); cudaMemsetAsync(s.Wdl, 0, nd * 2, st);
-  // window views: dims (x, jr, ch), strides (CS*2, L*2) bytes
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)N * TC_CP, (cuuint64_t)N, (cuuint64_t)TC_C2};
-    cuuint64_t str[2] = {(cuuint64_t)TC_CP * 2, (cuuint64_t)LF * 2};
-    cuuint32_t box[3] = {TC_KC, 12, 20};
-    if (tc_encode(s, &s.fB_h, s.Wfh, 3, dims, str, box) || tc_encode(s, &s.fB_l, s.Wfl, 3, dims, str, box)) return -1;
-  }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)N * TC_OP, (cuuint64_t)N, (cuuint64_t)TC_C1};
-    cuuint64_t str[2] = {(cuuint64_t)TC_OP * 2, (cuuint64_t)LD * 2};
-    cuuint32_t box[3] = {TC_KC, 24, 10};
-    if (tc_encode(s, &s.dB_h, s.Wdh, 3, dims, str, box) || tc_encode(s, &s.dB_l, s.Wdl, 3, dims, str, box)) return -1;
-  }
+  g_tc_encode = (PFN_encodeTiled)fn;
   cudaFuncSetAttribute(toep_gemm_k<240>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024);
   cudaFuncSetAttribute(wgrad_gemm_k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_STAGES * (2 * TC_KC * TC_BM * 2 + 2 * TC_KC * TC_WN * 2) + 1024);
-  s.ready = 1;
   return 0;
 }
+static int tc_pad16(int c) { return (c * 2) % 16 == 0 ? c : (c + 7) / 8 * 8; }   // channel stride with 16-byte rows
 
-static void tc_destroy(TcState& s) {
-  if (s.Wfh) cudaFree(s.Wfh); if (s.Wfl) cudaFree(s.Wfl); if (s.Wdh) cudaFree(s.Wdh); if (s.Wdl) cudaFree(s.Wdl);
-  s.Wfh = s.Wfl = s.Wdh = s.Wdl = nullptr; s.ready = 0;
-}
-
-// (re)build the tensor maps over the activation planes
-static int tc_bind_planes(TcState& s, const __nv_bfloat16* yh, const __nv_bfloat16* yl, const __nv_bfloat16* dh, const __nv_bfloat16* dl) {
-  const int N = s.N;
-  if (yh && (yh != s.yh || yl != s.yl)) {
-    cuuint64_t dims[2] = {(cuuint64_t)N * TC_CP, (cuuint64_t)s.max_rows};
-    cuuint64_t str[1] = {(cuuint64_t)N * TC_CP * 2};
-    cuuint32_t boxk[2] = {TC_KC, TC_BM};
-    if (tc_encode(s, &s.fA_h, yh, 2, dims, str, boxk) || tc_encode(s, &s.fA_l, yl, 2, dims, str, boxk)) return -1;
-    s.yh = yh; s.yl = yl;
+static int tc_plan_init(ToepPlan& pl, int N, int Cin, int Cout, int fCT, int fJT, int dCT, int dJT, cudaStream_t st) {
+  memset(&pl, 0, sizeof pl);
+  pl.N = N; pl.Cin = Cin; pl.Cout = Cout; pl.CSi = tc_pad16(Cin); pl.CSo = tc_pad16(Cout);
+  pl.fCT = fCT; pl.fJT = fJT; pl.dCT = dCT; pl.dJT = dJT;
+  if (fCT * fJT != 240 || dCT * dJT != 240 || Cout % fCT || Cin % dCT) { snprintf(g_tc_err, sizeof g_tc_err, "bad tile shape"); return -1; }
+  const long long LF = (long long)(2 * N - 1) * pl.CSi, LD = (long long)(2 * N - 1) * pl.CSo;
+  size_t nf = (size_t)Cout * LF + 2 * TC_KC, nd = (size_t)Cin * LD + 2 * TC_KC;
+  if (cudaMalloc(&pl.Wfh, nf * 2) || cudaMalloc(&pl.Wfl, nf * 2) || cudaMalloc(&pl.Wdh, nd * 2) || cudaMalloc(&pl.Wdl, nd * 2)) {
+    snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of staged weights failed"); return -1;
   }
-  if (dh && (dh != s.dh || dl != s.dl)) {
-    cuuint64_t dims[2] = {(cuuint64_t)N * TC_OP, (cuuint64_t)s.max_rows};
-    cuuint64_t str[1] = {(cuuint64_t)N * TC_OP * 2};
-    cuuint32_t boxk[2] = {TC_KC, TC_BM};
-    if (tc_encode(s, &s.dA_h, dh, 2, dims, str, boxk) || tc_encode(s, &s.dA_l, dl, 2, dims, str, boxk)) return -1;
-    s.dh = dh; s.dl = dl;
+  cudaMemsetAsync(pl.Wfh, 0, nf * 2, st); cudaMemsetAsync(pl.Wfl, 0, nf * 2, st);
+  cudaMemsetAsync(pl.Wdh, 0, nd * 2, st); cudaMemsetAsync(pl.Wdl, 0, nd * 2, st);
+  {   // window views: dims (x, jr, ch), strides (CS*2, L*2) bytes -- the jr stride is smaller than the x extent
+    cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSi, (cuuint64_t)N, (cuuint64_t)Cout};
+    cuuint64_t str[2] = {(cuuint64_t)pl.CSi * 2, (cuuint64_t)LF * 2};
+    cuuint32_t box[3] = {TC_KC, (cuuint32_t)fJT, (cuuint32_t)fCT};
+    if (tc_encode(&pl.fB_h, pl.Wfh, 3, dims, str, box) || tc_encode(&pl.fB_l, pl.Wfl, 3, dims, str, box)) return -1;
   }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSo, (cuuint64_t)N, (cuuint64_t)Cin};
+    cuuint64_t str[2] = {(cuuint64_t)pl.CSo * 2, (cuuint64_t)LD * 2};
+    cuuint32_t box[3] = {TC_KC, (cuuint32_t)dJT, (cuuint32_t)dCT};
+    if (tc_encode(&pl.dB_h, pl.Wdh, 3, dims, str, box) || tc_encode(&pl.dB_l, pl.Wdl, 3, dims, str, box)) return -1;
+  }
+  pl.ready = 1;
   return 0;
 }
-// wgrad reduces over the rows, so its maps are bounded by the exact row count (TMA zero-fills beyond)
-static int tc_bind_wgrad(TcState& s, const __nv_bfloat16* yh, const __nv_bfloat16* yl, const __nv_bfloat16* dh, const __nv_bfloat16* dl,
-                         long long rows) {
-  const int N = s.N;
-  if (yh == s.wyh && dh == s.wdh && rows == s.wrows) return 0;
-  cuuint32_t boxm[2] = {64, TC_KC};
-  { cuuint64_t dims[2] = {(cuuint64_t)N * TC_CP, (cuuint64_t)rows}; cuuint64_t str[1] = {(cuuint64_t)N * TC_CP * 2};
-    if (tc_encode(s, &s.wA_h, yh, 2, dims, str, boxm) || tc_encode(s, &s.wA_l, yl, 2, dims, str, boxm)) return -1; }
-  { cuuint64_t dims[2] = {(cuuint64_t)N * TC_OP, (cuuint64_t)rows}; cuuint64_t str[1] = {(cuuint64_t)N * TC_OP * 2};
-    if (tc_encode(s, &s.wB_h, dh, 2, dims, str, boxm) || tc_encode(s, &s.wB_l, dl, 2, dims, str, boxm)) return -1; }
-  s.wyh = yh; s.wdh = dh; s.wrows = rows;
-  return 0;
+static void tc_plan_destroy(ToepPlan& pl) {
+  if (pl.Wfh) cudaFree(pl.Wfh); if (pl.Wfl) cudaFree(pl.Wfl); if (pl.Wdh) cudaFree(pl.Wdh); if (pl.Wdl) cudaFree(pl.Wdl);
+  memset(&pl, 0, sizeof pl);
 }
-
 static int tc_check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "%s launch: %s", what, cudaGetErrorString(e)); return -1; }
   return 0;
 }
-
-static int tc_prepare_weights(TcState& s, const float* w1, int N, cudaStream_t st) {
-  if (!s.ready) { snprintf(g_tc_err, sizeof g_tc_err, "tc state not initialised"); return -1; }
-  long long total = (long long)TC_C2 * (2 * N - 1) * TC_CP + (long long)TC_C1 * (2 * N - 1) * TC_OP;
-  tc_stage_weights_k<<<cdiv(total, 256), 256, 0, st>>>(w1, s.Wfh, s.Wfl, s.Wdh, s.Wdl, N);
+static int tc_plan_stage(ToepPlan& pl, const float* w, int Ctot, int coff, cudaStream_t st) {
+  if (!pl.ready) { snprintf(g_tc_err, sizeof g_tc_err, "plan not initialised"); return -1; }
+  long long total = (long long)pl.Cout * (2 * pl.N - 1) * pl.CSi + (long long)pl.Cin * (2 * pl.N - 1) * pl.CSo;
+  tc_stage_weights_k<<<cdiv(total, 256), 256, 0, st>>>(w, pl.Wfh, pl.Wfl, pl.Wdh, pl.Wdl, pl.N, Ctot, coff, pl.Cin, pl.Cout, pl.CSi, pl.CSo);
   return tc_check_launch("tc_stage_weights_k");
 }
+static int tc_split(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int CS, cudaStream_t st) {
+  tc_split_planes_k<<<cdiv(rows * C, 256), 256, 0, st>>>(src, hi, lo, rows, C, CS);
+  return tc_check_launch("tc_split_planes_k");
+}
+static const size_t TC_TOEP_SMEM = TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024;
+static const size_t TC_WGRAD_SMEM = TC_STAGES * (2 * TC_KC * TC_BM * 2 + 2 * TC_KC * TC_WN * 2) + 1024;
 
-static int tc_fwd(TcState& s, const __nv_bfloat16* Yhi, const __nv_bfloat16* Ylo, float* O12, long long rows, int N, cudaStream_t st) {
-  if (tc_bind_planes(s, Yhi, Ylo, nullptr, nullptr)) return -1;
-  ToepArgs a; a.out = O12; a.rows = rows; a.N = N; a.Cout = TC_C2; a.CS = TC_CP; a.CT = 20; a.JT = 12; a.n_ctiles = 1;
-  a.n_jtiles = (N + 11) / 12; a.pad_rows = N - 1 - (N - 1) / 2; a.KA = N * TC_CP;
+// out[rows, N*Cout] (+)= in[rows, N*CSi planes] . Toeplitz(w)
+static int tc_plan_fwd(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat16* inl, float* out, long long rows, long long rows_alloc,
+                       int accumulate, cudaStream_t st) {
+  CUtensorMap ah, al;
+  if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM)) return -1;
+  ToepArgs a; a.out = out; a.rows = rows; a.N = pl.N; a.Cout = pl.Cout; a.CS = pl.CSi; a.CT = pl.fCT; a.JT = pl.fJT;
+  a.n_ctiles = pl.Cout / pl.fCT; a.n_jtiles = (pl.N + pl.fJT - 1) / pl.fJT; a.pad_rows = pl.N - 1 - (pl.N - 1) / 2; a.KA = pl.N * pl.CSi;
+  a.accumulate = accumulate;
   unsigned grid = (unsigned)(((rows + TC_BM - 1) / TC_BM) * a.n_ctiles * a.n_jtiles);
-  size_t smem = TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024;
-  toep_gemm_k<240><<<grid, 192, smem, st>>>(s.fA_h, s.fA_l, s.fB_h, s.fB_l, a);
+  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.fB_h, pl.fB_l, a);
   return tc_check_launch("toep_gemm_k(fwd)");
 }
-
-static int tc_dgrad(TcState& s, const __nv_bfloat16* dOhi, const __nv_bfloat16* dOlo, float* dY12, long long rows, int N, cudaStream_t st) {
-  if (tc_bind_planes(s, nullptr, nullptr, dOhi, dOlo)) return -1;
-  ToepArgs a; a.out = dY12; a.rows = rows; a.N = N; a.Cout = TC_C1; a.CS = TC_OP; a.CT = 10; a.JT = 24; a.n_ctiles = 5;
-  a.n_jtiles = (N + 23) / 24; a.pad_rows = (N - 1) / 2; a.KA = N * TC_OP;
+// din[rows, N*Cin] (+)= dout[rows, N*CSo planes] . Toeplitz(w)^T
+static int tc_plan_dgrad(ToepPlan& pl, const __nv_bfloat16* doh, const __nv_bfloat16* dol, float* din, long long rows, long long rows_alloc,
+                         int accumulate, cudaStream_t st) {
+  CUtensorMap ah, al;
+  if (tc_encode_rows(&ah, doh, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM) || tc_encode_rows(&al, dol, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM)) return -1;
+  ToepArgs a; a.out = din; a.rows = rows; a.N = pl.N; a.Cout = pl.Cin; a.CS = pl.CSo; a.CT = pl.dCT; a.JT = pl.dJT;
+  a.n_ctiles = pl.Cin / pl.dCT; a.n_jtiles = (pl.N + pl.dJT - 1) / pl.dJT; a.pad_rows = (pl.N - 1) / 2; a.KA = pl.N * pl.CSo;
+  a.accumulate = accumulate;
   unsigned grid = (unsigned)(((rows + TC_BM - 1) / TC_BM) * a.n_ctiles * a.n_jtiles);
-  size_t smem = TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024;
-  toep_gemm_k<240><<<grid, 192, smem, st>>>(s.dA_h, s.dA_l, s.dB_h, s.dB_l, a);
+  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.dB_h, pl.dB_l, a);
   return tc_check_launch("toep_gemm_k(dgrad)");
 }
-
-static int tc_wgrad(TcState& s, const __nv_bfloat16* Yhi, const __nv_bfloat16* Ylo, const __nv_bfloat16* dOhi, const __nv_bfloat16* dOlo,
-                    float* gw1, long long rows, int N, cudaStream_t st) {
-  if (tc_bind_wgrad(s, Yhi, Ylo, dOhi, dOlo, rows)) return -1;
-  WgradArgs a; a.dw1 = gw1; a.rows = rows; a.N = N; a.n_ntiles = (N * TC_OP + TC_WN - 1) / TC_WN;
-  int n_mtiles = (N * TC_CP + TC_BM - 1) / TC_BM;
+// dw[t, coff+c, q] += sum_rows sum_j in[row, j+t-p, c] dout[row, j, q]
+static int tc_plan_wgrad(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat16* inl, const __nv_bfloat16* doh, const __nv_bfloat16* dol,
+                         float* dw, int Ctot, int coff, long long rows, cudaStream_t st) {
+  CUtensorMap ah, al, bh, bl;     // bounded by the exact row count: TMA zero-fills the K tail
+  if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows, 64, TC_KC) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows, 64, TC_KC) ||
+      tc_encode_rows(&bh, doh, (long long)pl.N * pl.CSo, rows, 64, TC_KC) || tc_encode_rows(&bl, dol, (long long)pl.N * pl.CSo, rows, 64, TC_KC)) return -1;
+  WgradArgs a; a.dw = dw; a.rows = rows; a.N = pl.N; a.CSi = pl.CSi; a.Cin = pl.Cin; a.CSo = pl.CSo; a.Cout = pl.Cout; a.Ctot = Ctot; a.coff = coff;
+  a.n_ntiles = (pl.N * pl.CSo + TC_WN - 1) / TC_WN;
+  int n_mtiles = (pl.N * pl.CSi + TC_BM - 1) / TC_BM;
   long long tiles = (long long)n_mtiles * a.n_ntiles;
   long long kchunks = (rows + TC_KC - 1) / TC_KC;
   int ks = 1;
   while (tiles * ks < 2 * 148 && ks * 8 < kchunks) ks *= 2;     // fill the 148 SMs when N is small
   a.ksplit = ks;
-  size_t smem = TC_STAGES * (2 * TC_KC * TC_BM * 2 + 2 * TC_KC * TC_WN * 2) + 1024;
-  wgrad_gemm_k<<<(unsigned)(tiles * ks), 192, smem, st>>>(s.wA_h, s.wA_l, s.wB_h, s.wB_l, a);
+  wgrad_gemm_k<<<(unsigned)(tiles * ks), TC_THREADS, TC_WGRAD_SMEM, st>>>(ah, al, bh, bl, a);
   return tc_check_launch("wgrad_gemm_k");
+}
+
+static int tc_init(TcState& s, int N, int Chv, long long B, cudaStream_t st) {
+  memset(&s, 0, sizeof s);
+  if (tc_global_init()) return -1;
+  if (tc_plan_init(s.l1, N, TC_C1, TC_C2, 20, 12, 10, 24, st)) return -1;
+  if (tc_plan_init(s.l0a, N, Chv, TC_C1, 10, 24, 10, 24, st)) return -1;
+  if (tc_plan_init(s.l0c, N, Chv, TC_C1, 10, 24, 10, 24, st)) return -1;
+  size_t ni = (size_t)B * N * s.l0a.CSi, no = (size_t)B * N * s.l0a.CSo;
+  __nv_bfloat16** ps[8] = {&s.ah, &s.al, &s.ch, &s.cl, &s.dsh, &s.dsl, &s.drh, &s.drl};
+  for (int i = 0; i < 8; ++i) {
+    size_t n = i < 4 ? ni : no;
+    if (cudaMalloc(ps[i], n * 2)) { snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of layer-0 planes failed"); return -1; }
+    cudaMemsetAsync(*ps[i], 0, n * 2, st);
+  }
+  s.ready = 1;
+  return 0;
+}
+static void tc_destroy(TcState& s) {
+  tc_plan_destroy(s.l1); tc_plan_destroy(s.l0a); tc_plan_destroy(s.l0c);
+  __nv_bfloat16* ps[8] = {s.ah, s.al, s.ch, s.cl, s.dsh, s.dsl, s.drh, s.drl};
+  for (int i = 0; i < 8; ++i) if (ps[i]) cudaFree(ps[i]);
+  memset(&s, 0, sizeof s);
 }

@@ -102,7 +102,6 @@ __global__ void toep_vec_bwd_w_k(const float* __restrict__ in, const float* __re
 }
 
 // ---- Y producer: E1 (fp32, kept for the BN_e1 backward) and Y = relu(BN_e1(E1)) ------------------
-// one CTA per (graph, i); threads loop over (j, o).
 struct YOut {
   float* E1;              // [Bc, N, N, C1]
   float* Yf;              // fp32 mode: [2][Bc*N][N*C1]
@@ -111,37 +110,75 @@ struct YOut {
   int CP;
   int bf16;
 };
-__global__ void __launch_bounds__(256) y_producer_k(const float* __restrict__ a, const float* __restrict__ c,
-                                                    const float* __restrict__ WSa, const float* __restrict__ WSc,
-                                                    const float* __restrict__ Rc, const float* __restrict__ Sa,
-                                                    const float* __restrict__ b0, const float* __restrict__ gam1,
-                                                    const float* __restrict__ bet1, YOut Y, int Bc, int N, int Ch, int C1) {
-  extern __shared__ float sm[];
-  float* sa = sm;                 // [Ch]  a_i
-  float* ssa = sm + Ch;           // [C1]  Sa_i + 2 b0
-  long long row = blockIdx.x;     // local (b, i)
-  int i = (int)(row % N); long long b = row / N;
-  for (int t = threadIdx.x; t < Ch; t += blockDim.x) sa[t] = a[row * Ch + t];
-  for (int t = threadIdx.x; t < C1; t += blockDim.x) ssa[t] = Sa[row * C1 + t] + 2.f * b0[t];
-  __syncthreads();
-  const float* wci = WSc + (size_t)i * C1 * Ch;     // WSc[i][o][ch]
-  long long plane = (long long)Bc * N * N;           // elements per direction / channel stride
-  for (int idx = threadIdx.x; idx < N * C1; idx += blockDim.x) {
-    int j = idx / C1, o = idx - j * C1;
-    const float* wa = WSa + ((size_t)j * C1 + o) * Ch;
-    const float* wc = wci + (size_t)o * Ch;
-    const float* cj = c + (b * N + j) * Ch;
-    float acc = ssa[o] + Rc[(b * N + j) * C1 + o];
-    for (int ch = 0; ch < Ch; ++ch) { acc = fmaf(sa[ch], wa[ch], acc); acc = fmaf(cj[ch], wc[ch], acc); }
-    Y.E1[row * N * C1 + idx] = acc;
-    float y = fmaxf(fmaf(acc, gam1[o] * BN_RS, bet1[o]), 0.f);
-    long long e0 = (b * N + i) * N + j, e1 = (b * N + j) * N + i;     // [b,i,j] and [b,j,i]
-    if (Y.bf16) {
-      __nv_bfloat16 hi, lo; split_bf16(y, hi, lo);
-      Y.Yhi[e0 * Y.CP + o] = hi; Y.Ylo[e0 * Y.CP + o] = lo;
-      Y.Yhi[(plane + e1) * Y.CP + o] = hi; Y.Ylo[(plane + e1) * Y.CP + o] = lo;
-    } else {
-      Y.Yf[e0 * C1 + o] = y; Y.Yf[(plane + e1) * C1 + o] = y;
+// Register-resident weights: CTA = (i, tile of YP_TJ positions j); thread = one (j, o) output and
+// keeps WSa[j][o][:] and WSc[i][o][:] (2*Ch floats) in registers while the CTA sweeps the graphs of
+// the chunk, YP_TB graphs per __syncthreads (a_i and c_j rows staged in shared memory, 128-bit
+// broadcast reads).  Per (graph, output): 2*Ch FMAs, 2*Ch/4 LDS.128.
+#define YP_TJ 8
+#define YP_TB 8
+#define YP_CH 40     /* max supported half-width Ch (2H) */
+template <int CH>
+__global__ void __launch_bounds__(YP_TJ * 64) y_producer_k(const float* __restrict__ a, const float* __restrict__ c,
+                                                           const float* __restrict__ WSa, const float* __restrict__ WSc,
+                                                           const float* __restrict__ Rc, const float* __restrict__ Sa,
+                                                           const float* __restrict__ b0, const float* __restrict__ gam1,
+                                                           const float* __restrict__ bet1, YOut Y, int Bc, int N, int C1) {
+  __shared__ __align__(16) float s_a[YP_TB][CH];
+  __shared__ __align__(16) float s_c[YP_TB][YP_TJ][CH];
+  const int i = blockIdx.y;
+  const int j0 = blockIdx.x * YP_TJ;
+  const int tj = threadIdx.x / 64, o = threadIdx.x % 64;      // 64 lanes per j: o < C1 active
+  const int j = j0 + tj;
+  const bool active = o < C1 && j < N;
+  float wa[CH], wc[CH];
+  if (active) {
+    const float4* pa = reinterpret_cast<const float4*>(WSa + ((size_t)j * C1 + o) * CH);
+    const float4* pc = reinterpret_cast<const float4*>(WSc + ((size_t)i * C1 + o) * CH);
+#pragma unroll
+    for (int v = 0; v < CH / 4; ++v) {
+      float4 x = __ldg(pa + v), y = __ldg(pc + v);
+      wa[4 * v] = x.x; wa[4 * v + 1] = x.y; wa[4 * v + 2] = x.z; wa[4 * v + 3] = x.w;
+      wc[4 * v] = y.x; wc[4 * v + 1] = y.y; wc[4 * v + 2] = y.z; wc[4 * v + 3] = y.w;
+    }
+  }
+  const float g1 = active ? gam1[o] * BN_RS : 0.f, bt1 = active ? bet1[o] : 0.f, bb0 = active ? 2.f * b0[o] : 0.f;
+  const long long plane = (long long)Bc * N * N;
+  for (int bb = 0; bb < Bc; bb += YP_TB) {
+    __syncthreads();
+    // stage a[b, i, :] and c[b, j0.., :] for YP_TB graphs
+    for (int t = threadIdx.x; t < YP_TB * CH; t += blockDim.x) {
+      int tb = t / CH, ch = t - tb * CH;
+      s_a[tb][ch] = (bb + tb < Bc) ? a[((long long)(bb + tb) * N + i) * CH + ch] : 0.f;
+    }
+    for (int t = threadIdx.x; t < YP_TB * YP_TJ * CH; t += blockDim.x) {
+      int tb = t / (YP_TJ * CH), r = t - tb * (YP_TJ * CH); int jj = r / CH, ch = r - jj * CH;
+      s_c[tb][jj][ch] = (bb + tb < Bc && j0 + jj < N) ? c[((long long)(bb + tb) * N + j0 + jj) * CH + ch] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+#pragma unroll 2
+    for (int tb = 0; tb < YP_TB; ++tb) {
+      const int b = bb + tb;
+      if (b >= Bc) break;
+      float acc = bb0 + __ldg(Rc + ((long long)b * N + j) * C1 + o) + __ldg(Sa + ((long long)b * N + i) * C1 + o);
+      const float4* xa = reinterpret_cast<const float4*>(&s_a[tb][0]);
+      const float4* xc = reinterpret_cast<const float4*>(&s_c[tb][tj][0]);
+#pragma unroll
+      for (int v = 0; v < CH / 4; ++v) {
+        float4 p = xa[v], q = xc[v];
+        acc = fmaf(p.x, wa[4 * v], acc); acc = fmaf(p.y, wa[4 * v + 1], acc); acc = fmaf(p.z, wa[4 * v + 2], acc); acc = fmaf(p.w, wa[4 * v + 3], acc);
+        acc = fmaf(q.x, wc[4 * v], acc); acc = fmaf(q.y, wc[4 * v + 1], acc); acc = fmaf(q.z, wc[4 * v + 2], acc); acc = fmaf(q.w, wc[4 * v + 3], acc);
+      }
+      const long long e0 = ((long long)b * N + i) * N + j, e1 = ((long long)b * N + j) * N + i;
+      Y.E1[e0 * C1 + o] = acc;
+      const float y = fmaxf(fmaf(acc, g1, bt1), 0.f);
+      if (Y.bf16) {
+        __nv_bfloat16 hi, lo; split_bf16(y, hi, lo);
+        Y.Yhi[e0 * Y.CP + o] = hi; Y.Ylo[e0 * Y.CP + o] = lo;
+        Y.Yhi[(plane + e1) * Y.CP + o] = hi; Y.Ylo[(plane + e1) * Y.CP + o] = lo;
+      } else {
+        Y.Yf[e0 * C1 + o] = y; Y.Yf[(plane + e1) * C1 + o] = y;
+      }
     }
   }
 }
@@ -197,6 +234,15 @@ __global__ void e2e_l1_simt_wgrad_k(const float* __restrict__ Yf, const float* _
     for (int s = lo; s <= hi; ++s) acc = fmaf(y[(s + t - p) * C1 + o], d[s * C2 + q], acc);
   }
   atomicAdd(dw1 + idx, acc);
+}
+
+// argmax(softmax([l0, l1])) of model.py:208 in fp32 with first-index tie breaking, in closed form.
+// softmax = exp(x - max) / sum: class 1 wins iff exp(l0 - l1) rounds below 1, and a correctly
+// rounded fp32 exp(d) equals 1.0f exactly for -2^-25 <= d <= 0 (1 - 2^-25 is the round-to-even
+// midpoint of 1 - 2^-24 and 1).  So the rule is  l1 - l0 > 2^-25  (l0 - l1 is an exact fp32
+// subtraction for nearby values, Sterbenz); it does not depend on the last ulp of an exp routine.
+__device__ __forceinline__ long long threshold_rule(float p0, float p1) {
+  return (p0 - p1) < -2.98023223876953125e-8f ? 1 : 0;
 }
 
 // ---- edge epilogue: logits, mask, threshold, CE loss, and dO (fused forward tail + backward head) -
@@ -263,8 +309,8 @@ __global__ void __launch_bounds__(128) edge_epilogue_k(EpiParams P, int Bc, int 
     float mx = fmaxf(p0, p1);
     float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
     float s = e0 + e1;
-    float s0 = e0 / s, s1 = e1 / s;
-    if (P.gen_adj) P.gen_adj[e] = (s1 > s0) ? 1 : 0;      // tf.argmax: first index on ties
+    float s1 = e1 / s;
+    if (P.gen_adj) P.gen_adj[e] = threshold_rule(p0, p1); // tf.argmax: first index on ties
     if (P.At) {
       float A = P.At[e];
       float lse = mx + logf(s);
@@ -325,7 +371,8 @@ __global__ void threshold_logits_k(const float* __restrict__ lg, long long n, lo
   float mx = fmaxf(p0, p1);
   float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
   float s = e0 + e1;
-  out[idx] = (e1 / s > e0 / s) ? 1 : 0;
+  (void)mx; (void)e0; (void)e1; (void)s;
+  out[idx] = threshold_rule(p0, p1);
 }
 
 // ---- combine the two dgrad directions, go back through relu / BN_e1 --------------------------------

@@ -95,6 +95,18 @@ __global__ void xtdy_k(const float* __restrict__ X, int ldx, const float* __rest
   }
 }
 
+// col[r, t*Ci + ci] = X[r + t - pb, ci] (zero outside the graph): the conv1d weight gradient is then
+// the library GEMM  dK[(t,ci), co] += col^T . dY
+__global__ void im2col_k(const float* __restrict__ X, float* __restrict__ col, long long rows, int N, int Ci, int ktaps) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = ktaps * Ci;
+  if (idx >= rows * W) return;
+  long long r = idx / W; int q = (int)(idx - r * W); int t = q / Ci, ci = q - t * Ci;
+  int pb = (ktaps - 1) / 2;
+  int nn = (int)(r % N) + t - pb;
+  col[idx] = (nn >= 0 && nn < N) ? X[(r + t - pb) * Ci + ci] : 0.f;
+}
+
 // db[c] += sum_r dY[r, c]
 __global__ void colsum_k(const float* __restrict__ dY, int ldy, float* __restrict__ db, long long rows, int C) {
   long long r0 = (long long)blockIdx.x * XTDY_SLAB;

@@ -114,6 +114,10 @@ struct SgcScratch {      // per-sample activations of one layer (global memory)
   float* ee;             // [samples, cap, h0]
   float* dpx;            // [samples, N, C]
   float* dapx;           // [samples, N, C]
+  // coefficient matrices of the parameter gradients (dM = coef^T . grad as library GEMMs):
+  float* coef1;          // [samples, cap, 3C+4]  per edge:  [deg_j phi(x_i), deg_j phi(x_j), apx_j, deg_j phi(r), s_j, G, deg_j]
+  float* coef2;          // [samples, N, 2C+2+h0] per node:  [deg_i phi(x_i), apx_i, s_i, T_i, deg_i]
+  float* coef3;          // [samples, N, C+h1+1]  per node:  [phi(x_i), phi(m2s_i), 1]
 };
 
 // bracket of m3s for edge (i,j), channel h (without the leading A_ij)
@@ -241,6 +245,44 @@ __global__ void __launch_bounds__(256) sgc_layer_bwd_k(const float* __restrict__
     float br = sgc_bracket(W, x, apx, i, j, h, deg[j], ssum[j], epr[e], eG[e]);
     ee[idx] = a * a * dT[i * h0 + h] * lrelu_g(a * br);
   }
+  // coefficient rows for the parameter-gradient GEMMs (rows e >= ne of coef1 / ee stay zero)
+  {
+    const int K1 = 3 * C + 4, K2 = 2 * C + 2 + h0, K3 = C + h1 + 1;
+    float* c1 = Sx.coef1 + ls * (long long)E.cap * K1;
+    float* c2 = Sx.coef2 + ls * (long long)N * K2;
+    float* c3 = Sx.coef3 + ls * (long long)N * K3;
+    const float* T = Sx.T + ls * N * h0;
+    for (int idx = threadIdx.x; idx < E.cap * K1; idx += blockDim.x) {
+      int e = idx / K1, r = idx - e * K1;
+      float v = 0.f;
+      if (e < ne) {
+        int i = erow[e], j = ecol[e];
+        if (r < C) v = deg[j] * lrelu_f(x[i * C + r]);
+        else if (r < 2 * C) v = deg[j] * lrelu_f(x[j * C + r - C]);
+        else if (r < 3 * C) v = apx[j * C + r - 2 * C];
+        else if (r == 3 * C) v = deg[j] * epr[e];
+        else if (r == 3 * C + 1) v = ssum[j];
+        else if (r == 3 * C + 2) v = eG[e];
+        else v = deg[j];
+      }
+      c1[idx] = v;
+    }
+    for (int idx = threadIdx.x; idx < N * K2; idx += blockDim.x) {
+      int i = idx / K2, r = idx - i * K2;
+      float v;
+      if (r < C) v = deg[i] * lrelu_f(x[i * C + r]);
+      else if (r < 2 * C) v = apx[i * C + r - C];
+      else if (r == 2 * C) v = ssum[i];
+      else if (r < 2 * C + 1 + h0) v = T[i * h0 + r - 2 * C - 1];
+      else v = deg[i];
+      c2[idx] = v;
+    }
+    for (int idx = threadIdx.x; idx < N * K3; idx += blockDim.x) {
+      int i = idx / K3, r = idx - i * K3;
+      c3[idx] = r < C ? lrelu_f(x[i * C + r]) : (r < C + h1 ? lrelu_f(m2s[i * h1 + r - C]) : 1.f);
+    }
+    for (int idx = ne * h0 + threadIdx.x; idx < E.cap * h0; idx += blockDim.x) ee[idx] = 0.f;
+  }
   __syncthreads();
   if (!dx) return;
   // (d) edge contributions to d phi(x) and d apx
@@ -270,78 +312,3 @@ __global__ void __launch_bounds__(256) sgc_layer_bwd_k(const float* __restrict__
   for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) dx[idx] += dpx[idx] * lrelu_g(x[idx]);
 }
 
-// parameter gradients of one SGC layer.  grid = (ceil(nparams/256), sample groups);
-// each thread owns one parameter entry, loops over SGC_PG samples, one atomicAdd.
-#define SGC_PG 16
-__global__ void __launch_bounds__(256) sgc_param_grad_k(const float* __restrict__ xin, const float* __restrict__ dyin,
-                                                        SgcEdges E, SgcW W, SgcW G, SgcScratch Sx, int N,
-                                                        long long nsamples, long long e_off) {
-  const int C = W.C, h0 = W.h0, h1 = W.h1, h2 = W.h2;
-  const int n1 = (3 * C + 4) * h0;          // M1 rows + bias1
-  const int n2 = (2 * C + 2 + h0) * h1;     // M2 rows + bias2
-  const int n3 = (C + h1 + 1) * h2;         // M3 rows + bias3
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n1 + n2 + n3) return;
-  long long s0 = (long long)blockIdx.y * SGC_PG, s1 = s0 + SGC_PG;
-  if (s1 > nsamples) s1 = nsamples;
-  float acc = 0.f;
-  float* dst;
-  if (p < n1) {
-    int row = p / h0, h = p - row * h0;
-    dst = row < 3 * C + 3 ? G.M1 + row * h0 + h : G.b1 + h;
-    for (long long ls = s0; ls < s1; ++ls) {
-      long long gs = ls + e_off;
-      const float* x = xin + ls * N * C; const float* apx = Sx.apx + ls * N * C;
-      const float* ee = Sx.ee + ls * (long long)E.cap * h0;
-      const int* erow = E.erow + gs * E.cap; const int* ecol = E.ecol + gs * E.cap;
-      const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
-      const float* epr = E.epr + gs * E.cap; const float* eG = E.eG + gs * E.cap;
-      int ne = E.nedges[gs];
-      for (int e = 0; e < ne; ++e) {
-        int i = erow[e], j = ecol[e];
-        float coef;
-        if (row < C) coef = deg[j] * lrelu_f(x[i * C + row]);
-        else if (row < 2 * C) coef = deg[j] * lrelu_f(x[j * C + row - C]);
-        else if (row < 3 * C) coef = apx[j * C + row - 2 * C];
-        else if (row == 3 * C) coef = deg[j] * epr[e];
-        else if (row == 3 * C + 1) coef = ssum[j];
-        else if (row == 3 * C + 2) coef = eG[e];
-        else coef = deg[j];
-        acc = fmaf(coef, ee[e * h0 + h], acc);
-      }
-    }
-  } else if (p < n1 + n2) {
-    int q = p - n1; int row = q / h1, h = q - row * h1;
-    dst = row < 2 * C + 1 + h0 ? G.M2 + row * h1 + h : G.b2 + h;
-    for (long long ls = s0; ls < s1; ++ls) {
-      long long gs = ls + e_off;
-      const float* x = xin + ls * N * C; const float* apx = Sx.apx + ls * N * C;
-      const float* T = Sx.T + ls * N * h0; const float* dm2s = Sx.dm2s + ls * N * h1;
-      const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
-      for (int i = 0; i < N; ++i) {
-        float coef;
-        if (row < C) coef = deg[i] * lrelu_f(x[i * C + row]);
-        else if (row < 2 * C) coef = apx[i * C + row - C];
-        else if (row == 2 * C) coef = ssum[i];
-        else if (row < 2 * C + 1 + h0) coef = T[i * h0 + row - 2 * C - 1];
-        else coef = deg[i];
-        acc = fmaf(coef, dm2s[i * h1 + h], acc);
-      }
-    }
-  } else {
-    int q = p - n1 - n2; int row = q / h2, h = q - row * h2;
-    dst = row < C + h1 ? G.M3 + row * h2 + h : G.b3 + h;
-    for (long long ls = s0; ls < s1; ++ls) {
-      const float* x = xin + ls * N * C; const float* m2s = Sx.m2s + ls * N * h1;
-      const float* dy = dyin + ls * N * h2;
-      for (int i = 0; i < N; ++i) {
-        float coef;
-        if (row < C) coef = lrelu_f(x[i * C + row]);
-        else if (row < C + h1) coef = lrelu_f(m2s[i * h1 + row - C]);
-        else coef = 1.f;
-        acc = fmaf(coef, dy[i * h2 + h], acc);
-      }
-    }
-  }
-  atomicAdd(dst, acc);
-}

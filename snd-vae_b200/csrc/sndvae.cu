@@ -61,6 +61,7 @@ struct sndvae_handle {
   float *s1p, *s1, *s2p, *s2, *s3p, *s3, *ppre, *phat, *dppre;
   float *a, *c, *Rc, *Sa, *WSa, *WSc, *da, *dc, *dRc, *dSa, *dWSa, *dWSc, *dv, *dsp0;
   float *gA, *gB, *gC;                 // generic [Rn, 64] backward temporaries
+  float *colbuf;                       // [Rn, 5 * 50] im2col staging for conv1d weight gradients
   float *E1, *O12, *dY12, *Yf, *dOf;   // chunk buffers (fp32)
   __nv_bfloat16 *Yhi, *Ylo, *dOhi, *dOlo;
   TcState tc;
@@ -239,6 +240,7 @@ static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long 
   DA(s.apx, samples * N * C); DA(s.T, samples * N * hs[0]); DA(s.m2s, samples * N * hs[1]); DA(s.y, samples * N * hs[2]);
   DA(s.dm2s, samples * N * hs[1]); DA(s.dT, samples * N * hs[0]); DA(s.ee, samples * cap * hs[0]);
   DA(s.dpx, samples * N * C); DA(s.dapx, samples * N * C);
+  DA(s.coef1, samples * cap * (3 * C + 4)); DA(s.coef2, samples * N * (2 * C + 2 + hs[0])); DA(s.coef3, samples * N * (C + hs[1] + 1));
   return 0;
 }
 
@@ -288,7 +290,7 @@ static int alloc_buffers(sndvae_t* h) {
   DA(h->da, Rn * Chv); DA(h->dc, Rn * Chv); DA(h->dRc, Rn * C1); DA(h->dSa, Rn * C1);
   DA(h->dWSa, (long long)N * C1 * Chv); DA(h->dWSc, (long long)N * C1 * Chv);
   DA(h->dv, Rn * Chv); DA(h->dsp0, Rn * Chv);
-  DA(h->gA, Rn * 64); DA(h->gB, Rn * 64); DA(h->gC, Rn * 64);
+  DA(h->gA, Rn * 64); DA(h->gB, Rn * 64); DA(h->gC, Rn * 64); DA(h->colbuf, Rn * KS * 64);
   const long long cells = (long long)h->Bc * N * N;
   DA(h->E1, cells * C1); DA(h->O12, 2 * cells * C2); DA(h->dY12, 2 * cells * C1);
   if (c.use_tensor_cores) {
@@ -341,10 +343,28 @@ static void conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, l
   LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS);
 }
 // weight/bias grads + optional input grad of a conv1d layer
-static void conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
-  LAUNCH(xtdy_k, cdiv(rows, XTDY_SLAB), 256, 0, in, Ci, dout, Co, h->G + k, rows, h->N, Ci, Co, KS);
+static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
+  LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
+  CKB(gemm_rm(h, true, false, KS * Ci, Co, (int)rows, 1.f, h->colbuf, KS * Ci, dout, Co, 1.f, h->G + k, Co));
   LAUNCH(colsum_k, cdiv(rows, XTDY_SLAB), 64, 0, dout, Co, h->G + b, rows, Co);
   if (din) LEW(conv1d_bwd_in_k, rows * Ci, dout, h->P + k, din, rows, h->N, Ci, Co, KS);
+  return 0;
+}
+struct SgcW; static SgcW sgc_w_fwd(sndvae_t* h, int l); static SgcW sgc_w_grad(sndvae_t* h, int l);
+// dM[K-1, hcols] += coef[:, :K-1]^T grad;  db[hcols] += coef[:, K-1]^T grad   (SGC parameter gradients)
+static int coef_grad(sndvae_t* h, const float* coef, int K, const float* grad, int hcols, long long rows, float* dM, float* db) {
+  CKB(gemm_rm(h, true, false, K - 1, hcols, (int)rows, 1.f, coef, K, grad, hcols, 1.f, dM, hcols));
+  CKB(gemm_rm(h, true, false, 1, hcols, (int)rows, 1.f, coef + (K - 1), K, grad, hcols, 1.f, db, hcols));
+  return 0;
+}
+static int sgc_param_grads(sndvae_t* h, int l, const float* dy, SgcScratch& Sx, long long ns) {
+  SgcW w = sgc_w_fwd(h, l); SgcW g = sgc_w_grad(h, l);
+  const int C = w.C, N = h->N; const long long cap = h->E.cap;
+  int r;
+  if ((r = coef_grad(h, Sx.coef1, 3 * C + 4, Sx.ee, w.h0, ns * cap, g.M1, g.b1))) return r;
+  if ((r = coef_grad(h, Sx.coef2, 2 * C + 2 + w.h0, Sx.dm2s, w.h1, ns * N, g.M2, g.b2))) return r;
+  if ((r = coef_grad(h, Sx.coef3, C + w.h1 + 1, dy, w.h2, ns * N, g.M3, g.b3))) return r;
+  return 0;
 }
 static SgcW sgc_w(sndvae_t* h, float* base, int l) {
   const sndvae_config& c = h->cfg; const PT& p = h->pt;
@@ -354,6 +374,8 @@ static SgcW sgc_w(sndvae_t* h, float* base, int l) {
   w.h0 = c.sg_conv_hidden[l][0]; w.h1 = c.sg_conv_hidden[l][1]; w.h2 = c.sg_conv_hidden[l][2];
   return w;
 }
+static SgcW sgc_w_fwd(sndvae_t* h, int l) { return sgc_w(h, h->P, l); }
+static SgcW sgc_w_grad(sndvae_t* h, int l) { return sgc_w(h, h->G, l); }
 static void ev_begin(sndvae_t* h, double flops) {
   if (h->ev_used < h->ev.size()) { h->ev[h->ev_used].flops = flops; cudaEventRecord(h->ev[h->ev_used].a, h->stream); }
 }
@@ -411,11 +433,14 @@ static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
     if ((r = lin_fwd(h, h->hs, p.s_lin[2], h->ls_s, B, c.s_hidden_size, c.s_latent_size))) return r;
   }
   // joint encoder (model.py:134-151): edge lists once per step, SGC x2 in sample chunks
+  mark(h, "sgc_edges");
   LAUNCH(sgc_build_edges_k, (unsigned)BS, 256, 0, in->adj, in->rel, h->E, N, h->errflag);
+  mark(h, "sgc_fwd");
   for (long long s0 = 0; s0 < BS; s0 += h->SC) {
     long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
     int r = sgc_chunk_fwd(h, in, s0, ns); if (r) return r;
   }
+  mark(h, "enc_heads");
   const int h12 = c.sg_conv_hidden[1][2];
   int r;
   if ((r = lin_fwd(h, h->fsg, p.sg_lin[0], h->hsg, BS, N * h12, c.sg_hidden_size))) return r;
@@ -490,10 +515,20 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   bn_fwd(h, h->v, Chv, p.e_bng[0] + Chv, p.e_bnb[0] + Chv, h->c, Chv, Rn, Chv, ACT_RELU, 0);
   LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSa, N, Ctot, 0, Chv, C1);
   LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSc, N, Ctot, Chv, Chv, C1);
-  LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
-  LEW(toep_vec_fwd_k, Rn * C1, h->a, w0, h->Sa, B, N, Ctot, 0, Chv, C1);
   const bool tc = c.use_tensor_cores != 0;
-  if (tc) { if ((r = tc_prepare_weights(h->tc, h->P + p.e_w[1], N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_prepare_weights failed: %s", tc_last_error()); h->launches += 1; }
+  if (tc) {
+    // Rc = c . Toeplitz(w0[:, Ch:, :]),  Sa = a . Toeplitz(w0[:, :Ch, :])  on the tensor cores (split-bf16)
+    TcState& T = h->tc;
+    if (tc_plan_stage(T.l1, h->P + p.e_w[1], C1, 0, h->stream) || tc_plan_stage(T.l0a, w0, Ctot, 0, h->stream) ||
+        tc_plan_stage(T.l0c, w0, Ctot, Chv, h->stream) ||
+        tc_split(h->a, T.ah, T.al, Rn, Chv, T.l0a.CSi, h->stream) || tc_split(h->c, T.ch, T.cl, Rn, Chv, T.l0c.CSi, h->stream) ||
+        tc_plan_fwd(T.l0c, T.ch, T.cl, h->Rc, B, B, 0, h->stream) || tc_plan_fwd(T.l0a, T.ah, T.al, h->Sa, B, B, 0, h->stream))
+      return fail(h, SNDVAE_E_CUDA, "tensor-core layer-0 products: %s", tc_last_error());
+    h->launches += 7;
+  } else {
+    LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
+    LEW(toep_vec_fwd_k, Rn * C1, h->a, w0, h->Sa, B, N, Ctot, 0, Chv, C1);
+  }
   if (backward) {
     CK(cudaMemsetAsync(h->dWSa, 0, sizeof(float) * N * C1 * Chv, h->stream));
     CK(cudaMemsetAsync(h->dWSc, 0, sizeof(float) * N * C1 * Chv, h->stream));
@@ -505,11 +540,14 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     const long long rows = (long long)bc * N, cells = rows * N;
     mark(h, "y_producer");
     YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = TC_CP; Y.bf16 = tc;
-    LAUNCH(y_producer_k, (unsigned)rows, 256, sizeof(float) * (Chv + C1), h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc,
-           h->Rc + b0 * N * C1, h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, Chv, C1);
+    { dim3 yg(cdiv(N, YP_TJ), N);
+      if (Chv == 40) LAUNCH(y_producer_k<40>, yg, YP_TJ * 64, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
+                            h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
+      else LAUNCH(y_producer_k<20>, yg, YP_TJ * 64, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
+                  h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1); }
     mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
-    if (tc) { if ((r = tc_fwd(h->tc, h->Yhi, h->Ylo, h->O12, 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_fwd: %s", tc_last_error()); h->launches++; }
+    if (tc) { if ((r = tc_plan_fwd(h->tc.l1, h->Yhi, h->Ylo, h->O12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc fwd: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_fwd_k, 2 * cells * C2, h->Yf, h->P + p.e_w[1], h->O12, 2 * rows, N, C1, C2);
     ev_end(h);
     mark(h, "epilogue");
@@ -530,12 +568,12 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     // backward of e2e layer 1: dgrad + wgrad
     mark(h, "gemm_dgrad");
     ev_begin(h, f1 * bc);
-    if (tc) { if ((r = tc_dgrad(h->tc, h->dOhi, h->dOlo, h->dY12, 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_dgrad: %s", tc_last_error()); h->launches++; }
+    if (tc) { if ((r = tc_plan_dgrad(h->tc.l1, h->dOhi, h->dOlo, h->dY12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc dgrad: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_dgrad_k, 2 * cells * C1, h->dOf, h->P + p.e_w[1], h->dY12, 2 * rows, N, C1, C2);
     ev_end(h);
     mark(h, "gemm_wgrad");
     ev_begin(h, f1 * bc);
-    if (tc) { if ((r = tc_wgrad(h->tc, h->Yhi, h->Ylo, h->dOhi, h->dOlo, h->G + p.e_w[1], 2 * rows, N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_wgrad: %s", tc_last_error()); h->launches++; }
+    if (tc) { if ((r = tc_plan_wgrad(h->tc.l1, h->Yhi, h->Ylo, h->dOhi, h->dOlo, h->G + p.e_w[1], C1, 0, 2 * rows, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc wgrad: %s", tc_last_error()); h->launches++; }
     else { dim3 g(cdiv((long long)N * C1 * C2, 256), cdiv(2 * rows, WGRAD_RG));
            LAUNCH(e2e_l1_simt_wgrad_k, g, 256, 0, h->Yf, h->dOf, h->G + p.e_w[1], 2 * rows, N, C1, C2); }
     ev_end(h);
@@ -568,11 +606,21 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   int r;
   mark(h, "l0_vec_bwd");
   // ---- e2e layer 0 vector terms and weight sums ----
-  LEW(toep_vec_bwd_in_k, Rn * Chv, h->dRc, w0, h->dc, B, N, Ctot, Chv, Chv, C1);
-  LEW(toep_vec_bwd_in_k, Rn * Chv, h->dSa, w0, h->da, B, N, Ctot, 0, Chv, C1);
-  { dim3 g(cdiv((long long)N * Chv * C1, 256), cdiv(B, TOEP_BG));
+  if (c.use_tensor_cores) {
+    TcState& T = h->tc;
+    if (tc_split(h->dRc, T.drh, T.drl, Rn, C1, T.l0c.CSo, h->stream) || tc_split(h->dSa, T.dsh, T.dsl, Rn, C1, T.l0a.CSo, h->stream) ||
+        tc_plan_dgrad(T.l0c, T.drh, T.drl, h->dc, B, B, 1, h->stream) || tc_plan_dgrad(T.l0a, T.dsh, T.dsl, h->da, B, B, 1, h->stream) ||
+        tc_plan_wgrad(T.l0c, T.ch, T.cl, T.drh, T.drl, h->G + p.e_w[0], Ctot, Chv, B, h->stream) ||
+        tc_plan_wgrad(T.l0a, T.ah, T.al, T.dsh, T.dsl, h->G + p.e_w[0], Ctot, 0, B, h->stream))
+      return fail(h, SNDVAE_E_CUDA, "tensor-core layer-0 backward products: %s", tc_last_error());
+    h->launches += 6;
+  } else {
+    LEW(toep_vec_bwd_in_k, Rn * Chv, h->dRc, w0, h->dc, B, N, Ctot, Chv, Chv, C1);
+    LEW(toep_vec_bwd_in_k, Rn * Chv, h->dSa, w0, h->da, B, N, Ctot, 0, Chv, C1);
+    dim3 g(cdiv((long long)N * Chv * C1, 256), cdiv(B, TOEP_BG));
     LAUNCH(toep_vec_bwd_w_k, g, 256, 0, h->c, h->dRc, h->G + p.e_w[0], B, N, Ctot, Chv, Chv, C1);
-    LAUNCH(toep_vec_bwd_w_k, g, 256, 0, h->a, h->dSa, h->G + p.e_w[0], B, N, Ctot, 0, Chv, C1); }
+    LAUNCH(toep_vec_bwd_w_k, g, 256, 0, h->a, h->dSa, h->G + p.e_w[0], B, N, Ctot, 0, Chv, C1);
+  }
   LEW(e2e_l0_prep_bwd_k, (long long)N * Chv * C1, h->dWSa, h->G + p.e_w[0], N, Ctot, 0, Chv, C1);
   LEW(e2e_l0_prep_bwd_k, (long long)N * Chv * C1, h->dWSc, h->G + p.e_w[0], N, Ctot, Chv, Chv, C1);
   mark(h, "dec_nodes_bwd");
@@ -587,9 +635,9 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   LEW(rowlin_bwd_in_k, Rn * nc[1], h->dxpre, F, h->P + p.d_n_lin2[0], h->gA, nc[1], Rn, nc[1], F, 0);      // dq3
   if (h->dis) bn_bwd(h, h->gA, nc[1], h->q2, nc[1], p.decnode_g, p.decnode_b, h->gA, nc[1], Rn, nc[1], ACT_NONE, 0);  // dq2
   bn_bwd(h, h->gA, nc[1], h->q2p, nc[1], p.n_bng[1], p.n_bnb[1], h->gA, nc[1], Rn, nc[1], dact, 0);                   // dq2p
-  conv_bwd(h, h->q1, p.n_k[1], p.n_b[1], h->gA, h->gB, Rn, nc[0], nc[1]);                                            // dq1
+  if ((r = conv_bwd(h, h->q1, p.n_k[1], p.n_b[1], h->gA, h->gB, Rn, nc[0], nc[1]))) return r;                                            // dq1
   bn_bwd(h, h->gB, nc[0], h->q1p, nc[0], p.n_bng[0], p.n_bnb[0], h->gB, nc[0], Rn, nc[0], dact, 0);                   // dq1p
-  conv_bwd(h, h->v, p.n_k[0], p.n_b[0], h->gB, h->gA, Rn, Chv, nc[0]);                                               // dv (node)
+  if ((r = conv_bwd(h, h->v, p.n_k[0], p.n_b[0], h->gB, h->gA, Rn, Chv, nc[0]))) return r;                                               // dv (node)
   LEW(add_inplace_k, Rn * Chv, h->dv, h->gA, Rn * Chv);
   // ---- spatial decoder ----
   const int* sc = c.s_d_channel;
@@ -597,11 +645,11 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   LAUNCH(colsum_k, cdiv(Rn, XTDY_SLAB), 32, 0, h->dppre, D, h->G + p.d_s_lin2[1], Rn, D);
   LEW(rowlin_bwd_in_k, Rn * sc[2], h->dppre, D, h->P + p.d_s_lin2[0], h->gA, sc[2], Rn, sc[2], D, 0);      // ds3
   bn_bwd(h, h->gA, sc[2], h->s3p, sc[2], p.s_bng[2], p.s_bnb[2], h->gA, sc[2], Rn, sc[2], dact, 0);                   // ds3p
-  conv_bwd(h, h->s2, p.s_k[2], p.s_b[2], h->gA, h->gB, Rn, sc[1], sc[2]);                                            // ds2
+  if ((r = conv_bwd(h, h->s2, p.s_k[2], p.s_b[2], h->gA, h->gB, Rn, sc[1], sc[2]))) return r;                                            // ds2
   bn_bwd(h, h->gB, sc[1], h->s2p, sc[1], p.s_bng[1], p.s_bnb[1], h->gB, sc[1], Rn, sc[1], dact, 0);
-  conv_bwd(h, h->s1, p.s_k[1], p.s_b[1], h->gB, h->gA, Rn, sc[0], sc[1]);                                            // ds1
+  if ((r = conv_bwd(h, h->s1, p.s_k[1], p.s_b[1], h->gB, h->gA, Rn, sc[0], sc[1]))) return r;                                            // ds1
   bn_bwd(h, h->gA, sc[0], h->s1p, sc[0], p.s_bng[0], p.s_bnb[0], h->gA, sc[0], Rn, sc[0], dact, 0);
-  conv_bwd(h, h->sp0, p.s_k[0], p.s_b[0], h->gA, h->dsp0, Rn, Chv, sc[0]);                                           // dsp0
+  if ((r = conv_bwd(h, h->sp0, p.s_k[0], p.s_b[0], h->gA, h->dsp0, Rn, Chv, sc[0]))) return r;                                           // dsp0
   // ---- split back into n_sg / n_s / n_g and through the z -> [N,H] linears ----
   if (h->dis) {
     LEW(copy_cols_k, Rn * H, h->dv, Chv, 0, h->dn_sg, H, 0, Rn, H, 0);
@@ -647,11 +695,11 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     if ((r = lin_bwd(h, h->fs, p.s_lin[0], h->dh, h->gA, B, N * ec[2], Hh))) return r;                              // dfs
     bn_bwd(h, h->gA, ec[2], h->h3, ec[2], p.encs_g, p.encs_b, h->gA, ec[2], Rn, ec[2], ACT_NONE, 0);                // dh3
     bn_bwd(h, h->gA, ec[2], h->h3p, ec[2], p.gs_bng[2], p.gs_bnb[2], h->gA, ec[2], Rn, ec[2], ACT_RELU, 0);         // dh3p
-    conv_bwd(h, h->h2, p.gs_k[2], p.gs_b[2], h->gA, h->gB, Rn, ec[1], ec[2]);
+    if ((r = conv_bwd(h, h->h2, p.gs_k[2], p.gs_b[2], h->gA, h->gB, Rn, ec[1], ec[2]))) return r;
     bn_bwd(h, h->gB, ec[1], h->h2p, ec[1], p.gs_bng[1], p.gs_bnb[1], h->gB, ec[1], Rn, ec[1], ACT_RELU, 0);
-    conv_bwd(h, h->h1, p.gs_k[1], p.gs_b[1], h->gB, h->gA, Rn, ec[0], ec[1]);
+    if ((r = conv_bwd(h, h->h1, p.gs_k[1], p.gs_b[1], h->gB, h->gA, Rn, ec[0], ec[1]))) return r;
     bn_bwd(h, h->gA, ec[0], h->h1p, ec[0], p.gs_bng[0], p.gs_bnb[0], h->gA, ec[0], Rn, ec[0], ACT_RELU, 0);
-    conv_bwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->gA, nullptr, Rn, D, ec[0]);
+    if ((r = conv_bwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->gA, nullptr, Rn, D, ec[0]))) return r;
   }
   mark(h, "enc_bwd_sgc");
   // joint head (z_sg rows are graph-major: row b*S+s; the S-mean gives dz = dzbar[b]/S)
@@ -666,20 +714,21 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     if ((r = lin_bwd(h, h->fsg, p.sg_lin[0], h->dh, h->dfsg, BS, N * h12, Hh))) return r;
     for (long long s0 = 0; s0 < BS; s0 += h->SC) {
       long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
+      mark(h, "sgc_refwd");
       if ((r = sgc_chunk_fwd(h, in, s0, ns))) return r;     // recompute the chunk's activations (cheap; bounds scratch to one chunk)
+      mark(h, "sgc_bwd_act");
       const float* x0 = in->features + s0 * N * F;
       // fsg = BN_encsg(x2); x2 = lrelu(BN_sg1(y1))
       bn_bwd(h, h->dfsg + s0 * N * h12, h12, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h12, ns * N, h12, ACT_NONE, 0);
       bn_bwd(h, h->dxa, h12, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->dxa, h12, ns * N, h12, ACT_LRELU, 0);      // dy1
       LAUNCH(sgc_layer_bwd_k, (unsigned)ns, 256, 0, h->x1, h->dxa, h->dxb, h->E, sgc_w(h, h->P, 1), h->S1, N, s0);  // dx1
-      { SgcW w = sgc_w(h, h->P, 1); int np = (3 * w.C + 4) * w.h0 + (2 * w.C + 2 + w.h0) * w.h1 + (w.C + w.h1 + 1) * w.h2;
-        dim3 g(cdiv(np, 256), cdiv(ns, SGC_PG));
-        LAUNCH(sgc_param_grad_k, g, 256, 0, h->x1, h->dxa, h->E, w, sgc_w(h, h->G, 1), h->S1, N, ns, s0); }
+      mark(h, "sgc_pgrad");
+      if ((r = sgc_param_grads(h, 1, h->dxa, h->S1, ns))) return r;
+      mark(h, "sgc_bwd_act");
       bn_bwd(h, h->dxb, h02, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->dxb, h02, ns * N, h02, ACT_LRELU, 0);      // dy0
       LAUNCH(sgc_layer_bwd_k, (unsigned)ns, 256, 0, x0, h->dxb, (float*)nullptr, h->E, sgc_w(h, h->P, 0), h->S0, N, s0);
-      { SgcW w = sgc_w(h, h->P, 0); int np = (3 * w.C + 4) * w.h0 + (2 * w.C + 2 + w.h0) * w.h1 + (w.C + w.h1 + 1) * w.h2;
-        dim3 g(cdiv(np, 256), cdiv(ns, SGC_PG));
-        LAUNCH(sgc_param_grad_k, g, 256, 0, x0, h->dxb, h->E, w, sgc_w(h, h->G, 0), h->S0, N, ns, s0); }
+      mark(h, "sgc_pgrad");
+      if ((r = sgc_param_grads(h, 0, h->dxb, h->S0, ns))) return r;
     }
   }
   return 0;
@@ -789,6 +838,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
   if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);
+  if (c.node_h_size != 20 || c.e_d_hidden[0] > 64) return fail(h, SNDVAE_E_ARG, "this build supports node_h_size = 20 and e_d_hidden[0] <= 64 (synthetic2, main.py:209)");
   if (c.g_conv_hidden[0] > 32 || c.g_conv_hidden[1] > 32) return fail(h, SNDVAE_E_ARG, "g_conv_hidden must be <= 32");
   h->N = c.num_nodes; h->F = c.num_feature; h->D = c.spatial_dim; h->S = c.sampling_num; h->H = c.node_h_size;
   h->Chv = h->dis ? 2 * h->H : h->H; h->C1 = c.e_d_hidden[0]; h->C2 = c.e_d_hidden[1];
@@ -804,7 +854,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   }
   if (c.chunk_graphs > h->B) c.chunk_graphs = (int)h->B;
   h->Bc = c.chunk_graphs;
-  { long long per_sample = (long long)h->N * 700 * 4 + (long long)c.edge_capacity * 75 * 4;
+  { long long per_sample = (long long)h->N * 900 * 4 + (long long)c.edge_capacity * 145 * 4;
     long long sc = (4LL << 30) / per_sample; if (sc < 1) sc = 1; if (sc > h->BS) sc = h->BS; h->SC = (int)sc; }
   if ((long long)2 * h->Bc * h->N * h->N * h->C1 > 2000000000LL) return fail(h, SNDVAE_E_ARG, "chunk too large for 32-bit GEMM dims");
   build_table(h);      // host-only: the table is valid even when no device is present (checked by the CPU tests)
@@ -822,7 +872,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   h->ev.resize(4096);
   for (auto& e : h->ev) { cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.flops = 0; }
   if (c.use_tensor_cores) {
-    if ((r = tc_init(h->tc, h->N, 2LL * h->Bc * h->N, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
+    if ((r = tc_init(h->tc, h->N, h->Chv, h->B, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
   }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
