@@ -113,23 +113,24 @@ struct YOut {
 // Register-resident weights: CTA = (i, tile of YP_TJ positions j); thread = one (j, o) output and
 // keeps WSa[j][o][:] and WSc[i][o][:] (2*Ch floats) in registers while the CTA sweeps the graphs of
 // the chunk, YP_TB graphs per __syncthreads (a_i and c_j rows staged in shared memory, 128-bit
-// broadcast reads).  Per (graph, output): 2*Ch FMAs, 2*Ch/4 LDS.128.
+// broadcast reads), YP_G graphs in flight per thread for instruction-level parallelism.
 #define YP_TJ 8
 #define YP_TB 8
-#define YP_CH 40     /* max supported half-width Ch (2H) */
+#define YP_G 4
+#define YP_THREADS 416     /* >= YP_TJ * C1 (C1 <= 52) */
 template <int CH>
-__global__ void __launch_bounds__(YP_TJ * 64) y_producer_k(const float* __restrict__ a, const float* __restrict__ c,
-                                                           const float* __restrict__ WSa, const float* __restrict__ WSc,
-                                                           const float* __restrict__ Rc, const float* __restrict__ Sa,
-                                                           const float* __restrict__ b0, const float* __restrict__ gam1,
-                                                           const float* __restrict__ bet1, YOut Y, int Bc, int N, int C1) {
+__global__ void __launch_bounds__(YP_THREADS) y_producer_k(const float* __restrict__ a, const float* __restrict__ c,
+                                                          const float* __restrict__ WSa, const float* __restrict__ WSc,
+                                                          const float* __restrict__ Rc, const float* __restrict__ Sa,
+                                                          const float* __restrict__ b0, const float* __restrict__ gam1,
+                                                          const float* __restrict__ bet1, YOut Y, int Bc, int N, int C1) {
   __shared__ __align__(16) float s_a[YP_TB][CH];
   __shared__ __align__(16) float s_c[YP_TB][YP_TJ][CH];
   const int i = blockIdx.y;
   const int j0 = blockIdx.x * YP_TJ;
-  const int tj = threadIdx.x / 64, o = threadIdx.x % 64;      // 64 lanes per j: o < C1 active
+  const int tj = threadIdx.x / C1, o = threadIdx.x - tj * C1;
   const int j = j0 + tj;
-  const bool active = o < C1 && j < N;
+  const bool active = tj < YP_TJ && j < N;
   float wa[CH], wc[CH];
   if (active) {
     const float4* pa = reinterpret_cast<const float4*>(WSa + ((size_t)j * C1 + o) * CH);
@@ -145,7 +146,6 @@ __global__ void __launch_bounds__(YP_TJ * 64) y_producer_k(const float* __restri
   const long long plane = (long long)Bc * N * N;
   for (int bb = 0; bb < Bc; bb += YP_TB) {
     __syncthreads();
-    // stage a[b, i, :] and c[b, j0.., :] for YP_TB graphs
     for (int t = threadIdx.x; t < YP_TB * CH; t += blockDim.x) {
       int tb = t / CH, ch = t - tb * CH;
       s_a[tb][ch] = (bb + tb < Bc) ? a[((long long)(bb + tb) * N + i) * CH + ch] : 0.f;
@@ -156,28 +156,40 @@ __global__ void __launch_bounds__(YP_TJ * 64) y_producer_k(const float* __restri
     }
     __syncthreads();
     if (!active) continue;
-#pragma unroll 2
-    for (int tb = 0; tb < YP_TB; ++tb) {
-      const int b = bb + tb;
-      if (b >= Bc) break;
-      float acc = bb0 + __ldg(Rc + ((long long)b * N + j) * C1 + o) + __ldg(Sa + ((long long)b * N + i) * C1 + o);
-      const float4* xa = reinterpret_cast<const float4*>(&s_a[tb][0]);
-      const float4* xc = reinterpret_cast<const float4*>(&s_c[tb][tj][0]);
+#pragma unroll
+    for (int t0 = 0; t0 < YP_TB; t0 += YP_G) {
+      float acc[YP_G];
+#pragma unroll
+      for (int g = 0; g < YP_G; ++g) {
+        const int b = min(bb + t0 + g, Bc - 1);
+        acc[g] = bb0 + __ldg(Rc + ((long long)b * N + j) * C1 + o) + __ldg(Sa + ((long long)b * N + i) * C1 + o);
+      }
 #pragma unroll
       for (int v = 0; v < CH / 4; ++v) {
-        float4 p = xa[v], q = xc[v];
-        acc = fmaf(p.x, wa[4 * v], acc); acc = fmaf(p.y, wa[4 * v + 1], acc); acc = fmaf(p.z, wa[4 * v + 2], acc); acc = fmaf(p.w, wa[4 * v + 3], acc);
-        acc = fmaf(q.x, wc[4 * v], acc); acc = fmaf(q.y, wc[4 * v + 1], acc); acc = fmaf(q.z, wc[4 * v + 2], acc); acc = fmaf(q.w, wc[4 * v + 3], acc);
+#pragma unroll
+        for (int g = 0; g < YP_G; ++g) {
+          const float4 p = reinterpret_cast<const float4*>(&s_a[t0 + g][0])[v];
+          const float4 q = reinterpret_cast<const float4*>(&s_c[t0 + g][tj][0])[v];
+          acc[g] = fmaf(p.x, wa[4 * v], acc[g]); acc[g] = fmaf(p.y, wa[4 * v + 1], acc[g]);
+          acc[g] = fmaf(p.z, wa[4 * v + 2], acc[g]); acc[g] = fmaf(p.w, wa[4 * v + 3], acc[g]);
+          acc[g] = fmaf(q.x, wc[4 * v], acc[g]); acc[g] = fmaf(q.y, wc[4 * v + 1], acc[g]);
+          acc[g] = fmaf(q.z, wc[4 * v + 2], acc[g]); acc[g] = fmaf(q.w, wc[4 * v + 3], acc[g]);
+        }
       }
-      const long long e0 = ((long long)b * N + i) * N + j, e1 = ((long long)b * N + j) * N + i;
-      Y.E1[e0 * C1 + o] = acc;
-      const float y = fmaxf(fmaf(acc, g1, bt1), 0.f);
-      if (Y.bf16) {
-        __nv_bfloat16 hi, lo; split_bf16(y, hi, lo);
-        Y.Yhi[e0 * Y.CP + o] = hi; Y.Ylo[e0 * Y.CP + o] = lo;
-        Y.Yhi[(plane + e1) * Y.CP + o] = hi; Y.Ylo[(plane + e1) * Y.CP + o] = lo;
-      } else {
-        Y.Yf[e0 * C1 + o] = y; Y.Yf[(plane + e1) * C1 + o] = y;
+#pragma unroll
+      for (int g = 0; g < YP_G; ++g) {
+        const int b = bb + t0 + g;
+        if (b >= Bc) break;
+        const long long e0 = ((long long)b * N + i) * N + j, e1 = ((long long)b * N + j) * N + i;
+        Y.E1[e0 * C1 + o] = acc[g];
+        const float y = fmaxf(fmaf(acc[g], g1, bt1), 0.f);
+        if (Y.bf16) {
+          __nv_bfloat16 hi, lo; split_bf16(y, hi, lo);
+          Y.Yhi[e0 * Y.CP + o] = hi; Y.Ylo[e0 * Y.CP + o] = lo;
+          Y.Yhi[(plane + e1) * Y.CP + o] = hi; Y.Ylo[(plane + e1) * Y.CP + o] = lo;
+        } else {
+          Y.Yf[e0 * C1 + o] = y; Y.Yf[(plane + e1) * C1 + o] = y;
+        }
       }
     }
   }
@@ -264,11 +276,24 @@ struct EpiParams {
   float gscale;           // 1 / (B_global N^2)
 };
 #define EPI_C2 20
-#define EPI_EPT 4
-__global__ void __launch_bounds__(128) edge_epilogue_k(EpiParams P, int Bc, int N) {
+#define EPI_T 16                 /* tile edge: one CTA iteration = 16 x 16 cells of one graph */
+#define EPI_CS 21                /* smem cell stride (floats), odd: conflict-free */
+#define EPI_RS (EPI_T * EPI_CS + 1)   /* smem row stride */
+#define EPI_SMEM_BYTES (2 * EPI_T * EPI_RS * 4 + 2 * EPI_T * EPI_T * 24 * 2)
+// Persistent CTAs loop over tiles.  Both operands are read with coalesced row segments (O1 rows
+// along j, O2^T rows along i), transposed through shared memory; dO planes go back out through
+// shared memory so that both plane layouts are written as contiguous segments.  Gradient sums are
+// accumulated in registers across tiles and reduced once per CTA.
+__global__ void __launch_bounds__(256) edge_epilogue_k(EpiParams P, int Bc, int N) {
   const int C2 = EPI_C2;
-  long long total = (long long)Bc * N * N;
-  long long plane = total;
+  extern __shared__ __align__(16) unsigned char epi_smem[];
+  float* sO1 = reinterpret_cast<float*>(epi_smem);
+  float* sO2 = sO1 + EPI_T * EPI_RS;
+  __nv_bfloat16* sdh = reinterpret_cast<__nv_bfloat16*>(sO2 + EPI_T * EPI_RS);   // [16][16][24]
+  __nv_bfloat16* sdl = sdh + EPI_T * EPI_T * 24;
+  const long long plane = (long long)Bc * N * N;
+  const int nt = (N + EPI_T - 1) / EPI_T;
+  const long long ntiles = (long long)Bc * nt * nt;
   float wme0[EPI_C2], wme1[EPI_C2], gsc[EPI_C2], gsh[EPI_C2], bb[EPI_C2];
 #pragma unroll
   for (int q = 0; q < C2; ++q) {
@@ -276,79 +301,104 @@ __global__ void __launch_bounds__(128) edge_epilogue_k(EpiParams P, int Bc, int 
     gsc[q] = P.gd ? P.gd[q] * BN_RS : 1.f; gsh[q] = P.bd ? P.bd[q] : 0.f;
     bb[q] = 2.f * P.b1[q];
   }
-  float be0 = P.be[0], be1 = P.be[1];
+  const float be0 = P.be[0], be1 = P.be[1];
   float acc_dO[EPI_C2], acc_gg[EPI_C2], acc_gb[EPI_C2], acc_m0[EPI_C2];
 #pragma unroll
   for (int q = 0; q < C2; ++q) { acc_dO[q] = 0.f; acc_gg[q] = 0.f; acc_gb[q] = 0.f; acc_m0[q] = 0.f; }
   float acc_l1 = 0.f, loss = 0.f;
-  long long base = ((long long)blockIdx.x * blockDim.x) * EPI_EPT + threadIdx.x;
-  for (int it = 0; it < EPI_EPT; ++it) {
-    long long e = base + (long long)it * blockDim.x;
-    if (e >= total) break;
-    int j = (int)(e % N); int i = (int)((e / N) % N); long long b = e / ((long long)N * N);
-    long long et = (b * N + j) * N + i;
-    const float4* o1 = reinterpret_cast<const float4*>(P.O12 + e * C2);
-    const float4* o2 = reinterpret_cast<const float4*>(P.O12 + (plane + et) * C2);
-    float O[EPI_C2];
-#pragma unroll
-    for (int v = 0; v < C2 / 4; ++v) {
-      float4 x = o1[v], y = o2[v];
-      O[4 * v] = x.x + y.x + bb[4 * v]; O[4 * v + 1] = x.y + y.y + bb[4 * v + 1];
-      O[4 * v + 2] = x.z + y.z + bb[4 * v + 2]; O[4 * v + 3] = x.w + y.w + bb[4 * v + 3];
+  const int il = threadIdx.x / EPI_T, jl = threadIdx.x % EPI_T;
+  const bool do_bwd = P.backward && P.At;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long b = tile / (nt * nt); const int tr = (int)(tile - b * nt * nt);
+    const int i0 = (tr / nt) * EPI_T, j0 = (tr % nt) * EPI_T;
+    __syncthreads();
+    // coalesced loads: 16 row segments of 16 cells x 20 floats for each operand
+    for (int f = threadIdx.x; f < EPI_T * EPI_T * C2; f += blockDim.x) {
+      const int r = f / (EPI_T * C2), w = f - r * (EPI_T * C2); const int cl = w / C2, q = w - cl * C2;
+      float v1 = 0.f, v2 = 0.f;
+      if (i0 + r < N && j0 + cl < N) v1 = P.O12[(((long long)b * N + i0 + r) * N + j0 + cl) * C2 + q];
+      if (j0 + r < N && i0 + cl < N) v2 = P.O12[(plane + ((long long)b * N + j0 + r) * N + i0 + cl) * C2 + q];
+      sO1[r * EPI_RS + cl * EPI_CS + q] = v1;       // [i][j][q]
+      sO2[r * EPI_RS + cl * EPI_CS + q] = v2;       // [j][i][q]
     }
-    float l0 = be0, l1 = be1;
-    float Z[EPI_C2];
+    __syncthreads();
+    const int i = i0 + il, j = j0 + jl;
+    const bool valid = i < N && j < N;
+    float dOv[EPI_C2];
 #pragma unroll
-    for (int q = 0; q < C2; ++q) {
-      float z = fmaxf(fmaf(O[q], gsc[q], gsh[q]), 0.f);
-      Z[q] = z; l0 = fmaf(z, wme0[q], l0); l1 = fmaf(z, wme1[q], l1);
-    }
-    float m = (i == j) ? 0.f : 1.f;
-    float p0 = m * l0 + (1.f - m), p1 = m * l1;           // model.py:205-206
-    if (P.logits) { P.logits[e * 2] = p0; P.logits[e * 2 + 1] = p1; }
-    float mx = fmaxf(p0, p1);
-    float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
-    float s = e0 + e1;
-    float s1 = e1 / s;
-    if (P.gen_adj) P.gen_adj[e] = threshold_rule(p0, p1); // tf.argmax: first index on ties
-    if (P.At) {
-      float A = P.At[e];
-      float lse = mx + logf(s);
-      loss += lse - ((1.f - A) * p0 + A * p1);
-      if (P.backward) {
-        float d1 = m * (s1 - A) * P.gscale;               // dL/dl1 = -dL/dl0
-        acc_l1 += d1;
-        float dOv[EPI_C2];
+    for (int q = 0; q < C2; ++q) dOv[q] = 0.f;
+    if (valid) {
+      const long long e = ((long long)b * N + i) * N + j, et = ((long long)b * N + j) * N + i;
+      float O[EPI_C2], Z[EPI_C2];
+      float l0 = be0, l1 = be1;
 #pragma unroll
-        for (int q = 0; q < C2; ++q) {
-          acc_m0[q] = fmaf(Z[q], d1, acc_m0[q]);          // dMe[q,1] = +, dMe[q,0] = -
-          float dz = d1 * (wme1[q] - wme0[q]);
-          float dd = Z[q] > 0.f ? dz : 0.f;
-          acc_gg[q] = fmaf(dd, O[q], acc_gg[q]); acc_gb[q] += dd;
-          float d = dd * gsc[q];
-          dOv[q] = d; acc_dO[q] += d;
+      for (int q = 0; q < C2; ++q) {
+        O[q] = sO1[il * EPI_RS + jl * EPI_CS + q] + sO2[jl * EPI_RS + il * EPI_CS + q] + bb[q];
+        const float z = fmaxf(fmaf(O[q], gsc[q], gsh[q]), 0.f);
+        Z[q] = z; l0 = fmaf(z, wme0[q], l0); l1 = fmaf(z, wme1[q], l1);
+      }
+      const float m = (i == j) ? 0.f : 1.f;
+      const float p0 = m * l0 + (1.f - m), p1 = m * l1;         // model.py:205-206
+      if (P.logits) { P.logits[e * 2] = p0; P.logits[e * 2 + 1] = p1; }
+      if (P.gen_adj) P.gen_adj[e] = threshold_rule(p0, p1);     // tf.argmax: first index on ties
+      if (P.At) {
+        const float mx = fmaxf(p0, p1);
+        const float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
+        const float sden = e0 + e1;
+        const float s1 = e1 / sden;
+        const float A = P.At[e];
+        loss += mx + logf(sden) - ((1.f - A) * p0 + A * p1);
+        if (P.backward) {
+          const float d1 = m * (s1 - A) * P.gscale;             // dL/dl1 = -dL/dl0
+          acc_l1 += d1;
+#pragma unroll
+          for (int q = 0; q < C2; ++q) {
+            acc_m0[q] = fmaf(Z[q], d1, acc_m0[q]);              // dMe[q,1] = +, dMe[q,0] = -
+            const float dz = d1 * (wme1[q] - wme0[q]);
+            const float dd = Z[q] > 0.f ? dz : 0.f;
+            acc_gg[q] = fmaf(dd, O[q], acc_gg[q]); acc_gb[q] += dd;
+            const float d = dd * gsc[q];
+            dOv[q] = d; acc_dO[q] += d;
+          }
+          if (!P.bf16) {
+            float* f0 = P.dOf + e * C2; float* f1 = P.dOf + (plane + et) * C2;
+#pragma unroll
+            for (int q = 0; q < C2; ++q) { f0[q] = dOv[q]; f1[q] = dOv[q]; }
+          }
         }
-        if (P.bf16) {
-          __nv_bfloat16 hi[EPI_C2], lo[EPI_C2];
+      }
+    }
+    if (do_bwd && P.bf16) {
+      // stage the tile's dO as bf16 hi / lo (pad channels zero), then write both layouts as row segments
+      __nv_bfloat16* ch = sdh + (il * EPI_T + jl) * 24; __nv_bfloat16* cl = sdl + (il * EPI_T + jl) * 24;
 #pragma unroll
-          for (int q = 0; q < C2; ++q) split_bf16(dOv[q], hi[q], lo[q]);
-          __nv_bfloat16* h0 = P.dOhi + e * P.OP; __nv_bfloat16* l0p = P.dOlo + e * P.OP;
-          __nv_bfloat16* h1 = P.dOhi + (plane + et) * P.OP; __nv_bfloat16* l1p = P.dOlo + (plane + et) * P.OP;
-#pragma unroll
-          for (int q = 0; q < C2; ++q) { h0[q] = hi[q]; l0p[q] = lo[q]; h1[q] = hi[q]; l1p[q] = lo[q]; }
-        } else {
-          float* f0 = P.dOf + e * C2; float* f1 = P.dOf + (plane + et) * C2;
-#pragma unroll
-          for (int q = 0; q < C2; ++q) { f0[q] = dOv[q]; f1[q] = dOv[q]; }
+      for (int q = 0; q < 24; ++q) {
+        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
+        if (q < C2) split_bf16(dOv[q], hi, lo);
+        ch[q] = hi; cl[q] = lo;
+      }
+      __syncthreads();
+      const uint32_t* wh = reinterpret_cast<const uint32_t*>(sdh); const uint32_t* wl = reinterpret_cast<const uint32_t*>(sdl);
+      uint32_t* gh = reinterpret_cast<uint32_t*>(P.dOhi); uint32_t* gl = reinterpret_cast<uint32_t*>(P.dOlo);
+      const int WPC = P.OP / 2;                                 // 32-bit words per cell (12)
+      for (int f = threadIdx.x; f < EPI_T * EPI_T * 12; f += blockDim.x) {
+        const int r = f / (EPI_T * 12), w = f - r * (EPI_T * 12); const int c2 = w / 12, ww = w - c2 * 12;
+        if (i0 + r < N && j0 + c2 < N) {       // layout 0: row (b, i0+r), cells j0..
+          const long long g = ((((long long)b * N + i0 + r) * N + j0 + c2) * WPC) + ww;
+          gh[g] = wh[(r * EPI_T + c2) * 12 + ww]; gl[g] = wl[(r * EPI_T + c2) * 12 + ww];
+        }
+        if (j0 + r < N && i0 + c2 < N) {       // layout 1: row (b, j0+r), cells i0..
+          const long long g = (((plane + ((long long)b * N + j0 + r) * N + i0 + c2)) * WPC) + ww;
+          gh[g] = wh[(c2 * EPI_T + r) * 12 + ww]; gl[g] = wl[(c2 * EPI_T + r) * 12 + ww];
         }
       }
     }
   }
-  // reductions: warp shuffle, then one atomic per warp and value
-  int lane = threadIdx.x & 31;
+  // reductions: warp shuffle, then one atomic per warp and value (once per CTA)
+  const int lane = threadIdx.x & 31;
   loss = warp_sum(loss);
   if (lane == 0 && P.loss_sum && P.At) atomicAdd(P.loss_sum, loss);
-  if (P.backward && P.At) {
+  if (do_bwd) {
     acc_l1 = warp_sum(acc_l1);
     if (lane == 0) { atomicAdd(P.g_be + 1, acc_l1); atomicAdd(P.g_be, -acc_l1); }
 #pragma unroll

@@ -541,9 +541,9 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     mark(h, "y_producer");
     YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = TC_CP; Y.bf16 = tc;
     { dim3 yg(cdiv(N, YP_TJ), N);
-      if (Chv == 40) LAUNCH(y_producer_k<40>, yg, YP_TJ * 64, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
+      if (Chv == 40) LAUNCH(y_producer_k<40>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
                             h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
-      else LAUNCH(y_producer_k<20>, yg, YP_TJ * 64, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
+      else LAUNCH(y_producer_k<20>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
                   h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1); }
     mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
@@ -563,7 +563,9 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     ep.g_b1 = h->G + p.e_b[1]; ep.g_gd = h->dis ? h->G + p.decadj_g : nullptr; ep.g_bd = h->dis ? h->G + p.decadj_b : nullptr;
     ep.g_Me = h->G + p.d_e_lin2[0]; ep.g_be = h->G + p.d_e_lin2[1];
     ep.gscale = 1.f / (gB * N * N);
-    LAUNCH(edge_epilogue_k, cdiv(cells, 128 * EPI_EPT), 128, 0, ep, bc, N);
+    { long long ntile = (long long)bc * cdiv(N, EPI_T) * cdiv(N, EPI_T);
+      unsigned grid = (unsigned)(ntile < 148 * 3 ? ntile : 148 * 3);
+      LAUNCH(edge_epilogue_k, grid, 256, EPI_SMEM_BYTES, ep, bc, N); }
     if (!backward) continue;
     // backward of e2e layer 1: dgrad + wgrad
     mark(h, "gemm_dgrad");
@@ -829,6 +831,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
   h->hf_features = nullptr;
+  cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
   h->stt.used = 0; h->stt.on = getenv("SNDVAE_STAGE_TIMING") != nullptr;
   sndvae_config& c = h->cfg;
   if (c.num_nodes < 2 || c.batch_size < 1 || c.num_feature < 1 || c.spatial_dim < 1 || c.node_h_size < 1)
@@ -838,7 +841,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
   if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);
-  if (c.node_h_size != 20 || c.e_d_hidden[0] > 64) return fail(h, SNDVAE_E_ARG, "this build supports node_h_size = 20 and e_d_hidden[0] <= 64 (synthetic2, main.py:209)");
+  if (c.node_h_size != 20 || c.e_d_hidden[0] > 52) return fail(h, SNDVAE_E_ARG, "this build supports node_h_size = 20 and e_d_hidden[0] <= 52 (synthetic2, main.py:209)");
   if (c.g_conv_hidden[0] > 32 || c.g_conv_hidden[1] > 32) return fail(h, SNDVAE_E_ARG, "g_conv_hidden must be <= 32");
   h->N = c.num_nodes; h->F = c.num_feature; h->D = c.spatial_dim; h->S = c.sampling_num; h->H = c.node_h_size;
   h->Chv = h->dis ? 2 * h->H : h->H; h->C1 = c.e_d_hidden[0]; h->C2 = c.e_d_hidden[1];
