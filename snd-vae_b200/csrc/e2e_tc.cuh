@@ -26,8 +26,8 @@
 
 #define TC_C1 50      /* e2e layer-1 input channels  */
 #define TC_C2 20      /* e2e layer-1 output channels */
-#define TC_CP 56      /* channel stride of Y planes   (112 B: TMA strides need 16 B multiples) */
-#define TC_OP 24      /* channel stride of dO planes  (48 B) */
+#define TC_CP 56      /* padded channel stride of Y planes  (112 B: TMA strides need 16 B multiples); compact = 50 */
+#define TC_OP 24      /* padded channel stride of dO planes (48 B); compact = 20 */
 #define TC_BM 128
 #define TC_KC 64      /* K elements per stage = one 128-byte swizzle row */
 #define TC_STAGES 2
@@ -134,20 +134,23 @@ struct ToepArgs {
   int pad_rows;        // zero rows in front of the padded weights (N-1-p fwd, p dgrad)
   int KA;              // K extent = N*CS
   int accumulate;      // out += result instead of out = result
+  int nsh;             // shifted weight copies: tile row n = (r, ch, u), position jr = jr0 + u*nsh + r
 };
+struct TMapSet { CUtensorMap h[4]; CUtensorMap l[4]; };   // window views of the nsh shifted copies (hi / lo)
 
 // Two-level accumulation.  tcgen05.mma adds into its fp32 TMEM accumulator with truncation
 // (measured here: a systematic shrink of ~1.7e-8 per accumulate, -4.5e-5 over the 2688 accumulates
 // of one N=256 output), so the K loop is cut into groups of TC_GROUP chunks: each group accumulates
 // into one of two TMEM slots, and the epilogue warps drain the finished slot into round-to-nearest
 // fp32 registers while the tensor pipe fills the other slot.
+#ifndef TC_GROUP
 #define TC_GROUP 8
+#endif
 #define TC_EPI_WARPS 8
 #define TC_THREADS (64 + 32 * TC_EPI_WARPS)
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-                                                             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-                                                             ToepArgs P) {
+                                                             const __grid_constant__ TMapSet tmB, ToepArgs P) {
   constexpr int A_BYTES = TC_BM * TC_KC * 2;       // 16 KB
   constexpr int B_BYTES = BN * TC_KC * 2;          // 30 KB at BN = 240
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -196,8 +199,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
         const int x = (kc_lo + it) * TC_KC;
         tma_load_2d(st, &tmAh, &full_bar[s], x, m0);
         tma_load_2d(st + A_BYTES, &tmAl, &full_bar[s], x, m0);
-        tma_load_3d(st + 2 * A_BYTES, &tmBh, &full_bar[s], x, jr0, ch0);
-        tma_load_3d(st + 2 * A_BYTES + B_BYTES, &tmBl, &full_bar[s], x, jr0, ch0);
+        // B tile rows = (shift r, channel, u): one sub-box per shifted copy, 128-byte rows, contiguous
+        const int sub = B_BYTES / P.nsh, u0 = jr0 / P.nsh;
+        for (int r = 0; r < P.nsh; ++r) {
+          tma_load_3d(st + 2 * A_BYTES + r * sub, &tmB.h[r], &full_bar[s], x, u0, ch0);
+          tma_load_3d(st + 2 * A_BYTES + B_BYTES + r * sub, &tmB.l[r], &full_bar[s], x, u0, ch0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -254,7 +261,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
         const int n = half * HC + i;
-        const int chl = n / P.JT, jr = jr0 + n - chl * P.JT;
+        const int jts = P.JT / P.nsh, per = P.CT * jts;
+        const int r = n / per, w = n - r * per;
+        const int chl = w / jts, u = w - chl * jts;
+        const int jr = jr0 + u * P.nsh + r;
         const int j = P.N - 1 - jr;
         if (j >= 0) {
           float* dst = orow + (long long)j * P.Cout + ch0 + chl;
@@ -418,20 +428,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
 // ------------------------------------------------------------------------------------------
 __global__ void tc_stage_weights_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ Wfh, __nv_bfloat16* __restrict__ Wfl,
                                    __nv_bfloat16* __restrict__ Wdh, __nv_bfloat16* __restrict__ Wdl, int N, int Ctot, int coff,
-                                   int Cin, int Cout, int CSi, int CSo) {
+                                   int Cin, int Cout, int CSi, int CSo, int nsf, int nsd, long long LFp, long long LDp) {
+  // copy r of the forward weights is shifted by r positions: Wf_r[q][y] = Wf[q][y + r*CSi] (16-byte aligned window starts)
   const int p = (N - 1) / 2;
-  const long long LF = (long long)(2 * N - 1) * CSi, LD = (long long)(2 * N - 1) * CSo;
-  const long long nf = (long long)Cout * LF, nd = (long long)Cin * LD;
+  const long long nf = (long long)nsf * Cout * LFp, nd = (long long)nsd * Cin * LDp;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < nf) {
-    int q = (int)(idx / LF); long long x = idx - q * LF; int rho = (int)(x / CSi), c = (int)(x - (long long)rho * CSi);
+    int r = (int)(idx / (Cout * LFp)); long long rem = idx - (long long)r * Cout * LFp;
+    int q = (int)(rem / LFp); long long x = rem - q * LFp + (long long)r * CSi;
+    int rho = (int)(x / CSi), c = (int)(x - (long long)rho * CSi);
     int t = rho - (N - 1 - p);
     float v = (c < Cin && t >= 0 && t < N) ? w[((size_t)t * Ctot + coff + c) * Cout + q] : 0.f;
     __nv_bfloat16 hi = __float2bfloat16_rn(v);
     Wfh[idx] = hi; Wfl[idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
   } else if (idx < nf + nd) {
     idx -= nf;
-    int c = (int)(idx / LD); long long x = idx - c * LD; int rho = (int)(x / CSo), q = (int)(x - (long long)rho * CSo);
+    int r = (int)(idx / (Cin * LDp)); long long rem = idx - (long long)r * Cin * LDp;
+    int c = (int)(rem / LDp); long long x = rem - c * LDp + (long long)r * CSo;
+    int rho = (int)(x / CSo), q = (int)(x - (long long)rho * CSo);
     int t = N - 1 + p - rho;
     float v = (q < Cout && t >= 0 && t < N) ? w[((size_t)t * Ctot + coff + c) * Cout + q] : 0.f;
     __nv_bfloat16 hi = __float2bfloat16_rn(v);
@@ -461,8 +475,10 @@ static PFN_encodeTiled g_tc_encode = nullptr;
 struct ToepPlan {
   int ready, N, Cin, Cout, CSi, CSo;
   int fCT, fJT, dCT, dJT;                  // tile shapes (channels x positions, product 240)
-  __nv_bfloat16 *Wfh, *Wfl, *Wdh, *Wdl;    // staged weights
-  CUtensorMap fB_h, fB_l, dB_h, dB_l;      // window views of the staged weights
+  int nsf, nsd;                            // shifted weight copies (window starts must be 16-byte aligned)
+  long long LFp, LDp;                      // padded row lengths of the staged weights
+  __nv_bfloat16 *Wfh, *Wfl, *Wdh, *Wdl;    // staged weights [nsh][channels][Lp]
+  TMapSet fB, dB;                          // window views of the staged weights
 };
 struct TcState {                           // all tensor-core products of the edge decoder
   int ready;
@@ -498,30 +514,43 @@ static int tc_global_init() {
   return 0;
 }
 static int tc_pad16(int c) { return (c * 2) % 16 == 0 ? c : (c + 7) / 8 * 8; }   // channel stride with 16-byte rows
+static int tc_gcd(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+// channel stride of a plane with C channels: compact (C) when the rows stay 16-byte aligned and the tile's position
+// count is a multiple of the number of shifted weight copies that compact windows need; padded to 8 otherwise
+static int tc_stride(int N, int C, int JT, int compact) {
+  if (compact && ((long long)N * C * 2) % 16 == 0) { int nsh = 16 / tc_gcd(16, C * 2); if (nsh <= 4 && JT % nsh == 0) return C; }
+  return tc_pad16(C);
+}
 
-static int tc_plan_init(ToepPlan& pl, int N, int Cin, int Cout, int fCT, int fJT, int dCT, int dJT, cudaStream_t st) {
+static int tc_plan_init(ToepPlan& pl, int N, int Cin, int Cout, int fCT, int fJT, int dCT, int dJT, int compact, cudaStream_t st) {
   memset(&pl, 0, sizeof pl);
-  pl.N = N; pl.Cin = Cin; pl.Cout = Cout; pl.CSi = tc_pad16(Cin); pl.CSo = tc_pad16(Cout);
+  pl.N = N; pl.Cin = Cin; pl.Cout = Cout;
+  pl.CSi = tc_stride(N, Cin, fJT, compact); pl.CSo = tc_stride(N, Cout, dJT, compact);
+  pl.nsf = 16 / tc_gcd(16, pl.CSi * 2); pl.nsd = 16 / tc_gcd(16, pl.CSo * 2);
   pl.fCT = fCT; pl.fJT = fJT; pl.dCT = dCT; pl.dJT = dJT;
-  if (fCT * fJT != 240 || dCT * dJT != 240 || Cout % fCT || Cin % dCT) { snprintf(g_tc_err, sizeof g_tc_err, "bad tile shape"); return -1; }
-  const long long LF = (long long)(2 * N - 1) * pl.CSi, LD = (long long)(2 * N - 1) * pl.CSo;
-  size_t nf = (size_t)Cout * LF + 2 * TC_KC, nd = (size_t)Cin * LD + 2 * TC_KC;
+  if (fCT * fJT != 240 || dCT * dJT != 240 || Cout % fCT || Cin % dCT || fJT % pl.nsf || dJT % pl.nsd) { snprintf(g_tc_err, sizeof g_tc_err, "bad tile shape"); return -1; }
+  pl.LFp = ((long long)(2 * N - 1 + 4) * pl.CSi + 7) / 8 * 8; pl.LDp = ((long long)(2 * N - 1 + 4) * pl.CSo + 7) / 8 * 8;
+  size_t nf = (size_t)pl.nsf * Cout * pl.LFp + 2 * TC_KC, nd = (size_t)pl.nsd * Cin * pl.LDp + 2 * TC_KC;
   if (cudaMalloc(&pl.Wfh, nf * 2) || cudaMalloc(&pl.Wfl, nf * 2) || cudaMalloc(&pl.Wdh, nd * 2) || cudaMalloc(&pl.Wdl, nd * 2)) {
     snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of staged weights failed"); return -1;
   }
   cudaMemsetAsync(pl.Wfh, 0, nf * 2, st); cudaMemsetAsync(pl.Wfl, 0, nf * 2, st);
   cudaMemsetAsync(pl.Wdh, 0, nd * 2, st); cudaMemsetAsync(pl.Wdl, 0, nd * 2, st);
-  {   // window views: dims (x, jr, ch), strides (CS*2, L*2) bytes -- the jr stride is smaller than the x extent
-    cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSi, (cuuint64_t)N, (cuuint64_t)Cout};
-    cuuint64_t str[2] = {(cuuint64_t)pl.CSi * 2, (cuuint64_t)LF * 2};
-    cuuint32_t box[3] = {TC_KC, (cuuint32_t)fJT, (cuuint32_t)fCT};
-    if (tc_encode(&pl.fB_h, pl.Wfh, 3, dims, str, box) || tc_encode(&pl.fB_l, pl.Wfl, 3, dims, str, box)) return -1;
+  // window views: dims (x, u, ch) with position jr = u*nsh + r; strides (nsh*CS*2, Lp*2) bytes -- the position stride is
+  // smaller than the x extent, so consecutive tile rows are overlapping windows of one weight row
+  for (int r = 0; r < pl.nsf; ++r) {
+    cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSi, (cuuint64_t)((N - r + pl.nsf - 1) / pl.nsf), (cuuint64_t)Cout};
+    cuuint64_t str[2] = {(cuuint64_t)pl.nsf * pl.CSi * 2, (cuuint64_t)pl.LFp * 2};
+    cuuint32_t box[3] = {TC_KC, (cuuint32_t)(fJT / pl.nsf), (cuuint32_t)fCT};
+    if (tc_encode(&pl.fB.h[r], pl.Wfh + (size_t)r * Cout * pl.LFp, 3, dims, str, box) ||
+        tc_encode(&pl.fB.l[r], pl.Wfl + (size_t)r * Cout * pl.LFp, 3, dims, str, box)) return -1;
   }
-  {
-    cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSo, (cuuint64_t)N, (cuuint64_t)Cin};
-    cuuint64_t str[2] = {(cuuint64_t)pl.CSo * 2, (cuuint64_t)LD * 2};
-    cuuint32_t box[3] = {TC_KC, (cuuint32_t)dJT, (cuuint32_t)dCT};
-    if (tc_encode(&pl.dB_h, pl.Wdh, 3, dims, str, box) || tc_encode(&pl.dB_l, pl.Wdl, 3, dims, str, box)) return -1;
+  for (int r = 0; r < pl.nsd; ++r) {
+    cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSo, (cuuint64_t)((N - r + pl.nsd - 1) / pl.nsd), (cuuint64_t)Cin};
+    cuuint64_t str[2] = {(cuuint64_t)pl.nsd * pl.CSo * 2, (cuuint64_t)pl.LDp * 2};
+    cuuint32_t box[3] = {TC_KC, (cuuint32_t)(dJT / pl.nsd), (cuuint32_t)dCT};
+    if (tc_encode(&pl.dB.h[r], pl.Wdh + (size_t)r * Cin * pl.LDp, 3, dims, str, box) ||
+        tc_encode(&pl.dB.l[r], pl.Wdl + (size_t)r * Cin * pl.LDp, 3, dims, str, box)) return -1;
   }
   pl.ready = 1;
   return 0;
@@ -537,8 +566,9 @@ static int tc_check_launch(const char* what) {
 }
 static int tc_plan_stage(ToepPlan& pl, const float* w, int Ctot, int coff, cudaStream_t st) {
   if (!pl.ready) { snprintf(g_tc_err, sizeof g_tc_err, "plan not initialised"); return -1; }
-  long long total = (long long)pl.Cout * (2 * pl.N - 1) * pl.CSi + (long long)pl.Cin * (2 * pl.N - 1) * pl.CSo;
-  tc_stage_weights_k<<<cdiv(total, 256), 256, 0, st>>>(w, pl.Wfh, pl.Wfl, pl.Wdh, pl.Wdl, pl.N, Ctot, coff, pl.Cin, pl.Cout, pl.CSi, pl.CSo);
+  long long total = (long long)pl.nsf * pl.Cout * pl.LFp + (long long)pl.nsd * pl.Cin * pl.LDp;
+  tc_stage_weights_k<<<cdiv(total, 256), 256, 0, st>>>(w, pl.Wfh, pl.Wfl, pl.Wdh, pl.Wdl, pl.N, Ctot, coff, pl.Cin, pl.Cout, pl.CSi, pl.CSo,
+                                                      pl.nsf, pl.nsd, pl.LFp, pl.LDp);
   return tc_check_launch("tc_stage_weights_k");
 }
 static int tc_split(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long long rows, int C, int CS, cudaStream_t st) {
@@ -555,9 +585,9 @@ static int tc_plan_fwd(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat
   if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM)) return -1;
   ToepArgs a; a.out = out; a.rows = rows; a.N = pl.N; a.Cout = pl.Cout; a.CS = pl.CSi; a.CT = pl.fCT; a.JT = pl.fJT;
   a.n_ctiles = pl.Cout / pl.fCT; a.n_jtiles = (pl.N + pl.fJT - 1) / pl.fJT; a.pad_rows = pl.N - 1 - (pl.N - 1) / 2; a.KA = pl.N * pl.CSi;
-  a.accumulate = accumulate;
+  a.accumulate = accumulate; a.nsh = pl.nsf;
   unsigned grid = (unsigned)(((rows + TC_BM - 1) / TC_BM) * a.n_ctiles * a.n_jtiles);
-  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.fB_h, pl.fB_l, a);
+  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.fB, a);
   return tc_check_launch("toep_gemm_k(fwd)");
 }
 // din[rows, N*Cin] (+)= dout[rows, N*CSo planes] . Toeplitz(w)^T
@@ -567,9 +597,9 @@ static int tc_plan_dgrad(ToepPlan& pl, const __nv_bfloat16* doh, const __nv_bflo
   if (tc_encode_rows(&ah, doh, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM) || tc_encode_rows(&al, dol, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM)) return -1;
   ToepArgs a; a.out = din; a.rows = rows; a.N = pl.N; a.Cout = pl.Cin; a.CS = pl.CSo; a.CT = pl.dCT; a.JT = pl.dJT;
   a.n_ctiles = pl.Cin / pl.dCT; a.n_jtiles = (pl.N + pl.dJT - 1) / pl.dJT; a.pad_rows = (pl.N - 1) / 2; a.KA = pl.N * pl.CSo;
-  a.accumulate = accumulate;
+  a.accumulate = accumulate; a.nsh = pl.nsd;
   unsigned grid = (unsigned)(((rows + TC_BM - 1) / TC_BM) * a.n_ctiles * a.n_jtiles);
-  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.dB_h, pl.dB_l, a);
+  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.dB, a);
   return tc_check_launch("toep_gemm_k(dgrad)");
 }
 // dw[t, coff+c, q] += sum_rows sum_j in[row, j+t-p, c] dout[row, j, q]
@@ -593,9 +623,10 @@ static int tc_plan_wgrad(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bflo
 static int tc_init(TcState& s, int N, int Chv, long long B, cudaStream_t st) {
   memset(&s, 0, sizeof s);
   if (tc_global_init()) return -1;
-  if (tc_plan_init(s.l1, N, TC_C1, TC_C2, 20, 12, 10, 24, st)) return -1;
-  if (tc_plan_init(s.l0a, N, Chv, TC_C1, 10, 24, 10, 24, st)) return -1;
-  if (tc_plan_init(s.l0c, N, Chv, TC_C1, 10, 24, 10, 24, st)) return -1;
+  const int compact = getenv("SNDVAE_TC_PADDED") ? 0 : 1;      // compact channel strides cut the padded-K MMA work
+  if (tc_plan_init(s.l1, N, TC_C1, TC_C2, 20, 12, 10, 24, compact, st)) return -1;
+  if (tc_plan_init(s.l0a, N, Chv, TC_C1, 10, 24, 10, 24, 0, st)) return -1;
+  if (tc_plan_init(s.l0c, N, Chv, TC_C1, 10, 24, 10, 24, 0, st)) return -1;
   size_t ni = (size_t)B * N * s.l0a.CSi, no = (size_t)B * N * s.l0a.CSo;
   __nv_bfloat16** ps[8] = {&s.ah, &s.al, &s.ch, &s.cl, &s.dsh, &s.dsl, &s.drh, &s.drl};
   for (int i = 0; i < 8; ++i) {

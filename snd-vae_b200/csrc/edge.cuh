@@ -284,7 +284,7 @@ struct EpiParams {
 // along j, O2^T rows along i), transposed through shared memory; dO planes go back out through
 // shared memory so that both plane layouts are written as contiguous segments.  Gradient sums are
 // accumulated in registers across tiles and reduced once per CTA.
-__global__ void __launch_bounds__(256) edge_epilogue_k(EpiParams P, int Bc, int N) {
+__global__ void __launch_bounds__(256, 2) edge_epilogue_k(EpiParams P, int Bc, int N) {
   const int C2 = EPI_C2;
   extern __shared__ __align__(16) unsigned char epi_smem[];
   float* sO1 = reinterpret_cast<float*>(epi_smem);
@@ -294,13 +294,14 @@ __global__ void __launch_bounds__(256) edge_epilogue_k(EpiParams P, int Bc, int 
   const long long plane = (long long)Bc * N * N;
   const int nt = (N + EPI_T - 1) / EPI_T;
   const long long ntiles = (long long)Bc * nt * nt;
-  float wme0[EPI_C2], wme1[EPI_C2], gsc[EPI_C2], gsh[EPI_C2], bb[EPI_C2];
-#pragma unroll
-  for (int q = 0; q < C2; ++q) {
+  __shared__ float wme0[EPI_C2], wme1[EPI_C2], gsc[EPI_C2], gsh[EPI_C2], bb[EPI_C2];   // broadcast reads
+  if (threadIdx.x < C2) {
+    const int q = threadIdx.x;
     wme0[q] = P.Me[q * 2]; wme1[q] = P.Me[q * 2 + 1];
     gsc[q] = P.gd ? P.gd[q] * BN_RS : 1.f; gsh[q] = P.bd ? P.bd[q] : 0.f;
     bb[q] = 2.f * P.b1[q];
   }
+  __syncthreads();
   const float be0 = P.be[0], be1 = P.be[1];
   float acc_dO[EPI_C2], acc_gg[EPI_C2], acc_gb[EPI_C2], acc_m0[EPI_C2];
 #pragma unroll
@@ -324,18 +325,16 @@ __global__ void __launch_bounds__(256) edge_epilogue_k(EpiParams P, int Bc, int 
     __syncthreads();
     const int i = i0 + il, j = j0 + jl;
     const bool valid = i < N && j < N;
-    float dOv[EPI_C2];
-#pragma unroll
-    for (int q = 0; q < C2; ++q) dOv[q] = 0.f;
+    __nv_bfloat16* ch = sdh + (il * EPI_T + jl) * P.OP; __nv_bfloat16* cl = sdl + (il * EPI_T + jl) * P.OP;
+    const float* c1 = sO1 + il * EPI_RS + jl * EPI_CS; const float* c2 = sO2 + jl * EPI_RS + il * EPI_CS;
+    float d1 = 0.f;                                          // dL/dl1 = -dL/dl0 of this cell
     if (valid) {
-      const long long e = ((long long)b * N + i) * N + j, et = ((long long)b * N + j) * N + i;
-      float O[EPI_C2], Z[EPI_C2];
+      const long long e = ((long long)b * N + i) * N + j;
       float l0 = be0, l1 = be1;
 #pragma unroll
       for (int q = 0; q < C2; ++q) {
-        O[q] = sO1[il * EPI_RS + jl * EPI_CS + q] + sO2[jl * EPI_RS + il * EPI_CS + q] + bb[q];
-        const float z = fmaxf(fmaf(O[q], gsc[q], gsh[q]), 0.f);
-        Z[q] = z; l0 = fmaf(z, wme0[q], l0); l1 = fmaf(z, wme1[q], l1);
+        const float z = fmaxf(fmaf(c1[q] + c2[q] + bb[q], gsc[q], gsh[q]), 0.f);
+        l0 = fmaf(z, wme0[q], l0); l1 = fmaf(z, wme1[q], l1);
       }
       const float m = (i == j) ? 0.f : 1.f;
       const float p0 = m * l0 + (1.f - m), p1 = m * l1;         // model.py:205-206
@@ -345,51 +344,44 @@ __global__ void __launch_bounds__(256) edge_epilogue_k(EpiParams P, int Bc, int 
         const float mx = fmaxf(p0, p1);
         const float e0 = expf(p0 - mx), e1 = expf(p1 - mx);
         const float sden = e0 + e1;
-        const float s1 = e1 / sden;
         const float A = P.At[e];
         loss += mx + logf(sden) - ((1.f - A) * p0 + A * p1);
-        if (P.backward) {
-          const float d1 = m * (s1 - A) * P.gscale;             // dL/dl1 = -dL/dl0
-          acc_l1 += d1;
+        d1 = m * (e1 / sden - A) * P.gscale;
+      }
+    }
+    if (do_bwd) {
+      acc_l1 += d1;
+      const long long e = ((long long)b * N + i) * N + j, et = ((long long)b * N + j) * N + i;
 #pragma unroll
-          for (int q = 0; q < C2; ++q) {
-            acc_m0[q] = fmaf(Z[q], d1, acc_m0[q]);              // dMe[q,1] = +, dMe[q,0] = -
-            const float dz = d1 * (wme1[q] - wme0[q]);
-            const float dd = Z[q] > 0.f ? dz : 0.f;
-            acc_gg[q] = fmaf(dd, O[q], acc_gg[q]); acc_gb[q] += dd;
-            const float d = dd * gsc[q];
-            dOv[q] = d; acc_dO[q] += d;
-          }
-          if (!P.bf16) {
-            float* f0 = P.dOf + e * C2; float* f1 = P.dOf + (plane + et) * C2;
-#pragma unroll
-            for (int q = 0; q < C2; ++q) { f0[q] = dOv[q]; f1[q] = dOv[q]; }
-          }
-        }
+      for (int q = 0; q < C2; ++q) {
+        const float o = c1[q] + c2[q] + bb[q];
+        const float z = fmaxf(fmaf(o, gsc[q], gsh[q]), 0.f);
+        acc_m0[q] = fmaf(z, d1, acc_m0[q]);                   // dMe[q,1] = +, dMe[q,0] = -
+        const float dd = z > 0.f ? d1 * (wme1[q] - wme0[q]) : 0.f;
+        acc_gg[q] = fmaf(dd, o, acc_gg[q]); acc_gb[q] += dd;
+        const float d = dd * gsc[q];
+        acc_dO[q] += d;
+        if (P.bf16) { __nv_bfloat16 hi, lo; split_bf16(d, hi, lo); ch[q] = hi; cl[q] = lo; }
+        else if (valid) { P.dOf[e * C2 + q] = d; P.dOf[(plane + et) * C2 + q] = d; }
       }
     }
     if (do_bwd && P.bf16) {
-      // stage the tile's dO as bf16 hi / lo (pad channels zero), then write both layouts as row segments
-      __nv_bfloat16* ch = sdh + (il * EPI_T + jl) * 24; __nv_bfloat16* cl = sdl + (il * EPI_T + jl) * 24;
+      // dO staged as bf16 hi / lo (pad channels zero); both plane layouts are written as row segments
 #pragma unroll
-      for (int q = 0; q < 24; ++q) {
-        __nv_bfloat16 hi = __float2bfloat16_rn(0.f), lo = hi;
-        if (q < C2) split_bf16(dOv[q], hi, lo);
-        ch[q] = hi; cl[q] = lo;
-      }
+      for (int q = C2; q < P.OP; ++q) { ch[q] = __float2bfloat16_rn(0.f); cl[q] = __float2bfloat16_rn(0.f); }
       __syncthreads();
       const uint32_t* wh = reinterpret_cast<const uint32_t*>(sdh); const uint32_t* wl = reinterpret_cast<const uint32_t*>(sdl);
       uint32_t* gh = reinterpret_cast<uint32_t*>(P.dOhi); uint32_t* gl = reinterpret_cast<uint32_t*>(P.dOlo);
-      const int WPC = P.OP / 2;                                 // 32-bit words per cell (12)
-      for (int f = threadIdx.x; f < EPI_T * EPI_T * 12; f += blockDim.x) {
-        const int r = f / (EPI_T * 12), w = f - r * (EPI_T * 12); const int c2 = w / 12, ww = w - c2 * 12;
+      const int WPC = P.OP / 2;                                 // 32-bit words per cell (12 padded, 10 compact)
+      for (int f = threadIdx.x; f < EPI_T * EPI_T * WPC; f += blockDim.x) {
+        const int r = f / (EPI_T * WPC), w = f - r * (EPI_T * WPC); const int c2 = w / WPC, ww = w - c2 * WPC;
         if (i0 + r < N && j0 + c2 < N) {       // layout 0: row (b, i0+r), cells j0..
           const long long g = ((((long long)b * N + i0 + r) * N + j0 + c2) * WPC) + ww;
-          gh[g] = wh[(r * EPI_T + c2) * 12 + ww]; gl[g] = wl[(r * EPI_T + c2) * 12 + ww];
+          gh[g] = wh[(r * EPI_T + c2) * WPC + ww]; gl[g] = wl[(r * EPI_T + c2) * WPC + ww];
         }
         if (j0 + r < N && i0 + c2 < N) {       // layout 1: row (b, j0+r), cells i0..
           const long long g = (((plane + ((long long)b * N + j0 + r) * N + i0 + c2)) * WPC) + ww;
-          gh[g] = wh[(c2 * EPI_T + r) * 12 + ww]; gl[g] = wl[(c2 * EPI_T + r) * 12 + ww];
+          gh[g] = wh[(c2 * EPI_T + r) * WPC + ww]; gl[g] = wl[(c2 * EPI_T + r) * WPC + ww];
         }
       }
     }

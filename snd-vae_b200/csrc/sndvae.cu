@@ -539,7 +539,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     const int bc = (int)(B - b0 < h->Bc ? B - b0 : h->Bc);
     const long long rows = (long long)bc * N, cells = rows * N;
     mark(h, "y_producer");
-    YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = TC_CP; Y.bf16 = tc;
+    YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = tc ? h->tc.l1.CSi : C1; Y.bf16 = tc;
     { dim3 yg(cdiv(N, YP_TJ), N);
       if (Chv == 40) LAUNCH(y_producer_k<40>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
                             h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
@@ -558,7 +558,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     ep.At = in ? in->adj_truth + b0 * N * N : nullptr;
     ep.gen_adj = (out && out->generated_adj) ? (long long*)out->generated_adj + b0 * N * N : nullptr;
     ep.logits = (out && out->generated_adj_prob) ? out->generated_adj_prob + b0 * N * N * 2 : nullptr;
-    ep.dOf = h->dOf; ep.dOhi = h->dOhi; ep.dOlo = h->dOlo; ep.OP = TC_OP; ep.bf16 = tc; ep.backward = backward;
+    ep.dOf = h->dOf; ep.dOhi = h->dOhi; ep.dOlo = h->dOlo; ep.OP = tc ? h->tc.l1.CSo : C2; ep.bf16 = tc; ep.backward = backward;
     ep.loss_sum = h->loss + 0;
     ep.g_b1 = h->G + p.e_b[1]; ep.g_gd = h->dis ? h->G + p.decadj_g : nullptr; ep.g_bd = h->dis ? h->G + p.decadj_b : nullptr;
     ep.g_Me = h->G + p.d_e_lin2[0]; ep.g_be = h->G + p.d_e_lin2[1];
