@@ -18,7 +18,8 @@
 //
 // Kernels: one CTA (320 threads) per 128 x BN output tile; warp 0 = TMA producer, warp 1 =
 // TMEM allocator + single-thread tcgen05.mma issuer, warps 2..9 = accumulate/epilogue (tcgen05.ld).
-// smem ring of 2 stages (K chunk 64, SWIZZLE_128B), mbarrier full/empty pipeline.
+// smem ring: 2 stages of K chunk 64 (SWIZZLE_128B rows) for the K-major kernel, 4 stages of 32 K-rows for the
+// MN-major one; mbarrier full/empty pipeline.
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
@@ -29,8 +30,11 @@
 #define TC_CP 56      /* padded channel stride of Y planes  (112 B: TMA strides need 16 B multiples); compact = 50 */
 #define TC_OP 24      /* padded channel stride of dO planes (48 B); compact = 20 */
 #define TC_BM 128
-#define TC_KC 64      /* K elements per stage = one 128-byte swizzle row */
-#define TC_STAGES 2
+#define TC_KC 64      /* K elements per stage of the K-major (fwd / dgrad) kernel = one 128-byte swizzle row.  (32 with
+                         SWIZZLE_64B and 4 stages also works but measured 20 % slower: fwd 66 -> 82 ms per 512 graphs.) */
+#define TC_STAGES 2   /* 92 KB per stage */
+#define TC_WKC 32     /* K rows per stage of the MN-major (wgrad) kernel */
+#define TC_WSTAGES 4
 
 static char g_tc_err[256] = "";
 static const char* tc_last_error() { return g_tc_err; }
@@ -109,9 +113,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t layout) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return umma_desc(saddr, lbo_bytes, sbo_bytes, 2ull);     // SWIZZLE_128B
+}
+// K-major operand whose rows are TC_KC bf16 wide: 128-byte rows -> SWIZZLE_128B (atoms of 8 rows = 1024 B),
+// 64-byte rows -> SWIZZLE_64B (layout 4, atoms of 512 B)
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
+  return TC_KC == 64 ? umma_desc(saddr, 16, 1024, 2ull) : umma_desc(saddr, 16, 512, 4ull);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn_major, int b_mn_major) {
@@ -144,7 +156,7 @@ struct TMapSet { CUtensorMap h[4]; CUtensorMap l[4]; };   // window views of the
 // into one of two TMEM slots, and the epilogue warps drain the finished slot into round-to-nearest
 // fp32 registers while the tensor pipe fills the other slot.
 #ifndef TC_GROUP
-#define TC_GROUP 8
+#define TC_GROUP (512 / TC_KC)   /* K chunks per accumulation group: 512 K elements = 96 accumulates */
 #endif
 #define TC_EPI_WARPS 8
 #define TC_THREADS (64 + 32 * TC_EPI_WARPS)
@@ -220,11 +232,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
         const uint32_t td = tmem_d + slot * 256;
 #pragma unroll
         for (int k = 0; k < TC_KC / 16; ++k) {
-          // K-major SWIZZLE_128B: 8-row groups 1024 B apart; +32 B per 16-element K step
-          const uint64_t ah = umma_desc_sw128(sa + k * 32, 16, 1024);
-          const uint64_t al = umma_desc_sw128(sa + A_BYTES + k * 32, 16, 1024);
-          const uint64_t bh = umma_desc_sw128(sa + 2 * A_BYTES + k * 32, 16, 1024);
-          const uint64_t bl = umma_desc_sw128(sa + 2 * A_BYTES + B_BYTES + k * 32, 16, 1024);
+          // K-major swizzled rows: 8-row groups one atom apart; +32 B per 16-element K step
+          const uint64_t ah = umma_desc_kmajor(sa + k * 32);
+          const uint64_t al = umma_desc_kmajor(sa + A_BYTES + k * 32);
+          const uint64_t bh = umma_desc_kmajor(sa + 2 * A_BYTES + k * 32);
+          const uint64_t bl = umma_desc_kmajor(sa + 2 * A_BYTES + B_BYTES + k * 32);
           umma_bf16(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
           umma_bf16(td, ah, bl, idesc, 1u);
           umma_bf16(td, al, bh, idesc, 1u);
@@ -293,17 +305,18 @@ struct WgradArgs {
   int ksplit;          // CTAs per output tile along K
 };
 #define TC_WN 256
+#define TC_WGROUP (512 / TC_WKC)
 __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                                                               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                                                               WgradArgs P) {
-  constexpr int A_BYTES = TC_KC * TC_BM * 2;       // [2 x (64 k-rows x 128 B)] = 16 KB
-  constexpr int B_BYTES = TC_KC * TC_WN * 2;       // [4 x (64 k-rows x 128 B)] = 32 KB
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 96 KB
-  constexpr int BLK = TC_KC * 128;                 // one 64(mn) x 64(k) box = 8 KB
+  constexpr int A_BYTES = TC_WKC * TC_BM * 2;      // [2 x (TC_WKC k-rows x 128 B)]
+  constexpr int B_BYTES = TC_WKC * TC_WN * 2;      // [4 x (TC_WKC k-rows x 128 B)]
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 48 KB at TC_WKC = 32
+  constexpr int BLK = TC_WKC * 128;                // one 64(mn) x TC_WKC(k) box
   constexpr int HC = TC_WN / 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full_bar[TC_WSTAGES], empty_bar[TC_WSTAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / P.ksplit, ks = blockIdx.x % P.ksplit;
@@ -315,16 +328,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
   const int j_lo = n0 / P.CSo, j_hi = min(P.N - 1, (n0 + TC_WN - 1) / P.CSo);
   if (jp_lo > P.N - 1 || j_lo > P.N - 1) return;
   if (jp_hi - j_lo + p < 0 || jp_lo - j_hi + p > P.N - 1) return;
-  const long long kchunks = (P.rows + TC_KC - 1) / TC_KC;
+  const long long kchunks = (P.rows + TC_WKC - 1) / TC_WKC;
   const long long per = (kchunks + P.ksplit - 1) / P.ksplit;
   const long long kc_lo = (long long)ks * per;
   long long kc_hi = kc_lo + per; if (kc_hi > kchunks) kc_hi = kchunks;
   const int nk = kc_hi > kc_lo ? (int)(kc_hi - kc_lo) : 0;
   if (nk == 0) return;
-  const int ngroups = (nk + TC_GROUP - 1) / TC_GROUP;
+  const int ngroups = (nk + TC_WGROUP - 1) / TC_WGROUP;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < TC_WSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -337,11 +350,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < nk; ++it) {
-        const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
+        const int s = it % TC_WSTAGES; const uint32_t ph = (it / TC_WSTAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int r0 = (int)((kc_lo + it) * TC_KC);
+        const int r0 = (int)((kc_lo + it) * TC_WKC);
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           tma_load_2d(st + b * BLK, &tmAh, &full_bar[s], m0 + 64 * b, r0);
@@ -358,15 +371,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(TC_BM, TC_WN, 1, 1);
       for (int it = 0; it < nk; ++it) {
-        const int g = it / TC_GROUP, gi = it - g * TC_GROUP, slot = g & 1;
+        const int g = it / TC_WGROUP, gi = it - g * TC_WGROUP, slot = g & 1;
         if (gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
-        const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
+        const int s = it % TC_WSTAGES; const uint32_t ph = (it / TC_WSTAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint32_t td = tmem_d + slot * 256;
 #pragma unroll
-        for (int k = 0; k < TC_KC / 16; ++k) {
+        for (int k = 0; k < TC_WKC / 16; ++k) {
           // MN-major SWIZZLE_128B: 64-element MN blocks BLK bytes apart (LBO), 8-row K groups
           // 1024 B apart (SBO); +2048 B per 16-row K step
           const uint64_t ah = umma_desc_sw128(sa + k * 2048, BLK, 1024);
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
           umma_bf16(td, al, bh, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);
-        if (gi == TC_GROUP - 1 || it == nk - 1) umma_commit(&acc_full[slot]);
+        if (gi == TC_WGROUP - 1 || it == nk - 1) umma_commit(&acc_full[slot]);
       }
     }
   } else {
@@ -488,19 +501,22 @@ struct TcState {                           // all tensor-core products of the ed
   __nv_bfloat16 *dsh, *dsl, *drh, *drl;    // dSa / dRc planes  [B, N*CSo]
 };
 
-static int tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b, const cuuint32_t* box) {
+static int tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_b, const cuuint32_t* box,
+                     CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = g_tc_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_b, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled failed: %d (rank %d)", (int)r, rank); return -1; }
   return 0;
 }
-static int tc_encode_rows(CUtensorMap* tm, const void* base, long long width, long long rows, int box0, int box1) {
+#define TC_KSWZ (TC_KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)
+static int tc_encode_rows(CUtensorMap* tm, const void* base, long long width, long long rows, int box0, int box1,
+                          CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
   cuuint64_t str[1] = {(cuuint64_t)width * 2};
   cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
-  return tc_encode(tm, base, 2, dims, str, box);
+  return tc_encode(tm, base, 2, dims, str, box, swz);
 }
 static int tc_global_init() {
   if (g_tc_encode) return 0;
@@ -510,7 +526,7 @@ static int tc_global_init() {
   }
   g_tc_encode = (PFN_encodeTiled)fn;
   cudaFuncSetAttribute(toep_gemm_k<240>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024);
-  cudaFuncSetAttribute(wgrad_gemm_k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_STAGES * (2 * TC_KC * TC_BM * 2 + 2 * TC_KC * TC_WN * 2) + 1024);
+  cudaFuncSetAttribute(wgrad_gemm_k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_WSTAGES * (2 * TC_WKC * TC_BM * 2 + 2 * TC_WKC * TC_WN * 2) + 1024);
   return 0;
 }
 static int tc_pad16(int c) { return (c * 2) % 16 == 0 ? c : (c + 7) / 8 * 8; }   // channel stride with 16-byte rows
@@ -542,15 +558,15 @@ static int tc_plan_init(ToepPlan& pl, int N, int Cin, int Cout, int fCT, int fJT
     cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSi, (cuuint64_t)((N - r + pl.nsf - 1) / pl.nsf), (cuuint64_t)Cout};
     cuuint64_t str[2] = {(cuuint64_t)pl.nsf * pl.CSi * 2, (cuuint64_t)pl.LFp * 2};
     cuuint32_t box[3] = {TC_KC, (cuuint32_t)(fJT / pl.nsf), (cuuint32_t)fCT};
-    if (tc_encode(&pl.fB.h[r], pl.Wfh + (size_t)r * Cout * pl.LFp, 3, dims, str, box) ||
-        tc_encode(&pl.fB.l[r], pl.Wfl + (size_t)r * Cout * pl.LFp, 3, dims, str, box)) return -1;
+    if (tc_encode(&pl.fB.h[r], pl.Wfh + (size_t)r * Cout * pl.LFp, 3, dims, str, box, TC_KSWZ) ||
+        tc_encode(&pl.fB.l[r], pl.Wfl + (size_t)r * Cout * pl.LFp, 3, dims, str, box, TC_KSWZ)) return -1;
   }
   for (int r = 0; r < pl.nsd; ++r) {
     cuuint64_t dims[3] = {(cuuint64_t)N * pl.CSo, (cuuint64_t)((N - r + pl.nsd - 1) / pl.nsd), (cuuint64_t)Cin};
     cuuint64_t str[2] = {(cuuint64_t)pl.nsd * pl.CSo * 2, (cuuint64_t)pl.LDp * 2};
     cuuint32_t box[3] = {TC_KC, (cuuint32_t)(dJT / pl.nsd), (cuuint32_t)dCT};
-    if (tc_encode(&pl.dB.h[r], pl.Wdh + (size_t)r * Cin * pl.LDp, 3, dims, str, box) ||
-        tc_encode(&pl.dB.l[r], pl.Wdl + (size_t)r * Cin * pl.LDp, 3, dims, str, box)) return -1;
+    if (tc_encode(&pl.dB.h[r], pl.Wdh + (size_t)r * Cin * pl.LDp, 3, dims, str, box, TC_KSWZ) ||
+        tc_encode(&pl.dB.l[r], pl.Wdl + (size_t)r * Cin * pl.LDp, 3, dims, str, box, TC_KSWZ)) return -1;
   }
   pl.ready = 1;
   return 0;
@@ -576,13 +592,13 @@ static int tc_split(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long
   return tc_check_launch("tc_split_planes_k");
 }
 static const size_t TC_TOEP_SMEM = TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024;
-static const size_t TC_WGRAD_SMEM = TC_STAGES * (2 * TC_KC * TC_BM * 2 + 2 * TC_KC * TC_WN * 2) + 1024;
+static const size_t TC_WGRAD_SMEM = TC_WSTAGES * (2 * TC_WKC * TC_BM * 2 + 2 * TC_WKC * TC_WN * 2) + 1024;
 
 // out[rows, N*Cout] (+)= in[rows, N*CSi planes] . Toeplitz(w)
 static int tc_plan_fwd(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat16* inl, float* out, long long rows, long long rows_alloc,
                        int accumulate, cudaStream_t st) {
   CUtensorMap ah, al;
-  if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM)) return -1;
+  if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM, TC_KSWZ) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows_alloc, TC_KC, TC_BM, TC_KSWZ)) return -1;
   ToepArgs a; a.out = out; a.rows = rows; a.N = pl.N; a.Cout = pl.Cout; a.CS = pl.CSi; a.CT = pl.fCT; a.JT = pl.fJT;
   a.n_ctiles = pl.Cout / pl.fCT; a.n_jtiles = (pl.N + pl.fJT - 1) / pl.fJT; a.pad_rows = pl.N - 1 - (pl.N - 1) / 2; a.KA = pl.N * pl.CSi;
   a.accumulate = accumulate; a.nsh = pl.nsf;
@@ -594,7 +610,7 @@ static int tc_plan_fwd(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat
 static int tc_plan_dgrad(ToepPlan& pl, const __nv_bfloat16* doh, const __nv_bfloat16* dol, float* din, long long rows, long long rows_alloc,
                          int accumulate, cudaStream_t st) {
   CUtensorMap ah, al;
-  if (tc_encode_rows(&ah, doh, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM) || tc_encode_rows(&al, dol, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM)) return -1;
+  if (tc_encode_rows(&ah, doh, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM, TC_KSWZ) || tc_encode_rows(&al, dol, (long long)pl.N * pl.CSo, rows_alloc, TC_KC, TC_BM, TC_KSWZ)) return -1;
   ToepArgs a; a.out = din; a.rows = rows; a.N = pl.N; a.Cout = pl.Cin; a.CS = pl.CSo; a.CT = pl.dCT; a.JT = pl.dJT;
   a.n_ctiles = pl.Cin / pl.dCT; a.n_jtiles = (pl.N + pl.dJT - 1) / pl.dJT; a.pad_rows = (pl.N - 1) / 2; a.KA = pl.N * pl.CSo;
   a.accumulate = accumulate; a.nsh = pl.nsd;
@@ -606,13 +622,13 @@ static int tc_plan_dgrad(ToepPlan& pl, const __nv_bfloat16* doh, const __nv_bflo
 static int tc_plan_wgrad(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat16* inl, const __nv_bfloat16* doh, const __nv_bfloat16* dol,
                          float* dw, int Ctot, int coff, long long rows, cudaStream_t st) {
   CUtensorMap ah, al, bh, bl;     // bounded by the exact row count: TMA zero-fills the K tail
-  if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows, 64, TC_KC) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows, 64, TC_KC) ||
-      tc_encode_rows(&bh, doh, (long long)pl.N * pl.CSo, rows, 64, TC_KC) || tc_encode_rows(&bl, dol, (long long)pl.N * pl.CSo, rows, 64, TC_KC)) return -1;
+  if (tc_encode_rows(&ah, inh, (long long)pl.N * pl.CSi, rows, 64, TC_WKC) || tc_encode_rows(&al, inl, (long long)pl.N * pl.CSi, rows, 64, TC_WKC) ||
+      tc_encode_rows(&bh, doh, (long long)pl.N * pl.CSo, rows, 64, TC_WKC) || tc_encode_rows(&bl, dol, (long long)pl.N * pl.CSo, rows, 64, TC_WKC)) return -1;
   WgradArgs a; a.dw = dw; a.rows = rows; a.N = pl.N; a.CSi = pl.CSi; a.Cin = pl.Cin; a.CSo = pl.CSo; a.Cout = pl.Cout; a.Ctot = Ctot; a.coff = coff;
   a.n_ntiles = (pl.N * pl.CSo + TC_WN - 1) / TC_WN;
   int n_mtiles = (pl.N * pl.CSi + TC_BM - 1) / TC_BM;
   long long tiles = (long long)n_mtiles * a.n_ntiles;
-  long long kchunks = (rows + TC_KC - 1) / TC_KC;
+  long long kchunks = (rows + TC_WKC - 1) / TC_WKC;
   int ks = 1;
   while (tiles * ks < 2 * 148 && ks * 8 < kchunks) ks *= 2;     // fill the 148 SMs when N is small
   a.ksplit = ks;
