@@ -10,6 +10,17 @@
 // sampled adjacency matter; the samples are spanning forests
 // (input_data.py:18-38: nnz <= 2(N-1)).  sgc_build_edges_k streams `adj` once
 // (the HBM-bound stage of the encoder) and gathers the few `rel` entries needed.
+//
+// Work split.  Everything that is a per-node dense map is written as a product of a per-node
+// coefficient row with a small weight block, so that the whole chunk of samples is ONE tall
+// library GEMM (rows = samples x N):
+//     P    = xphi  . M1a                       xphi  = phi(x)                          [C]
+//     Qc   = coefQ . [M1b; M1c; w5; b1]        coefQ = [deg phi(x), apx, s, deg]       [2C+2]
+//     m2s  = coef2 . [M2; b2]                  coef2 = [deg phi(x), apx, s, T, deg]    [2C+2+h0]
+//     y    = coef3 . [M3; b3]                  coef3 = [phi(x), phi(m2s), 1]           [C+h1+1]
+// so that the bracket of m3s is  deg_j P_i + Qc_j + deg_j phi(r_ij) w4 + G_ij w6  (4 FMAs per edge
+// and channel).  The kernels below only do the O(E h) edge work and the element-wise glue; the
+// backward uses the transposed GEMMs and the same coefficient rows for the parameter gradients.
 #pragma once
 #include "common.cuh"
 
@@ -98,217 +109,193 @@ __global__ void __launch_bounds__(256) sgc_build_edges_k(const float* __restrict
   }
 }
 
-struct SgcW {            // parameter (or gradient) pointers of one SGC layer
-  float *M1, *b1, *M2, *b2, *M3, *b3;
-  int C, h0, h1, h2;
-};
+struct SgcDims { int C, h0, h1, h2; };
 
-struct SgcScratch {      // per-sample activations of one layer (global memory)
-  float* apx;            // [samples, N, C]   sum_k A_jk phi(x_k)
-  float* T;              // [samples, N, h0]
-  float* m2s;            // [samples, N, h1]
-  float* y;              // [samples, N, h2]  layer output before BN
+struct SgcScratch {      // activations of one layer for a chunk of samples (rows = samples x N)
+  float* xphi;           // [rows, C]         phi(x)
+  float* coefQ;          // [rows, 2C+2]      [deg phi(x), apx, s, deg]
+  float* P;              // [rows, h0]
+  float* Qc;             // [rows, h0]
+  float* coef2;          // [rows, 2C+2+h0]   [deg phi(x), apx, s, T, deg]
+  float* m2s;            // [rows, h1]
+  float* coef3;          // [rows, C+h1+1]    [phi(x), phi(m2s), 1]
+  float* y;              // [rows, h2]        layer output before BN
   // backward
-  float* dm2s;           // [samples, N, h1]
-  float* dT;             // [samples, N, h0]
-  float* ee;             // [samples, cap, h0]
-  float* dpx;            // [samples, N, C]
-  float* dapx;           // [samples, N, C]
-  // coefficient matrices of the parameter gradients (dM = coef^T . grad as library GEMMs):
-  float* coef1;          // [samples, cap, 3C+4]  per edge:  [deg_j phi(x_i), deg_j phi(x_j), apx_j, deg_j phi(r), s_j, G, deg_j]
-  float* coef2;          // [samples, N, 2C+2+h0] per node:  [deg_i phi(x_i), apx_i, s_i, T_i, deg_i]
-  float* coef3;          // [samples, N, C+h1+1]  per node:  [phi(x_i), phi(m2s_i), 1]
+  float* dcoef3;         // [rows, C+h1+1]
+  float* dm2s;           // [rows, h1]
+  float* dcoef2;         // [rows, 2C+2+h0]
+  float* dP;             // [rows, h0]
+  float* dQc;            // [rows, h0]
+  float* dxphi;          // [rows, C]
+  float* dcoefQ;         // [rows, 2C+2]
+  float* dpx;            // [rows, C]
+  // per-step weight blocks assembled from the arena (and their gradients)
+  float* WQ;             // [2C+2, h0]   [M1b; M1c; w5; b1]
+  float* W2;             // [2C+2+h0, h1] [M2; b2]
+  float* W3;             // [C+h1+1, h2]  [M3; b3]
+  float* dWQ;            // gradient of WQ (scattered back into M1 / b1 after the step)
+  float* w46;            // [2, h0] gradient partial sums of w4, w6 (rows 3C and 3C+2 of M1)
 };
 
-// bracket of m3s for edge (i,j), channel h (without the leading A_ij)
-__device__ __forceinline__ float sgc_bracket(const SgcW& W, const float* __restrict__ x, const float* __restrict__ apx,
-                                             int i, int j, int h, float degj, float sj, float pr, float G) {
-  const int C = W.C, h0 = W.h0;
-  float pq = 0.f, ar = 0.f;
-  for (int c = 0; c < C; ++c) {
-    pq = fmaf(lrelu_f(x[i * C + c]), W.M1[c * h0 + h], pq);
-    pq = fmaf(lrelu_f(x[j * C + c]), W.M1[(C + c) * h0 + h], pq);
-    ar = fmaf(apx[j * C + c], W.M1[(2 * C + c) * h0 + h], ar);
+// (1) phi(x), apx = A phi(x), coefQ.  One CTA per sample.
+__global__ void __launch_bounds__(256) sgc_prep_k(const float* __restrict__ xin, SgcEdges E, SgcDims D, SgcScratch Sx, int N, long long e_off) {
+  const long long ls = blockIdx.x, gs = ls + e_off;
+  const int C = D.C, KQ = 2 * C + 2;
+  const float* x = xin + ls * N * C;
+  const int* rowstart = E.rowstart + gs * N; const int* rowcnt = E.rowcnt + gs * N;
+  const int* ecol = E.ecol + gs * E.cap; const float* ea = E.ea + gs * E.cap;
+  const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
+  float* xphi = Sx.xphi + ls * N * C; float* cq = Sx.coefQ + ls * (long long)N * KQ;
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+    const int i = idx / C, c = idx - i * C;
+    const float px = lrelu_f(x[idx]);
+    float acc = 0.f;
+    for (int q = rowstart[i]; q < rowstart[i] + rowcnt[i]; ++q) acc = fmaf(ea[q], lrelu_f(x[ecol[q] * C + c]), acc);
+    xphi[idx] = px;
+    cq[i * KQ + c] = deg[i] * px; cq[i * KQ + C + c] = acc;
   }
-  return degj * (pq + pr * W.M1[(3 * C) * h0 + h] + W.b1[h]) + ar + sj * W.M1[(3 * C + 1) * h0 + h] +
-         G * W.M1[(3 * C + 2) * h0 + h];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { cq[i * KQ + 2 * C] = ssum[i]; cq[i * KQ + 2 * C + 1] = deg[i]; }
 }
 
-// forward of one SGC layer; one CTA per sample (sample index = blockIdx.x + s_off)
-__global__ void __launch_bounds__(256) sgc_layer_fwd_k(const float* __restrict__ xin, SgcEdges E, SgcW W, SgcScratch Sx,
-                                                       int N, long long e_off) {
-  long long ls = blockIdx.x;             // local sample (scratch / x index)
-  long long gs = ls + e_off;             // global sample (edge storage index)
-  const int C = W.C, h0 = W.h0, h1 = W.h1, h2 = W.h2;
-  const float* x = xin + ls * N * C;
+// (2) T_i = sum_j A_ij phi(m3s_ij) from P, Qc; writes coef2.  One CTA per sample.
+__global__ void __launch_bounds__(256) sgc_edge_fwd_k(SgcEdges E, SgcDims D, SgcScratch Sx, const float* __restrict__ w4,
+                                                      const float* __restrict__ w6, int N, long long e_off) {
+  const long long ls = blockIdx.x, gs = ls + e_off;
+  const int C = D.C, h0 = D.h0, KQ = 2 * C + 2, K2 = 2 * C + 2 + h0;
   const int* rowstart = E.rowstart + gs * N; const int* rowcnt = E.rowcnt + gs * N;
   const int* ecol = E.ecol + gs * E.cap;
   const float* ea = E.ea + gs * E.cap; const float* epr = E.epr + gs * E.cap; const float* eG = E.eG + gs * E.cap;
-  const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
-  float* apx = Sx.apx + ls * N * C; float* T = Sx.T + ls * N * h0;
-  float* m2s = Sx.m2s + ls * N * h1; float* y = Sx.y + ls * N * h2;
-  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
-    int i = idx / C, c = idx - i * C;
-    float acc = 0.f;
-    for (int q = rowstart[i]; q < rowstart[i] + rowcnt[i]; ++q) acc = fmaf(ea[q], lrelu_f(x[ecol[q] * C + c]), acc);
-    apx[idx] = acc;
-  }
-  __syncthreads();
+  const float* deg = E.deg + gs * N;
+  const float* P = Sx.P + ls * N * h0; const float* Qc = Sx.Qc + ls * N * h0;
+  const float* cq = Sx.coefQ + ls * (long long)N * KQ; float* c2 = Sx.coef2 + ls * (long long)N * K2;
   for (int idx = threadIdx.x; idx < N * h0; idx += blockDim.x) {
-    int i = idx / h0, h = idx - i * h0;
+    const int i = idx / h0, h = idx - i * h0;
+    const float pi = P[idx], a4 = w4[h], a6 = w6[h];
     float acc = 0.f;
     for (int q = rowstart[i]; q < rowstart[i] + rowcnt[i]; ++q) {
-      int j = ecol[q];
-      float br = sgc_bracket(W, x, apx, i, j, h, deg[j], ssum[j], epr[q], eG[q]);
-      acc = fmaf(ea[q], lrelu_f(ea[q] * br), acc);
+      const int j = ecol[q]; const float dj = deg[j], a = ea[q];
+      const float br = fmaf(dj, pi, Qc[j * h0 + h]) + dj * epr[q] * a4 + eG[q] * a6;
+      acc = fmaf(a, lrelu_f(a * br), acc);
     }
-    T[idx] = acc;
+    c2[i * K2 + 2 * C + 1 + h] = acc;
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < N * h1; idx += blockDim.x) {
-    int i = idx / h1, h = idx - i * h1;
-    float u = W.b2[h], av = 0.f;
-    for (int c = 0; c < C; ++c) {
-      u = fmaf(lrelu_f(x[i * C + c]), W.M2[c * h1 + h], u);
-      av = fmaf(apx[i * C + c], W.M2[(C + c) * h1 + h], av);
-    }
-    float acc = deg[i] * u + av + ssum[i] * W.M2[(2 * C) * h1 + h];
-    for (int k = 0; k < h0; ++k) acc = fmaf(T[i * h0 + k], W.M2[(2 * C + 1 + k) * h1 + h], acc);
-    m2s[idx] = acc;
+  for (int idx = threadIdx.x; idx < N * (2 * C + 1); idx += blockDim.x) {
+    const int i = idx / (2 * C + 1), r = idx - i * (2 * C + 1);
+    c2[i * K2 + r] = cq[i * KQ + r];                       // [deg phi(x), apx, s]
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < N * h2; idx += blockDim.x) {
-    int i = idx / h2, h = idx - i * h2;
-    float acc = W.b3[h];
-    for (int c = 0; c < C; ++c) acc = fmaf(lrelu_f(x[i * C + c]), W.M3[c * h2 + h], acc);
-    for (int k = 0; k < h1; ++k) acc = fmaf(lrelu_f(m2s[i * h1 + k]), W.M3[(C + k) * h2 + h], acc);
-    y[idx] = acc;
-  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) c2[i * K2 + K2 - 1] = deg[i];
 }
 
-// backward of one SGC layer w.r.t. activations; one CTA per sample.
-// dy: [samples, N, h2].  dx (optional): [samples, N, C] gradient w.r.t. the layer input.
-// Leaves dm2s / ee in scratch for sgc_param_grad_k.
-__global__ void __launch_bounds__(256) sgc_layer_bwd_k(const float* __restrict__ xin, const float* __restrict__ dyin,
-                                                       float* __restrict__ dxout, SgcEdges E, SgcW W, SgcScratch Sx,
-                                                       int N, long long e_off) {
-  long long ls = blockIdx.x, gs = ls + e_off;
-  const int C = W.C, h0 = W.h0, h1 = W.h1, h2 = W.h2;
-  const float* x = xin + ls * N * C;
-  const float* dy = dyin + ls * N * h2;
+// (3) coef3 = [phi(x), phi(m2s), 1]   (element-wise over rows)
+__global__ void sgc_cat_k(const float* __restrict__ xphi, const float* __restrict__ m2s, float* __restrict__ coef3, long long rows, int C, int h1) {
+  const int K3 = C + h1 + 1;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * K3) return;
+  const long long r = idx / K3; const int k = (int)(idx - r * K3);
+  coef3[idx] = k < C ? xphi[r * C + k] : (k < C + h1 ? lrelu_f(m2s[r * h1 + k - C]) : 1.f);
+}
+
+// (4) backward through the lrelu of the concat: dx_direct = dcoef3[:, :C] phi'(x), dm2s = dcoef3[:, C:C+h1] phi'(m2s)
+__global__ void sgc_cat_bwd_k(const float* __restrict__ dcoef3, const float* __restrict__ x, const float* __restrict__ m2s,
+                              float* __restrict__ dx, float* __restrict__ dm2s, long long rows, int C, int h1) {
+  const int K3 = C + h1 + 1, W = C + h1;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * W) return;
+  const long long r = idx / W; const int k = (int)(idx - r * W);
+  const float g = dcoef3[r * K3 + k];
+  if (k < C) { if (dx) dx[r * C + k] = g * lrelu_g(x[r * C + k]); }
+  else dm2s[r * h1 + k - C] = g * lrelu_g(m2s[r * h1 + k - C]);
+}
+
+// (5) edge backward: ee = A^2 dT phi'(m3s);  dP_i = sum_j deg_j ee,  dQc_j += ee (atomics),  w4 / w6 gradient sums.
+// One CTA per sample.  dQc must be zeroed by the caller.
+__global__ void __launch_bounds__(256) sgc_edge_bwd_k(SgcEdges E, SgcDims D, SgcScratch Sx, const float* __restrict__ w4,
+                                                      const float* __restrict__ w6, int N, long long e_off) {
+  extern __shared__ float sw[];          // [2][h0] partial sums of the w4 / w6 gradients
+  const long long ls = blockIdx.x, gs = ls + e_off;
+  const int C = D.C, h0 = D.h0, K2 = 2 * C + 2 + h0;
   const int* rowstart = E.rowstart + gs * N; const int* rowcnt = E.rowcnt + gs * N;
-  const int* erow = E.erow + gs * E.cap; const int* ecol = E.ecol + gs * E.cap;
+  const int* ecol = E.ecol + gs * E.cap;
   const float* ea = E.ea + gs * E.cap; const float* epr = E.epr + gs * E.cap; const float* eG = E.eG + gs * E.cap;
-  const float* deg = E.deg + gs * N; const float* ssum = E.ssum + gs * N;
-  const int ne = E.nedges[gs];
-  const float* apx = Sx.apx + ls * N * C; const float* m2s = Sx.m2s + ls * N * h1;
-  float* dm2s = Sx.dm2s + ls * N * h1; float* dT = Sx.dT + ls * N * h0;
-  float* ee = Sx.ee + ls * (long long)E.cap * h0;
-  float* dpx = Sx.dpx + ls * N * C; float* dapx = Sx.dapx + ls * N * C;
-  float* dx = dxout ? dxout + ls * N * C : nullptr;
-  // (a) through M3 and the lrelu of the concat [x || m2s]
-  int qlo = dx ? 0 : C;
-  for (int idx = threadIdx.x; idx < N * (C + h1 - qlo); idx += blockDim.x) {
-    int i = idx / (C + h1 - qlo), q = qlo + idx - i * (C + h1 - qlo);
-    float cv = q < C ? x[i * C + q] : m2s[i * h1 + q - C];
-    float acc = 0.f;
-    for (int k = 0; k < h2; ++k) acc = fmaf(dy[i * h2 + k], W.M3[q * h2 + k], acc);
-    acc *= lrelu_g(cv);
-    if (q < C) dx[i * C + q] = acc; else dm2s[i * h1 + q - C] = acc;
-  }
+  const float* deg = E.deg + gs * N;
+  const float* P = Sx.P + ls * N * h0; const float* Qc = Sx.Qc + ls * N * h0;
+  const float* dc2 = Sx.dcoef2 + ls * (long long)N * K2;
+  float* dP = Sx.dP + ls * N * h0; float* dQc = Sx.dQc + ls * N * h0;
+  for (int t = threadIdx.x; t < 2 * h0; t += blockDim.x) sw[t] = 0.f;
   __syncthreads();
-  // (b) through M2
   for (int idx = threadIdx.x; idx < N * h0; idx += blockDim.x) {
-    int i = idx / h0, k = idx - i * h0;
-    float acc = 0.f;
-    for (int h = 0; h < h1; ++h) acc = fmaf(dm2s[i * h1 + h], W.M2[(2 * C + 1 + k) * h1 + h], acc);
-    dT[idx] = acc;
-  }
-  if (dx) {
-    for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
-      int i = idx / C, c = idx - i * C;
-      float a0 = 0.f, a1 = 0.f;
-      for (int h = 0; h < h1; ++h) {
-        float d = dm2s[i * h1 + h];
-        a0 = fmaf(d, W.M2[c * h1 + h], a0);
-        a1 = fmaf(d, W.M2[(C + c) * h1 + h], a1);
-      }
-      dpx[idx] = deg[i] * a0; dapx[idx] = a1;
+    const int i = idx / h0, h = idx - i * h0;
+    const float pi = P[idx], a4 = w4[h], a6 = w6[h], dT = dc2[i * K2 + 2 * C + 1 + h];
+    float accP = 0.f, acc4 = 0.f, acc6 = 0.f;
+    for (int q = rowstart[i]; q < rowstart[i] + rowcnt[i]; ++q) {
+      const int j = ecol[q]; const float dj = deg[j], a = ea[q];
+      const float br = fmaf(dj, pi, Qc[j * h0 + h]) + dj * epr[q] * a4 + eG[q] * a6;
+      const float ee = a * a * dT * lrelu_g(a * br);
+      accP = fmaf(dj, ee, accP);
+      acc4 = fmaf(dj * epr[q], ee, acc4); acc6 = fmaf(eG[q], ee, acc6);
+      atomicAdd(dQc + j * h0 + h, ee);
     }
+    dP[idx] = accP;
+    atomicAdd(sw + h, acc4); atomicAdd(sw + h0 + h, acc6);
   }
   __syncthreads();
-  // (c) per (edge, channel): gradient w.r.t. the bracket
-  for (int idx = threadIdx.x; idx < ne * h0; idx += blockDim.x) {
-    int e = idx / h0, h = idx - e * h0;
-    int i = erow[e], j = ecol[e];
-    float a = ea[e];
-    float br = sgc_bracket(W, x, apx, i, j, h, deg[j], ssum[j], epr[e], eG[e]);
-    ee[idx] = a * a * dT[i * h0 + h] * lrelu_g(a * br);
-  }
-  // coefficient rows for the parameter-gradient GEMMs (rows e >= ne of coef1 / ee stay zero)
-  {
-    const int K1 = 3 * C + 4, K2 = 2 * C + 2 + h0, K3 = C + h1 + 1;
-    float* c1 = Sx.coef1 + ls * (long long)E.cap * K1;
-    float* c2 = Sx.coef2 + ls * (long long)N * K2;
-    float* c3 = Sx.coef3 + ls * (long long)N * K3;
-    const float* T = Sx.T + ls * N * h0;
-    for (int idx = threadIdx.x; idx < E.cap * K1; idx += blockDim.x) {
-      int e = idx / K1, r = idx - e * K1;
-      float v = 0.f;
-      if (e < ne) {
-        int i = erow[e], j = ecol[e];
-        if (r < C) v = deg[j] * lrelu_f(x[i * C + r]);
-        else if (r < 2 * C) v = deg[j] * lrelu_f(x[j * C + r - C]);
-        else if (r < 3 * C) v = apx[j * C + r - 2 * C];
-        else if (r == 3 * C) v = deg[j] * epr[e];
-        else if (r == 3 * C + 1) v = ssum[j];
-        else if (r == 3 * C + 2) v = eG[e];
-        else v = deg[j];
-      }
-      c1[idx] = v;
-    }
-    for (int idx = threadIdx.x; idx < N * K2; idx += blockDim.x) {
-      int i = idx / K2, r = idx - i * K2;
-      float v;
-      if (r < C) v = deg[i] * lrelu_f(x[i * C + r]);
-      else if (r < 2 * C) v = apx[i * C + r - C];
-      else if (r == 2 * C) v = ssum[i];
-      else if (r < 2 * C + 1 + h0) v = T[i * h0 + r - 2 * C - 1];
-      else v = deg[i];
-      c2[idx] = v;
-    }
-    for (int idx = threadIdx.x; idx < N * K3; idx += blockDim.x) {
-      int i = idx / K3, r = idx - i * K3;
-      c3[idx] = r < C ? lrelu_f(x[i * C + r]) : (r < C + h1 ? lrelu_f(m2s[i * h1 + r - C]) : 1.f);
-    }
-    for (int idx = ne * h0 + threadIdx.x; idx < E.cap * h0; idx += blockDim.x) ee[idx] = 0.f;
+  for (int t = threadIdx.x; t < 2 * h0; t += blockDim.x) atomicAdd(Sx.w46 + t, sw[t]);
+}
+
+// (6) node backward: d phi(x) = dxphi + deg (dcoefQ[:, :C] + dcoef2[:, :C]);  d apx = dcoefQ[:, C:2C] + dcoef2[:, C:2C];
+//     apx_j = sum_k A_jk phi(x_k)  =>  d phi(x_k) += A_jk d apx_j;  dx += d phi(x) phi'(x).   One CTA per sample.
+__global__ void __launch_bounds__(256) sgc_node_bwd_k(const float* __restrict__ xin, float* __restrict__ dxio, SgcEdges E, SgcDims D,
+                                                      SgcScratch Sx, int N, long long e_off) {
+  const long long ls = blockIdx.x, gs = ls + e_off;
+  const int C = D.C, h0 = D.h0, KQ = 2 * C + 2, K2 = 2 * C + 2 + h0;
+  const int* erow = E.erow + gs * E.cap; const int* ecol = E.ecol + gs * E.cap; const float* ea = E.ea + gs * E.cap;
+  const float* deg = E.deg + gs * N;
+  const int ne = E.nedges[gs];
+  const float* x = xin + ls * N * C; float* dx = dxio + ls * N * C;
+  const float* dxphi = Sx.dxphi + ls * N * C;
+  const float* dcq = Sx.dcoefQ + ls * (long long)N * KQ; const float* dc2 = Sx.dcoef2 + ls * (long long)N * K2;
+  float* dpx = Sx.dpx + ls * N * C;
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+    const int i = idx / C, c = idx - i * C;
+    dpx[idx] = dxphi[idx] + deg[i] * (dcq[i * KQ + c] + dc2[i * K2 + c]);
   }
   __syncthreads();
-  if (!dx) return;
-  // (d) edge contributions to d phi(x) and d apx
   for (int idx = threadIdx.x; idx < ne * C; idx += blockDim.x) {
-    int e = idx / C, c = idx - e * C;
-    int i = erow[e], j = ecol[e];
-    float dj = deg[j];
-    float si = 0.f, sj = 0.f, sa = 0.f;
-    for (int h = 0; h < h0; ++h) {
-      float v = ee[e * h0 + h];
-      si = fmaf(v, W.M1[c * h0 + h], si);
-      sj = fmaf(v, W.M1[(C + c) * h0 + h], sj);
-      sa = fmaf(v, W.M1[(2 * C + c) * h0 + h], sa);
-    }
-    atomicAdd(dpx + i * C + c, dj * si);
-    atomicAdd(dpx + j * C + c, dj * sj);
-    atomicAdd(dapx + j * C + c, sa);
+    const int e = idx / C, c = idx - e * C; const int j = erow[e];
+    atomicAdd(dpx + ecol[e] * C + c, ea[e] * (dcq[j * KQ + C + c] + dc2[j * K2 + C + c]));
   }
   __syncthreads();
-  // (e) apx_j = sum_k A_jk phi(x_k):  d phi(x_k) += A_jk d apx_j
-  for (int idx = threadIdx.x; idx < ne * C; idx += blockDim.x) {
-    int e = idx / C, c = idx - e * C;
-    atomicAdd(dpx + ecol[e] * C + c, ea[e] * dapx[erow[e] * C + c]);
-  }
-  __syncthreads();
-  // (f) dx = dx_direct + dphi(x) * phi'(x)
   for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) dx[idx] += dpx[idx] * lrelu_g(x[idx]);
 }
 
+// assemble the per-step weight blocks from the arena
+__global__ void sgc_pack_weights_k(const float* __restrict__ M1, const float* __restrict__ b1, const float* __restrict__ M2,
+                                   const float* __restrict__ b2, const float* __restrict__ M3, const float* __restrict__ b3,
+                                   float* __restrict__ WQ, float* __restrict__ W2, float* __restrict__ W3, SgcDims D) {
+  const int C = D.C, h0 = D.h0, h1 = D.h1, h2 = D.h2;
+  const int nQ = (2 * C + 2) * h0, n2 = (2 * C + 2 + h0) * h1, n3 = (C + h1 + 1) * h2;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < nQ) {
+    const int r = idx / h0, h = idx - r * h0;
+    WQ[idx] = r < 2 * C ? M1[(C + r) * h0 + h] : (r == 2 * C ? M1[(3 * C + 1) * h0 + h] : b1[h]);
+  } else if (idx < nQ + n2) {
+    const int q = idx - nQ; const int r = q / h1, h = q - r * h1;
+    W2[q] = r < 2 * C + 1 + h0 ? M2[r * h1 + h] : b2[h];
+  } else if (idx < nQ + n2 + n3) {
+    const int q = idx - nQ - n2; const int r = q / h2, h = q - r * h2;
+    W3[q] = r < C + h1 ? M3[r * h2 + h] : b3[h];
+  }
+}
+// scatter the gradient of WQ and the w4 / w6 sums back into M1 / b1 (once per step and layer)
+__global__ void sgc_unpack_grads_k(const float* __restrict__ dWQ, const float* __restrict__ w46, float* __restrict__ gM1,
+                                   float* __restrict__ gb1, SgcDims D) {
+  const int C = D.C, h0 = D.h0;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (2 * C + 4) * h0) return;
+  const int r = idx / h0, h = idx - r * h0;
+  if (r < 2 * C) gM1[(C + r) * h0 + h] += dWQ[idx];
+  else if (r == 2 * C) gM1[(3 * C + 1) * h0 + h] += dWQ[idx];
+  else if (r == 2 * C + 1) gb1[h] += dWQ[idx];
+  else if (r == 2 * C + 2) gM1[(3 * C) * h0 + h] += w46[h];
+  else gM1[(3 * C + 2) * h0 + h] += w46[h0 + h];
+}

@@ -237,10 +237,13 @@ static int dalloc(sndvae_t* h, T** p, long long n) {
 #define DA(ptr, n) do { int r_ = dalloc(h, &(ptr), (long long)(n)); if (r_) return r_; } while (0)
 
 static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long long samples, int N, int cap) {
-  DA(s.apx, samples * N * C); DA(s.T, samples * N * hs[0]); DA(s.m2s, samples * N * hs[1]); DA(s.y, samples * N * hs[2]);
-  DA(s.dm2s, samples * N * hs[1]); DA(s.dT, samples * N * hs[0]); DA(s.ee, samples * cap * hs[0]);
-  DA(s.dpx, samples * N * C); DA(s.dapx, samples * N * C);
-  DA(s.coef1, samples * cap * (3 * C + 4)); DA(s.coef2, samples * N * (2 * C + 2 + hs[0])); DA(s.coef3, samples * N * (C + hs[1] + 1));
+  const long long rows = samples * N; const int KQ = 2 * C + 2, K2 = 2 * C + 2 + hs[0], K3 = C + hs[1] + 1;
+  (void)cap;
+  DA(s.xphi, rows * C); DA(s.coefQ, rows * KQ); DA(s.P, rows * hs[0]); DA(s.Qc, rows * hs[0]); DA(s.coef2, rows * K2);
+  DA(s.m2s, rows * hs[1]); DA(s.coef3, rows * K3); DA(s.y, rows * hs[2]);
+  DA(s.dcoef3, rows * K3); DA(s.dm2s, rows * hs[1]); DA(s.dcoef2, rows * K2); DA(s.dP, rows * hs[0]); DA(s.dQc, rows * hs[0]);
+  DA(s.dxphi, rows * C); DA(s.dcoefQ, rows * KQ); DA(s.dpx, rows * C);
+  DA(s.WQ, KQ * hs[0]); DA(s.W2, K2 * hs[1]); DA(s.W3, K3 * hs[2]); DA(s.dWQ, KQ * hs[0]); DA(s.w46, 2 * hs[0]);
   return 0;
 }
 
@@ -350,32 +353,66 @@ static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* d
   if (din) LEW(conv1d_bwd_in_k, rows * Ci, dout, h->P + k, din, rows, h->N, Ci, Co, KS);
   return 0;
 }
-struct SgcW; static SgcW sgc_w_fwd(sndvae_t* h, int l); static SgcW sgc_w_grad(sndvae_t* h, int l);
 // dM[K-1, hcols] += coef[:, :K-1]^T grad;  db[hcols] += coef[:, K-1]^T grad   (SGC parameter gradients)
 static int coef_grad(sndvae_t* h, const float* coef, int K, const float* grad, int hcols, long long rows, float* dM, float* db) {
   CKB(gemm_rm(h, true, false, K - 1, hcols, (int)rows, 1.f, coef, K, grad, hcols, 1.f, dM, hcols));
   CKB(gemm_rm(h, true, false, 1, hcols, (int)rows, 1.f, coef + (K - 1), K, grad, hcols, 1.f, db, hcols));
   return 0;
 }
-static int sgc_param_grads(sndvae_t* h, int l, const float* dy, SgcScratch& Sx, long long ns) {
-  SgcW w = sgc_w_fwd(h, l); SgcW g = sgc_w_grad(h, l);
-  const int C = w.C, N = h->N; const long long cap = h->E.cap;
-  int r;
-  if ((r = coef_grad(h, Sx.coef1, 3 * C + 4, Sx.ee, w.h0, ns * cap, g.M1, g.b1))) return r;
-  if ((r = coef_grad(h, Sx.coef2, 2 * C + 2 + w.h0, Sx.dm2s, w.h1, ns * N, g.M2, g.b2))) return r;
-  if ((r = coef_grad(h, Sx.coef3, C + w.h1 + 1, dy, w.h2, ns * N, g.M3, g.b3))) return r;
+static SgcDims sgc_dims(sndvae_t* h, int l) {
+  const sndvae_config& c = h->cfg;
+  SgcDims d; d.C = l == 0 ? c.num_feature : c.sg_conv_hidden[0][2];
+  d.h0 = c.sg_conv_hidden[l][0]; d.h1 = c.sg_conv_hidden[l][1]; d.h2 = c.sg_conv_hidden[l][2];
+  return d;
+}
+// assemble [M1b; M1c; w5; b1], [M2; b2], [M3; b3] for both layers (once per step)
+static void sgc_pack(sndvae_t* h) {
+  const PT& p = h->pt;
+  for (int l = 0; l < 2; ++l) {
+    SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+    int n = (2 * d.C + 2) * d.h0 + (2 * d.C + 2 + d.h0) * d.h1 + (d.C + d.h1 + 1) * d.h2;
+    LEW(sgc_pack_weights_k, n, h->P + p.sg_M1[l], h->P + p.sg_b1[l], h->P + p.sg_M2[l], h->P + p.sg_b2[l], h->P + p.sg_M3[l],
+        h->P + p.sg_b3[l], S.WQ, S.W2, S.W3, d);
+  }
+}
+// forward of SGC layer l for `ns` samples starting at global sample s0; x: [ns*N, C]; result in S.y
+static int sgc_layer_fwd(sndvae_t* h, int l, const float* x, long long s0, long long ns) {
+  const PT& p = h->pt; SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+  const int N = h->N, C = d.C, KQ = 2 * C + 2, K2 = 2 * C + 2 + d.h0, K3 = C + d.h1 + 1; const int rows = (int)(ns * N);
+  const float* M1 = h->P + p.sg_M1[l];
+  LAUNCH(sgc_prep_k, (unsigned)ns, 256, 0, x, h->E, d, S, N, s0);
+  CKB(gemm_rm(h, false, false, rows, d.h0, C, 1.f, S.xphi, C, M1, d.h0, 0.f, S.P, d.h0));
+  CKB(gemm_rm(h, false, false, rows, d.h0, KQ, 1.f, S.coefQ, KQ, S.WQ, d.h0, 0.f, S.Qc, d.h0));
+  LAUNCH(sgc_edge_fwd_k, (unsigned)ns, 256, 0, h->E, d, S, M1 + (size_t)(3 * C) * d.h0, M1 + (size_t)(3 * C + 2) * d.h0, N, s0);
+  CKB(gemm_rm(h, false, false, rows, d.h1, K2, 1.f, S.coef2, K2, S.W2, d.h1, 0.f, S.m2s, d.h1));
+  LEW(sgc_cat_k, (long long)rows * K3, S.xphi, S.m2s, S.coef3, (long long)rows, C, d.h1);
+  CKB(gemm_rm(h, false, false, rows, d.h2, K3, 1.f, S.coef3, K3, S.W3, d.h2, 0.f, S.y, d.h2));
   return 0;
 }
-static SgcW sgc_w(sndvae_t* h, float* base, int l) {
-  const sndvae_config& c = h->cfg; const PT& p = h->pt;
-  SgcW w; w.M1 = base + p.sg_M1[l]; w.b1 = base + p.sg_b1[l]; w.M2 = base + p.sg_M2[l]; w.b2 = base + p.sg_b2[l];
-  w.M3 = base + p.sg_M3[l]; w.b3 = base + p.sg_b3[l];
-  w.C = l == 0 ? c.num_feature : c.sg_conv_hidden[0][2];
-  w.h0 = c.sg_conv_hidden[l][0]; w.h1 = c.sg_conv_hidden[l][1]; w.h2 = c.sg_conv_hidden[l][2];
-  return w;
+// backward of SGC layer l (activations of the chunk must be in S): dy [ns*N, h2] -> parameter gradients and,
+// when dx != NULL, dx [ns*N, C]
+static int sgc_layer_bwd(sndvae_t* h, int l, const float* x, const float* dy, float* dx, long long s0, long long ns) {
+  const PT& p = h->pt; SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+  const int N = h->N, C = d.C, KQ = 2 * C + 2, K2 = 2 * C + 2 + d.h0, K3 = C + d.h1 + 1; const int rows = (int)(ns * N);
+  const float* M1 = h->P + p.sg_M1[l];
+  int r;
+  CKB(gemm_rm(h, false, true, rows, K3, d.h2, 1.f, dy, d.h2, S.W3, d.h2, 0.f, S.dcoef3, K3));
+  LEW(sgc_cat_bwd_k, (long long)rows * (C + d.h1), S.dcoef3, x, S.m2s, dx, S.dm2s, (long long)rows, C, d.h1);
+  CKB(gemm_rm(h, false, true, rows, K2, d.h1, 1.f, S.dm2s, d.h1, S.W2, d.h1, 0.f, S.dcoef2, K2));
+  CK(cudaMemsetAsync(S.dQc, 0, sizeof(float) * (size_t)rows * d.h0, h->stream));
+  LAUNCH(sgc_edge_bwd_k, (unsigned)ns, 256, sizeof(float) * 2 * d.h0, h->E, d, S, M1 + (size_t)(3 * C) * d.h0, M1 + (size_t)(3 * C + 2) * d.h0, N, s0);
+  // parameter gradients: coefficient rows (transposed) times the gradient rows
+  if ((r = coef_grad(h, S.coef3, K3, dy, d.h2, rows, h->G + p.sg_M3[l], h->G + p.sg_b3[l]))) return r;
+  if ((r = coef_grad(h, S.coef2, K2, S.dm2s, d.h1, rows, h->G + p.sg_M2[l], h->G + p.sg_b2[l]))) return r;
+  CKB(gemm_rm(h, true, false, C, d.h0, rows, 1.f, S.xphi, C, S.dP, d.h0, 1.f, h->G + p.sg_M1[l], d.h0));       // dM1a
+  CKB(gemm_rm(h, true, false, KQ, d.h0, rows, 1.f, S.coefQ, KQ, S.dQc, d.h0, 1.f, S.dWQ, d.h0));                // d[M1b; M1c; w5; b1]
+  if (dx) {
+    CKB(gemm_rm(h, false, true, rows, C, d.h0, 1.f, S.dP, d.h0, M1, d.h0, 0.f, S.dxphi, C));
+    CKB(gemm_rm(h, false, true, rows, KQ, d.h0, 1.f, S.dQc, d.h0, S.WQ, d.h0, 0.f, S.dcoefQ, KQ));
+    LAUNCH(sgc_node_bwd_k, (unsigned)ns, 256, 0, x, dx, h->E, d, S, N, s0);
+  }
+  return 0;
 }
-static SgcW sgc_w_fwd(sndvae_t* h, int l) { return sgc_w(h, h->P, l); }
-static SgcW sgc_w_grad(sndvae_t* h, int l) { return sgc_w(h, h->G, l); }
 static void ev_begin(sndvae_t* h, double flops) {
   if (h->ev_used < h->ev.size()) { h->ev[h->ev_used].flops = flops; cudaEventRecord(h->ev[h->ev_used].a, h->stream); }
 }
@@ -391,9 +428,10 @@ static int sgc_chunk_fwd(sndvae_t* h, const sndvae_inputs* in, long long s0, lon
   const sndvae_config& c = h->cfg; const PT& p = h->pt; const int N = h->N, F = h->F;
   const int h02 = c.sg_conv_hidden[0][2], h12 = c.sg_conv_hidden[1][2];
   const float* x0 = in->features + s0 * N * F;
-  LAUNCH(sgc_layer_fwd_k, (unsigned)ns, 256, 0, x0, h->E, sgc_w(h, h->P, 0), h->S0, N, s0);
+  int r;
+  if ((r = sgc_layer_fwd(h, 0, x0, s0, ns))) return r;
   bn_fwd(h, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->x1, h02, ns * N, h02, ACT_LRELU, 0);
-  LAUNCH(sgc_layer_fwd_k, (unsigned)ns, 256, 0, h->x1, h->E, sgc_w(h, h->P, 1), h->S1, N, s0);
+  if ((r = sgc_layer_fwd(h, 1, h->x1, s0, ns))) return r;
   bn_fwd(h, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->x2, h12, ns * N, h12, ACT_LRELU, 0);
   // encoder_sg BN (model.py:148; absent in model_joint.py:83)
   bn_fwd(h, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->fsg + s0 * N * h12, h12, ns * N, h12, ACT_NONE, 0);
@@ -436,6 +474,7 @@ static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
   mark(h, "sgc_edges");
   LAUNCH(sgc_build_edges_k, (unsigned)BS, 256, 0, in->adj, in->rel, h->E, N, h->errflag);
   mark(h, "sgc_fwd");
+  sgc_pack(h);
   for (long long s0 = 0; s0 < BS; s0 += h->SC) {
     long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
     int r = sgc_chunk_fwd(h, in, s0, ns); if (r) return r;
@@ -714,6 +753,11 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     if ((r = lin_bwd(h, h->hsg, p.sg_lin[2], h->dls, tmp, BS, Hh, L))) return r;
     LEW(add_inplace_k, BS * Hh, h->dh, tmp, BS * Hh);
     if ((r = lin_bwd(h, h->fsg, p.sg_lin[0], h->dh, h->dfsg, BS, N * h12, Hh))) return r;
+    for (int l = 0; l < 2; ++l) {
+      SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+      CK(cudaMemsetAsync(S.dWQ, 0, sizeof(float) * (2 * d.C + 2) * d.h0, h->stream));
+      CK(cudaMemsetAsync(S.w46, 0, sizeof(float) * 2 * d.h0, h->stream));
+    }
     for (long long s0 = 0; s0 < BS; s0 += h->SC) {
       long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
       mark(h, "sgc_refwd");
@@ -723,14 +767,14 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
       // fsg = BN_encsg(x2); x2 = lrelu(BN_sg1(y1))
       bn_bwd(h, h->dfsg + s0 * N * h12, h12, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h12, ns * N, h12, ACT_NONE, 0);
       bn_bwd(h, h->dxa, h12, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->dxa, h12, ns * N, h12, ACT_LRELU, 0);      // dy1
-      LAUNCH(sgc_layer_bwd_k, (unsigned)ns, 256, 0, h->x1, h->dxa, h->dxb, h->E, sgc_w(h, h->P, 1), h->S1, N, s0);  // dx1
-      mark(h, "sgc_pgrad");
-      if ((r = sgc_param_grads(h, 1, h->dxa, h->S1, ns))) return r;
+      if ((r = sgc_layer_bwd(h, 1, h->x1, h->dxa, h->dxb, s0, ns))) return r;                                       // dx1
       mark(h, "sgc_bwd_act");
       bn_bwd(h, h->dxb, h02, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->dxb, h02, ns * N, h02, ACT_LRELU, 0);      // dy0
-      LAUNCH(sgc_layer_bwd_k, (unsigned)ns, 256, 0, x0, h->dxb, (float*)nullptr, h->E, sgc_w(h, h->P, 0), h->S0, N, s0);
-      mark(h, "sgc_pgrad");
-      if ((r = sgc_param_grads(h, 0, h->dxb, h->S0, ns))) return r;
+      if ((r = sgc_layer_bwd(h, 0, x0, h->dxb, nullptr, s0, ns))) return r;
+    }
+    for (int l = 0; l < 2; ++l) {
+      SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+      LEW(sgc_unpack_grads_k, (2 * d.C + 4) * d.h0, S.dWQ, S.w46, h->G + p.sg_M1[l], h->G + p.sg_b1[l], d);
     }
   }
   return 0;
@@ -857,7 +901,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   }
   if (c.chunk_graphs > h->B) c.chunk_graphs = (int)h->B;
   h->Bc = c.chunk_graphs;
-  { long long per_sample = (long long)h->N * 900 * 4 + (long long)c.edge_capacity * 145 * 4;
+  { long long per_sample = (long long)h->N * 1200 * 4;     // SGC scratch: ~820 + ~210 floats per node for the two layers
     long long sc = (4LL << 30) / per_sample; if (sc < 1) sc = 1; if (sc > h->BS) sc = h->BS; h->SC = (int)sc; }
   if ((long long)2 * h->Bc * h->N * h->N * h->C1 > 2000000000LL) return fail(h, SNDVAE_E_ARG, "chunk too large for 32-bit GEMM dims");
   build_table(h);      // host-only: the table is valid even when no device is present (checked by the CPU tests)
