@@ -160,7 +160,7 @@ struct TMapSet { CUtensorMap h[4]; CUtensorMap l[4]; };   // window views of the
 #endif
 #define TC_EPI_WARPS 8
 #define TC_THREADS (64 + 32 * TC_EPI_WARPS)
-template <int BN>
+template <int BN, int NSTAGE>
 __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                                                              const __grid_constant__ TMapSet tmB, ToepArgs P) {
   constexpr int A_BYTES = TC_BM * TC_KC * 2;       // 16 KB
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
   static_assert(BN <= 256 && HC % 8 == 0, "tile shape");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
   const int ngroups = (nk + TC_GROUP - 1) / TC_GROUP;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       for (int it = 0; it < nk; ++it) {
-        const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
+        const int s = it % NSTAGE; const uint32_t ph = (it / NSTAGE) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + (size_t)s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
       for (int it = 0; it < nk; ++it) {
         const int g = it / TC_GROUP, gi = it - g * TC_GROUP, slot = g & 1;
         if (gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }   // slot drained by the epilogue
-        const int s = it % TC_STAGES; const uint32_t ph = (it / TC_STAGES) & 1;
+        const int s = it % NSTAGE; const uint32_t ph = (it / NSTAGE) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
@@ -288,6 +288,184 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster share one 256 x BN tile.  Each CTA loads its own
+// 128 rows of A and HALF of the B tile; the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads
+// the B halves from both CTAs' shared memory, and each CTA's TMEM receives its own 128 rows.  Per CTA this
+// halves the B fill traffic and shrinks a stage to 62 KB (3-stage ring), relieving the shared-memory
+// bandwidth that bounds the single-CTA kernel (SS-mode MMA reads + TMA fills > 128 B/cycle/SM).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+#define TC2_STAGES 3
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+toep_gemm2_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ TMapSet tmB, ToepArgs P) {
+  constexpr int A_BYTES = TC_BM * TC_KC * 2;       // 16 KB: this CTA's 128 rows
+  constexpr int BH_BYTES = (BN / 2) * TC_KC * 2;   // 15 KB: this CTA's half of the B tile
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr int HC = BN / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[TC2_STAGES], empty_bar[TC2_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cl = blockIdx.x >> 1;
+  const int ntile = cl % (P.n_ctiles * P.n_jtiles);
+  const int mpair = cl / (P.n_ctiles * P.n_jtiles);
+  const int ct = ntile % P.n_ctiles, jt = ntile / P.n_ctiles;
+  const int ch0 = ct * P.CT, jr0 = jt * P.JT;
+  const int m0 = mpair * 2 * TC_BM + (int)rank * TC_BM;
+  long long xlo = (long long)(P.pad_rows - jr0 - P.JT + 1) * P.CS - (TC_KC - 1);
+  long long xhi = (long long)(P.pad_rows + P.N - jr0) * P.CS;
+  if (xlo < 0) xlo = 0;
+  if (xhi > P.KA) xhi = P.KA;
+  const int kc_lo = (int)(xlo / TC_KC);
+  const int kc_hi = (int)((xhi + TC_KC - 1) / TC_KC);
+  const int nk = kc_hi > kc_lo ? kc_hi - kc_lo : 0;
+  const int ngroups = (nk + TC_GROUP - 1) / TC_GROUP;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // both CTAs' barriers are initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // this CTA's rows of the B tile: sub-boxes [rank * nsh/2, (rank+1) * nsh/2) of the nsh shifted copies
+      const int sub = (BN * TC_KC * 2) / P.nsh, u0 = jr0 / P.nsh, r_lo = (int)rank * (P.nsh / 2);
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % TC2_STAGES; const uint32_t ph = (it / TC2_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+        const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[s]), 0);      // the leader's full barrier
+        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);        // bytes of both CTAs
+        const int x = (kc_lo + it) * TC_KC;
+        tma_load_2d_2sm(st, &tmAh, lead_full, x, m0);
+        tma_load_2d_2sm(st + A_BYTES, &tmAl, lead_full, x, m0);
+        for (int r = 0; r < P.nsh / 2; ++r) {
+          tma_load_3d_2sm(st + 2 * A_BYTES + r * sub, &tmB.h[r_lo + r], lead_full, x, u0, ch0);
+          tma_load_3d_2sm(st + 2 * A_BYTES + BH_BYTES + r * sub, &tmB.l[r_lo + r], lead_full, x, u0, ch0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(2 * TC_BM, BN, 0, 0);
+      for (int it = 0; it < nk; ++it) {
+        const int g = it / TC_GROUP, gi = it - g * TC_GROUP, slot = g & 1;
+        if (gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }   // drained by both CTAs
+        const int s = it % TC2_STAGES; const uint32_t ph = (it / TC2_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t td = tmem_d + slot * 256;
+#pragma unroll
+        for (int k = 0; k < TC_KC / 16; ++k) {
+          const uint64_t ah = umma_desc_kmajor(sa + k * 32);
+          const uint64_t al = umma_desc_kmajor(sa + A_BYTES + k * 32);
+          const uint64_t bh = umma_desc_kmajor(sa + 2 * A_BYTES + k * 32);
+          const uint64_t bl = umma_desc_kmajor(sa + 2 * A_BYTES + BH_BYTES + k * 32);
+          umma_bf16_2sm(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
+          umma_bf16_2sm(td, ah, bl, idesc, 1u);
+          umma_bf16_2sm(td, al, bh, idesc, 1u);
+        }
+        umma_commit_2sm(&empty_bar[s]);                                          // frees the stage in both CTAs
+        if (gi == TC_GROUP - 1 || it == nk - 1) umma_commit_2sm(&acc_full[slot]); // group complete, both CTAs
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float acc[HC];
+#pragma unroll
+    for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+    for (int g = 0; g < ngroups; ++g) {
+      const int slot = g & 1;
+      mbar_wait(&acc_full[slot], (g >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ta = tmem_d + slot * 256 + ((uint32_t)(q * 32) << 16) + half * HC;
+#pragma unroll
+      for (int c0 = 0; c0 < HC; c0 += 8) {
+        uint32_t r[8];
+        tmem_ld8(ta + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[slot]), 0));   // the leader collects 16 arrivals
+    }
+    const long long row = (long long)m0 + q * 32 + lane;
+    if (row < P.rows) {
+      float* orow = P.out + row * (long long)P.N * P.Cout;
+#pragma unroll
+      for (int i = 0; i < HC; ++i) {
+        const int n = half * HC + i;
+        const int jts = P.JT / P.nsh, per = P.CT * jts;
+        const int r = n / per, w = n - r * per;
+        const int chl = w / jts, u = w - chl * jts;
+        const int jr = jr0 + u * P.nsh + r;
+        const int j = P.N - 1 - jr;
+        if (j >= 0) {
+          float* dst = orow + (long long)j * P.Cout + ch0 + chl;
+          *dst = P.accumulate ? *dst + acc[i] : acc[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // no CTA of the pair exits while the other may still signal it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -484,10 +662,13 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_tc_encode = nullptr;
+static size_t tc_toep2_smem(int bn) { return (size_t)TC2_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * (bn / 2) * TC_KC * 2) + 1024; }
+static int g_tc_2cta = -1;
+static size_t tc_toep_smem(int bn, int stages) { return (size_t)stages * (2 * TC_BM * TC_KC * 2 + 2 * bn * TC_KC * 2) + 1024; }
 
 struct ToepPlan {
   int ready, N, Cin, Cout, CSi, CSo;
-  int fCT, fJT, dCT, dJT;                  // tile shapes (channels x positions, product 240)
+  int fCT, fJT, dCT, dJT;                  // tile shapes (channels x positions); product = BN in {240, 160}
   int nsf, nsd;                            // shifted weight copies (window starts must be 16-byte aligned)
   long long LFp, LDp;                      // padded row lengths of the staged weights
   __nv_bfloat16 *Wfh, *Wfl, *Wdh, *Wdl;    // staged weights [nsh][channels][Lp]
@@ -525,7 +706,9 @@ static int tc_global_init() {
     snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled entry point not found"); return -1;
   }
   g_tc_encode = (PFN_encodeTiled)fn;
-  cudaFuncSetAttribute(toep_gemm_k<240>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024);
+  cudaFuncSetAttribute(toep_gemm_k<240, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep_smem(240, 2));
+  cudaFuncSetAttribute(toep_gemm_k<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep_smem(160, 3));
+  cudaFuncSetAttribute(toep_gemm2_k<240>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep2_smem(240));
   cudaFuncSetAttribute(wgrad_gemm_k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_WSTAGES * (2 * TC_WKC * TC_BM * 2 + 2 * TC_WKC * TC_WN * 2) + 1024);
   return 0;
 }
@@ -544,7 +727,7 @@ static int tc_plan_init(ToepPlan& pl, int N, int Cin, int Cout, int fCT, int fJT
   pl.CSi = tc_stride(N, Cin, fJT, compact); pl.CSo = tc_stride(N, Cout, dJT, compact);
   pl.nsf = 16 / tc_gcd(16, pl.CSi * 2); pl.nsd = 16 / tc_gcd(16, pl.CSo * 2);
   pl.fCT = fCT; pl.fJT = fJT; pl.dCT = dCT; pl.dJT = dJT;
-  if (fCT * fJT != 240 || dCT * dJT != 240 || Cout % fCT || Cin % dCT || fJT % pl.nsf || dJT % pl.nsd) { snprintf(g_tc_err, sizeof g_tc_err, "bad tile shape"); return -1; }
+  if ((fCT * fJT != 240 && fCT * fJT != 160) || (dCT * dJT != 240 && dCT * dJT != 160) || Cout % fCT || Cin % dCT || fJT % pl.nsf || dJT % pl.nsd) { snprintf(g_tc_err, sizeof g_tc_err, "bad tile shape"); return -1; }
   pl.LFp = ((long long)(2 * N - 1 + 4) * pl.CSi + 7) / 8 * 8; pl.LDp = ((long long)(2 * N - 1 + 4) * pl.CSo + 7) / 8 * 8;
   size_t nf = (size_t)pl.nsf * Cout * pl.LFp + 2 * TC_KC, nd = (size_t)pl.nsd * Cin * pl.LDp + 2 * TC_KC;
   if (cudaMalloc(&pl.Wfh, nf * 2) || cudaMalloc(&pl.Wfl, nf * 2) || cudaMalloc(&pl.Wdh, nd * 2) || cudaMalloc(&pl.Wdl, nd * 2)) {
@@ -591,7 +774,6 @@ static int tc_split(const float* src, __nv_bfloat16* hi, __nv_bfloat16* lo, long
   tc_split_planes_k<<<cdiv(rows * C, 256), 256, 0, st>>>(src, hi, lo, rows, C, CS);
   return tc_check_launch("tc_split_planes_k");
 }
-static const size_t TC_TOEP_SMEM = TC_STAGES * (2 * TC_BM * TC_KC * 2 + 2 * 240 * TC_KC * 2) + 1024;
 static const size_t TC_WGRAD_SMEM = TC_WSTAGES * (2 * TC_WKC * TC_BM * 2 + 2 * TC_WKC * TC_WN * 2) + 1024;
 
 // out[rows, N*Cout] (+)= in[rows, N*CSi planes] . Toeplitz(w)
@@ -603,7 +785,12 @@ static int tc_plan_fwd(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bfloat
   a.n_ctiles = pl.Cout / pl.fCT; a.n_jtiles = (pl.N + pl.fJT - 1) / pl.fJT; a.pad_rows = pl.N - 1 - (pl.N - 1) / 2; a.KA = pl.N * pl.CSi;
   a.accumulate = accumulate; a.nsh = pl.nsf;
   unsigned grid = (unsigned)(((rows + TC_BM - 1) / TC_BM) * a.n_ctiles * a.n_jtiles);
-  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.fB, a);
+  if (g_tc_2cta < 0) g_tc_2cta = getenv("SNDVAE_TC_2CTA") ? atoi(getenv("SNDVAE_TC_2CTA")) : 1;   // CTA pairs by default
+  if (g_tc_2cta && a.CT * a.JT == 240 && a.nsh >= 2) {
+    unsigned grid2 = (unsigned)(2 * ((rows + 2 * TC_BM - 1) / (2 * TC_BM)) * a.n_ctiles * a.n_jtiles);
+    toep_gemm2_k<240><<<grid2, TC_THREADS, tc_toep2_smem(240), st>>>(ah, al, pl.fB, a);
+  } else if (a.CT * a.JT == 240) toep_gemm_k<240, 2><<<grid, TC_THREADS, tc_toep_smem(240, 2), st>>>(ah, al, pl.fB, a);
+  else toep_gemm_k<160, 3><<<grid, TC_THREADS, tc_toep_smem(160, 3), st>>>(ah, al, pl.fB, a);
   return tc_check_launch("toep_gemm_k(fwd)");
 }
 // din[rows, N*Cin] (+)= dout[rows, N*CSo planes] . Toeplitz(w)^T
@@ -615,7 +802,12 @@ static int tc_plan_dgrad(ToepPlan& pl, const __nv_bfloat16* doh, const __nv_bflo
   a.n_ctiles = pl.Cin / pl.dCT; a.n_jtiles = (pl.N + pl.dJT - 1) / pl.dJT; a.pad_rows = (pl.N - 1) / 2; a.KA = pl.N * pl.CSo;
   a.accumulate = accumulate; a.nsh = pl.nsd;
   unsigned grid = (unsigned)(((rows + TC_BM - 1) / TC_BM) * a.n_ctiles * a.n_jtiles);
-  toep_gemm_k<240><<<grid, TC_THREADS, TC_TOEP_SMEM, st>>>(ah, al, pl.dB, a);
+  if (g_tc_2cta < 0) g_tc_2cta = getenv("SNDVAE_TC_2CTA") ? atoi(getenv("SNDVAE_TC_2CTA")) : 1;   // CTA pairs by default
+  if (g_tc_2cta && a.CT * a.JT == 240 && a.nsh >= 2) {
+    unsigned grid2 = (unsigned)(2 * ((rows + 2 * TC_BM - 1) / (2 * TC_BM)) * a.n_ctiles * a.n_jtiles);
+    toep_gemm2_k<240><<<grid2, TC_THREADS, tc_toep2_smem(240), st>>>(ah, al, pl.dB, a);
+  } else if (a.CT * a.JT == 240) toep_gemm_k<240, 2><<<grid, TC_THREADS, tc_toep_smem(240, 2), st>>>(ah, al, pl.dB, a);
+  else toep_gemm_k<160, 3><<<grid, TC_THREADS, tc_toep_smem(160, 3), st>>>(ah, al, pl.dB, a);
   return tc_check_launch("toep_gemm_k(dgrad)");
 }
 // dw[t, coff+c, q] += sum_rows sum_j in[row, j+t-p, c] dout[row, j, q]
@@ -640,7 +832,9 @@ static int tc_init(TcState& s, int N, int Chv, long long B, cudaStream_t st) {
   memset(&s, 0, sizeof s);
   if (tc_global_init()) return -1;
   const int compact = getenv("SNDVAE_TC_PADDED") ? 0 : 1;      // compact channel strides cut the padded-K MMA work
-  if (tc_plan_init(s.l1, N, TC_C1, TC_C2, 20, 12, 10, 24, compact, st)) return -1;
+  // SNDVAE_TC_BN160: 128x160 tiles with a 3-stage ring instead of 128x240 with 2 stages
+  const int bn160 = getenv("SNDVAE_TC_BN160") ? 1 : 0;
+  if (tc_plan_init(s.l1, N, TC_C1, TC_C2, 20, bn160 ? 8 : 12, 10, bn160 ? 16 : 24, compact, st)) return -1;
   if (tc_plan_init(s.l0a, N, Chv, TC_C1, 10, 24, 10, 24, 0, st)) return -1;
   if (tc_plan_init(s.l0c, N, Chv, TC_C1, 10, 24, 10, 24, 0, st)) return -1;
   size_t ni = (size_t)B * N * s.l0a.CSi, no = (size_t)B * N * s.l0a.CSo;
