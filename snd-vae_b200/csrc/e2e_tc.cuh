@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) toep_gemm_k(const __grid_consta
         const int chl = w / jts, u = w - chl * jts;
         const int jr = jr0 + u * P.nsh + r;
         const int j = P.N - 1 - jr;
-        if (j >= 0) {
+        if (j >= 0 && ch0 + chl < P.Cout) {
           float* dst = orow + (long long)j * P.Cout + ch0 + chl;
           *dst = P.accumulate ? *dst + acc[i] : acc[i];
         }
@@ -452,7 +452,7 @@ toep_gemm2_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ C
         const int chl = w / jts, u = w - chl * jts;
         const int jr = jr0 + u * P.nsh + r;
         const int j = P.N - 1 - jr;
-        if (j >= 0) {
+        if (j >= 0 && ch0 + chl < P.Cout) {
           float* dst = orow + (long long)j * P.Cout + ch0 + chl;
           *dst = P.accumulate ? *dst + acc[i] : acc[i];
         }
@@ -481,6 +481,7 @@ struct WgradArgs {
   int Ctot, coff;
   int n_ntiles;        // ceil(N*CSo / 256)
   int ksplit;          // CTAs per output tile along K
+  int plain;           // 1: no Toeplitz folding: dw[(m / CSi) * Cin + m % CSi][n] += D[m, n] for n < Cout (row stride Cout)
 };
 #define TC_WN 256
 #define TC_WGROUP (512 / TC_WKC)
@@ -504,8 +505,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
   // band test: does any (j', j) in this tile have 0 <= j'-j+p < N ?
   const int jp_lo = m0 / P.CSi, jp_hi = min(P.N - 1, (m0 + TC_BM - 1) / P.CSi);
   const int j_lo = n0 / P.CSo, j_hi = min(P.N - 1, (n0 + TC_WN - 1) / P.CSo);
-  if (jp_lo > P.N - 1 || j_lo > P.N - 1) return;
-  if (jp_hi - j_lo + p < 0 || jp_lo - j_hi + p > P.N - 1) return;
+  if (!P.plain) {
+    if (jp_lo > P.N - 1 || j_lo > P.N - 1) return;
+    if (jp_hi - j_lo + p < 0 || jp_lo - j_hi + p > P.N - 1) return;
+  }
   const long long kchunks = (P.rows + TC_WKC - 1) / TC_WKC;
   const long long per = (kchunks + P.ksplit - 1) / P.ksplit;
   const long long kc_lo = (long long)ks * per;
@@ -595,7 +598,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) wgrad_gemm_k(const __grid_const
     }
     const int m = m0 + q * 32 + lane;
     const int jp = m / P.CSi, c = m - jp * P.CSi;
-    if (jp < P.N && c < P.Cin) {
+    if (P.plain) {
+      if (jp < P.N && c < P.Cin) {
+#pragma unroll
+        for (int i = 0; i < HC; ++i) {
+          const int n = n0 + half * HC + i;
+          if (n < P.Cout) atomicAdd(P.dw + ((size_t)jp * P.Cin + c) * P.Cout + n, acc[i]);
+        }
+      }
+    } else if (jp < P.N && c < P.Cin) {
 #pragma unroll
       for (int i = 0; i < HC; ++i) {
         const int n = n0 + half * HC + i;
@@ -709,6 +720,7 @@ static int tc_global_init() {
   cudaFuncSetAttribute(toep_gemm_k<240, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep_smem(240, 2));
   cudaFuncSetAttribute(toep_gemm_k<160, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep_smem(160, 3));
   cudaFuncSetAttribute(toep_gemm2_k<240>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep2_smem(240));
+  cudaFuncSetAttribute(toep_gemm_k<48, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_toep_smem(48, 4));
   cudaFuncSetAttribute(wgrad_gemm_k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_WSTAGES * (2 * TC_WKC * TC_BM * 2 + 2 * TC_WKC * TC_WN * 2) + 1024);
   return 0;
 }
@@ -823,7 +835,7 @@ static int tc_plan_wgrad(ToepPlan& pl, const __nv_bfloat16* inh, const __nv_bflo
   long long kchunks = (rows + TC_WKC - 1) / TC_WKC;
   int ks = 1;
   while (tiles * ks < 2 * 148 && ks * 8 < kchunks) ks *= 2;     // fill the 148 SMs when N is small
-  a.ksplit = ks;
+  a.ksplit = ks; a.plain = 0;
   wgrad_gemm_k<<<(unsigned)(tiles * ks), TC_THREADS, TC_WGRAD_SMEM, st>>>(ah, al, bh, bl, a);
   return tc_check_launch("wgrad_gemm_k");
 }
@@ -852,4 +864,92 @@ static void tc_destroy(TcState& s) {
   __nv_bfloat16* ps[8] = {s.ah, s.al, s.ch, s.cl, s.dsh, s.dsl, s.drh, s.drl};
   for (int i = 0; i < 8; ++i) if (ps[i]) cudaFree(ps[i]);
   memset(&s, 0, sizeof s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Layer-0 dense contractions on the tensor cores (the K = 2H products with the [rows, N*C1] tensors):
+//   da[(b,i), :]     = dE1[(b,i), (j,o)] . WSa[(j,o), :]   (and dc with dE1^T / WSc)
+//   dWSa[(j,o), :]  += dE1^T . a                           (and dWSc with dE1^T^T / c)
+// They reuse the Toeplitz kernels with trivial window maps (one position, or position stride = a whole weight row).
+// ------------------------------------------------------------------------------------------
+struct L0Dense {
+  int ready, N, Ch, CSk, C1, CSe;      // Ch = 2H (K of the forward product), CSk its plane stride; CSe = channel stride of dE1 planes
+  __nv_bfloat16 *wf_h[2], *wf_l[2];    // forward B planes  [jr][o][CSk]      (0 = WSa, 1 = WSc)
+  __nv_bfloat16 *wb_h[2], *wb_l[2];    // backward B planes [48][N*CSe]       rows = ch
+  TMapSet mf[2], mb[2];
+};
+// WS fp32 [N][C1][Ch] -> forward planes (position reversed) and backward planes (channel-major rows over k = (j, o))
+__global__ void tc_stage_ws_k(const float* __restrict__ WS, __nv_bfloat16* __restrict__ fh, __nv_bfloat16* __restrict__ fl,
+                              __nv_bfloat16* __restrict__ bh, __nv_bfloat16* __restrict__ bl, int N, int C1, int Ch, int CSk, int CSe) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * C1 * Ch) return;
+  const int ch = idx % Ch; const int o = (idx / Ch) % C1; const int j = idx / ((long long)Ch * C1);
+  const float v = WS[idx];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v), lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const long long f = ((long long)(N - 1 - j) * C1 + o) * CSk + ch;
+  fh[f] = hi; fl[f] = lo;
+  const long long b = (long long)ch * N * CSe + (long long)j * CSe + o;
+  bh[b] = hi; bl[b] = lo;
+}
+static int l0d_init(L0Dense& d, int N, int Ch, int C1, cudaStream_t st) {
+  memset(&d, 0, sizeof d);
+  d.N = N; d.Ch = Ch; d.C1 = C1; d.CSk = tc_pad16(Ch); d.CSe = tc_stride(N, C1, 4, 1);
+  for (int w = 0; w < 2; ++w) {
+    size_t nf = (size_t)N * C1 * d.CSk + 2 * TC_KC, nb = (size_t)48 * N * d.CSe + 2 * TC_KC;
+    if (cudaMalloc(&d.wf_h[w], nf * 2) || cudaMalloc(&d.wf_l[w], nf * 2) || cudaMalloc(&d.wb_h[w], nb * 2) || cudaMalloc(&d.wb_l[w], nb * 2)) {
+      snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of layer-0 dense planes failed"); return -1;
+    }
+    cudaMemsetAsync(d.wf_h[w], 0, nf * 2, st); cudaMemsetAsync(d.wf_l[w], 0, nf * 2, st);
+    cudaMemsetAsync(d.wb_h[w], 0, nb * 2, st); cudaMemsetAsync(d.wb_l[w], 0, nb * 2, st);
+    {   // forward: dims (x = Ch, jr = N positions, o = C1 channels); row (o, jr) = planes[jr][o][:]
+      cuuint64_t dims[3] = {(cuuint64_t)Ch, (cuuint64_t)N, (cuuint64_t)C1};
+      cuuint64_t str[2] = {(cuuint64_t)C1 * d.CSk * 2, (cuuint64_t)d.CSk * 2};
+      cuuint32_t box[3] = {TC_KC, 24, 10};
+      if (tc_encode(&d.mf[w].h[0], d.wf_h[w], 3, dims, str, box, TC_KSWZ) || tc_encode(&d.mf[w].l[0], d.wf_l[w], 3, dims, str, box, TC_KSWZ)) return -1;
+    }
+    {   // backward: dims (x = N*CSe, one position, ch = Ch channels); box of 48 channel rows (rows >= Ch are zero-filled)
+      cuuint64_t dims[3] = {(cuuint64_t)N * d.CSe, 1, (cuuint64_t)Ch};
+      cuuint64_t str[2] = {(cuuint64_t)N * d.CSe * 2, (cuuint64_t)N * d.CSe * 2};
+      cuuint32_t box[3] = {TC_KC, 1, 48};
+      if (tc_encode(&d.mb[w].h[0], d.wb_h[w], 3, dims, str, box, TC_KSWZ) || tc_encode(&d.mb[w].l[0], d.wb_l[w], 3, dims, str, box, TC_KSWZ)) return -1;
+    }
+  }
+  d.ready = 1;
+  return 0;
+}
+static void l0d_destroy(L0Dense& d) {
+  for (int w = 0; w < 2; ++w) { if (d.wf_h[w]) cudaFree(d.wf_h[w]); if (d.wf_l[w]) cudaFree(d.wf_l[w]); if (d.wb_h[w]) cudaFree(d.wb_h[w]); if (d.wb_l[w]) cudaFree(d.wb_l[w]); }
+  memset(&d, 0, sizeof d);
+}
+static int l0d_stage(L0Dense& d, int w, const float* WS, cudaStream_t st) {
+  long long n = (long long)d.N * d.C1 * d.Ch;
+  tc_stage_ws_k<<<cdiv(n, 256), 256, 0, st>>>(WS, d.wf_h[w], d.wf_l[w], d.wb_h[w], d.wb_l[w], d.N, d.C1, d.Ch, d.CSk, d.CSe);
+  return tc_check_launch("tc_stage_ws_k");
+}
+// dact[rows, Ch] = dE1 planes[rows, N*CSe] . WS
+static int l0d_bwd_act(L0Dense& d, int w, const __nv_bfloat16* eh_, const __nv_bfloat16* el_, float* dact, long long rows, long long rows_alloc,
+                       cudaStream_t st) {
+  CUtensorMap ah, al;
+  if (tc_encode_rows(&ah, eh_, (long long)d.N * d.CSe, rows_alloc, TC_KC, TC_BM, TC_KSWZ) || tc_encode_rows(&al, el_, (long long)d.N * d.CSe, rows_alloc, TC_KC, TC_BM, TC_KSWZ)) return -1;
+  ToepArgs a; a.out = dact; a.rows = rows; a.N = 1; a.Cout = d.Ch; a.CS = d.N * d.CSe; a.CT = 48; a.JT = 1; a.n_ctiles = 1; a.n_jtiles = 1;
+  a.pad_rows = 0; a.KA = d.N * d.CSe; a.accumulate = 0; a.nsh = 1;
+  unsigned grid = (unsigned)((rows + TC_BM - 1) / TC_BM);
+  toep_gemm_k<48, 4><<<grid, TC_THREADS, tc_toep_smem(48, 4), st>>>(ah, al, d.mb[w], a);
+  return tc_check_launch("toep_gemm_k(l0 dense bwd)");
+}
+// dWS[(j,o), ch] += sum_rows dE1[row, (j,o)] act[row, ch]
+static int l0d_bwd_w(L0Dense& d, const __nv_bfloat16* eh_, const __nv_bfloat16* el_, const __nv_bfloat16* ah_, const __nv_bfloat16* al_,
+                     float* dWS, long long rows, cudaStream_t st) {
+  CUtensorMap ah, al, bh, bl;
+  if (tc_encode_rows(&ah, eh_, (long long)d.N * d.CSe, rows, 64, TC_WKC) || tc_encode_rows(&al, el_, (long long)d.N * d.CSe, rows, 64, TC_WKC) ||
+      tc_encode_rows(&bh, ah_, d.CSk, rows, 64, TC_WKC) || tc_encode_rows(&bl, al_, d.CSk, rows, 64, TC_WKC)) return -1;
+  WgradArgs a; a.dw = dWS; a.rows = rows; a.N = d.N; a.CSi = d.CSe; a.Cin = d.C1; a.CSo = d.CSk; a.Cout = d.Ch; a.Ctot = 0; a.coff = 0;
+  a.n_ntiles = 1; a.plain = 1;
+  int n_mtiles = (d.N * d.CSe + TC_BM - 1) / TC_BM;
+  long long kchunks = (rows + TC_WKC - 1) / TC_WKC;
+  int ks = 1;
+  while ((long long)n_mtiles * ks < 2 * 148 && ks * 8 < kchunks) ks *= 2;
+  a.ksplit = ks;
+  wgrad_gemm_k<<<(unsigned)(n_mtiles * ks), TC_THREADS, TC_WGRAD_SMEM, st>>>(ah, al, bh, bl, a);
+  return tc_check_launch("wgrad_gemm_k(l0 dense)");
 }

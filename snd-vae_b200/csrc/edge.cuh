@@ -195,6 +195,65 @@ __global__ void __launch_bounds__(YP_THREADS) y_producer_k(const float* __restri
   }
 }
 
+// backward counterpart of l0_combine_k for the tensor-core path: dE1 leaves as bf16 hi / lo planes in both
+// layouts (operands of the da / dc / dWS products), dSa[b,i,:] = sum_j dE1 is reduced here.
+__global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float* __restrict__ E1, const float* __restrict__ gam1,
+                                    const float* __restrict__ bet1, float* __restrict__ g_gam1, float* __restrict__ g_bet1,
+                                    float* __restrict__ g_b0, __nv_bfloat16* __restrict__ Ph, __nv_bfloat16* __restrict__ Pl,
+                                    float* __restrict__ dSa, int Bc, int N, int C1, int CS) {
+  extern __shared__ float sm[];           // [4][blockDim]
+  const long long row = blockIdx.x;
+  const int i = (int)(row % N); const long long b = row / N;
+  const long long plane_f = (long long)Bc * N * N * C1, plane_c = (long long)Bc * N * N;
+  const int o = threadIdx.x % C1;
+  const float g = gam1[o] * BN_RS, bt = bet1[o];
+  float sg = 0.f, sb = 0.f, s0 = 0.f;
+  for (int idx = threadIdx.x; idx < N * C1; idx += blockDim.x) {
+    const int j = idx / C1;
+    const long long a0 = row * N * C1 + idx;
+    const long long c1 = (b * N + j) * N + i;
+    const float dy = dY12[a0] + dY12[plane_f + c1 * C1 + o];
+    const float e = E1[a0];
+    const float dd = fmaf(e, g, bt) > 0.f ? dy : 0.f;
+    sg = fmaf(dd, e, sg); sb += dd;
+    const float de = dd * g;
+    s0 += de;
+    __nv_bfloat16 hi, lo; split_bf16(de, hi, lo);
+    const long long c0 = row * N + j;
+    Ph[c0 * CS + o] = hi; Pl[c0 * CS + o] = lo;
+    Ph[(plane_c + c1) * CS + o] = hi; Pl[(plane_c + c1) * CS + o] = lo;
+  }
+  float* r0 = sm; float* r1 = sm + blockDim.x; float* r2 = sm + 2 * blockDim.x;
+  r0[threadIdx.x] = sg; r1[threadIdx.x] = sb; r2[threadIdx.x] = s0;
+  __syncthreads();
+  if (threadIdx.x < C1) {
+    float a = 0.f, bq = 0.f, cq = 0.f;
+    for (int t = threadIdx.x; t < blockDim.x; t += C1) { a += r0[t]; bq += r1[t]; cq += r2[t]; }
+    atomicAdd(g_gam1 + o, a * BN_RS); atomicAdd(g_bet1 + o, bq); atomicAdd(g_b0 + o, 2.f * cq);
+    dSa[row * C1 + o] = cq;
+  }
+}
+
+// out[row, o] = sum_s (hi + lo)[row, s, o] over bf16 planes [rows, N, CS]  (dRc from the transposed dE1 planes)
+__global__ void rowsum_planes_k(const __nv_bfloat16* __restrict__ Ph, const __nv_bfloat16* __restrict__ Pl, float* __restrict__ out,
+                                int N, int C, int CS) {
+  extern __shared__ float sm[];
+  const long long row = blockIdx.x;
+  const int o = threadIdx.x % C;
+  float s = 0.f;
+  for (int idx = threadIdx.x; idx < N * C; idx += blockDim.x) {
+    const long long a = (row * N + idx / C) * CS + o;
+    s += __bfloat162float(Ph[a]) + __bfloat162float(Pl[a]);
+  }
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.f;
+    for (int t = threadIdx.x; t < blockDim.x; t += C) a += sm[t];
+    out[row * C + o] = a;
+  }
+}
+
 // ---- e2e layer 1, fp32 SIMT reference kernels (stacked operands, one "row" = (dir, b, r)) --------
 // out[row, s, q] = sum_{s'} sum_o Yf[row, s', o] w1[s'-s+p][o][q]
 __global__ void e2e_l1_simt_fwd_k(const float* __restrict__ Yf, const float* __restrict__ w1, float* __restrict__ out,

@@ -107,15 +107,15 @@ __global__ void im2col_k(const float* __restrict__ X, float* __restrict__ col, l
   col[idx] = (nn >= 0 && nn < N) ? X[(r + t - pb) * Ci + ci] : 0.f;
 }
 
-// db[c] += sum_r dY[r, c]
+// db[c] += sum_r dY[r, c];  grid = (row slabs, column tiles of blockDim.x)
 __global__ void colsum_k(const float* __restrict__ dY, int ldy, float* __restrict__ db, long long rows, int C) {
   long long r0 = (long long)blockIdx.x * XTDY_SLAB;
   long long r1 = r0 + XTDY_SLAB; if (r1 > rows) r1 = rows;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
-    for (long long r = r0; r < r1; ++r) acc += dY[r * ldy + c];
-    atomicAdd(db + c, acc);
-  }
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += dY[r * ldy + c];
+  atomicAdd(db + c, acc);
 }
 
 // ---- Keras BN (inference affine, SURVEY finding 3) fused with an activation ------------

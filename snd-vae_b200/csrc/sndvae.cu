@@ -64,7 +64,7 @@ struct sndvae_handle {
   float *colbuf;                       // [Rn, 5 * 50] im2col staging for conv1d weight gradients
   float *E1, *O12, *dY12, *Yf, *dOf;   // chunk buffers (fp32)
   __nv_bfloat16 *Yhi, *Ylo, *dOhi, *dOlo;
-  TcState tc;
+  TcState tc; L0Dense l0d;
   float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg
   int* errflag;
   float* pinned_loss;
@@ -330,7 +330,7 @@ static int lin_fwd(sndvae_t* h, const float* X, const long* mb, float* Y, long l
 // dW += X^T dY; db += colsum(dY); dX = dY W^T (optional)
 static int lin_bwd(sndvae_t* h, const float* X, const long* mb, const float* dY, float* dX, long long rows, int i, int o) {
   CKB(gemm_rm(h, true, false, i, o, (int)rows, 1.f, X, i, dY, o, 1.f, h->G + mb[0], o));
-  LAUNCH(colsum_k, cdiv(rows, XTDY_SLAB), 128, 0, dY, o, h->G + mb[1], rows, o);
+  LAUNCH(colsum_k, dim3(cdiv(rows, XTDY_SLAB), cdiv(o, 128)), 128, 0, dY, o, h->G + mb[1], rows, o);
   if (dX) CKB(gemm_rm(h, false, true, (int)rows, i, o, 1.f, dY, o, h->P + mb[0], o, 0.f, dX, i));
   return 0;
 }
@@ -349,7 +349,7 @@ static void conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, l
 static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
   LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
   CKB(gemm_rm(h, true, false, KS * Ci, Co, (int)rows, 1.f, h->colbuf, KS * Ci, dout, Co, 1.f, h->G + k, Co));
-  LAUNCH(colsum_k, cdiv(rows, XTDY_SLAB), 64, 0, dout, Co, h->G + b, rows, Co);
+  LAUNCH(colsum_k, dim3(cdiv(rows, XTDY_SLAB), cdiv(Co, 128)), 128, 0, dout, Co, h->G + b, rows, Co);
   if (din) LEW(conv1d_bwd_in_k, rows * Ci, dout, h->P + k, din, rows, h->N, Ci, Co, KS);
   return 0;
 }
@@ -563,7 +563,9 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
         tc_split(h->a, T.ah, T.al, Rn, Chv, T.l0a.CSi, h->stream) || tc_split(h->c, T.ch, T.cl, Rn, Chv, T.l0c.CSi, h->stream) ||
         tc_plan_fwd(T.l0c, T.ch, T.cl, h->Rc, B, B, 0, h->stream) || tc_plan_fwd(T.l0a, T.ah, T.al, h->Sa, B, B, 0, h->stream))
       return fail(h, SNDVAE_E_CUDA, "tensor-core layer-0 products: %s", tc_last_error());
-    h->launches += 7;
+    if (l0d_stage(h->l0d, 0, h->WSa, h->stream) || l0d_stage(h->l0d, 1, h->WSc, h->stream))
+      return fail(h, SNDVAE_E_CUDA, "layer-0 dense staging: %s", tc_last_error());
+    h->launches += 9;
   } else {
     LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
     LEW(toep_vec_fwd_k, Rn * C1, h->a, w0, h->Sa, B, N, Ctot, 0, Chv, C1);
@@ -579,11 +581,15 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     const long long rows = (long long)bc * N, cells = rows * N;
     mark(h, "y_producer");
     YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = tc ? h->tc.l1.CSi : C1; Y.bf16 = tc;
-    { dim3 yg(cdiv(N, YP_TJ), N);
+    {
+      // E1 / Y on the fp32 pipes (register-resident WS rows).  Routing the two K = 2H products through the tensor-core
+      // kernel was measured slower (44 vs 31 ms per 512 graphs): with a single K chunk its epilogue dominates.
+      dim3 yg(cdiv(N, YP_TJ), N);
       if (Chv == 40) LAUNCH(y_producer_k<40>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
                             h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
       else LAUNCH(y_producer_k<20>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
-                  h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1); }
+                  h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
+    }
     mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
     if (tc) { if ((r = tc_plan_fwd(h->tc.l1, h->Yhi, h->Ylo, h->O12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc fwd: %s", tc_last_error()); h->launches++; }
@@ -620,18 +626,33 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     ev_end(h);
     mark(h, "combine");
     // back through relu/BN_e1 to dE1 (both layouts), then the layer-0 contractions
-    LAUNCH(l0_combine_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
-           h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], bc, N, C1);
-    const float* dE1 = h->dY12; const float* dE1t = h->dY12 + cells * C1;
-    LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1, h->dSa + b0 * N * C1, N, C1);
-    LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1t, h->dRc + b0 * N * C1, N, C1);
-    mark(h, "l0_gemms");
-    // da[i,:] = sum_{(j,o)} dE1[i,(j,o)] WSa[(j,o),:];  dc[j,:] = sum_{(i,o)} dE1t[j,(i,o)] WSc[(i,o),:]
-    CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1, N * C1, h->WSa, Chv, 0.f, h->da + b0 * N * Chv, Chv));
-    CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1t, N * C1, h->WSc, Chv, 0.f, h->dc + b0 * N * Chv, Chv));
-    // dWSa[(j,o),:] += sum_rows dE1[row,(j,o)] a[row,:]
-    CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1, N * C1, h->a + b0 * N * Chv, Chv, 1.f, h->dWSa, Chv));
-    CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1t, N * C1, h->c + b0 * N * Chv, Chv, 1.f, h->dWSc, Chv));
+    if (tc) {
+      TcState& T = h->tc; L0Dense& Ld = h->l0d;
+      const int CSe = Ld.CSe; const long long poff = cells * CSe;        // direction-1 planes
+      LAUNCH(l0_combine_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
+             h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], h->Yhi, h->Ylo, h->dSa + b0 * N * C1, bc, N, C1, CSe);
+      LAUNCH(rowsum_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, h->Yhi + poff, h->Ylo + poff, h->dRc + b0 * N * C1, N, C1, CSe);
+      mark(h, "l0_gemms");
+      if (l0d_bwd_act(Ld, 0, h->Yhi, h->Ylo, h->da + b0 * N * Chv, rows, rows, h->stream) ||
+          l0d_bwd_act(Ld, 1, h->Yhi + poff, h->Ylo + poff, h->dc + b0 * N * Chv, rows, rows, h->stream) ||
+          l0d_bwd_w(Ld, h->Yhi, h->Ylo, T.ah + b0 * N * Ld.CSk, T.al + b0 * N * Ld.CSk, h->dWSa, rows, h->stream) ||
+          l0d_bwd_w(Ld, h->Yhi + poff, h->Ylo + poff, T.ch + b0 * N * Ld.CSk, T.cl + b0 * N * Ld.CSk, h->dWSc, rows, h->stream))
+        return fail(h, SNDVAE_E_CUDA, "layer-0 dense backward: %s", tc_last_error());
+      h->launches += 4;
+    } else {
+      LAUNCH(l0_combine_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
+             h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], bc, N, C1);
+      const float* dE1 = h->dY12; const float* dE1t = h->dY12 + cells * C1;
+      LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1, h->dSa + b0 * N * C1, N, C1);
+      LAUNCH(rowsum_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, dE1t, h->dRc + b0 * N * C1, N, C1);
+      mark(h, "l0_gemms");
+      // da[i,:] = sum_{(j,o)} dE1[i,(j,o)] WSa[(j,o),:];  dc[j,:] = sum_{(i,o)} dE1t[j,(i,o)] WSc[(i,o),:]
+      CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1, N * C1, h->WSa, Chv, 0.f, h->da + b0 * N * Chv, Chv));
+      CKB(gemm_rm(h, false, false, (int)rows, Chv, N * C1, 1.f, dE1t, N * C1, h->WSc, Chv, 0.f, h->dc + b0 * N * Chv, Chv));
+      // dWSa[(j,o),:] += sum_rows dE1[row,(j,o)] a[row,:]
+      CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1, N * C1, h->a + b0 * N * Chv, Chv, 1.f, h->dWSa, Chv));
+      CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1t, N * C1, h->c + b0 * N * Chv, Chv, 1.f, h->dWSc, Chv));
+    }
   }
   return 0;
 }
@@ -672,7 +693,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   // ---- node-feature decoder ----
   const int* nc = c.n_d_channel;
   LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, h->q3, nc[1], h->dxpre, F, h->G + p.d_n_lin2[0], Rn, N, nc[1], F, 1);
-  LAUNCH(colsum_k, cdiv(Rn, XTDY_SLAB), 32, 0, h->dxpre, F, h->G + p.d_n_lin2[1], Rn, F);
+  LAUNCH(colsum_k, dim3(cdiv(Rn, XTDY_SLAB), cdiv(F, 128)), 128, 0, h->dxpre, F, h->G + p.d_n_lin2[1], Rn, F);
   LEW(rowlin_bwd_in_k, Rn * nc[1], h->dxpre, F, h->P + p.d_n_lin2[0], h->gA, nc[1], Rn, nc[1], F, 0);      // dq3
   if (h->dis) bn_bwd(h, h->gA, nc[1], h->q2, nc[1], p.decnode_g, p.decnode_b, h->gA, nc[1], Rn, nc[1], ACT_NONE, 0);  // dq2
   bn_bwd(h, h->gA, nc[1], h->q2p, nc[1], p.n_bng[1], p.n_bnb[1], h->gA, nc[1], Rn, nc[1], dact, 0);                   // dq2p
@@ -683,7 +704,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   // ---- spatial decoder ----
   const int* sc = c.s_d_channel;
   LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, h->s3, sc[2], h->dppre, D, h->G + p.d_s_lin2[0], Rn, N, sc[2], D, 1);
-  LAUNCH(colsum_k, cdiv(Rn, XTDY_SLAB), 32, 0, h->dppre, D, h->G + p.d_s_lin2[1], Rn, D);
+  LAUNCH(colsum_k, dim3(cdiv(Rn, XTDY_SLAB), cdiv(D, 128)), 128, 0, h->dppre, D, h->G + p.d_s_lin2[1], Rn, D);
   LEW(rowlin_bwd_in_k, Rn * sc[2], h->dppre, D, h->P + p.d_s_lin2[0], h->gA, sc[2], Rn, sc[2], D, 0);      // ds3
   bn_bwd(h, h->gA, sc[2], h->s3p, sc[2], p.s_bng[2], p.s_bnb[2], h->gA, sc[2], Rn, sc[2], dact, 0);                   // ds3p
   if ((r = conv_bwd(h, h->s2, p.s_k[2], p.s_b[2], h->gA, h->gB, Rn, sc[1], sc[2]))) return r;                                            // ds2
@@ -920,6 +941,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   for (auto& e : h->ev) { cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.flops = 0; }
   if (c.use_tensor_cores) {
     if ((r = tc_init(h->tc, h->N, h->Chv, h->B, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
+    if ((r = l0d_init(h->l0d, h->N, h->Chv, h->C1, h->stream))) return fail(h, SNDVAE_E_CUDA, "l0d_init: %s", tc_last_error());
   }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -928,7 +950,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
 int sndvae_destroy(sndvae_t* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
-  tc_destroy(h->tc);
+  tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (h->pinned_loss) cudaFreeHost(h->pinned_loss);
