@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(YP_THREADS) y_producer_k(const float* __restri
           __nv_bfloat16 hi, lo; split_bf16(y, hi, lo);
           Y.Yhi[e0 * Y.CP + o] = hi; Y.Ylo[e0 * Y.CP + o] = lo;
           Y.Yhi[(plane + e1) * Y.CP + o] = hi; Y.Ylo[(plane + e1) * Y.CP + o] = lo;
-        } else {
+        } else if (Y.Yf) {
           Y.Yf[e0 * C1 + o] = y; Y.Yf[(plane + e1) * C1 + o] = y;
         }
       }

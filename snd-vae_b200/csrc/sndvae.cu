@@ -11,6 +11,7 @@
 #include "edge.cuh"
 #include "adam.cuh"
 #include "e2e_tc.cuh"
+#include "spectral.cuh"
 #include <cublas_v2.h>
 #include <string>
 #include <vector>
@@ -65,6 +66,7 @@ struct sndvae_handle {
   float *E1, *O12, *dY12, *Yf, *dOf;   // chunk buffers (fp32)
   __nv_bfloat16 *Yhi, *Ylo, *dOhi, *dOlo;
   TcState tc; L0Dense l0d;
+  SpecState sp; int spec;              // use_tensor_cores == 2: e2e layer 1 in the frequency domain (spectral.cuh)
   float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg
   int* errflag;
   float* pinned_loss;
@@ -296,7 +298,11 @@ static int alloc_buffers(sndvae_t* h) {
   DA(h->gA, Rn * 64); DA(h->gB, Rn * 64); DA(h->gC, Rn * 64); DA(h->colbuf, Rn * KS * 64);
   const long long cells = (long long)h->Bc * N * N;
   DA(h->E1, cells * C1); DA(h->O12, 2 * cells * C2); DA(h->dY12, 2 * cells * C1);
-  if (c.use_tensor_cores) {
+  if (c.use_tensor_cores == 2) {
+    // spectral path: the bf16 planes only carry dE1 (layer-0 backward operands); dO stays fp32
+    DA(h->Yhi, 2 * cells * TC_CP); DA(h->Ylo, 2 * cells * TC_CP); DA(h->dOf, 2 * cells * C2);
+    h->Yf = nullptr; h->dOhi = h->dOlo = nullptr;
+  } else if (c.use_tensor_cores) {
     DA(h->Yhi, 2 * cells * TC_CP); DA(h->Ylo, 2 * cells * TC_CP); DA(h->dOhi, 2 * cells * TC_OP); DA(h->dOlo, 2 * cells * TC_OP);
     h->Yf = nullptr; h->dOf = nullptr;
   } else {
@@ -558,18 +564,20 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   if (tc) {
     // Rc = c . Toeplitz(w0[:, Ch:, :]),  Sa = a . Toeplitz(w0[:, :Ch, :])  on the tensor cores (split-bf16)
     TcState& T = h->tc;
-    if (tc_plan_stage(T.l1, h->P + p.e_w[1], C1, 0, h->stream) || tc_plan_stage(T.l0a, w0, Ctot, 0, h->stream) ||
+    if ((!h->spec && tc_plan_stage(T.l1, h->P + p.e_w[1], C1, 0, h->stream)) || tc_plan_stage(T.l0a, w0, Ctot, 0, h->stream) ||
         tc_plan_stage(T.l0c, w0, Ctot, Chv, h->stream) ||
         tc_split(h->a, T.ah, T.al, Rn, Chv, T.l0a.CSi, h->stream) || tc_split(h->c, T.ch, T.cl, Rn, Chv, T.l0c.CSi, h->stream) ||
         tc_plan_fwd(T.l0c, T.ch, T.cl, h->Rc, B, B, 0, h->stream) || tc_plan_fwd(T.l0a, T.ah, T.al, h->Sa, B, B, 0, h->stream))
       return fail(h, SNDVAE_E_CUDA, "tensor-core layer-0 products: %s", tc_last_error());
     if (l0d_stage(h->l0d, 0, h->WSa, h->stream) || l0d_stage(h->l0d, 1, h->WSc, h->stream))
       return fail(h, SNDVAE_E_CUDA, "layer-0 dense staging: %s", tc_last_error());
+    if (h->spec && spec_stage_weights(h->sp, h->P + p.e_w[1], h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral weight staging: %s", tc_last_error());
     h->launches += 9;
   } else {
     LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
     LEW(toep_vec_fwd_k, Rn * C1, h->a, w0, h->Sa, B, N, Ctot, 0, Chv, C1);
   }
+  if (backward && h->spec && spec_zero_wgrad(h->sp, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral wgrad reset failed");
   if (backward) {
     CK(cudaMemsetAsync(h->dWSa, 0, sizeof(float) * N * C1 * Chv, h->stream));
     CK(cudaMemsetAsync(h->dWSc, 0, sizeof(float) * N * C1 * Chv, h->stream));
@@ -580,7 +588,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     const int bc = (int)(B - b0 < h->Bc ? B - b0 : h->Bc);
     const long long rows = (long long)bc * N, cells = rows * N;
     mark(h, "y_producer");
-    YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = tc ? h->tc.l1.CSi : C1; Y.bf16 = tc;
+    YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = tc ? h->tc.l1.CSi : C1; Y.bf16 = tc && !h->spec;
     {
       // E1 / Y on the fp32 pipes (register-resident WS rows).  Routing the two K = 2H products through the tensor-core
       // kernel was measured slower (44 vs 31 ms per 512 graphs): with a single K chunk its epilogue dominates.
@@ -592,7 +600,8 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     }
     mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
-    if (tc) { if ((r = tc_plan_fwd(h->tc.l1, h->Yhi, h->Ylo, h->O12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc fwd: %s", tc_last_error()); h->launches++; }
+    if (h->spec) { if (spec_forward(h->sp, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1], rows, h->O12, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral fwd: %s", tc_last_error()); h->launches += 3; }
+    else if (tc) { if ((r = tc_plan_fwd(h->tc.l1, h->Yhi, h->Ylo, h->O12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc fwd: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_fwd_k, 2 * cells * C2, h->Yf, h->P + p.e_w[1], h->O12, 2 * rows, N, C1, C2);
     ev_end(h);
     mark(h, "epilogue");
@@ -603,7 +612,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     ep.At = in ? in->adj_truth + b0 * N * N : nullptr;
     ep.gen_adj = (out && out->generated_adj) ? (long long*)out->generated_adj + b0 * N * N : nullptr;
     ep.logits = (out && out->generated_adj_prob) ? out->generated_adj_prob + b0 * N * N * 2 : nullptr;
-    ep.dOf = h->dOf; ep.dOhi = h->dOhi; ep.dOlo = h->dOlo; ep.OP = tc ? h->tc.l1.CSo : C2; ep.bf16 = tc; ep.backward = backward;
+    ep.dOf = h->dOf; ep.dOhi = h->dOhi; ep.dOlo = h->dOlo; ep.OP = (tc && !h->spec) ? h->tc.l1.CSo : C2; ep.bf16 = tc && !h->spec; ep.backward = backward;
     ep.loss_sum = h->loss + 0;
     ep.g_b1 = h->G + p.e_b[1]; ep.g_gd = h->dis ? h->G + p.decadj_g : nullptr; ep.g_bd = h->dis ? h->G + p.decadj_b : nullptr;
     ep.g_Me = h->G + p.d_e_lin2[0]; ep.g_be = h->G + p.d_e_lin2[1];
@@ -614,16 +623,18 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     if (!backward) continue;
     // backward of e2e layer 1: dgrad + wgrad
     mark(h, "gemm_dgrad");
-    ev_begin(h, f1 * bc);
-    if (tc) { if ((r = tc_plan_dgrad(h->tc.l1, h->dOhi, h->dOlo, h->dY12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc dgrad: %s", tc_last_error()); h->launches++; }
+    ev_begin(h, (h->spec ? 2.0 : 1.0) * f1 * bc);
+    if (h->spec) { if (spec_backward(h->sp, h->dOf, rows, h->dY12, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral bwd: %s", tc_last_error()); h->launches += 4; }
+    else if (tc) { if ((r = tc_plan_dgrad(h->tc.l1, h->dOhi, h->dOlo, h->dY12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc dgrad: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_dgrad_k, 2 * cells * C1, h->dOf, h->P + p.e_w[1], h->dY12, 2 * rows, N, C1, C2);
     ev_end(h);
     mark(h, "gemm_wgrad");
-    ev_begin(h, f1 * bc);
-    if (tc) { if ((r = tc_plan_wgrad(h->tc.l1, h->Yhi, h->Ylo, h->dOhi, h->dOlo, h->G + p.e_w[1], C1, 0, 2 * rows, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc wgrad: %s", tc_last_error()); h->launches++; }
+    if (!h->spec) ev_begin(h, f1 * bc);
+    if (h->spec) {}
+    else if (tc) { if ((r = tc_plan_wgrad(h->tc.l1, h->Yhi, h->Ylo, h->dOhi, h->dOlo, h->G + p.e_w[1], C1, 0, 2 * rows, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc wgrad: %s", tc_last_error()); h->launches++; }
     else { dim3 g(cdiv((long long)N * C1 * C2, 256), cdiv(2 * rows, WGRAD_RG));
            LAUNCH(e2e_l1_simt_wgrad_k, g, 256, 0, h->Yf, h->dOf, h->G + p.e_w[1], 2 * rows, N, C1, C2); }
-    ev_end(h);
+    if (!h->spec) ev_end(h);
     mark(h, "combine");
     // back through relu/BN_e1 to dE1 (both layouts), then the layer-0 contractions
     if (tc) {
@@ -653,6 +664,10 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
       CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1, N * C1, h->a + b0 * N * Chv, Chv, 1.f, h->dWSa, Chv));
       CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1t, N * C1, h->c + b0 * N * Chv, Chv, 1.f, h->dWSc, Chv));
     }
+  }
+  if (backward && h->spec) {     // fold the accumulated frequency-domain weight gradient into dw1 (once per step)
+    if (spec_finalize_wgrad(h->sp, h->G + p.e_w[1], h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral wgrad: %s", tc_last_error());
+    h->launches++;
   }
   return 0;
 }
@@ -903,6 +918,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     return fail(h, SNDVAE_E_ARG, "bad config: num_nodes=%d batch_size=%d", c.num_nodes, c.batch_size);
   if (c.model_type != SNDVAE_MODEL_DISENTANGLED && c.model_type != SNDVAE_MODEL_BASE) return fail(h, SNDVAE_E_ARG, "bad model_type %d", c.model_type);
   h->dis = c.model_type == SNDVAE_MODEL_DISENTANGLED;
+  h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp);
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
   if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);
@@ -917,7 +933,10 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (c.chunk_graphs <= 0) {
     // bound the N^2 staging buffers to ~24 GB: E1 200 + O12 160 + dY12 400 + Y planes 448 + dO planes 192 B per (i,j) cell
     long long per_graph = (long long)h->N * h->N * 1400;
-    long long bc = (24LL << 30) / per_graph; if (bc < 1) bc = 1; if (bc > h->B) bc = h->B; if (bc > 512) bc = 512;
+    long long budget = 24LL << 30;
+    if (c.use_tensor_cores == 2) {   // + spectra: F frequencies x 2N lines x (Y^ planes 416 + O^ 160 + dO^ planes 160 + dY^ 400) B
+      per_graph += (long long)(spec_pick_L(h->N) / 2 + 1) * 2 * h->N * 1136; budget = 56LL << 30; }
+    long long bc = budget / per_graph; if (bc < 1) bc = 1; if (bc > h->B) bc = h->B; if (bc > 512) bc = 512;
     c.chunk_graphs = (int)bc;
   }
   if (c.chunk_graphs > h->B) c.chunk_graphs = (int)h->B;
@@ -942,6 +961,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (c.use_tensor_cores) {
     if ((r = tc_init(h->tc, h->N, h->Chv, h->B, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
     if ((r = l0d_init(h->l0d, h->N, h->Chv, h->C1, h->stream))) return fail(h, SNDVAE_E_CUDA, "l0d_init: %s", tc_last_error());
+    if (h->spec && (r = spec_init(h->sp, h->N, 2LL * h->Bc * h->N, h->stream))) return fail(h, SNDVAE_E_CUDA, "spec_init: %s", tc_last_error());
   }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -951,6 +971,7 @@ int sndvae_destroy(sndvae_t* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
+  if (h->spec) spec_destroy(h->sp);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (h->pinned_loss) cudaFreeHost(h->pinned_loss);

@@ -1,0 +1,746 @@
+// spectral.cuh -- e2e layer 1 (layers.py:431-450 at model.py:202) in the frequency domain.
+//
+// The width-N "cross" convolution of e2e is a full-width 1-D correlation along one axis of the [N, N] grid:
+//     O[line, s, q] = sum_{s', c} Y[line, s', c] w1[s' - s + p, c, q]         (line = (direction, graph, i or j))
+// i.e. a circular convolution of the zero-padded line with g[m] = w1[p - m] (m in [-q, p], q = N-1-p) as soon as
+// the transform length L >= N + q.  N = 256 gives L = 384 = 3 * 2^7, exactly.  In the frequency domain
+//     O^[f, q]  = sum_c Y^[f, c] G^[f, c, q]                 (fwd)
+//     dY^[f, c] = sum_q dO^[f, q] conj(G^[f, c, q])          (dgrad)
+//     dG^[f, c, q] = sum_lines conj(Y^[f, c]) dO^[f, q]      (wgrad; dw1[t] = irfft(dG^)[p - t])
+// so per frequency the channel mix is a small dense GEMM shared by every line of the batch: K = 2*50 real
+// (re | im), N = 2*20.  That is ~30x fewer tensor flops than the block-Toeplitz GEMM (e2e_tc.cuh), and the stage
+// becomes HBM-bound.  Pipeline per micro-batch (all hand-written):
+//     spec_fft_fwd_k   fp32 lines (optionally through BN+relu) -> Stockham FFT in shared memory (two real channels
+//                      per complex transform) -> bf16 hi/lo planes A^[f][line][re c.. | im c..]
+//     spec_gemm_k      tcgen05 kind::f16, 3-pass split-bf16, one [128 lines x K] x [K x N] product per (f, line tile);
+//                      TMA-fed ring, TMEM slot per item, epilogue staged in smem and written with a bulk copy
+//     spec_fft_inv_k   fp32 spectra -> inverse Stockham FFT -> fp32 lines (first N positions, scaled by 1/L)
+//     spec_wgrad_k     per frequency  P[f] += A^[f]^T . dO^[f]  (MN-major operands straight from the same planes),
+//                      two-level (TMEM -> fp32 register) accumulation, atomics into P; folded to dw1 once per step
+#pragma once
+#include "e2e_tc.cuh"
+#include <vector>
+#include <cmath>
+
+#define SP_KA1 104     /* row stride (bf16) of the Y^ planes: [re c0..49 | im c0..49 | 4 pad] = 208 B (TMA: 16 B multiples) */
+#define SP_KA2 40      /* row stride (bf16) of the dO^ planes: [re q0..19 | im q0..19] = 80 B */
+#define SP_NF 48       /* fwd GEMM N: 40 -> 48 (N % 16 == 0 at M = 128) */
+#define SP_ND 112      /* dgrad GEMM N: 100 -> 112 */
+#define SP_FFT_THREADS_MAX 512
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmulnegi(float2 a) { return make_float2(a.y, -a.x); }      // a * (-i)
+
+// ---- small forward DFTs on registers (natural order in and out; e^{-2 pi i / R}) -----------------------------
+template <int R> __device__ __forceinline__ void dft_r(float2* v);
+template <> __device__ __forceinline__ void dft_r<2>(float2* v) {
+  const float2 a = v[0], b = v[1]; v[0] = caddf(a, b); v[1] = csubf(a, b);
+}
+template <> __device__ __forceinline__ void dft_r<4>(float2* v) {
+  const float2 t0 = caddf(v[0], v[2]), t1 = csubf(v[0], v[2]), t2 = caddf(v[1], v[3]), t3 = cmulnegi(csubf(v[1], v[3]));
+  v[0] = caddf(t0, t2); v[1] = caddf(t1, t3); v[2] = csubf(t0, t2); v[3] = csubf(t1, t3);
+}
+template <> __device__ __forceinline__ void dft_r<8>(float2* v) {
+  float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+  dft_r<4>(e); dft_r<4>(o);
+  const float s = 0.70710678118654752f;
+  const float2 o1 = make_float2(s * (o[1].x + o[1].y), s * (o[1].y - o[1].x));        // * (s, -s)
+  const float2 o2 = cmulnegi(o[2]);
+  const float2 o3 = make_float2(s * (o[3].y - o[3].x), -s * (o[3].x + o[3].y));       // * (-s, -s)
+  v[0] = caddf(e[0], o[0]); v[4] = csubf(e[0], o[0]);
+  v[1] = caddf(e[1], o1);   v[5] = csubf(e[1], o1);
+  v[2] = caddf(e[2], o2);   v[6] = csubf(e[2], o2);
+  v[3] = caddf(e[3], o3);   v[7] = csubf(e[3], o3);
+}
+template <> __device__ __forceinline__ void dft_r<3>(float2* v) {
+  const float h = 0.86602540378443865f;
+  const float2 s = caddf(v[1], v[2]), d = csubf(v[1], v[2]);
+  const float2 m = make_float2(v[0].x - 0.5f * s.x, v[0].y - 0.5f * s.y);
+  const float2 n = make_float2(h * d.y, -h * d.x);                                    // (-i sqrt(3)/2) d
+  v[0] = caddf(v[0], s); v[1] = caddf(m, n); v[2] = csubf(m, n);
+}
+template <> __device__ __forceinline__ void dft_r<6>(float2* v) {
+  float2 e[3] = {v[0], v[2], v[4]}, o[3] = {v[1], v[3], v[5]};
+  dft_r<3>(e); dft_r<3>(o);
+  const float h = 0.86602540378443865f;
+  const float2 o1 = cmulf(o[1], make_float2(0.5f, -h)), o2 = cmulf(o[2], make_float2(-0.5f, -h));
+  v[0] = caddf(e[0], o[0]); v[3] = csubf(e[0], o[0]);
+  v[1] = caddf(e[1], o1);   v[4] = csubf(e[1], o1);
+  v[2] = caddf(e[2], o2);   v[5] = csubf(e[2], o2);
+}
+
+// ---- sources / sinks of a Stockham pass ------------------------------------------------------------------------
+struct SmemIO {                       // [pos][g] complex buffer in shared memory
+  float2* p; int g;
+  __device__ __forceinline__ float2 ld(int pos, int cp) const { return p[pos * g + cp]; }
+  __device__ __forceinline__ void st(int pos, int cp, float2 v) const { p[pos * g + cp] = v; }
+};
+struct LineSrc {                      // fp32 line in global memory, two real channels per complex value, zero padded past N
+  const float* base; long long pstride; int N; const float* sg; const float* sb;   // sg/sb: BN scale/shift in smem (or NULL)
+  __device__ __forceinline__ float2 ld(int pos, int cp) const {
+    if (pos >= N) return make_float2(0.f, 0.f);
+    float2 x = *reinterpret_cast<const float2*>(base + (long long)pos * pstride + 2 * cp);
+    if (sg) { x.x = fmaxf(fmaf(x.x, sg[2 * cp], sb[2 * cp]), 0.f); x.y = fmaxf(fmaf(x.y, sg[2 * cp + 1], sb[2 * cp + 1]), 0.f); }
+    return x;
+  }
+};
+struct LineDst {                      // inverse transform tail: (re, im) swapped back, scaled, first N positions only
+  float* base; int C; int N; float scale;
+  __device__ __forceinline__ void st(int pos, int cp, float2 v) const {
+    if (pos < N) *reinterpret_cast<float2*>(base + (long long)pos * C + 2 * cp) = make_float2(v.y * scale, v.x * scale);
+  }
+};
+
+// one Stockham autosort pass of radix R over T = L / R butterflies x g channel pairs:
+//   v[r] = in[j + r T] * tw^(r k L / (Ns R)),  k = j mod Ns;  out[(j - k) R + k + r Ns] = DFT_R(v)[r]
+template <int R, class Src, class Dst>
+__device__ __forceinline__ void fft_pass(const Src& in, const Dst& out, const float2* __restrict__ tw, int L, int Ns, int g) {
+  const int T = L / R, tstep = L / (Ns * R);
+  for (int w = threadIdx.x; w < T * g; w += blockDim.x) {
+    const int j = w / g, cp = w - j * g;
+    const int k = j % Ns;
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = in.ld(j + r * T, cp);
+    if (Ns > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], tw[r * k * tstep]);
+    }
+    dft_r<R>(v);
+    const int j0 = (j - k) * R + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) out.st(j0 + r * Ns, cp, v[r]);
+  }
+}
+template <class Src, class Dst>
+__device__ __forceinline__ void fft_pass_any(int R, const Src& in, const Dst& out, const float2* tw, int L, int Ns, int g) {
+  switch (R) {
+    case 2: fft_pass<2>(in, out, tw, L, Ns, g); break;
+    case 3: fft_pass<3>(in, out, tw, L, Ns, g); break;
+    case 4: fft_pass<4>(in, out, tw, L, Ns, g); break;
+    case 6: fft_pass<6>(in, out, tw, L, Ns, g); break;
+    default: fft_pass<8>(in, out, tw, L, Ns, g); break;
+  }
+}
+
+struct FftPlan { int L, F, npass, rad[8]; };
+
+// ---- forward: lines -> bf16 hi/lo spectra planes ------------------------------------------------------------------
+struct FftFwdArgs {
+  const float* in;
+  long long lines0;       // lines [0, lines0): contiguous, base = line * N * C, position stride C
+  long long lines;        // lines [lines0, lines): line' = line - lines0
+  int dir1_strided;       //   1: line' = (b, j) of a [b, N, N, C] tensor read along its first N axis (base = (b N N + j) C, stride N C)
+                          //   0: contiguous like direction 0 (base = line * N * C)
+  const float* gam; const float* bet;     // optional: x <- relu(x * gam * BN_RS + bet)  (BN_e1 + relu, model.py:201-202)
+  __nv_bfloat16* oh; __nv_bfloat16* ol;   // [F][RA][KA]
+  long long RA; int KA;
+  int N, C, G;            // C real channels (even), G channel pairs per shared-memory group
+  const float2* tw;       // exp(-2 pi i k / L), k < L
+  FftPlan pl;
+};
+__global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_fwd_k(FftFwdArgs A) {
+  extern __shared__ __align__(16) float2 fft_sm[];
+  __shared__ float s_g[64], s_b[64];
+  const int L = A.pl.L, F = A.pl.F, CP = A.C / 2;
+  float2* tw = fft_sm; float2* buf0 = tw + L; float2* buf1 = buf0 + (size_t)L * A.G;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) tw[t] = A.tw[t];
+  if (A.gam) for (int t = threadIdx.x; t < A.C; t += blockDim.x) { s_g[t] = A.gam[t] * BN_RS; s_b[t] = A.bet[t]; }
+  for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
+    const float* base; long long pstride;
+    if (line < A.lines0 || !A.dir1_strided) { base = A.in + line * A.N * A.C; pstride = A.C; }
+    else { const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
+           base = A.in + (b * A.N * A.N + j) * A.C; pstride = (long long)A.N * A.C; }
+    for (int cp0 = 0; cp0 < CP; cp0 += A.G) {
+      const int g = min(A.G, CP - cp0);
+      __syncthreads();
+      LineSrc src; src.base = base + 2 * cp0; src.pstride = pstride; src.N = A.N;
+      src.sg = A.gam ? s_g + 2 * cp0 : nullptr; src.sb = s_b + 2 * cp0;
+      SmemIO cur; cur.p = buf0; cur.g = g; SmemIO oth; oth.p = buf1; oth.g = g;
+      fft_pass_any(A.pl.rad[0], src, cur, tw, L, 1, g);
+      int Ns = A.pl.rad[0];
+      for (int ps = 1; ps < A.pl.npass; ++ps) {
+        __syncthreads();
+        fft_pass_any(A.pl.rad[ps], cur, oth, tw, L, Ns, g);
+        Ns *= A.pl.rad[ps];
+        float2* t = cur.p; cur.p = oth.p; oth.p = t;
+      }
+      __syncthreads();
+      // separate the two real channels packed in each complex transform: X1 = (Z[f] + conj Z[L-f]) / 2,
+      // X2 = (Z[f] - conj Z[L-f]) / (2i); split to bf16 hi / lo and store [re | im]
+      for (int w = threadIdx.x; w < F * g; w += blockDim.x) {
+        const int f = w / g, cp = w - f * g;
+        const float2 z1 = cur.p[f * g + cp], z2 = cur.p[(f == 0 ? 0 : L - f) * g + cp];
+        const float x1r = 0.5f * (z1.x + z2.x), x1i = 0.5f * (z1.y - z2.y);
+        const float x2r = 0.5f * (z1.y + z2.y), x2i = 0.5f * (z2.x - z1.x);
+        const long long o = ((long long)f * A.RA + line) * A.KA + 2 * (cp0 + cp);
+        __nv_bfloat162 h, l;
+        h.x = __float2bfloat16_rn(x1r); h.y = __float2bfloat16_rn(x2r);
+        l.x = __float2bfloat16_rn(x1r - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2r - __bfloat162float(h.y));
+        *reinterpret_cast<__nv_bfloat162*>(A.oh + o) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o) = l;
+        h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
+        l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
+        *reinterpret_cast<__nv_bfloat162*>(A.oh + o + A.C) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o + A.C) = l;
+      }
+    }
+  }
+}
+
+// ---- inverse: fp32 spectra [F][RA][2C] ([re c.. | im c..]) -> fp32 lines [line][N][C] -----------------------------
+struct FftInvArgs {
+  const float* in; long long RA;
+  float* out; long long lines;
+  int N, C, G;
+  const float2* tw;
+  FftPlan pl;
+};
+__global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvArgs A) {
+  extern __shared__ __align__(16) float2 fft_sm[];
+  const int L = A.pl.L, F = A.pl.F, CP = A.C / 2, W = 2 * A.C;
+  float2* tw = fft_sm; float2* buf0 = tw + L; float2* buf1 = buf0 + (size_t)L * A.G;
+  for (int t = threadIdx.x; t < L; t += blockDim.x) tw[t] = A.tw[t];
+  const float scale = 1.f / (float)L;
+  for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
+    for (int cp0 = 0; cp0 < CP; cp0 += A.G) {
+      const int g = min(A.G, CP - cp0);
+      __syncthreads();
+      // Z = X1 + i X2 over the full circle (X[L-f] = conj X[f]); inverse DFT = swap . forward DFT . swap
+      for (int w = threadIdx.x; w < F * g; w += blockDim.x) {
+        const int f = w / g, cp = w - f * g;
+        const float* row = A.in + ((long long)f * A.RA + line) * W + 2 * (cp0 + cp);
+        const float2 a = *reinterpret_cast<const float2*>(row);
+        float2 b = *reinterpret_cast<const float2*>(row + A.C);
+        const bool selfc = (f == 0) || (2 * f == L);
+        if (selfc) b = make_float2(0.f, 0.f);
+        buf0[f * g + cp] = make_float2(b.x + a.y, a.x - b.y);
+        if (!selfc) buf0[(L - f) * g + cp] = make_float2(a.y - b.x, a.x + b.y);
+      }
+      SmemIO cur; cur.p = buf0; cur.g = g; SmemIO oth; oth.p = buf1; oth.g = g;
+      LineDst dst; dst.base = A.out + line * A.N * A.C + 2 * cp0; dst.C = A.C; dst.N = A.N; dst.scale = scale;
+      int Ns = 1;
+      for (int ps = 0; ps < A.pl.npass; ++ps) {
+        __syncthreads();
+        if (ps == A.pl.npass - 1) fft_pass_any(A.pl.rad[ps], cur, dst, tw, L, Ns, g);
+        else fft_pass_any(A.pl.rad[ps], cur, oth, tw, L, Ns, g);
+        Ns *= A.pl.rad[ps];
+        float2* t = cur.p; cur.p = oth.p; oth.p = t;
+      }
+    }
+  }
+}
+
+// ---- per-step weight spectra and GEMM operand staging -----------------------------------------------------------
+// G^[f][c][q] = sum_t w1[t][c][q] exp(-2 pi i f (p - t) / L)   (double accumulation over the exact table)
+//   fwd   B (K-major, [f][n][k], k < 128): n = q: (k=c: Gr, k=C1+c: -Gi);  n = C2+q: (k=c: Gi, k=C1+c: Gr)
+//   dgrad B ([f][n][k], k < 64):           n = c: (k=q: Gr, k=C2+q: Gi);   n = C1+c: (k=q: -Gi, k=C2+q: Gr)
+__global__ void spec_stage_weights_k(const float* __restrict__ w1, const double2* __restrict__ twd, __nv_bfloat16* __restrict__ Bfh,
+                                     __nv_bfloat16* __restrict__ Bfl, __nv_bfloat16* __restrict__ Bdh, __nv_bfloat16* __restrict__ Bdl,
+                                     int N, int L, int F, int C1, int C2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)F * C1 * C2) return;
+  const int q = (int)(idx % C2), c = (int)((idx / C2) % C1), f = (int)(idx / ((long long)C1 * C2));
+  const int p = (N - 1) / 2;
+  double gr = 0.0, gi = 0.0;
+  for (int t = 0; t < N; ++t) {
+    int m = (p - t) % L; if (m < 0) m += L;
+    const double2 e = twd[(int)(((long long)f * m) % L)];
+    const double w = (double)w1[((size_t)t * C1 + c) * C2 + q];
+    gr += w * e.x; gi += w * e.y;
+  }
+  const float Gr = (float)gr, Gi = (float)gi;
+  auto put = [](__nv_bfloat16* hi, __nv_bfloat16* lo, size_t o, float v) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v); hi[o] = h; lo[o] = __float2bfloat16_rn(v - __bfloat162float(h)); };
+  const size_t bf = (size_t)f * SP_NF * 128, bd = (size_t)f * SP_ND * 64;
+  put(Bfh, Bfl, bf + (size_t)q * 128 + c, Gr);            put(Bfh, Bfl, bf + (size_t)q * 128 + C1 + c, -Gi);
+  put(Bfh, Bfl, bf + (size_t)(C2 + q) * 128 + c, Gi);     put(Bfh, Bfl, bf + (size_t)(C2 + q) * 128 + C1 + c, Gr);
+  put(Bdh, Bdl, bd + (size_t)c * 64 + q, Gr);             put(Bdh, Bdl, bd + (size_t)c * 64 + C2 + q, Gi);
+  put(Bdh, Bdl, bd + (size_t)(C1 + c) * 64 + q, -Gi);     put(Bdh, Bdl, bd + (size_t)(C1 + c) * 64 + C2 + q, Gr);
+}
+// dw1[t][c][q] += (1/L) sum_f kappa_f Re(dG^[f][c][q] e^{+2 pi i f (p - t) / L}),  dG^ = conj(Y^) dO^ from the 2x2 blocks of P:
+//   dGr = P[c][q] + P[C1+c][C2+q],  dGi = P[c][C2+q] - P[C1+c][q]      (P[f]: [128][SP_NF])
+__global__ void spec_wgrad_finalize_k(const float* __restrict__ P, const double2* __restrict__ twd, float* __restrict__ dw1,
+                                      int N, int L, int F, int C1, int C2) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * C1 * C2) return;
+  const int q = (int)(idx % C2), c = (int)((idx / C2) % C1), t = (int)(idx / ((long long)C1 * C2));
+  const int p = (N - 1) / 2;
+  int m = (p - t) % L; if (m < 0) m += L;
+  double acc = 0.0;
+  for (int f = 0; f < F; ++f) {
+    const float* Pf = P + (size_t)f * 128 * SP_NF;
+    const double gr = (double)Pf[c * SP_NF + q] + (double)Pf[(C1 + c) * SP_NF + C2 + q];
+    const double gi = (double)Pf[c * SP_NF + C2 + q] - (double)Pf[(C1 + c) * SP_NF + q];
+    const double2 e = twd[(int)(((long long)f * m) % L)];        // e^{-i theta}: cos = e.x, sin(theta) = -e.y
+    const double kap = (f == 0 || 2 * f == L) ? 1.0 : 2.0;
+    acc += kap * (gr * e.x + gi * e.y);                           // Re((gr + i gi)(cos + i sin)) = gr cos - gi sin
+  }
+  dw1[idx] += (float)(acc / (double)L);
+}
+
+// ---- per-frequency channel-mix GEMM on the tensor cores -------------------------------------------------------------
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct SpecGemmArgs {
+  float* out;            // [F][RA][WOUT] fp32
+  long long RA, rows;    // allocated / valid lines per frequency
+  int F, MT;             // frequencies, 128-line tiles per frequency
+  long long items;       // F * MT
+};
+// BN: MMA N (48 fwd / 112 dgrad); KSTEPS: 16-wide K steps actually multiplied (7 / 3); ABOX: 64-wide K boxes per plane (2 / 1);
+// WOUT: valid output columns (40 / 100).  192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
+template <int BN, int KSTEPS, int ABOX, int WOUT, int NSTAGE>
+__global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                                                      const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                                                      SpecGemmArgs P) {
+  constexpr int A_BOX = 128 * 64 * 2;              // 16 KB
+  constexpr int A_PLANE = ABOX * A_BOX;
+  constexpr int A_STAGE = 2 * A_PLANE;
+  constexpr int B_BOX = BN * 64 * 2;
+  constexpr int B_PLANE = ABOX * B_BOX;
+  constexpr int B_BYTES = 2 * B_PLANE;
+  constexpr int SLOT_COLS = BN <= 64 ? 64 : 128;
+  constexpr int NSLOT = 512 / SLOT_COLS;
+  constexpr int STG_BYTES = 128 * WOUT * 4;
+  constexpr int NLD = (WOUT + 7) / 8;              // tcgen05.ld x8 per row
+  static_assert(NLD * 8 <= BN, "epilogue reads past the accumulator");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem + (size_t)NSTAGE * A_STAGE;
+  float* stg = reinterpret_cast<float*>(sB + B_BYTES);
+  __shared__ uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], bfull, bempty, acc_full[NSLOT], acc_empty[NSLOT];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long per = (P.items + gridDim.x - 1) / gridDim.x;
+  const long long item0 = (long long)blockIdx.x * per;
+  long long item1 = item0 + per; if (item1 > P.items) item1 = P.items;
+  const int nit = item1 > item0 ? (int)(item1 - item0) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&bfull, 1); mbar_init(&bempty, 1);
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int cur_f = -1, nb = 0;
+      for (int it = 0; it < nit; ++it) {
+        const long long id = item0 + it; const int f = (int)(id / P.MT), mt = (int)(id - (long long)f * P.MT);
+        if (f != cur_f) {
+          mbar_wait(&bempty, (nb & 1) ^ 1);            // every MMA that read the previous frequency's B has retired
+          mbar_expect_tx(&bfull, B_BYTES);
+#pragma unroll
+          for (int b = 0; b < ABOX; ++b) {
+            tma_load_3d(sB + b * B_BOX, &tmBh, &bfull, 64 * b, 0, f);
+            tma_load_3d(sB + B_PLANE + b * B_BOX, &tmBl, &bfull, 64 * b, 0, f);
+          }
+          cur_f = f; ++nb;
+        }
+        const int s = it % NSTAGE; const uint32_t ph = (it / NSTAGE) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + (size_t)s * A_STAGE;
+        mbar_expect_tx(&full_bar[s], A_STAGE);
+#pragma unroll
+        for (int b = 0; b < ABOX; ++b) {
+          tma_load_3d(st + b * A_BOX, &tmAh, &full_bar[s], 64 * b, mt * 128, f);
+          tma_load_3d(st + A_PLANE + b * A_BOX, &tmAl, &full_bar[s], 64 * b, mt * 128, f);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, BN, 0, 0);
+      int cur_f = -1, nb = 0;
+      const uint32_t sb = smem_u32(sB);
+      for (int it = 0; it < nit; ++it) {
+        const long long id = item0 + it; const int f = (int)(id / P.MT);
+        if (f != cur_f) { mbar_wait(&bfull, nb & 1); ++nb; cur_f = f; }
+        const int slot = it % NSLOT;
+        mbar_wait(&acc_empty[slot], ((it / NSLOT) & 1) ^ 1);
+        const int s = it % NSTAGE; const uint32_t ph = (it / NSTAGE) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * A_STAGE);
+        const uint32_t td = tmem_d + slot * SLOT_COLS;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const int box = ks >> 2, kk = ks & 3;
+          const uint64_t ah = umma_desc(sa + box * A_BOX + kk * 32, 16, 1024, 2ull);
+          const uint64_t al = umma_desc(sa + A_PLANE + box * A_BOX + kk * 32, 16, 1024, 2ull);
+          const uint64_t bh = umma_desc(sb + box * B_BOX + kk * 32, 16, 1024, 2ull);
+          const uint64_t bl = umma_desc(sb + B_PLANE + box * B_BOX + kk * 32, 16, 1024, 2ull);
+          umma_bf16(td, ah, bh, idesc, ks ? 1u : 0u);
+          umma_bf16(td, ah, bl, idesc, 1u);
+          umma_bf16(td, al, bh, idesc, 1u);
+        }
+        umma_commit(&empty_bar[s]);
+        umma_commit(&acc_full[slot]);
+        const bool last_of_f = (it == nit - 1) || ((int)((id + 1) / P.MT) != f);
+        if (last_of_f) umma_commit(&bempty);
+      }
+    }
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;                  // row of the tile
+    for (int it = 0; it < nit; ++it) {
+      const long long id = item0 + it; const int f = (int)(id / P.MT), mt = (int)(id - (long long)f * P.MT);
+      const int slot = it % NSLOT;
+      mbar_wait(&acc_full[slot], (it / NSLOT) & 1);
+      tc_fence_after();
+      if (threadIdx.x == 64) bulk_wait_read();    // the previous bulk store has finished reading the staging tile
+      epi_bar();
+      const uint32_t ta = tmem_d + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
+      float* srow = stg + (size_t)r * WOUT;
+#pragma unroll
+      for (int c0 = 0; c0 < NLD * 8; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(ta + c0, v);
+        if (c0 + 8 <= WOUT) {
+          *reinterpret_cast<float4*>(srow + c0) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          *reinterpret_cast<float4*>(srow + c0 + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (c0 + i < WOUT) srow[c0 + i] = __uint_as_float(v[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      fence_async_smem();
+      epi_bar();
+      if (threadIdx.x == 64) {
+        const long long m0 = (long long)mt * 128;
+        long long nr = P.rows - m0; if (nr > 128) nr = 128;
+        if (nr > 0) bulk_store(P.out + ((long long)f * P.RA + m0) * WOUT, stg, (uint32_t)(nr * WOUT * 4));
+      }
+    }
+    if (threadIdx.x == 64) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 512); }
+}
+
+// ---- wgrad: P[f][m][n] += sum_lines A^[f][line][m] dO^[f][line][n]  (m < 128 over [re c | im c], n < 48 over [re q | im q]) ----
+struct SpecWgradArgs {
+  float* P;              // [F][128][SP_NF]
+  long long rows;        // valid lines
+  int F, KS;             // frequencies, K splits per frequency
+  int MV, NV;            // valid m / n extents (2*C1, 2*C2)
+};
+#define SP_WKC 32
+#define SP_WSTAGES 6
+#define SP_WGROUP 16     /* K chunks per TMEM accumulation group: 16 * 2 k-steps * 3 passes = 96 accumulates */
+__global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
+                                                              const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+                                                              SpecWgradArgs P) {
+  constexpr int BLK = SP_WKC * 128;                 // one [32 k-rows x 64 mn] box = 4 KB
+  constexpr int A_PLANE = 2 * BLK, B_PLANE = BLK;
+  constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // 24 KB
+  constexpr int HC = SP_NF / 2;                     // accumulator columns per epilogue thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[SP_WSTAGES], empty_bar[SP_WSTAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long units = (long long)P.F * P.KS;
+  const long long upc = (units + gridDim.x - 1) / gridDim.x;
+  const long long u0 = (long long)blockIdx.x * upc;
+  long long u1 = u0 + upc; if (u1 > units) u1 = units;
+  const long long kchunks = (P.rows + SP_WKC - 1) / SP_WKC;
+  const long long cper = (kchunks + P.KS - 1) / P.KS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SP_WSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (long long u = u0; u < u1; ++u) {
+        const int f = (int)(u / P.KS), ks = (int)(u - (long long)f * P.KS);
+        const long long c_lo = (long long)ks * cper; long long c_hi = c_lo + cper; if (c_hi > kchunks) c_hi = kchunks;
+        for (long long ch = c_lo; ch < c_hi; ++ch, ++it) {
+          const int s = it % SP_WSTAGES; const uint32_t ph = (it / SP_WSTAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int r0 = (int)(ch * SP_WKC);
+          tma_load_3d(st, &tmAh, &full_bar[s], 0, r0, f);
+          tma_load_3d(st + BLK, &tmAh, &full_bar[s], 64, r0, f);
+          tma_load_3d(st + A_PLANE, &tmAl, &full_bar[s], 0, r0, f);
+          tma_load_3d(st + A_PLANE + BLK, &tmAl, &full_bar[s], 64, r0, f);
+          tma_load_3d(st + 2 * A_PLANE, &tmBh, &full_bar[s], 0, r0, f);
+          tma_load_3d(st + 2 * A_PLANE + B_PLANE, &tmBl, &full_bar[s], 0, r0, f);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, SP_NF, 1, 1);
+      int it = 0, gcount = 0;
+      for (long long u = u0; u < u1; ++u) {
+        const int ks = (int)(u % P.KS);
+        const long long c_lo = (long long)ks * cper; long long c_hi = c_lo + cper; if (c_hi > kchunks) c_hi = kchunks;
+        const int nk = c_hi > c_lo ? (int)(c_hi - c_lo) : 0;
+        for (int i = 0; i < nk; ++i, ++it) {
+          const int gi = i % SP_WGROUP;
+          const int slot = gcount & 1;
+          if (gi == 0) { mbar_wait(&acc_empty[slot], ((gcount >> 1) & 1) ^ 1); tc_fence_after(); }
+          const int s = it % SP_WSTAGES; const uint32_t ph = (it / SP_WSTAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint32_t td = tmem_d + slot * 64;
+#pragma unroll
+          for (int k = 0; k < SP_WKC / 16; ++k) {
+            const uint64_t ah = umma_desc_sw128(sa + k * 2048, BLK, 1024);
+            const uint64_t al = umma_desc_sw128(sa + A_PLANE + k * 2048, BLK, 1024);
+            const uint64_t bh = umma_desc_sw128(sa + 2 * A_PLANE + k * 2048, BLK, 1024);
+            const uint64_t bl = umma_desc_sw128(sa + 2 * A_PLANE + B_PLANE + k * 2048, BLK, 1024);
+            umma_bf16(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
+            umma_bf16(td, ah, bl, idesc, 1u);
+            umma_bf16(td, al, bh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (gi == SP_WGROUP - 1 || i == nk - 1) { umma_commit(&acc_full[slot]); ++gcount; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    float acc[HC];
+#pragma unroll
+    for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+    int gcount = 0;
+    for (long long u = u0; u < u1; ++u) {
+      const int f = (int)(u / P.KS), ks = (int)(u - (long long)f * P.KS);
+      const long long c_lo = (long long)ks * cper; long long c_hi = c_lo + cper; if (c_hi > kchunks) c_hi = kchunks;
+      const int nk = c_hi > c_lo ? (int)(c_hi - c_lo) : 0;
+      const int ng = (nk + SP_WGROUP - 1) / SP_WGROUP;
+      for (int g = 0; g < ng; ++g, ++gcount) {
+        const int slot = gcount & 1;
+        mbar_wait(&acc_full[slot], (gcount >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_d + slot * 64 + ((uint32_t)(q * 32) << 16) + half * HC;
+#pragma unroll
+        for (int c0 = 0; c0 < HC; c0 += 8) {
+          uint32_t v[8];
+          tmem_ld8(ta + c0, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(v[i]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      }
+      // flush when the next unit belongs to another frequency (or this CTA is done)
+      const bool flush = (u == u1 - 1) || ((int)((u + 1) / P.KS) != f);
+      if (flush) {
+        if (m < P.MV) {
+          float* Pf = P.P + ((size_t)f * 128 + m) * SP_NF + half * HC;
+#pragma unroll
+          for (int i = 0; i < HC; ++i) if (half * HC + i < P.NV) atomicAdd(Pf + i, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < HC; ++i) acc[i] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 128); }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------------
+struct SpecState {
+  int ready, N, C1, C2, G1, G2;
+  FftPlan pl;
+  long long RA;                          // allocated lines per frequency (2 * chunk graphs * N)
+  float2* tw; double2* twd;
+  __nv_bfloat16 *Ah, *Al, *Dh, *Dl;      // Y^ planes [F][RA][SP_KA1], dO^ planes [F][RA][SP_KA2]
+  float *Oc, *dYc;                       // O^ [F][RA][2 C2], dY^ [F][RA][2 C1]
+  __nv_bfloat16 *Bfh, *Bfl, *Bdh, *Bdl;  // staged weight spectra
+  float* P;                              // wgrad accumulator [F][128][SP_NF]
+  CUtensorMap mBfh, mBfl, mBdh, mBdl;
+  int fft_threads, grid_sms;
+};
+static size_t spec_fft_smem(int L, int G) { return (size_t)(L + 2 * (size_t)L * G) * sizeof(float2); }
+static constexpr int SPF_STAGES = 2, SPD_STAGES = 4;
+static size_t spec_gemm_smem(int BN, int ABOX, int WOUT, int NSTAGE) {
+  return (size_t)NSTAGE * 2 * ABOX * 128 * 64 * 2 + (size_t)2 * ABOX * BN * 64 * 2 + (size_t)128 * WOUT * 4 + 1024;
+}
+static const size_t SP_WGRAD_SMEM = (size_t)SP_WSTAGES * (2 * 2 * SP_WKC * 128 + 2 * SP_WKC * 128) + 1024;
+
+// transform length: smallest even L in {2^a, 3 * 2^a} with L >= N + q, q = N - 1 - (N-1)/2
+static int spec_pick_L(int N) {
+  const int need = N + (N - 1 - (N - 1) / 2);
+  int best = 0;
+  for (int a = 1; a < 20; ++a) {
+    const int c2 = 1 << a, c3 = 3 << a;
+    if (c2 >= need && (!best || c2 < best)) best = c2;
+    if (c3 >= need && (!best || c3 < best)) best = c3;
+    if (best && c2 > best) break;
+  }
+  return best < 4 ? 4 : best;
+}
+static void spec_make_plan(FftPlan& pl, int L) {
+  pl.L = L; pl.F = L / 2 + 1; pl.npass = 0;
+  int n = L;
+  if (n % 3 == 0) { n /= 3; if (n % 2 == 0) { n /= 2; pl.rad[pl.npass++] = 6; } else pl.rad[pl.npass++] = 3; }
+  while (n % 8 == 0) { pl.rad[pl.npass++] = 8; n /= 8; }
+  if (n > 1) pl.rad[pl.npass++] = n;    // 2 or 4
+}
+static int spec_pick_G(int L, int CP) {
+  int g = CP;
+  while (g > 1 && spec_fft_smem(L, g) > 200 * 1024) --g;
+  return g;
+}
+static int spec_enc3(CUtensorMap* tm, const void* base, long long d0, long long d1, long long d2, long long s1_b, long long s2_b, int b0, int b1) {
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t str[2] = {(cuuint64_t)s1_b, (cuuint64_t)s2_b};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+  return tc_encode(tm, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static void spec_destroy(SpecState& s) {
+  void* ps[] = {s.tw, s.twd, s.Ah, s.Al, s.Dh, s.Dl, s.Oc, s.dYc, s.Bfh, s.Bfl, s.Bdh, s.Bdl, s.P};
+  for (void* p : ps) if (p) cudaFree(p);
+  memset(&s, 0, sizeof s);
+}
+static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st) {
+  memset(&s, 0, sizeof s);
+  if (tc_global_init()) return -1;
+  s.N = N; s.C1 = TC_C1; s.C2 = TC_C2; s.RA = rows_alloc;
+  const int L = spec_pick_L(N);
+  spec_make_plan(s.pl, L);
+  const int F = s.pl.F;
+  s.G1 = spec_pick_G(L, s.C1 / 2); s.G2 = spec_pick_G(L, s.C2 / 2);
+  std::vector<float2> tw(L); std::vector<double2> twd(L);
+  for (int k = 0; k < L; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)L;
+    twd[k].x = cos(a); twd[k].y = sin(a); tw[k].x = (float)twd[k].x; tw[k].y = (float)twd[k].y;
+  }
+  const size_t nA = (size_t)F * rows_alloc * SP_KA1 + 256, nD = (size_t)F * rows_alloc * SP_KA2 + 256;
+  const size_t nO = (size_t)F * rows_alloc * 2 * s.C2, nY = (size_t)F * rows_alloc * 2 * s.C1;
+  const size_t nBf = (size_t)F * SP_NF * 128, nBd = (size_t)F * SP_ND * 64, nP = (size_t)F * 128 * SP_NF;
+  if (cudaMalloc(&s.tw, L * sizeof(float2)) || cudaMalloc(&s.twd, L * sizeof(double2)) || cudaMalloc(&s.Ah, nA * 2) || cudaMalloc(&s.Al, nA * 2) ||
+      cudaMalloc(&s.Dh, nD * 2) || cudaMalloc(&s.Dl, nD * 2) || cudaMalloc(&s.Oc, nO * 4) || cudaMalloc(&s.dYc, nY * 4) ||
+      cudaMalloc(&s.Bfh, nBf * 2) || cudaMalloc(&s.Bfl, nBf * 2) || cudaMalloc(&s.Bdh, nBd * 2) || cudaMalloc(&s.Bdl, nBd * 2) ||
+      cudaMalloc(&s.P, nP * 4)) {
+    snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of spectral buffers failed (%s)", cudaGetErrorString(cudaGetLastError())); return -1;
+  }
+  cudaMemcpyAsync(s.tw, tw.data(), L * sizeof(float2), cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(s.twd, twd.data(), L * sizeof(double2), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);               // the host vectors go out of scope
+  cudaMemsetAsync(s.Ah, 0, nA * 2, st); cudaMemsetAsync(s.Al, 0, nA * 2, st); cudaMemsetAsync(s.Dh, 0, nD * 2, st); cudaMemsetAsync(s.Dl, 0, nD * 2, st);
+  cudaMemsetAsync(s.Bfh, 0, nBf * 2, st); cudaMemsetAsync(s.Bfl, 0, nBf * 2, st); cudaMemsetAsync(s.Bdh, 0, nBd * 2, st); cudaMemsetAsync(s.Bdl, 0, nBd * 2, st);
+  cudaMemsetAsync(s.P, 0, nP * 4, st);
+  if (spec_enc3(&s.mBfh, s.Bfh, 128, SP_NF, F, 128 * 2, (long long)SP_NF * 128 * 2, 64, SP_NF) ||
+      spec_enc3(&s.mBfl, s.Bfl, 128, SP_NF, F, 128 * 2, (long long)SP_NF * 128 * 2, 64, SP_NF) ||
+      spec_enc3(&s.mBdh, s.Bdh, 64, SP_ND, F, 64 * 2, (long long)SP_ND * 64 * 2, 64, SP_ND) ||
+      spec_enc3(&s.mBdl, s.Bdl, 64, SP_ND, F, 64 * 2, (long long)SP_ND * 64 * 2, 64, SP_ND)) return -1;
+  cudaFuncSetAttribute(spec_fft_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(spec_fft_inv_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES));
+  cudaFuncSetAttribute(spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES));
+  cudaFuncSetAttribute(spec_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_WGRAD_SMEM);
+  s.fft_threads = getenv("SNDVAE_FFT_THREADS") ? atoi(getenv("SNDVAE_FFT_THREADS")) : (L == 384 ? 400 : 256);
+  if (s.fft_threads > SP_FFT_THREADS_MAX) s.fft_threads = SP_FFT_THREADS_MAX;
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  s.grid_sms = sms;
+  s.ready = 1;
+  return 0;
+}
+// per step: weight spectra -> GEMM operand planes
+static int spec_stage_weights(SpecState& s, const float* w1, cudaStream_t st) {
+  const long long n = (long long)s.pl.F * s.C1 * s.C2;
+  spec_stage_weights_k<<<cdiv(n, 128), 128, 0, st>>>(w1, s.twd, s.Bfh, s.Bfl, s.Bdh, s.Bdl, s.N, s.pl.L, s.pl.F, s.C1, s.C2);
+  return tc_check_launch("spec_stage_weights_k");
+}
+static int spec_fft_fwd(SpecState& s, const float* in, long long lines0, long long lines, int dir1_strided, const float* gam, const float* bet,
+                        __nv_bfloat16* oh, __nv_bfloat16* ol, int KA, int C, int G, cudaStream_t st) {
+  FftFwdArgs a; a.in = in; a.lines0 = lines0; a.lines = lines; a.dir1_strided = dir1_strided; a.gam = gam; a.bet = bet; a.oh = oh; a.ol = ol;
+  a.RA = s.RA; a.KA = KA; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  const unsigned grid = (unsigned)(lines < s.grid_sms ? lines : s.grid_sms);
+  spec_fft_fwd_k<<<grid, s.fft_threads, spec_fft_smem(s.pl.L, G), st>>>(a);
+  return tc_check_launch("spec_fft_fwd_k");
+}
+static int spec_fft_inv(SpecState& s, const float* in, float* out, long long lines, int C, int G, cudaStream_t st) {
+  FftInvArgs a; a.in = in; a.RA = s.RA; a.out = out; a.lines = lines; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  const unsigned grid = (unsigned)(lines < s.grid_sms ? lines : s.grid_sms);
+  spec_fft_inv_k<<<grid, s.fft_threads, spec_fft_smem(s.pl.L, G), st>>>(a);
+  return tc_check_launch("spec_fft_inv_k");
+}
+// forward: O12[2 rows][N C2] = e2e-layer-1 row / column products of Y = relu(BN_e1(E1));  rows = bc * N
+static int spec_forward(SpecState& s, const float* E1, const float* gam1, const float* bet1, long long rows, float* O12, cudaStream_t st) {
+  const long long lines = 2 * rows; const int F = s.pl.F;
+  if (spec_fft_fwd(s, E1, rows, lines, 1, gam1, bet1, s.Ah, s.Al, SP_KA1, s.C1, s.G1, st)) return -1;
+  CUtensorMap ah, al;
+  if (spec_enc3(&ah, s.Ah, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, 128) ||
+      spec_enc3(&al, s.Al, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, 128)) return -1;
+  SpecGemmArgs g; g.out = s.Oc; g.RA = s.RA; g.rows = lines; g.F = F; g.MT = (int)((lines + 127) / 128); g.items = (long long)F * g.MT;
+  const unsigned grid = (unsigned)(g.items < s.grid_sms ? g.items : s.grid_sms);
+  spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES><<<grid, 192, spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES), st>>>(ah, al, s.mBfh, s.mBfl, g);
+  if (tc_check_launch("spec_gemm_k(fwd)")) return -1;
+  return spec_fft_inv(s, s.Oc, O12, lines, s.C2, s.G2, st);
+}
+// backward: dY12[2 rows][N C1] from dO [2 rows][N C2] (fp32, both layouts), and P += Y^^T dO^
+static int spec_backward(SpecState& s, const float* dO, long long rows, float* dY12, cudaStream_t st) {
+  const long long lines = 2 * rows; const int F = s.pl.F;
+  if (spec_fft_fwd(s, dO, lines, lines, 0, nullptr, nullptr, s.Dh, s.Dl, SP_KA2, s.C2, s.G2, st)) return -1;
+  CUtensorMap dh, dl;
+  if (spec_enc3(&dh, s.Dh, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128) ||
+      spec_enc3(&dl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128)) return -1;
+  SpecGemmArgs g; g.out = s.dYc; g.RA = s.RA; g.rows = lines; g.F = F; g.MT = (int)((lines + 127) / 128); g.items = (long long)F * g.MT;
+  const unsigned grid = (unsigned)(g.items < s.grid_sms ? g.items : s.grid_sms);
+  spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES><<<grid, 192, spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES), st>>>(dh, dl, s.mBdh, s.mBdl, g);
+  if (tc_check_launch("spec_gemm_k(dgrad)")) return -1;
+  if (spec_fft_inv(s, s.dYc, dY12, lines, s.C1, s.G1, st)) return -1;
+  // wgrad: MN-major views of the same planes, 32 lines per K chunk
+  CUtensorMap ah, al, bh, bl;
+  if (spec_enc3(&ah, s.Ah, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, SP_WKC) ||
+      spec_enc3(&al, s.Al, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, SP_WKC) ||
+      spec_enc3(&bh, s.Dh, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, SP_WKC) ||
+      spec_enc3(&bl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, SP_WKC)) return -1;
+  SpecWgradArgs w; w.P = s.P; w.rows = lines; w.F = F; w.MV = 2 * s.C1; w.NV = 2 * s.C2;
+  const long long kchunks = (lines + SP_WKC - 1) / SP_WKC;
+  int ks = (int)((8LL * s.grid_sms + F - 1) / F); if (ks > kchunks) ks = (int)kchunks; if (ks < 1) ks = 1;
+  w.KS = ks;
+  const long long units = (long long)F * ks;
+  const unsigned wgrid = (unsigned)(units < s.grid_sms ? units : s.grid_sms);
+  spec_wgrad_k<<<wgrid, TC_THREADS, SP_WGRAD_SMEM, st>>>(ah, al, bh, bl, w);
+  return tc_check_launch("spec_wgrad_k");
+}
+static int spec_zero_wgrad(SpecState& s, cudaStream_t st) {
+  return cudaMemsetAsync(s.P, 0, (size_t)s.pl.F * 128 * SP_NF * 4, st) == cudaSuccess ? 0 : -1;
+}
+static int spec_finalize_wgrad(SpecState& s, float* dw1, cudaStream_t st) {
+  const long long n = (long long)s.N * s.C1 * s.C2;
+  spec_wgrad_finalize_k<<<cdiv(n, 128), 128, 0, st>>>(s.P, s.twd, dw1, s.N, s.pl.L, s.pl.F, s.C1, s.C2);
+  return tc_check_launch("spec_wgrad_finalize_k");
+}

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sndvae_b200 as sv
 from oracle import sndvae_oracle as O
 ap = argparse.ArgumentParser(); ap.add_argument("--n", type=int, default=256); ap.add_argument("--b", type=int, default=4)
-ap.add_argument("--s", type=int, default=2); ap.add_argument("--chunk", type=int, default=3)
+ap.add_argument("--s", type=int, default=2); ap.add_argument("--chunk", type=int, default=3); ap.add_argument("--tc", type=int, default=1)
 a = ap.parse_args()
 cfg = O.Config(num_nodes=a.n, sampling_num=a.s)
 P = O.init_params(cfg, 7, torch.float32)
@@ -13,7 +13,7 @@ g = torch.Generator().manual_seed(1)
 for k in P: P[k] = P[k] + 0.05 * torch.randn(P[k].shape, generator=g)
 inp = O.synthetic_inputs(cfg, a.b, 5, torch.float32); noise = O.synthetic_noise(cfg, a.b, 9, torch.float32)
 out = {}
-for name, tc, chunk in (("simt", 0, a.chunk), ("tc", 1, a.chunk)):
+for name, tc, chunk in (("simt", 0, a.chunk), ("tc", a.tc, a.chunk)):
     eng = sv.Engine(sv.make_config(a.n, a.b, "disentangled", sampling_num=a.s, use_tensor_cores=tc, chunk_graphs=chunk))
     eng.set_params(P); r = eng.grads(inp, noise, fetch=("generated_adj_prob",))
     out[name] = (r["overall_loss"], eng.get_grads(), r["generated_adj_prob"].cpu())
