@@ -231,6 +231,174 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvAr
   }
 }
 
+// ---- specialised transforms: compile-time plan (R0 x R1 x R2), all G channel pairs of a line in one group, next line prefetched
+//      with cp.async into a staging buffer while the current one is transformed --------------------------------------------
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int R, int NS, int L, int G, int NT, class Src, class Dst>
+__device__ __forceinline__ void fft_pass_ct(const Src& in, const Dst& out, const float2* __restrict__ tw) {
+  constexpr int T = L / R, ITEMS = T * G, TSTEP = L / (NS * R);
+#pragma unroll
+  for (int w0 = 0; w0 < ITEMS; w0 += NT) {
+    const int w = w0 + threadIdx.x;
+    if (ITEMS % NT == 0 || w < ITEMS) {
+      const int j = w / G, cp = w - j * G;
+      const int k = j % NS;
+      float2 v[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = in.ld(j + r * T, cp);
+      if (NS > 1) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], tw[r * k * TSTEP]);
+      }
+      dft_r<R>(v);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) out.st(j0 + r * NS, cp, v[r]);
+    }
+  }
+}
+template <int G> struct SmemCT {      // [pos][G] complex buffer, compile-time pitch
+  float2* p;
+  __device__ __forceinline__ float2 ld(int pos, int cp) const { return p[pos * G + cp]; }
+  __device__ __forceinline__ void st(int pos, int cp, float2 v) const { p[pos * G + cp] = v; }
+};
+template <int G> struct StageSrc {    // staged fp32 line [pos][2G] in shared memory, BN + relu on the fly, zero padded past N
+  const float* s; int N; const float* sg; const float* sb;
+  __device__ __forceinline__ float2 ld(int pos, int cp) const {
+    if (pos >= N) return make_float2(0.f, 0.f);
+    float2 x = *reinterpret_cast<const float2*>(s + pos * (2 * G) + 2 * cp);
+    if (sg) { x.x = fmaxf(fmaf(x.x, sg[2 * cp], sb[2 * cp]), 0.f); x.y = fmaxf(fmaf(x.y, sg[2 * cp + 1], sb[2 * cp + 1]), 0.f); }
+    return x;
+  }
+};
+template <int R0, int R1, int R2, int G>
+struct FastCfg {
+  static constexpr int L = R0 * R1 * (R2 ? R2 : 1), F = L / 2 + 1;
+  static constexpr size_t BUF = (size_t)F * G * 16 > (size_t)L * G * 8 ? (size_t)F * G * 16 : (size_t)L * G * 8;   // bytes of one ping-pong buffer
+  static size_t smem_fwd(int N) { return (size_t)L * 8 + 2 * BUF + (size_t)N * 2 * G * 4; }
+  static size_t smem_inv(bool alias) { return (size_t)L * 8 + (alias ? 2 : 3) * BUF; }
+};
+
+template <int R0, int R1, int R2, int G, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
+  using Cfg = FastCfg<R0, R1, R2, G>;
+  constexpr int L = Cfg::L, F = Cfg::F, C = 2 * G;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  __shared__ float s_g[2 * G], s_b[2 * G];
+  float2* tw = reinterpret_cast<float2*>(fsm);
+  float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
+  float2* bufB = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
+  float* stage = reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
+  for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  if (A.gam) for (int t = threadIdx.x; t < C; t += NT) { s_g[t] = A.gam[t] * BN_RS; s_b[t] = A.bet[t]; }
+  const int N = A.N;
+  const bool vec16 = ((long long)N * C) % 4 == 0;
+  auto prefetch = [&](long long line) {
+    if (line >= A.lines) return;
+    if (line < A.lines0 || !A.dir1_strided) {
+      const float* base = A.in + line * N * C;
+      if (vec16) { for (int t = threadIdx.x; t < N * C / 4; t += NT) cp_async16(stage + 4 * t, base + 4 * t); }
+      else { for (int t = threadIdx.x; t < N * G; t += NT) cp_async8(stage + 2 * t, base + 2 * t); }
+    } else {
+      const long long l1 = line - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
+      const float* base = A.in + (b * N * N + j) * C; const long long ps = (long long)N * C;
+      for (int t = threadIdx.x; t < N * G; t += NT) { const int pos = t / G, cp = t - pos * G; cp_async8(stage + 2 * t, base + pos * ps + 2 * cp); }
+    }
+  };
+  prefetch(blockIdx.x);
+  cp_async_commit();
+  for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();                       // staged line visible; previous line's readers of bufA / bufB are done
+    StageSrc<G> src; src.s = stage; src.N = N; src.sg = A.gam ? s_g : nullptr; src.sb = s_b;
+    SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
+    fft_pass_ct<R0, 1, L, G, NT>(src, a, tw);
+    __syncthreads();
+    prefetch(line + gridDim.x);            // the staging buffer is free: overlap the next line's loads with passes 2, 3 and the store
+    cp_async_commit();
+    fft_pass_ct<R1, R0, L, G, NT>(a, b, tw);
+    __syncthreads();
+    const float2* res = bufB;
+    if (R2) { fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(b, a, tw); __syncthreads(); res = bufA; }
+    for (int w = threadIdx.x; w < F * G; w += NT) {
+      const int f = w / G, cp = w - f * G;
+      const float2 z1 = res[f * G + cp], z2 = res[(f == 0 ? 0 : L - f) * G + cp];
+      const float x1r = 0.5f * (z1.x + z2.x), x1i = 0.5f * (z1.y - z2.y);
+      const float x2r = 0.5f * (z1.y + z2.y), x2i = 0.5f * (z2.x - z1.x);
+      const long long o = ((long long)f * A.RA + line) * A.KA + 2 * cp;
+      __nv_bfloat162 h, l;
+      h.x = __float2bfloat16_rn(x1r); h.y = __float2bfloat16_rn(x2r);
+      l.x = __float2bfloat16_rn(x1r - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2r - __bfloat162float(h.y));
+      *reinterpret_cast<__nv_bfloat162*>(A.oh + o) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o) = l;
+      h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
+      l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
+      *reinterpret_cast<__nv_bfloat162*>(A.oh + o + C) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o + C) = l;
+    }
+  }
+  cp_async_wait_all();
+}
+
+// inverse: the raw spectrum rows of a line ([f][2C] fp32) are staged with cp.async; ALIAS = the staging buffer is bufB
+// (3-pass plans at G = 25 do not fit a third buffer; the prefetch then overlaps only the last pass)
+template <int R0, int R1, int R2, int G, int NT, int MINB, bool ALIAS>
+__global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
+  using Cfg = FastCfg<R0, R1, R2, G>;
+  constexpr int L = Cfg::L, F = Cfg::F, C = 2 * G, W = 4 * G;
+  static_assert(!ALIAS || R2 != 0, "aliasing the staging buffer needs a 3-pass plan");
+  extern __shared__ __align__(16) uint8_t fsm[];
+  float2* tw = reinterpret_cast<float2*>(fsm);
+  float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
+  float2* bufB = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
+  float* stage = ALIAS ? reinterpret_cast<float*>(bufB) : reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
+  for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  const float scale = 1.f / (float)L;
+  auto prefetch = [&](long long line) {
+    if (line >= A.lines) return;
+    for (int t = threadIdx.x; t < F * G; t += NT) {          // 16 bytes = two channel pairs' worth of one half row
+      const int f = t / G, x = t - f * G;
+      cp_async16(stage + (size_t)f * W + 4 * x, A.in + ((long long)f * A.RA + line) * W + 4 * x);
+    }
+  };
+  prefetch(blockIdx.x);
+  cp_async_commit();
+  for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();
+    for (int w = threadIdx.x; w < F * G; w += NT) {
+      const int f = w / G, cp = w - f * G;
+      const float2 a = *reinterpret_cast<const float2*>(stage + (size_t)f * W + 2 * cp);
+      float2 b = *reinterpret_cast<const float2*>(stage + (size_t)f * W + C + 2 * cp);
+      const bool selfc = (f == 0) || (2 * f == L);
+      if (selfc) b = make_float2(0.f, 0.f);
+      bufA[f * G + cp] = make_float2(b.x + a.y, a.x - b.y);
+      if (!selfc) bufA[(L - f) * G + cp] = make_float2(a.y - b.x, a.x + b.y);
+    }
+    __syncthreads();
+    SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
+    LineDst dst; dst.base = A.out + line * A.N * C; dst.C = C; dst.N = A.N; dst.scale = scale;
+    if (!ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
+    fft_pass_ct<R0, 1, L, G, NT>(a, b, tw);
+    __syncthreads();
+    if (R2) {
+      fft_pass_ct<R1, R0, L, G, NT>(b, a, tw);
+      __syncthreads();
+      if (ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
+      fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(a, dst, tw);
+    } else {
+      fft_pass_ct<R1, R0, L, G, NT>(b, dst, tw);
+    }
+  }
+  cp_async_wait_all();
+}
+
 // ---- per-step weight spectra and GEMM operand staging -----------------------------------------------------------
 // G^[f][c][q] = sum_t w1[t][c][q] exp(-2 pi i f (p - t) / L)   (double accumulation over the exact table)
 //   fwd   B (K-major, [f][n][k], k < 128): n = q: (k=c: Gr, k=C1+c: -Gi);  n = C2+q: (k=c: Gi, k=C1+c: Gr)
@@ -588,7 +756,7 @@ struct SpecState {
   __nv_bfloat16 *Bfh, *Bfl, *Bdh, *Bdl;  // staged weight spectra
   float* P;                              // wgrad accumulator [F][128][SP_NF]
   CUtensorMap mBfh, mBfl, mBdh, mBdl;
-  int fft_threads, grid_sms;
+  int fft_threads, fft_threads_generic, generic_only, grid_sms;
 };
 static size_t spec_fft_smem(int L, int G) { return (size_t)(L + 2 * (size_t)L * G) * sizeof(float2); }
 static constexpr int SPF_STAGES = 2, SPD_STAGES = 4;
@@ -669,8 +837,9 @@ static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st)
   cudaFuncSetAttribute(spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES));
   cudaFuncSetAttribute(spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES));
   cudaFuncSetAttribute(spec_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_WGRAD_SMEM);
-  s.fft_threads = getenv("SNDVAE_FFT_THREADS") ? atoi(getenv("SNDVAE_FFT_THREADS")) : (L == 384 ? 400 : 256);
-  if (s.fft_threads > SP_FFT_THREADS_MAX) s.fft_threads = SP_FFT_THREADS_MAX;
+  s.fft_threads = getenv("SNDVAE_FFT_THREADS") ? atoi(getenv("SNDVAE_FFT_THREADS")) : 400;
+  s.fft_threads_generic = L == 384 ? 400 : 256;
+  s.generic_only = getenv("SNDVAE_FFT_GENERIC") ? 1 : 0;     // force the runtime-plan kernels (any N)
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   s.grid_sms = sms;
   s.ready = 1;
@@ -682,18 +851,60 @@ static int spec_stage_weights(SpecState& s, const float* w1, cudaStream_t st) {
   spec_stage_weights_k<<<cdiv(n, 128), 128, 0, st>>>(w1, s.twd, s.Bfh, s.Bfl, s.Bdh, s.Bdl, s.N, s.pl.L, s.pl.F, s.C1, s.C2);
   return tc_check_launch("spec_stage_weights_k");
 }
+// fast-path launchers: one instantiation per (plan, channel pairs); 0 = launched, 1 = no matching instantiation
+template <int R0, int R1, int R2, int G, int NT, int MINB>
+static int spec_launch_fwd_fast(SpecState& s, const FftFwdArgs& a, cudaStream_t st) {
+  using Cfg = FastCfg<R0, R1, R2, G>;
+  const size_t smem = Cfg::smem_fwd(a.N);
+  if (smem > 225 * 1024) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(spec_fft_fwd_fast_k<R0, R1, R2, G, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); attr = true; }
+  const long long want = (long long)s.grid_sms * MINB;
+  spec_fft_fwd_fast_k<R0, R1, R2, G, NT, MINB><<<(unsigned)(a.lines < want ? a.lines : want), NT, smem, st>>>(a);
+  return 0;
+}
+template <int R0, int R1, int R2, int G, int NT, int MINB, bool ALIAS>
+static int spec_launch_inv_fast(SpecState& s, const FftInvArgs& a, cudaStream_t st) {
+  using Cfg = FastCfg<R0, R1, R2, G>;
+  const size_t smem = Cfg::smem_inv(ALIAS);
+  if (smem > 225 * 1024) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(spec_fft_inv_fast_k<R0, R1, R2, G, NT, MINB, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); attr = true; }
+  const long long want = (long long)s.grid_sms * MINB;
+  spec_fft_inv_fast_k<R0, R1, R2, G, NT, MINB, ALIAS><<<(unsigned)(a.lines < want ? a.lines : want), NT, smem, st>>>(a);
+  return 0;
+}
+static bool spec_plan_is(const FftPlan& pl, int r0, int r1, int r2) {
+  return pl.npass == (r2 ? 3 : 2) && pl.rad[0] == r0 && pl.rad[1] == r1 && (!r2 || pl.rad[2] == r2);
+}
 static int spec_fft_fwd(SpecState& s, const float* in, long long lines0, long long lines, int dir1_strided, const float* gam, const float* bet,
                         __nv_bfloat16* oh, __nv_bfloat16* ol, int KA, int C, int G, cudaStream_t st) {
   FftFwdArgs a; a.in = in; a.lines0 = lines0; a.lines = lines; a.dir1_strided = dir1_strided; a.gam = gam; a.bet = bet; a.oh = oh; a.ol = ol;
   a.RA = s.RA; a.KA = KA; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  int r = 1;
+  if (!s.generic_only) {
+    if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_fwd_fast<6, 8, 8, 25, 800, 1>(s, a, st) : spec_launch_fwd_fast<6, 8, 8, 25, 400, 1>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 8) && C == 20) r = spec_launch_fwd_fast<6, 8, 8, 10, 320, 2>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 0) && C == 50) r = spec_launch_fwd_fast<6, 8, 0, 25, 200, 2>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 0) && C == 20) r = spec_launch_fwd_fast<6, 8, 0, 10, 160, 2>(s, a, st);
+  }
+  if (r == 0) return tc_check_launch("spec_fft_fwd_fast_k");
   const unsigned grid = (unsigned)(lines < s.grid_sms ? lines : s.grid_sms);
-  spec_fft_fwd_k<<<grid, s.fft_threads, spec_fft_smem(s.pl.L, G), st>>>(a);
+  spec_fft_fwd_k<<<grid, s.fft_threads_generic, spec_fft_smem(s.pl.L, G), st>>>(a);
   return tc_check_launch("spec_fft_fwd_k");
 }
 static int spec_fft_inv(SpecState& s, const float* in, float* out, long long lines, int C, int G, cudaStream_t st) {
   FftInvArgs a; a.in = in; a.RA = s.RA; a.out = out; a.lines = lines; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  int r = 1;
+  if (!s.generic_only) {
+    if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_inv_fast<6, 8, 8, 25, 800, 1, true>(s, a, st) : spec_launch_inv_fast<6, 8, 8, 25, 400, 1, true>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 8) && C == 20) r = spec_launch_inv_fast<6, 8, 8, 10, 320, 2, false>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 0) && C == 50) r = spec_launch_inv_fast<6, 8, 0, 25, 200, 2, false>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 0) && C == 20) r = spec_launch_inv_fast<6, 8, 0, 10, 160, 2, false>(s, a, st);
+  }
+  if (r == 0) return tc_check_launch("spec_fft_inv_fast_k");
   const unsigned grid = (unsigned)(lines < s.grid_sms ? lines : s.grid_sms);
-  spec_fft_inv_k<<<grid, s.fft_threads, spec_fft_smem(s.pl.L, G), st>>>(a);
+  spec_fft_inv_k<<<grid, s.fft_threads_generic, spec_fft_smem(s.pl.L, G), st>>>(a);
   return tc_check_launch("spec_fft_inv_k");
 }
 // forward: O12[2 rows][N C2] = e2e-layer-1 row / column products of Y = relu(BN_e1(E1));  rows = bc * N
