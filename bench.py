@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--sampling", type=int, default=10)
     ap.add_argument("--model", default="disentangled", choices=["disentangled", "base"])
     ap.add_argument("--pool", type=int, default=256, help="distinct synthetic graphs generated on the host, tiled to --batch")
-    ap.add_argument("--tc", type=int, default=1)
+    ap.add_argument("--tc", type=int, default=2, help="e2e layer 1: 2 = spectral (FFT + per-frequency tcgen05 GEMMs), 1 = block-Toeplitz tcgen05 GEMMs, 0 = fp32 SIMT")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-sample", type=int, default=2, help="graphs in the CPU-baseline sample")
@@ -66,6 +66,21 @@ def f1_flops(N, C1=50, C2=20):
     q = N - 1 - p
     V = N * N - p * (p + 1) // 2 - q * (q + 1) // 2
     return 2.0 * 2.0 * N * V * C1 * C2
+
+
+def spectral_len(N):
+    """Transform length of the spectral e2e layer 1 (spectral.cuh spec_pick_L): smallest even L in {2^a, 3*2^a} >= N + q."""
+    need = N + (N - 1 - (N - 1) // 2)
+    cands = [c for a in range(1, 20) for c in (1 << a, 3 << a) if c >= need]
+    return max(4, min(cands))
+
+
+def spectral_bytes(N, C1=50, C2=20):
+    """Compulsory HBM bytes per graph of the spectral e2e layer-1 stage (each kernel reads its inputs and writes its
+    outputs once): fft(Y) + mix + ifft(O) forward; fft(dO) + mix + ifft(dY) + wgrad backward.  DESIGN.md section 4."""
+    F = spectral_len(N) // 2 + 1
+    lines = 2 * N
+    return lines * (8 * N * (C1 + C2) + 8 * F * 5 * (C1 + C2))
 
 
 class ClockSampler:
@@ -273,7 +288,25 @@ def run_ours(args):
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained"
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    roofline = {
+    if args.tc == 2:
+        peak_bw = peaks.get("hbm_gbs") or 6650.0
+        per_graph = spectral_bytes(N)
+        ach_bw = per_graph * B * args.steps / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else None
+        roofline = {
+            "bound": "hbm", "kernel": "e2e layer-1 spectral stage: spec_fft_fwd_fast_k, spec_gemm_k (fwd, dgrad), spec_fft_inv_fast_k, spec_wgrad_k",
+            "achieved": ach_bw, "peak": peak_bw, "unit": "GB/s", "frac": (ach_bw / peak_bw) if ach_bw else None, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+            "algorithmic_bytes_per_graph": per_graph,
+            "direct_form_equivalent_tflops": achieved,
+            "note": "achieved = compulsory bytes of the seven launches of the stage (inputs read once + outputs written once, "
+                    f"{per_graph / 1e6:.0f} MB per graph at N={N}) / their CUDA-event time; direct_form_equivalent_tflops = 3*F1 per graph "
+                    "(the block-Toeplitz GEMM flops this stage replaces, SURVEY 8d) / the same time, for comparison with the "
+                    "bf16x3 tensor ceiling (measured bf16 peak / 3)",
+            "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+            "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+        }
+    else:
+      roofline = {
         "bound": "tensor", "kernel": "toep_gemm_k<240> (fwd, dgrad) + wgrad_gemm_k: e2e layer-1 block-Toeplitz GEMMs",
         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
         "traffic": None, "peak_source": peak_src,
@@ -282,7 +315,7 @@ def run_ours(args):
                 "the 3-pass split-bf16 product executes >= 3x those FLOPs on the tensor pipe",
         "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
         "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
-    }
+      }
     cpu = None
     if not args.no_cpu_baseline:
         cb = cpu_reference(args, 2, 1)
@@ -294,7 +327,7 @@ def run_ours(args):
                 f"inputs {sum(feeds_np[k].nbytes for k in used) / 1e9:.1f} GB per rank >> L2)",
         "config": {"workload": f"SND-VAE {args.model} model (model.py) train step fwd+bwd+Adam, N={N}, S={S}, {B} graphs/step/GPU, "
                                f"global batch {world * B}", "num_nodes": N, "batch_per_gpu": B, "sampling_num": S,
-                   "parallelism": f"dp{world}", "chunk_graphs": int(eng.cfg.chunk_graphs), "tensor_cores": bool(args.tc),
+                   "parallelism": f"dp{world}", "chunk_graphs": int(eng.cfg.chunk_graphs), "tensor_cores": bool(args.tc), "e2e_layer1": {0: "fp32 SIMT", 1: "block-Toeplitz tcgen05 bf16x3", 2: "spectral: FFT + per-frequency tcgen05 bf16x3"}[args.tc],
                    "l2": "inputs larger than L2 (no flush needed)"},
         "clocks": cs.summary(), "gpu_launches": int(launches), "final_loss": final_loss,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -200,10 +200,15 @@ __global__ void __launch_bounds__(YP_THREADS) y_producer_k(const float* __restri
 __global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float* __restrict__ E1, const float* __restrict__ gam1,
                                     const float* __restrict__ bet1, float* __restrict__ g_gam1, float* __restrict__ g_bet1,
                                     float* __restrict__ g_b0, __nv_bfloat16* __restrict__ Ph, __nv_bfloat16* __restrict__ Pl,
-                                    float* __restrict__ dSa, int Bc, int N, int C1, int CS) {
+                                    float* __restrict__ dSa, int Bc, int N, int C1, int CS, int e1_tiled,
+                                    const float* __restrict__ Sa, const float* __restrict__ b0) {
   extern __shared__ float sm[];           // [4][blockDim]
   const long long row = blockIdx.x;
   const int i = (int)(row % N); const long long b = row / N;
+  // e1_tiled: E1 in the graph-tiled layout of y_producer_tc_k, row (b, i) at (((b / 128) N + i) 128 + b % 128) N C1
+  // (that layout leaves out the line-constant Sa[b,i,:] + 2 b0, added back here)
+  const float* E1row = E1 + (e1_tiled ? (((b / 128) * N + i) * 128 + (b % 128)) : row) * (long long)N * C1;
+  const float eb = e1_tiled ? Sa[row * C1 + threadIdx.x % C1] + 2.f * b0[threadIdx.x % C1] : 0.f;
   const long long plane_f = (long long)Bc * N * N * C1, plane_c = (long long)Bc * N * N;
   const int o = threadIdx.x % C1;
   const float g = gam1[o] * BN_RS, bt = bet1[o];
@@ -213,7 +218,7 @@ __global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float*
     const long long a0 = row * N * C1 + idx;
     const long long c1 = (b * N + j) * N + i;
     const float dy = dY12[a0] + dY12[plane_f + c1 * C1 + o];
-    const float e = E1[a0];
+    const float e = E1row[idx] + eb;
     const float dd = fmaf(e, g, bt) > 0.f ? dy : 0.f;
     sg = fmaf(dd, e, sg); sb += dd;
     const float de = dd * g;

@@ -63,10 +63,10 @@ struct sndvae_handle {
   float *a, *c, *Rc, *Sa, *WSa, *WSc, *da, *dc, *dRc, *dSa, *dWSa, *dWSc, *dv, *dsp0;
   float *gA, *gB, *gC;                 // generic [Rn, 64] backward temporaries
   float *colbuf;                       // [Rn, 5 * 50] im2col staging for conv1d weight gradients
-  float *E1, *O12, *dY12, *Yf, *dOf;   // chunk buffers (fp32)
+  float *E1, *E1T, *O12, *dY12, *Yf, *dOf;   // chunk buffers (fp32); E1T: transposed copy, spectral path only
   __nv_bfloat16 *Yhi, *Ylo, *dOhi, *dOlo;
   TcState tc; L0Dense l0d;
-  SpecState sp; int spec;              // use_tensor_cores == 2: e2e layer 1 in the frequency domain (spectral.cuh)
+  SpecState sp; YtcState ytc; int spec;              // use_tensor_cores == 2: e2e layer 1 in the frequency domain (spectral.cuh)
   float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg
   int* errflag;
   float* pinned_loss;
@@ -297,7 +297,11 @@ static int alloc_buffers(sndvae_t* h) {
   DA(h->dv, Rn * Chv); DA(h->dsp0, Rn * Chv);
   DA(h->gA, Rn * 64); DA(h->gB, Rn * 64); DA(h->gC, Rn * 64); DA(h->colbuf, Rn * KS * 64);
   const long long cells = (long long)h->Bc * N * N;
-  DA(h->E1, cells * C1); DA(h->O12, 2 * cells * C2); DA(h->dY12, 2 * cells * C1);
+  if (c.use_tensor_cores == 2) {     // graph-tiled layouts: whole tiles of 128 graphs
+    const long long tcells = (long long)((h->Bc + 127) / 128) * 128 * N * N;
+    DA(h->E1, tcells * C1); DA(h->E1T, tcells * C1);
+  } else { DA(h->E1, cells * C1); h->E1T = nullptr; }
+  DA(h->O12, 2 * cells * C2); DA(h->dY12, 2 * cells * C1);
   if (c.use_tensor_cores == 2) {
     // spectral path: the bf16 planes only carry dE1 (layer-0 backward operands); dO stays fp32
     DA(h->Yhi, 2 * cells * TC_CP); DA(h->Ylo, 2 * cells * TC_CP); DA(h->dOf, 2 * cells * C2);
@@ -571,7 +575,8 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
       return fail(h, SNDVAE_E_CUDA, "tensor-core layer-0 products: %s", tc_last_error());
     if (l0d_stage(h->l0d, 0, h->WSa, h->stream) || l0d_stage(h->l0d, 1, h->WSc, h->stream))
       return fail(h, SNDVAE_E_CUDA, "layer-0 dense staging: %s", tc_last_error());
-    if (h->spec && spec_stage_weights(h->sp, h->P + p.e_w[1], h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral weight staging: %s", tc_last_error());
+    if (h->spec && (spec_stage_weights(h->sp, h->P + p.e_w[1], h->stream) || ytc_stage(h->ytc, h->WSa, h->WSc, h->stream)))
+      return fail(h, SNDVAE_E_CUDA, "spectral weight staging: %s", tc_last_error());
     h->launches += 9;
   } else {
     LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
@@ -589,7 +594,15 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     const long long rows = (long long)bc * N, cells = rows * N;
     mark(h, "y_producer");
     YOut Y; Y.E1 = h->E1; Y.Yf = h->Yf; Y.Yhi = h->Yhi; Y.Ylo = h->Ylo; Y.CP = tc ? h->tc.l1.CSi : C1; Y.bf16 = tc && !h->spec;
-    {
+    if (h->spec) {
+      // batch-major tcgen05 form (spectral.cuh): only E1 is written; Y = relu(BN(E1)) is applied inside the forward FFT
+      TcState& T = h->tc; const long long po = b0 * N * h->ytc.CS;
+      // E1 (rows (b,i) sweep j) and its transpose E1T (rows (b,j) sweep i): the same kernel with the roles of a / c swapped
+      if (ytc_run(h->ytc, T.ah + po, T.al + po, T.ch + po, T.cl + po, 0, h->Rc + b0 * N * C1, h->Sa + b0 * N * C1, h->P + p.e_b[0], h->E1, bc, h->stream) ||
+          ytc_run(h->ytc, T.ch + po, T.cl + po, T.ah + po, T.al + po, 1, h->Sa + b0 * N * C1, h->Rc + b0 * N * C1, h->P + p.e_b[0], h->E1T, bc, h->stream))
+        return fail(h, SNDVAE_E_CUDA, "y_producer_tc: %s", tc_last_error());
+      h->launches += 2;
+    } else {
       // E1 / Y on the fp32 pipes (register-resident WS rows).  Routing the two K = 2H products through the tensor-core
       // kernel was measured slower (44 vs 31 ms per 512 graphs): with a single K chunk its epilogue dominates.
       dim3 yg(cdiv(N, YP_TJ), N);
@@ -600,7 +613,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     }
     mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
-    if (h->spec) { if (spec_forward(h->sp, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1], rows, h->O12, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral fwd: %s", tc_last_error()); h->launches += 3; }
+    if (h->spec) { if (spec_forward(h->sp, h->E1, h->E1T, h->P + p.e_bng[1], h->P + p.e_bnb[1], h->Sa + b0 * N * C1, h->Rc + b0 * N * C1, h->P + p.e_b[0], rows, h->O12, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral fwd: %s", tc_last_error()); h->launches += 3; }
     else if (tc) { if ((r = tc_plan_fwd(h->tc.l1, h->Yhi, h->Ylo, h->O12, 2 * rows, 2LL * h->Bc * N, 0, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc fwd: %s", tc_last_error()); h->launches++; }
     else LEW(e2e_l1_simt_fwd_k, 2 * cells * C2, h->Yf, h->P + p.e_w[1], h->O12, 2 * rows, N, C1, C2);
     ev_end(h);
@@ -641,7 +654,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
       TcState& T = h->tc; L0Dense& Ld = h->l0d;
       const int CSe = Ld.CSe; const long long poff = cells * CSe;        // direction-1 planes
       LAUNCH(l0_combine_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
-             h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], h->Yhi, h->Ylo, h->dSa + b0 * N * C1, bc, N, C1, CSe);
+             h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], h->Yhi, h->Ylo, h->dSa + b0 * N * C1, bc, N, C1, CSe, h->spec, h->Sa + b0 * N * C1, h->P + p.e_b[0]);
       LAUNCH(rowsum_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, h->Yhi + poff, h->Ylo + poff, h->dRc + b0 * N * C1, N, C1, CSe);
       mark(h, "l0_gemms");
       if (l0d_bwd_act(Ld, 0, h->Yhi, h->Ylo, h->da + b0 * N * Chv, rows, rows, h->stream) ||
@@ -918,7 +931,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     return fail(h, SNDVAE_E_ARG, "bad config: num_nodes=%d batch_size=%d", c.num_nodes, c.batch_size);
   if (c.model_type != SNDVAE_MODEL_DISENTANGLED && c.model_type != SNDVAE_MODEL_BASE) return fail(h, SNDVAE_E_ARG, "bad model_type %d", c.model_type);
   h->dis = c.model_type == SNDVAE_MODEL_DISENTANGLED;
-  h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp);
+  h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp); memset(&h->ytc, 0, sizeof h->ytc);
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
   if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);
@@ -932,7 +945,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     return fail(h, SNDVAE_E_ARG, "tensor-core e2e path requires e_d_hidden = (%d, %d)", TC_C1, TC_C2);
   if (c.chunk_graphs <= 0) {
     // bound the N^2 staging buffers to ~24 GB: E1 200 + O12 160 + dY12 400 + Y planes 448 + dO planes 192 B per (i,j) cell
-    long long per_graph = (long long)h->N * h->N * 1400;
+    long long per_graph = (long long)h->N * h->N * 1400;     // (+ 200 for the transposed E1 copy of the spectral path, inside its budget)
     long long budget = 24LL << 30;
     if (c.use_tensor_cores == 2) {   // + spectra: F frequencies x 2N lines x (Y^ planes 416 + O^ 160 + dO^ planes 160 + dY^ 400) B
       per_graph += (long long)(spec_pick_L(h->N) / 2 + 1) * 2 * h->N * 1136; budget = 56LL << 30; }
@@ -962,6 +975,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     if ((r = tc_init(h->tc, h->N, h->Chv, h->B, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
     if ((r = l0d_init(h->l0d, h->N, h->Chv, h->C1, h->stream))) return fail(h, SNDVAE_E_CUDA, "l0d_init: %s", tc_last_error());
     if (h->spec && (r = spec_init(h->sp, h->N, 2LL * h->Bc * h->N, h->stream))) return fail(h, SNDVAE_E_CUDA, "spec_init: %s", tc_last_error());
+    if (h->spec && (r = ytc_init(h->ytc, h->N, h->Chv, h->C1, h->stream))) return fail(h, SNDVAE_E_CUDA, "ytc_init: %s", tc_last_error());
   }
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -971,7 +985,7 @@ int sndvae_destroy(sndvae_t* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
-  if (h->spec) spec_destroy(h->sp);
+  if (h->spec) { spec_destroy(h->sp); ytc_destroy(h->ytc); }
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (h->pinned_loss) cudaFreeHost(h->pinned_loss);

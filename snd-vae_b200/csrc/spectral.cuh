@@ -134,7 +134,12 @@ struct FftFwdArgs {
   long long lines;        // lines [lines0, lines): line' = line - lines0
   int dir1_strided;       //   1: line' = (b, j) of a [b, N, N, C] tensor read along its first N axis (base = (b N N + j) C, stride N C)
                           //   0: contiguous like direction 0 (base = line * N * C)
+                          //   2: graph-tiled pair of tensors (y_producer_tc_k): line = (b, x) lives at in (dir 0) / in1 (dir 1)
+                          //      + ((((b / 128) N + x) 128 + b % 128) N C, contiguous
+  const float* in1;
   const float* gam; const float* bet;     // optional: x <- relu(x * gam * BN_RS + bet)  (BN_e1 + relu, model.py:201-202)
+  const float* bias0; const float* bias1; const float* b0;   // optional (with gam): x <- x + bias{0,1}[(b N + pos of the line), :] + 2 b0
+                                                              // before the BN (direction 0 / 1 lines; see y_producer_tc_k)
   __nv_bfloat16* oh; __nv_bfloat16* ol;   // [F][RA][KA]
   long long RA; int KA;
   int N, C, G;            // C real channels (even), G channel pairs per shared-memory group
@@ -150,9 +155,17 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_fwd_k(FftFwdAr
   if (A.gam) for (int t = threadIdx.x; t < A.C; t += blockDim.x) { s_g[t] = A.gam[t] * BN_RS; s_b[t] = A.bet[t]; }
   for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
     const float* base; long long pstride;
-    if (line < A.lines0 || !A.dir1_strided) { base = A.in + line * A.N * A.C; pstride = A.C; }
+    if (A.dir1_strided == 2) {
+      const bool d1 = line >= A.lines0; const long long l1 = d1 ? line - A.lines0 : line; const long long b = l1 / A.N; const int x = (int)(l1 - b * A.N);
+      base = (d1 ? A.in1 : A.in) + (((b / 128) * A.N + x) * 128 + (b % 128)) * A.N * A.C; pstride = A.C;
+    } else if (line < A.lines0 || !A.dir1_strided) { base = A.in + line * A.N * A.C; pstride = A.C; }
     else { const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
            base = A.in + (b * A.N * A.N + j) * A.C; pstride = (long long)A.N * A.C; }
+    if (A.gam && A.bias0) {            // per-line shift: (bias + 2 b0) * g + beta
+      __syncthreads();
+      const bool d1 = line >= A.lines0; const float* br = (d1 ? A.bias1 + (line - A.lines0) * A.C : A.bias0 + line * A.C);
+      for (int t = threadIdx.x; t < A.C; t += blockDim.x) s_b[t] = fmaf(br[t] + 2.f * A.b0[t], s_g[t], A.bet[t]);
+    }
     for (int cp0 = 0; cp0 < CP; cp0 += A.G) {
       const int g = min(A.G, CP - cp0);
       __syncthreads();
@@ -303,8 +316,12 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
   const bool vec16 = ((long long)N * C) % 4 == 0;
   auto prefetch = [&](long long line) {
     if (line >= A.lines) return;
-    if (line < A.lines0 || !A.dir1_strided) {
+    if (line < A.lines0 || A.dir1_strided != 1) {
       const float* base = A.in + line * N * C;
+      if (A.dir1_strided == 2) {
+        const bool d1 = line >= A.lines0; const long long l1 = d1 ? line - A.lines0 : line; const long long b = l1 / N; const int x = (int)(l1 - b * N);
+        base = (d1 ? A.in1 : A.in) + (((b / 128) * N + x) * 128 + (b % 128)) * N * C;
+      }
       if (vec16) { for (int t = threadIdx.x; t < N * C / 4; t += NT) cp_async16(stage + 4 * t, base + 4 * t); }
       else { for (int t = threadIdx.x; t < N * G; t += NT) cp_async8(stage + 2 * t, base + 2 * t); }
     } else {
@@ -317,6 +334,11 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
   cp_async_commit();
   for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
     cp_async_wait_all();
+    if (A.gam && A.bias0 && threadIdx.x < C) {     // per-line shift: (bias + 2 b0) * g + beta  (pass 1 of the previous line is long done)
+      const bool d1 = line >= A.lines0; const float* br = (d1 ? A.bias1 + (line - A.lines0) * C : A.bias0 + line * C);
+      const int t = threadIdx.x;
+      s_b[t] = fmaf(__ldg(br + t) + 2.f * __ldg(A.b0 + t), s_g[t], __ldg(A.bet + t));
+    }
     __syncthreads();                       // staged line visible; previous line's readers of bufA / bufB are done
     StageSrc<G> src; src.s = stage; src.N = N; src.sg = A.gam ? s_g : nullptr; src.sb = s_b;
     SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
@@ -877,9 +899,10 @@ static int spec_launch_inv_fast(SpecState& s, const FftInvArgs& a, cudaStream_t 
 static bool spec_plan_is(const FftPlan& pl, int r0, int r1, int r2) {
   return pl.npass == (r2 ? 3 : 2) && pl.rad[0] == r0 && pl.rad[1] == r1 && (!r2 || pl.rad[2] == r2);
 }
-static int spec_fft_fwd(SpecState& s, const float* in, long long lines0, long long lines, int dir1_strided, const float* gam, const float* bet,
+static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long long lines0, long long lines, int dir1_strided, const float* gam, const float* bet,
+                        const float* bias0, const float* bias1, const float* b0,
                         __nv_bfloat16* oh, __nv_bfloat16* ol, int KA, int C, int G, cudaStream_t st) {
-  FftFwdArgs a; a.in = in; a.lines0 = lines0; a.lines = lines; a.dir1_strided = dir1_strided; a.gam = gam; a.bet = bet; a.oh = oh; a.ol = ol;
+  FftFwdArgs a; a.in = in; a.in1 = in1; a.bias0 = bias0; a.bias1 = bias1; a.b0 = b0; a.lines0 = lines0; a.lines = lines; a.dir1_strided = dir1_strided; a.gam = gam; a.bet = bet; a.oh = oh; a.ol = ol;
   a.RA = s.RA; a.KA = KA; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
   int r = 1;
   if (!s.generic_only) {
@@ -908,9 +931,12 @@ static int spec_fft_inv(SpecState& s, const float* in, float* out, long long lin
   return tc_check_launch("spec_fft_inv_k");
 }
 // forward: O12[2 rows][N C2] = e2e-layer-1 row / column products of Y = relu(BN_e1(E1));  rows = bc * N
-static int spec_forward(SpecState& s, const float* E1, const float* gam1, const float* bet1, long long rows, float* O12, cudaStream_t st) {
+// E1 / E1T: graph-tiled layer-0 outputs of y_producer_tc_k (row and column lines both contiguous)
+// Sa / Rc / b0: the line-constant bias rows left out of E1 / E1T
+static int spec_forward(SpecState& s, const float* E1, const float* E1T, const float* gam1, const float* bet1, const float* Sa, const float* Rc,
+                        const float* b0, long long rows, float* O12, cudaStream_t st) {
   const long long lines = 2 * rows; const int F = s.pl.F;
-  if (spec_fft_fwd(s, E1, rows, lines, 1, gam1, bet1, s.Ah, s.Al, SP_KA1, s.C1, s.G1, st)) return -1;
+  if (spec_fft_fwd(s, E1, E1T, rows, lines, 2, gam1, bet1, Sa, Rc, b0, s.Ah, s.Al, SP_KA1, s.C1, s.G1, st)) return -1;
   CUtensorMap ah, al;
   if (spec_enc3(&ah, s.Ah, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, 128) ||
       spec_enc3(&al, s.Al, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, 128)) return -1;
@@ -923,7 +949,7 @@ static int spec_forward(SpecState& s, const float* E1, const float* gam1, const 
 // backward: dY12[2 rows][N C1] from dO [2 rows][N C2] (fp32, both layouts), and P += Y^^T dO^
 static int spec_backward(SpecState& s, const float* dO, long long rows, float* dY12, cudaStream_t st) {
   const long long lines = 2 * rows; const int F = s.pl.F;
-  if (spec_fft_fwd(s, dO, lines, lines, 0, nullptr, nullptr, s.Dh, s.Dl, SP_KA2, s.C2, s.G2, st)) return -1;
+  if (spec_fft_fwd(s, dO, nullptr, lines, lines, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s.Dh, s.Dl, SP_KA2, s.C2, s.G2, st)) return -1;
   CUtensorMap dh, dl;
   if (spec_enc3(&dh, s.Dh, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128) ||
       spec_enc3(&dl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128)) return -1;
@@ -954,4 +980,287 @@ static int spec_finalize_wgrad(SpecState& s, float* dw1, cudaStream_t st) {
   const long long n = (long long)s.N * s.C1 * s.C2;
   spec_wgrad_finalize_k<<<cdiv(n, 128), 128, 0, st>>>(s.P, s.twd, dw1, s.N, s.pl.L, s.pl.F, s.C1, s.C2);
   return tc_check_launch("spec_wgrad_finalize_k");
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// e2e layer 0 (collapsed) on the tensor cores, batch-major:
+//     E1[b, i, j, :] = [a[b,i,:] | c[b,j,:]] . [WSa[j]; WSc[i]] + Rc[b,j,:] + Sa[b,i,:] + 2 b0
+// (the kernel stores E1 - Sa[b,i,:] - 2 b0: that part is constant along the line the CTA sweeps and is added by the readers)
+// For a fixed (i, j) this is a GEMM over the graphs of the micro-batch: M = 128 graphs (TMEM lanes), K = 2 * 2H (3 + 3
+// k-steps of 16, zero padded by TMA), N = 64 (50 valid).  A CTA owns (graph tile, i): a[.,i,:] and WSc[i] stay in shared
+// memory while it sweeps j with a TMA ring of (c[.,j,:], WSa[j]) stages; positions are processed in pairs so that each
+// thread (= graph) writes 400 contiguous bytes of E1.  3-pass split-bf16, fp32 accumulation in TMEM.
+// ------------------------------------------------------------------------------------------------------------------------
+struct YtcArgs {
+  float* E1;             // tiled [nbt][N (fixed pos)][128 graphs][N (swept pos)][C1]; WITHOUT the fixed position's bias row and 2 b0
+                         // (constant along a line: the consumers -- forward FFT, l0_combine_planes_k -- add them)
+  const float* Rc;       // [Bc*N, C1] bias rows of the swept position
+  const float* Sa;       // unused (bias rows of the fixed position are added by the consumers)
+  const float* b0;       // unused
+  int Bc, N, C1, nbt;    // graphs in the micro-batch, nodes, channels (<= 56), graph tiles of 128
+};
+#define YTC_STAGES 2
+__global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant__ CUtensorMap tmAah, const __grid_constant__ CUtensorMap tmAal,
+                                                          const __grid_constant__ CUtensorMap tmAch, const __grid_constant__ CUtensorMap tmAcl,
+                                                          const __grid_constant__ CUtensorMap tmWah, const __grid_constant__ CUtensorMap tmWal,
+                                                          const __grid_constant__ CUtensorMap tmWch, const __grid_constant__ CUtensorMap tmWcl,
+                                                          YtcArgs P) {
+  constexpr int A_BYTES = 128 * 64 * 2;     // one plane of an activation tile: 128 graphs x 64 (K, 40 valid)
+  constexpr int W_BYTES = 64 * 64 * 2;      // one plane of a weight tile: 64 (o) x 64 (K)
+  constexpr int FIX_BYTES = 2 * A_BYTES + 2 * W_BYTES;       // a[., i] hi/lo + WSc[i] hi/lo
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;     // c[., j] hi/lo + WSa[j] hi/lo
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* fix = smem; uint8_t* ring = smem + FIX_BYTES;
+  float* xbuf = reinterpret_cast<float*>(ring + (size_t)YTC_STAGES * STAGE_BYTES);     // 4 epilogue warps x 12.8 KB
+  __shared__ uint64_t fix_full, fix_empty, full_bar[YTC_STAGES], empty_bar[YTC_STAGES], acc_full[4], acc_empty[4];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = P.N;
+  const long long nwork = (long long)P.nbt * N;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&fix_full, 1); mbar_init(&fix_empty, 1);
+    for (int s = 0; s < YTC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, nw = 0;
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++nw) {
+        const int bt = (int)(w / N), i = (int)(w - (long long)bt * N);
+        mbar_wait(&fix_empty, (nw & 1) ^ 1);
+        mbar_expect_tx(&fix_full, FIX_BYTES);
+        tma_load_3d(fix, &tmAah, &fix_full, 0, i, bt * 128);
+        tma_load_3d(fix + A_BYTES, &tmAal, &fix_full, 0, i, bt * 128);
+        tma_load_3d(fix + 2 * A_BYTES, &tmWch, &fix_full, 0, 0, i);
+        tma_load_3d(fix + 2 * A_BYTES + W_BYTES, &tmWcl, &fix_full, 0, 0, i);
+        for (int j = 0; j < N; ++j, ++it) {
+          const int s = it % YTC_STAGES; const uint32_t ph = (it / YTC_STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = ring + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_3d(st, &tmAch, &full_bar[s], 0, j, bt * 128);
+          tma_load_3d(st + A_BYTES, &tmAcl, &full_bar[s], 0, j, bt * 128);
+          tma_load_3d(st + 2 * A_BYTES, &tmWah, &full_bar[s], 0, 0, j);
+          tma_load_3d(st + 2 * A_BYTES + W_BYTES, &tmWal, &full_bar[s], 0, 0, j);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, 64, 0, 0);
+      int it = 0, nw = 0, pc = 0;
+      const uint32_t sf = smem_u32(fix);
+      for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++nw) {
+        mbar_wait(&fix_full, nw & 1);
+        tc_fence_after();
+        for (int j = 0; j < N; ++j, ++it) {
+          const int slot = pc & 3, half = j & 1;
+          if (half == 0) { mbar_wait(&acc_empty[slot], ((pc >> 2) & 1) ^ 1); tc_fence_after(); }
+          const int s = it % YTC_STAGES; const uint32_t ph = (it / YTC_STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t ss = smem_u32(ring + (size_t)s * STAGE_BYTES);
+          const uint32_t td = tmem_d + slot * 128 + half * 64;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {      // a[., i] . WSa[j]
+            const uint64_t ah = umma_desc(sf + k * 32, 16, 1024, 2ull), al = umma_desc(sf + A_BYTES + k * 32, 16, 1024, 2ull);
+            const uint64_t bh = umma_desc(ss + 2 * A_BYTES + k * 32, 16, 1024, 2ull), bl = umma_desc(ss + 2 * A_BYTES + W_BYTES + k * 32, 16, 1024, 2ull);
+            umma_bf16(td, ah, bh, idesc, k ? 1u : 0u); umma_bf16(td, ah, bl, idesc, 1u); umma_bf16(td, al, bh, idesc, 1u);
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {      // c[., j] . WSc[i]
+            const uint64_t ah = umma_desc(ss + k * 32, 16, 1024, 2ull), al = umma_desc(ss + A_BYTES + k * 32, 16, 1024, 2ull);
+            const uint64_t bh = umma_desc(sf + 2 * A_BYTES + k * 32, 16, 1024, 2ull), bl = umma_desc(sf + 2 * A_BYTES + W_BYTES + k * 32, 16, 1024, 2ull);
+            umma_bf16(td, ah, bh, idesc, 1u); umma_bf16(td, ah, bl, idesc, 1u); umma_bf16(td, al, bh, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (half == 1 || j == N - 1) { umma_commit(&acc_full[slot]); ++pc; }
+        }
+        umma_commit(&fix_empty);
+      }
+    }
+  } else {
+    // epilogue: thread = graph (TMEM lane).  Output layout is tiled so that the 128 graphs of a tile are 51 KB apart, not a
+    // whole [N,N,C1] plane apart:  out[((bt N + x) 128 + bl) N + y][C1]  (x = fixed position of the CTA, y = swept position)
+    constexpr int C1 = TC_C1;                   // 50: a pair of positions is 100 floats = 25 x 16 bytes
+    const int q = warp & 3;
+    int pc = 0;
+    const bool v4 = (N % 2) == 0;
+    for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const int bt = (int)(w / N), x = (int)(w - (long long)bt * N);
+      const int bl = q * 32 + lane, b = bt * 128 + bl;
+      const bool valid = b < P.Bc;
+      const int bb = valid ? b : 0;
+      float* erow = P.E1 + (((long long)bt * N + x) * 128 + bl) * N * C1;
+      const float* rrow = P.Rc + (long long)bb * N * C1;
+      if (v4) {
+        // Even N: a pair of positions is one 16-byte aligned 400-byte run per graph.  The warp moves its 32 x 400 B block
+        // cooperatively (consecutive lanes = consecutive 16-byte chunks, so every global instruction touches a few lines
+        // instead of 32) through a private shared-memory tile; each thread then adds its TMEM row in place.
+        float4* xw = reinterpret_cast<float4*>(xbuf) + (size_t)(warp - 2) * 800;      // [32 rows][25 x 16 B]
+        float* etile = P.E1 + (((long long)bt * N + x) * 128 + q * 32) * N * C1;
+        int osrc[25], odst[25]; uint32_t vmask = 0;
+#pragma unroll
+        for (int t = 0; t < 25; ++t) {
+          const int k = lane + 32 * t, row = k / 25, col = k - row * 25;
+          const int bg = bt * 128 + q * 32 + row;
+          osrc[t] = (bg < P.Bc ? bg : 0) * N * C1 + 4 * col;
+          odst[t] = row * N * C1 + 4 * col;
+          if (bg < P.Bc) vmask |= 1u << t;
+        }
+        float4 pf[25];
+#pragma unroll
+        for (int t = 0; t < 25; ++t) pf[t] = __ldg(reinterpret_cast<const float4*>(P.Rc + osrc[t]));
+        for (int j0 = 0; j0 < N; j0 += 2, ++pc) {
+          const int slot = pc & 3;
+          mbar_wait(&acc_full[slot], (pc >> 2) & 1);
+          tc_fence_after();
+          const uint32_t ta = tmem_d + slot * 128 + ((uint32_t)(q * 32) << 16);
+          float2* xr = reinterpret_cast<float2*>(xw + lane * 25);
+          // TMEM columns [0, 50) and [64, 114) -> floats [0, 50) and [50, 100) of this graph's row of the tile
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+#pragma unroll
+            for (int c0 = 0; c0 < 56; c0 += 8) {
+              uint32_t v[8];
+              tmem_ld8(ta + jj * 64 + c0, v);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (c0 + 2 * u < C1) xr[(jj * C1 + c0) / 2 + u] = make_float2(__uint_as_float(v[2 * u]), __uint_as_float(v[2 * u + 1]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[slot]);
+          // cooperative phase: tile chunk + prefetched bias chunk -> global; then prefetch the next pair's bias rows
+#pragma unroll
+          for (int t = 0; t < 25; ++t) {
+            float4 v = xw[lane + 32 * t];
+            v.x += pf[t].x; v.y += pf[t].y; v.z += pf[t].z; v.w += pf[t].w;
+            if (vmask >> t & 1) *reinterpret_cast<float4*>(etile + odst[t] + j0 * C1) = v;
+          }
+          if (j0 + 2 < N) {
+#pragma unroll
+            for (int t = 0; t < 25; ++t) pf[t] = __ldg(reinterpret_cast<const float4*>(P.Rc + osrc[t] + (j0 + 2) * C1));
+          }
+          __syncwarp();
+        }
+        continue;
+      }
+      for (int j0 = 0; j0 < N; j0 += 2, ++pc) {
+        const int slot = pc & 3;
+        const int nj = N - j0 < 2 ? N - j0 : 2;
+        float r[2 * C1];
+        {
+          const float2* rc = reinterpret_cast<const float2*>(rrow + (long long)j0 * C1);
+#pragma unroll
+          for (int u = 0; u < C1; ++u) { float2 t = make_float2(0.f, 0.f); if (u < nj * (C1 / 2)) t = __ldg(rc + u); r[2 * u] = t.x; r[2 * u + 1] = t.y; }
+        }
+        mbar_wait(&acc_full[slot], (pc >> 2) & 1);
+        tc_fence_after();
+        const uint32_t ta = tmem_d + slot * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          if (jj < nj) {
+#pragma unroll
+            for (int c0 = 0; c0 < 56; c0 += 8) {
+              uint32_t v[8];
+              tmem_ld8(ta + jj * 64 + c0, v);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) if (c0 + u < C1) r[jj * C1 + c0 + u] += __uint_as_float(v[u]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+        if (valid) {
+          float2* dst = reinterpret_cast<float2*>(erow + (long long)j0 * C1);
+#pragma unroll
+          for (int u = 0; u < C1; ++u) if (u < nj * (C1 / 2)) dst[u] = make_float2(r[2 * u], r[2 * u + 1]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 512); }
+}
+
+// WS fp32 [N][C1][Ch] -> bf16 hi / lo planes of the same shape (row stride CS = Ch padded to 16 bytes)
+__global__ void ytc_stage_ws_k(const float* __restrict__ WS, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long rows, int Ch, int CS) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Ch) return;
+  const long long r = idx / Ch; const int ch = (int)(idx - r * Ch);
+  const float v = WS[idx];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[r * CS + ch] = h; lo[r * CS + ch] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+struct YtcState {
+  int ready, N, Ch, CS, C1;
+  __nv_bfloat16 *Wah, *Wal, *Wch, *Wcl;      // [N][C1][CS]
+  CUtensorMap mWah, mWal, mWch, mWcl;
+  int grid_sms;
+};
+static const size_t YTC_SMEM = (size_t)(1 + YTC_STAGES) * (2 * 128 * 64 * 2 + 2 * 64 * 64 * 2) + 4 * 12800 + 1024;
+static void ytc_destroy(YtcState& y) {
+  void* ps[] = {y.Wah, y.Wal, y.Wch, y.Wcl};
+  for (void* p : ps) if (p) cudaFree(p);
+  memset(&y, 0, sizeof y);
+}
+static int ytc_enc3(CUtensorMap* tm, const void* base, long long d0, long long d1, long long d2, long long s1_b, long long s2_b, int b0, int b1, int b2) {
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t str[2] = {(cuuint64_t)s1_b, (cuuint64_t)s2_b};
+  cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+  return tc_encode(tm, base, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int ytc_init(YtcState& y, int N, int Ch, int C1, cudaStream_t st) {
+  memset(&y, 0, sizeof y);
+  if (tc_global_init()) return -1;
+  if (C1 != TC_C1 || Ch > 48) { snprintf(g_tc_err, sizeof g_tc_err, "y_producer_tc: C1 = %d and 2H <= 48 required", TC_C1); return -1; }
+  y.N = N; y.Ch = Ch; y.CS = tc_pad16(Ch); y.C1 = C1;
+  const size_t n = (size_t)N * C1 * y.CS + 256;
+  if (cudaMalloc(&y.Wah, n * 2) || cudaMalloc(&y.Wal, n * 2) || cudaMalloc(&y.Wch, n * 2) || cudaMalloc(&y.Wcl, n * 2)) {
+    snprintf(g_tc_err, sizeof g_tc_err, "cudaMalloc of y_producer_tc weights failed"); return -1;
+  }
+  cudaMemsetAsync(y.Wah, 0, n * 2, st); cudaMemsetAsync(y.Wal, 0, n * 2, st); cudaMemsetAsync(y.Wch, 0, n * 2, st); cudaMemsetAsync(y.Wcl, 0, n * 2, st);
+  // dims (k = Ch, o = C1, position = N): out-of-bounds k / o are zero-filled up to the 64 x 64 box
+  if (ytc_enc3(&y.mWah, y.Wah, Ch, C1, N, y.CS * 2, (long long)C1 * y.CS * 2, 64, 64, 1) || ytc_enc3(&y.mWal, y.Wal, Ch, C1, N, y.CS * 2, (long long)C1 * y.CS * 2, 64, 64, 1) ||
+      ytc_enc3(&y.mWch, y.Wch, Ch, C1, N, y.CS * 2, (long long)C1 * y.CS * 2, 64, 64, 1) || ytc_enc3(&y.mWcl, y.Wcl, Ch, C1, N, y.CS * 2, (long long)C1 * y.CS * 2, 64, 64, 1)) return -1;
+  cudaFuncSetAttribute(y_producer_tc_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)YTC_SMEM);
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  y.grid_sms = sms;
+  y.ready = 1;
+  return 0;
+}
+static int ytc_stage(YtcState& y, const float* WSa, const float* WSc, cudaStream_t st) {
+  const long long rows = (long long)y.N * y.C1;
+  ytc_stage_ws_k<<<cdiv(rows * y.Ch, 256), 256, 0, st>>>(WSa, y.Wah, y.Wal, rows, y.Ch, y.CS);
+  ytc_stage_ws_k<<<cdiv(rows * y.Ch, 256), 256, 0, st>>>(WSc, y.Wch, y.Wcl, rows, y.Ch, y.CS);
+  return tc_check_launch("ytc_stage_ws_k");
+}
+// ah/al, ch/cl: bf16 planes of a / c for the graphs of this micro-batch, [bc*N][CS]
+// fixed-side planes (fh/fl: a for E1, c for the transposed copy), swept-side planes (rh/rl); swap = 0: fixed weights WSc, swept WSa;
+// Rc = bias rows of the swept position, Sa = bias rows of the fixed position
+static int ytc_run(YtcState& y, const __nv_bfloat16* ah, const __nv_bfloat16* al, const __nv_bfloat16* ch, const __nv_bfloat16* cl, int swap,
+                   const float* Rc, const float* Sa, const float* b0, float* E1, int bc, cudaStream_t st) {
+  CUtensorMap mah, mal, mch, mcl;
+  const int N = y.N;
+  if (ytc_enc3(&mah, ah, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128) || ytc_enc3(&mal, al, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128) ||
+      ytc_enc3(&mch, ch, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128) || ytc_enc3(&mcl, cl, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128)) return -1;
+  YtcArgs a; a.E1 = E1; a.Rc = Rc; a.Sa = Sa; a.b0 = b0; a.Bc = bc; a.N = N; a.C1 = y.C1; a.nbt = (bc + 127) / 128;
+  const long long nwork = (long long)a.nbt * N;
+  const unsigned grid = (unsigned)(nwork < y.grid_sms ? nwork : y.grid_sms);
+  if (swap) y_producer_tc_k<<<grid, 192, YTC_SMEM, st>>>(mah, mal, mch, mcl, y.mWch, y.mWcl, y.mWah, y.mWal, a);
+  else y_producer_tc_k<<<grid, 192, YTC_SMEM, st>>>(mah, mal, mch, mcl, y.mWah, y.mWal, y.mWch, y.mWcl, a);
+  return tc_check_launch("y_producer_tc_k");
 }

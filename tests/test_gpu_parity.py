@@ -38,6 +38,10 @@ CASES = [  # model, N, B, S, tc, chunk
     ("disentangled", 25, 7, 10, 1, 3),      # BASELINE config 1 shape, ragged chunking (7 = 3 + 3 + 1)
     ("disentangled", 7, 5, 2, 1, 2),        # odd N (p = 3, q = 3), ragged
     ("base", 25, 3, 1, 1, 0),
+    # use_tensor_cores = 2: e2e layer 1 in the frequency domain (spectral.cuh); N=8 -> L=12 (radix 6,2), N=7 -> L=12,
+    # N=25 -> L=48 (radix 6,8: the compile-time-plan kernels), ragged chunking
+    ("disentangled", 8, 4, 3, 2, 0), ("base", 8, 4, 1, 2, 0), ("disentangled", 25, 7, 10, 2, 3), ("disentangled", 7, 5, 2, 2, 2),
+    ("base", 25, 3, 1, 2, 0), ("disentangled", 13, 3, 2, 2, 2),    # N=13 -> L=24 (radix 6,4)
 ]
 
 
@@ -72,7 +76,7 @@ def test_forward_backward_parity(built, model, N, B, S, tc, chunk):
     eng.close()
 
 
-@pytest.mark.parametrize("name,tc", [("dis_n8", 0), ("dis_n8", 1), ("base_n8", 1), ("dis_n25", 1)])
+@pytest.mark.parametrize("name,tc", [("dis_n8", 0), ("dis_n8", 1), ("base_n8", 1), ("dis_n25", 1), ("dis_n8", 2), ("base_n8", 2), ("dis_n25", 2)])
 def test_golden_fixtures(built, name, tc):
     z = np.load(os.path.join(GOLD, name + ".npz"))
     model = "base" if name.startswith("base") else "disentangled"
@@ -157,19 +161,19 @@ def test_threshold_rule_bit_exact(built):
 
 
 def test_tc_matches_simt_at_n100(built):
-    """tcgen05 split-bf16 path vs the fp32 SIMT reference kernels at a size the CPU oracle also
-    finishes in seconds (N=100: K = 5000 per output)."""
+    """tcgen05 split-bf16 Toeplitz path (1) and the spectral path (2; N=100 -> L=192, radix 6,8,4) vs the fp32 SIMT
+    reference kernels at a size the CPU oracle also finishes in seconds (N=100: K = 5000 per output)."""
     N, B, S = 100, 3, 2
     cfg, P, inp, noise = _setup(N, B, S, "disentangled")
     enc, z, dec, L, grads = O.loss_and_grads(P, inp, noise, cfg, "factored")
     out = {}
-    for tc in (0, 1):
+    for tc in (0, 1, 2):
         eng = _engine(built, N, B, S, "disentangled", tc)
         eng.set_params(P)
         r = eng.grads(inp, noise, fetch=("generated_adj_prob",))
         out[tc] = (r, eng.get_grads())
         eng.close()
-    for tc in (0, 1):
+    for tc in (0, 1, 2):
         r, gg = out[tc]
         np.testing.assert_allclose(r["overall_loss"], [x.item() for x in L["overall_loss"]], rtol=1e-4)
         assert _relmax(r["generated_adj_prob"].cpu().numpy(), dec["generated_adj_prob"].detach().numpy()) < 1e-4
@@ -178,7 +182,8 @@ def test_tc_matches_simt_at_n100(built):
             assert _relmax(gg[k].numpy(), grads[k].numpy()) < 1e-3, (tc, k)
 
 
-def test_full_size_properties_n256(built):
+@pytest.mark.parametrize("tc", [1, 2])
+def test_full_size_properties_n256(built, tc):
     """At BASELINE's N=256 the oracle is too slow for a batch, so check size-independent
     properties of the tensor-core path: (i) linearity of e2e layer 1 in its weights is implied by
     parity above; here (ii) batch independence: permuting graphs permutes outputs and leaves the
@@ -187,7 +192,7 @@ def test_full_size_properties_n256(built):
     gradient, (v) one graph against the oracle."""
     N, B, S = 256, 4, 2
     cfg, P, inp, noise = _setup(N, B, S, "disentangled", dtype=torch.float32)
-    eng = _engine(built, N, B, S, "disentangled", 1, chunk=3)
+    eng = _engine(built, N, B, S, "disentangled", tc, chunk=3)
     eng.set_params(P)
     r = eng.grads(inp, noise, fetch=("generated_adj_prob", "generated_adj"))
     g_full = eng.get_grads()
@@ -202,7 +207,7 @@ def test_full_size_properties_n256(built):
     np.testing.assert_allclose(r2["overall_loss"], r["overall_loss"], rtol=1e-5)
     eng.close()
     # shard sum: two engines' worth of half batches with global_batch = B
-    eng2 = _engine(built, N, B // 2, S, "disentangled", 1)
+    eng2 = _engine(built, N, B // 2, S, "disentangled", tc)
     eng2.set_params(P)
     acc = None
     for h in range(2):
@@ -219,7 +224,7 @@ def test_full_size_properties_n256(built):
     n1 = {"eps_s": noise["eps_s"][:1], "eps_g": noise["eps_g"][:1], "eps_sg": noise["eps_sg"][:S]}
     enc, z, dec, L = O.forward(O.cast(P, torch.float64), O.cast(i1, torch.float64), O.cast(n1, torch.float64), cfg)
     eng2.close()
-    eng3 = _engine(built, N, 1, S, "disentangled", 1)
+    eng3 = _engine(built, N, 1, S, "disentangled", tc)
     eng3.set_params(P)
     r3 = eng3.forward(i1, n1, fetch=("generated_adj_prob",))
     np.testing.assert_allclose(r3["overall_loss"], [x.item() for x in L["overall_loss"]], rtol=1e-4)
@@ -236,7 +241,7 @@ def test_edge_cases(built):
     inp["adj"] = inp["adj"].clone(); inp["adj"][0] = 0; inp["adj"][1] = 0            # graph 0: no sampled edges at all
     inp["adj_truth"] = inp["adj_truth"].clone(); inp["adj_truth"][0] = 0
     enc, z, dec, L, grads = O.loss_and_grads(P, inp, noise, cfg)
-    eng = _engine(built, N, B, S, "disentangled", 1)
+    eng = _engine(built, N, B, S, "disentangled", 2)
     eng.set_params(P)
     r = eng.grads(inp, noise, fetch=("generated_adj_prob",))
     np.testing.assert_allclose(r["overall_loss"], [x.item() for x in L["overall_loss"]], rtol=1e-4)
@@ -311,3 +316,27 @@ def test_host_entry_point_and_shims(built):
     for k in P1:
         np.testing.assert_allclose(P1[k].numpy(), P2[k].numpy(), rtol=0, atol=2e-6, err_msg=k)      # atomics order: not bit-identical
     F.reset()
+
+
+def test_spectral_matches_toeplitz_n256(built):
+    """The two tensor-core formulations of e2e layer 1 -- block-Toeplitz GEMM (1) and per-frequency channel mix between
+    Stockham FFTs (2; N=256 -> L=384, radix 6,8,8) -- agree on the logits and on dw1 at BASELINE's N; the generic
+    runtime-plan FFT kernels (SNDVAE_FFT_GENERIC=1) agree with the compile-time-plan ones."""
+    N, B, S = 256, 3, 2
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", dtype=torch.float32)
+    out = {}
+    for name, tc, env in (("toep", 1, None), ("spec", 2, None), ("spec_generic", 2, "1")):
+        if env: os.environ["SNDVAE_FFT_GENERIC"] = env
+        try:
+            eng = _engine(built, N, B, S, "disentangled", tc, chunk=2)
+        finally:
+            os.environ.pop("SNDVAE_FFT_GENERIC", None)
+        eng.set_params(P)
+        r = eng.grads(inp, noise, fetch=("generated_adj_prob",))
+        out[name] = (r["generated_adj_prob"].cpu().numpy(), eng.get_grads(), r["overall_loss"])
+        eng.close()
+    for name in ("spec", "spec_generic"):
+        assert _relmax(out[name][0], out["toep"][0]) < 5e-5, name
+        np.testing.assert_allclose(out[name][2], out["toep"][2], rtol=2e-5)
+        for k in ("decoder/e1_deconv/w1", "decoder/e1_deconv/biases1", "decoder/d_bn_e1/gamma", "decoder/e0_deconv/w1"):
+            assert _relmax(out[name][1][k].numpy(), out["toep"][1][k].numpy()) < 1e-3, (name, k)
