@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(YP_THREADS) y_producer_k(const float* __restri
 __global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float* __restrict__ E1, const float* __restrict__ gam1,
                                     const float* __restrict__ bet1, float* __restrict__ g_gam1, float* __restrict__ g_bet1,
                                     float* __restrict__ g_b0, __nv_bfloat16* __restrict__ Ph, __nv_bfloat16* __restrict__ Pl,
-                                    float* __restrict__ dSa, int Bc, int N, int C1, int CS, int e1_tiled,
+                                    float* __restrict__ dSa, int Bc, int N, int C1, int CS, int e1_tiled,     /* e1_tiled also: dY12 plane 1 is in the [b,i,j,c] layout */
                                     const float* __restrict__ Sa, const float* __restrict__ b0) {
   extern __shared__ float sm[];           // [4][blockDim]
   const long long row = blockIdx.x;
@@ -217,7 +217,7 @@ __global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float*
     const int j = idx / C1;
     const long long a0 = row * N * C1 + idx;
     const long long c1 = (b * N + j) * N + i;
-    const float dy = dY12[a0] + dY12[plane_f + c1 * C1 + o];
+    const float dy = dY12[a0] + (e1_tiled ? dY12[plane_f + a0] : dY12[plane_f + c1 * C1 + o]);
     const float e = E1row[idx] + eb;
     const float dd = fmaf(e, g, bt) > 0.f ? dy : 0.f;
     sg = fmaf(dd, e, sg); sb += dd;
@@ -464,6 +464,91 @@ __global__ void __launch_bounds__(256, 2) edge_epilogue_k(EpiParams P, int Bc, i
         atomicAdd(P.g_Me + q * 2 + 1, v0); atomicAdd(P.g_Me + q * 2, -v0);
         if (P.g_gd) { atomicAdd(P.g_gd + q, v1 * BN_RS); atomicAdd(P.g_bd + q, v2); }
         atomicAdd(P.g_b1 + q, 2.f * v3);                  // bias added twice (layers.py:438,446)
+      }
+    }
+  }
+}
+
+// ---- elementwise variant for the spectral path: both e2e directions arrive in the [b, i, j, q] layout (plane 0 / plane 1 of
+// O12) and dO leaves in that layout only, so there is nothing to transpose: one thread per cell, grid-stride. ------------------
+__global__ void __launch_bounds__(256, 2) edge_epilogue_ew_k(EpiParams P, int Bc, int N) {
+  constexpr int C2 = EPI_C2;
+  __shared__ float wme0[C2], wme1[C2], gsc[C2], gsh[C2], bb[C2];
+  if (threadIdx.x < C2) {
+    const int q = threadIdx.x;
+    wme0[q] = P.Me[q * 2]; wme1[q] = P.Me[q * 2 + 1];
+    gsc[q] = P.gd ? P.gd[q] * BN_RS : 1.f; gsh[q] = P.bd ? P.bd[q] : 0.f;
+    bb[q] = 2.f * P.b1[q];
+  }
+  __syncthreads();
+  const float be0 = P.be[0], be1 = P.be[1];
+  const long long cells = (long long)Bc * N * N;
+  const bool do_bwd = P.backward && P.At;
+  float acc_gg[C2], acc_gb[C2], acc_m0[C2];        // sum dO[q] = gsc[q] * acc_gb[q]
+#pragma unroll
+  for (int q = 0; q < C2; ++q) { acc_gg[q] = 0.f; acc_gb[q] = 0.f; acc_m0[q] = 0.f; }
+  float acc_l1 = 0.f, loss = 0.f;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cells; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % N), i = (int)((e / N) % N);
+    float o[C2];
+    {
+      const float4* p1 = reinterpret_cast<const float4*>(P.O12 + e * C2);
+      const float4* p2 = reinterpret_cast<const float4*>(P.O12 + (cells + e) * C2);
+#pragma unroll
+      for (int v = 0; v < C2 / 4; ++v) {
+        const float4 x = p1[v], y = p2[v];
+        o[4 * v] = x.x + y.x + bb[4 * v]; o[4 * v + 1] = x.y + y.y + bb[4 * v + 1];
+        o[4 * v + 2] = x.z + y.z + bb[4 * v + 2]; o[4 * v + 3] = x.w + y.w + bb[4 * v + 3];
+      }
+    }
+    float l0 = be0, l1 = be1;
+#pragma unroll
+    for (int q = 0; q < C2; ++q) {
+      const float z = fmaxf(fmaf(o[q], gsc[q], gsh[q]), 0.f);
+      l0 = fmaf(z, wme0[q], l0); l1 = fmaf(z, wme1[q], l1);
+    }
+    const float m = (i == j) ? 0.f : 1.f;
+    const float p0 = m * l0 + (1.f - m), p1v = m * l1;         // model.py:205-206
+    if (P.logits) *reinterpret_cast<float2*>(P.logits + e * 2) = make_float2(p0, p1v);
+    if (P.gen_adj) P.gen_adj[e] = threshold_rule(p0, p1v);
+    float d1 = 0.f;
+    if (P.At) {
+      const float mx = fmaxf(p0, p1v);
+      const float e0 = expf(p0 - mx), e1 = expf(p1v - mx);
+      const float sden = e0 + e1;
+      const float A = P.At[e];
+      loss += mx + logf(sden) - ((1.f - A) * p0 + A * p1v);
+      d1 = m * (e1 / sden - A) * P.gscale;
+    }
+    if (do_bwd) {
+      acc_l1 += d1;
+      float d[C2];
+#pragma unroll
+      for (int q = 0; q < C2; ++q) {
+        const float z = fmaxf(fmaf(o[q], gsc[q], gsh[q]), 0.f);
+        acc_m0[q] = fmaf(z, d1, acc_m0[q]);
+        const float dd = z > 0.f ? d1 * (wme1[q] - wme0[q]) : 0.f;
+        acc_gg[q] = fmaf(dd, o[q], acc_gg[q]); acc_gb[q] += dd;
+        d[q] = dd * gsc[q];
+      }
+      float4* pd = reinterpret_cast<float4*>(P.dOf + e * C2);
+#pragma unroll
+      for (int v = 0; v < C2 / 4; ++v) pd[v] = make_float4(d[4 * v], d[4 * v + 1], d[4 * v + 2], d[4 * v + 3]);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  loss = warp_sum(loss);
+  if (lane == 0 && P.loss_sum && P.At) atomicAdd(P.loss_sum, loss);
+  if (do_bwd) {
+    acc_l1 = warp_sum(acc_l1);
+    if (lane == 0) { atomicAdd(P.g_be + 1, acc_l1); atomicAdd(P.g_be, -acc_l1); }
+#pragma unroll
+    for (int q = 0; q < C2; ++q) {
+      float v0 = warp_sum(acc_m0[q]), v1 = warp_sum(acc_gg[q]), v2 = warp_sum(acc_gb[q]), v3 = v2 * gsc[q];
+      if (lane == 0) {
+        atomicAdd(P.g_Me + q * 2 + 1, v0); atomicAdd(P.g_Me + q * 2, -v0);
+        if (P.g_gd) { atomicAdd(P.g_gd + q, v1 * BN_RS); atomicAdd(P.g_bd + q, v2); }
+        atomicAdd(P.g_b1 + q, 2.f * v3);
       }
     }
   }

@@ -76,7 +76,18 @@ struct sndvae_handle {
   // gemm timing
   std::vector<EvPair> ev; size_t ev_used;
   StageTimer stt;
+  // per-graph views: every buffer indexed by graph (or by sample) registers its per-graph byte size; view_shift moves all of
+  // them at once so that the forward functions can run on a contiguous piece of the batch (pipelined host step)
+  struct Shift { char** p; long long bytes; };
+  std::vector<Shift> shifts;
+  cudaStream_t cs, ds;                 // host-step copy streams (H2D feeds, D2H generated_adj)
+  std::vector<cudaEvent_t> pev;        // per-piece events: 2 per piece (feeds landed, piece computed)
+  cudaEvent_t ev_start;
 };
+static void view_shift(sndvae_handle* h, long long g) { for (auto& s : h->shifts) *s.p += g * s.bytes; }
+template <typename T> static void reg_shift(sndvae_handle* h, T** p, long long elems_per_graph) {
+  h->shifts.push_back({reinterpret_cast<char**>(p), elems_per_graph * (long long)sizeof(T)});
+}
 // optional per-stage timing (env SNDVAE_STAGE_TIMING=1): mark(h, "name") closes the previous stage
 static void mark(sndvae_handle* h, const char* name) {
   StageTimer& t = h->stt;
@@ -249,53 +260,55 @@ static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long 
   return 0;
 }
 
+// DG: a buffer with `pg` elements per graph of the batch (registered for view_shift)
+#define DG(ptr, pg) do { DA(ptr, B * (long long)(pg)); reg_shift(h, &(ptr), (long long)(pg)); } while (0)
 static int alloc_buffers(sndvae_t* h) {
   const sndvae_config& c = h->cfg;
-  const long long B = h->B, BS = h->BS, Rn = h->Rn;
-  const int N = h->N, F = h->F, D = h->D, H = h->H, Chv = h->Chv, C1 = h->C1, C2 = h->C2;
+  const long long B = h->B;
+  const int N = h->N, F = h->F, D = h->D, H = h->H, Chv = h->Chv, C1 = h->C1, C2 = h->C2, S = h->S;
   DA(h->P, h->nparam); DA(h->G, h->nparam); DA(h->M, h->nparam); DA(h->V, h->nparam);
   if (h->dis) {
     int g0 = c.g_conv_hidden[0], g1c = c.g_conv_hidden[1];
-    DA(h->t0, Rn * g0); DA(h->c0, Rn * g0); DA(h->g1, Rn * (g0 + F)); DA(h->t1, Rn * g1c); DA(h->c1, Rn * g1c);
-    DA(h->g2, Rn * (g1c + F)); DA(h->fg, Rn * (g1c + F));
-    DA(h->hg, B * c.g_hidden_size); DA(h->mu_g, B * c.g_latent_size); DA(h->ls_g, B * c.g_latent_size);
-    DA(h->h1p, Rn * c.s_channel[0]); DA(h->h1, Rn * c.s_channel[0]); DA(h->h2p, Rn * c.s_channel[1]); DA(h->h2, Rn * c.s_channel[1]);
-    DA(h->h3p, Rn * c.s_channel[2]); DA(h->h3, Rn * c.s_channel[2]); DA(h->fs, Rn * c.s_channel[2]);
-    DA(h->hs, B * c.s_hidden_size); DA(h->mu_s, B * c.s_latent_size); DA(h->ls_s, B * c.s_latent_size);
-    DA(h->z_s, B * c.s_latent_size); DA(h->z_g, B * c.g_latent_size); DA(h->dz_s, B * c.s_latent_size); DA(h->dz_g, B * c.g_latent_size);
-    DA(h->n_s, Rn * H); DA(h->n_g, Rn * H); DA(h->dn_s, Rn * H); DA(h->dn_g, Rn * H);
+    DG(h->t0, N * g0); DG(h->c0, N * g0); DG(h->g1, N * (g0 + F)); DG(h->t1, N * g1c); DG(h->c1, N * g1c);
+    DG(h->g2, N * (g1c + F)); DG(h->fg, N * (g1c + F));
+    DG(h->hg, c.g_hidden_size); DG(h->mu_g, c.g_latent_size); DG(h->ls_g, c.g_latent_size);
+    DG(h->h1p, N * c.s_channel[0]); DG(h->h1, N * c.s_channel[0]); DG(h->h2p, N * c.s_channel[1]); DG(h->h2, N * c.s_channel[1]);
+    DG(h->h3p, N * c.s_channel[2]); DG(h->h3, N * c.s_channel[2]); DG(h->fs, N * c.s_channel[2]);
+    DG(h->hs, c.s_hidden_size); DG(h->mu_s, c.s_latent_size); DG(h->ls_s, c.s_latent_size);
+    DG(h->z_s, c.s_latent_size); DG(h->z_g, c.g_latent_size); DG(h->dz_s, c.s_latent_size); DG(h->dz_g, c.g_latent_size);
+    DG(h->n_s, N * H); DG(h->n_g, N * H); DG(h->dn_s, N * H); DG(h->dn_g, N * H);
   }
   const int hl = c.sg_conv_hidden[1][2];
-  DA(h->fsg, BS * N * hl); DA(h->dfsg, BS * N * hl);
-  DA(h->hsg, BS * c.sg_hidden_size); DA(h->mu_sg, BS * c.sg_latent_size); DA(h->ls_sg, BS * c.sg_latent_size);
+  DG(h->fsg, (long long)S * N * hl); DG(h->dfsg, (long long)S * N * hl);
+  DG(h->hsg, S * c.sg_hidden_size); DG(h->mu_sg, S * c.sg_latent_size); DG(h->ls_sg, S * c.sg_latent_size);
   // edge storage for all samples, SGC activations for one chunk of SC samples
   SgcEdges& E = h->E; E.cap = c.edge_capacity;
-  DA(E.rowstart, BS * N); DA(E.rowcnt, BS * N); DA(E.erow, BS * E.cap); DA(E.ecol, BS * E.cap);
-  DA(E.ea, BS * E.cap); DA(E.epr, BS * E.cap); DA(E.eG, BS * E.cap); DA(E.deg, BS * N); DA(E.ssum, BS * N); DA(E.nedges, BS);
+  DG(E.rowstart, S * N); DG(E.rowcnt, S * N); DG(E.erow, (long long)S * E.cap); DG(E.ecol, (long long)S * E.cap);
+  DG(E.ea, (long long)S * E.cap); DG(E.epr, (long long)S * E.cap); DG(E.eG, (long long)S * E.cap); DG(E.deg, S * N); DG(E.ssum, S * N); DG(E.nedges, S);
   const long long SC = h->SC;
   int r;
   if ((r = alloc_scratch(h, h->S0, F, c.sg_conv_hidden[0], SC, N, E.cap))) return r;
   if ((r = alloc_scratch(h, h->S1, c.sg_conv_hidden[0][2], c.sg_conv_hidden[1], SC, N, E.cap))) return r;
   DA(h->x1, SC * N * c.sg_conv_hidden[0][2]); DA(h->x2, SC * N * hl); DA(h->dxa, SC * N * hl); DA(h->dxb, SC * N * hl);
-  DA(h->z_sg, BS * c.sg_latent_size); DA(h->zbar, B * c.sg_latent_size); DA(h->dzbar, B * c.sg_latent_size);
+  DG(h->z_sg, S * c.sg_latent_size); DG(h->zbar, c.sg_latent_size); DG(h->dzbar, c.sg_latent_size);
   long long maxL = c.sg_latent_size > c.sg_hidden_size ? c.sg_latent_size : c.sg_hidden_size;
   if (h->dis) { int m2 = c.s_latent_size > c.g_latent_size ? c.s_latent_size : c.g_latent_size; if (m2 > maxL) maxL = m2;
                 if (c.s_hidden_size > maxL) maxL = c.s_hidden_size; if (c.g_hidden_size > maxL) maxL = c.g_hidden_size; }
-  DA(h->dmu, BS * maxL); DA(h->dls, BS * maxL); DA(h->dh, BS * maxL);
-  DA(h->n_sg, Rn * H); DA(h->dn_sg, Rn * H);
-  DA(h->v, Rn * Chv);
-  if (h->dis) DA(h->sp0, Rn * Chv); else h->sp0 = h->v;
-  DA(h->q1p, Rn * c.n_d_channel[0]); DA(h->q1, Rn * c.n_d_channel[0]); DA(h->q2p, Rn * c.n_d_channel[1]); DA(h->q2, Rn * c.n_d_channel[1]);
-  if (h->dis) DA(h->q3, Rn * c.n_d_channel[1]); else h->q3 = h->q2;
-  DA(h->xpre, Rn * F); DA(h->xhat, Rn * F); DA(h->dxpre, Rn * F);
-  DA(h->s1p, Rn * c.s_d_channel[0]); DA(h->s1, Rn * c.s_d_channel[0]); DA(h->s2p, Rn * c.s_d_channel[1]); DA(h->s2, Rn * c.s_d_channel[1]);
-  DA(h->s3p, Rn * c.s_d_channel[2]); DA(h->s3, Rn * c.s_d_channel[2]); DA(h->ppre, Rn * D); DA(h->phat, Rn * D); DA(h->dppre, Rn * D);
-  DA(h->a, Rn * Chv); DA(h->c, Rn * Chv); DA(h->Rc, Rn * C1); DA(h->Sa, Rn * C1);
+  DG(h->dmu, S * maxL); DG(h->dls, S * maxL); DG(h->dh, S * maxL);
+  DG(h->n_sg, N * H); DG(h->dn_sg, N * H);
+  DG(h->v, N * Chv);
+  if (h->dis) DG(h->sp0, N * Chv); else { h->sp0 = h->v; reg_shift(h, &h->sp0, (long long)N * Chv); }
+  DG(h->q1p, N * c.n_d_channel[0]); DG(h->q1, N * c.n_d_channel[0]); DG(h->q2p, N * c.n_d_channel[1]); DG(h->q2, N * c.n_d_channel[1]);
+  if (h->dis) DG(h->q3, N * c.n_d_channel[1]); else { h->q3 = h->q2; reg_shift(h, &h->q3, (long long)N * c.n_d_channel[1]); }
+  DG(h->xpre, N * F); DG(h->xhat, N * F); DG(h->dxpre, N * F);
+  DG(h->s1p, N * c.s_d_channel[0]); DG(h->s1, N * c.s_d_channel[0]); DG(h->s2p, N * c.s_d_channel[1]); DG(h->s2, N * c.s_d_channel[1]);
+  DG(h->s3p, N * c.s_d_channel[2]); DG(h->s3, N * c.s_d_channel[2]); DG(h->ppre, N * D); DG(h->phat, N * D); DG(h->dppre, N * D);
+  DG(h->a, N * Chv); DG(h->c, N * Chv); DG(h->Rc, N * C1); DG(h->Sa, N * C1);
   DA(h->WSa, (long long)N * C1 * Chv); DA(h->WSc, (long long)N * C1 * Chv);
-  DA(h->da, Rn * Chv); DA(h->dc, Rn * Chv); DA(h->dRc, Rn * C1); DA(h->dSa, Rn * C1);
+  DG(h->da, N * Chv); DG(h->dc, N * Chv); DG(h->dRc, N * C1); DG(h->dSa, N * C1);
   DA(h->dWSa, (long long)N * C1 * Chv); DA(h->dWSc, (long long)N * C1 * Chv);
-  DA(h->dv, Rn * Chv); DA(h->dsp0, Rn * Chv);
-  DA(h->gA, Rn * 64); DA(h->gB, Rn * 64); DA(h->gC, Rn * 64); DA(h->colbuf, Rn * KS * 64);
+  DG(h->dv, N * Chv); DG(h->dsp0, N * Chv);
+  DG(h->gA, N * 64); DG(h->gB, N * 64); DG(h->gC, N * 64); DG(h->colbuf, N * KS * 64);
   const long long cells = (long long)h->Bc * N * N;
   if (c.use_tensor_cores == 2) {     // graph-tiled layouts: whole tiles of 128 graphs
     const long long tcells = (long long)((h->Bc + 127) / 128) * 128 * N * N;
@@ -562,30 +575,17 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   const float* w0 = h->P + p.e_w[0];
   bn_fwd(h, h->v, Chv, p.e_bng[0], p.e_bnb[0], h->a, Chv, Rn, Chv, ACT_RELU, 0);
   bn_fwd(h, h->v, Chv, p.e_bng[0] + Chv, p.e_bnb[0] + Chv, h->c, Chv, Rn, Chv, ACT_RELU, 0);
-  LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSa, N, Ctot, 0, Chv, C1);
-  LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSc, N, Ctot, Chv, Chv, C1);
   const bool tc = c.use_tensor_cores != 0;
   if (tc) {
     // Rc = c . Toeplitz(w0[:, Ch:, :]),  Sa = a . Toeplitz(w0[:, :Ch, :])  on the tensor cores (split-bf16)
     TcState& T = h->tc;
-    if ((!h->spec && tc_plan_stage(T.l1, h->P + p.e_w[1], C1, 0, h->stream)) || tc_plan_stage(T.l0a, w0, Ctot, 0, h->stream) ||
-        tc_plan_stage(T.l0c, w0, Ctot, Chv, h->stream) ||
-        tc_split(h->a, T.ah, T.al, Rn, Chv, T.l0a.CSi, h->stream) || tc_split(h->c, T.ch, T.cl, Rn, Chv, T.l0c.CSi, h->stream) ||
+    if (tc_split(h->a, T.ah, T.al, Rn, Chv, T.l0a.CSi, h->stream) || tc_split(h->c, T.ch, T.cl, Rn, Chv, T.l0c.CSi, h->stream) ||
         tc_plan_fwd(T.l0c, T.ch, T.cl, h->Rc, B, B, 0, h->stream) || tc_plan_fwd(T.l0a, T.ah, T.al, h->Sa, B, B, 0, h->stream))
       return fail(h, SNDVAE_E_CUDA, "tensor-core layer-0 products: %s", tc_last_error());
-    if (l0d_stage(h->l0d, 0, h->WSa, h->stream) || l0d_stage(h->l0d, 1, h->WSc, h->stream))
-      return fail(h, SNDVAE_E_CUDA, "layer-0 dense staging: %s", tc_last_error());
-    if (h->spec && (spec_stage_weights(h->sp, h->P + p.e_w[1], h->stream) || ytc_stage(h->ytc, h->WSa, h->WSc, h->stream)))
-      return fail(h, SNDVAE_E_CUDA, "spectral weight staging: %s", tc_last_error());
-    h->launches += 9;
+    h->launches += 4;
   } else {
     LEW(toep_vec_fwd_k, Rn * C1, h->c, w0, h->Rc, B, N, Ctot, Chv, Chv, C1);
     LEW(toep_vec_fwd_k, Rn * C1, h->a, w0, h->Sa, B, N, Ctot, 0, Chv, C1);
-  }
-  if (backward && h->spec && spec_zero_wgrad(h->sp, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral wgrad reset failed");
-  if (backward) {
-    CK(cudaMemsetAsync(h->dWSa, 0, sizeof(float) * N * C1 * Chv, h->stream));
-    CK(cudaMemsetAsync(h->dWSc, 0, sizeof(float) * N * C1 * Chv, h->stream));
   }
   const double f1 = 2.0 * 2.0 * N * ((double)N * N - (double)((N - 1) / 2) * ((N - 1) / 2 + 1) / 2.0 -
                                      (double)(N - 1 - (N - 1) / 2) * (N - (N - 1) / 2) / 2.0) * C1 * C2;
@@ -632,7 +632,8 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     ep.gscale = 1.f / (gB * N * N);
     { long long ntile = (long long)bc * cdiv(N, EPI_T) * cdiv(N, EPI_T);
       unsigned grid = (unsigned)(ntile < 148 * 3 ? ntile : 148 * 3);
-      LAUNCH(edge_epilogue_k, grid, 256, EPI_SMEM_BYTES, ep, bc, N); }
+      if (h->spec) LAUNCH(edge_epilogue_ew_k, 148 * 4, 256, 0, ep, bc, N);
+      else LAUNCH(edge_epilogue_k, grid, 256, EPI_SMEM_BYTES, ep, bc, N); }
     if (!backward) continue;
     // backward of e2e layer 1: dgrad + wgrad
     mark(h, "gemm_dgrad");
@@ -678,8 +679,38 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
       CKB(gemm_rm(h, true, false, N * C1, Chv, (int)rows, 1.f, dE1t, N * C1, h->c + b0 * N * Chv, Chv, 1.f, h->dWSc, Chv));
     }
   }
+  return 0;
+}
+
+// per-step staging shared by every piece of the batch: layer-0 weight sums, tensor-core operand copies of the e2e weights,
+// accumulator resets  (decoder_finish folds the frequency-domain weight gradient into dw1 once all pieces are done)
+static int decoder_prepare(sndvae_t* h, bool backward) {
+  const sndvae_config& c = h->cfg; const PT& p = h->pt;
+  const int N = h->N, Chv = h->Chv, C1 = h->C1; const int Ctot = 2 * Chv;
+  const float* w0 = h->P + p.e_w[0];
+  LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSa, N, Ctot, 0, Chv, C1);
+  LEW(e2e_l0_prep_k, (long long)N * C1 * Chv, w0, h->WSc, N, Ctot, Chv, Chv, C1);
+  if (c.use_tensor_cores) {
+    TcState& T = h->tc;
+    if ((!h->spec && tc_plan_stage(T.l1, h->P + p.e_w[1], C1, 0, h->stream)) || tc_plan_stage(T.l0a, w0, Ctot, 0, h->stream) ||
+        tc_plan_stage(T.l0c, w0, Ctot, Chv, h->stream))
+      return fail(h, SNDVAE_E_CUDA, "tensor-core weight staging: %s", tc_last_error());
+    if (l0d_stage(h->l0d, 0, h->WSa, h->stream) || l0d_stage(h->l0d, 1, h->WSc, h->stream))
+      return fail(h, SNDVAE_E_CUDA, "layer-0 dense staging: %s", tc_last_error());
+    if (h->spec && (spec_stage_weights(h->sp, h->P + p.e_w[1], h->stream) || ytc_stage(h->ytc, h->WSa, h->WSc, h->stream)))
+      return fail(h, SNDVAE_E_CUDA, "spectral weight staging: %s", tc_last_error());
+    h->launches += 5;
+  }
+  if (backward && h->spec && spec_zero_wgrad(h->sp, h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral wgrad reset failed");
+  if (backward) {
+    CK(cudaMemsetAsync(h->dWSa, 0, sizeof(float) * N * C1 * Chv, h->stream));
+    CK(cudaMemsetAsync(h->dWSc, 0, sizeof(float) * N * C1 * Chv, h->stream));
+  }
+  return 0;
+}
+static int decoder_finish(sndvae_t* h, bool backward) {
   if (backward && h->spec) {     // fold the accumulated frequency-domain weight gradient into dw1 (once per step)
-    if (spec_finalize_wgrad(h->sp, h->G + p.e_w[1], h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral wgrad: %s", tc_last_error());
+    if (spec_finalize_wgrad(h->sp, h->G + h->pt.e_w[1], h->stream)) return fail(h, SNDVAE_E_CUDA, "spectral wgrad: %s", tc_last_error());
     h->launches++;
   }
   return 0;
@@ -877,17 +908,87 @@ static int fetch_losses(sndvae_t* h, float* losses_host) {
   return 0;
 }
 
+// views of the feed / noise / output structs for the graphs [g0, g0 + gn)
+static void slice_io(sndvae_t* h, long long g0, const sndvae_inputs* in, const sndvae_noise* nz, const sndvae_outputs* out,
+                     sndvae_inputs* vin, sndvae_noise* vnz, sndvae_outputs* vout) {
+  const sndvae_config& c = h->cfg; const long long N = h->N, S = h->S, F = h->F, D = h->D;
+#define OFF_(ptr, n) ((ptr) ? (ptr) + g0 * (n) : nullptr)
+  if (in) {
+    vin->features = OFF_(in->features, S * N * F); vin->spatial = OFF_(in->spatial, S * N * D); vin->adj = OFF_(in->adj, S * N * N);
+    vin->rel = OFF_(in->rel, S * N * N); vin->adj_truth = OFF_(in->adj_truth, N * N); vin->feature_truth = OFF_(in->feature_truth, N * F);
+    vin->spatial_truth = OFF_(in->spatial_truth, N * D); vin->rel_truth = OFF_(in->rel_truth, N * N);
+  }
+  if (nz) { vnz->eps_s = OFF_(nz->eps_s, c.s_latent_size); vnz->eps_sg = OFF_(nz->eps_sg, S * c.sg_latent_size); vnz->eps_g = OFF_(nz->eps_g, c.g_latent_size); }
+  if (out) {
+    vout->z_mean_s = OFF_(out->z_mean_s, c.s_latent_size); vout->z_std_s = OFF_(out->z_std_s, c.s_latent_size); vout->z_s = OFF_(out->z_s, c.s_latent_size);
+    vout->z_mean_g = OFF_(out->z_mean_g, c.g_latent_size); vout->z_std_g = OFF_(out->z_std_g, c.g_latent_size); vout->z_g = OFF_(out->z_g, c.g_latent_size);
+    vout->z_mean_sg = OFF_(out->z_mean_sg, S * c.sg_latent_size); vout->z_std_sg = OFF_(out->z_std_sg, S * c.sg_latent_size);
+    vout->z_sg = OFF_(out->z_sg, S * c.sg_latent_size);
+    vout->generated_adj = OFF_(out->generated_adj, N * N); vout->generated_adj_prob = OFF_(out->generated_adj_prob, N * N * 2);
+    vout->generated_spatial = OFF_(out->generated_spatial, N * D); vout->generated_node_feat = OFF_(out->generated_node_feat, N * F);
+  }
+#undef OFF_
+}
+
+// Host feeds of one piece -> device staging, on the copy stream (sndvae_train_step_host)
+struct HostFeeds { const sndvae_inputs* in; const sndvae_noise* nz; int64_t* gen_adj; };
+
+// The step.  Every graph's forward is independent of the rest of the batch (frozen-affine BN, SURVEY finding 3), so the
+// encoder + decoder + N^2 backward run piece by piece over contiguous graph ranges; with host feeds the H2D copy of piece k+1
+// and the D2H copy of piece k-1's generated_adj overlap piece k's kernels.  The node-level backward runs once at the end.
 static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host,
-               bool backward, long long global_batch) {
+               bool backward, long long global_batch, const HostFeeds* hf = nullptr) {
   int r = check_inputs(h, in, nz); if (r) return r;
-  const float gB = (float)(global_batch > 0 ? global_batch : h->B);
+  const sndvae_config& c = h->cfg;
+  const long long Bfull = h->B; const int N = h->N, S = h->S;
+  const float gB = (float)(global_batch > 0 ? global_batch : Bfull);
   CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * 8, h->stream));
   if (backward) CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
-  mark(h, "encoder");
-  if ((r = encoder_fwd(h, in))) return r;
-  if ((r = reparam_fwd(h, nz))) return r;
-  if ((r = copy_latents(h, out))) return r;
-  if ((r = decoder_fwd(h, in, out, backward, gB))) return r;
+  if ((r = decoder_prepare(h, backward))) return r;
+  const long long piece = hf ? (h->Bc < Bfull ? h->Bc : Bfull) : Bfull;
+  const long long npieces = (Bfull + piece - 1) / piece;
+  if (hf) {
+    while ((long long)h->pev.size() < 2 * npieces) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->pev.push_back(e); }
+    CK(cudaEventRecord(h->ev_start, h->stream));             // staging buffers are free once earlier work on the stream is done
+    CK(cudaStreamWaitEvent(h->cs, h->ev_start, 0));
+    // enqueue every piece's feeds now: the copy engine runs ahead of the kernels
+    for (long long pi = 0; pi < npieces; ++pi) {
+      const long long g0 = pi * piece, gn = (Bfull - g0 < piece ? Bfull - g0 : piece);
+      sndvae_inputs hs, ds; sndvae_noise hn, dn; memset(&hs, 0, sizeof hs); memset(&ds, 0, sizeof ds); memset(&hn, 0, sizeof hn); memset(&dn, 0, sizeof dn);
+      slice_io(h, g0, hf->in, hf->nz, nullptr, &hs, &hn, nullptr);
+      slice_io(h, g0, in, nz, nullptr, &ds, &dn, nullptr);
+#define H2D_(f, n) CK(cudaMemcpyAsync((void*)ds.f, hs.f, sizeof(float) * (size_t)(gn * (n)), cudaMemcpyHostToDevice, h->cs))
+      H2D_(features, (long long)S * N * h->F); H2D_(adj, (long long)S * N * N); H2D_(rel, (long long)S * N * N); H2D_(adj_truth, (long long)N * N);
+      H2D_(feature_truth, (long long)N * h->F); H2D_(spatial_truth, (long long)N * h->D);
+#undef H2D_
+      CK(cudaMemcpyAsync((void*)dn.eps_sg, hn.eps_sg, sizeof(float) * (size_t)(gn * S * c.sg_latent_size), cudaMemcpyHostToDevice, h->cs));
+      if (h->dis) {
+        CK(cudaMemcpyAsync((void*)dn.eps_s, hn.eps_s, sizeof(float) * (size_t)(gn * c.s_latent_size), cudaMemcpyHostToDevice, h->cs));
+        CK(cudaMemcpyAsync((void*)dn.eps_g, hn.eps_g, sizeof(float) * (size_t)(gn * c.g_latent_size), cudaMemcpyHostToDevice, h->cs));
+      }
+      CK(cudaEventRecord(h->pev[2 * pi], h->cs));
+    }
+  }
+  for (long long pi = 0; pi < npieces; ++pi) {
+    const long long g0 = pi * piece, gn = (Bfull - g0 < piece ? Bfull - g0 : piece);
+    sndvae_inputs vin; sndvae_noise vnz; sndvae_outputs vout; memset(&vin, 0, sizeof vin); memset(&vnz, 0, sizeof vnz); memset(&vout, 0, sizeof vout);
+    slice_io(h, g0, in, nz, out, &vin, &vnz, &vout);
+    if (hf) CK(cudaStreamWaitEvent(h->stream, h->pev[2 * pi], 0));
+    view_shift(h, g0); h->B = gn; h->BS = gn * S; h->Rn = gn * N;
+    mark(h, "encoder");
+    r = encoder_fwd(h, &vin);
+    if (!r) r = reparam_fwd(h, &vnz);
+    if (!r) r = copy_latents(h, out ? &vout : nullptr);
+    if (!r) r = decoder_fwd(h, &vin, out ? &vout : nullptr, backward, gB);
+    view_shift(h, -g0); h->B = Bfull; h->BS = Bfull * S; h->Rn = Bfull * N;
+    if (r) return r;
+    if (hf && hf->gen_adj && out && out->generated_adj) {
+      CK(cudaEventRecord(h->pev[2 * pi + 1], h->stream));
+      CK(cudaStreamWaitEvent(h->ds, h->pev[2 * pi + 1], 0));
+      CK(cudaMemcpyAsync(hf->gen_adj + g0 * N * N, out->generated_adj + g0 * N * N, sizeof(int64_t) * (size_t)(gn * N * N), cudaMemcpyDeviceToHost, h->ds));
+    }
+  }
+  if ((r = decoder_finish(h, backward))) return r;
   if (backward && (r = backward_rest(h, in, nz, gB))) return r;
   mark(h, "end");
   CK(cudaGetLastError());
@@ -923,7 +1024,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
-  h->hf_features = nullptr;
+  h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
   h->stt.used = 0; h->stt.on = getenv("SNDVAE_STAGE_TIMING") != nullptr;
   sndvae_config& c = h->cfg;
@@ -974,6 +1075,9 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (c.use_tensor_cores) {
     if ((r = tc_init(h->tc, h->N, h->Chv, h->B, h->stream))) return fail(h, SNDVAE_E_CUDA, "tc_init: %s", tc_last_error());
     if ((r = l0d_init(h->l0d, h->N, h->Chv, h->C1, h->stream))) return fail(h, SNDVAE_E_CUDA, "l0d_init: %s", tc_last_error());
+    { TcState& T = h->tc; const long long ni = (long long)h->N * T.l0a.CSi, no = (long long)h->N * T.l0a.CSo;
+      reg_shift(h, &T.ah, ni); reg_shift(h, &T.al, ni); reg_shift(h, &T.ch, ni); reg_shift(h, &T.cl, ni);
+      reg_shift(h, &T.dsh, no); reg_shift(h, &T.dsl, no); reg_shift(h, &T.drh, no); reg_shift(h, &T.drl, no); }
     if (h->spec && (r = spec_init(h->sp, h->N, 2LL * h->Bc * h->N, h->stream))) return fail(h, SNDVAE_E_CUDA, "spec_init: %s", tc_last_error());
     if (h->spec && (r = ytc_init(h->ytc, h->N, h->Chv, h->C1, h->stream))) return fail(h, SNDVAE_E_CUDA, "ytc_init: %s", tc_last_error());
   }
@@ -988,6 +1092,10 @@ int sndvae_destroy(sndvae_t* h) {
   if (h->spec) { spec_destroy(h->sp); ytc_destroy(h->ytc); }
   for (void* p : h->allocs) cudaFree(p);
   for (auto& e : h->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& e : h->pev) cudaEventDestroy(e);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->cs) cudaStreamDestroy(h->cs);
+  if (h->ds) cudaStreamDestroy(h->ds);
   if (h->pinned_loss) cudaFreeHost(h->pinned_loss);
   if (h->blas) cublasDestroy(h->blas);
   delete h;
@@ -1066,7 +1174,8 @@ int sndvae_generate(sndvae_t* h, const float* z_s, const float* z_sg, const floa
     CK(cudaMemcpyAsync(h->z_s, z_s, sizeof(float) * h->B * c.s_latent_size, cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(h->z_g, z_g, sizeof(float) * h->B * c.g_latent_size, cudaMemcpyDeviceToDevice, h->stream));
   }
-  int r = decoder_fwd(h, nullptr, out, false, (float)h->B); if (r) return r;
+  int r = decoder_prepare(h, false); if (r) return r;
+  r = decoder_fwd(h, nullptr, out, false, (float)h->B); if (r) return r;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return 0;
@@ -1082,20 +1191,19 @@ int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_no
     DA(h->hf_eps_s, B * c.s_latent_size); DA(h->hf_eps_sg, BS * c.sg_latent_size); DA(h->hf_eps_g, B * c.g_latent_size);
     DA(h->hf_gen_adj, B * N * N);
   }
-#define H2D(dst, src, n) CK(cudaMemcpyAsync(dst, src, sizeof(float) * (n), cudaMemcpyHostToDevice, h->stream))
-  H2D(h->hf_features, in->features, BS * N * h->F); H2D(h->hf_adj, in->adj, BS * N * N); H2D(h->hf_rel, in->rel, BS * N * N);
-  H2D(h->hf_adj_truth, in->adj_truth, B * N * N); H2D(h->hf_feature_truth, in->feature_truth, B * N * h->F);
-  H2D(h->hf_spatial_truth, in->spatial_truth, B * N * h->D);
-  H2D(h->hf_eps_sg, nz->eps_sg, BS * c.sg_latent_size);
-  if (h->dis) { H2D(h->hf_eps_s, nz->eps_s, B * c.s_latent_size); H2D(h->hf_eps_g, nz->eps_g, B * c.g_latent_size); }
-#undef H2D
+  if (!h->cs) {
+    CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->ds, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+  }
   sndvae_inputs din; memset(&din, 0, sizeof din);
   din.features = h->hf_features; din.adj = h->hf_adj; din.rel = h->hf_rel; din.adj_truth = h->hf_adj_truth;
   din.feature_truth = h->hf_feature_truth; din.spatial_truth = h->hf_spatial_truth;
   sndvae_noise dnz; dnz.eps_s = h->hf_eps_s; dnz.eps_sg = h->hf_eps_sg; dnz.eps_g = h->hf_eps_g;
   sndvae_outputs o; memset(&o, 0, sizeof o); o.generated_adj = gen_adj_host ? (int64_t*)h->hf_gen_adj : nullptr;
-  r = sndvae_train_step(h, &din, &dnz, &o, losses_host); if (r) return r;
-  if (gen_adj_host) { CK(cudaMemcpyAsync(gen_adj_host, h->hf_gen_adj, sizeof(int64_t) * B * N * N, cudaMemcpyDeviceToHost, h->stream)); }
+  HostFeeds hfd; hfd.in = in; hfd.nz = nz; hfd.gen_adj = gen_adj_host;
+  r = run(h, &din, &dnz, &o, losses_host, true, 0, &hfd); if (r) return r;
+  r = sndvae_apply_adam(h); if (r) return r;
+  CK(cudaStreamSynchronize(h->ds));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

@@ -87,9 +87,9 @@ struct LineSrc {                      // fp32 line in global memory, two real ch
   }
 };
 struct LineDst {                      // inverse transform tail: (re, im) swapped back, scaled, first N positions only
-  float* base; int C; int N; float scale;
+  float* base; long long pstride; int N; float scale;
   __device__ __forceinline__ void st(int pos, int cp, float2 v) const {
-    if (pos < N) *reinterpret_cast<float2*>(base + (long long)pos * C + 2 * cp) = make_float2(v.y * scale, v.x * scale);
+    if (pos < N) *reinterpret_cast<float2*>(base + (long long)pos * pstride + 2 * cp) = make_float2(v.y * scale, v.x * scale);
   }
 };
 
@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_fwd_k(FftFwdAr
 struct FftInvArgs {
   const float* in; long long RA;
   float* out; long long lines;
+  long long lines0; float* out1;     // out1 != NULL: lines >= lines0 are (b, j) columns written TRANSPOSED into out1[b][pos][j][C]
+                                     // (position stride N C), so that both directions share the [b, i, j, C] layout
   int N, C, G;
   const float2* tw;
   FftPlan pl;
@@ -231,7 +233,11 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvAr
         if (!selfc) buf0[(L - f) * g + cp] = make_float2(a.y - b.x, a.x + b.y);
       }
       SmemIO cur; cur.p = buf0; cur.g = g; SmemIO oth; oth.p = buf1; oth.g = g;
-      LineDst dst; dst.base = A.out + line * A.N * A.C + 2 * cp0; dst.C = A.C; dst.N = A.N; dst.scale = scale;
+      LineDst dst; dst.base = A.out + line * A.N * A.C + 2 * cp0; dst.pstride = A.C; dst.N = A.N; dst.scale = scale;
+      if (A.out1 && line >= A.lines0) {
+        const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
+        dst.base = A.out1 + (b * A.N * A.N + j) * A.C + 2 * cp0; dst.pstride = (long long)A.N * A.C;
+      }
       int Ns = 1;
       for (int ps = 0; ps < A.pl.npass; ++ps) {
         __syncthreads();
@@ -405,7 +411,11 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
     }
     __syncthreads();
     SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
-    LineDst dst; dst.base = A.out + line * A.N * C; dst.C = C; dst.N = A.N; dst.scale = scale;
+    LineDst dst; dst.base = A.out + line * A.N * C; dst.pstride = C; dst.N = A.N; dst.scale = scale;
+    if (A.out1 && line >= A.lines0) {
+      const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
+      dst.base = A.out1 + (b * A.N * A.N + j) * C; dst.pstride = (long long)A.N * C;
+    }
     if (!ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
     fft_pass_ct<R0, 1, L, G, NT>(a, b, tw);
     __syncthreads();
@@ -916,8 +926,8 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
   spec_fft_fwd_k<<<grid, s.fft_threads_generic, spec_fft_smem(s.pl.L, G), st>>>(a);
   return tc_check_launch("spec_fft_fwd_k");
 }
-static int spec_fft_inv(SpecState& s, const float* in, float* out, long long lines, int C, int G, cudaStream_t st) {
-  FftInvArgs a; a.in = in; a.RA = s.RA; a.out = out; a.lines = lines; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, long long lines0, long long lines, int C, int G, cudaStream_t st) {
+  FftInvArgs a; a.in = in; a.RA = s.RA; a.out = out; a.out1 = out1; a.lines0 = lines0; a.lines = lines; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
   int r = 1;
   if (!s.generic_only) {
     if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_inv_fast<6, 8, 8, 25, 800, 1, true>(s, a, st) : spec_launch_inv_fast<6, 8, 8, 25, 400, 1, true>(s, a, st);
@@ -944,12 +954,14 @@ static int spec_forward(SpecState& s, const float* E1, const float* E1T, const f
   const unsigned grid = (unsigned)(g.items < s.grid_sms ? g.items : s.grid_sms);
   spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES><<<grid, 192, spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES), st>>>(ah, al, s.mBfh, s.mBfl, g);
   if (tc_check_launch("spec_gemm_k(fwd)")) return -1;
-  return spec_fft_inv(s, s.Oc, O12, lines, s.C2, s.G2, st);
+  // both directions land in the [b, i, j, C2] layout: O12 plane 0 = row products, plane 1 = column products
+  return spec_fft_inv(s, s.Oc, O12, O12 + rows * s.N * s.C2, rows, lines, s.C2, s.G2, st);
 }
-// backward: dY12[2 rows][N C1] from dO [2 rows][N C2] (fp32, both layouts), and P += Y^^T dO^
+// backward: dY12[2][rows][N C1] (both planes in the [b, i, j, C1] layout) from dO [rows][N C2] (fp32, one layout: the
+// column lines are read strided), and P += Y^^T dO^
 static int spec_backward(SpecState& s, const float* dO, long long rows, float* dY12, cudaStream_t st) {
   const long long lines = 2 * rows; const int F = s.pl.F;
-  if (spec_fft_fwd(s, dO, nullptr, lines, lines, 0, nullptr, nullptr, nullptr, nullptr, nullptr, s.Dh, s.Dl, SP_KA2, s.C2, s.G2, st)) return -1;
+  if (spec_fft_fwd(s, dO, nullptr, rows, lines, 1, nullptr, nullptr, nullptr, nullptr, nullptr, s.Dh, s.Dl, SP_KA2, s.C2, s.G2, st)) return -1;
   CUtensorMap dh, dl;
   if (spec_enc3(&dh, s.Dh, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128) ||
       spec_enc3(&dl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128)) return -1;
@@ -957,7 +969,7 @@ static int spec_backward(SpecState& s, const float* dO, long long rows, float* d
   const unsigned grid = (unsigned)(g.items < s.grid_sms ? g.items : s.grid_sms);
   spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES><<<grid, 192, spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES), st>>>(dh, dl, s.mBdh, s.mBdl, g);
   if (tc_check_launch("spec_gemm_k(dgrad)")) return -1;
-  if (spec_fft_inv(s, s.dYc, dY12, lines, s.C1, s.G1, st)) return -1;
+  if (spec_fft_inv(s, s.dYc, dY12, dY12 + rows * s.N * s.C1, rows, lines, s.C1, s.G1, st)) return -1;
   // wgrad: MN-major views of the same planes, 32 lines per K chunk
   CUtensorMap ah, al, bh, bl;
   if (spec_enc3(&ah, s.Ah, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, SP_WKC) ||
