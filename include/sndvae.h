@@ -57,7 +57,8 @@ typedef struct sndvae_config {
   int32_t batch_size;        /* B graphs per step = FLAGS.batch_size  main.py:213 */
   int32_t chunk_graphs;      /* graphs per device micro-batch for the N^2 stages (0 = auto) */
   int32_t edge_capacity;     /* per-sample nnz capacity of `adj` (0 = 4N) */
-  int32_t use_tensor_cores;  /* 1: tcgen05 bf16x3 e2e GEMMs; 0: fp32 SIMT reference kernels */
+  int32_t use_tensor_cores;  /* e2e layer 1 (layers.py:431-450): 2 (default): spectral -- Stockham FFT lines + per-frequency tcgen05
+                              * bf16x3 channel-mix GEMMs; 1: block-Toeplitz tcgen05 bf16x3 GEMMs; 0: fp32 SIMT reference kernels */
   float   learning_rate;     /* FLAGS.learning_rate                   main.py:211 */
   float   beta;              /* KL weight                             main.py:515 */
   float   adam_beta1, adam_beta2, adam_eps;   /* tf.train.AdamOptimizer defaults */

@@ -1013,7 +1013,7 @@ int sndvae_default_config(sndvae_config* c) {
   c->sg_hidden_size = 100; c->sg_latent_size = 100;
   c->s_d_channel[0] = 50; c->s_d_channel[1] = 20; c->s_d_channel[2] = 10;
   c->n_d_channel[0] = 50; c->n_d_channel[1] = 20; c->e_d_hidden[0] = 50; c->e_d_hidden[1] = 20;
-  c->batch_size = 10; c->chunk_graphs = 0; c->edge_capacity = 0; c->use_tensor_cores = 1;
+  c->batch_size = 10; c->chunk_graphs = 0; c->edge_capacity = 0; c->use_tensor_cores = 2;
   c->learning_rate = 0.0008f; c->beta = 1.f; c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f; c->adam_eps = 1e-8f;
   return 0;
 }
