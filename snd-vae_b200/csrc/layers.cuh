@@ -107,6 +107,20 @@ __global__ void im2col_k(const float* __restrict__ X, float* __restrict__ col, l
   col[idx] = (nn >= 0 && nn < N) ? X[(r + t - pb) * Ci + ci] : 0.f;
 }
 
+// transpose of im2col_k: dX[r, ci] = sum_t dcol[r - t + pb, t, ci] over the taps whose source row is in the same graph
+__global__ void col2im_k(const float* __restrict__ dcol, float* __restrict__ dX, long long rows, int N, int Ci, int ktaps) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Ci) return;
+  long long r = idx / Ci; int ci = (int)(idx - r * Ci);
+  const int n = (int)(r % N), pb = (ktaps - 1) / 2, W = ktaps * Ci;
+  float acc = 0.f;
+  for (int t = 0; t < ktaps; ++t) {
+    const int nn = n - t + pb;
+    if (nn >= 0 && nn < N) acc += dcol[(r - t + pb) * W + t * Ci + ci];
+  }
+  dX[idx] = acc;
+}
+
 // db[c] += sum_r dY[r, c];  grid = (row slabs, column tiles of blockDim.x)
 __global__ void colsum_k(const float* __restrict__ dY, int ldy, float* __restrict__ db, long long rows, int C) {
   long long r0 = (long long)blockIdx.x * XTDY_SLAB;

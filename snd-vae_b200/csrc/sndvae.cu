@@ -365,15 +365,22 @@ static void bn_bwd(sndvae_t* h, const float* dout, int ldd, const float* in, int
   LAUNCH(bn_act_bwd_k, cdiv(rows, BN_SLAB), 64, 0, dout, ldd, in, ldi, g >= 0 ? h->P + g : nullptr, b >= 0 ? h->P + b : nullptr,
          din, ldn, g >= 0 ? h->G + g : nullptr, b >= 0 ? h->G + b : nullptr, rows, C, act, order);
 }
+// conv1d k5 SAME over the node axis (model.py:122,191,216) as im2col + one tall library GEMM
 static void conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, long long rows, int Ci, int Co) {
-  LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS);
+  if (rows * Ci < 4096) { LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS); return; }
+  LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
+  LEW(bias_rows_k, rows * Co, out, h->P + b, rows, Co);
+  gemm_rm(h, false, false, (int)rows, Co, KS * Ci, 1.f, h->colbuf, KS * Ci, h->P + k, Co, 1.f, out, Co);
 }
 // weight/bias grads + optional input grad of a conv1d layer
 static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
   LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
   CKB(gemm_rm(h, true, false, KS * Ci, Co, (int)rows, 1.f, h->colbuf, KS * Ci, dout, Co, 1.f, h->G + k, Co));
   LAUNCH(colsum_k, dim3(cdiv(rows, XTDY_SLAB), cdiv(Co, 128)), 128, 0, dout, Co, h->G + b, rows, Co);
-  if (din) LEW(conv1d_bwd_in_k, rows * Ci, dout, h->P + k, din, rows, h->N, Ci, Co, KS);
+  if (din) {      // dcol = dout . K^T (re-using the im2col buffer), then the transposed gather
+    CKB(gemm_rm(h, false, true, (int)rows, KS * Ci, Co, 1.f, dout, Co, h->P + k, Co, 0.f, h->colbuf, KS * Ci));
+    LEW(col2im_k, rows * Ci, h->colbuf, din, rows, h->N, Ci, KS);
+  }
   return 0;
 }
 // dM[K-1, hcols] += coef[:, :K-1]^T grad;  db[hcols] += coef[:, K-1]^T grad   (SGC parameter gradients)
@@ -1066,7 +1073,9 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (prop.major < 10) return fail(h, SNDVAE_E_CUDA, "device sm_%d%d is not sm_100: this library is built for B200 only", prop.major, prop.minor);
   if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(h, SNDVAE_E_CUDA, "cublasCreate failed");
   cublasSetStream(h->blas, h->stream);
-  cublasSetMathMode(h->blas, CUBLAS_PEDANTIC_MATH);       // plain fp32 library GEMMs, no TF32
+  // plain library GEMMs in fp32-grade arithmetic: BF16x9 emulation on the tensor cores (3 x 3 split products, fp32 accumulate; no
+  // TF32 down-conversion) unless SNDVAE_CUBLAS_PEDANTIC=1 forces the fp32 SIMT kernels
+  cublasSetMathMode(h->blas, getenv("SNDVAE_CUBLAS_PEDANTIC") ? CUBLAS_PEDANTIC_MATH : CUBLAS_FP32_EMULATED_BF16X9_MATH);
   int r = alloc_buffers(h); if (r) return r;
   if (cudaMallocHost((void**)&h->pinned_loss, 64) != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMallocHost failed");
   h->b1p = c.adam_beta1; h->b2p = c.adam_beta2;
