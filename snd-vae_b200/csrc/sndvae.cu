@@ -1073,9 +1073,9 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (prop.major < 10) return fail(h, SNDVAE_E_CUDA, "device sm_%d%d is not sm_100: this library is built for B200 only", prop.major, prop.minor);
   if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(h, SNDVAE_E_CUDA, "cublasCreate failed");
   cublasSetStream(h->blas, h->stream);
-  // plain library GEMMs in fp32-grade arithmetic: BF16x9 emulation on the tensor cores (3 x 3 split products, fp32 accumulate; no
-  // TF32 down-conversion) unless SNDVAE_CUBLAS_PEDANTIC=1 forces the fp32 SIMT kernels
-  cublasSetMathMode(h->blas, getenv("SNDVAE_CUBLAS_PEDANTIC") ? CUBLAS_PEDANTIC_MATH : CUBLAS_FP32_EMULATED_BF16X9_MATH);
+  // plain fp32 library GEMMs, no TF32.  (SNDVAE_CUBLAS_BF16X9=1 asks for cuBLAS's BF16x9 fp32 emulation instead; the cuBLAS 12.8
+  // that PyTorch loads into the process ignores it -- measured: no change in kernels or time.)
+  cublasSetMathMode(h->blas, getenv("SNDVAE_CUBLAS_BF16X9") ? CUBLAS_FP32_EMULATED_BF16X9_MATH : CUBLAS_PEDANTIC_MATH);
   int r = alloc_buffers(h); if (r) return r;
   if (cudaMallocHost((void**)&h->pinned_loss, 64) != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMallocHost failed");
   h->b1p = c.adam_beta1; h->b2p = c.adam_beta2;
