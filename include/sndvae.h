@@ -62,7 +62,20 @@ typedef struct sndvae_config {
   float   learning_rate;     /* FLAGS.learning_rate                   main.py:211 */
   float   beta;              /* KL weight                             main.py:515 */
   float   adam_beta1, adam_beta2, adam_eps;   /* tf.train.AdamOptimizer defaults */
+  /* loss branch of OptimizerVAE (optimizer.py:160-190; disentangled model only):
+   *   SNDVAE_LOSS_ELBO      'disentangled' / 'base':  mse + beta (kl_sg + kl_s + kl_g)
+   *   SNDVAE_LOSS_CAPACITY  'disentangled_C':         mse + gamma relu(kl_sg - C) + kl_s + kl_g,
+   *                          C = clip(C_max C_step / C_stop_iter (global_iter // C_step), 0, C_max)   (optimizer.py:170-172)
+   *   SNDVAE_LOSS_DIP       'NED-VAE-IP':             mse + kl + beta sum_latents DIP(z_mean, lambda_od, lambda_d)  (optimizer.py:7-21,183)
+   * 'beta-TCVAE' (O(B^2 L) pairwise densities) is not built. */
+  int32_t loss_variant;
+  float   gamma, C_max, C_stop_iter, C_step;  /* main.py:95-98 */
+  float   dip_lambda_od, dip_lambda_d;        /* 10, 100 (optimizer.py:183) */
 } sndvae_config;
+
+#define SNDVAE_LOSS_ELBO      0
+#define SNDVAE_LOSS_CAPACITY  1
+#define SNDVAE_LOSS_DIP       2
 
 /* The eight feeds of construct_feed_dict_train (preprocessing.py:32-42) with
  * the static shapes of main.py:253-264.  fp32, C-contiguous.  `spatial` and
@@ -174,6 +187,9 @@ int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in_host, const sndv
 
 /* Number of library kernels launched since create (bench.py's gpu_launches). */
 int64_t sndvae_launch_count(const sndvae_t* h);
+
+/* The `global_iter` placeholder (main.py:262,329): only the 'disentangled_C' loss reads it (optimizer.py:172). */
+int sndvae_set_global_iter(sndvae_t* h, int64_t global_iter);
 
 /* Average duration (ms) and launch count of the e2e layer-1 GEMM launches
  * (forward + dgrad + wgrad) since the last reset, measured with CUDA events on

@@ -74,6 +74,15 @@ class Config:
     learning_rate: float = 0.0008                # main.py:211
     beta: float = 1.0                            # main.py:515
     num_edge_feature: int = 2                    # model_joint.py:171 (undefined flag)
+    # loss variants of optimizer.py:166-190 (FLAGS.model_type selects the branch; the network is model.py's in all of them)
+    loss_variant: str = "elbo"                   # "elbo" | "disentangled_C" | "NED-VAE-IP"
+    gamma: float = 100.0                         # main.py:97
+    C_max: float = 100.0                         # main.py:95
+    C_stop_iter: float = 1e2                     # main.py:96
+    C_step: float = 20.0                         # main.py:98
+    global_iter: int = 0                         # placeholder fed per epoch (main.py:329)
+    dip_lambda_od: float = 10.0                  # DIP(enc_mean, 10, 100), optimizer.py:183
+    dip_lambda_d: float = 100.0
 
     @property
     def N(self): return self.num_nodes
@@ -509,12 +518,32 @@ def losses(P, inp, enc, dec, cfg: Config):
     if cfg.model_type != "base":
         L["kl_s"] = kl(enc["z_mean_s"], enc["z_std_s"])
         L["kl_g"] = kl(enc["z_mean_g"], enc["z_std_g"])
-        L["cost"] = adj_cost + node_cost + spatial_cost + cfg.beta * (kl_sg + L["kl_s"] + L["kl_g"])
+        mse = adj_cost + node_cost + spatial_cost
+        if cfg.loss_variant == "disentangled_C":
+            # optimizer.py:166-174: capacity-controlled joint KL; C follows global_iter in steps of C_step
+            C = min(max(cfg.C_max * cfg.C_step / cfg.C_stop_iter * (cfg.global_iter // int(cfg.C_step)), 0.0), cfg.C_max)
+            L["C"] = C
+            L["cost"] = mse + cfg.gamma * torch.relu(kl_sg - C) + L["kl_s"] + L["kl_g"]
+        elif cfg.loss_variant == "NED-VAE-IP":
+            # optimizer.py:176-183: ELBO (KL weight 1) + beta * DIP-VAE-I regulariser on the three posterior means
+            L["dip"] = sum(dip_regulariser(enc[k], cfg.dip_lambda_od, cfg.dip_lambda_d) for k in ("z_mean_s", "z_mean_g", "z_mean_sg"))
+            L["cost"] = mse + (kl_sg + L["kl_s"] + L["kl_g"]) + cfg.beta * L["dip"]
+        else:
+            L["cost"] = mse + cfg.beta * (kl_sg + L["kl_s"] + L["kl_g"])
         L["overall_loss"] = [L["cost"], spatial_cost, adj_cost, node_cost, L["kl_g"], L["kl_s"], kl_sg]
     else:
         L["cost"] = adj_cost + node_cost + spatial_cost + cfg.beta * kl_sg
         L["overall_loss"] = [L["cost"], spatial_cost, adj_cost, node_cost, kl_sg]
     return L
+
+
+def dip_regulariser(mu, lambda_od, lambda_d):
+    """DIP() of optimizer.py:7-21: covariance of the posterior means over the batch, pushed towards the identity."""
+    m = mu.mean(dim=0)
+    cov = (mu.unsqueeze(1) * mu.unsqueeze(2)).mean(dim=0) - m.unsqueeze(0) * m.unsqueeze(1)
+    d = torch.diagonal(cov)
+    off = cov - torch.diag(d)
+    return lambda_d * ((d - 1) ** 2).sum() + lambda_od * (off ** 2).sum()
 
 
 def forward(P, inp, noise, cfg: Config, mode="factored"):

@@ -26,7 +26,12 @@ class Config(C.Structure):
         ("s_d_channel", I32 * 3), ("n_d_channel", I32 * 2), ("e_d_hidden", I32 * 2),
         ("batch_size", I32), ("chunk_graphs", I32), ("edge_capacity", I32), ("use_tensor_cores", I32),
         ("learning_rate", F32), ("beta", F32), ("adam_beta1", F32), ("adam_beta2", F32), ("adam_eps", F32),
+        ("loss_variant", I32), ("gamma", F32), ("C_max", F32), ("C_stop_iter", F32), ("C_step", F32),
+        ("dip_lambda_od", F32), ("dip_lambda_d", F32),
     ]
+
+
+LOSS_VARIANTS = {"disentangled": 0, "base": 0, "disentangled_C": 1, "NED-VAE-IP": 2}
 
 
 class Inputs(C.Structure):
@@ -71,6 +76,7 @@ SYMBOLS = {
     "sndvae_train_step": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.POINTER(Outputs), C.c_void_p]),
     "sndvae_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Outputs)]),
     "sndvae_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.c_void_p, C.c_void_p]),
+    "sndvae_set_global_iter": (C.c_int, [C.c_void_p, I64]),
     "sndvae_launch_count": (I64, [C.c_void_p]),
     "sndvae_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(C.c_double)]),
     "sndvae_threshold_logits": (C.c_int, [C.c_void_p, C.c_void_p, I64, C.c_void_p]),

@@ -254,12 +254,16 @@ __global__ void reparam_kl_k(const float* __restrict__ mu, const float* __restri
 
 // dmu = dz + w*mu;  dls = dz*eps*exp(ls) + w*(exp(2 ls) - 1),  w = beta/(rows_global*L)
 // dz_rep > 1: dz row index = row / dz_rep and scaled by 1/dz_rep (the S-mean, model.py:180)
+// gate_sum != NULL: the KL weight is w only while the batch-mean KL  gate_sum[0] * gate_inv  exceeds gate_C (the relu of the
+// 'disentangled_C' capacity loss, optimizer.py:173), otherwise 0
 __global__ void reparam_kl_bwd_k(const float* __restrict__ mu, const float* __restrict__ ls,
                                  const float* __restrict__ eps, const float* __restrict__ dz,
                                  float* __restrict__ dmu, float* __restrict__ dls,
-                                 long long rows, int L, int dz_rep, float w) {
+                                 long long rows, int L, int dz_rep, float w,
+                                 const float* __restrict__ gate_sum = nullptr, float gate_inv = 0.f, float gate_C = 0.f) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * L) return;
+  if (gate_sum && !(gate_sum[0] * gate_inv > gate_C)) w = 0.f;
   long long r = idx / L; int c = (int)(idx - r * L);
   float g = dz[(r / dz_rep) * L + c] / (float)dz_rep;
   float m = mu[idx], l = ls[idx];
@@ -302,4 +306,27 @@ __global__ void sigmoid_mse_k(const float* __restrict__ pre, const float* __rest
 __global__ void add_inplace_k(float* __restrict__ a, const float* __restrict__ b, long long n) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) a[idx] += b[idx];
+}
+
+// ---- DIP-VAE-I regulariser on a batch of posterior means (optimizer.py:7-21) ---------------------------------------
+// cov = E[mu mu^T] - m m^T (E over the rows);  reg = ld sum_i (cov_ii - 1)^2 + lod sum_{i != j} cov_ij^2
+// in : S = mu^T mu [L, L] (unnormalised), msum [L] column sums.  out: G = d reg / d cov [L, L], m [L], reg_sum += reg
+__global__ void dip_cov_k(const float* __restrict__ S, const float* __restrict__ msum, float* __restrict__ G, float* __restrict__ m,
+                          float* __restrict__ reg_sum, int L, float inv_rows, float lod, float ld) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float r = 0.f;
+  if (idx < L * L) {
+    const int i = idx / L, j = idx - i * L;
+    const float mi = msum[i] * inv_rows, mj = msum[j] * inv_rows;
+    const float cov = S[idx] * inv_rows - mi * mj;
+    if (i == j) { G[idx] = 2.f * ld * (cov - 1.f); r = ld * (cov - 1.f) * (cov - 1.f); m[i] = mi; }
+    else { G[idx] = 2.f * lod * cov; r = lod * cov * cov; }
+  }
+  r = warp_sum(r);
+  if ((threadIdx.x & 31) == 0 && r != 0.f) atomicAdd(reg_sum, r);
+}
+// dmu[r, :] -= alpha * v   (the mean term of d reg / d mu = (2 / rows) (mu - m) G, with v = m G)
+__global__ void sub_row_k(float* __restrict__ dmu, const float* __restrict__ v, long long rows, int L, float alpha) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < rows * L) dmu[idx] -= alpha * v[idx % L];
 }

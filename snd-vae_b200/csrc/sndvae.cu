@@ -67,7 +67,9 @@ struct sndvae_handle {
   __nv_bfloat16 *Yhi, *Ylo, *dOhi, *dOlo;
   TcState tc; L0Dense l0d;
   SpecState sp; YtcState ytc; int spec;              // use_tensor_cores == 2: e2e layer 1 in the frequency domain (spectral.cuh)
-  float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg
+  float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg, dip
+  long long global_iter;               // main.py:329 (only the capacity loss reads it)
+  float *dipS, *dipG[3], *dipm[3], *dipv;   // DIP regulariser: mu^T mu scratch, d reg / d cov, batch means, m G
   int* errflag;
   float* pinned_loss;
   // host-feed staging (sndvae_train_step_host)
@@ -327,6 +329,12 @@ static int alloc_buffers(sndvae_t* h) {
     h->Yhi = h->Ylo = h->dOhi = h->dOlo = nullptr;
   }
   DA(h->loss, 8); DA(h->errflag, 1);
+  if (c.loss_variant == SNDVAE_LOSS_DIP) {
+    const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
+    int Lm = 0; for (int i = 0; i < 3; ++i) if (Ls[i] > Lm) Lm = Ls[i];
+    DA(h->dipS, (long long)Lm * Lm); DA(h->dipv, Lm);
+    for (int i = 0; i < 3; ++i) { DA(h->dipG[i], (long long)Ls[i] * Ls[i]); DA(h->dipm[i], Ls[i]); }
+  }
   return 0;
 }
 
@@ -723,6 +731,38 @@ static int decoder_finish(sndvae_t* h, bool backward) {
   return 0;
 }
 
+// ---- loss variants on the latents (optimizer.py:166-183) -------------------------------------------------------------
+static float capacity_C(const sndvae_t* h) {     // optimizer.py:172
+  const sndvae_config& c = h->cfg;
+  const long long step = (long long)c.C_step > 0 ? (long long)c.C_step : 1;
+  float C = c.C_max * c.C_step / c.C_stop_iter * (float)(h->global_iter / step);
+  return C < 0.f ? 0.f : (C > c.C_max ? c.C_max : C);
+}
+// DIP forward for the three posterior means: batch covariance -> regulariser value (loss[6]) and d reg / d cov (kept for backward)
+static int dip_forward(sndvae_t* h) {
+  const sndvae_config& c = h->cfg;
+  const float* mus[3] = {h->mu_s, h->mu_g, h->mu_sg};
+  const long long rows[3] = {h->B, h->B, h->BS};
+  const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
+  for (int i = 0; i < 3; ++i) {
+    const int L = Ls[i];
+    CK(cudaMemsetAsync(h->dipv, 0, sizeof(float) * L, h->stream));
+    LAUNCH(colsum_k, dim3(cdiv(rows[i], XTDY_SLAB), cdiv(L, 128)), 128, 0, mus[i], L, h->dipv, rows[i], L);
+    CKB(gemm_rm(h, true, false, L, L, (int)rows[i], 1.f, mus[i], L, mus[i], L, 0.f, h->dipS, L));
+    LAUNCH(dip_cov_k, cdiv((long long)L * L, 256), 256, 0, h->dipS, h->dipv, h->dipG[i], h->dipm[i], h->loss + 6, L, 1.f / (float)rows[i],
+           c.dip_lambda_od, c.dip_lambda_d);
+  }
+  return 0;
+}
+// dmu += beta (2 / rows) (mu - m) G
+static int dip_backward(sndvae_t* h, int which, const float* mu, float* dmu, long long rows, int L) {
+  const float alpha = h->cfg.beta * 2.f / (float)rows;
+  CKB(gemm_rm(h, false, false, (int)rows, L, L, alpha, mu, L, h->dipG[which], L, 1.f, dmu, L));
+  CKB(gemm_rm(h, false, false, 1, L, L, 1.f, h->dipm[which], L, h->dipG[which], L, 0.f, h->dipv, L));
+  LEW(sub_row_k, rows * L, dmu, h->dipv, rows, L, alpha);
+  return 0;
+}
+
 // backward of everything except the per-chunk N^2 stages (already done inside decoder_fwd)
 static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, float gB) {
   const sndvae_config& c = h->cfg; const PT& p = h->pt;
@@ -793,12 +833,16 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   if ((r = lin_bwd(h, h->zbar, p.d_sg_lin1, h->dn_sg, h->dzbar, B, c.sg_latent_size, N * H))) return r;
   mark(h, "enc_bwd_small");
   // ---- reparameterisation + KL, heads, encoders ----
-  const float beta = c.beta;
+  // KL weights of the loss branch: ELBO beta each; capacity loss 1, 1, gamma * 1[kl_sg > C]; DIP 1 each (optimizer.py:164,173,182)
+  const int lv = c.loss_variant;
+  const float beta = lv == SNDVAE_LOSS_ELBO ? c.beta : 1.f;
+  const float beta_sg = lv == SNDVAE_LOSS_CAPACITY ? c.gamma : beta;
   if (h->dis) {
     // graph head
     int L = c.g_latent_size, Hh = c.g_hidden_size;
     int g0 = c.g_conv_hidden[0], g1c = c.g_conv_hidden[1];
     LEW(reparam_kl_bwd_k, B * L, h->mu_g, h->ls_g, nz->eps_g, h->dz_g, h->dmu, h->dls, B, L, 1, beta / (gB * L));
+    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 1, h->mu_g, h->dmu, B, L))) return r;
     if ((r = lin_bwd(h, h->hg, p.g_lin[1], h->dmu, h->dh, B, Hh, L))) return r;
     if ((r = lin_bwd(h, h->hg, p.g_lin[2], h->dls, h->gC, B, Hh, L))) return r;
     LEW(add_inplace_k, B * Hh, h->dh, h->gC, B * Hh);
@@ -817,6 +861,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     L = c.s_latent_size; Hh = c.s_hidden_size;
     const int* ec = c.s_channel;
     LEW(reparam_kl_bwd_k, B * L, h->mu_s, h->ls_s, nz->eps_s, h->dz_s, h->dmu, h->dls, B, L, 1, beta / (gB * L));
+    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 0, h->mu_s, h->dmu, B, L))) return r;
     if ((r = lin_bwd(h, h->hs, p.s_lin[1], h->dmu, h->dh, B, Hh, L))) return r;
     if ((r = lin_bwd(h, h->hs, p.s_lin[2], h->dls, h->gC, B, Hh, L))) return r;
     LEW(add_inplace_k, B * Hh, h->dh, h->gC, B * Hh);
@@ -834,7 +879,11 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   {
     int L = c.sg_latent_size, Hh = c.sg_hidden_size;
     const int h02 = c.sg_conv_hidden[0][2], h12 = c.sg_conv_hidden[1][2];
-    LEW(reparam_kl_bwd_k, BS * L, h->mu_sg, h->ls_sg, nz->eps_sg, h->dzbar, h->dmu, h->dls, BS, L, S, beta / (gB * S * L));
+    if (lv == SNDVAE_LOSS_CAPACITY)
+      LEW(reparam_kl_bwd_k, BS * L, h->mu_sg, h->ls_sg, nz->eps_sg, h->dzbar, h->dmu, h->dls, BS, L, S, beta_sg / (gB * S * L), h->loss + 5,
+          1.f / ((float)BS * L), capacity_C(h));
+    else LEW(reparam_kl_bwd_k, BS * L, h->mu_sg, h->ls_sg, nz->eps_sg, h->dzbar, h->dmu, h->dls, BS, L, S, beta_sg / (gB * S * L));
+    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 2, h->mu_sg, h->dmu, BS, L))) return r;
     if ((r = lin_bwd(h, h->hsg, p.sg_lin[1], h->dmu, h->dh, BS, Hh, L))) return r;
     float* tmp = h->dmu;   // reuse: dmu is consumed
     if ((r = lin_bwd(h, h->hsg, p.sg_lin[2], h->dls, tmp, BS, Hh, L))) return r;
@@ -906,7 +955,9 @@ static int fetch_losses(sndvae_t* h, float* losses_host) {
   float kl_sg = (float)(L[5] / ((double)h->BS * c.sg_latent_size));
   if (h->dis) {
     float kl_s = (float)(L[3] / (B * c.s_latent_size)), kl_g = (float)(L[4] / (B * c.g_latent_size));
-    losses_host[0] = adj + node + sp + c.beta * (kl_sg + kl_s + kl_g);
+    if (c.loss_variant == SNDVAE_LOSS_CAPACITY) { const float ex = kl_sg - capacity_C(h); losses_host[0] = adj + node + sp + c.gamma * (ex > 0.f ? ex : 0.f) + kl_s + kl_g; }
+    else if (c.loss_variant == SNDVAE_LOSS_DIP) losses_host[0] = adj + node + sp + (kl_sg + kl_s + kl_g) + c.beta * L[6];
+    else losses_host[0] = adj + node + sp + c.beta * (kl_sg + kl_s + kl_g);
     losses_host[1] = sp; losses_host[2] = adj; losses_host[3] = node; losses_host[4] = kl_g; losses_host[5] = kl_s; losses_host[6] = kl_sg;
   } else {
     losses_host[0] = adj + node + sp + c.beta * kl_sg;
@@ -996,6 +1047,7 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
     }
   }
   if ((r = decoder_finish(h, backward))) return r;
+  if (c.loss_variant == SNDVAE_LOSS_DIP && (r = dip_forward(h))) return r;      // needs every piece's posterior means
   if (backward && (r = backward_rest(h, in, nz, gB))) return r;
   mark(h, "end");
   CK(cudaGetLastError());
@@ -1022,6 +1074,8 @@ int sndvae_default_config(sndvae_config* c) {
   c->n_d_channel[0] = 50; c->n_d_channel[1] = 20; c->e_d_hidden[0] = 50; c->e_d_hidden[1] = 20;
   c->batch_size = 10; c->chunk_graphs = 0; c->edge_capacity = 0; c->use_tensor_cores = 2;
   c->learning_rate = 0.0008f; c->beta = 1.f; c->adam_beta1 = 0.9f; c->adam_beta2 = 0.999f; c->adam_eps = 1e-8f;
+  c->loss_variant = SNDVAE_LOSS_ELBO; c->gamma = 100.f; c->C_max = 100.f; c->C_stop_iter = 100.f; c->C_step = 20.f;
+  c->dip_lambda_od = 10.f; c->dip_lambda_d = 100.f;
   return 0;
 }
 
@@ -1039,6 +1093,9 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     return fail(h, SNDVAE_E_ARG, "bad config: num_nodes=%d batch_size=%d", c.num_nodes, c.batch_size);
   if (c.model_type != SNDVAE_MODEL_DISENTANGLED && c.model_type != SNDVAE_MODEL_BASE) return fail(h, SNDVAE_E_ARG, "bad model_type %d", c.model_type);
   h->dis = c.model_type == SNDVAE_MODEL_DISENTANGLED;
+  h->global_iter = 0;
+  if (c.loss_variant < 0 || c.loss_variant > SNDVAE_LOSS_DIP || (c.loss_variant != SNDVAE_LOSS_ELBO && c.model_type != SNDVAE_MODEL_DISENTANGLED))
+    return fail(h, SNDVAE_E_ARG, "loss_variant %d needs the disentangled model (optimizer.py:166-190)", c.loss_variant);
   h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp); memset(&h->ytc, 0, sizeof h->ytc);
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
@@ -1218,6 +1275,7 @@ int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_no
 }
 
 int64_t sndvae_launch_count(const sndvae_t* h) { return h ? h->launches : 0; }
+int sndvae_set_global_iter(sndvae_t* h, int64_t it) { if (!h) return SNDVAE_E_ARG; h->global_iter = it; return 0; }
 
 int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms, int64_t* launches, double* flops) {
   if (!h) return SNDVAE_E_ARG;

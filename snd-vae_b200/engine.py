@@ -250,6 +250,10 @@ class Engine:
         self._check(self.lib.sndvae_train_step_host(self._h, C.byref(inp), C.byref(nz), gen_adj_np.ctypes.data,
                                                     losses_np.ctypes.data))
 
+    def set_global_iter(self, it: int):
+        """The `global_iter` feed (main.py:329); read by the 'disentangled_C' loss only."""
+        self._check(self.lib.sndvae_set_global_iter(self._h, int(it)))
+
     def generate(self, z_s, z_sg, z_g, fetch=("generated_adj", "generated_adj_prob", "generated_spatial", "generated_node_feat")):
         zs = self._dev("z_s", z_s) if self.dis else None
         zg = self._dev("z_g", z_g) if self.dis else None

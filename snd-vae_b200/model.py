@@ -19,6 +19,9 @@ _MODEL_FETCHES = ("z_mean_s", "z_std_s", "z_mean_g", "z_std_g", "z_mean_sg", "z_
                   "generated_adj", "generated_adj_prob", "generated_spatial", "generated_node_feat")
 
 
+from ._lib import LOSS_VARIANTS
+
+
 class _ModelBase:
     model_type = "disentangled"
 
@@ -34,7 +37,10 @@ class _ModelBase:
             sg_conv_hidden=F.sg_conv_hidden, sg_hidden_size=F.sg_hidden_size, sg_latent_size=F.sg_latent_size,
             s_d_channel=F.s_d_channel[:3], n_d_channel=F.n_d_channel[:F.graph_deconv_layers],
             e_d_hidden=F.e_d_hidden[:F.graph_deconv_layers], learning_rate=F.learning_rate,
-            use_tensor_cores=F.use_tensor_cores, chunk_graphs=F.chunk_graphs)
+            use_tensor_cores=F.use_tensor_cores, chunk_graphs=F.chunk_graphs,
+            # loss branch of OptimizerVAE selected by FLAGS.model_type (optimizer.py:160-190)
+            loss_variant=LOSS_VARIANTS.get(F.model_type, 0), gamma=float(F.gamma), C_max=float(F.C_max),
+            C_stop_iter=float(F.C_stop_iter), C_step=float(F.C_step))
         self.engine = Engine(cfg)
         self.engine.set_params({k: torch.from_numpy(v) for k, v in init_params(self.engine.table, seed).items()})
         self.mode = F.type                     # 'train' | 'test_reconstruct' | 'test_generation' (model.py:79-90)
@@ -60,6 +66,8 @@ class _ModelBase:
             key = ph.name if isinstance(ph, Placeholder) else str(ph)
             feeds[key] = val
         noise = self._noise(feeds)
+        if "global_iter" in feeds:             # main.py:329: only the capacity loss reads it
+            self.engine.set_global_iter(int(np.asarray(feeds["global_iter"]).reshape(-1)[0]))
         loss_names = _LOSS_NAMES_DIS if self.engine.dis else _LOSS_NAMES_BASE
         want_opt = "opt_op" in names
         want_loss = any(n in loss_names or n == "overall_loss" for n in names)

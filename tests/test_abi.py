@@ -37,6 +37,9 @@ def test_config_struct_layout(built):
     assert (cfg.sg_hidden_size, cfg.sg_latent_size, cfg.batch_size) == (100, 100, 10)
     assert abs(cfg.learning_rate - 0.0008) < 1e-9 and cfg.beta == 1.0
     assert abs(cfg.adam_beta1 - 0.9) < 1e-7 and abs(cfg.adam_beta2 - 0.999) < 1e-7 and abs(cfg.adam_eps - 1e-8) < 1e-15
+    # loss-branch tail of the struct (main.py:95-98, optimizer.py:183): a layout slip between header and ctypes mirror shows here
+    assert (cfg.loss_variant, cfg.gamma, cfg.C_max, cfg.C_stop_iter, cfg.C_step, cfg.dip_lambda_od, cfg.dip_lambda_d) == (0, 100.0, 100.0, 100.0, 20.0, 10.0, 100.0)
+    assert cfg.use_tensor_cores == 2
 
 
 @pytest.mark.parametrize("model,N", [("disentangled", 25), ("base", 25), ("disentangled", 256)])
@@ -73,6 +76,12 @@ def test_bad_config_rejected(built):
     h = C.c_void_p()
     assert lib.sndvae_create(C.byref(cfg), None, C.byref(h)) == -1
     assert b"bad config" in lib.sndvae_last_error(h)
+    lib.sndvae_destroy(h)
+    # the capacity / DIP losses exist for the 3-latent model only (optimizer.py:166-183 read z_mean_s / z_mean_g)
+    cfg = built.make_config(25, 4, "base", loss_variant=1)
+    h = C.c_void_p()
+    assert lib.sndvae_create(C.byref(cfg), None, C.byref(h)) == -1
+    assert b"loss_variant" in lib.sndvae_last_error(h)
     lib.sndvae_destroy(h)
 
 

@@ -318,6 +318,36 @@ def test_host_entry_point_and_shims(built):
     F.reset()
 
 
+@pytest.mark.parametrize("variant,it", [("disentangled_C", 0), ("disentangled_C", 40), ("NED-VAE-IP", 0)])
+def test_loss_variants(built, variant, it):
+    """The capacity ('disentangled_C', optimizer.py:166-174) and DIP ('NED-VAE-IP', optimizer.py:7-21,176-183) branches of
+    OptimizerVAE against the oracle: cost and every gradient.  global_iter = 0 gives C = 0 (gate open: gamma * kl_sg),
+    global_iter = 40 gives C = 40 > kl_sg (gate closed: no KL gradient into the joint head)."""
+    N, B, S = 9, 5, 3
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled")
+    cfg.loss_variant = variant; cfg.global_iter = it
+    enc, z, dec, L, grads = O.loss_and_grads(P, inp, noise, cfg, "factored")
+    eng = built.Engine(built.make_config(N, B, "disentangled", sampling_num=S, chunk_graphs=2,
+                                         loss_variant=built._lib.LOSS_VARIANTS[variant]))
+    eng.set_params(P); eng.set_global_iter(it)
+    res = eng.grads(inp, noise)
+    np.testing.assert_allclose(res["overall_loss"], [x.item() for x in L["overall_loss"]], rtol=1e-4)
+    gg = eng.get_grads()
+    # DIP: d reg / d mu = (2/B) (mu - m) G sums to zero over the batch, so bias-like gradients (BN beta, head biases) are small
+    # differences of O(lambda_d) terms -- fp32 cancellation noise of a few 1e-3 of the tensor maximum against the fp64 oracle
+    # (the head biases see only that noise: their exact DIP gradient is zero), so for DIP the error of a tensor is measured
+    # against max(|tensor|, 1 % of the largest encoder-head gradient) instead of |tensor| alone
+    floor = 0.0
+    if variant == "NED-VAE-IP":
+        floor = 1e-2 * max(grads[k].abs().max().item() for k in grads if "_lin/" in k and k.startswith("encoder/"))
+    for k, v in grads.items():
+        err = np.abs(gg[k].double().numpy() - v.numpy()).max() / max(v.abs().max().item(), floor, 1e-30)
+        assert err < 1e-3, (k, err)
+    f = eng.forward(inp, noise, fetch=("z_mean_sg",))                      # forward-only cost includes the regulariser too
+    np.testing.assert_allclose(f["overall_loss"][0], float(L["cost"]), rtol=1e-4)
+    eng.close()
+
+
 @pytest.mark.parametrize("tc", [1, 2])
 def test_pipelined_host_step_equals_device_step(built, tc):
     """sndvae_train_step_host runs the step piece by piece (one micro-batch of graphs per piece, the next piece's feeds

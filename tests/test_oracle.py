@@ -167,3 +167,32 @@ def test_golden_vectors(name):
     for k in g:
         d = z["gradsum/" + k]
         assert np.allclose([g[k].sum().item(), g[k].abs().sum().item()], d, rtol=1e-7, atol=1e-12), k
+
+
+def test_loss_variants_of_the_oracle():
+    """optimizer.py:166-183: the capacity schedule C(global_iter), the relu gate of 'disentangled_C', and DIP() against a
+    direct numpy evaluation of its definition (covariance of the posterior means over the batch)."""
+    cfg0 = O.Config(num_nodes=6, sampling_num=2)
+    P = O.init_params(cfg0, 7, torch.float64)
+    g = torch.Generator().manual_seed(1)
+    for k in P:
+        P[k] = P[k] + 0.05 * torch.randn(P[k].shape, generator=g, dtype=torch.float64)
+    inp = O.synthetic_inputs(cfg0, 3, 5, torch.float64); nz = O.synthetic_noise(cfg0, 3, 9, torch.float64)
+    base = O.forward(P, inp, nz, cfg0)[3]
+    mse = base["adj_cost"] + base["node_cost"] + base["spatial_cost"]
+    for it, C in ((0, 0.0), (19, 0.0), (20, 20.0), (45, 40.0), (100, 100.0), (500, 100.0)):   # 100 * 20 / 100 * (it // 20), clipped
+        cfg = O.Config(num_nodes=6, sampling_num=2, loss_variant="disentangled_C", global_iter=it)
+        L = O.forward(P, inp, nz, cfg)[3]
+        assert L["C"] == C
+        want = mse + 100.0 * max(float(base["kl_sg"]) - C, 0.0) + base["kl_s"] + base["kl_g"]
+        assert abs(float(L["cost"]) - float(want)) < 1e-12
+    cfg = O.Config(num_nodes=6, sampling_num=2, loss_variant="NED-VAE-IP")
+    enc, _, _, L = O.forward(P, inp, nz, cfg)
+    tot = 0.0
+    for k in ("z_mean_s", "z_mean_g", "z_mean_sg"):
+        mu = enc[k].numpy()
+        cov = np.cov(mu.T, bias=True)
+        d = np.diag(cov)
+        tot += 100.0 * ((d - 1) ** 2).sum() + 10.0 * ((cov - np.diag(d)) ** 2).sum()
+    assert abs(float(L["dip"]) - tot) < 1e-8 * max(tot, 1.0)
+    assert abs(float(L["cost"]) - float(mse + base["kl_sg"] + base["kl_s"] + base["kl_g"] + tot)) < 1e-8 * max(tot, 1.0)
