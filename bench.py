@@ -51,7 +51,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=4096, help="graphs per step per GPU")
     ap.add_argument("--sampling", type=int, default=10)
     ap.add_argument("--model", default="disentangled", choices=["disentangled", "base"])
-    ap.add_argument("--pool", type=int, default=256, help="distinct synthetic graphs generated on the host, tiled to --batch")
+    ap.add_argument("--pool", type=int, default=256, help="--data host: distinct synthetic graphs generated on the host, tiled to --batch")
+    ap.add_argument("--data", default="device", choices=["device", "host"],
+                    help="device: all --batch graphs generated on the GPU (sndvae_synth_inputs, SURVEY 8f N2); host: scipy pool, tiled")
     ap.add_argument("--tc", type=int, default=2, help="e2e layer 1: 2 = spectral (FFT + per-frequency tcgen05 GEMMs), 1 = block-Toeplitz tcgen05 GEMMs, 0 = fp32 SIMT")
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=1)
@@ -193,15 +195,24 @@ def run_ours(args):
     P = params.init_params(eng.table, seed=7)                   # identical on every rank
     eng.set_params({k: torch.from_numpy(v) for k, v in P.items()})
 
-    pool_n = min(args.pool, B)
-    pool = data.synthetic_graphs(N, pool_n, S, seed=1234 + rank)
-    feeds_np = data.tile_pool(pool, B, pool_n, S)
+    used = ("features", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth")
+    if args.data == "device":
+        pool_n = B
+        gen = eng.synth_inputs(seed=1234 + rank)                   # B distinct graphs, S spanning forests each, built in HBM
+        feeds_dev = {k: gen[k] for k in used}
+        input_bytes = sum(feeds_dev[k].numel() * 4 for k in used)
+        del gen
+        feeds_np = None
+    else:
+        pool_n = min(args.pool, B)
+        pool = data.synthetic_graphs(N, pool_n, S, seed=1234 + rank)
+        feeds_np = data.tile_pool(pool, B, pool_n, S)
+        feeds_dev = {k: torch.from_numpy(np.ascontiguousarray(feeds_np[k])).to(dev) for k in used}
+        input_bytes = sum(feeds_np[k].nbytes for k in used)
     g = torch.Generator().manual_seed(4321 + rank)
     noise_np = {"eps_s": torch.randn(B, cfg.s_latent_size, generator=g).numpy(),
                 "eps_sg": torch.randn(B * S, cfg.sg_latent_size, generator=g).numpy(),
                 "eps_g": torch.randn(B, cfg.g_latent_size, generator=g).numpy()}
-    used = ("features", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth")
-    feeds_dev = {k: torch.from_numpy(np.ascontiguousarray(feeds_np[k])).to(dev) for k in used}
     noise_dev = {k: torch.from_numpy(v).to(dev) for k, v in noise_np.items()}
     inp, nz, keep = eng._pack(feeds_dev, noise_dev)
     out, res = eng._outs(("generated_adj",))
@@ -249,7 +260,13 @@ def run_ours(args):
     if not args.no_e2e:
         try:
             pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-            hf = {k: pin(feeds_np[k]) for k in used}
+            if feeds_np is None:                                 # device-generated feeds: one D2H copy into pinned host buffers
+                hf = {}
+                for k in used:
+                    t = torch.empty(feeds_dev[k].shape, dtype=torch.float32, pin_memory=True); t.copy_(feeds_dev[k]); hf[k] = t.numpy()
+                torch.cuda.synchronize()
+            else:
+                hf = {k: pin(feeds_np[k]) for k in used}
             hn = {k: pin(v) for k, v in noise_np.items()}
             gen = torch.empty((B, N, N), dtype=torch.int64).pin_memory().numpy()
             hl = np.zeros(8, dtype=np.float32)
@@ -326,8 +343,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": f"synthetic (random-geometric spatial graphs + spanning-tree samples; {pool_n} distinct graphs per rank tiled to the batch; "
-                f"inputs {sum(feeds_np[k].nbytes for k in used) / 1e9:.1f} GB per rank >> L2)",
+        "data": f"synthetic (random-geometric spatial graphs + spanning-tree samples; {pool_n} distinct graphs per rank"
+                f"{' generated on the device' if args.data == 'device' else ' tiled to the batch'}; inputs {input_bytes / 1e9:.1f} GB per rank >> L2)",
         "config": {"workload": f"SND-VAE {args.model} model (model.py) train step fwd+bwd+Adam, N={N}, S={S}, {B} graphs/step/GPU, "
                                f"global batch {world * B}", "num_nodes": N, "batch_per_gpu": B, "sampling_num": S,
                    "parallelism": f"dp{world}", "chunk_graphs": int(eng.cfg.chunk_graphs), "tensor_cores": bool(args.tc), "e2e_layer1": {0: "fp32 SIMT", 1: "block-Toeplitz tcgen05 bf16x3", 2: "spectral: FFT + per-frequency tcgen05 bf16x3"}[args.tc],

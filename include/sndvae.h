@@ -186,6 +186,12 @@ int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in_host, const sndv
                            int64_t* generated_adj_host, float* losses_host);
 
 /* Number of library kernels launched since create (bench.py's gpu_launches). */
+/* Device-side synthetic data (replaces input_data.py:18-38,54-96 for synthetic spatial graphs): fills the
+ * caller's DEVICE feed buffers (shapes as in sndvae_inputs; any pointer except spatial_truth and adj may be NULL) with
+ * random-geometric graphs in the unit square and `sampling_num` random spanning forests per graph, reproducibly from `seed`
+ * (counter-based hash; oracle/synth.py gives the same arrays bit for bit).  The pointers are written despite the const. */
+int sndvae_synth_inputs(sndvae_t* h, uint64_t seed, const sndvae_inputs* device_buffers);
+
 int64_t sndvae_launch_count(const sndvae_t* h);
 
 /* The `global_iter` placeholder (main.py:262,329): only the 'disentangled_C' loss reads it (optimizer.py:172). */

@@ -77,6 +77,7 @@ SYMBOLS = {
     "sndvae_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Outputs)]),
     "sndvae_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.c_void_p, C.c_void_p]),
     "sndvae_set_global_iter": (C.c_int, [C.c_void_p, I64]),
+    "sndvae_synth_inputs": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Inputs)]),
     "sndvae_launch_count": (I64, [C.c_void_p]),
     "sndvae_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(C.c_double)]),
     "sndvae_threshold_logits": (C.c_int, [C.c_void_p, C.c_void_p, I64, C.c_void_p]),

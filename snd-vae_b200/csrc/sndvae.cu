@@ -12,6 +12,7 @@
 #include "adam.cuh"
 #include "e2e_tc.cuh"
 #include "spectral.cuh"
+#include "synth.cuh"
 #include <cublas_v2.h>
 #include <string>
 #include <vector>
@@ -1270,6 +1271,21 @@ int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_no
   r = run(h, &din, &dnz, &o, losses_host, true, 0, &hfd); if (r) return r;
   r = sndvae_apply_adam(h); if (r) return r;
   CK(cudaStreamSynchronize(h->ds));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int sndvae_synth_inputs(sndvae_t* h, uint64_t seed, const sndvae_inputs* io) {
+  if (!h || !io) return SNDVAE_E_ARG;
+  const int N = h->N, F = h->F, D = h->D, S = h->S; const long long B = h->B, BS = h->BS;
+  if (N > SY_MAXN) return fail(h, SNDVAE_E_ARG, "sndvae_synth_inputs supports num_nodes <= %d", SY_MAXN);
+  if (!io->spatial_truth || !io->adj) return fail(h, SNDVAE_E_ARG, "sndvae_synth_inputs needs at least spatial_truth and adj buffers");
+  const float r2 = (float)(6.0 / (3.14159265358979323846 * (double)N));       // radius of the random geometric graph: mean degree ~ 6
+  LAUNCH(synth_graph_k, (unsigned)B, 256, sizeof(float) * N * D, (unsigned long long)seed, N, F, D, S, r2, (float*)io->spatial_truth,
+         (float*)io->feature_truth, (float*)io->rel_truth, (float*)io->adj_truth, (float*)io->features, (float*)io->spatial);
+  const size_t smem = (size_t)N * (8 + 4 + 4 * D + 1) + 16;
+  LAUNCH(synth_sample_k, (unsigned)BS, SY_THREADS, smem, (unsigned long long)seed, N, D, S, r2, io->spatial_truth, (float*)io->adj, (float*)io->rel);
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }

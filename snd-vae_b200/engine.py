@@ -250,6 +250,17 @@ class Engine:
         self._check(self.lib.sndvae_train_step_host(self._h, C.byref(inp), C.byref(nz), gen_adj_np.ctypes.data,
                                                     losses_np.ctypes.data))
 
+    def synth_inputs(self, seed: int) -> Dict[str, torch.Tensor]:
+        """Device-side synthetic feeds (random-geometric graphs + spanning-forest samples) for this engine's batch:
+        the eight arrays of construct_feed_dict_train as CUDA tensors (sndvae_synth_inputs)."""
+        B, S, N, F, D = self.B, self.S, self.N, self.F, self.D
+        shapes = {"features": (B * S, N, F), "spatial": (B * S, N, D), "adj": (B * S, N, N), "rel": (B * S, N, N, 1),
+                  "adj_truth": (B, N, N), "feature_truth": (B, N, F), "spatial_truth": (B, N, D), "rel_truth": (B, N, N, 1)}
+        t = {k: torch.empty(v, dtype=torch.float32, device=self.device) for k, v in shapes.items()}
+        io = _lib.Inputs(**{k: v.data_ptr() for k, v in t.items()})
+        self._check(self.lib.sndvae_synth_inputs(self._h, int(seed) & (2 ** 64 - 1), C.byref(io)))
+        return t
+
     def set_global_iter(self, it: int):
         """The `global_iter` feed (main.py:329); read by the 'disentangled_C' loss only."""
         self._check(self.lib.sndvae_set_global_iter(self._h, int(it)))

@@ -318,6 +318,40 @@ def test_host_entry_point_and_shims(built):
     F.reset()
 
 
+@pytest.mark.parametrize("N,B,S", [(25, 3, 4), (8, 5, 2), (61, 2, 3)])
+def test_device_synthetic_data_bit_exact(built, N, B, S):
+    """sndvae_synth_inputs (synth.cuh: hashed coordinates, single-rounding distances, Prim forests) against oracle/synth.py
+    (Kruskal): all eight feeds bit for bit -- integer / index work must be exact, and the float steps are single IEEE operations."""
+    from oracle import synth
+    eng = _engine(built, N, B, S, "disentangled", 2)
+    got = eng.synth_inputs(seed=1234567)
+    ref = synth.synth_inputs(N, B, S, 1, 2, seed=1234567)
+    for k, v in ref.items():
+        assert np.array_equal(got[k].cpu().numpy(), v), k
+    eng.close()
+
+
+def test_device_synthetic_data_properties_n256(built):
+    """At BASELINE's N = 256 (oracle too slow for a batch): every sample is a spanning forest of its graph's truth adjacency, and a
+    train step on the generated feeds runs."""
+    from scipy.sparse.csgraph import connected_components
+    N, B, S = 256, 6, 10
+    eng = _engine(built, N, B, S, "disentangled", 2)
+    d = eng.synth_inputs(seed=42)
+    A = d["adj_truth"].cpu().numpy(); As = d["adj"].cpu().numpy()
+    assert (A == A.transpose(0, 2, 1)).all() and 4.0 < A.sum() / (B * N) < 7.0
+    for b in range(B):
+        nc, _ = connected_components(A[b])
+        for s in range(S):
+            T = As[b * S + s]
+            assert (T == T.T).all() and (T <= A[b]).all() and T.sum() / 2 == N - nc and connected_components(T)[0] == nc
+    cfg = O.Config(num_nodes=N, sampling_num=S)
+    eng.set_params(O.init_params(cfg, 7, torch.float32))
+    r = eng.train_step(d, O.synthetic_noise(cfg, B, 9, torch.float32))
+    assert np.isfinite(r["overall_loss"]).all() and 0.6 < r["overall_loss"][2] < 0.8      # adj_cost ~ ln 2 at init (SURVEY App. G)
+    eng.close()
+
+
 @pytest.mark.parametrize("variant,it", [("disentangled_C", 0), ("disentangled_C", 40), ("NED-VAE-IP", 0)])
 def test_loss_variants(built, variant, it):
     """The capacity ('disentangled_C', optimizer.py:166-174) and DIP ('NED-VAE-IP', optimizer.py:7-21,176-183) branches of

@@ -196,3 +196,30 @@ def test_loss_variants_of_the_oracle():
         tot += 100.0 * ((d - 1) ** 2).sum() + 10.0 * ((cov - np.diag(d)) ** 2).sum()
     assert abs(float(L["dip"]) - tot) < 1e-8 * max(tot, 1.0)
     assert abs(float(L["cost"]) - float(mse + base["kl_sg"] + base["kl_s"] + base["kl_g"] + tot)) < 1e-8 * max(tot, 1.0)
+
+
+def test_synthetic_data_oracle_invariants():
+    """oracle/synth.py (the checker of the device-side generator): coordinates / features in [0,1), rel = pairwise
+    distance, symmetric zero-diagonal adjacency, and every sample a spanning forest of its graph's adjacency (|E| = N - #components,
+    acyclic, subset of the truth edges) -- the properties of input_data.py:18-38,62-67,77-82."""
+    from scipy.sparse.csgraph import connected_components
+    from oracle import synth
+    N, B, S = 25, 3, 4
+    d = synth.synth_inputs(N, B, S, 1, 2, seed=99)
+    P, A, As, rel = d["spatial_truth"], d["adj_truth"], d["adj"], d["rel_truth"][..., 0]
+    assert P.min() >= 0 and P.max() < 1 and d["feature_truth"].min() >= 0 and d["feature_truth"].max() < 1
+    np.testing.assert_allclose(rel, np.sqrt(((P[:, :, None] - P[:, None]) ** 2).sum(-1)), rtol=1e-6, atol=1e-7)
+    assert (A == A.transpose(0, 2, 1)).all() and (A[:, np.arange(N), np.arange(N)] == 0).all()
+    assert 2.0 < A.sum() / (B * N) < 9.0                       # mean degree ~ 6 (boundary effects lower it)
+    for b in range(B):
+        nc, _ = connected_components(A[b])
+        for s in range(S):
+            T = As[b * S + s]
+            assert (T == T.T).all() and (T <= A[b]).all() and T.sum() / 2 == N - nc
+            assert connected_components(T)[0] == nc            # N - nc edges and nc components: a forest spanning every component
+    assert not (As[0] == As[1]).all()                          # different samples of one graph differ
+    for k in ("features", "spatial", "rel"):
+        assert d[k].shape[0] == B * S
+    assert (d["rel"][S:2 * S, ..., 0] == rel[1]).all() and (d["features"][S:2 * S] == d["feature_truth"][1]).all()
+    again = synth.synth_inputs(N, B, S, 1, 2, seed=99)
+    assert all((again[k] == d[k]).all() for k in d)
