@@ -239,6 +239,76 @@ __global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float*
   }
 }
 
+// two channels per thread (float2 loads, bf16x2 stores): the spectral-path form of l0_combine_planes_k.  blockDim = 5 * C1 / 2;
+// dY12 plane 1 in the [b,i,j,c] layout, E1 graph-tiled without Sa[b,i,:] + 2 b0 (added back here).
+__global__ void l0_combine_planes2_k(const float* __restrict__ dY12, const float* __restrict__ E1, const float* __restrict__ gam1,
+                                     const float* __restrict__ bet1, float* __restrict__ g_gam1, float* __restrict__ g_bet1,
+                                     float* __restrict__ g_b0, __nv_bfloat16* __restrict__ Ph, __nv_bfloat16* __restrict__ Pl,
+                                     float* __restrict__ dSa, int Bc, int N, int C1, int CS,
+                                     const float* __restrict__ Sa, const float* __restrict__ b0) {
+  extern __shared__ float sm[];           // [6][blockDim]
+  const long long row = blockIdx.x;
+  const int i = (int)(row % N); const long long b = row / N;
+  const int HP = C1 / 2;                   // channel pairs
+  const int op = threadIdx.x % HP, o = 2 * op;
+  const float2* E1row = reinterpret_cast<const float2*>(E1 + (((b / 128) * N + i) * 128 + (b % 128)) * (long long)N * C1);
+  const float2* d0 = reinterpret_cast<const float2*>(dY12 + row * N * C1);
+  const float2* d1 = reinterpret_cast<const float2*>(dY12 + (long long)Bc * N * N * C1 + row * N * C1);
+  const long long plane_c = (long long)Bc * N * N;
+  const float ebx = Sa[row * C1 + o] + 2.f * b0[o], eby = Sa[row * C1 + o + 1] + 2.f * b0[o + 1];
+  const float gx = gam1[o] * BN_RS, gy = gam1[o + 1] * BN_RS, btx = bet1[o], bty = bet1[o + 1];
+  float sgx = 0.f, sgy = 0.f, sbx = 0.f, sby = 0.f, s0x = 0.f, s0y = 0.f;
+  for (int idx = threadIdx.x; idx < N * HP; idx += blockDim.x) {
+    const int j = idx / HP;
+    const float2 a = d0[idx], c = d1[idx], ev = E1row[idx];
+    const float ex = ev.x + ebx, ey = ev.y + eby;
+    const float ddx = fmaf(ex, gx, btx) > 0.f ? a.x + c.x : 0.f, ddy = fmaf(ey, gy, bty) > 0.f ? a.y + c.y : 0.f;
+    sgx = fmaf(ddx, ex, sgx); sgy = fmaf(ddy, ey, sgy); sbx += ddx; sby += ddy;
+    const float dex = ddx * gx, dey = ddy * gy;
+    s0x += dex; s0y += dey;
+    __nv_bfloat162 h, l;
+    h.x = __float2bfloat16_rn(dex); h.y = __float2bfloat16_rn(dey);
+    l.x = __float2bfloat16_rn(dex - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(dey - __bfloat162float(h.y));
+    const long long c0 = row * N + j, c1 = (b * N + j) * N + i;
+    *reinterpret_cast<__nv_bfloat162*>(Ph + c0 * CS + o) = h; *reinterpret_cast<__nv_bfloat162*>(Pl + c0 * CS + o) = l;
+    *reinterpret_cast<__nv_bfloat162*>(Ph + (plane_c + c1) * CS + o) = h; *reinterpret_cast<__nv_bfloat162*>(Pl + (plane_c + c1) * CS + o) = l;
+  }
+  const int nt = blockDim.x;
+  sm[threadIdx.x] = sgx; sm[nt + threadIdx.x] = sgy; sm[2 * nt + threadIdx.x] = sbx; sm[3 * nt + threadIdx.x] = sby;
+  sm[4 * nt + threadIdx.x] = s0x; sm[5 * nt + threadIdx.x] = s0y;
+  __syncthreads();
+  if (threadIdx.x < HP) {
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = threadIdx.x; t < nt; t += HP)
+      for (int q = 0; q < 6; ++q) v[q] += sm[q * nt + t];
+    atomicAdd(g_gam1 + o, v[0] * BN_RS); atomicAdd(g_gam1 + o + 1, v[1] * BN_RS);
+    atomicAdd(g_bet1 + o, v[2]); atomicAdd(g_bet1 + o + 1, v[3]);
+    atomicAdd(g_b0 + o, 2.f * v[4]); atomicAdd(g_b0 + o + 1, 2.f * v[5]);
+    dSa[row * C1 + o] = v[4]; dSa[row * C1 + o + 1] = v[5];
+  }
+}
+// two channels per thread: out[row, o] = sum_s (hi + lo)[row, s, o]
+__global__ void rowsum_planes2_k(const __nv_bfloat16* __restrict__ Ph, const __nv_bfloat16* __restrict__ Pl, float* __restrict__ out,
+                                 int N, int C, int CS) {
+  extern __shared__ float sm[];
+  const long long row = blockIdx.x;
+  const int HP = C / 2, op = threadIdx.x % HP;
+  float sx = 0.f, sy = 0.f;
+  for (int idx = threadIdx.x; idx < N * HP; idx += blockDim.x) {
+    const long long a = (row * N + idx / HP) * CS + 2 * op;
+    const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ph + a));
+    const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Pl + a));
+    sx += h.x + l.x; sy += h.y + l.y;
+  }
+  sm[threadIdx.x] = sx; sm[blockDim.x + threadIdx.x] = sy;
+  __syncthreads();
+  if (threadIdx.x < HP) {
+    float ax = 0.f, ay = 0.f;
+    for (int t = threadIdx.x; t < blockDim.x; t += HP) { ax += sm[t]; ay += sm[blockDim.x + t]; }
+    out[row * C + 2 * op] = ax; out[row * C + 2 * op + 1] = ay;
+  }
+}
+
 // out[row, o] = sum_s (hi + lo)[row, s, o] over bf16 planes [rows, N, CS]  (dRc from the transposed dE1 planes)
 __global__ void rowsum_planes_k(const __nv_bfloat16* __restrict__ Ph, const __nv_bfloat16* __restrict__ Pl, float* __restrict__ out,
                                 int N, int C, int CS) {

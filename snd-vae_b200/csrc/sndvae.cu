@@ -670,9 +670,16 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     if (tc) {
       TcState& T = h->tc; L0Dense& Ld = h->l0d;
       const int CSe = Ld.CSe; const long long poff = cells * CSe;        // direction-1 planes
-      LAUNCH(l0_combine_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
+      if (h->spec && C1 % 2 == 0 && CSe % 2 == 0) {          // two channels per thread: 4-byte plane stores, 8-byte loads
+        const int nt = 5 * C1 / 2 * 2;                         // 10 positions x C1/2 channel pairs
+        LAUNCH(l0_combine_planes2_k, (unsigned)rows, nt, sizeof(float) * 6 * nt, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
+               h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], h->Yhi, h->Ylo, h->dSa + b0 * N * C1, bc, N, C1, CSe, h->Sa + b0 * N * C1, h->P + p.e_b[0]);
+        LAUNCH(rowsum_planes2_k, (unsigned)rows, nt, sizeof(float) * 2 * nt, h->Yhi + poff, h->Ylo + poff, h->dRc + b0 * N * C1, N, C1, CSe);
+      } else {
+        LAUNCH(l0_combine_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 15 * C1, h->dY12, h->E1, h->P + p.e_bng[1], h->P + p.e_bnb[1],
              h->G + p.e_bng[1], h->G + p.e_bnb[1], h->G + p.e_b[0], h->Yhi, h->Ylo, h->dSa + b0 * N * C1, bc, N, C1, CSe, h->spec, h->Sa + b0 * N * C1, h->P + p.e_b[0]);
-      LAUNCH(rowsum_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, h->Yhi + poff, h->Ylo + poff, h->dRc + b0 * N * C1, N, C1, CSe);
+        LAUNCH(rowsum_planes_k, (unsigned)rows, 5 * C1, sizeof(float) * 5 * C1, h->Yhi + poff, h->Ylo + poff, h->dRc + b0 * N * C1, N, C1, CSe);
+      }
       mark(h, "l0_gemms");
       if (l0d_bwd_act(Ld, 0, h->Yhi, h->Ylo, h->da + b0 * N * Chv, rows, rows, h->stream) ||
           l0d_bwd_act(Ld, 1, h->Yhi + poff, h->Ylo + poff, h->dc + b0 * N * Chv, rows, rows, h->stream) ||

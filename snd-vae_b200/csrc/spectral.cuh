@@ -507,7 +507,11 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
   constexpr int B_BOX = BN * 64 * 2;
   constexpr int B_PLANE = ABOX * B_BOX;
   constexpr int B_BYTES = 2 * B_PLANE;
-  constexpr int SLOT_COLS = BN <= 64 ? 64 : 128;
+  // Two accumulators per item: a short-N tcgen05.mma into the tile the previous one is still updating costs ~170-300 cycles of
+  // latency (measured), so the 3 x KSTEPS accumulates of an item are split into two independent chains (summed by the
+  // epilogue) instead of one.
+  constexpr int ACC_COLS = BN <= 64 ? 64 : 128;
+  constexpr int SLOT_COLS = 2 * ACC_COLS;
   constexpr int NSLOT = 512 / SLOT_COLS;
   constexpr int STG_BYTES = 128 * WOUT * 4;
   constexpr int NLD = (WOUT + 7) / 8;              // tcgen05.ld x8 per row
@@ -584,9 +588,10 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
           const uint64_t al = umma_desc(sa + A_PLANE + box * A_BOX + kk * 32, 16, 1024, 2ull);
           const uint64_t bh = umma_desc(sb + box * B_BOX + kk * 32, 16, 1024, 2ull);
           const uint64_t bl = umma_desc(sb + B_PLANE + box * B_BOX + kk * 32, 16, 1024, 2ull);
+          // chain 0: hi.hi (+ hi.lo on even k steps);  chain 1: lo.hi (+ hi.lo on odd k steps)
           umma_bf16(td, ah, bh, idesc, ks ? 1u : 0u);
-          umma_bf16(td, ah, bl, idesc, 1u);
-          umma_bf16(td, al, bh, idesc, 1u);
+          umma_bf16(td + ACC_COLS, al, bh, idesc, ks ? 1u : 0u);
+          umma_bf16((ks & 1) ? td + ACC_COLS : td, ah, bl, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);
         umma_commit(&acc_full[slot]);
@@ -608,8 +613,11 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
       float* srow = stg + (size_t)r * WOUT;
 #pragma unroll
       for (int c0 = 0; c0 < NLD * 8; c0 += 8) {
-        uint32_t v[8];
+        uint32_t v[8], v2[8];
         tmem_ld8(ta + c0, v);
+        tmem_ld8(ta + ACC_COLS + c0, v2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
         if (c0 + 8 <= WOUT) {
           *reinterpret_cast<float4*>(srow + c0) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
           *reinterpret_cast<float4*>(srow + c0 + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
@@ -670,7 +678,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 128);
+  if (warp == 1) tmem_alloc(&tmem_base_s, 256);     // 2 slots x 2 accumulate chains (one per 16-line K step of a chunk) x 64 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -713,14 +721,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t td = tmem_d + slot * 64;
+          const uint32_t td0 = tmem_d + slot * 128;
 #pragma unroll
           for (int k = 0; k < SP_WKC / 16; ++k) {
             const uint64_t ah = umma_desc_sw128(sa + k * 2048, BLK, 1024);
             const uint64_t al = umma_desc_sw128(sa + A_PLANE + k * 2048, BLK, 1024);
             const uint64_t bh = umma_desc_sw128(sa + 2 * A_PLANE + k * 2048, BLK, 1024);
             const uint64_t bl = umma_desc_sw128(sa + 2 * A_PLANE + B_PLANE + k * 2048, BLK, 1024);
-            umma_bf16(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
+            const uint32_t td = td0 + k * 64;            // independent chain per K step: no back-to-back accumulates into one tile
+            umma_bf16(td, ah, bh, idesc, gi ? 1u : 0u);
             umma_bf16(td, ah, bl, idesc, 1u);
             umma_bf16(td, al, bh, idesc, 1u);
           }
@@ -745,13 +754,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
         const int slot = gcount & 1;
         mbar_wait(&acc_full[slot], (gcount >> 1) & 1);
         tc_fence_after();
-        const uint32_t ta = tmem_d + slot * 64 + ((uint32_t)(q * 32) << 16) + half * HC;
+        const uint32_t ta = tmem_d + slot * 128 + ((uint32_t)(q * 32) << 16) + half * HC;
 #pragma unroll
         for (int c0 = 0; c0 < HC; c0 += 8) {
-          uint32_t v[8];
+          uint32_t v[8], v2[8];
           tmem_ld8(ta + c0, v);
+          tmem_ld8(ta + 64 + c0, v2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(v[i]) + __uint_as_float(v2[i]);
         }
         tc_fence_before();
         __syncwarp();
@@ -772,7 +782,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 128); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 256); }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -1025,7 +1035,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* fix = smem; uint8_t* ring = smem + FIX_BYTES;
   float* xbuf = reinterpret_cast<float*>(ring + (size_t)YTC_STAGES * STAGE_BYTES);     // 4 epilogue warps x 12.8 KB
-  __shared__ uint64_t fix_full, fix_empty, full_bar[YTC_STAGES], empty_bar[YTC_STAGES], acc_full[4], acc_empty[4];
+  __shared__ uint64_t fix_full, fix_empty, full_bar[YTC_STAGES], empty_bar[YTC_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = P.N;
@@ -1034,7 +1044,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(&fix_full, 1); mbar_init(&fix_empty, 1);
     for (int s = 0; s < YTC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
@@ -1075,13 +1085,14 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
         mbar_wait(&fix_full, nw & 1);
         tc_fence_after();
         for (int j = 0; j < N; ++j, ++it) {
-          const int slot = pc & 3, half = j & 1;
-          if (half == 0) { mbar_wait(&acc_empty[slot], ((pc >> 2) & 1) ^ 1); tc_fence_after(); }
+          const int slot = pc & 1, half = j & 1;
+          if (half == 0) { mbar_wait(&acc_empty[slot], ((pc >> 1) & 1) ^ 1); tc_fence_after(); }
           const int s = it % YTC_STAGES; const uint32_t ph = (it / YTC_STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t ss = smem_u32(ring + (size_t)s * STAGE_BYTES);
-          const uint32_t td = tmem_d + slot * 128 + half * 64;
+          // two independent accumulate chains per position (a-part / c-part), summed by the epilogue
+          const uint32_t td = tmem_d + slot * 256 + half * 64, td2 = td + 128;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {      // a[., i] . WSa[j]
             const uint64_t ah = umma_desc(sf + k * 32, 16, 1024, 2ull), al = umma_desc(sf + A_BYTES + k * 32, 16, 1024, 2ull);
@@ -1092,7 +1103,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
           for (int k = 0; k < 3; ++k) {      // c[., j] . WSc[i]
             const uint64_t ah = umma_desc(ss + k * 32, 16, 1024, 2ull), al = umma_desc(ss + A_BYTES + k * 32, 16, 1024, 2ull);
             const uint64_t bh = umma_desc(sf + 2 * A_BYTES + k * 32, 16, 1024, 2ull), bl = umma_desc(sf + 2 * A_BYTES + W_BYTES + k * 32, 16, 1024, 2ull);
-            umma_bf16(td, ah, bh, idesc, 1u); umma_bf16(td, ah, bl, idesc, 1u); umma_bf16(td, al, bh, idesc, 1u);
+            umma_bf16(td2, ah, bh, idesc, k ? 1u : 0u); umma_bf16(td2, ah, bl, idesc, 1u); umma_bf16(td2, al, bh, idesc, 1u);
           }
           umma_commit(&empty_bar[s]);
           if (half == 1 || j == N - 1) { umma_commit(&acc_full[slot]); ++pc; }
@@ -1133,21 +1144,23 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
 #pragma unroll
         for (int t = 0; t < 25; ++t) pf[t] = __ldg(reinterpret_cast<const float4*>(P.Rc + osrc[t]));
         for (int j0 = 0; j0 < N; j0 += 2, ++pc) {
-          const int slot = pc & 3;
-          mbar_wait(&acc_full[slot], (pc >> 2) & 1);
+          const int slot = pc & 1;
+          mbar_wait(&acc_full[slot], (pc >> 1) & 1);
           tc_fence_after();
-          const uint32_t ta = tmem_d + slot * 128 + ((uint32_t)(q * 32) << 16);
+          const uint32_t ta = tmem_d + slot * 256 + ((uint32_t)(q * 32) << 16);
           float2* xr = reinterpret_cast<float2*>(xw + lane * 25);
           // TMEM columns [0, 50) and [64, 114) -> floats [0, 50) and [50, 100) of this graph's row of the tile
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
 #pragma unroll
             for (int c0 = 0; c0 < 56; c0 += 8) {
-              uint32_t v[8];
+              uint32_t v[8], v2[8];
               tmem_ld8(ta + jj * 64 + c0, v);
+              tmem_ld8(ta + 128 + jj * 64 + c0, v2);
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (c0 + 2 * u < C1) xr[(jj * C1 + c0) / 2 + u] = make_float2(__uint_as_float(v[2 * u]), __uint_as_float(v[2 * u + 1]));
+                if (c0 + 2 * u < C1) xr[(jj * C1 + c0) / 2 + u] = make_float2(__uint_as_float(v[2 * u]) + __uint_as_float(v2[2 * u]),
+                                                                             __uint_as_float(v[2 * u + 1]) + __uint_as_float(v2[2 * u + 1]));
             }
           }
           tc_fence_before();
@@ -1169,7 +1182,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
         continue;
       }
       for (int j0 = 0; j0 < N; j0 += 2, ++pc) {
-        const int slot = pc & 3;
+        const int slot = pc & 1;
         const int nj = N - j0 < 2 ? N - j0 : 2;
         float r[2 * C1];
         {
@@ -1177,18 +1190,19 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
 #pragma unroll
           for (int u = 0; u < C1; ++u) { float2 t = make_float2(0.f, 0.f); if (u < nj * (C1 / 2)) t = __ldg(rc + u); r[2 * u] = t.x; r[2 * u + 1] = t.y; }
         }
-        mbar_wait(&acc_full[slot], (pc >> 2) & 1);
+        mbar_wait(&acc_full[slot], (pc >> 1) & 1);
         tc_fence_after();
-        const uint32_t ta = tmem_d + slot * 128 + ((uint32_t)(q * 32) << 16);
+        const uint32_t ta = tmem_d + slot * 256 + ((uint32_t)(q * 32) << 16);
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           if (jj < nj) {
 #pragma unroll
             for (int c0 = 0; c0 < 56; c0 += 8) {
-              uint32_t v[8];
+              uint32_t v[8], v2[8];
               tmem_ld8(ta + jj * 64 + c0, v);
+              tmem_ld8(ta + 128 + jj * 64 + c0, v2);
 #pragma unroll
-              for (int u = 0; u < 8; ++u) if (c0 + u < C1) r[jj * C1 + c0 + u] += __uint_as_float(v[u]);
+              for (int u = 0; u < 8; ++u) if (c0 + u < C1) r[jj * C1 + c0 + u] += __uint_as_float(v[u]) + __uint_as_float(v2[u]);
             }
           }
         }
