@@ -8,16 +8,21 @@ A "step" is one pass of the hot path over one batch of synthetic spatial graphs:
 encoder + reparameterisation + decoder + ELBO + backward + TF-Adam for
 `--batch` graphs per GPU (weak scaling).  Workload = BASELINE.json configs[2]:
 the 3-latent model (model.py) at N=256, 4096 graphs per step per GPU, S=10
-spanning-tree samples per graph, fp32 arithmetic (e2e layer 1 as 3-pass split-bf16
-on tcgen05 with fp32 accumulation).
+spanning-tree samples per graph, fp32 arithmetic (e2e layer 1 in the frequency
+domain: fp32 Stockham FFT kernels around per-frequency 3-pass split-bf16 tcgen05
+GEMMs with fp32 accumulation; --tc 1 = the block-Toeplitz tcgen05 GEMM form).
+Feeds are generated on the device (sndvae_synth_inputs; --data host = scipy pool).
 
 `value`   : device-resident inputs (CUDA events around K steps, max over ranks).
 `e2e`     : the same step through the host-buffer entry point
             (sndvae_train_step_host: pinned numpy feeds in, losses + int64
             adjacency out), host<->device copies inside the timed region.
-`roofline`: the e2e layer-1 GEMM launches (fwd, dgrad, wgrad), timed live with CUDA
-            events on the launching stream; algorithmic FLOPs (SURVEY 8d F1 per
-            graph per GEMM) over measured bf16 peak.  Executed MMA FLOPs are 3x.
+`roofline`: the e2e layer-1 stage (7 launches per micro-batch: 2 + 2 FFT kernels, 3
+            per-frequency GEMM kernels), timed live with CUDA events on the launching
+            stream.  Spectral path: bound "hbm", compulsory bytes of the stage over the
+            measured HBM peak (+ measured DRAM traffic from ncu).  --tc 1: bound
+            "tensor", algorithmic FLOPs (SURVEY 8d F1 per graph per GEMM) over the
+            measured bf16 peak; executed MMA FLOPs are 3x.
 `cpu_baseline` / `--impl reference`: TensorFlow is not installable here, so the
             reference arm is the oracle's CPU restatement of the reference
             (kind "port"), timed on a bounded sample of the same workload.
@@ -326,16 +331,16 @@ def run_ours(args):
             "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
         }
     else:
-      roofline = {
-        "bound": "tensor", "kernel": "toep_gemm_k<240> (fwd, dgrad) + wgrad_gemm_k: e2e layer-1 block-Toeplitz GEMMs",
-        "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-        "traffic": None, "peak_source": peak_src,
-        "executed_mma_tflops": (3.0 * achieved * (56 / 50)) if achieved else None,
-        "note": "achieved = algorithmic FLOPs (F1 = 2*2*N*V(N)*50*20 per graph per GEMM, SURVEY 8d) / CUDA-event time of the GEMM launches; "
-                "the 3-pass split-bf16 product executes >= 3x those FLOPs on the tensor pipe",
-        "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
-        "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
-      }
+        roofline = {
+            "bound": "tensor", "kernel": "toep_gemm_k<240> (fwd, dgrad) + wgrad_gemm_k: e2e layer-1 block-Toeplitz GEMMs",
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+            "traffic": None, "peak_source": peak_src,
+            "executed_mma_tflops": (3.0 * achieved * (56 / 50)) if achieved else None,
+            "note": "achieved = algorithmic FLOPs (F1 = 2*2*N*V(N)*50*20 per graph per GEMM, SURVEY 8d) / CUDA-event time of the GEMM launches; "
+                    "the 3-pass split-bf16 product executes >= 3x those FLOPs on the tensor pipe",
+            "gemm_launches": int(gemm_n), "gemm_ms_per_step": gemm_ms / args.steps, "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+            "avg_launch_ms": gemm_ms / gemm_n if gemm_n else None,
+        }
     cpu = None
     if not args.no_cpu_baseline:
         cb = cpu_reference(args, 2, 1)
