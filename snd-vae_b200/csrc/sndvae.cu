@@ -1123,6 +1123,8 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     if (c.use_tensor_cores == 2) {   // + spectra: F frequencies x 2N lines x (Y^ planes 416 + O^ 160 + dO^ planes 160 + dY^ 400) B
       per_graph += (long long)(spec_pick_L(h->N) / 2 + 1) * 2 * h->N * 1136; budget = 56LL << 30; }
     long long bc = budget / per_graph; if (bc < 1) bc = 1; if (bc > h->B) bc = h->B; if (bc > 512) bc = 512;
+    if (c.use_tensor_cores == 2 && bc >= 128) bc = bc / 128 * 128;     // whole 128-graph tiles for the batch-major layer-0 GEMM
+    if ((long long)2 * bc * h->N * h->N * h->C1 > 2000000000LL) bc = 2000000000LL / ((long long)2 * h->N * h->N * h->C1);
     c.chunk_graphs = (int)bc;
   }
   if (c.chunk_graphs > h->B) c.chunk_graphs = (int)h->B;
