@@ -928,6 +928,8 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
   if (!s.generic_only) {
     if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_fwd_fast<6, 8, 8, 25, 800, 1>(s, a, st) : spec_launch_fwd_fast<6, 8, 8, 25, 400, 1>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 8) && C == 20) r = spec_launch_fwd_fast<6, 8, 8, 10, 320, 2>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 4) && C == 50) r = spec_launch_fwd_fast<6, 8, 4, 25, 400, 2>(s, a, st);      // N = 65..128 (L = 192)
+    else if (spec_plan_is(s.pl, 6, 8, 4) && C == 20) r = spec_launch_fwd_fast<6, 8, 4, 10, 160, 4>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 0) && C == 50) r = spec_launch_fwd_fast<6, 8, 0, 25, 200, 2>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 0) && C == 20) r = spec_launch_fwd_fast<6, 8, 0, 10, 160, 2>(s, a, st);
   }
@@ -942,6 +944,8 @@ static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, 
   if (!s.generic_only) {
     if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_inv_fast<6, 8, 8, 25, 800, 1, true>(s, a, st) : spec_launch_inv_fast<6, 8, 8, 25, 400, 1, true>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 8) && C == 20) r = spec_launch_inv_fast<6, 8, 8, 10, 320, 2, false>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 4) && C == 50) r = spec_launch_inv_fast<6, 8, 4, 25, 400, 2, true>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 4) && C == 20) r = spec_launch_inv_fast<6, 8, 4, 10, 160, 4, false>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 0) && C == 50) r = spec_launch_inv_fast<6, 8, 0, 25, 200, 2, false>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 0) && C == 20) r = spec_launch_inv_fast<6, 8, 0, 10, 160, 2, false>(s, a, st);
   }
