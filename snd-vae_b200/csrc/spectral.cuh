@@ -274,8 +274,14 @@ __device__ __forceinline__ void fft_pass_ct(const Src& in, const Dst& out, const
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = in.ld(j + r * T, cp);
       if (NS > 1) {
+        // one table read per butterfly; the other powers by multiplication (shared-memory instructions, not FP32 issue, bound
+        // these kernels): w^2 = w w, w^3 = w^2 w, w^4 = w^2 w^2, ... each at most three products deep
+        float2 w[R];
+        w[1] = tw[k * TSTEP];
 #pragma unroll
-        for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], tw[r * k * TSTEP]);
+        for (int r = 2; r < R; ++r) w[r] = (r & 1) ? cmulf(w[r - 1], w[1]) : cmulf(w[r / 2], w[r / 2]);
+#pragma unroll
+        for (int r = 1; r < R; ++r) v[r] = cmulf(v[r], w[r]);
       }
       dft_r<R>(v);
       const int j0 = (j - k) * R + k;
