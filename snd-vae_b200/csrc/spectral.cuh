@@ -657,13 +657,13 @@ struct SpecWgradArgs {
   int F, KS;             // frequencies, K splits per frequency
   int MV, NV;            // valid m / n extents (2*C1, 2*C2)
 };
-#define SP_WKC 32
-#define SP_WSTAGES 6
-#define SP_WGROUP 16     /* K chunks per TMEM accumulation group: 16 * 2 k-steps * 3 passes = 96 accumulates */
+#define SP_WKC 64
+#define SP_WSTAGES 3
+#define SP_WGROUP 8      /* K chunks per TMEM accumulation group: 8 * 4 k-steps * 3 passes = 96 accumulates over two chains */
 __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                                                               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                                                               SpecWgradArgs P) {
-  constexpr int BLK = SP_WKC * 128;                 // one [32 k-rows x 64 mn] box = 4 KB
+  constexpr int BLK = SP_WKC * 128;                 // one [SP_WKC k-rows x 64 mn] box
   constexpr int A_PLANE = 2 * BLK, B_PLANE = BLK;
   constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // 24 KB
   constexpr int HC = SP_NF / 2;                     // accumulator columns per epilogue thread
@@ -734,8 +734,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
             const uint64_t al = umma_desc_sw128(sa + A_PLANE + k * 2048, BLK, 1024);
             const uint64_t bh = umma_desc_sw128(sa + 2 * A_PLANE + k * 2048, BLK, 1024);
             const uint64_t bl = umma_desc_sw128(sa + 2 * A_PLANE + B_PLANE + k * 2048, BLK, 1024);
-            const uint32_t td = td0 + k * 64;            // independent chain per K step: no back-to-back accumulates into one tile
-            umma_bf16(td, ah, bh, idesc, gi ? 1u : 0u);
+            const uint32_t td = td0 + (k & 1) * 64;      // two independent chains: no back-to-back accumulates into one tile
+            umma_bf16(td, ah, bh, idesc, (gi | (k >> 1)) ? 1u : 0u);
             umma_bf16(td, ah, bl, idesc, 1u);
             umma_bf16(td, al, bh, idesc, 1u);
           }
