@@ -56,6 +56,7 @@ struct sndvae_handle {
   float *fsg, *hsg, *mu_sg, *ls_sg, *dfsg;
   float *x1, *x2, *dxa, *dxb;          // SGC chunk activations / grads
   SgcEdges E; SgcScratch S0, S1;
+  int sgc_keep;                        // forward activations of the joint encoder kept for every sample (no recompute in backward)
   float *z_s, *z_g, *z_sg, *zbar, *dz_s, *dz_g, *dzbar;
   float *dmu, *dls, *dh;               // head backward temporaries (sized for BS rows)
   float *n_sg, *n_s, *n_g, *dn_sg, *dn_s, *dn_g;
@@ -252,15 +253,33 @@ static int dalloc(sndvae_t* h, T** p, long long n) {
 }
 #define DA(ptr, n) do { int r_ = dalloc(h, &(ptr), (long long)(n)); if (r_) return r_; } while (0)
 
-static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long long samples, int N, int cap) {
-  const long long rows = samples * N; const int KQ = 2 * C + 2, K2 = 2 * C + 2 + hs[0], K3 = C + hs[1] + 1;
-  (void)cap;
-  DA(s.xphi, rows * C); DA(s.coefQ, rows * KQ); DA(s.P, rows * hs[0]); DA(s.Qc, rows * hs[0]); DA(s.coef2, rows * K2);
-  DA(s.m2s, rows * hs[1]); DA(s.coef3, rows * K3); DA(s.y, rows * hs[2]);
+// forward activations: for `fwd_samples` samples (chunk-sized, or -- sgc_keep -- for the whole batch: then they are per-graph
+// buffers registered for view_shift, `per_graph_samples` = S); backward temporaries: always for one chunk of `bwd_samples`
+static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long long fwd_samples, long long bwd_samples, int N, int per_graph_samples) {
+  const long long rf = fwd_samples * N, rows = bwd_samples * N; const int KQ = 2 * C + 2, K2 = 2 * C + 2 + hs[0], K3 = C + hs[1] + 1;
+  DA(s.xphi, rf * C); DA(s.coefQ, rf * KQ); DA(s.P, rf * hs[0]); DA(s.Qc, rf * hs[0]); DA(s.coef2, rf * K2);
+  DA(s.m2s, rf * hs[1]); DA(s.coef3, rf * K3); DA(s.y, rf * hs[2]);
+  if (per_graph_samples > 0) {
+    const long long pg = (long long)per_graph_samples * N;
+    reg_shift(h, &s.xphi, pg * C); reg_shift(h, &s.coefQ, pg * KQ); reg_shift(h, &s.P, pg * hs[0]); reg_shift(h, &s.Qc, pg * hs[0]);
+    reg_shift(h, &s.coef2, pg * K2); reg_shift(h, &s.m2s, pg * hs[1]); reg_shift(h, &s.coef3, pg * K3); reg_shift(h, &s.y, pg * hs[2]);
+  }
   DA(s.dcoef3, rows * K3); DA(s.dm2s, rows * hs[1]); DA(s.dcoef2, rows * K2); DA(s.dP, rows * hs[0]); DA(s.dQc, rows * hs[0]);
   DA(s.dxphi, rows * C); DA(s.dcoefQ, rows * KQ); DA(s.dpx, rows * C);
   DA(s.WQ, KQ * hs[0]); DA(s.W2, K2 * hs[1]); DA(s.W3, K3 * hs[2]); DA(s.dWQ, KQ * hs[0]); DA(s.w46, 2 * hs[0]);
   return 0;
+}
+// the scratch of layer l as seen by the chunk of samples starting at s0 (kernels index it with chunk-local sample numbers)
+static SgcScratch sgc_view(sndvae_t* h, int l, long long s0) {
+  SgcScratch S = l == 0 ? h->S0 : h->S1;
+  if (h->sgc_keep) {
+    const sndvae_config& c = h->cfg;
+    const int C = l == 0 ? c.num_feature : c.sg_conv_hidden[0][2]; const int* hs = c.sg_conv_hidden[l];
+    const int KQ = 2 * C + 2, K2 = 2 * C + 2 + hs[0], K3 = C + hs[1] + 1; const long long r0 = s0 * h->N;
+    S.xphi += r0 * C; S.coefQ += r0 * KQ; S.P += r0 * hs[0]; S.Qc += r0 * hs[0]; S.coef2 += r0 * K2; S.m2s += r0 * hs[1];
+    S.coef3 += r0 * K3; S.y += r0 * hs[2];
+  }
+  return S;
 }
 
 // DG: a buffer with `pg` elements per graph of the batch (registered for view_shift)
@@ -290,9 +309,20 @@ static int alloc_buffers(sndvae_t* h) {
   DG(E.ea, (long long)S * E.cap); DG(E.epr, (long long)S * E.cap); DG(E.eG, (long long)S * E.cap); DG(E.deg, S * N); DG(E.ssum, S * N); DG(E.nedges, S);
   const long long SC = h->SC;
   int r;
-  if ((r = alloc_scratch(h, h->S0, F, c.sg_conv_hidden[0], SC, N, E.cap))) return r;
-  if ((r = alloc_scratch(h, h->S1, c.sg_conv_hidden[0][2], c.sg_conv_hidden[1], SC, N, E.cap))) return r;
-  DA(h->x1, SC * N * c.sg_conv_hidden[0][2]); DA(h->x2, SC * N * hl); DA(h->dxa, SC * N * hl); DA(h->dxb, SC * N * hl);
+  {
+    // keep the joint encoder's forward activations for every sample when they fit (626 floats per node at the synthetic2 sizes:
+    // 26 GB at N=256, B=4096, S=10) -- the backward pass then re-uses them instead of recomputing each chunk's forward
+    const int* h0s = c.sg_conv_hidden[0]; const int* h1s = c.sg_conv_hidden[1]; const int C1s = h0s[2];
+    const long long fl = (F + (2 * F + 2) + 2 * h0s[0] + (2 * F + 2 + h0s[0]) + h0s[1] + (F + h0s[1] + 1) + h0s[2]) +
+                         (C1s + (2 * C1s + 2) + 2 * h1s[0] + (2 * C1s + 2 + h1s[0]) + h1s[1] + (C1s + h1s[1] + 1) + h1s[2]) + h0s[2] + hl;
+    const long long bytes = h->BS * N * fl * 4;
+    h->sgc_keep = (bytes <= (32LL << 30)) && !(getenv("SNDVAE_SGC_KEEP") && atoi(getenv("SNDVAE_SGC_KEEP")) == 0);
+  }
+  const long long SF = h->sgc_keep ? h->BS : SC; const int pgs = h->sgc_keep ? S : 0;
+  if ((r = alloc_scratch(h, h->S0, F, c.sg_conv_hidden[0], SF, SC, N, pgs))) return r;
+  if ((r = alloc_scratch(h, h->S1, c.sg_conv_hidden[0][2], c.sg_conv_hidden[1], SF, SC, N, pgs))) return r;
+  DA(h->x1, SF * N * c.sg_conv_hidden[0][2]); DA(h->x2, SF * N * hl); DA(h->dxa, SC * N * hl); DA(h->dxb, SC * N * hl);
+  if (h->sgc_keep) { reg_shift(h, &h->x1, (long long)S * N * c.sg_conv_hidden[0][2]); reg_shift(h, &h->x2, (long long)S * N * hl); }
   DG(h->z_sg, S * c.sg_latent_size); DG(h->zbar, c.sg_latent_size); DG(h->dzbar, c.sg_latent_size);
   long long maxL = c.sg_latent_size > c.sg_hidden_size ? c.sg_latent_size : c.sg_hidden_size;
   if (h->dis) { int m2 = c.s_latent_size > c.g_latent_size ? c.s_latent_size : c.g_latent_size; if (m2 > maxL) maxL = m2;
@@ -416,7 +446,7 @@ static void sgc_pack(sndvae_t* h) {
 }
 // forward of SGC layer l for `ns` samples starting at global sample s0; x: [ns*N, C]; result in S.y
 static int sgc_layer_fwd(sndvae_t* h, int l, const float* x, long long s0, long long ns) {
-  const PT& p = h->pt; SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+  const PT& p = h->pt; SgcDims d = sgc_dims(h, l); const SgcScratch S = sgc_view(h, l, s0);
   const int N = h->N, C = d.C, KQ = 2 * C + 2, K2 = 2 * C + 2 + d.h0, K3 = C + d.h1 + 1; const int rows = (int)(ns * N);
   const float* M1 = h->P + p.sg_M1[l];
   LAUNCH(sgc_prep_k, (unsigned)ns, 256, 0, x, h->E, d, S, N, s0);
@@ -431,7 +461,7 @@ static int sgc_layer_fwd(sndvae_t* h, int l, const float* x, long long s0, long 
 // backward of SGC layer l (activations of the chunk must be in S): dy [ns*N, h2] -> parameter gradients and,
 // when dx != NULL, dx [ns*N, C]
 static int sgc_layer_bwd(sndvae_t* h, int l, const float* x, const float* dy, float* dx, long long s0, long long ns) {
-  const PT& p = h->pt; SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
+  const PT& p = h->pt; SgcDims d = sgc_dims(h, l); const SgcScratch S = sgc_view(h, l, s0);
   const int N = h->N, C = d.C, KQ = 2 * C + 2, K2 = 2 * C + 2 + d.h0, K3 = C + d.h1 + 1; const int rows = (int)(ns * N);
   const float* M1 = h->P + p.sg_M1[l];
   int r;
@@ -468,12 +498,13 @@ static int sgc_chunk_fwd(sndvae_t* h, const sndvae_inputs* in, long long s0, lon
   const int h02 = c.sg_conv_hidden[0][2], h12 = c.sg_conv_hidden[1][2];
   const float* x0 = in->features + s0 * N * F;
   int r;
+  float* x1 = h->x1 + (h->sgc_keep ? s0 * N * h02 : 0); float* x2 = h->x2 + (h->sgc_keep ? s0 * N * h12 : 0);
   if ((r = sgc_layer_fwd(h, 0, x0, s0, ns))) return r;
-  bn_fwd(h, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->x1, h02, ns * N, h02, ACT_LRELU, 0);
-  if ((r = sgc_layer_fwd(h, 1, h->x1, s0, ns))) return r;
-  bn_fwd(h, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->x2, h12, ns * N, h12, ACT_LRELU, 0);
+  bn_fwd(h, sgc_view(h, 0, s0).y, h02, p.sg_bng[0], p.sg_bnb[0], x1, h02, ns * N, h02, ACT_LRELU, 0);
+  if ((r = sgc_layer_fwd(h, 1, x1, s0, ns))) return r;
+  bn_fwd(h, sgc_view(h, 1, s0).y, h12, p.sg_bng[1], p.sg_bnb[1], x2, h12, ns * N, h12, ACT_LRELU, 0);
   // encoder_sg BN (model.py:148; absent in model_joint.py:83)
-  bn_fwd(h, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->fsg + s0 * N * h12, h12, ns * N, h12, ACT_NONE, 0);
+  bn_fwd(h, x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->fsg + s0 * N * h12, h12, ns * N, h12, ACT_NONE, 0);
   return 0;
 }
 
@@ -905,15 +936,17 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     for (long long s0 = 0; s0 < BS; s0 += h->SC) {
       long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
       mark(h, "sgc_refwd");
-      if ((r = sgc_chunk_fwd(h, in, s0, ns))) return r;     // recompute the chunk's activations (cheap; bounds scratch to one chunk)
+      // chunk-sized scratch: recompute the chunk's activations; sgc_keep: they are still there from the forward pass
+      if (!h->sgc_keep && (r = sgc_chunk_fwd(h, in, s0, ns))) return r;
+      const float* x1 = h->x1 + (h->sgc_keep ? s0 * N * h02 : 0); const float* x2 = h->x2 + (h->sgc_keep ? s0 * N * h12 : 0);
       mark(h, "sgc_bwd_act");
       const float* x0 = in->features + s0 * N * F;
       // fsg = BN_encsg(x2); x2 = lrelu(BN_sg1(y1))
-      bn_bwd(h, h->dfsg + s0 * N * h12, h12, h->x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h12, ns * N, h12, ACT_NONE, 0);
-      bn_bwd(h, h->dxa, h12, h->S1.y, h12, p.sg_bng[1], p.sg_bnb[1], h->dxa, h12, ns * N, h12, ACT_LRELU, 0);      // dy1
-      if ((r = sgc_layer_bwd(h, 1, h->x1, h->dxa, h->dxb, s0, ns))) return r;                                       // dx1
+      bn_bwd(h, h->dfsg + s0 * N * h12, h12, x2, h12, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h12, ns * N, h12, ACT_NONE, 0);
+      bn_bwd(h, h->dxa, h12, sgc_view(h, 1, s0).y, h12, p.sg_bng[1], p.sg_bnb[1], h->dxa, h12, ns * N, h12, ACT_LRELU, 0);      // dy1
+      if ((r = sgc_layer_bwd(h, 1, x1, h->dxa, h->dxb, s0, ns))) return r;                                       // dx1
       mark(h, "sgc_bwd_act");
-      bn_bwd(h, h->dxb, h02, h->S0.y, h02, p.sg_bng[0], p.sg_bnb[0], h->dxb, h02, ns * N, h02, ACT_LRELU, 0);      // dy0
+      bn_bwd(h, h->dxb, h02, sgc_view(h, 0, s0).y, h02, p.sg_bng[0], p.sg_bnb[0], h->dxb, h02, ns * N, h02, ACT_LRELU, 0);      // dy0
       if ((r = sgc_layer_bwd(h, 0, x0, h->dxb, nullptr, s0, ns))) return r;
     }
     for (int l = 0; l < 2; ++l) {
