@@ -1044,15 +1044,21 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
   CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * 8, h->stream));
   if (backward) CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
   if ((r = decoder_prepare(h, backward))) return r;
+  // piece schedule: host mode walks the batch in chunk-sized pieces, with a half-sized first piece so that less of the
+  // first H2D copy is exposed before any kernel can start
   const long long piece = hf ? (h->Bc < Bfull ? h->Bc : Bfull) : Bfull;
-  const long long npieces = (Bfull + piece - 1) / piece;
+  std::vector<long long> pstart;
+  { long long g = 0; if (hf && piece >= 2 && Bfull > piece / 2) { pstart.push_back(0); g = piece / 2; }
+    for (; g < Bfull; g += piece) pstart.push_back(g); }
+  pstart.push_back(Bfull);
+  const long long npieces = (long long)pstart.size() - 1;
   if (hf) {
     while ((long long)h->pev.size() < 2 * npieces) { cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); h->pev.push_back(e); }
     CK(cudaEventRecord(h->ev_start, h->stream));             // staging buffers are free once earlier work on the stream is done
     CK(cudaStreamWaitEvent(h->cs, h->ev_start, 0));
     // enqueue every piece's feeds now: the copy engine runs ahead of the kernels
     for (long long pi = 0; pi < npieces; ++pi) {
-      const long long g0 = pi * piece, gn = (Bfull - g0 < piece ? Bfull - g0 : piece);
+      const long long g0 = pstart[pi], gn = pstart[pi + 1] - g0;
       sndvae_inputs hs, ds; sndvae_noise hn, dn; memset(&hs, 0, sizeof hs); memset(&ds, 0, sizeof ds); memset(&hn, 0, sizeof hn); memset(&dn, 0, sizeof dn);
       slice_io(h, g0, hf->in, hf->nz, nullptr, &hs, &hn, nullptr);
       slice_io(h, g0, in, nz, nullptr, &ds, &dn, nullptr);
@@ -1069,7 +1075,7 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
     }
   }
   for (long long pi = 0; pi < npieces; ++pi) {
-    const long long g0 = pi * piece, gn = (Bfull - g0 < piece ? Bfull - g0 : piece);
+    const long long g0 = pstart[pi], gn = pstart[pi + 1] - g0;
     sndvae_inputs vin; sndvae_noise vnz; sndvae_outputs vout; memset(&vin, 0, sizeof vin); memset(&vnz, 0, sizeof vnz); memset(&vout, 0, sizeof vout);
     slice_io(h, g0, in, nz, out, &vin, &vnz, &vout);
     if (hf) CK(cudaStreamWaitEvent(h->stream, h->pev[2 * pi], 0));

@@ -310,7 +310,7 @@ def test_host_entry_point_and_shims(built):
     gen = np.zeros((3, N, N), np.int64); ls = np.zeros(8, np.float32)
     used = {k: np.ascontiguousarray(npf[k]) for k in ("features", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth")}
     eng.train_step_host(used, {k: noise[k].numpy() for k in noise}, gen, ls)
-    np.testing.assert_allclose(ls[:7], outs[1], rtol=1e-6)
+    np.testing.assert_allclose(ls[:7], outs[1], rtol=2e-5)      # the host step sums the losses piece by piece
     assert np.array_equal(gen, outs[2])
     P2 = eng.get_params()
     for k in P1:
