@@ -67,7 +67,10 @@ typedef struct sndvae_config {
    *   SNDVAE_LOSS_CAPACITY  'disentangled_C':         mse + gamma relu(kl_sg - C) + kl_s + kl_g,
    *                          C = clip(C_max C_step / C_stop_iter (global_iter // C_step), 0, C_max)   (optimizer.py:170-172)
    *   SNDVAE_LOSS_DIP       'NED-VAE-IP':             mse + kl + beta sum_latents DIP(z_mean, lambda_od, lambda_d)  (optimizer.py:7-21,183)
-   * 'beta-TCVAE' (O(B^2 L) pairwise densities) is not built. */
+   *   SNDVAE_LOSS_TC        'beta-TCVAE':             mse + beta kl + 10 sum_latents TC(z, z_mean, z_std): the minibatch
+   *                          total-correlation estimate over all pairs of rows (optimizer.py:23-63,185-190); latent sizes <= 128
+   * DIP and TC are statistics of the batch the handle sees (per rank under data parallelism; their gradients are
+   * weighted batch_size / global_batch so that the all-reduced sum is the mean over ranks). */
   int32_t loss_variant;
   float   gamma, C_max, C_stop_iter, C_step;  /* main.py:95-98 */
   float   dip_lambda_od, dip_lambda_d;        /* 10, 100 (optimizer.py:183) */
@@ -76,6 +79,7 @@ typedef struct sndvae_config {
 #define SNDVAE_LOSS_ELBO      0
 #define SNDVAE_LOSS_CAPACITY  1
 #define SNDVAE_LOSS_DIP       2
+#define SNDVAE_LOSS_TC        3
 
 /* The eight feeds of construct_feed_dict_train (preprocessing.py:32-42) with
  * the static shapes of main.py:253-264.  fp32, C-contiguous.  `spatial` and

@@ -75,7 +75,7 @@ class Config:
     beta: float = 1.0                            # main.py:515
     num_edge_feature: int = 2                    # model_joint.py:171 (undefined flag)
     # loss variants of optimizer.py:166-190 (FLAGS.model_type selects the branch; the network is model.py's in all of them)
-    loss_variant: str = "elbo"                   # "elbo" | "disentangled_C" | "NED-VAE-IP"
+    loss_variant: str = "elbo"                   # "elbo" | "disentangled_C" | "NED-VAE-IP" | "beta-TCVAE"
     gamma: float = 100.0                         # main.py:97
     C_max: float = 100.0                         # main.py:95
     C_stop_iter: float = 1e2                     # main.py:96
@@ -500,7 +500,7 @@ def decoder(P, z, cfg: Config, mode="factored"):
     return out
 
 
-def losses(P, inp, enc, dec, cfg: Config):
+def losses(P, inp, enc, dec, cfg: Config, z=None):
     """optimizer.py:126-164,192-204.  Returns dict + overall_loss list order."""
     At = inp["adj_truth"] if cfg.model_type != "base" else inp["adj_truth"]
     lab = torch.stack([1 - At, At], dim=-1)
@@ -528,6 +528,10 @@ def losses(P, inp, enc, dec, cfg: Config):
             # optimizer.py:176-183: ELBO (KL weight 1) + beta * DIP-VAE-I regulariser on the three posterior means
             L["dip"] = sum(dip_regulariser(enc[k], cfg.dip_lambda_od, cfg.dip_lambda_d) for k in ("z_mean_s", "z_mean_g", "z_mean_sg"))
             L["cost"] = mse + (kl_sg + L["kl_s"] + L["kl_g"]) + cfg.beta * L["dip"]
+        elif cfg.loss_variant == "beta-TCVAE":
+            # optimizer.py:185-190: ELBO + 10 * minibatch total-correlation estimate of each latent group
+            L["tc"] = sum(total_correlation(z[k], enc["z_mean" + k[1:]], enc["z_std" + k[1:]]) for k in ("z_s", "z_g", "z_sg"))
+            L["cost"] = mse + cfg.beta * (kl_sg + L["kl_s"] + L["kl_g"]) + 10.0 * L["tc"]
         else:
             L["cost"] = mse + cfg.beta * (kl_sg + L["kl_s"] + L["kl_g"])
         L["overall_loss"] = [L["cost"], spatial_cost, adj_cost, node_cost, L["kl_g"], L["kl_s"], kl_sg]
@@ -546,11 +550,23 @@ def dip_regulariser(mu, lambda_od, lambda_d):
     return lambda_d * ((d - 1) ** 2).sum() + lambda_od * (off ** 2).sum()
 
 
+def total_correlation(z, z_mean, z_logstd):
+    """total_correlation() of optimizer.py:30-63 with gaussian_log_density (optimizer.py:23-28): the minibatch estimate
+    mean_j [ log sum_i prod_l q(z_jl | x_i)  -  sum_l log sum_i q(z_jl | x_i) ], constants dropped as the reference does.
+    z, z_mean, z_logstd: [rows, L]."""
+    logvar = torch.log(torch.exp(z_logstd) * torch.exp(z_logstd))                     # optimizer.py:43
+    d = z.unsqueeze(1) - z_mean.unsqueeze(0)                                          # [j, i, l]
+    lq = -0.5 * (d * d * torch.exp(-logvar).unsqueeze(0) + logvar.unsqueeze(0) + math.log(2.0 * math.pi))
+    log_qz_product = torch.logsumexp(lq, dim=1).sum(dim=1)
+    log_qz = torch.logsumexp(lq.sum(dim=2), dim=1)
+    return (log_qz - log_qz_product).mean()
+
+
 def forward(P, inp, noise, cfg: Config, mode="factored"):
     enc = encoder(P, inp, cfg, mode)
     z = get_z(enc, noise, cfg)
     dec = decoder(P, z, cfg, mode)
-    L = losses(P, inp, enc, dec, cfg)
+    L = losses(P, inp, enc, dec, cfg, z)
     return enc, z, dec, L
 
 

@@ -31,7 +31,7 @@ class Config(C.Structure):
     ]
 
 
-LOSS_VARIANTS = {"disentangled": 0, "base": 0, "disentangled_C": 1, "NED-VAE-IP": 2}
+LOSS_VARIANTS = {"disentangled": 0, "base": 0, "disentangled_C": 1, "NED-VAE-IP": 2, "beta-TCVAE": 3}
 
 
 class Inputs(C.Structure):

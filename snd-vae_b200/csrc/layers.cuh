@@ -330,3 +330,145 @@ __global__ void sub_row_k(float* __restrict__ dmu, const float* __restrict__ v, 
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < rows * L) dmu[idx] -= alpha * v[idx % L];
 }
+
+// ---- minibatch total correlation (beta-TCVAE; optimizer.py:23-63,185-190) ----------------------------------------
+// lq(j,i,l) = -0.5 ((z_jl - mu_il)^2 p_il + 2 ls_il + log 2pi),  p = exp(-2 ls)   (log-variance = log(exp(ls)^2), optimizer.py:43)
+// TC = mean_j [ lse_i sum_l lq(j,i,l)  -  sum_l lse_i lq(j,i,l) ]
+// One CTA per row of the [rows, rows] pair grid, 4 warps striding over the other index; lane owns l = lane + 32 k.
+#define TCOR_THREADS 128
+#define TCOR_LK 4                      // L <= 128
+#define TCOR_LOG2PI 1.8378770664093453f
+
+__global__ void tc_prec_k(const float* __restrict__ ls, float* __restrict__ p, long long n) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) p[idx] = expf(-2.f * ls[idx]);
+}
+
+__device__ __forceinline__ void lse_push(float& mx, float& sm, float q) {
+  if (q > mx) { sm = sm * expf(mx - q) + 1.f; mx = q; } else sm += expf(q - mx);
+}
+// The joint logit sum_l lq is ~ -1.5 L: its fp32 rounding (1e-5 at L = 100) would be the relative error of every softmax
+// weight, so the sum over the warp and the running maximum are carried in fp64 (differences are rounded to fp32 for expf).
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void lse_push_d(double& mx, float& sm, double q) {
+  if (q > mx) { sm = sm * expf((float)(mx - q)) + 1.f; mx = q; } else sm += expf((float)(q - mx));
+}
+
+// forward: lseJ[j], lseL[j, l], tc_sum += scale * (lseJ[j] - sum_l lseL[j, l])
+__global__ void __launch_bounds__(TCOR_THREADS) tc_fwd_k(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ ls,
+                                                        const float* __restrict__ p, double* __restrict__ lseJ, float* __restrict__ lseL,
+                                                        float* __restrict__ tc_sum, long long rows, int L, float scale) {
+  __shared__ float smx[4][TCOR_THREADS], ssm[4][TCOR_THREADS], sjs[4], sred[4];
+  __shared__ double sjm[4];
+  const long long j = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float zj[TCOR_LK], mx[TCOR_LK], sm[TCOR_LK];
+#pragma unroll
+  for (int k = 0; k < TCOR_LK; ++k) { const int l = lane + 32 * k; zj[k] = l < L ? z[j * L + l] : 0.f; mx[k] = -INFINITY; sm[k] = 0.f; }
+  double mJ = -INFINITY; float sJ = 0.f;
+  for (long long i = warp; i < rows; i += 4) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < TCOR_LK; ++k) {
+      const int l = lane + 32 * k;
+      if (l < L) {
+        const float d = zj[k] - mu[i * L + l];
+        const float q = -0.5f * (d * d * p[i * L + l] + 2.f * ls[i * L + l] + TCOR_LOG2PI);
+        lse_push(mx[k], sm[k], q); t += q;
+      }
+    }
+    lse_push_d(mJ, sJ, warp_sum_d((double)t));
+  }
+#pragma unroll
+  for (int k = 0; k < TCOR_LK; ++k) { smx[warp][lane + 32 * k] = mx[k]; ssm[warp][lane + 32 * k] = sm[k]; }
+  if (lane == 0) { sjm[warp] = mJ; sjs[warp] = sJ; }
+  __syncthreads();
+  const int l = threadIdx.x;
+  float v = 0.f;
+  if (l < L) {
+    float M = fmaxf(fmaxf(smx[0][l], smx[1][l]), fmaxf(smx[2][l], smx[3][l])), s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) if (ssm[w][l] > 0.f) s += ssm[w][l] * expf(smx[w][l] - M);
+    v = M + logf(s);
+    lseL[j * L + l] = v;
+  }
+  v = warp_sum(v);
+  if (lane == 0) sred[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double M = fmax(fmax(sjm[0], sjm[1]), fmax(sjm[2], sjm[3])); float s = 0.f;
+    for (int w = 0; w < 4; ++w) if (sjs[w] > 0.f) s += sjs[w] * expf((float)(sjm[w] - M));
+    const double J = M + (double)logf(s);
+    lseJ[j] = J;
+    atomicAdd(tc_sum, scale * (float)(J - (double)(sred[0] + sred[1] + sred[2] + sred[3])));
+  }
+}
+
+// backward.  d TC / d lq(j,i,l) = (W_ji - V_jil) / rows,  W = softmax_i of the joint logits, V = softmax_i per latent.
+// BY_I = false: CTA = j, sums over i  -> dz[j, l]   = scale sum_i g (-(z - mu) p)
+// BY_I = true : CTA = i, sums over j  -> dmu[i, l]  = scale sum_j g (z - mu) p,   dls[i, l] = scale sum_j g ((z - mu)^2 p - 1)
+template <bool BY_I>
+__global__ void __launch_bounds__(TCOR_THREADS) tc_bwd_k(const float* __restrict__ z, const float* __restrict__ mu, const float* __restrict__ ls,
+                                                        const float* __restrict__ p, const double* __restrict__ lseJ, const float* __restrict__ lseL,
+                                                        float* __restrict__ o0, float* __restrict__ o1, long long rows, int L, float scale) {
+  __shared__ float s0[4][TCOR_THREADS], s1[4][TCOR_THREADS];
+  const long long own = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float a[TCOR_LK], b[TCOR_LK], c[TCOR_LK], acc0[TCOR_LK], acc1[TCOR_LK];       // own row: (z, lseL) or (mu, p, ls)
+#pragma unroll
+  for (int k = 0; k < TCOR_LK; ++k) {
+    const int l = lane + 32 * k; acc0[k] = acc1[k] = 0.f; a[k] = b[k] = c[k] = 0.f;
+    if (l < L) {
+      if (BY_I) { a[k] = mu[own * L + l]; b[k] = p[own * L + l]; c[k] = ls[own * L + l]; }
+      else { a[k] = z[own * L + l]; b[k] = lseL[own * L + l]; }
+    }
+  }
+  const double ownJ = BY_I ? 0.0 : lseJ[own];
+  for (long long o = warp; o < rows; o += 4) {
+    float q[TCOR_LK], d[TCOR_LK], pp[TCOR_LK], lL[TCOR_LK], t = 0.f;
+#pragma unroll
+    for (int k = 0; k < TCOR_LK; ++k) {
+      const int l = lane + 32 * k; q[k] = d[k] = pp[k] = lL[k] = 0.f;
+      if (l < L) {
+        float lsv;
+        if (BY_I) { d[k] = z[o * L + l] - a[k]; pp[k] = b[k]; lsv = c[k]; lL[k] = lseL[o * L + l]; }
+        else { d[k] = a[k] - mu[o * L + l]; pp[k] = p[o * L + l]; lsv = ls[o * L + l]; lL[k] = b[k]; }
+        q[k] = -0.5f * (d[k] * d[k] * pp[k] + 2.f * lsv + TCOR_LOG2PI);
+        t += q[k];
+      }
+    }
+    const float W = expf((float)(warp_sum_d((double)t) - (BY_I ? lseJ[o] : ownJ)));
+#pragma unroll
+    for (int k = 0; k < TCOR_LK; ++k) {
+      const int l = lane + 32 * k;
+      if (l < L) {
+        const float g = W - expf(q[k] - lL[k]);
+        const float dp = d[k] * pp[k];
+        if (BY_I) { acc0[k] += g * dp; acc1[k] += g * (d[k] * dp - 1.f); }
+        else acc0[k] -= g * dp;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < TCOR_LK; ++k) { s0[warp][lane + 32 * k] = acc0[k]; s1[warp][lane + 32 * k] = acc1[k]; }
+  __syncthreads();
+  const int l = threadIdx.x;
+  if (l < L) {
+    o0[own * L + l] = scale * (s0[0][l] + s0[1][l] + s0[2][l] + s0[3][l]);
+    if (BY_I) o1[own * L + l] = scale * (s1[0][l] + s1[1][l] + s1[2][l] + s1[3][l]);
+  }
+}
+
+// dmu += tdz + tdmu;  dls += tdz eps exp(ls) + tdls      (z = mu + eps exp(ls))
+__global__ void tc_apply_k(float* __restrict__ dmu, float* __restrict__ dls, const float* __restrict__ tdz, const float* __restrict__ tdmu,
+                           const float* __restrict__ tdls, const float* __restrict__ eps, const float* __restrict__ ls, long long n) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const float g = tdz[idx];
+  dmu[idx] += g + tdmu[idx];
+  dls[idx] += g * eps[idx] * expf(ls[idx]) + tdls[idx];
+}

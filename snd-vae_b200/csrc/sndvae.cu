@@ -72,6 +72,7 @@ struct sndvae_handle {
   float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg, dip
   long long global_iter;               // main.py:329 (only the capacity loss reads it)
   float *dipS, *dipG[3], *dipm[3], *dipv;   // DIP regulariser: mu^T mu scratch, d reg / d cov, batch means, m G
+  float *tcp, *tcL[3], *tcd[3]; double* tcJ[3];   // total correlation: exp(-2 ls), per-latent / joint log-sum-exps, (dz, dmu, dls) scratch
   int* errflag;
   float* pinned_loss;
   // host-feed staging (sndvae_train_step_host)
@@ -365,6 +366,12 @@ static int alloc_buffers(sndvae_t* h) {
     int Lm = 0; for (int i = 0; i < 3; ++i) if (Ls[i] > Lm) Lm = Ls[i];
     DA(h->dipS, (long long)Lm * Lm); DA(h->dipv, Lm);
     for (int i = 0; i < 3; ++i) { DA(h->dipG[i], (long long)Ls[i] * Ls[i]); DA(h->dipm[i], Ls[i]); }
+  }
+  if (c.loss_variant == SNDVAE_LOSS_TC) {
+    const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
+    const long long rows[3] = {h->B, h->B, h->BS};
+    long long mx = 0; for (int i = 0; i < 3; ++i) if (rows[i] * Ls[i] > mx) mx = rows[i] * Ls[i];
+    DA(h->tcp, mx); for (int i = 0; i < 3; ++i) { DA(h->tcJ[i], rows[i]); DA(h->tcL[i], rows[i] * Ls[i]); DA(h->tcd[i], mx); }
   }
   return 0;
 }
@@ -793,12 +800,36 @@ static int dip_forward(sndvae_t* h) {
   }
   return 0;
 }
-// dmu += beta (2 / rows) (mu - m) G
-static int dip_backward(sndvae_t* h, int which, const float* mu, float* dmu, long long rows, int L) {
-  const float alpha = h->cfg.beta * 2.f / (float)rows;
+// dmu += beta (B / global batch) (2 / rows) (mu - m) G
+static int dip_backward(sndvae_t* h, int which, const float* mu, float* dmu, long long rows, int L, float gB) {
+  const float alpha = h->cfg.beta * 2.f / (float)rows * ((float)h->B / gB);
   CKB(gemm_rm(h, false, false, (int)rows, L, L, alpha, mu, L, h->dipG[which], L, 1.f, dmu, L));
   CKB(gemm_rm(h, false, false, 1, L, L, 1.f, h->dipm[which], L, h->dipG[which], L, 0.f, h->dipv, L));
   LEW(sub_row_k, rows * L, dmu, h->dipv, rows, L, alpha);
+  return 0;
+}
+
+// Total correlation of the three latent groups (optimizer.py:190): loss[6] += sum TC, log-sum-exps kept for backward.
+// O(rows^2 L) pairwise Gaussian log-densities, recomputed in each pass instead of stored ([rows, rows, L] in the reference).
+static int tc_forward(sndvae_t* h) {
+  const sndvae_config& c = h->cfg;
+  const float* zs[3] = {h->z_s, h->z_g, h->z_sg}; const float* mus[3] = {h->mu_s, h->mu_g, h->mu_sg}; const float* lss[3] = {h->ls_s, h->ls_g, h->ls_sg};
+  const long long rows[3] = {h->B, h->B, h->BS};
+  const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
+  for (int i = 0; i < 3; ++i) {
+    LEW(tc_prec_k, rows[i] * Ls[i], lss[i], h->tcp, rows[i] * Ls[i]);
+    LAUNCH(tc_fwd_k, (unsigned)rows[i], TCOR_THREADS, 0, zs[i], mus[i], lss[i], h->tcp, h->tcJ[i], h->tcL[i], h->loss + 6, rows[i], Ls[i], 1.f / (float)rows[i]);
+  }
+  return 0;
+}
+// dmu, dls += 10 (B / global batch) d TC / d (mu, ls), including the path through z = mu + eps exp(ls)
+static int tc_backward(sndvae_t* h, int which, const float* z, const float* mu, const float* ls, const float* eps, float* dmu, float* dls,
+                       long long rows, int L, float gB) {
+  const float scale = 10.f / (float)rows * ((float)h->B / gB);
+  LEW(tc_prec_k, rows * L, ls, h->tcp, rows * L);
+  LAUNCH(tc_bwd_k<false>, (unsigned)rows, TCOR_THREADS, 0, z, mu, ls, h->tcp, h->tcJ[which], h->tcL[which], h->tcd[0], (float*)nullptr, rows, L, scale);
+  LAUNCH(tc_bwd_k<true>, (unsigned)rows, TCOR_THREADS, 0, z, mu, ls, h->tcp, h->tcJ[which], h->tcL[which], h->tcd[1], h->tcd[2], rows, L, scale);
+  LEW(tc_apply_k, rows * L, dmu, dls, h->tcd[0], h->tcd[1], h->tcd[2], eps, ls, rows * L);
   return 0;
 }
 
@@ -874,14 +905,15 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   // ---- reparameterisation + KL, heads, encoders ----
   // KL weights of the loss branch: ELBO beta each; capacity loss 1, 1, gamma * 1[kl_sg > C]; DIP 1 each (optimizer.py:164,173,182)
   const int lv = c.loss_variant;
-  const float beta = lv == SNDVAE_LOSS_ELBO ? c.beta : 1.f;
+  const float beta = (lv == SNDVAE_LOSS_ELBO || lv == SNDVAE_LOSS_TC) ? c.beta : 1.f;
   const float beta_sg = lv == SNDVAE_LOSS_CAPACITY ? c.gamma : beta;
   if (h->dis) {
     // graph head
     int L = c.g_latent_size, Hh = c.g_hidden_size;
     int g0 = c.g_conv_hidden[0], g1c = c.g_conv_hidden[1];
     LEW(reparam_kl_bwd_k, B * L, h->mu_g, h->ls_g, nz->eps_g, h->dz_g, h->dmu, h->dls, B, L, 1, beta / (gB * L));
-    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 1, h->mu_g, h->dmu, B, L))) return r;
+    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 1, h->mu_g, h->dmu, B, L, gB))) return r;
+    if (lv == SNDVAE_LOSS_TC && (r = tc_backward(h, 1, h->z_g, h->mu_g, h->ls_g, nz->eps_g, h->dmu, h->dls, B, L, gB))) return r;
     if ((r = lin_bwd(h, h->hg, p.g_lin[1], h->dmu, h->dh, B, Hh, L))) return r;
     if ((r = lin_bwd(h, h->hg, p.g_lin[2], h->dls, h->gC, B, Hh, L))) return r;
     LEW(add_inplace_k, B * Hh, h->dh, h->gC, B * Hh);
@@ -900,7 +932,8 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     L = c.s_latent_size; Hh = c.s_hidden_size;
     const int* ec = c.s_channel;
     LEW(reparam_kl_bwd_k, B * L, h->mu_s, h->ls_s, nz->eps_s, h->dz_s, h->dmu, h->dls, B, L, 1, beta / (gB * L));
-    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 0, h->mu_s, h->dmu, B, L))) return r;
+    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 0, h->mu_s, h->dmu, B, L, gB))) return r;
+    if (lv == SNDVAE_LOSS_TC && (r = tc_backward(h, 0, h->z_s, h->mu_s, h->ls_s, nz->eps_s, h->dmu, h->dls, B, L, gB))) return r;
     if ((r = lin_bwd(h, h->hs, p.s_lin[1], h->dmu, h->dh, B, Hh, L))) return r;
     if ((r = lin_bwd(h, h->hs, p.s_lin[2], h->dls, h->gC, B, Hh, L))) return r;
     LEW(add_inplace_k, B * Hh, h->dh, h->gC, B * Hh);
@@ -922,7 +955,8 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
       LEW(reparam_kl_bwd_k, BS * L, h->mu_sg, h->ls_sg, nz->eps_sg, h->dzbar, h->dmu, h->dls, BS, L, S, beta_sg / (gB * S * L), h->loss + 5,
           1.f / ((float)BS * L), capacity_C(h));
     else LEW(reparam_kl_bwd_k, BS * L, h->mu_sg, h->ls_sg, nz->eps_sg, h->dzbar, h->dmu, h->dls, BS, L, S, beta_sg / (gB * S * L));
-    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 2, h->mu_sg, h->dmu, BS, L))) return r;
+    if (lv == SNDVAE_LOSS_DIP && (r = dip_backward(h, 2, h->mu_sg, h->dmu, BS, L, gB))) return r;
+    if (lv == SNDVAE_LOSS_TC && (r = tc_backward(h, 2, h->z_sg, h->mu_sg, h->ls_sg, nz->eps_sg, h->dmu, h->dls, BS, L, gB))) return r;
     if ((r = lin_bwd(h, h->hsg, p.sg_lin[1], h->dmu, h->dh, BS, Hh, L))) return r;
     float* tmp = h->dmu;   // reuse: dmu is consumed
     if ((r = lin_bwd(h, h->hsg, p.sg_lin[2], h->dls, tmp, BS, Hh, L))) return r;
@@ -998,6 +1032,7 @@ static int fetch_losses(sndvae_t* h, float* losses_host) {
     float kl_s = (float)(L[3] / (B * c.s_latent_size)), kl_g = (float)(L[4] / (B * c.g_latent_size));
     if (c.loss_variant == SNDVAE_LOSS_CAPACITY) { const float ex = kl_sg - capacity_C(h); losses_host[0] = adj + node + sp + c.gamma * (ex > 0.f ? ex : 0.f) + kl_s + kl_g; }
     else if (c.loss_variant == SNDVAE_LOSS_DIP) losses_host[0] = adj + node + sp + (kl_sg + kl_s + kl_g) + c.beta * L[6];
+    else if (c.loss_variant == SNDVAE_LOSS_TC) losses_host[0] = adj + node + sp + c.beta * (kl_sg + kl_s + kl_g) + 10.f * L[6];
     else losses_host[0] = adj + node + sp + c.beta * (kl_sg + kl_s + kl_g);
     losses_host[1] = sp; losses_host[2] = adj; losses_host[3] = node; losses_host[4] = kl_g; losses_host[5] = kl_s; losses_host[6] = kl_sg;
   } else {
@@ -1095,6 +1130,7 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
   }
   if ((r = decoder_finish(h, backward))) return r;
   if (c.loss_variant == SNDVAE_LOSS_DIP && (r = dip_forward(h))) return r;      // needs every piece's posterior means
+  if (c.loss_variant == SNDVAE_LOSS_TC && (r = tc_forward(h))) return r;        // ... and samples
   if (backward && (r = backward_rest(h, in, nz, gB))) return r;
   mark(h, "end");
   CK(cudaGetLastError());
@@ -1141,8 +1177,10 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   if (c.model_type != SNDVAE_MODEL_DISENTANGLED && c.model_type != SNDVAE_MODEL_BASE) return fail(h, SNDVAE_E_ARG, "bad model_type %d", c.model_type);
   h->dis = c.model_type == SNDVAE_MODEL_DISENTANGLED;
   h->global_iter = 0;
-  if (c.loss_variant < 0 || c.loss_variant > SNDVAE_LOSS_DIP || (c.loss_variant != SNDVAE_LOSS_ELBO && c.model_type != SNDVAE_MODEL_DISENTANGLED))
+  if (c.loss_variant < 0 || c.loss_variant > SNDVAE_LOSS_TC || (c.loss_variant != SNDVAE_LOSS_ELBO && c.model_type != SNDVAE_MODEL_DISENTANGLED))
     return fail(h, SNDVAE_E_ARG, "loss_variant %d needs the disentangled model (optimizer.py:166-190)", c.loss_variant);
+  if (c.loss_variant == SNDVAE_LOSS_TC && (c.s_latent_size > 32 * TCOR_LK || c.g_latent_size > 32 * TCOR_LK || c.sg_latent_size > 32 * TCOR_LK))
+    return fail(h, SNDVAE_E_ARG, "the total-correlation kernels take latent sizes <= %d", 32 * TCOR_LK);
   h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp); memset(&h->ytc, 0, sizeof h->ytc);
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");

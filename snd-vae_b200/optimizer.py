@@ -3,7 +3,7 @@ attribute names (optimizer.py:144-203).  The ELBO, its backward pass and the TF1
 update run inside the engine; this object only exposes the fetch handles.  `pos_weight`,
 `norm` and `labels_rel` are accepted and unused; `global_iter` is read by
 the 'disentangled_C' branch only (optimizer.py:172) and reaches the engine through the feed
-dict.  Branches built: 'disentangled', 'base', 'disentangled_C', 'NED-VAE-IP'."""
+dict.  Branches built: 'disentangled', 'base', 'disentangled_C', 'NED-VAE-IP', 'beta-TCVAE'."""
 from .flags import FLAGS
 from .session import Fetch
 
@@ -11,12 +11,12 @@ from .session import Fetch
 class OptimizerVAE(object):
     def __init__(self, preds_edge, preds_node, preds_spatial, labels_edge, labels_node, labels_spatial, labels_rel, model,
                  num_nodes, pos_weight, norm, beta, global_iter):
-        if FLAGS.model_type not in ("disentangled", "base", "disentangled_C", "NED-VAE-IP"):
-            raise ValueError(f"model_type '{FLAGS.model_type}' is not built (beta-TCVAE, geoGCN, posGCN: SURVEY section 2 rows 8, 13)")
+        if FLAGS.model_type not in ("disentangled", "base", "disentangled_C", "NED-VAE-IP", "beta-TCVAE"):
+            raise ValueError(f"model_type '{FLAGS.model_type}' is not built (geoGCN, posGCN: SURVEY section 2 row 13)")
         self.model = model
         model.optimizer = self
         model.engine.cfg.beta = float(beta)
-        if float(beta) != 1.0 and FLAGS.model_type in ("disentangled", "base"):
+        if float(beta) != 1.0 and FLAGS.model_type in ("disentangled", "base", "beta-TCVAE"):
             raise ValueError("beta is fixed at engine creation; construct the model with FLAGS beta=1 (main.py:515)")
         for name in ("opt_op", "cost", "adj_cost", "node_cost", "spatial_cost", "kl_sg", "kl_s", "kl_g"):
             setattr(self, name, Fetch(self, name))

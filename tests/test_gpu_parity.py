@@ -352,10 +352,10 @@ def test_device_synthetic_data_properties_n256(built):
     eng.close()
 
 
-@pytest.mark.parametrize("variant,it", [("disentangled_C", 0), ("disentangled_C", 40), ("NED-VAE-IP", 0)])
+@pytest.mark.parametrize("variant,it", [("disentangled_C", 0), ("disentangled_C", 40), ("NED-VAE-IP", 0), ("beta-TCVAE", 0)])
 def test_loss_variants(built, variant, it):
-    """The capacity ('disentangled_C', optimizer.py:166-174) and DIP ('NED-VAE-IP', optimizer.py:7-21,176-183) branches of
-    OptimizerVAE against the oracle: cost and every gradient.  global_iter = 0 gives C = 0 (gate open: gamma * kl_sg),
+    """The capacity ('disentangled_C', optimizer.py:166-174), DIP ('NED-VAE-IP', optimizer.py:7-21,176-183) and total-correlation
+    ('beta-TCVAE', optimizer.py:23-63,185-190) branches of OptimizerVAE against the oracle: cost and every gradient.  global_iter = 0 gives C = 0 (gate open: gamma * kl_sg),
     global_iter = 40 gives C = 40 > kl_sg (gate closed: no KL gradient into the joint head)."""
     N, B, S = 9, 5, 3
     cfg, P, inp, noise = _setup(N, B, S, "disentangled")
@@ -371,8 +371,9 @@ def test_loss_variants(built, variant, it):
     # differences of O(lambda_d) terms -- fp32 cancellation noise of a few 1e-3 of the tensor maximum against the fp64 oracle
     # (the head biases see only that noise: their exact DIP gradient is zero), so for DIP the error of a tensor is measured
     # against max(|tensor|, 1 % of the largest encoder-head gradient) instead of |tensor| alone
+    # (beta-TCVAE likewise: lq depends on z_j - mu_i only, so sum_i dmu_i + sum_j dz_j = 0 and bias-like gradients cancel)
     floor = 0.0
-    if variant == "NED-VAE-IP":
+    if variant in ("NED-VAE-IP", "beta-TCVAE"):
         floor = 1e-2 * max(grads[k].abs().max().item() for k in grads if "_lin/" in k and k.startswith("encoder/"))
     for k, v in grads.items():
         err = np.abs(gg[k].double().numpy() - v.numpy()).max() / max(v.abs().max().item(), floor, 1e-30)
@@ -398,7 +399,7 @@ def test_pipelined_host_step_equals_device_step(built, tc):
     gen = np.zeros((B, N, N), np.int64); ls = np.zeros(8, np.float32)
     used = {k: np.ascontiguousarray(inp[k].numpy()) for k in ("features", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth")}
     eng.train_step_host(used, {k: noise[k].numpy() for k in noise}, gen, ls)
-    np.testing.assert_allclose(ls[:7], r["overall_loss"], rtol=2e-6)
+    np.testing.assert_allclose(ls[:7], r["overall_loss"], rtol=2e-5)
     assert np.array_equal(gen, r["generated_adj"].cpu().numpy())
     Ph = eng.get_params(); eng.close()
     for k in Pd:

@@ -170,8 +170,9 @@ def test_golden_vectors(name):
 
 
 def test_loss_variants_of_the_oracle():
-    """optimizer.py:166-183: the capacity schedule C(global_iter), the relu gate of 'disentangled_C', and DIP() against a
-    direct numpy evaluation of its definition (covariance of the posterior means over the batch)."""
+    """optimizer.py:166-190: the capacity schedule C(global_iter), the relu gate of 'disentangled_C', DIP() against a
+    direct numpy evaluation of its definition (covariance of the posterior means over the batch), and total_correlation()
+    against plain loops."""
     cfg0 = O.Config(num_nodes=6, sampling_num=2)
     P = O.init_params(cfg0, 7, torch.float64)
     g = torch.Generator().manual_seed(1)
@@ -196,6 +197,20 @@ def test_loss_variants_of_the_oracle():
         tot += 100.0 * ((d - 1) ** 2).sum() + 10.0 * ((cov - np.diag(d)) ** 2).sum()
     assert abs(float(L["dip"]) - tot) < 1e-8 * max(tot, 1.0)
     assert abs(float(L["cost"]) - float(mse + base["kl_sg"] + base["kl_s"] + base["kl_g"] + tot)) < 1e-8 * max(tot, 1.0)
+    # 'beta-TCVAE' (optimizer.py:23-63,185-190): the minibatch total correlation against plain loops over its definition
+    cfg = O.Config(num_nodes=6, sampling_num=2, loss_variant="beta-TCVAE")
+    enc, z, _, L = O.forward(P, inp, nz, cfg)
+    tot = 0.0
+    for k in ("s", "g", "sg"):
+        zz, mu, lv = z["z_" + k].numpy(), enc["z_mean_" + k].numpy(), 2.0 * enc["z_std_" + k].numpy()
+        R, Ld = zz.shape
+        acc = 0.0
+        for j in range(R):
+            lq = np.array([[-0.5 * ((zz[j, l] - mu[i, l]) ** 2 * np.exp(-lv[i, l]) + lv[i, l] + np.log(2 * np.pi)) for l in range(Ld)] for i in range(R)])
+            acc += np.log(np.exp(lq.sum(1)).sum()) - np.log(np.exp(lq).sum(0)).sum()
+        tot += acc / R
+    assert abs(float(L["tc"]) - tot) < 1e-9 * max(abs(tot), 1.0)
+    assert abs(float(L["cost"]) - float(mse + base["kl_sg"] + base["kl_s"] + base["kl_g"] + 10.0 * tot)) < 1e-8 * max(abs(tot), 1.0)
 
 
 def test_synthetic_data_oracle_invariants():
