@@ -207,6 +207,12 @@ int sndvae_set_global_iter(sndvae_t* h, int64_t global_iter);
 int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms_host, int64_t* launches_host,
                        double* flops_host);
 
+/* InnerProductDecoder._call (layers.py:400-410): logits[b] = z[b] z[b]^T, no activation (the layer returns the raw
+ * product).  z: device [batch, num_nodes, dim] fp32, logits: device [batch, num_nodes, num_nodes] fp32; shapes are the
+ * caller's, independent of the handle's config.  NOT used by the reference's models (model.py / model_joint.py decode edges
+ * with the e2e layers); offered as a standalone operator because layers.py defines it.  tcgen05 bf16x3. */
+int sndvae_inner_product_decode(sndvae_t* h, const float* z, int64_t batch, int32_t num_nodes, int32_t dim, float* logits);
+
 /* argmax(softmax([l0,l1])) of model.py:208 on caller logits [n,2] -> int64 [n];
  * exposed so the thresholding rule can be checked bit-exactly on its own. */
 int sndvae_threshold_logits(sndvae_t* h, const float* logits, int64_t n, int64_t* out);

@@ -13,6 +13,7 @@
 #include "e2e_tc.cuh"
 #include "spectral.cuh"
 #include "synth.cuh"
+#include "zzt.cuh"
 #include <cublas_v2.h>
 #include <string>
 #include <vector>
@@ -72,6 +73,7 @@ struct sndvae_handle {
   float* loss;                         // device [8]: ce, node, spatial, kl_s, kl_g, kl_sg, dip
   long long global_iter;               // main.py:329 (only the capacity loss reads it)
   float *dipS, *dipG[3], *dipm[3], *dipv;   // DIP regulariser: mu^T mu scratch, d reg / d cov, batch means, m G
+  void* zz_planes; size_t zz_cap;           // bf16 hi / lo planes of the last sndvae_inner_product_decode call (grow-only)
   float *tcp, *tcL[3], *tcd[3]; double* tcJ[3];   // total correlation: exp(-2 ls), per-latent / joint log-sum-exps, (dz, dmu, dls) scratch
   int* errflag;
   float* pinned_loss;
@@ -1168,7 +1170,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
-  h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr;
+  h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr; h->zz_planes = nullptr; h->zz_cap = 0;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
   h->stt.used = 0; h->stt.on = getenv("SNDVAE_STAGE_TIMING") != nullptr;
   sndvae_config& c = h->cfg;
@@ -1244,6 +1246,7 @@ int sndvae_destroy(sndvae_t* h) {
   tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
   if (h->spec) { spec_destroy(h->sp); ytc_destroy(h->ytc); }
   for (void* p : h->allocs) cudaFree(p);
+  if (h->zz_planes) cudaFree(h->zz_planes);
   for (auto& e : h->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto& e : h->pev) cudaEventDestroy(e);
   if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -1252,6 +1255,14 @@ int sndvae_destroy(sndvae_t* h) {
   if (h->pinned_loss) cudaFreeHost(h->pinned_loss);
   if (h->blas) cublasDestroy(h->blas);
   delete h;
+  return 0;
+}
+
+int sndvae_inner_product_decode(sndvae_t* h, const float* z, int64_t batch, int32_t num_nodes, int32_t dim, float* logits) {
+  if (!h || !z || !logits) return SNDVAE_E_ARG;
+  if (batch < 1 || num_nodes < 1 || dim < 1) return fail(h, SNDVAE_E_ARG, "inner_product_decode: batch=%lld num_nodes=%d dim=%d", (long long)batch, num_nodes, dim);
+  if (zzt_run(z, batch, num_nodes, dim, logits, &h->zz_planes, &h->zz_cap, h->stream)) return fail(h, SNDVAE_E_CUDA, "inner_product_decode: %s", tc_last_error());
+  h->launches += 2;
   return 0;
 }
 

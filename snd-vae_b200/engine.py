@@ -281,6 +281,18 @@ class Engine:
         self._check(self.lib.sndvae_threshold_logits(self._h, lg.data_ptr(), n, out.data_ptr()))
         return out
 
+    def inner_product_decode(self, z: torch.Tensor) -> torch.Tensor:
+        """InnerProductDecoder._call (layers.py:400-410): z [B, N, h] -> z z^T [B, N, N] (raw logits).  Not part of the
+        reference's models; see include/sndvae.h."""
+        zz = z.to(device=self.device, dtype=torch.float32).contiguous()
+        if zz.dim() != 3:
+            raise ValueError("inner_product_decode expects [batch, num_nodes, dim]")
+        Bn, N, hd = zz.shape
+        out = torch.empty((Bn, N, N), dtype=torch.float32, device=self.device)
+        self._check(self.lib.sndvae_inner_product_decode(self._h, zz.data_ptr(), Bn, N, hd, out.data_ptr()))
+        torch.cuda.synchronize(self.device)      # zz must outlive the kernels on the handle's stream
+        return out
+
     def debug_read(self, name: str, n: int) -> np.ndarray:
         buf = np.empty(n, dtype=np.float32)
         got = self.lib.sndvae_debug_read(self._h, name.encode(), buf.ctypes.data, n)

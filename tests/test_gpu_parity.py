@@ -4,6 +4,7 @@ committed golden fixtures.  Tolerances (BASELINE.json north_star): losses / outp
 in fp32, gradients 1e-3 (relative to the tensor's max magnitude), thresholded adjacency
 bit-exact given the same logits.  Nothing here reads /root/reference."""
 import os
+from importlib import import_module
 
 import numpy as np
 import pytest
@@ -428,3 +429,19 @@ def test_spectral_matches_toeplitz_n256(built):
         np.testing.assert_allclose(out[name][2], out["toep"][2], rtol=2e-5)
         for k in ("decoder/e1_deconv/w1", "decoder/e1_deconv/biases1", "decoder/d_bn_e1/gamma", "decoder/e0_deconv/w1"):
             assert _relmax(out[name][1][k].numpy(), out["toep"][1][k].numpy()) < 1e-3, (name, k)
+
+
+@pytest.mark.parametrize("B,N,hd", [(3, 9, 5), (2, 100, 20), (2, 256, 40), (1, 300, 100), (2, 131, 72)])
+def test_inner_product_decoder(built, B, N, hd):
+    """InnerProductDecoder (layers.py:400-410; standalone operator, not used by the reference's models): z z^T per graph on
+    the tensor cores (bf16x3) against numpy fp64, at ragged N (tile edges) and embedding widths (K padding, two K chunks)."""
+    eng = built.Engine(built.make_config(8, 2, "disentangled", sampling_num=2))
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn((B, N, hd), generator=g, dtype=torch.float32)
+    layer = import_module("snd-vae_b200.layers").InnerProductDecoder(hd, eng)
+    out = layer(z).cpu().numpy()
+    want = np.einsum("bik,bjk->bij", z.double().numpy(), z.double().numpy())
+    assert out.shape == (B, N, N)
+    np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-4 * np.sqrt(hd))
+    assert np.abs(out - want).max() < 2e-5 * np.abs(want).max()
+    eng.close()
