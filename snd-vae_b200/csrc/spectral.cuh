@@ -261,18 +261,22 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Work item w = it NT + tid is butterfly j = w / G of channel pair cp = w % G.  NT is a multiple of G, so cp and
+// jb = tid / G are fixed per thread (computed once per kernel) and j = it (NT / G) + jb: no division in the loops, and the
+// sources address  tid + (compile-time offset) G  relative to their base.
 template <int R, int NS, int L, int G, int NT, class Src, class Dst>
-__device__ __forceinline__ void fft_pass_ct(const Src& in, const Dst& out, const float2* __restrict__ tw) {
-  constexpr int T = L / R, ITEMS = T * G, TSTEP = L / (NS * R);
+__device__ __forceinline__ void fft_pass_ct(const Src& in, const Dst& out, const float2* __restrict__ tw, const int jb, const int cp) {
+  constexpr int T = L / R, TSTEP = L / (NS * R), JS = NT / G;
+  static_assert(NT % G == 0, "the thread count must be a multiple of the channel pairs");
+  const int tid = threadIdx.x;
 #pragma unroll
-  for (int w0 = 0; w0 < ITEMS; w0 += NT) {
-    const int w = w0 + threadIdx.x;
-    if (ITEMS % NT == 0 || w < ITEMS) {
-      const int j = w / G, cp = w - j * G;
+  for (int j00 = 0; j00 < T; j00 += JS) {
+    const int j = j00 + jb;
+    if (T % JS == 0 || j < T) {
       const int k = j % NS;
       float2 v[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = in.ld(j + r * T, cp);
+      for (int r = 0; r < R; ++r) v[r] = in.ld(jb, tid, j00 + r * T);
       if (NS > 1) {
         // one table read per butterfly; the other powers by multiplication (shared-memory instructions, not FP32 issue, bound
         // these kernels): w^2 = w w, w^3 = w^2 w, w^4 = w^2 w^2, ... each at most three products deep
@@ -290,18 +294,24 @@ __device__ __forceinline__ void fft_pass_ct(const Src& in, const Dst& out, const
     }
   }
 }
-template <int G> struct SmemCT {      // [pos][G] complex buffer, compile-time pitch
+template <int G> struct SmemCT {      // [pos][G] complex buffer, compile-time pitch; loads at position jb + off, pair cp: index tid + off G
   float2* p;
-  __device__ __forceinline__ float2 ld(int pos, int cp) const { return p[pos * G + cp]; }
+  __device__ __forceinline__ float2 ld(int, int tid, int off) const { return p[tid + off * G]; }
   __device__ __forceinline__ void st(int pos, int cp, float2 v) const { p[pos * G + cp] = v; }
 };
 template <int G> struct StageSrc {    // staged fp32 line [pos][2G] in shared memory, BN + relu on the fly, zero padded past N
-  const float* s; int N; const float* sg; const float* sb;
-  __device__ __forceinline__ float2 ld(int pos, int cp) const {
-    if (pos >= N) return make_float2(0.f, 0.f);
-    float2 x = *reinterpret_cast<const float2*>(s + pos * (2 * G) + 2 * cp);
-    if (sg) { x.x = fmaxf(fmaf(x.x, sg[2 * cp], sb[2 * cp]), 0.f); x.y = fmaxf(fmaf(x.y, sg[2 * cp + 1], sb[2 * cp + 1]), 0.f); }
+  const float2* s; int N; bool bn; float gx, gy, bx, by;      // the thread's channel pair is fixed: its BN scale / shift live in registers
+  __device__ __forceinline__ float2 ld(int jb, int tid, int off) const {
+    if (jb + off >= N) return make_float2(0.f, 0.f);
+    float2 x = s[tid + off * G];
+    if (bn) { x.x = fmaxf(fmaf(x.x, gx, bx), 0.f); x.y = fmaxf(fmaf(x.y, gy, by), 0.f); }
     return x;
+  }
+};
+struct LineDstCT {                    // inverse transform tail for a fixed channel pair: base already points at the pair
+  float* base; int pstride; int N; float scale;
+  __device__ __forceinline__ void st(int pos, int, float2 v) const {
+    if (pos < N) *reinterpret_cast<float2*>(base + (size_t)(unsigned)(pos * pstride)) = make_float2(v.y * scale, v.x * scale);
   }
 };
 template <int R0, int R1, int R2, int G>
@@ -325,6 +335,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
   for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
   if (A.gam) for (int t = threadIdx.x; t < C; t += NT) { s_g[t] = A.gam[t] * BN_RS; s_b[t] = A.bet[t]; }
   const int N = A.N;
+  const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;      // this thread's channel pair and first butterfly / frequency
   const bool vec16 = ((long long)N * C) % 4 == 0;
   auto prefetch = [&](long long line) {
     if (line >= A.lines) return;
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
     } else {
       const long long l1 = line - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
       const float* base = A.in + (b * N * N + j) * C; const long long ps = (long long)N * C;
-      for (int t = threadIdx.x; t < N * G; t += NT) { const int pos = t / G, cp = t - pos * G; cp_async8(stage + 2 * t, base + pos * ps + 2 * cp); }
+      for (int pos = jb; pos < N; pos += NT / G) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
     }
   };
   prefetch(blockIdx.x);
@@ -352,29 +363,33 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
       s_b[t] = fmaf(__ldg(br + t) + 2.f * __ldg(A.b0 + t), s_g[t], __ldg(A.bet + t));
     }
     __syncthreads();                       // staged line visible; previous line's readers of bufA / bufB are done
-    StageSrc<G> src; src.s = stage; src.N = N; src.sg = A.gam ? s_g : nullptr; src.sb = s_b;
+    StageSrc<G> src; src.s = reinterpret_cast<const float2*>(stage); src.N = N; src.bn = A.gam != nullptr;
+    if (src.bn) { src.gx = s_g[2 * cp]; src.gy = s_g[2 * cp + 1]; src.bx = s_b[2 * cp]; src.by = s_b[2 * cp + 1]; }
     SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
-    fft_pass_ct<R0, 1, L, G, NT>(src, a, tw);
+    fft_pass_ct<R0, 1, L, G, NT>(src, a, tw, jb, cp);
     __syncthreads();
     prefetch(line + gridDim.x);            // the staging buffer is free: overlap the next line's loads with passes 2, 3 and the store
     cp_async_commit();
-    fft_pass_ct<R1, R0, L, G, NT>(a, b, tw);
+    fft_pass_ct<R1, R0, L, G, NT>(a, b, tw, jb, cp);
     __syncthreads();
     const float2* res = bufB;
-    if (R2) { fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(b, a, tw); __syncthreads(); res = bufA; }
-    for (int w = threadIdx.x; w < F * G; w += NT) {
-      const int f = w / G, cp = w - f * G;
+    if (R2) { fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(b, a, tw, jb, cp); __syncthreads(); res = bufA; }
+    // spectra of the pair's two real channels, split into bf16 hi / lo rows of the GEMM operand: f = jb, jb + NT / G, ...
+    __nv_bfloat16* oh = A.oh + ((long long)jb * A.RA + line) * A.KA + 2 * cp;
+    __nv_bfloat16* ol = A.ol + ((long long)jb * A.RA + line) * A.KA + 2 * cp;
+    const long long fstep = (long long)(NT / G) * A.RA * A.KA;
+#pragma unroll 4
+    for (int f = jb; f < F; f += NT / G, oh += fstep, ol += fstep) {
       const float2 z1 = res[f * G + cp], z2 = res[(f == 0 ? 0 : L - f) * G + cp];
       const float x1r = 0.5f * (z1.x + z2.x), x1i = 0.5f * (z1.y - z2.y);
       const float x2r = 0.5f * (z1.y + z2.y), x2i = 0.5f * (z2.x - z1.x);
-      const long long o = ((long long)f * A.RA + line) * A.KA + 2 * cp;
       __nv_bfloat162 h, l;
       h.x = __float2bfloat16_rn(x1r); h.y = __float2bfloat16_rn(x2r);
       l.x = __float2bfloat16_rn(x1r - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2r - __bfloat162float(h.y));
-      *reinterpret_cast<__nv_bfloat162*>(A.oh + o) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o) = l;
+      *reinterpret_cast<__nv_bfloat162*>(oh) = h; *reinterpret_cast<__nv_bfloat162*>(ol) = l;
       h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
       l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
-      *reinterpret_cast<__nv_bfloat162*>(A.oh + o + C) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o + C) = l;
+      *reinterpret_cast<__nv_bfloat162*>(oh + C) = h; *reinterpret_cast<__nv_bfloat162*>(ol + C) = l;
     }
   }
   cp_async_wait_all();
@@ -394,22 +409,22 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
   float* stage = ALIAS ? reinterpret_cast<float*>(bufB) : reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
   for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
   const float scale = 1.f / (float)L;
+  const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;      // this thread's channel pair and first butterfly / frequency
   auto prefetch = [&](long long line) {
     if (line >= A.lines) return;
-    for (int t = threadIdx.x; t < F * G; t += NT) {          // 16 bytes = two channel pairs' worth of one half row
-      const int f = t / G, x = t - f * G;
-      cp_async16(stage + (size_t)f * W + 4 * x, A.in + ((long long)f * A.RA + line) * W + 4 * x);
-    }
+    const float* src = A.in + ((long long)jb * A.RA + line) * W + 4 * cp;     // 16 bytes = two channel pairs' worth of one half row
+    const long long fstep = (long long)(NT / G) * A.RA * W;
+    for (int f = jb; f < F; f += NT / G, src += fstep) cp_async16(stage + f * W + 4 * cp, src);
   };
   prefetch(blockIdx.x);
   cp_async_commit();
   for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
     cp_async_wait_all();
     __syncthreads();
-    for (int w = threadIdx.x; w < F * G; w += NT) {
-      const int f = w / G, cp = w - f * G;
-      const float2 a = *reinterpret_cast<const float2*>(stage + (size_t)f * W + 2 * cp);
-      float2 b = *reinterpret_cast<const float2*>(stage + (size_t)f * W + C + 2 * cp);
+#pragma unroll 4
+    for (int f = jb; f < F; f += NT / G) {
+      const float2 a = *reinterpret_cast<const float2*>(stage + f * W + 2 * cp);
+      float2 b = *reinterpret_cast<const float2*>(stage + f * W + C + 2 * cp);
       const bool selfc = (f == 0) || (2 * f == L);
       if (selfc) b = make_float2(0.f, 0.f);
       bufA[f * G + cp] = make_float2(b.x + a.y, a.x - b.y);
@@ -417,21 +432,21 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
     }
     __syncthreads();
     SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
-    LineDst dst; dst.base = A.out + line * A.N * C; dst.pstride = C; dst.N = A.N; dst.scale = scale;
+    LineDstCT dst; dst.base = A.out + line * A.N * C + 2 * cp; dst.pstride = C; dst.N = A.N; dst.scale = scale;
     if (A.out1 && line >= A.lines0) {
       const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
-      dst.base = A.out1 + (b * A.N * A.N + j) * C; dst.pstride = (long long)A.N * C;
+      dst.base = A.out1 + (b * A.N * A.N + j) * C + 2 * cp; dst.pstride = A.N * C;
     }
     if (!ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
-    fft_pass_ct<R0, 1, L, G, NT>(a, b, tw);
+    fft_pass_ct<R0, 1, L, G, NT>(a, b, tw, jb, cp);
     __syncthreads();
     if (R2) {
-      fft_pass_ct<R1, R0, L, G, NT>(b, a, tw);
+      fft_pass_ct<R1, R0, L, G, NT>(b, a, tw, jb, cp);
       __syncthreads();
       if (ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
-      fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(a, dst, tw);
+      fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(a, dst, tw, jb, cp);
     } else {
-      fft_pass_ct<R1, R0, L, G, NT>(b, dst, tw);
+      fft_pass_ct<R1, R0, L, G, NT>(b, dst, tw, jb, cp);
     }
   }
   cp_async_wait_all();
