@@ -1156,18 +1156,17 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
         // instead of 32) through a private shared-memory tile; each thread then adds its TMEM row in place.
         float4* xw = reinterpret_cast<float4*>(xbuf) + (size_t)(warp - 2) * 800;      // [32 rows][25 x 16 B]
         float* etile = P.E1 + (((long long)bt * N + x) * 128 + q * 32) * N * C1;
-        int osrc[25], odst[25]; uint32_t vmask = 0;
+        const float* rtile = P.Rc + (long long)(bt * 128 + q * 32) * N * C1;          // same row pitch as the output tile
+        int odst[25]; uint32_t vmask = 0;
 #pragma unroll
         for (int t = 0; t < 25; ++t) {
           const int k = lane + 32 * t, row = k / 25, col = k - row * 25;
-          const int bg = bt * 128 + q * 32 + row;
-          osrc[t] = (bg < P.Bc ? bg : 0) * N * C1 + 4 * col;
           odst[t] = row * N * C1 + 4 * col;
-          if (bg < P.Bc) vmask |= 1u << t;
+          if (bt * 128 + q * 32 + row < P.Bc) vmask |= 1u << t;
         }
         float4 pf[25];
 #pragma unroll
-        for (int t = 0; t < 25; ++t) pf[t] = __ldg(reinterpret_cast<const float4*>(P.Rc + osrc[t]));
+        for (int t = 0; t < 25; ++t) pf[t] = (vmask >> t & 1) ? __ldg(reinterpret_cast<const float4*>(rtile + odst[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int j0 = 0; j0 < N; j0 += 2, ++pc) {
           const int slot = pc & 1;
           mbar_wait(&acc_full[slot], (pc >> 1) & 1);
@@ -1178,12 +1177,13 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
 #pragma unroll
-            for (int c0 = 0; c0 < 56; c0 += 8) {
-              uint32_t v[8], v2[8];
-              tmem_ld8(ta + jj * 64 + c0, v);
-              tmem_ld8(ta + 128 + jj * 64 + c0, v2);
+            for (int c0 = 0; c0 < 64; c0 += 16) {      // 16 columns of both accumulators per tcgen05.wait::ld (8 for the tail)
+              uint32_t v[16], v2[16];
+              if (c0 < 48) { tmem_ld16_nowait(ta + jj * 64 + c0, v); tmem_ld16_nowait(ta + 128 + jj * 64 + c0, v2); }
+              else { tmem_ld8_nowait(ta + jj * 64 + c0, v); tmem_ld8_nowait(ta + 128 + jj * 64 + c0, v2); }
+              tmem_ld_wait();
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
+              for (int u = 0; u < 8; ++u)
                 if (c0 + 2 * u < C1) xr[(jj * C1 + c0) / 2 + u] = make_float2(__uint_as_float(v[2 * u]) + __uint_as_float(v2[2 * u]),
                                                                              __uint_as_float(v[2 * u + 1]) + __uint_as_float(v2[2 * u + 1]));
             }
@@ -1200,7 +1200,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
           }
           if (j0 + 2 < N) {
 #pragma unroll
-            for (int t = 0; t < 25; ++t) pf[t] = __ldg(reinterpret_cast<const float4*>(P.Rc + osrc[t] + (j0 + 2) * C1));
+            for (int t = 0; t < 25; ++t) if (vmask >> t & 1) pf[t] = __ldg(reinterpret_cast<const float4*>(rtile + odst[t] + (j0 + 2) * C1));
           }
           __syncwarp();
         }
