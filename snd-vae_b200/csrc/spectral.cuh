@@ -1045,6 +1045,7 @@ struct YtcArgs {
   const float* Sa;       // unused (bias rows of the fixed position are added by the consumers)
   const float* b0;       // unused
   int Bc, N, C1, nbt;    // graphs in the micro-batch, nodes, channels (<= 56), graph tiles of 128
+  int JS;                // work items per (graph tile, fixed position): the swept positions are cut into JS ranges (tail balance)
 };
 #define YTC_STAGES 2
 __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant__ CUtensorMap tmAah, const __grid_constant__ CUtensorMap tmAal,
@@ -1064,7 +1065,8 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = P.N;
-  const long long nwork = (long long)P.nbt * N;
+  const int JS = P.JS, NJ = N / JS;          // NJ swept positions per work item (even when JS > 1)
+  const long long nwork = (long long)P.nbt * N * JS;
 
   if (threadIdx.x == 0) {
     mbar_init(&fix_full, 1); mbar_init(&fix_empty, 1);
@@ -1082,14 +1084,14 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
     if (lane == 0) {
       int it = 0, nw = 0;
       for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++nw) {
-        const int bt = (int)(w / N), i = (int)(w - (long long)bt * N);
+        const int bt = (int)(w / (N * JS)), rem = (int)(w - (long long)bt * N * JS), i = rem / JS, jlo = (rem - i * JS) * NJ;
         mbar_wait(&fix_empty, (nw & 1) ^ 1);
         mbar_expect_tx(&fix_full, FIX_BYTES);
         tma_load_3d(fix, &tmAah, &fix_full, 0, i, bt * 128);
         tma_load_3d(fix + A_BYTES, &tmAal, &fix_full, 0, i, bt * 128);
         tma_load_3d(fix + 2 * A_BYTES, &tmWch, &fix_full, 0, 0, i);
         tma_load_3d(fix + 2 * A_BYTES + W_BYTES, &tmWcl, &fix_full, 0, 0, i);
-        for (int j = 0; j < N; ++j, ++it) {
+        for (int j = jlo; j < jlo + NJ; ++j, ++it) {
           const int s = it % YTC_STAGES; const uint32_t ph = (it / YTC_STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = ring + (size_t)s * STAGE_BYTES;
@@ -1109,7 +1111,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
       for (long long w = blockIdx.x; w < nwork; w += gridDim.x, ++nw) {
         mbar_wait(&fix_full, nw & 1);
         tc_fence_after();
-        for (int j = 0; j < N; ++j, ++it) {
+        for (int j = 0; j < NJ; ++j, ++it) {
           const int slot = pc & 1, half = j & 1;
           if (half == 0) { mbar_wait(&acc_empty[slot], ((pc >> 1) & 1) ^ 1); tc_fence_after(); }
           const int s = it % YTC_STAGES; const uint32_t ph = (it / YTC_STAGES) & 1;
@@ -1131,7 +1133,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
             umma_bf16(td2, ah, bh, idesc, k ? 1u : 0u); umma_bf16(td2, ah, bl, idesc, 1u); umma_bf16(td2, al, bh, idesc, 1u);
           }
           umma_commit(&empty_bar[s]);
-          if (half == 1 || j == N - 1) { umma_commit(&acc_full[slot]); ++pc; }
+          if (half == 1 || j == NJ - 1) { umma_commit(&acc_full[slot]); ++pc; }
         }
         umma_commit(&fix_empty);
       }
@@ -1144,7 +1146,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
     int pc = 0;
     const bool v4 = (N % 2) == 0;
     for (long long w = blockIdx.x; w < nwork; w += gridDim.x) {
-      const int bt = (int)(w / N), x = (int)(w - (long long)bt * N);
+      const int bt = (int)(w / (N * JS)), rem = (int)(w - (long long)bt * N * JS), x = rem / JS, jlo = (rem - x * JS) * NJ;
       const int bl = q * 32 + lane, b = bt * 128 + bl;
       const bool valid = b < P.Bc;
       const int bb = valid ? b : 0;
@@ -1166,8 +1168,8 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
         }
         float4 pf[25];
 #pragma unroll
-        for (int t = 0; t < 25; ++t) pf[t] = (vmask >> t & 1) ? __ldg(reinterpret_cast<const float4*>(rtile + odst[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int j0 = 0; j0 < N; j0 += 2, ++pc) {
+        for (int t = 0; t < 25; ++t) pf[t] = (vmask >> t & 1) ? __ldg(reinterpret_cast<const float4*>(rtile + odst[t] + jlo * C1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j0 = jlo; j0 < jlo + NJ; j0 += 2, ++pc) {
           const int slot = pc & 1;
           mbar_wait(&acc_full[slot], (pc >> 1) & 1);
           tc_fence_after();
@@ -1198,7 +1200,7 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
             v.x += pf[t].x; v.y += pf[t].y; v.z += pf[t].z; v.w += pf[t].w;
             if (vmask >> t & 1) *reinterpret_cast<float4*>(etile + odst[t] + j0 * C1) = v;
           }
-          if (j0 + 2 < N) {
+          if (j0 + 2 < jlo + NJ) {
 #pragma unroll
             for (int t = 0; t < 25; ++t) if (vmask >> t & 1) pf[t] = __ldg(reinterpret_cast<const float4*>(rtile + odst[t] + (j0 + 2) * C1));
           }
@@ -1309,7 +1311,18 @@ static int ytc_run(YtcState& y, const __nv_bfloat16* ah, const __nv_bfloat16* al
   if (ytc_enc3(&mah, ah, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128) || ytc_enc3(&mal, al, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128) ||
       ytc_enc3(&mch, ch, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128) || ytc_enc3(&mcl, cl, y.Ch, N, bc, y.CS * 2, (long long)N * y.CS * 2, 64, 1, 128)) return -1;
   YtcArgs a; a.E1 = E1; a.Rc = Rc; a.Sa = Sa; a.b0 = b0; a.Bc = bc; a.N = N; a.C1 = y.C1; a.nbt = (bc + 127) / 128;
-  const long long nwork = (long long)a.nbt * N;
+  // cut the swept positions into JS ranges per (tile, fixed position) when that shortens the last wave of the persistent grid
+  // (nbt N items over 148 CTAs: 512 items = 4 waves at N = 256, 1024 half-items = 7 half-waves); each range re-loads the 48 KB
+  // fixed operands, hence the small penalty per split
+  a.JS = 1;
+  { double best = 1e30;
+    for (int js = 1; js <= 8; js *= 2) {
+      if (N % (2 * js) != 0) break;
+      const long long items = (long long)a.nbt * N * js;
+      const double cost = (double)((items + y.grid_sms - 1) / y.grid_sms) / js * (1.0 + 0.01 * js);
+      if (cost < best - 1e-9) { best = cost; a.JS = js; }
+    } }
+  const long long nwork = (long long)a.nbt * N * a.JS;
   const unsigned grid = (unsigned)(nwork < y.grid_sms ? nwork : y.grid_sms);
   if (swap) y_producer_tc_k<<<grid, 192, YTC_SMEM, st>>>(mah, mal, mch, mcl, y.mWch, y.mWcl, y.mWah, y.mWal, a);
   else y_producer_tc_k<<<grid, 192, YTC_SMEM, st>>>(mah, mal, mch, mcl, y.mWah, y.mWal, y.mWch, y.mWcl, a);
