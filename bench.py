@@ -278,6 +278,18 @@ def run_ours(args):
             del feeds_dev, keep
             torch.cuda.empty_cache()
             eng.train_step_host(hf, hn, gen, hl)                # warm (allocates the staging buffers)
+            prep_ok = 1
+        except Exception as ex:            # e.g. not enough pinnable host memory on the box
+            prep_ok = 0
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
+        if world > 1:                      # a rank that failed must not leave the others waiting in the barrier below
+            t = torch.tensor([prep_ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0 and prep_ok:
+                e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": "another rank could not stage its host feeds"}
+            prep_ok = int(t.item())
+    if not args.no_e2e and prep_ok:
+        try:
             barrier()
             t0 = time.perf_counter()
             for _ in range(args.e2e_steps):
