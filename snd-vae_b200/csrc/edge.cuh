@@ -541,7 +541,8 @@ __global__ void __launch_bounds__(256, 2) edge_epilogue_k(EpiParams P, int Bc, i
 
 // ---- elementwise variant for the spectral path: both e2e directions arrive in the [b, i, j, q] layout (plane 0 / plane 1 of
 // O12) and dO leaves in that layout only, so there is nothing to transpose: one thread per cell, grid-stride. ------------------
-__global__ void __launch_bounds__(256, 2) edge_epilogue_ew_k(EpiParams P, int Bc, int N) {
+#define EPI_EW_THREADS 128     /* three CTAs of 128 threads per SM: 168 registers per thread hold the 60 per-thread gradient sums without spilling */
+__global__ void __launch_bounds__(EPI_EW_THREADS, 2) edge_epilogue_ew_k(EpiParams P, int Bc, int N) {
   constexpr int C2 = EPI_C2;
   __shared__ float wme0[C2], wme1[C2], gsc[C2], gsh[C2], bb[C2];
   if (threadIdx.x < C2) {
@@ -566,11 +567,12 @@ __global__ void __launch_bounds__(256, 2) edge_epilogue_ew_k(EpiParams P, int Bc
       const float4* p2 = reinterpret_cast<const float4*>(P.O12 + (cells + e) * C2);
 #pragma unroll
       for (int v = 0; v < C2 / 4; ++v) {
-        const float4 x = p1[v], y = p2[v];
+        const float4 x = __ldg(p1 + v), y = __ldg(p2 + v);
         o[4 * v] = x.x + y.x + bb[4 * v]; o[4 * v + 1] = x.y + y.y + bb[4 * v + 1];
         o[4 * v + 2] = x.z + y.z + bb[4 * v + 2]; o[4 * v + 3] = x.w + y.w + bb[4 * v + 3];
       }
     }
+    const float A = P.At ? __ldg(P.At + e) : 0.f;      // fetched with the inputs, not after the stores below
     float l0 = be0, l1 = be1;
 #pragma unroll
     for (int q = 0; q < C2; ++q) {
@@ -586,7 +588,6 @@ __global__ void __launch_bounds__(256, 2) edge_epilogue_ew_k(EpiParams P, int Bc
       const float mx = fmaxf(p0, p1v);
       const float e0 = expf(p0 - mx), e1 = expf(p1v - mx);
       const float sden = e0 + e1;
-      const float A = P.At[e];
       loss += mx + logf(sden) - ((1.f - A) * p0 + A * p1v);
       d1 = m * (e1 / sden - A) * P.gscale;
     }

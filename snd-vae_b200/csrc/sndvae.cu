@@ -688,7 +688,7 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
     ep.gscale = 1.f / (gB * N * N);
     { long long ntile = (long long)bc * cdiv(N, EPI_T) * cdiv(N, EPI_T);
       unsigned grid = (unsigned)(ntile < 148 * 3 ? ntile : 148 * 3);
-      if (h->spec) LAUNCH(edge_epilogue_ew_k, 148 * 4, 256, 0, ep, bc, N);
+      if (h->spec) LAUNCH(edge_epilogue_ew_k, 148 * 6, EPI_EW_THREADS, 0, ep, bc, N);
       else LAUNCH(edge_epilogue_k, grid, 256, EPI_SMEM_BYTES, ep, bc, N); }
     if (!backward) continue;
     // backward of e2e layer 1: dgrad + wgrad
