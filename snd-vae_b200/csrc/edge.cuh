@@ -258,8 +258,17 @@ __global__ void l0_combine_planes2_k(const float* __restrict__ dY12, const float
   const float ebx = Sa[row * C1 + o] + 2.f * b0[o], eby = Sa[row * C1 + o + 1] + 2.f * b0[o + 1];
   const float gx = gam1[o] * BN_RS, gy = gam1[o + 1] * BN_RS, btx = bet1[o], bty = bet1[o + 1];
   float sgx = 0.f, sgy = 0.f, sbx = 0.f, sby = 0.f, s0x = 0.f, s0y = 0.f;
-  for (int idx = threadIdx.x; idx < N * HP; idx += blockDim.x) {
-    const int j = idx / HP;
+  // blockDim is a multiple of the channel pairs: the thread keeps its pair and walks positions j = p0, p0 + PS, ... with
+  // pointer increments only (no index division or 64-bit multiplies in the loop)
+  const int PS = blockDim.x / HP, p0 = threadIdx.x / HP;
+  const int nit = p0 < N ? (N - p0 + PS - 1) / PS : 0;
+  const int step = PS * HP;                                                    // float2 elements per iteration
+  __nv_bfloat16* ph0 = Ph + (row * N + p0) * CS + o; __nv_bfloat16* pl0 = Pl + (row * N + p0) * CS + o;
+  __nv_bfloat16* ph1 = Ph + (plane_c + (b * N + p0) * N + i) * CS + o; __nv_bfloat16* pl1 = Pl + (plane_c + (b * N + p0) * N + i) * CS + o;
+  const long long st0 = (long long)PS * CS, st1 = (long long)PS * N * CS;
+#pragma unroll 4
+  for (int it = 0; it < nit; ++it, ph0 += st0, pl0 += st0, ph1 += st1, pl1 += st1) {
+    const int idx = threadIdx.x + it * step;
     const float2 a = d0[idx], c = d1[idx], ev = E1row[idx];
     const float ex = ev.x + ebx, ey = ev.y + eby;
     const float ddx = fmaf(ex, gx, btx) > 0.f ? a.x + c.x : 0.f, ddy = fmaf(ey, gy, bty) > 0.f ? a.y + c.y : 0.f;
@@ -269,9 +278,8 @@ __global__ void l0_combine_planes2_k(const float* __restrict__ dY12, const float
     __nv_bfloat162 h, l;
     h.x = __float2bfloat16_rn(dex); h.y = __float2bfloat16_rn(dey);
     l.x = __float2bfloat16_rn(dex - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(dey - __bfloat162float(h.y));
-    const long long c0 = row * N + j, c1 = (b * N + j) * N + i;
-    *reinterpret_cast<__nv_bfloat162*>(Ph + c0 * CS + o) = h; *reinterpret_cast<__nv_bfloat162*>(Pl + c0 * CS + o) = l;
-    *reinterpret_cast<__nv_bfloat162*>(Ph + (plane_c + c1) * CS + o) = h; *reinterpret_cast<__nv_bfloat162*>(Pl + (plane_c + c1) * CS + o) = l;
+    *reinterpret_cast<__nv_bfloat162*>(ph0) = h; *reinterpret_cast<__nv_bfloat162*>(pl0) = l;
+    *reinterpret_cast<__nv_bfloat162*>(ph1) = h; *reinterpret_cast<__nv_bfloat162*>(pl1) = l;
   }
   const int nt = blockDim.x;
   sm[threadIdx.x] = sgx; sm[nt + threadIdx.x] = sgy; sm[2 * nt + threadIdx.x] = sbx; sm[3 * nt + threadIdx.x] = sby;
@@ -294,10 +302,16 @@ __global__ void rowsum_planes2_k(const __nv_bfloat16* __restrict__ Ph, const __n
   const long long row = blockIdx.x;
   const int HP = C / 2, op = threadIdx.x % HP;
   float sx = 0.f, sy = 0.f;
-  for (int idx = threadIdx.x; idx < N * HP; idx += blockDim.x) {
-    const long long a = (row * N + idx / HP) * CS + 2 * op;
-    const float2 h = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Ph + a));
-    const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Pl + a));
+  // blockDim is a multiple of the channel pairs: fixed pair per thread, positions p0, p0 + PS, ...; eight loads in flight
+  const int PS = blockDim.x / HP, p0 = threadIdx.x / HP;
+  const int nit = p0 < N ? (N - p0 + PS - 1) / PS : 0;
+  const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(Ph + (row * N + p0) * CS + 2 * op);
+  const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(Pl + (row * N + p0) * CS + 2 * op);
+  const int st = PS * CS / 2;
+#pragma unroll 4
+  for (int it = 0; it < nit; ++it) {
+    const float2 h = __bfloat1622float2(ph[(long long)it * st]);
+    const float2 l = __bfloat1622float2(pl[(long long)it * st]);
     sx += h.x + l.x; sy += h.y + l.y;
   }
   sm[threadIdx.x] = sx; sm[blockDim.x + threadIdx.x] = sy;
