@@ -145,6 +145,7 @@ struct FftFwdArgs {
   int N, C, G;            // C real channels (even), G channel pairs per shared-memory group
   const float2* tw;       // exp(-2 pi i k / L), k < L
   FftPlan pl;
+  int order;              // fast kernels: order in which the persistent grid walks the lines (LineWalk)
 };
 __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_fwd_k(FftFwdArgs A) {
   extern __shared__ __align__(16) float2 fft_sm[];
@@ -196,6 +197,8 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_fwd_k(FftFwdAr
         h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
         l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
         *reinterpret_cast<__nv_bfloat162*>(A.oh + o + A.C) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o + A.C) = l;
+        if (cp0 + cp == CP - 1) for (int e = A.C + 2; e < A.KA - 2 * (CP - 1); e += 2) {   // the row's pad: no partly written sectors
+          *reinterpret_cast<uint32_t*>(A.oh + o + e) = 0u; *reinterpret_cast<uint32_t*>(A.ol + o + e) = 0u; }
       }
     }
   }
@@ -210,6 +213,7 @@ struct FftInvArgs {
   int N, C, G;
   const float2* tw;
   FftPlan pl;
+  int order;                         // fast kernels: LineWalk order
 };
 __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvArgs A) {
   extern __shared__ __align__(16) float2 fft_sm[];
@@ -314,6 +318,23 @@ struct LineDstCT {                    // inverse transform tail for a fixed chan
     if (pos < N) *reinterpret_cast<float2*>(base + (size_t)(unsigned)(pos * pstride)) = make_float2(v.y * scale, v.x * scale);
   }
 };
+// Order in which a persistent CTA walks the lines.  The spectrum rows of a line are 80 .. 400 bytes (2.5 .. 12.5 sectors) and
+// the transposed column-line chunks 80 / 200 bytes, so two neighbouring lines share a 32-byte sector; when they are processed
+// by different CTAs that drift apart, the half-written sector leaves L2 before its other half arrives (a DRAM read-modify-write).
+//   order 0: line = cta + it * grid (the plain grid stride)
+//   order 1: each CTA takes PAIRS of neighbouring lines back to back: position o = 2 (cta + (it / 2) grid) + (it & 1), line = o
+//   order 2: pairs, and the positions run graph by graph (N row lines of graph b, then its N column lines): a tensor that
+//            both directions read (dO, 20 N^2 B per graph) is fetched from DRAM once and found in L2 the second time
+struct LineWalk {
+  long long lines, lines0; int N, order;
+  __device__ __forceinline__ long long at(long long it) const {      // >= lines: past the end (positions grow with it)
+    if (order == 0) return (long long)blockIdx.x + it * gridDim.x;
+    const long long o = 2 * ((long long)blockIdx.x + (it >> 1) * gridDim.x) + (it & 1);
+    if (order == 1 || o >= lines) return o;
+    const long long b = o / (2 * N); const int r = (int)(o - b * (2 * N));
+    return r < N ? b * N + r : lines0 + b * N + (r - N);
+  }
+};
 template <int R0, int R1, int R2, int G>
 struct FastCfg {
   static constexpr int L = R0 * R1 * (R2 ? R2 : 1), F = L / 2 + 1;
@@ -350,12 +371,20 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
     } else {
       const long long l1 = line - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
       const float* base = A.in + (b * N * N + j) * C; const long long ps = (long long)N * C;
-      for (int pos = jb; pos < N; pos += NT / G) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
+      if constexpr (G % 2 == 0) {        // a position's C floats are whole 16-byte pieces (and every chunk starts 16-byte aligned)
+        constexpr int Q = G / 2;
+        for (int t = threadIdx.x; t < N * Q; t += NT) { const int pos = t / Q, k = t - pos * Q; cp_async16(stage + pos * C + 4 * k, base + pos * ps + 4 * k); }
+      } else {
+        for (int pos = jb; pos < N; pos += NT / G) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
+      }
     }
   };
-  prefetch(blockIdx.x);
+  LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = N; walk.order = A.order;
+  long long line = walk.at(0);
+  prefetch(line);
   cp_async_commit();
-  for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
+  for (long long it = 0; line < A.lines; ++it) {
+    const long long next = walk.at(it + 1);
     cp_async_wait_all();
     if (A.gam && A.bias0 && threadIdx.x < C) {     // per-line shift: (bias + 2 b0) * g + beta  (pass 1 of the previous line is long done)
       const bool d1 = line >= A.lines0; const float* br = (d1 ? A.bias1 + (line - A.lines0) * C : A.bias0 + line * C);
@@ -368,7 +397,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
     SmemCT<G> a; a.p = bufA; SmemCT<G> b; b.p = bufB;
     fft_pass_ct<R0, 1, L, G, NT>(src, a, tw, jb, cp);
     __syncthreads();
-    prefetch(line + gridDim.x);            // the staging buffer is free: overlap the next line's loads with passes 2, 3 and the store
+    prefetch(next);                        // the staging buffer is free: overlap the next line's loads with passes 2, 3 and the store
     cp_async_commit();
     fft_pass_ct<R1, R0, L, G, NT>(a, b, tw, jb, cp);
     __syncthreads();
@@ -378,6 +407,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
     __nv_bfloat16* oh = A.oh + ((long long)jb * A.RA + line) * A.KA + 2 * cp;
     __nv_bfloat16* ol = A.ol + ((long long)jb * A.RA + line) * A.KA + 2 * cp;
     const long long fstep = (long long)(NT / G) * A.RA * A.KA;
+    const int padw = cp == G - 1 ? A.KA - 2 * C : 0;       // the last pair's thread also writes the row's pad (bf16 elements)
 #pragma unroll 4
     for (int f = jb; f < F; f += NT / G, oh += fstep, ol += fstep) {
       const float2 z1 = res[f * G + cp], z2 = res[(f == 0 ? 0 : L - f) * G + cp];
@@ -390,7 +420,12 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
       h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
       l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
       *reinterpret_cast<__nv_bfloat162*>(oh + C) = h; *reinterpret_cast<__nv_bfloat162*>(ol + C) = l;
+      // the row's pad (KA - 2C elements the tensor maps never read) is written too: a sector that leaves L2 partly written
+      // costs a DRAM read-modify-write (measured: +1.7 GB of reads per 256 graphs, one sector per row and plane)
+      if (padw == 4) { *reinterpret_cast<uint2*>(oh + C + 2) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(ol + C + 2) = make_uint2(0u, 0u); }
+      else for (int e = 0; e < padw; e += 2) { *reinterpret_cast<uint32_t*>(oh + C + 2 + e) = 0u; *reinterpret_cast<uint32_t*>(ol + C + 2 + e) = 0u; }
     }
+    line = next;
   }
   cp_async_wait_all();
 }
@@ -416,9 +451,12 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
     const long long fstep = (long long)(NT / G) * A.RA * W;
     for (int f = jb; f < F; f += NT / G, src += fstep) cp_async16(stage + f * W + 4 * cp, src);
   };
-  prefetch(blockIdx.x);
+  LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = A.N; walk.order = A.order;
+  long long line = walk.at(0);
+  prefetch(line);
   cp_async_commit();
-  for (long long line = blockIdx.x; line < A.lines; line += gridDim.x) {
+  for (long long it = 0; line < A.lines; ++it) {
+    const long long next = walk.at(it + 1);
     cp_async_wait_all();
     __syncthreads();
 #pragma unroll 4
@@ -437,17 +475,18 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
       const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
       dst.base = A.out1 + (b * A.N * A.N + j) * C + 2 * cp; dst.pstride = A.N * C;
     }
-    if (!ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
+    if (!ALIAS) { prefetch(next); cp_async_commit(); }
     fft_pass_ct<R0, 1, L, G, NT>(a, b, tw, jb, cp);
     __syncthreads();
     if (R2) {
       fft_pass_ct<R1, R0, L, G, NT>(b, a, tw, jb, cp);
       __syncthreads();
-      if (ALIAS) { prefetch(line + gridDim.x); cp_async_commit(); }
+      if (ALIAS) { prefetch(next); cp_async_commit(); }
       fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(a, dst, tw, jb, cp);
     } else {
       fft_pass_ct<R1, R0, L, G, NT>(b, dst, tw, jb, cp);
     }
+    line = next;
   }
   cp_async_wait_all();
 }
@@ -819,7 +858,7 @@ struct SpecState {
   __nv_bfloat16 *Bfh, *Bfl, *Bdh, *Bdl;  // staged weight spectra
   float* P;                              // wgrad accumulator [F][128][SP_NF]
   CUtensorMap mBfh, mBfl, mBdh, mBdl;
-  int fft_threads, fft_threads_generic, generic_only, grid_sms;
+  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv;
 };
 static size_t spec_fft_smem(int L, int G) { return (size_t)(L + 2 * (size_t)L * G) * sizeof(float2); }
 static constexpr int SPF_STAGES = 2, SPD_STAGES = 4;
@@ -903,6 +942,8 @@ static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st)
   s.fft_threads = getenv("SNDVAE_FFT_THREADS") ? atoi(getenv("SNDVAE_FFT_THREADS")) : 400;
   s.fft_threads_generic = L == 384 ? 400 : 256;
   s.generic_only = getenv("SNDVAE_FFT_GENERIC") ? 1 : 0;     // force the runtime-plan kernels (any N)
+  s.fft_order = getenv("SNDVAE_FFT_ORDER") ? atoi(getenv("SNDVAE_FFT_ORDER")) : -1;              // LineWalk order of the forward / inverse
+  s.fft_order_inv = getenv("SNDVAE_FFT_ORDER_INV") ? atoi(getenv("SNDVAE_FFT_ORDER_INV")) : -1;  // fast transforms (-1: default)
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   s.grid_sms = sms;
   s.ready = 1;
@@ -922,8 +963,8 @@ static int spec_launch_fwd_fast(SpecState& s, const FftFwdArgs& a, cudaStream_t 
   if (smem > 225 * 1024) return 1;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(spec_fft_fwd_fast_k<R0, R1, R2, G, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); attr = true; }
-  const long long want = (long long)s.grid_sms * MINB;
-  spec_fft_fwd_fast_k<R0, R1, R2, G, NT, MINB><<<(unsigned)(a.lines < want ? a.lines : want), NT, smem, st>>>(a);
+  const long long want = (long long)s.grid_sms * MINB, units = a.order ? (a.lines + 1) / 2 : a.lines;
+  spec_fft_fwd_fast_k<R0, R1, R2, G, NT, MINB><<<(unsigned)(units < want ? units : want), NT, smem, st>>>(a);
   return 0;
 }
 template <int R0, int R1, int R2, int G, int NT, int MINB, bool ALIAS>
@@ -933,8 +974,8 @@ static int spec_launch_inv_fast(SpecState& s, const FftInvArgs& a, cudaStream_t 
   if (smem > 225 * 1024) return 1;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(spec_fft_inv_fast_k<R0, R1, R2, G, NT, MINB, ALIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024); attr = true; }
-  const long long want = (long long)s.grid_sms * MINB;
-  spec_fft_inv_fast_k<R0, R1, R2, G, NT, MINB, ALIAS><<<(unsigned)(a.lines < want ? a.lines : want), NT, smem, st>>>(a);
+  const long long want = (long long)s.grid_sms * MINB, units = a.order ? (a.lines + 1) / 2 : a.lines;
+  spec_fft_inv_fast_k<R0, R1, R2, G, NT, MINB, ALIAS><<<(unsigned)(units < want ? units : want), NT, smem, st>>>(a);
   return 0;
 }
 static bool spec_plan_is(const FftPlan& pl, int r0, int r1, int r2) {
@@ -945,6 +986,9 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
                         __nv_bfloat16* oh, __nv_bfloat16* ol, int KA, int C, int G, cudaStream_t st) {
   FftFwdArgs a; a.in = in; a.in1 = in1; a.bias0 = bias0; a.bias1 = bias1; a.b0 = b0; a.lines0 = lines0; a.lines = lines; a.dir1_strided = dir1_strided; a.gam = gam; a.bet = bet; a.oh = oh; a.ol = ol;
   a.RA = s.RA; a.KA = KA; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  // a tensor read by both directions (dir1_strided == 1) is walked graph by graph, otherwise neighbouring lines in pairs (LineWalk)
+  a.order = s.fft_order >= 0 ? s.fft_order : (dir1_strided == 1 ? 2 : 1);
+  if (a.order == 2 && (lines != 2 * lines0 || lines0 % s.N != 0)) a.order = 1;
   int r = 1;
   if (!s.generic_only) {
     if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_fwd_fast<6, 8, 8, 25, 800, 1>(s, a, st) : spec_launch_fwd_fast<6, 8, 8, 25, 400, 1>(s, a, st);
@@ -961,6 +1005,8 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
 }
 static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, long long lines0, long long lines, int C, int G, cudaStream_t st) {
   FftInvArgs a; a.in = in; a.RA = s.RA; a.out = out; a.out1 = out1; a.lines0 = lines0; a.lines = lines; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  a.order = s.fft_order_inv >= 0 ? s.fft_order_inv : 0;      // measured: pairs do not help the inverse (its rows are read, not written)
+  if (a.order == 2 && (lines != 2 * lines0 || lines0 % s.N != 0)) a.order = 1;
   int r = 1;
   if (!s.generic_only) {
     if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_inv_fast<6, 8, 8, 25, 800, 1, true>(s, a, st) : spec_launch_inv_fast<6, 8, 8, 25, 400, 1, true>(s, a, st);
@@ -1013,7 +1059,26 @@ static int spec_backward(SpecState& s, const float* dO, long long rows, float* d
       spec_enc3(&bl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, SP_WKC)) return -1;
   SpecWgradArgs w; w.P = s.P; w.rows = lines; w.F = F; w.MV = 2 * s.C1; w.NV = 2 * s.C2;
   const long long kchunks = (lines + SP_WKC - 1) / SP_WKC;
-  int ks = (int)((8LL * s.grid_sms + F - 1) / F); if (ks > kchunks) ks = (int)kchunks; if (ks < 1) ks = 1;
+  // K splits per frequency: the kernel hands each CTA ceil(F KS / grid) consecutive (frequency, split) units, so KS is chosen
+  // to level the CTAs' chunk counts (F = 193 over 148 CTAs: KS = 7 left 12 SMs idle and the rest at 10 units, 91 %)
+  int ks = 1; long long best = -1;
+  for (int cand = 1; cand <= 32 && cand <= kchunks; ++cand) {
+    const long long units = (long long)F * cand, grid = units < s.grid_sms ? units : s.grid_sms;
+    const long long upc = (units + grid - 1) / grid, cper = (kchunks + cand - 1) / cand;
+    long long worst = 0;
+    for (long long c = 0; c < grid; ++c) {
+      long long load = 0;
+      for (long long u = c * upc; u < (c + 1) * upc && u < units; ++u) {
+        const long long lo = (u % cand) * cper; long long hi = lo + cper; if (hi > kchunks) hi = kchunks;
+        if (hi > lo) load += hi - lo;
+      }
+      if (load > worst) worst = load;
+    }
+    worst += 2 * upc;        // a unit's pipeline fill / drain and its share of the flush atomics, in chunk units
+    if (best < 0 || worst < best) { best = worst; ks = cand; }
+  }
+  if (getenv("SNDVAE_WGRAD_KS")) ks = atoi(getenv("SNDVAE_WGRAD_KS"));
+  if (ks > kchunks) ks = (int)kchunks; if (ks < 1) ks = 1;
   w.KS = ks;
   const long long units = (long long)F * ks;
   const unsigned wgrid = (unsigned)(units < s.grid_sms ? units : s.grid_sms);

@@ -431,6 +431,35 @@ def test_spectral_matches_toeplitz_n256(built):
             assert _relmax(out[name][1][k].numpy(), out["toep"][1][k].numpy()) < 1e-3, (name, k)
 
 
+@pytest.mark.parametrize("N,B,S,chunk", [(256, 3, 2, 2), (100, 5, 2, 0), (25, 7, 3, 3)])
+def test_fft_line_walk_orders_bit_identical(built, N, B, S, chunk):
+    """The compile-time-plan transforms walk the lines in pairs / graph by graph (LineWalk in spectral.cuh; chosen for DRAM
+    sector merging and L2 reuse of dO).  Lines are independent, so the order must not change one bit of the logits, of dO's
+    products (da, dc -> the decoder's input gradients) or of the losses; ragged micro-batches (3 = 2 + 1, 7 = 3 + 3 + 1)
+    give an odd number of graphs per walk."""
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", dtype=torch.float32)
+    out = {}
+    for name, env in (("default", None), ("plain", ("0", "0")), ("pairs", ("1", "1")), ("graphs", ("2", "2"))):
+        if env: os.environ["SNDVAE_FFT_ORDER"], os.environ["SNDVAE_FFT_ORDER_INV"] = env
+        try:
+            eng = _engine(built, N, B, S, "disentangled", 2, chunk=chunk)
+        finally:
+            os.environ.pop("SNDVAE_FFT_ORDER", None); os.environ.pop("SNDVAE_FFT_ORDER_INV", None)
+        eng.set_params(P)
+        r = eng.grads(inp, noise, fetch=("generated_adj_prob", "generated_adj"))
+        g = eng.get_grads()
+        out[name] = (r["generated_adj_prob"].cpu().numpy(), r["generated_adj"].cpu().numpy(), np.asarray(r["overall_loss"]),
+                     g["decoder/d_sg_lin1/Matrix"].numpy(), g["decoder/d_g_lin1/Matrix"].numpy())
+        eng.close()
+    for name in ("plain", "pairs", "graphs"):
+        assert np.array_equal(out[name][0], out["default"][0]), name
+        assert np.array_equal(out[name][1], out["default"][1]), name
+        # the loss sums and the weight gradients go through atomics (order of addition is not fixed): tolerance, not bits
+        np.testing.assert_allclose(out[name][2], out["default"][2], rtol=1e-6)
+        for a, b in zip(out[name][3:], out["default"][3:]):
+            assert _relmax(a, b) < 1e-5, name
+
+
 @pytest.mark.parametrize("B,N,hd", [(3, 9, 5), (2, 100, 20), (2, 256, 40), (1, 300, 100), (2, 131, 72)])
 def test_inner_product_decoder(built, B, N, hd):
     """InnerProductDecoder (layers.py:400-410; standalone operator, not used by the reference's models): z z^T per graph on

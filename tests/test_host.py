@@ -125,3 +125,46 @@ def test_data_parallel_allreduce_gloo_world2():
         p.join(timeout=300)
         assert p.exitcode == 0
     assert q.get(timeout=10) < 1e-13
+
+
+def _line_walk_at(cta, it, grid, lines, lines0, N, order):
+    """Host restatement of LineWalk::at (snd-vae_b200/csrc/spectral.cuh): the line a persistent FFT CTA transforms at its
+    it-th iteration (>= lines: past the end)."""
+    if order == 0:
+        return cta + it * grid
+    o = 2 * (cta + (it >> 1) * grid) + (it & 1)
+    if order == 1 or o >= lines:
+        return o
+    b, r = divmod(o, 2 * N)
+    return b * N + r if r < N else lines0 + b * N + (r - N)
+
+
+def test_fft_line_walk_is_a_permutation():
+    """Every order of the persistent FFT grids (plain stride, pairs of neighbouring lines, graph-major pairs) visits each
+    line exactly once for any grid size, odd / even N and ragged micro-batches, and a CTA's lines end with the first one
+    past the end (the kernels stop there)."""
+    for order in (0, 1, 2):
+        for N in (7, 8, 25, 256):
+            for graphs in (1, 2, 3, 5):
+                lines0 = graphs * N
+                lines = 2 * lines0
+                for grid_sms in (1, 3, 148, 296):
+                    units = (lines + 1) // 2 if order else lines
+                    grid = min(grid_sms, units)
+                    seen = []
+                    for cta in range(grid):
+                        it = 0
+                        line = _line_walk_at(cta, 0, grid, lines, lines0, N, order)
+                        while line < lines:
+                            seen.append(line)
+                            it += 1
+                            line = _line_walk_at(cta, it, grid, lines, lines0, N, order)
+                        # nothing valid may follow the first out-of-range position
+                        assert all(_line_walk_at(cta, it + k, grid, lines, lines0, N, order) >= lines for k in range(1, 4))
+                    assert sorted(seen) == list(range(lines)), (order, N, graphs, grid_sms)
+    # graph-major order: the row lines and the column lines of a graph are walked within 2N consecutive positions
+    N, lines0 = 8, 24
+    pos = [_line_walk_at(0, it, 1, 48, lines0, N, 2) for it in range(48)]
+    for b in range(3):
+        blk = pos[2 * N * b: 2 * N * (b + 1)]
+        assert sorted(blk) == list(range(b * N, (b + 1) * N)) + list(range(lines0 + b * N, lines0 + (b + 1) * N))
