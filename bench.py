@@ -84,10 +84,12 @@ def spectral_len(N):
 
 def spectral_bytes(N, C1=50, C2=20):
     """Compulsory HBM bytes per graph of the spectral e2e layer-1 stage (each kernel reads its inputs and writes its
-    outputs once): fft(Y) + mix + ifft(O) forward; fft(dO) + mix + ifft(dY) + wgrad backward.  DESIGN.md section 4."""
+    outputs once): fft(Y) + mix + ifft(O) forward; fft(dO) + mix + ifft(dY) + wgrad backward.  DESIGN.md section 4.
+    dO feeds the row lines AND the column lines of one launch, so it counts once (the graph-major line walk of the
+    forward transform finds the second read in L2); E1 / E1T, O12 and dY12 are separate tensors per direction."""
     F = spectral_len(N) // 2 + 1
     lines = 2 * N
-    return lines * (8 * N * (C1 + C2) + 8 * F * 5 * (C1 + C2))
+    return lines * (8 * N * (C1 + C2) + 8 * F * 5 * (C1 + C2)) - N * 4 * N * C2
 
 
 class ClockSampler:

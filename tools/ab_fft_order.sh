@@ -7,7 +7,7 @@ for cfg in "$@"; do
   set -- $cfg
   tag="f${1}_i${2}"
   SNDVAE_FFT_ORDER=$1 SNDVAE_FFT_ORDER_INV=$2 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
-    --clock-control none -k "regex:spec_fft|spec_wgrad_k" --csv --log-file gpurun_out/ab_${tag}.csv \
+    --clock-control none -k "regex:spec_fft|spec_wgrad_k|spec_gemm_k|y_producer_tc_k" --csv --log-file gpurun_out/ab_${tag}.csv \
     python bench.py --batch 256 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ab_${tag}.log 2>&1
   echo "== order fwd=$1 inv=$2 (exit $?)"
   python - gpurun_out/ab_${tag}.csv <<'EOF'
@@ -21,7 +21,7 @@ def to(v, u, base):
     f = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "byte": 1e-9, "Kbyte": 1e-6, "Mbyte": 1e-3, "Gbyte": 1.0}
     return v * f.get(u, 1.0)
 keys = list(per)
-for k in keys[-5:]:                      # the last step: fwd Y, inv O, fwd dO, inv dY, wgrad
+for k in keys[-9:]:                      # the last step: y_producer x2, fwd Y, gemm, inv O, fwd dO, gemm, inv dY, wgrad
     m = per[k]
     t = to(*m["gpu__time_duration.sum"], "ms"); rd = to(*m["dram__bytes_read.sum"], "GB"); wr = to(*m["dram__bytes_write.sum"], "GB")
     print(f"  {k[1]:46s} {t:7.3f} ms  rd {rd:6.2f} GB  wr {wr:6.2f} GB  {(rd + wr) / t:6.2f} TB/s")
