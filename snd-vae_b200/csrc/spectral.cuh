@@ -623,11 +623,7 @@ struct SpecGemmArgs {
 };
 // BN: MMA N (48 fwd / 112 dgrad); KSTEPS: 16-wide K steps actually multiplied (7 / 3); ABOX: 64-wide K boxes per plane (2 / 1);
 // WOUT: valid output columns (40 / 100).  192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue.
-// STACK: the hi and lo rows of B are neighbours in shared memory ([box][hi BN rows | lo BN rows]), so ONE N = 2 BN instruction
-// multiplies A_hi with both (D columns [0, BN) = hi.hi, [BN, 2 BN) = hi.lo) and a second, N = BN one puts A_lo B_hi into columns
-// [2 BN, 3 BN): two tcgen05.mma per K step instead of three (a short-N MMA costs ~170 cycles whatever its N); the epilogue adds
-// the three column groups.
-template <int BN, int KSTEPS, int ABOX, int WOUT, int NSTAGE, bool STACK>
+template <int BN, int KSTEPS, int ABOX, int WOUT, int NSTAGE>
 __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                                                       const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                                                       SpecGemmArgs P) {
@@ -640,10 +636,9 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
   // Two accumulators per item: a short-N tcgen05.mma into the tile the previous one is still updating costs ~170-300 cycles of
   // latency (measured), so the 3 x KSTEPS accumulates of an item are split into two independent chains (summed by the
   // epilogue) instead of one.
-  constexpr int ACC_COLS = STACK ? BN : (BN <= 64 ? 64 : 128);
-  constexpr int SLOT_COLS = STACK ? ((3 * BN + 31) / 32) * 32 : 2 * ACC_COLS;
+  constexpr int ACC_COLS = BN <= 64 ? 64 : 128;
+  constexpr int SLOT_COLS = 2 * ACC_COLS;
   constexpr int NSLOT = 512 / SLOT_COLS;
-  static_assert(!STACK || (BN % 8 == 0 && 2 * BN <= 256 && NSLOT >= 2), "stacked B: whole 8-row atoms, one instruction, two slots");
   constexpr int STG_BYTES = 128 * WOUT * 4;
   constexpr int NLD = (WOUT + 7) / 8;              // tcgen05.ld x8 per row
   static_assert(NLD * 8 <= BN, "epilogue reads past the accumulator");
@@ -681,8 +676,8 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
           mbar_expect_tx(&bfull, B_BYTES);
 #pragma unroll
           for (int b = 0; b < ABOX; ++b) {
-            tma_load_3d(sB + (STACK ? 2 * b * B_BOX : b * B_BOX), &tmBh, &bfull, 64 * b, 0, f);
-            tma_load_3d(sB + (STACK ? (2 * b + 1) * B_BOX : B_PLANE + b * B_BOX), &tmBl, &bfull, 64 * b, 0, f);
+            tma_load_3d(sB + b * B_BOX, &tmBh, &bfull, 64 * b, 0, f);
+            tma_load_3d(sB + B_PLANE + b * B_BOX, &tmBl, &bfull, 64 * b, 0, f);
           }
           cur_f = f; ++nb;
         }
@@ -717,19 +712,12 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
           const int box = ks >> 2, kk = ks & 3;
           const uint64_t ah = umma_desc(sa + box * A_BOX + kk * 32, 16, 1024, 2ull);
           const uint64_t al = umma_desc(sa + A_PLANE + box * A_BOX + kk * 32, 16, 1024, 2ull);
-          if constexpr (STACK) {
-            constexpr uint32_t idesc2 = umma_idesc(128, 2 * BN, 0, 0);
-            const uint64_t bhl = umma_desc(sb + 2 * box * B_BOX + kk * 32, 16, 1024, 2ull);     // rows [0, BN) hi, [BN, 2 BN) lo
-            umma_bf16(td, ah, bhl, idesc2, ks ? 1u : 0u);               // chain 0: [hi.hi | hi.lo]
-            umma_bf16(td + 2 * BN, al, bhl, idesc, ks ? 1u : 0u);       // chain 1: lo.hi
-          } else {
-            const uint64_t bh = umma_desc(sb + box * B_BOX + kk * 32, 16, 1024, 2ull);
-            const uint64_t bl = umma_desc(sb + B_PLANE + box * B_BOX + kk * 32, 16, 1024, 2ull);
-            // chain 0: hi.hi (+ hi.lo on even k steps);  chain 1: lo.hi (+ hi.lo on odd k steps)
-            umma_bf16(td, ah, bh, idesc, ks ? 1u : 0u);
-            umma_bf16(td + ACC_COLS, al, bh, idesc, ks ? 1u : 0u);
-            umma_bf16((ks & 1) ? td + ACC_COLS : td, ah, bl, idesc, 1u);
-          }
+          const uint64_t bh = umma_desc(sb + box * B_BOX + kk * 32, 16, 1024, 2ull);
+          const uint64_t bl = umma_desc(sb + B_PLANE + box * B_BOX + kk * 32, 16, 1024, 2ull);
+          // chain 0: hi.hi (+ hi.lo on even k steps);  chain 1: lo.hi (+ hi.lo on odd k steps)
+          umma_bf16(td, ah, bh, idesc, ks ? 1u : 0u);
+          umma_bf16(td + ACC_COLS, al, bh, idesc, ks ? 1u : 0u);
+          umma_bf16((ks & 1) ? td + ACC_COLS : td, ah, bl, idesc, 1u);
         }
         umma_commit(&empty_bar[s]);
         umma_commit(&acc_full[slot]);
@@ -756,11 +744,6 @@ __global__ void __launch_bounds__(192, 1) spec_gemm_k(const __grid_constant__ CU
         tmem_ld8(ta + ACC_COLS + c0, v2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-        if constexpr (STACK) {
-          tmem_ld8(ta + 2 * ACC_COLS + c0, v2);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
-        }
         if (c0 + 8 <= WOUT) {
           *reinterpret_cast<float4*>(srow + c0) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
           *reinterpret_cast<float4*>(srow + c0 + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
@@ -793,10 +776,11 @@ struct SpecWgradArgs {
   long long rows;        // valid lines
   int F, KS;             // frequencies, K splits per frequency
   int MV, NV;            // valid m / n extents (2*C1, 2*C2)
-  int stack;             // 1: hi / lo boxes of dO^ multiplied by ONE N = 128 instruction (2 instead of 3 tcgen05.mma per 16 lines)
+  int stages;            // TMA ring depth (<= SP_WSTAGES_MAX), 48 KB per stage
 };
 #define SP_WKC 64
 #define SP_WSTAGES 3
+#define SP_WSTAGES_MAX 4
 #define SP_WGROUP 8      /* K chunks per TMEM accumulation group: 8 * 4 k-steps * 3 passes = 96 accumulates over two chains */
 __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                                                               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
@@ -807,7 +791,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
   constexpr int HC = SP_NF / 2;                     // accumulator columns per epilogue thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[SP_WSTAGES], empty_bar[SP_WSTAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full_bar[SP_WSTAGES_MAX], empty_bar[SP_WSTAGES_MAX], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long units = (long long)P.F * P.KS;
@@ -818,11 +802,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
   const long long cper = (kchunks + P.KS - 1) / P.KS;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < SP_WSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < SP_WSTAGES_MAX; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 512);     // 2 slots x 2 accumulate chains (k-step parity) x [hh + lh | hl] x 64 columns
+  if (warp == 1) tmem_alloc(&tmem_base_s, 256);     // 2 slots x 2 accumulate chains (one per 16-line K step of a chunk) x 64 columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -835,7 +819,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
         const int f = (int)(u / P.KS), ks = (int)(u - (long long)f * P.KS);
         const long long c_lo = (long long)ks * cper; long long c_hi = c_lo + cper; if (c_hi > kchunks) c_hi = kchunks;
         for (long long ch = c_lo; ch < c_hi; ++ch, ++it) {
-          const int s = it % SP_WSTAGES; const uint32_t ph = (it / SP_WSTAGES) & 1;
+          const int s = it % P.stages; const uint32_t ph = (it / P.stages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
@@ -851,10 +835,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // The hi and lo boxes of dO^ are neighbours in the stage, so ONE N = 128 instruction multiplies A_hi with both
-      // ([hh | hl] in columns 0..63 / 64..127) and a second, N = SP_NF one adds A_lo B_hi onto the hh columns: two
-      // tcgen05.mma per 16 lines instead of three (these small-N MMAs cost ~170 cycles each whatever their N).
-      constexpr uint32_t idesc2 = umma_idesc(128, 128, 1, 1), idesc1 = umma_idesc(128, SP_NF, 1, 1);
+      constexpr uint32_t idesc = umma_idesc(128, SP_NF, 1, 1);
       int it = 0, gcount = 0;
       for (long long u = u0; u < u1; ++u) {
         const int ks = (int)(u % P.KS);
@@ -864,21 +845,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
           const int gi = i % SP_WGROUP;
           const int slot = gcount & 1;
           if (gi == 0) { mbar_wait(&acc_empty[slot], ((gcount >> 1) & 1) ^ 1); tc_fence_after(); }
-          const int s = it % SP_WSTAGES; const uint32_t ph = (it / SP_WSTAGES) & 1;
+          const int s = it % P.stages; const uint32_t ph = (it / P.stages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint32_t td0 = tmem_d + slot * 256;
-          static_assert(B_PLANE == BLK, "the lo box of dO^ must follow the hi box at the N-atom stride");
+          const uint32_t td0 = tmem_d + slot * 128;
 #pragma unroll
           for (int k = 0; k < SP_WKC / 16; ++k) {
             const uint64_t ah = umma_desc_sw128(sa + k * 2048, BLK, 1024);
             const uint64_t al = umma_desc_sw128(sa + A_PLANE + k * 2048, BLK, 1024);
-            const uint64_t bh = umma_desc_sw128(sa + 2 * A_PLANE + k * 2048, BLK, 1024);     // N atom 0 = hi box, atom 1 = lo box
-            const uint32_t td = td0 + (k & 1) * 128;     // two independent chains
-            umma_bf16(td, ah, bh, P.stack ? idesc2 : idesc1, (gi | (k >> 1)) ? 1u : 0u);
-            if (!P.stack) umma_bf16(td, ah, umma_desc_sw128(sa + 2 * A_PLANE + B_PLANE + k * 2048, BLK, 1024), idesc1, 1u);   // hi.lo onto the same columns
-            umma_bf16(td, al, bh, idesc1, 1u);
+            const uint64_t bh = umma_desc_sw128(sa + 2 * A_PLANE + k * 2048, BLK, 1024);
+            const uint64_t bl = umma_desc_sw128(sa + 2 * A_PLANE + B_PLANE + k * 2048, BLK, 1024);
+            const uint32_t td = td0 + (k & 1) * 64;      // two independent chains: no back-to-back accumulates into one tile
+            umma_bf16(td, ah, bh, idesc, (gi | (k >> 1)) ? 1u : 0u);
+            umma_bf16(td, ah, bl, idesc, 1u);
+            umma_bf16(td, al, bh, idesc, 1u);
           }
           umma_commit(&empty_bar[s]);
           if (gi == SP_WGROUP - 1 || i == nk - 1) { umma_commit(&acc_full[slot]); ++gcount; }
@@ -901,19 +882,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
         const int slot = gcount & 1;
         mbar_wait(&acc_full[slot], (gcount >> 1) & 1);
         tc_fence_after();
-        const uint32_t ta = tmem_d + slot * 256 + ((uint32_t)(q * 32) << 16) + half * HC;
+        const uint32_t ta = tmem_d + slot * 128 + ((uint32_t)(q * 32) << 16) + half * HC;
 #pragma unroll
         for (int c0 = 0; c0 < HC; c0 += 8) {
-          uint32_t v[8], v2[8], v3[8], v4[8];
-          tmem_ld8(ta + c0, v);                 // chain 0: hh + lh (+ hl when not stacked)
-          tmem_ld8(ta + 128 + c0, v3);          // chain 1
-          if (P.stack) { tmem_ld8(ta + 64 + c0, v2); tmem_ld8(ta + 192 + c0, v4); }      // hl of both chains
+          uint32_t v[8], v2[8];
+          tmem_ld8(ta + c0, v);
+          tmem_ld8(ta + 64 + c0, v2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float t = __uint_as_float(v[i]) + __uint_as_float(v3[i]);
-            if (P.stack) t += __uint_as_float(v2[i]) + __uint_as_float(v4[i]);
-            acc[c0 + i] += t;
-          }
+          for (int i = 0; i < 8; ++i) acc[c0 + i] += __uint_as_float(v[i]) + __uint_as_float(v2[i]);
         }
         tc_fence_before();
         __syncwarp();
@@ -934,7 +910,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 512); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_d, 256); }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -950,14 +926,14 @@ struct SpecState {
   __nv_bfloat16 *Bfh, *Bfl, *Bdh, *Bdl;  // staged weight spectra
   float* P;                              // wgrad accumulator [F][128][SP_NF]
   CUtensorMap mBfh, mBfl, mBdh, mBdl;
-  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv, gemm_stack, fft_inv2, wgrad_stack;
+  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv, fft_inv2, wgrad_stages;
 };
 static size_t spec_fft_smem(int L, int G) { return (size_t)(L + 2 * (size_t)L * G) * sizeof(float2); }
 static constexpr int SPF_STAGES = 2, SPD_STAGES = 4;
 static size_t spec_gemm_smem(int BN, int ABOX, int WOUT, int NSTAGE) {
   return (size_t)NSTAGE * 2 * ABOX * 128 * 64 * 2 + (size_t)2 * ABOX * BN * 64 * 2 + (size_t)128 * WOUT * 4 + 1024;
 }
-static const size_t SP_WGRAD_SMEM = (size_t)SP_WSTAGES * (2 * 2 * SP_WKC * 128 + 2 * SP_WKC * 128) + 1024;
+static const size_t SP_WGRAD_SMEM = (size_t)SP_WSTAGES_MAX * (2 * 2 * SP_WKC * 128 + 2 * SP_WKC * 128) + 1024;
 
 // transform length: smallest even L in {2^a, 3 * 2^a} with L >= N + q, q = N - 1 - (N-1)/2
 static int spec_pick_L(int N) {
@@ -1028,16 +1004,15 @@ static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st)
       spec_enc3(&s.mBdl, s.Bdl, 64, SP_ND, F, 64 * 2, (long long)SP_ND * 64 * 2, 64, SP_ND)) return -1;
   cudaFuncSetAttribute(spec_fft_fwd_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(spec_fft_inv_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES));
-  cudaFuncSetAttribute(spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES));
-  cudaFuncSetAttribute(spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES));
-  s.fft_inv2 = getenv("SNDVAE_FFT_INV2") ? atoi(getenv("SNDVAE_FFT_INV2")) : 0;
-  s.gemm_stack = getenv("SNDVAE_GEMM_STACK") ? atoi(getenv("SNDVAE_GEMM_STACK")) : 0;
-  s.wgrad_stack = getenv("SNDVAE_WGRAD_STACK") ? atoi(getenv("SNDVAE_WGRAD_STACK")) : 0;
+  cudaFuncSetAttribute(spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES));
+  cudaFuncSetAttribute(spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES));
   cudaFuncSetAttribute(spec_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_WGRAD_SMEM);
   s.fft_threads = getenv("SNDVAE_FFT_THREADS") ? atoi(getenv("SNDVAE_FFT_THREADS")) : 400;
   s.fft_threads_generic = L == 384 ? 400 : 256;
   s.generic_only = getenv("SNDVAE_FFT_GENERIC") ? 1 : 0;     // force the runtime-plan kernels (any N)
+  s.fft_inv2 = getenv("SNDVAE_FFT_INV2") ? atoi(getenv("SNDVAE_FFT_INV2")) : 1;
+  s.wgrad_stages = getenv("SNDVAE_WGRAD_STAGES") ? atoi(getenv("SNDVAE_WGRAD_STAGES")) : SP_WSTAGES;
+  if (s.wgrad_stages < 2 || s.wgrad_stages > SP_WSTAGES_MAX) s.wgrad_stages = SP_WSTAGES;
   s.fft_order = getenv("SNDVAE_FFT_ORDER") ? atoi(getenv("SNDVAE_FFT_ORDER")) : -1;              // LineWalk order of the forward / inverse
   s.fft_order_inv = getenv("SNDVAE_FFT_ORDER_INV") ? atoi(getenv("SNDVAE_FFT_ORDER_INV")) : -1;  // fast transforms (-1: default)
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1115,11 +1090,11 @@ static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, 
   a.order = s.fft_order_inv >= 0 ? s.fft_order_inv : 0;      // measured: pairs do not help the inverse (its rows are read, not written)
   if (a.order == 2 && (lines != 2 * lines0 || lines0 % s.N != 0)) a.order = 1;
   int r = 1;
-  if (!s.generic_only && s.fft_inv2) {      // 3-pass plans: split staging, extension fused into pass 1
-    if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = spec_launch_inv_fast2<6, 8, 8, 25, 400, 1>(s, a, st);
-    else if (spec_plan_is(s.pl, 6, 8, 8) && C == 20) r = spec_launch_inv_fast2<6, 8, 8, 10, 320, 2>(s, a, st);
-    else if (spec_plan_is(s.pl, 6, 8, 4) && C == 50) r = spec_launch_inv_fast2<6, 8, 4, 25, 400, 2>(s, a, st);
-    else if (spec_plan_is(s.pl, 6, 8, 4) && C == 20) r = spec_launch_inv_fast2<6, 8, 4, 10, 160, 4>(s, a, st);
+  if (!s.generic_only && s.fft_inv2 && C == 50) {      // 3-pass plans at G = 25: split staging, extension fused into pass 1
+    // (measured at N = 256: 4.88 -> 4.69 ms per 256 graphs; the G = 10 transforms, which have room for a separate staging
+    // buffer anyway, lose 3 % with it and stay on the first form)
+    if (spec_plan_is(s.pl, 6, 8, 8)) r = spec_launch_inv_fast2<6, 8, 8, 25, 400, 1>(s, a, st);
+    else if (spec_plan_is(s.pl, 6, 8, 4)) r = spec_launch_inv_fast2<6, 8, 4, 25, 400, 2>(s, a, st);
     if (r == 0) return tc_check_launch("spec_fft_inv_fast2_k");
   }
   if (!s.generic_only) {
@@ -1147,8 +1122,7 @@ static int spec_forward(SpecState& s, const float* E1, const float* E1T, const f
       spec_enc3(&al, s.Al, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, 128)) return -1;
   SpecGemmArgs g; g.out = s.Oc; g.RA = s.RA; g.rows = lines; g.F = F; g.MT = (int)((lines + 127) / 128); g.items = (long long)F * g.MT;
   const unsigned grid = (unsigned)(g.items < s.grid_sms ? g.items : s.grid_sms);
-  if (s.gemm_stack) spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES, true><<<grid, 192, spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES), st>>>(ah, al, s.mBfh, s.mBfl, g);
-  else spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES, false><<<grid, 192, spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES), st>>>(ah, al, s.mBfh, s.mBfl, g);
+  spec_gemm_k<SP_NF, 7, 2, 40, SPF_STAGES><<<grid, 192, spec_gemm_smem(SP_NF, 2, 40, SPF_STAGES), st>>>(ah, al, s.mBfh, s.mBfl, g);
   if (tc_check_launch("spec_gemm_k(fwd)")) return -1;
   // both directions land in the [b, i, j, C2] layout: O12 plane 0 = row products, plane 1 = column products
   return spec_fft_inv(s, s.Oc, O12, O12 + rows * s.N * s.C2, rows, lines, s.C2, s.G2, st);
@@ -1163,7 +1137,7 @@ static int spec_backward(SpecState& s, const float* dO, long long rows, float* d
       spec_enc3(&dl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, 128)) return -1;
   SpecGemmArgs g; g.out = s.dYc; g.RA = s.RA; g.rows = lines; g.F = F; g.MT = (int)((lines + 127) / 128); g.items = (long long)F * g.MT;
   const unsigned grid = (unsigned)(g.items < s.grid_sms ? g.items : s.grid_sms);
-  spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES, false><<<grid, 192, spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES), st>>>(dh, dl, s.mBdh, s.mBdl, g);
+  spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES><<<grid, 192, spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES), st>>>(dh, dl, s.mBdh, s.mBdl, g);
   if (tc_check_launch("spec_gemm_k(dgrad)")) return -1;
   if (spec_fft_inv(s, s.dYc, dY12, dY12 + rows * s.N * s.C1, rows, lines, s.C1, s.G1, st)) return -1;
   // wgrad: MN-major views of the same planes, 32 lines per K chunk
@@ -1172,7 +1146,7 @@ static int spec_backward(SpecState& s, const float* dO, long long rows, float* d
       spec_enc3(&al, s.Al, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, SP_WKC) ||
       spec_enc3(&bh, s.Dh, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, SP_WKC) ||
       spec_enc3(&bl, s.Dl, 2 * s.C2, lines, F, SP_KA2 * 2, s.RA * SP_KA2 * 2, 64, SP_WKC)) return -1;
-  SpecWgradArgs w; w.P = s.P; w.rows = lines; w.F = F; w.MV = 2 * s.C1; w.NV = 2 * s.C2; w.stack = s.wgrad_stack;
+  SpecWgradArgs w; w.P = s.P; w.rows = lines; w.F = F; w.MV = 2 * s.C1; w.NV = 2 * s.C2; w.stages = s.wgrad_stages;
   const long long kchunks = (lines + SP_WKC - 1) / SP_WKC;
   // K splits per frequency: the kernel hands each CTA ceil(F KS / grid) consecutive (frequency, split) units, so KS is chosen
   // to level the CTAs' chunk counts (F = 193 over 148 CTAs: KS = 7 left 12 SMs idle and the rest at 10 units, 91 %)
@@ -1226,7 +1200,6 @@ struct YtcArgs {
   const float* b0;       // unused
   int Bc, N, C1, nbt;    // graphs in the micro-batch, nodes, channels (<= 56), graph tiles of 128
   int JS;                // work items per (graph tile, fixed position): the swept positions are cut into JS ranges (tail balance)
-  int stack;             // 1: hi / lo weight tiles multiplied by ONE N = 128 instruction (12 instead of 18 tcgen05.mma per position)
 };
 #define YTC_STAGES 2
 __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant__ CUtensorMap tmAah, const __grid_constant__ CUtensorMap tmAal,
@@ -1299,28 +1272,6 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t ss = smem_u32(ring + (size_t)s * STAGE_BYTES);
-          if (P.stack) {
-            // the lo weight tile follows the hi tile in shared memory (64 rows each), so an N = 128 instruction gives
-            // [A_hi W_hi | A_hi W_lo] in columns [0, 64) / [64, 128) of the position's accumulator and an N = 64 one adds
-            // A_lo W_hi onto the first half; both parts (a, c) accumulate into the same 128 columns
-            constexpr uint32_t idesc2 = umma_idesc(128, 128, 0, 0);
-            const uint32_t tp = tmem_d + slot * 256 + half * 128;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {      // a[., i] . WSa[j]
-              const uint64_t ah = umma_desc(sf + k * 32, 16, 1024, 2ull), al = umma_desc(sf + A_BYTES + k * 32, 16, 1024, 2ull);
-              const uint64_t bhl = umma_desc(ss + 2 * A_BYTES + k * 32, 16, 1024, 2ull);
-              umma_bf16(tp, ah, bhl, idesc2, k ? 1u : 0u); umma_bf16(tp, al, bhl, idesc, 1u);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {      // c[., j] . WSc[i]
-              const uint64_t ah = umma_desc(ss + k * 32, 16, 1024, 2ull), al = umma_desc(ss + A_BYTES + k * 32, 16, 1024, 2ull);
-              const uint64_t bhl = umma_desc(sf + 2 * A_BYTES + k * 32, 16, 1024, 2ull);
-              umma_bf16(tp, ah, bhl, idesc2, 1u); umma_bf16(tp, al, bhl, idesc, 1u);
-            }
-            umma_commit(&empty_bar[s]);
-            if (half == 1 || j == NJ - 1) { umma_commit(&acc_full[slot]); ++pc; }
-            continue;
-          }
           // two independent accumulate chains per position (a-part / c-part), summed by the epilogue
           const uint32_t td = tmem_d + slot * 256 + half * 64, td2 = td + 128;
 #pragma unroll
@@ -1381,12 +1332,11 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
           // TMEM columns [0, 50) and [64, 114) -> floats [0, 50) and [50, 100) of this graph's row of the tile
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
-            const uint32_t t1 = ta + (P.stack ? jj * 128 : jj * 64), t2 = ta + (P.stack ? jj * 128 + 64 : 128 + jj * 64);
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 16) {      // 16 columns of both accumulators per tcgen05.wait::ld (8 for the tail)
               uint32_t v[16], v2[16];
-              if (c0 < 48) { tmem_ld16_nowait(t1 + c0, v); tmem_ld16_nowait(t2 + c0, v2); }
-              else { tmem_ld8_nowait(t1 + c0, v); tmem_ld8_nowait(t2 + c0, v2); }
+              if (c0 < 48) { tmem_ld16_nowait(ta + jj * 64 + c0, v); tmem_ld16_nowait(ta + 128 + jj * 64 + c0, v2); }
+              else { tmem_ld8_nowait(ta + jj * 64 + c0, v); tmem_ld8_nowait(ta + 128 + jj * 64 + c0, v2); }
               tmem_ld_wait();
 #pragma unroll
               for (int u = 0; u < 8; ++u)
@@ -1430,8 +1380,8 @@ __global__ void __launch_bounds__(192, 1) y_producer_tc_k(const __grid_constant_
 #pragma unroll
             for (int c0 = 0; c0 < 56; c0 += 8) {
               uint32_t v[8], v2[8];
-              tmem_ld8(ta + (P.stack ? jj * 128 : jj * 64) + c0, v);
-              tmem_ld8(ta + (P.stack ? jj * 128 + 64 : 128 + jj * 64) + c0, v2);
+              tmem_ld8(ta + jj * 64 + c0, v);
+              tmem_ld8(ta + 128 + jj * 64 + c0, v2);
 #pragma unroll
               for (int u = 0; u < 8; ++u) if (c0 + u < C1) r[jj * C1 + c0 + u] += __uint_as_float(v[u]) + __uint_as_float(v2[u]);
             }
@@ -1518,7 +1468,6 @@ static int ytc_run(YtcState& y, const __nv_bfloat16* ah, const __nv_bfloat16* al
   // cut the swept positions into JS ranges per (tile, fixed position) when that shortens the last wave of the persistent grid
   // (nbt N items over 148 CTAs: 512 items = 4 waves at N = 256, 1024 half-items = 7 half-waves); each range re-loads the 48 KB
   // fixed operands, hence the small penalty per split
-  a.stack = getenv("SNDVAE_YTC_STACK") ? atoi(getenv("SNDVAE_YTC_STACK")) : 0;
   a.JS = 1;
   { double best = 1e30;
     for (int js = 1; js <= 8; js *= 2) {
