@@ -332,8 +332,8 @@ def run_ours(args):
             "bound": "hbm", "kernel": "e2e layer-1 spectral stage: spec_fft_fwd_fast_k, spec_gemm_k (fwd, dgrad), spec_fft_inv_fast_k, spec_wgrad_k",
             "achieved": ach_bw, "peak": peak_bw, "unit": "GB/s", "frac": (ach_bw / peak_bw) if ach_bw else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of the seven launches, one `ncu --set full` capture of a 256-graph
-            # micro-batch (profiles/ncu_r1_final_b256.txt): 96.1 GB per 256 graphs = 375 MB per graph, scaled to the graphs of one step
-            "traffic": (375e6 * B) if N == 256 else None, "traffic_per_graph": 375e6 if N == 256 else None,
+            # micro-batch (profiles/ncu_r1_final_b256.txt): 92.5 GB per 256 graphs = 361 MB per graph, scaled to the graphs of one step
+            "traffic": (361e6 * B) if N == 256 else None, "traffic_per_graph": 361e6 if N == 256 else None,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
             "algorithmic_bytes_per_graph": per_graph,
             "direct_form_equivalent_tflops": achieved,
