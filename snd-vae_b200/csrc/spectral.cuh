@@ -256,6 +256,9 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvAr
 
 // ---- specialised transforms: compile-time plan (R0 x R1 x R2), all G channel pairs of a line in one group, next line prefetched
 //      with cp.async into a staging buffer while the current one is transformed --------------------------------------------
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
 }
@@ -348,18 +351,24 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
   using Cfg = FastCfg<R0, R1, R2, G>;
   constexpr int L = Cfg::L, F = Cfg::F, C = 2 * G;
   extern __shared__ __align__(16) uint8_t fsm[];
-  __shared__ float s_g[2 * G], s_b[2 * G];
+  __shared__ float s_g[2 * G], s_b[2 * G], s_raw[2 * G];
   float2* tw = reinterpret_cast<float2*>(fsm);
   float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
   float2* bufB = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
   float* stage = reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
   for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
   if (A.gam) for (int t = threadIdx.x; t < C; t += NT) { s_g[t] = A.gam[t] * BN_RS; s_b[t] = A.bet[t]; }
+  // thread t < C owns channel t of the per-line shift (bias + 2 b0) g + beta: the constant part lives in a register and the line's
+  // bias element arrives with the line (cp.async by the same thread, so no barrier between its arrival and its use)
+  const bool shifter = A.gam && A.bias0 && threadIdx.x < C;
+  float sh_g = 0.f, sh_c = 0.f;
+  if (shifter) { sh_g = A.gam[threadIdx.x] * BN_RS; sh_c = fmaf(2.f * A.b0[threadIdx.x], sh_g, A.bet[threadIdx.x]); }
   const int N = A.N;
   const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;      // this thread's channel pair and first butterfly / frequency
   const bool vec16 = ((long long)N * C) % 4 == 0;
   auto prefetch = [&](long long line) {
     if (line >= A.lines) return;
+    if (shifter) cp_async4(s_raw + threadIdx.x, (line >= A.lines0 ? A.bias1 + (line - A.lines0) * C : A.bias0 + line * C) + threadIdx.x);
     if (line < A.lines0 || A.dir1_strided != 1) {
       const float* base = A.in + line * N * C;
       if (A.dir1_strided == 2) {
@@ -386,11 +395,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
   for (long long it = 0; line < A.lines; ++it) {
     const long long next = walk.at(it + 1);
     cp_async_wait_all();
-    if (A.gam && A.bias0 && threadIdx.x < C) {     // per-line shift: (bias + 2 b0) * g + beta  (pass 1 of the previous line is long done)
-      const bool d1 = line >= A.lines0; const float* br = (d1 ? A.bias1 + (line - A.lines0) * C : A.bias0 + line * C);
-      const int t = threadIdx.x;
-      s_b[t] = fmaf(__ldg(br + t) + 2.f * __ldg(A.b0 + t), s_g[t], __ldg(A.bet + t));
-    }
+    if (shifter) s_b[threadIdx.x] = fmaf(s_raw[threadIdx.x], sh_g, sh_c);     // pass 1 of the previous line is long done with s_b
     __syncthreads();                       // staged line visible; previous line's readers of bufA / bufB are done
     StageSrc<G> src; src.s = reinterpret_cast<const float2*>(stage); src.N = N; src.bn = A.gam != nullptr;
     if (src.bn) { src.gx = s_g[2 * cp]; src.gy = s_g[2 * cp + 1]; src.bx = s_b[2 * cp]; src.by = s_b[2 * cp + 1]; }
