@@ -194,6 +194,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     N, B, S = args.nodes, args.batch, (args.sampling if args.model != "base" else 1)
 
