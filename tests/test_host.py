@@ -168,3 +168,25 @@ def test_fft_line_walk_is_a_permutation():
     for b in range(3):
         blk = pos[2 * N * b: 2 * N * (b + 1)]
         assert sorted(blk) == list(range(b * N, (b + 1) * N)) + list(range(lines0 + b * N, lines0 + (b + 1) * N))
+
+
+def test_bench_compulsory_bytes_of_the_spectral_stage():
+    """bench.py's roofline numerator: per graph, 2N lines, each transform / GEMM reads its inputs and writes
+    its outputs once; dO feeds the row and the column lines of one launch and counts once."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    N, C1, C2 = 256, 50, 20
+    L = bench.spectral_len(N)
+    assert L == 384 and L >= N + (N - 1 - (N - 1) // 2)
+    F = L // 2 + 1
+    lines = 2 * N
+    fwd_y = lines * (4 * N * C1 + 8 * F * C1)                 # fp32 line in, bf16 hi + lo [re | im] rows out
+    gemm_f = lines * (8 * F * C1 + 8 * F * C2)                # planes in, fp32 [re | im] rows out
+    inv_o = lines * (8 * F * C2 + 4 * N * C2)
+    fwd_do = N * 4 * N * C2 + lines * 8 * F * C2              # dO once
+    gemm_d = lines * (8 * F * C2 + 8 * F * C1)
+    inv_dy = lines * (8 * F * C1 + 4 * N * C1)
+    wgrad = lines * (8 * F * C1 + 8 * F * C2)
+    assert bench.spectral_bytes(N) == fwd_y + gemm_f + inv_o + fwd_do + gemm_d + inv_dy + wgrad
