@@ -315,6 +315,77 @@ def sgc_factored(adj, x, rel, P, name):
     return lrelu(torch.cat([x, m2s], dim=2)) @ M3 + b3
 
 
+def sgc3d_literal(adj, x, rel, P, name):
+    """SpatialGraphConvolution_3D (layers.py:200-277; the `protein` / `mnist` branch, model.py:139-140), materialising the
+    [B,N,N,N,N,4C+5] tensor as TF does.  Parameters name/Matrix0..3, name/bias0..3 (layers.py:210-225).  SURVEY 8(f) N4:
+    restatement only -- no CUDA path yet; `tests/test_oracle.py::test_sgc3d_factored_equals_literal` pins the two forms
+    against each other."""
+    Bn, N, C = x.shape
+    r = rel.reshape(Bn, N, N, 1)
+    e = lambda t, shape: t.reshape(shape).expand(Bn, N, N, N, N, t.shape[-1])
+    m4 = torch.cat([e(x, (Bn, N, 1, 1, 1, C)), e(x, (Bn, 1, N, 1, 1, C)), e(x, (Bn, 1, 1, N, 1, C)), e(x, (Bn, 1, 1, 1, N, C)),
+                    e(r, (Bn, N, N, 1, 1, 1)), e(r, (Bn, 1, N, N, 1, 1)), e(r, (Bn, 1, 1, N, N, 1)),
+                    e(r, (Bn, N, 1, N, 1, 1)), e(r, (Bn, N, 1, 1, N, 1))], dim=-1)         # i, j, k, p; r_ij, r_jk, r_kp, r_ik, r_ip
+    m4 = lrelu(m4) @ P[name + "/Matrix0"] + P[name + "/bias0"]                            # [B,N,N,N,N,h0]
+    adj4 = (adj.reshape(Bn, N, N, 1, 1) * adj.reshape(Bn, 1, N, N, 1) * adj.reshape(Bn, 1, 1, N, N))   # A_ij A_jk A_kp
+    m4s = (m4 * adj4.unsqueeze(-1)).sum(dim=4)                                            # sum over p
+    f = lambda t, shape: t.reshape(shape).expand(Bn, N, N, N, t.shape[-1])
+    m3 = torch.cat([f(x, (Bn, N, 1, 1, C)), f(x, (Bn, 1, N, 1, C)), f(x, (Bn, 1, 1, N, C)),
+                    f(r, (Bn, N, N, 1, 1)), f(r, (Bn, 1, N, N, 1)), f(r, (Bn, N, 1, N, 1)), m4s], dim=-1)
+    m3 = lrelu(m3) @ P[name + "/Matrix1"] + P[name + "/bias1"]                            # [B,N,N,N,h1]
+    adj3 = adj.reshape(Bn, N, N, 1) * adj.reshape(Bn, 1, N, N)                            # A_ij A_jk
+    m3s = (m3 * adj3.unsqueeze(-1)).sum(dim=3)                                            # sum over k
+    m2 = torch.cat([x.reshape(Bn, N, 1, C).expand(Bn, N, N, C), x.reshape(Bn, 1, N, C).expand(Bn, N, N, C), r, m3s], dim=3)
+    m2 = lrelu(m2) @ P[name + "/Matrix2"] + P[name + "/bias2"]                            # [B,N,N,h2]
+    m2s = (m2 * adj.unsqueeze(-1)).sum(dim=2)                                             # sum over j
+    return lrelu(torch.cat([x, m2s], dim=2)) @ P[name + "/Matrix3"] + P[name + "/bias3"]
+
+
+def sgc3d_factored(adj, x, rel, P, name):
+    """Exact factorisation of layers.py:228-273: the p-sum is linear (no nonlinearity between Matrix0 and it), so the N^4
+    tensor collapses to per-(i,j,k) closed forms; the k-sum keeps one N^3 h0 pointwise term (lrelu of m4_sum), the j-sum one
+    N^2 h1 term.  With deg_k = sum_p A_kp, s_k = sum_p A_kp phi(r_kp), G_ik = sum_p A_kp phi(r_ip):
+      m4s_ijk = A_ij A_jk [deg_k (P0_i + Q0_j + R0_k + phi(r_ij) a1 + phi(r_jk) a2 + phi(r_ik) a4 + b0) + (A S0)_k + s_k a3 + G_ik a5]
+      m3s_ij  = A_ij [deg_j (P1_i + Q1_j + phi(r_ij) c1 + b1) + (A R1)_j + s_j c2 + G_ij c3 + (sum_k A_jk phi(m4s_ijk)) M1e]
+      m2s_i   = deg_i (U_i + b2) + (A V)_i + s_i M2c + (sum_j A_ij phi(m3s_ij)) M2d"""
+    Bn, N, C = x.shape
+    M0, b0 = P[name + "/Matrix0"], P[name + "/bias0"]
+    M1, b1 = P[name + "/Matrix1"], P[name + "/bias1"]
+    M2, b2 = P[name + "/Matrix2"], P[name + "/bias2"]
+    M3, b3 = P[name + "/Matrix3"], P[name + "/bias3"]
+    h0, h1 = M0.shape[1], M1.shape[1]
+    px = lrelu(x)
+    pr = lrelu(rel.reshape(Bn, N, N))
+    deg = adj.sum(dim=2)
+    s = (adj * pr).sum(dim=2)
+    G = pr @ adj.transpose(1, 2)
+    # level 4 -> m4s [B,N,N,N,h0]
+    P0, Q0, R0, S0 = px @ M0[0:C], px @ M0[C:2 * C], px @ M0[2 * C:3 * C], px @ M0[3 * C:4 * C]
+    a1, a2, a3, a4, a5 = (M0[4 * C + t] for t in range(5))                                # r_ij, r_jk, r_kp, r_ik, r_ip
+    AS = adj @ S0
+    inner4 = (deg.reshape(Bn, 1, 1, N, 1) * (P0.reshape(Bn, N, 1, 1, h0) + Q0.reshape(Bn, 1, N, 1, h0) + R0.reshape(Bn, 1, 1, N, h0)
+                                             + pr.reshape(Bn, N, N, 1, 1) * a1 + pr.reshape(Bn, 1, N, N, 1) * a2
+                                             + pr.reshape(Bn, N, 1, N, 1) * a4 + b0)
+              + AS.reshape(Bn, 1, 1, N, h0) + s.reshape(Bn, 1, 1, N, 1) * a3 + G.reshape(Bn, N, 1, N, 1) * a5)
+    adj3 = adj.reshape(Bn, N, N, 1) * adj.reshape(Bn, 1, N, N)
+    m4s = adj3.unsqueeze(-1) * inner4
+    # level 3 -> m3s [B,N,N,h1]
+    P1, Q1, R1 = px @ M1[0:C], px @ M1[C:2 * C], px @ M1[2 * C:3 * C]
+    c1, c2, c3 = M1[3 * C], M1[3 * C + 1], M1[3 * C + 2]                                  # r_ij, r_jk, r_ik
+    M1e = M1[3 * C + 3:]
+    T3 = (adj.reshape(Bn, 1, N, N, 1) * lrelu(m4s)).sum(dim=3)                            # sum_k A_jk phi(m4s_ijk)
+    AR = adj @ R1
+    inner3 = (deg.reshape(Bn, 1, N, 1) * (P1.reshape(Bn, N, 1, h1) + Q1.reshape(Bn, 1, N, h1) + pr.unsqueeze(-1) * c1 + b1)
+              + AR.reshape(Bn, 1, N, h1) + s.reshape(Bn, 1, N, 1) * c2 + G.unsqueeze(-1) * c3 + T3 @ M1e)
+    m3s = adj.unsqueeze(-1) * inner3
+    # level 2 -> m2s [B,N,h2]
+    M2a, M2b, M2c, M2d = M2[0:C], M2[C:2 * C], M2[2 * C], M2[2 * C + 1:]
+    U, V = px @ M2a, px @ M2b
+    T2 = (adj.unsqueeze(-1) * lrelu(m3s)).sum(dim=2)
+    m2s = deg.unsqueeze(-1) * (U + b2) + adj @ V + s.unsqueeze(-1) * M2c + T2 @ M2d
+    return lrelu(torch.cat([x, m2s], dim=2)) @ M3 + b3
+
+
 def e2e_literal(x, w1, bias):
     """layers.py:431-450 via conv2d on a materialised [B,N,N,C] tensor.
     w1: [1,N,C,O].  TF SAME padding: pad_before=(k-1)//2."""

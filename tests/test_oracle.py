@@ -238,3 +238,29 @@ def test_synthetic_data_oracle_invariants():
     assert (d["rel"][S:2 * S, ..., 0] == rel[1]).all() and (d["features"][S:2 * S] == d["feature_truth"][1]).all()
     again = synth.synth_inputs(N, B, S, 1, 2, seed=99)
     assert all((again[k] == d[k]).all() for k in d)
+
+
+def test_sgc3d_factored_equals_literal():
+    """the 3-hop SpatialGraphConvolution_3D (layers.py:200-277).  The literal restatement materialises the
+    [B,N,N,N,N,4C+5] tensor; the factored one removes the N^4 term exactly (the p-sum is linear).  fp64, real-valued
+    adjacency (the identity does not need 0/1 entries), forests and dense graphs."""
+    torch.manual_seed(3)
+    Bn, N, C = 2, 5, 3
+    h = (4, 5, 6, 7)
+    name = "sg3"
+    P = {name + "/Matrix0": 0.3 * torch.randn(4 * C + 5, h[0], dtype=torch.float64), name + "/bias0": 0.1 * torch.randn(h[0], dtype=torch.float64),
+         name + "/Matrix1": 0.3 * torch.randn(3 * C + 3 + h[0], h[1], dtype=torch.float64), name + "/bias1": 0.1 * torch.randn(h[1], dtype=torch.float64),
+         name + "/Matrix2": 0.3 * torch.randn(2 * C + 1 + h[1], h[2], dtype=torch.float64), name + "/bias2": 0.1 * torch.randn(h[2], dtype=torch.float64),
+         name + "/Matrix3": 0.3 * torch.randn(C + h[2], h[3], dtype=torch.float64), name + "/bias3": 0.1 * torch.randn(h[3], dtype=torch.float64)}
+    x = torch.randn(Bn, N, C, dtype=torch.float64)
+    rel = torch.randn(Bn, N, N, 1, dtype=torch.float64)           # signed: exercises both branches of the leaky relu
+    for kind in ("dense_real", "binary"):
+        adj = torch.randn(Bn, N, N, dtype=torch.float64) if kind == "dense_real" else (torch.rand(Bn, N, N) < 0.4).double()
+        lit = O.sgc3d_literal(adj, x, rel, P, name)
+        fac = O.sgc3d_factored(adj, x, rel, P, name)
+        assert lit.shape == (Bn, N, h[3])
+        assert (lit - fac).abs().max().item() < 1e-11 * max(1.0, lit.abs().max().item()), kind
+    # with no edges only the x -> Matrix3 path is left
+    out = O.sgc3d_factored(torch.zeros(Bn, N, N, dtype=torch.float64), x, rel, P, name)
+    ref = O.lrelu(torch.cat([x, torch.zeros(Bn, N, h[2], dtype=torch.float64)], dim=2)) @ P[name + "/Matrix3"] + P[name + "/bias3"]
+    assert torch.allclose(out, ref, atol=1e-14)
