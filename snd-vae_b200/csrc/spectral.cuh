@@ -215,6 +215,7 @@ struct FftInvArgs {
   const float2* tw;
   FftPlan pl;
   int order;                         // fast kernels: LineWalk order
+  int bulk;                          // fast kernels: spectrum rows staged by one cp.async.bulk per row (experimental, off by default)
 };
 __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvArgs A) {
   extern __shared__ __align__(16) float2 fft_sm[];
@@ -462,10 +463,19 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
   float2* bufB = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
   float* stage = ALIAS ? reinterpret_cast<float*>(bufB) : reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
   for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  __shared__ uint64_t stage_bar;             // bulk staging: completion of a line's F row copies
+  if (threadIdx.x == 0) { mbar_init(&stage_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t stage_ph = 0;
   const float scale = 1.f / (float)L;
   const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;      // this thread's channel pair and first butterfly / frequency
   auto prefetch = [&](long long line) {
     if (line >= A.lines) return;
+    if (A.bulk) {                              // one bulk copy per spectrum row (W floats), all counted on one mbarrier phase
+      if (threadIdx.x == 0) mbar_expect_tx(&stage_bar, (uint32_t)(F * W * 4));
+      for (int f = threadIdx.x; f < F; f += NT) bulk_load(stage + f * W, A.in + ((long long)f * A.RA + line) * W, (uint32_t)(W * 4), &stage_bar);
+      return;
+    }
     const float* src = A.in + ((long long)jb * A.RA + line) * W + 4 * cp;     // 16 bytes = two channel pairs' worth of one half row
     const long long fstep = (long long)(NT / G) * A.RA * W;
     for (int f = jb; f < F; f += NT / G, src += fstep) cp_async16(stage + f * W + 4 * cp, src);
@@ -477,6 +487,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
   for (long long it = 0; line < A.lines; ++it) {
     const long long next = walk.at(it + 1);
     cp_async_wait_all();
+    if (A.bulk) { mbar_wait(&stage_bar, stage_ph); stage_ph ^= 1; }
     __syncthreads();
 #pragma unroll 4
     for (int f = jb; f < F; f += NT / G) {
@@ -539,10 +550,22 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast2_k(FftInvArgs A) {
   float2* bq = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
   float* h1 = reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);         // rows [0, FH)
   for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  __shared__ uint64_t stage_bar;             // bulk staging: completion of a line's F row copies (both halves on one phase)
+  if (threadIdx.x == 0) { mbar_init(&stage_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t stage_ph = 0;
   const float scale = 1.f / (float)L;
   const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;
   auto prefetch = [&](long long line, int part, float* h2) {      // 16 bytes = two channel pairs' worth of one half row
     if (line >= A.lines) return;
+    if (A.bulk) {
+      // the phase's single arrival (with the whole line's byte count) comes with part 0; part 1's copies only complete bytes
+      if (part == 0 && threadIdx.x == 0) mbar_expect_tx(&stage_bar, (uint32_t)(F * W * 4));
+      const int f0 = part == 0 ? 0 : FH, f1 = part == 0 ? FH : F;
+      for (int f = f0 + threadIdx.x; f < f1; f += NT)
+        bulk_load((part == 0 ? h1 + f * W : h2 + (f - FH) * W), A.in + ((long long)f * A.RA + line) * W, (uint32_t)(W * 4), &stage_bar);
+      return;
+    }
     const float* src = A.in + ((long long)jb * A.RA + line) * W + 4 * cp;
     const long long fstep = (long long)JS * A.RA * W;
     for (int f = jb; f < F; f += JS, src += fstep)
@@ -555,6 +578,7 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast2_k(FftInvArgs A) {
   for (long long it = 0; line < A.lines; ++it) {
     const long long next = walk.at(it + 1);
     cp_async_wait_all();
+    if (A.bulk) { mbar_wait(&stage_bar, stage_ph); stage_ph ^= 1; }
     __syncthreads();                       // both halves of the line have landed; the previous line's last pass is done with bq
     SpecHalfSrc<L, G> src; src.h1 = h1; src.h2 = reinterpret_cast<const float*>(bp); src.cp = cp;
     SmemCT<G> p; p.p = bp; SmemCT<G> q; q.p = bq;
@@ -945,7 +969,7 @@ struct SpecState {
   __nv_bfloat16 *Bfh, *Bfl, *Bdh, *Bdl;  // staged weight spectra
   float* P;                              // wgrad accumulator [F][128][SP_NF]
   CUtensorMap mBfh, mBfl, mBdh, mBdl;
-  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv, fft_inv2, wgrad_stages, fft_bulk;
+  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv, fft_inv2, wgrad_stages, fft_bulk, fft_bulk_inv;
 };
 static size_t spec_fft_smem(int L, int G) { return (size_t)(L + 2 * (size_t)L * G) * sizeof(float2); }
 static constexpr int SPF_STAGES = 2, SPD_STAGES = 4;
@@ -1030,6 +1054,7 @@ static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st)
   s.fft_threads_generic = L == 384 ? 400 : 256;
   s.generic_only = getenv("SNDVAE_FFT_GENERIC") ? 1 : 0;     // force the runtime-plan kernels (any N)
   s.fft_bulk = getenv("SNDVAE_FFT_BULK") ? atoi(getenv("SNDVAE_FFT_BULK")) : 1;      // measured: forward Y 5.67 -> 5.54 ms per 256 graphs
+  s.fft_bulk_inv = getenv("SNDVAE_FFT_BULK_INV") ? atoi(getenv("SNDVAE_FFT_BULK_INV")) : 0;    // not measured yet (round 2)
   s.fft_inv2 = getenv("SNDVAE_FFT_INV2") ? atoi(getenv("SNDVAE_FFT_INV2")) : 1;
   s.wgrad_stages = getenv("SNDVAE_WGRAD_STAGES") ? atoi(getenv("SNDVAE_WGRAD_STAGES")) : SP_WSTAGES;
   if (s.wgrad_stages < 2 || s.wgrad_stages > SP_WSTAGES_MAX) s.wgrad_stages = SP_WSTAGES;
@@ -1108,6 +1133,7 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
 }
 static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, long long lines0, long long lines, int C, int G, cudaStream_t st) {
   FftInvArgs a; a.in = in; a.RA = s.RA; a.out = out; a.out1 = out1; a.lines0 = lines0; a.lines = lines; a.N = s.N; a.C = C; a.G = G; a.tw = s.tw; a.pl = s.pl;
+  a.bulk = s.fft_bulk_inv;
   a.order = s.fft_order_inv >= 0 ? s.fft_order_inv : 0;      // measured: pairs do not help the inverse (its rows are read, not written)
   if (a.order == 2 && (lines != 2 * lines0 || lines0 % s.N != 0)) a.order = 1;
   int r = 1;
