@@ -17,6 +17,10 @@
 //     spec_fft_inv_k   fp32 spectra -> inverse Stockham FFT -> fp32 lines (first N positions, scaled by 1/L)
 //     spec_wgrad_k     per frequency  P[f] += A^[f]^T . dO^[f]  (MN-major operands straight from the same planes),
 //                      two-level (TMEM -> fp32 register) accumulation, atomics into P; folded to dw1 once per step
+// spec_fft_fwd_k / spec_fft_inv_k are the runtime-plan transforms (any N); where a compile-time plan matches (L = 384,
+// 192, 48 with 50 / 20 channels) the persistent spec_fft_fwd_fast_k / spec_fft_inv_fast_k / spec_fft_inv_fast2_k run
+// instead: next line staged asynchronously (cp.async / cp.async.bulk) while the current one is transformed, fixed channel
+// pair per thread, lines walked in an order chosen for DRAM sector merging and L2 reuse (LineWalk).
 #pragma once
 #include "e2e_tc.cuh"
 #include <vector>
@@ -830,7 +834,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
                                                               SpecWgradArgs P) {
   constexpr int BLK = SP_WKC * 128;                 // one [SP_WKC k-rows x 64 mn] box
   constexpr int A_PLANE = 2 * BLK, B_PLANE = BLK;
-  constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // 24 KB
+  constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // 48 KB (35.8 KB of them real data: 100 / 40 of the 128 / 64 columns)
   constexpr int HC = SP_NF / 2;                     // accumulator columns per epilogue thread
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -1187,7 +1191,7 @@ static int spec_backward(SpecState& s, const float* dO, long long rows, float* d
   spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES><<<grid, 192, spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES), st>>>(dh, dl, s.mBdh, s.mBdl, g);
   if (tc_check_launch("spec_gemm_k(dgrad)")) return -1;
   if (spec_fft_inv(s, s.dYc, dY12, dY12 + rows * s.N * s.C1, rows, lines, s.C1, s.G1, st)) return -1;
-  // wgrad: MN-major views of the same planes, 32 lines per K chunk
+  // wgrad: MN-major views of the same planes, SP_WKC lines per K chunk
   CUtensorMap ah, al, bh, bl;
   if (spec_enc3(&ah, s.Ah, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, SP_WKC) ||
       spec_enc3(&al, s.Al, 2 * s.C1, lines, F, SP_KA1 * 2, s.RA * SP_KA1 * 2, 64, SP_WKC) ||
