@@ -460,6 +460,30 @@ def test_fft_line_walk_orders_bit_identical(built, N, B, S, chunk):
             assert _relmax(a, b) < 1e-5, name
 
 
+@pytest.mark.parametrize("N,B,S", [(256, 3, 2), (100, 4, 2)])
+def test_fft_staging_variants_agree(built, N, B, S):
+    """The transforms' staging variants -- per-thread cp.async instead of one bulk copy per line (SNDVAE_FFT_BULK=0), bulk
+    row copies in the inverse (SNDVAE_FFT_BULK_INV=1), the first-form inverse for the 50-channel lines (SNDVAE_FFT_INV2=0)
+    -- move the same numbers through different copy engines / buffers: logits and losses agree with the default path."""
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", dtype=torch.float32)
+    out = {}
+    for name, env in (("default", {}), ("no_bulk", {"SNDVAE_FFT_BULK": "0"}), ("bulk_inv", {"SNDVAE_FFT_BULK_INV": "1"}),
+                      ("inv_first_form", {"SNDVAE_FFT_INV2": "0"})):
+        os.environ.update(env)
+        try:
+            eng = _engine(built, N, B, S, "disentangled", 2, chunk=2)
+        finally:
+            for k in env: os.environ.pop(k, None)
+        eng.set_params(P)
+        r = eng.grads(inp, noise, fetch=("generated_adj_prob",))
+        out[name] = (r["generated_adj_prob"].cpu().numpy(), np.asarray(r["overall_loss"]), eng.get_grads()["decoder/e1_deconv/w1"].numpy())
+        eng.close()
+    for name in ("no_bulk", "bulk_inv", "inv_first_form"):
+        assert _relmax(out[name][0], out["default"][0]) < 5e-6, name
+        np.testing.assert_allclose(out[name][1], out["default"][1], rtol=1e-6)
+        assert _relmax(out[name][2], out["default"][2]) < 1e-4, name       # dw1 goes through atomics
+
+
 @pytest.mark.parametrize("B,N,hd", [(3, 9, 5), (2, 100, 20), (2, 256, 40), (1, 300, 100), (2, 131, 72)])
 def test_inner_product_decoder(built, B, N, hd):
     """InnerProductDecoder (layers.py:400-410; standalone operator, not used by the reference's models): z z^T per graph on
