@@ -1,7 +1,9 @@
 #!/bin/bash
-# A/B of the FFT line-walk orders (SNDVAE_FFT_ORDER / SNDVAE_FFT_ORDER_INV) on one 256-graph micro-batch at N=256:
-# per-launch time and DRAM bytes of the transforms from an ncu launch list (cold cache, serialised).
-# Usage (on the GPU box): bash tools/ab_fft_order.sh "<fwd> <inv>" ...   e.g.  "0 0" "-1 -1"
+# A/B harness for the kernels of the N^2 stage on one 256-graph micro-batch at N=256: per-launch time and DRAM bytes of
+# y_producer_tc_k, the transforms, the per-frequency GEMMs and spec_wgrad_k from an ncu launch list (cold cache, serialised).
+# Each argument "<fwd> <inv>" is one run with SNDVAE_FFT_ORDER / SNDVAE_FFT_ORDER_INV set (-1 = default); any other
+# diagnostic switch of DESIGN.md is taken from the caller's environment, e.g.
+#   SNDVAE_FFT_BULK_INV=1 bash tools/ab_fft_order.sh "-1 -1"      vs      bash tools/ab_fft_order.sh "-1 -1"
 mkdir -p gpurun_out
 for cfg in "$@"; do
   set -- $cfg
