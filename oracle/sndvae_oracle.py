@@ -63,7 +63,7 @@ class Config:
     g_conv_hidden: Tuple[int, ...] = (10, 20)
     g_hidden_size: int = 100
     g_latent_size: int = 100
-    sg_conv_hidden: Tuple[Tuple[int, int, int], ...] = ((20, 20, 20), (50, 50, 50))
+    sg_conv_hidden: Tuple[Tuple[int, ...], ...] = ((20, 20, 20), (50, 50, 50))   # 4-tuples select the 3-hop layer (protein / mnist)
     sg_hidden_size: int = 100
     sg_latent_size: int = 100
     s_d_channel: Tuple[int, ...] = (50, 20, 10)
@@ -114,6 +114,16 @@ def param_table(cfg: Config) -> List[Tuple[str, Tuple[int, ...], str]]:
 
     def sgc(name, C, hs):
         R = 1
+        if len(hs) == 4:        # SpatialGraphConvolution_3D (layers.py:210-225; protein / mnist branch, model.py:139-140)
+            t.append((f"{name}/Matrix0", (4 * C + 3 * R + 2, hs[0]), "normal02"))
+            t.append((f"{name}/bias0", (hs[0],), "zeros"))
+            t.append((f"{name}/Matrix1", (3 * C + 2 * R + hs[0] + 1, hs[1]), "normal02"))
+            t.append((f"{name}/bias1", (hs[1],), "zeros"))
+            t.append((f"{name}/Matrix2", (2 * C + R + hs[1], hs[2]), "normal02"))
+            t.append((f"{name}/bias2", (hs[2],), "zeros"))
+            t.append((f"{name}/Matrix3", (C + hs[2], hs[3]), "normal02"))
+            t.append((f"{name}/bias3", (hs[3],), "zeros"))
+            return
         t.append((f"{name}/Matrix1", (3 * C + 2 * R + 1, hs[0]), "normal02"))
         t.append((f"{name}/bias1", (hs[0],), "zeros"))
         t.append((f"{name}/Matrix2", (2 * C + hs[0] + R, hs[1]), "normal02"))
@@ -147,8 +157,8 @@ def param_table(cfg: Config) -> List[Tuple[str, Tuple[int, ...], str]]:
     c = F
     for i, hs in enumerate(cfg.sg_conv_hidden):
         sgc(f"encoder/g_sg{i}_conv", c, hs)
-        bn(f"encoder/g_bn_sg{i}", hs[2])
-        c = hs[2]
+        bn(f"encoder/g_bn_sg{i}", hs[-1])
+        c = hs[-1]
     if dis:
         bn("encoder/encoder_sg", c)
     lin("encoder/g_sg1_lin", N * c, cfg.sg_hidden_size)
@@ -474,8 +484,11 @@ def encoder(P, inp, cfg: Config, mode="factored"):
         out["z_std_s"] = linear(hs, P, "encoder/g_s3_lin")
     x, A, R = inp["features"], inp["adj"], inp["rel"]
     BS = x.shape[0]
+    sgc3 = sgc3d_literal if mode == "literal" else sgc3d_factored
     for i in range(len(cfg.sg_conv_hidden)):
-        x = lrelu(bn(sgc(A, x, R, P, f"encoder/g_sg{i}_conv"), P, f"encoder/g_bn_sg{i}"))
+        # a 4-tuple of hidden sizes selects the 3-hop layer (FLAGS.dataset in {protein, mnist}: main.py:225,241, model.py:139-140)
+        layer = sgc3 if len(cfg.sg_conv_hidden[i]) == 4 else sgc
+        x = lrelu(bn(layer(A, x, R, P, f"encoder/g_sg{i}_conv"), P, f"encoder/g_bn_sg{i}"))
     if dis:
         x = bn(x, P, "encoder/encoder_sg")
     hsg = linear(x.reshape(BS, -1), P, "encoder/g_sg1_lin")

@@ -264,3 +264,28 @@ def test_sgc3d_factored_equals_literal():
     out = O.sgc3d_factored(torch.zeros(Bn, N, N, dtype=torch.float64), x, rel, P, name)
     ref = O.lrelu(torch.cat([x, torch.zeros(Bn, N, h[2], dtype=torch.float64)], dim=2)) @ P[name + "/Matrix3"] + P[name + "/bias3"]
     assert torch.allclose(out, ref, atol=1e-14)
+
+
+def test_protein_branch_literal_equals_factored():
+    """The `protein` configuration of the reference (main.py:218-236: 3-hop SpatialGraphConvolution_3D layers, spatial_dim 3,
+    node_h_size 5, small latents) through the whole model: losses and every gradient of the literal restatement (N^4 tensors)
+    equal those of the factored one in fp64.  Checker side only -- the CUDA engine does not build this branch yet."""
+    cfg = O.Config(num_nodes=5, spatial_dim=3, node_h_size=5, sampling_num=2, sg_conv_hidden=((4, 4, 4, 4), (6, 6, 6, 6)),
+                   sg_hidden_size=8, sg_latent_size=8, s_hidden_size=5, s_latent_size=5, g_hidden_size=5, g_latent_size=5)
+    names = [n for n, _, _ in O.param_table(cfg)]
+    assert "encoder/g_sg0_conv/Matrix0" in names and "encoder/g_sg1_conv/bias3" in names
+    shapes = {n: sh for n, sh, _ in O.param_table(cfg)}
+    assert shapes["encoder/g_sg0_conv/Matrix0"] == (4 * 1 + 5, 4) and shapes["encoder/g_sg1_conv/Matrix1"] == (3 * 4 + 3 + 6, 6)
+    P = O.init_params(cfg, 7, torch.float64)
+    g = torch.Generator().manual_seed(2)
+    for k in P:
+        P[k] = P[k] + 0.1 * torch.randn(P[k].shape, generator=g, dtype=torch.float64)
+    inp = O.synthetic_inputs(cfg, 2, 5, torch.float64)
+    noise = O.synthetic_noise(cfg, 2, 9, torch.float64)
+    _, _, _, L1, g1 = O.loss_and_grads(P, inp, noise, cfg, "literal")
+    _, _, _, L2, g2 = O.loss_and_grads(P, inp, noise, cfg, "factored")
+    for a, b in zip(L1["overall_loss"], L2["overall_loss"]):
+        assert abs(a.item() - b.item()) < 1e-12 * max(1.0, abs(a.item()))
+    for k in g1:
+        assert (g1[k] - g2[k]).abs().max().item() < 1e-11 * max(1.0, g1[k].abs().max().item()), k
+    assert g1["encoder/g_sg0_conv/Matrix0"].abs().max().item() > 0
