@@ -190,3 +190,13 @@ def test_bench_compulsory_bytes_of_the_spectral_stage():
     inv_dy = lines * (8 * F * C1 + 4 * N * C1)
     wgrad = lines * (8 * F * C1 + 8 * F * C2)
     assert bench.spectral_bytes(N) == fwd_y + gemm_f + inv_o + fwd_do + gemm_d + inv_dy + wgrad
+
+
+def test_make_config_refuses_the_3hop_branch():
+    """The reference's protein / mnist configuration (four hidden sizes per SGC layer) is not built on the device: the host
+    mirror raises instead of silently truncating the tuple."""
+    sv = import_module("snd-vae_b200")
+    with pytest.raises(Exception, match="SpatialGraphConvolution_3D"):
+        sv.make_config(8, 2, "disentangled", sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)))
+    cfg = sv.make_config(8, 2, "disentangled", sg_conv_hidden=((4, 5, 6), (7, 8, 9)))
+    assert [list(r) for r in cfg.sg_conv_hidden] == [[4, 5, 6], [7, 8, 9]]
