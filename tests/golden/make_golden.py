@@ -19,8 +19,12 @@ from oracle import sndvae_oracle as O  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def make(name, model, N, B, S, adam_steps=(1, 3), full=True):
-    cfg = O.Config(num_nodes=N, model_type=model, sampling_num=S)
+PROTEIN = dict(spatial_dim=3, node_h_size=5, sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)), sg_hidden_size=50, sg_latent_size=50,
+               s_hidden_size=5, s_latent_size=5, g_hidden_size=5, g_latent_size=5)     # main.py:218-236 (3-hop SGC layers)
+
+
+def make(name, model, N, B, S, adam_steps=(1, 3), full=True, cfg_kw=None):
+    cfg = O.Config(num_nodes=N, model_type=model, sampling_num=S, **(cfg_kw or {}))
     P = O.init_params(cfg, 7, torch.float64)
     g = torch.Generator().manual_seed(1)
     for k in P:
@@ -54,3 +58,5 @@ if __name__ == "__main__":
     make("dis_n8", "disentangled", 8, 4, 3)
     make("base_n8", "base", 8, 4, 1)
     make("dis_n25", "disentangled", 25, 3, 10, full=False)
+    # the reference's protein configuration (SpatialGraphConvolution_3D): oracle-only until the CUDA engine builds the branch
+    make("protein_n6", "disentangled", 6, 3, 2, cfg_kw=PROTEIN)

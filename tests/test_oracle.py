@@ -289,3 +289,25 @@ def test_protein_branch_literal_equals_factored():
     for k in g1:
         assert (g1[k] - g2[k]).abs().max().item() < 1e-11 * max(1.0, g1[k].abs().max().item()), k
     assert g1["encoder/g_sg0_conv/Matrix0"].abs().max().item() > 0
+
+
+def test_golden_protein_fixture():
+    """tests/golden/protein_n6.npz (the reference's protein hyper-parameters, main.py:218-236, at N=6) is reproduced by the
+    factored oracle and, independently, by the literal restatement that materialises the N^4 tensors."""
+    z = np.load(os.path.join(GOLD, "protein_n6.npz"))
+    N, B, S = int(z["N"]), int(z["B"]), int(z["S"])
+    cfg = O.Config(num_nodes=N, sampling_num=S, spatial_dim=3, node_h_size=5, sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)),
+                   sg_hidden_size=50, sg_latent_size=50, s_hidden_size=5, s_latent_size=5, g_hidden_size=5, g_latent_size=5)
+    P = O.init_params(cfg, 7, torch.float64)
+    g = torch.Generator().manual_seed(1)
+    for k in P:
+        P[k] = P[k] + 0.05 * torch.randn(P[k].shape, generator=g, dtype=torch.float64)
+    inp = O.synthetic_inputs(cfg, B, 5, torch.float64)
+    noise = O.synthetic_noise(cfg, B, 9, torch.float64)
+    for mode, tol in (("factored", 1e-10), ("literal", 1e-9)):
+        enc, zz, dec, L, gr = O.loss_and_grads(P, inp, noise, cfg, mode)
+        assert np.allclose(np.array([x.item() for x in L["overall_loss"]]), z["overall_loss"], rtol=tol), mode
+        assert np.allclose(dec["generated_adj_prob"].detach().numpy(), z["generated_adj_prob"], rtol=0, atol=tol), mode
+        for k in gr:
+            d = z["gradsum/" + k]
+            assert np.allclose([gr[k].sum().item(), gr[k].abs().sum().item()], d, rtol=1e-6, atol=1e-11), (mode, k)
