@@ -41,7 +41,7 @@ def make_config(num_nodes: int, batch_size: int, model_type: str = "disentangled
             if k == "sg_conv_hidden":
                 if len(v) != 2 or any(len(hs) != 3 for hs in v):
                     # 4 sizes per layer = SpatialGraphConvolution_3D (layers.py:200-277; FLAGS.dataset protein / mnist): the
-                    # oracle restates it, the CUDA engine does not build it -- refuse instead of truncating
+                    # CUDA engine does not build that branch -- refuse instead of truncating
                     raise SndvaeError(f"sg_conv_hidden={v!r}: two layers of three hidden sizes required "
                                       "(the 3-hop SpatialGraphConvolution_3D branch is not built)")
                 for i in range(2):
