@@ -169,9 +169,37 @@ int sndvae_forward(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* noi
 int sndvae_grads(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* noise,
                  sndvae_outputs* out, float* losses_host, int64_t global_batch);
 
+/* Gradient accumulation over device-resident micro-batches (BASELINE config 4: a global batch larger than what one
+ * call holds).  The reference has no counterpart -- its batch is whatever one sess.run is fed (main.py:316-331) -- but
+ * the ELBO is a mean over the batch (optimizer.py:144-162), so the gradient of a batch of k micro-batches is the sum
+ * of k calls with global_batch = k * world * B:
+ *     sndvae_zero_grads(h);  k x sndvae_grads_accumulate(h, ..., k * world * B);  [sndvae_allreduce_grads(h);]
+ *     sndvae_apply_adam(h);
+ * sndvae_grads == sndvae_zero_grads + one sndvae_grads_accumulate.  losses_host is the micro-batch's own mean. */
+int sndvae_zero_grads(sndvae_t* h);
+int sndvae_grads_accumulate(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* noise,
+                            sndvae_outputs* out, float* losses_host, int64_t global_batch);
+
 /* The apply half of AdamOptimizer.minimize (optimizer.py:197): TF1 ApplyAdam on
  * the whole arena using the current gradient arena. */
 int sndvae_apply_adam(sndvae_t* h);
+
+/* The KL weight `beta` of OptimizerVAE(..., beta=...) (optimizer.py:124,164; main.py:515), settable after create
+ * because the reference passes it to the optimizer constructor, not to the model's. */
+int sndvae_set_beta(sndvae_t* h, float beta);
+
+/* Data parallelism (the reference is single-process).  One handle per rank; graphs are sharded, parameters
+ * replicated.  Rank 0 calls sndvae_comm_unique_id and distributes the 128 bytes (any side channel: torch.distributed
+ * broadcast, MPI, a file); every rank then calls sndvae_comm_init.  NCCL is resolved at run time from the process
+ * (PyTorch's libnccl.so.2) -- the library has no link-time dependency on it.  With a communicator,
+ * sndvae_train_step / sndvae_train_step_host run  grads (scaled 1 / (world B)) -> one ncclAllReduce(sum) of the
+ * gradient arena and of the loss sums over NVLink on the handle's stream -> Adam, and losses_host is the mean over
+ * the global batch.  sndvae_allreduce_grads is the bare collective for callers that drive sndvae_grads /
+ * sndvae_grads_accumulate themselves. */
+int sndvae_comm_unique_id(uint8_t* id_host /*[128]*/);
+int sndvae_comm_init(sndvae_t* h, const uint8_t* id_host /*[128]*/, int32_t rank, int32_t world);
+int sndvae_comm_info(const sndvae_t* h, int32_t* rank_host, int32_t* world_host);
+int sndvae_allreduce_grads(sndvae_t* h);
 
 /* sess.run([opt.opt_op, opt.overall_loss, model.generated_adj], feed)
  * (main.py:331): forward, backward and Adam on one device. */
@@ -188,6 +216,31 @@ int sndvae_generate(sndvae_t* h, const float* z_s, const float* z_sg, const floa
  * feeds host->device, runs the step, copies losses and generated_adj back. */
 int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in_host, const sndvae_noise* noise_host,
                            int64_t* generated_adj_host, float* losses_host);
+
+/* The gradient half of sndvae_train_step_host (host feeds in, generated_adj and the micro-batch's losses out, no
+ * all-reduce, no update): with `accumulate` != 0 the gradient arena is added to, as sndvae_grads_accumulate does. */
+int sndvae_grads_host(sndvae_t* h, const sndvae_inputs* in_host, const sndvae_noise* noise_host,
+                      int64_t* generated_adj_host, float* losses_host, int64_t global_batch, int32_t accumulate);
+
+/* Compact host feeds ("optional compact input formats").  The dense feed_dict of main.py:253-264 carries
+ * S identical copies of `rel` / `features` (np.tile, main.py:307-309) and 0/1 adjacencies as fp32: 84 N^2 bytes per graph.
+ * A loader that keeps what input_data.py:18-38,77-83 actually computes (one `rel` per graph, spanning forests as sets of
+ * edges) can hand over 5.4 N^2 bytes instead:
+ *   adjacency bit rows: W = ceil(N / 32) uint32 words per row, bit (j % 32) of word (j / 32) = (adj[i][j] != 0).
+ * Only valid for 0/1 adjacencies (what the reference's loaders produce); the dense entry points stay the default. */
+typedef struct sndvae_inputs_compact {
+  const float*    features;        /* [B, N, F]     per graph (dense row b*S+s = graph b's, main.py:307) */
+  const uint32_t* adj_bits;        /* [B*S, N, W]   sampled spanning forests */
+  const float*    rel;             /* [B, N, N]     per graph */
+  const uint32_t* adj_truth_bits;  /* [B, N, W] */
+  const float*    feature_truth;   /* [B, N, F] */
+  const float*    spatial_truth;   /* [B, N, D] */
+} sndvae_inputs_compact;
+
+/* sndvae_train_step_host on compact feeds: the packed bytes cross the bus, the dense tensors are rebuilt in HBM by
+ * unpack kernels; generated_adj comes back as bit rows [B, N, W] (may be NULL).  Same step, same results. */
+int sndvae_train_step_host_compact(sndvae_t* h, const sndvae_inputs_compact* in_host, const sndvae_noise* noise_host,
+                                   uint32_t* generated_adj_bits_host, float* losses_host);
 
 /* Number of library kernels launched since create (bench.py's gpu_launches). */
 /* Device-side synthetic data (replaces input_data.py:18-38,54-96 for synthetic spatial graphs): fills the
@@ -206,6 +259,12 @@ int sndvae_set_global_iter(sndvae_t* h, int64_t global_iter);
  * the handle's stream; used for bench.py's roofline block. */
 int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms_host, int64_t* launches_host,
                        double* flops_host);
+
+/* Per-stage CUDA-event times of the step (the reference prints wall time per step only, main.py:348-350): with
+ * `enable` != 0 every following step records an event at each stage boundary on the handle's stream.  A call returns
+ * the totals accumulated since the previous call -- up to `capacity` stages, names in 32-byte slots of names_host, ms
+ * in ms_host, the number of steps in *steps_host -- and resets them; the return value is the number of stages. */
+int sndvae_stage_times(sndvae_t* h, int32_t enable, char* names_host, double* ms_host, int32_t capacity, int64_t* steps_host);
 
 /* InnerProductDecoder._call (layers.py:400-410): logits[b] = z[b] z[b]^T, no activation (the layer returns the raw
  * product).  z: device [batch, num_nodes, dim] fp32, logits: device [batch, num_nodes, num_nodes] fp32; shapes are the

@@ -12,7 +12,8 @@ PARITY UNPINNED at the TensorFlow boundary: TensorFlow is not installed in the
 build image and not in /opt/wheelhouse, the reference ships no tests, golden
 vectors, logs or checkpoints.  The pin is therefore
 internal: (1) a *literal* restatement that materialises what TF materialises,
-(2) an independent *factored* restatement, (1)==(2) to 1e-12 in fp64,
+(2) an independent *factored* restatement, (1)==(2) to 1e-12 in fp64 (and a third form, mode "fft": the width-N
+correlations through torch.fft, == (2) to 1e-12, which is what scales to N = 1024 on a CPU),
 (3) autograd == central finite differences, (4) seeded golden vectors under
 tests/golden/ made by oracle/make_golden.py.
 
@@ -434,7 +435,31 @@ def e2e_toeplitz(x, w1, bias):
     return o1 + o2 + 2.0 * bias
 
 
-def e2e_l0_factored(a, c, w1, bias):
+def corr_same_fft(x, w):
+    """out[..., s, o] = sum_{s', c} x[..., s', c] w[s' - s + p, c, o]  (p = (N-1)//2, zero outside 0 <= s' - s + p < N): the
+    width-N SAME cross-correlation of layers.py:436,443 along the second-to-last axis, evaluated with torch.fft (a third,
+    independent form of the same sum, O(N log N) per line: what makes N = 1024 checkable on a CPU).
+    x: [..., N, C], w: [N, C, O].  Circular convolution of the zero-padded line with g[m] = w[p - m], L >= 2N."""
+    N, C, O = w.shape
+    p = (N - 1) // 2
+    L = 2 * N
+    g = torch.zeros((L, C, O), dtype=w.dtype)
+    m = torch.arange(p - N + 1, p + 1)                     # g[m] = w[p - m] for p-N+1 <= m <= p, indices mod L
+    g[m % L] = w[p - m]
+    Xf = torch.fft.rfft(x, n=L, dim=-2)                    # [..., L/2+1, C]
+    Gf = torch.fft.rfft(g, dim=0)                          # [L/2+1, C, O]
+    Of = torch.einsum("...fc,fco->...fo", Xf, Gf)
+    return torch.fft.irfft(Of, n=L, dim=-2)[..., :N, :]
+
+
+def e2e_fft(x, w1, bias):
+    """e2e (layers.py:431-450) with both directions evaluated by corr_same_fft."""
+    o1 = corr_same_fft(x, w1[0])                                               # slide along j
+    o2 = corr_same_fft(x.transpose(1, 2), w1[0]).transpose(1, 2)               # slide along i
+    return o1 + o2 + 2.0 * bias
+
+
+def e2e_l0_factored(a, c, w1, bias, fft=False):
     """e2e on the never-materialised pair tensor [a_i || c_j] (Appendix C.2).
     a, c: [B,N,Ch] (already BN+relu'd halves)."""
     Bn, N, Ch = a.shape
@@ -445,11 +470,14 @@ def e2e_l0_factored(a, c, w1, bias):
     valid = ((pos + t - p >= 0) & (pos + t - p < N)).to(w1.dtype)     # [pos,t]
     WSa = torch.einsum("pt,tco->pco", valid, wa)           # [N(j),Ch,O]
     WSc = torch.einsum("pt,tco->pco", valid, wc)           # [N(i),Ch,O]
-    Tc = toeplitz_matrix(wc.unsqueeze(0))                  # [(j',c),(j,o)]
-    Ta = toeplitz_matrix(wa.unsqueeze(0))
     O = w1.shape[3]
-    Rc = (c.reshape(Bn, N * Ch) @ Tc).reshape(Bn, N, O)    # depends on j
-    Sa = (a.reshape(Bn, N * Ch) @ Ta).reshape(Bn, N, O)    # depends on i
+    if fft:
+        Rc, Sa = corr_same_fft(c, wc), corr_same_fft(a, wa)
+    else:
+        Tc = toeplitz_matrix(wc.unsqueeze(0))              # [(j',c),(j,o)]
+        Ta = toeplitz_matrix(wa.unsqueeze(0))
+        Rc = (c.reshape(Bn, N * Ch) @ Tc).reshape(Bn, N, O)    # depends on j
+        Sa = (a.reshape(Bn, N * Ch) @ Ta).reshape(Bn, N, O)    # depends on i
     t1 = torch.einsum("bic,jco->bijo", a, WSa)
     t3 = torch.einsum("bjc,ico->bijo", c, WSc)
     return t1 + t3 + Rc.unsqueeze(1) + Sa.unsqueeze(2) + 2.0 * bias
@@ -575,8 +603,9 @@ def decoder(P, z, cfg: Config, mode="factored"):
         inv = gam * (1.0 / math.sqrt(1.0 + BN_EPS))
         a = torch.relu(v * inv[:Ch] + bet[:Ch])
         c = torch.relu(v * inv[Ch:] + bet[Ch:])
-        E = e2e_l0_factored(a, c, w0, b0)
-        E = e2e_toeplitz(torch.relu(bn(E, P, "decoder/d_bn_e1")), w1, b1)
+        E = e2e_l0_factored(a, c, w0, b0, fft=(mode == "fft"))
+        Y = torch.relu(bn(E, P, "decoder/d_bn_e1"))
+        E = e2e_fft(Y, w1, b1) if mode == "fft" else e2e_toeplitz(Y, w1, b1)
     if dis:
         E = bn(E, P, "decoder/decoder_adj")
     lg = linear(torch.relu(E).reshape(B * N * N, -1), P, "decoder/d_e_lin2").reshape(B, N, N, 2)

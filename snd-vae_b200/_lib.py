@@ -39,6 +39,10 @@ class Inputs(C.Structure):
                                             "spatial_truth", "rel_truth")]
 
 
+class InputsCompact(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("features", "adj_bits", "rel", "adj_truth_bits", "feature_truth", "spatial_truth")]
+
+
 class Noise(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("eps_s", "eps_sg", "eps_g")]
 
@@ -73,13 +77,23 @@ SYMBOLS = {
     "sndvae_forward": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.POINTER(Outputs), C.c_void_p]),
     "sndvae_grads": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.POINTER(Outputs), C.c_void_p, I64]),
     "sndvae_apply_adam": (C.c_int, [C.c_void_p]),
+    "sndvae_zero_grads": (C.c_int, [C.c_void_p]),
+    "sndvae_grads_accumulate": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.POINTER(Outputs), C.c_void_p, I64]),
+    "sndvae_set_beta": (C.c_int, [C.c_void_p, F32]),
+    "sndvae_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "sndvae_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, I32, I32]),
+    "sndvae_comm_info": (C.c_int, [C.c_void_p, C.POINTER(I32), C.POINTER(I32)]),
+    "sndvae_allreduce_grads": (C.c_int, [C.c_void_p]),
+    "sndvae_grads_host": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.c_void_p, C.c_void_p, I64, I32]),
     "sndvae_train_step": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.POINTER(Outputs), C.c_void_p]),
     "sndvae_generate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Outputs)]),
     "sndvae_train_step_host": (C.c_int, [C.c_void_p, C.POINTER(Inputs), C.POINTER(Noise), C.c_void_p, C.c_void_p]),
+    "sndvae_train_step_host_compact": (C.c_int, [C.c_void_p, C.POINTER(InputsCompact), C.POINTER(Noise), C.c_void_p, C.c_void_p]),
     "sndvae_set_global_iter": (C.c_int, [C.c_void_p, I64]),
     "sndvae_synth_inputs": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Inputs)]),
     "sndvae_launch_count": (I64, [C.c_void_p]),
     "sndvae_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(C.c_double)]),
+    "sndvae_stage_times": (C.c_int, [C.c_void_p, I32, C.c_void_p, C.c_void_p, I32, C.POINTER(I64)]),
     "sndvae_threshold_logits": (C.c_int, [C.c_void_p, C.c_void_p, I64, C.c_void_p]),
     "sndvae_inner_product_decode": (C.c_int, [C.c_void_p, C.c_void_p, I64, I32, I32, C.c_void_p]),
     "sndvae_debug_read": (I64, [C.c_void_p, C.c_char_p, C.c_void_p, I64]),

@@ -34,7 +34,8 @@ struct PT {   // parameter offsets (floats) into the flat arenas; -1 = absent
 };
 
 struct EvPair { cudaEvent_t a, b; double flops; };
-struct StageTimer { std::vector<cudaEvent_t> ev; std::vector<const char*> name; size_t used; int on; };
+struct StageTimer { std::vector<cudaEvent_t> ev; std::vector<const char*> name; size_t used; int on; int print;
+                    std::vector<std::pair<std::string, double>> total; long long steps; };
 
 struct sndvae_handle {
   sndvae_config cfg;
@@ -80,6 +81,8 @@ struct sndvae_handle {
   // host-feed staging (sndvae_train_step_host)
   float *hf_features, *hf_adj, *hf_rel, *hf_adj_truth, *hf_feature_truth, *hf_spatial_truth, *hf_eps_s, *hf_eps_sg, *hf_eps_g;
   long long* hf_gen_adj;
+  // compact host feeds: packed staging (bits / per-graph tensors) expanded on the device into the dense staging above
+  float *hc_features, *hc_rel; uint32_t *hc_adj_bits, *hc_adjt_bits, *hc_gen_bits; int hc_ready;
   // gemm timing
   std::vector<EvPair> ev; size_t ev_used;
   StageTimer stt;
@@ -87,6 +90,11 @@ struct sndvae_handle {
   // them at once so that the forward functions can run on a contiguous piece of the batch (pipelined host step)
   struct Shift { char** p; long long bytes; };
   std::vector<Shift> shifts;
+  int hf_ready;                        // every host-feed staging buffer is allocated
+  int max_c;                           // widest node-level channel count of the config (sizes gA / gB / gC / colbuf)
+  int poisoned;                        // a step failed half-way: arenas / losses are undefined until the next successful run
+  // data-parallel communicator (sndvae_comm_init): NCCL resolved at run time from the process (torch's libnccl.so.2)
+  void* comm; int rank, world;
   cudaStream_t cs, ds;                 // host-step copy streams (H2D feeds, D2H generated_adj)
   std::vector<cudaEvent_t> pev;        // per-piece events: 2 per piece (feeds landed, piece computed)
   cudaEvent_t ev_start;
@@ -113,9 +121,17 @@ static void report_stages(sndvae_handle* h) {
     for (auto& a : acc) if (a.first == t.name[i]) { a.second += ms; found = true; break; }
     if (!found) acc.push_back({t.name[i], ms});
   }
-  fprintf(stderr, "[sndvae stages]");
-  for (auto& a : acc) fprintf(stderr, " %s=%.2fms", a.first.c_str(), a.second);
-  fprintf(stderr, "\n");
+  for (auto& a : acc) {          // running totals for sndvae_stage_times
+    bool found = false;
+    for (auto& b : t.total) if (b.first == a.first) { b.second += a.second; found = true; break; }
+    if (!found) t.total.push_back(a);
+  }
+  t.steps++;
+  if (t.print) {
+    fprintf(stderr, "[sndvae stages]");
+    for (auto& a : acc) fprintf(stderr, " %s=%.2fms", a.first.c_str(), a.second);
+    fprintf(stderr, "\n");
+  }
   t.used = 0;
 }
 
@@ -249,8 +265,9 @@ static int dalloc(sndvae_t* h, T** p, long long n) {
   void* q = nullptr;
   cudaError_t e = cudaMalloc(&q, (size_t)n * sizeof(T));
   if (e != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMalloc(%lld bytes): %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
-  cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), h->stream);
   h->allocs.push_back(q);
+  e = cudaMemsetAsync(q, 0, (size_t)n * sizeof(T), h->stream);
+  if (e != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMemsetAsync(%lld bytes): %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
   *p = (T*)q;
   return 0;
 }
@@ -344,7 +361,12 @@ static int alloc_buffers(sndvae_t* h) {
   DG(h->da, N * Chv); DG(h->dc, N * Chv); DG(h->dRc, N * C1); DG(h->dSa, N * C1);
   DA(h->dWSa, (long long)N * C1 * Chv); DA(h->dWSc, (long long)N * C1 * Chv);
   DG(h->dv, N * Chv); DG(h->dsp0, N * Chv);
-  DG(h->gA, N * 64); DG(h->gB, N * 64); DG(h->gC, N * 64); DG(h->colbuf, N * KS * 64);
+  // generic backward temporaries: [N, widest channel count] per graph, and at least one hidden vector per graph (the
+  // latent heads park [B, hidden] gradients in gC)
+  { long long pg = (long long)N * h->max_c;
+    const int hid[3] = {c.s_hidden_size, c.g_hidden_size, c.sg_hidden_size};
+    for (int i = 0; i < 3; ++i) if (hid[i] > pg) pg = hid[i];
+    DG(h->gA, pg); DG(h->gB, pg); DG(h->gC, pg); DG(h->colbuf, (long long)N * KS * h->max_c); }
   const long long cells = (long long)h->Bc * N * N;
   if (c.use_tensor_cores == 2) {     // graph-tiled layouts: whole tiles of 128 graphs
     const long long tcells = (long long)((h->Bc + 127) / 128) * 128 * N * N;
@@ -414,11 +436,12 @@ static void bn_bwd(sndvae_t* h, const float* dout, int ldd, const float* in, int
          din, ldn, g >= 0 ? h->G + g : nullptr, b >= 0 ? h->G + b : nullptr, rows, C, act, order);
 }
 // conv1d k5 SAME over the node axis (model.py:122,191,216) as im2col + one tall library GEMM
-static void conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, long long rows, int Ci, int Co) {
-  if (rows * Ci < 4096) { LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS); return; }
+static int conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, long long rows, int Ci, int Co) {
+  if (rows * Ci < 4096) { LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS); return 0; }
   LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
   LEW(bias_rows_k, rows * Co, out, h->P + b, rows, Co);
-  gemm_rm(h, false, false, (int)rows, Co, KS * Ci, 1.f, h->colbuf, KS * Ci, h->P + k, Co, 1.f, out, Co);
+  CKB(gemm_rm(h, false, false, (int)rows, Co, KS * Ci, 1.f, h->colbuf, KS * Ci, h->P + k, Co, 1.f, out, Co));
+  return 0;
 }
 // weight/bias grads + optional input grad of a conv1d layer
 static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
@@ -538,11 +561,11 @@ static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
     if ((r = lin_fwd(h, h->hg, p.g_lin[2], h->ls_g, B, c.g_hidden_size, c.g_latent_size))) return r;
     // spatial encoder (model.py:119-129): relu(BN(conv1d k5 SAME)) x3
     const int* sc = c.s_channel;
-    conv_fwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->h1p, Rn, D, sc[0]);
+    if ((r = conv_fwd(h, in->spatial_truth, p.gs_k[0], p.gs_b[0], h->h1p, Rn, D, sc[0]))) return r;
     bn_fwd(h, h->h1p, sc[0], p.gs_bng[0], p.gs_bnb[0], h->h1, sc[0], Rn, sc[0], ACT_RELU, 0);
-    conv_fwd(h, h->h1, p.gs_k[1], p.gs_b[1], h->h2p, Rn, sc[0], sc[1]);
+    if ((r = conv_fwd(h, h->h1, p.gs_k[1], p.gs_b[1], h->h2p, Rn, sc[0], sc[1]))) return r;
     bn_fwd(h, h->h2p, sc[1], p.gs_bng[1], p.gs_bnb[1], h->h2, sc[1], Rn, sc[1], ACT_RELU, 0);
-    conv_fwd(h, h->h2, p.gs_k[2], p.gs_b[2], h->h3p, Rn, sc[1], sc[2]);
+    if ((r = conv_fwd(h, h->h2, p.gs_k[2], p.gs_b[2], h->h3p, Rn, sc[1], sc[2]))) return r;
     bn_fwd(h, h->h3p, sc[2], p.gs_bng[2], p.gs_bnb[2], h->h3, sc[2], Rn, sc[2], ACT_RELU, 0);
     bn_fwd(h, h->h3, sc[2], p.encs_g, p.encs_b, h->fs, sc[2], Rn, sc[2], ACT_NONE, 0);
     if ((r = lin_fwd(h, h->fs, p.s_lin[0], h->hs, B, N * sc[2], c.s_hidden_size))) return r;
@@ -603,9 +626,9 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
   }
   // node-feature decoder (model.py:186-194)
   const int* nc = c.n_d_channel;
-  conv_fwd(h, h->v, p.n_k[0], p.n_b[0], h->q1p, Rn, Chv, nc[0]);
+  if ((r = conv_fwd(h, h->v, p.n_k[0], p.n_b[0], h->q1p, Rn, Chv, nc[0]))) return r;
   bn_fwd(h, h->q1p, nc[0], p.n_bng[0], p.n_bnb[0], h->q1, nc[0], Rn, nc[0], dact, 0);
-  conv_fwd(h, h->q1, p.n_k[1], p.n_b[1], h->q2p, Rn, nc[0], nc[1]);
+  if ((r = conv_fwd(h, h->q1, p.n_k[1], p.n_b[1], h->q2p, Rn, nc[0], nc[1]))) return r;
   bn_fwd(h, h->q2p, nc[1], p.n_bng[1], p.n_bnb[1], h->q2, nc[1], Rn, nc[1], dact, 0);
   if (h->dis) bn_fwd(h, h->q2, nc[1], p.decnode_g, p.decnode_b, h->q3, nc[1], Rn, nc[1], ACT_NONE, 0);
   LEW(rowlin_fwd_k, Rn * F, h->q3, nc[1], h->P + p.d_n_lin2[0], h->P + p.d_n_lin2[1], h->xpre, F, Rn, nc[1], F, ACT_NONE);
@@ -613,11 +636,11 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
          Rn * F, 1.f / (gB * N * F));
   // spatial decoder (model.py:213-219)
   const int* sc = c.s_d_channel;
-  conv_fwd(h, h->sp0, p.s_k[0], p.s_b[0], h->s1p, Rn, Chv, sc[0]);
+  if ((r = conv_fwd(h, h->sp0, p.s_k[0], p.s_b[0], h->s1p, Rn, Chv, sc[0]))) return r;
   bn_fwd(h, h->s1p, sc[0], p.s_bng[0], p.s_bnb[0], h->s1, sc[0], Rn, sc[0], dact, 0);
-  conv_fwd(h, h->s1, p.s_k[1], p.s_b[1], h->s2p, Rn, sc[0], sc[1]);
+  if ((r = conv_fwd(h, h->s1, p.s_k[1], p.s_b[1], h->s2p, Rn, sc[0], sc[1]))) return r;
   bn_fwd(h, h->s2p, sc[1], p.s_bng[1], p.s_bnb[1], h->s2, sc[1], Rn, sc[1], dact, 0);
-  conv_fwd(h, h->s2, p.s_k[2], p.s_b[2], h->s3p, Rn, sc[1], sc[2]);
+  if ((r = conv_fwd(h, h->s2, p.s_k[2], p.s_b[2], h->s3p, Rn, sc[1], sc[2]))) return r;
   bn_fwd(h, h->s3p, sc[2], p.s_bng[2], p.s_bnb[2], h->s3, sc[2], Rn, sc[2], dact, 0);
   LEW(rowlin_fwd_k, Rn * D, h->s3, sc[2], h->P + p.d_s_lin2[0], h->P + p.d_s_lin2[1], h->ppre, D, Rn, sc[2], D, ACT_NONE);
   LEW(sigmoid_mse_k, Rn * D, h->ppre, in ? in->spatial_truth : nullptr, h->phat, backward ? h->dppre : nullptr, h->loss + 2,
@@ -994,6 +1017,46 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
 }
 
 // ------------------------------------------------------------------------------------------
+// data-parallel communicator: NCCL, resolved at run time (dlopen of the libnccl.so.2 already in the process -- PyTorch
+// loads it -- or on the loader path), so that libsndvae.so itself has no link-time dependency on it
+// ------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+typedef struct { char internal[128]; } nccl_unique_id;          // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+  int (*GetUniqueId)(nccl_unique_id*);
+  int (*CommInitRank)(void**, int, nccl_unique_id, int);
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+  int (*CommDestroy)(void*);
+  const char* (*GetErrorString)(int);
+  int ok;
+};
+static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+static const char* nccl_load() {
+  if (g_nccl.ok) return nullptr;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return "libnccl.so.2 is neither loaded in this process nor on the loader path";
+#define SYM_(f) do { *(void**)(&g_nccl.f) = dlsym(lib, "nccl" #f); if (!g_nccl.f) return "nccl" #f " not found in libnccl"; } while (0)
+  SYM_(GetUniqueId); SYM_(CommInitRank); SYM_(AllReduce); SYM_(AllGather); SYM_(CommDestroy); SYM_(GetErrorString);
+#undef SYM_
+  g_nccl.ok = 1;
+  return nullptr;
+}
+#define NCCL_FLOAT 7   /* ncclFloat32 */
+#define NCCL_SUM 0     /* ncclSum */
+#define CKN(call) do { int s_ = (call); if (s_ != 0) return fail(h, SNDVAE_E_CUDA, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(s_), __FILE__, __LINE__); } while (0)
+// sum of the gradient arena (and of the 8 loss sums) over the ranks of the communicator; no-op without one
+static int allreduce_arena(sndvae_t* h, bool with_losses) {
+  if (!h->comm || h->world <= 1) return 0;
+  CKN(g_nccl.AllReduce(h->G, h->G, (size_t)h->nparam, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
+  if (with_losses) CKN(g_nccl.AllReduce(h->loss, h->loss, 8, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
+  h->launches += with_losses ? 2 : 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // step drivers
 // ------------------------------------------------------------------------------------------
 static int check_inputs(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz) {
@@ -1018,7 +1081,7 @@ static int copy_latents(sndvae_t* h, sndvae_outputs* out) {
 }
 
 // losses_host <- optimizer.overall_loss (optimizer.py:200-203)
-static int fetch_losses(sndvae_t* h, float* losses_host) {
+static int fetch_losses(sndvae_t* h, float* losses_host, int ranks_summed = 1) {
   CK(cudaMemcpyAsync(h->pinned_loss, h->loss, sizeof(float) * 8, cudaMemcpyDeviceToHost, h->stream));
   int ef = 0;
   CK(cudaMemcpyAsync(&ef, h->errflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -1027,9 +1090,10 @@ static int fetch_losses(sndvae_t* h, float* losses_host) {
             return fail(h, SNDVAE_E_DENSE, "a sampled adjacency has more than edge_capacity=%d non-zeros; the joint encoder expects spanning-forest samples (input_data.py:18-38)", h->cfg.edge_capacity); }
   if (!losses_host) return 0;
   const sndvae_config& c = h->cfg; const float* L = h->pinned_loss;
-  const double B = (double)h->B, N = h->N;
+  const double B = (double)h->B * ranks_summed, N = h->N;
   float adj = (float)(L[0] / (B * N * N)), node = (float)(L[1] / (B * N * h->F)), sp = (float)(L[2] / (B * N * h->D));
-  float kl_sg = (float)(L[5] / ((double)h->BS * c.sg_latent_size));
+  float kl_sg = (float)(L[5] / ((double)h->BS * ranks_summed * c.sg_latent_size));
+  if (ranks_summed > 1) h->pinned_loss[6] /= (float)ranks_summed;     // DIP / TC regularisers are per-rank statistics: report their mean
   if (h->dis) {
     float kl_s = (float)(L[3] / (B * c.s_latent_size)), kl_g = (float)(L[4] / (B * c.g_latent_size));
     if (c.loss_variant == SNDVAE_LOSS_CAPACITY) { const float ex = kl_sg - capacity_C(h); losses_host[0] = adj + node + sp + c.gamma * (ex > 0.f ? ex : 0.f) + kl_s + kl_g; }
@@ -1066,20 +1130,68 @@ static void slice_io(sndvae_t* h, long long g0, const sndvae_inputs* in, const s
 #undef OFF_
 }
 
+// ---- compact host feeds (sndvae_inputs_compact): 0/1 adjacencies as bit rows, per-graph tensors once -----------------
+// dense[row, j] = bit j of bits[row, :]   (row = (sample or graph, i); W = ceil(N / 32) words per row)
+__global__ void expand_bits_k(const uint32_t* __restrict__ bits, float* __restrict__ dense, long long rows, int N, int W) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * N) return;
+  const long long r = idx / N; const int j = (int)(idx - r * N);
+  dense[idx] = (float)((__ldg(bits + r * W + (j >> 5)) >> (j & 31)) & 1u);
+}
+// out[(g * S + s), :] = in[g, :]   (per-graph tensor repeated for its S samples: `rel`, `features`)
+__global__ void repeat_rows_k(const float* __restrict__ in, float* __restrict__ out, long long graphs, int S, long long per) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= graphs * S * per) return;
+  const long long gs = idx / per, e = idx - gs * per;
+  out[idx] = __ldg(in + (gs / S) * per + e);
+}
+// bits[row, w] = the 32 adjacency entries j = 32 w .. 32 w + 31 of generated_adj[row, :]  (one warp per word via ballot)
+__global__ void pack_adj_bits_k(const long long* __restrict__ adj, uint32_t* __restrict__ bits, long long rows, int N, int W) {
+  const long long word = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (word >= rows * W) return;
+  const long long r = word / W; const int j = (int)(word - r * W) * 32 + lane;
+  const unsigned m = __ballot_sync(0xffffffffu, j < N && adj[r * N + j] != 0);
+  if (lane == 0) bits[word] = m;
+}
+
 // Host feeds of one piece -> device staging, on the copy stream (sndvae_train_step_host)
-struct HostFeeds { const sndvae_inputs* in; const sndvae_noise* nz; int64_t* gen_adj; };
+struct HostFeeds { const sndvae_inputs* in; const sndvae_noise* nz; int64_t* gen_adj;
+                   const sndvae_inputs_compact* cin; uint32_t* gen_bits; };
 
 // The step.  Every graph's forward is independent of the rest of the batch (frozen-affine BN, SURVEY finding 3), so the
 // encoder + decoder + N^2 backward run piece by piece over contiguous graph ranges; with host feeds the H2D copy of piece k+1
 // and the D2H copy of piece k-1's generated_adj overlap piece k's kernels.  The node-level backward runs once at the end.
+enum { RUN_ACCUMULATE = 1, RUN_ALLREDUCE = 2 };
+static int run_body(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host,
+                    bool backward, long long global_batch, const HostFeeds* hf, int flags);
+// a step that fails after work was enqueued leaves the gradient arena / loss sums half-written: drain the streams (the caller may
+// free its host buffers as soon as we return) and mark the handle so that the next call starts from a clean slate
 static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host,
-               bool backward, long long global_batch, const HostFeeds* hf = nullptr) {
+               bool backward, long long global_batch, const HostFeeds* hf = nullptr, int flags = 0) {
+  if (h->poisoned && (flags & RUN_ACCUMULATE))
+    return fail(h, SNDVAE_E_STATE, "the previous step failed half-way: gradients cannot be accumulated onto it; call sndvae_zero_grads first");
+  const int r = run_body(h, in, nz, out, losses_host, backward, global_batch, hf, flags);
+  if (r) {
+    std::string keep = h->err;
+    if (h->cs) cudaStreamSynchronize(h->cs);
+    if (h->ds) cudaStreamSynchronize(h->ds);
+    cudaStreamSynchronize(h->stream);
+    cudaGetLastError();
+    h->B = h->cfg.batch_size; h->BS = h->B * h->S; h->Rn = h->B * h->N;
+    h->poisoned = backward ? 1 : 0; h->stt.used = 0;
+    h->err = keep;
+  } else if (backward) h->poisoned = 0;
+  return r;
+}
+static int run_body(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host,
+                    bool backward, long long global_batch, const HostFeeds* hf, int flags) {
   int r = check_inputs(h, in, nz); if (r) return r;
   const sndvae_config& c = h->cfg;
   const long long Bfull = h->B; const int N = h->N, S = h->S;
   const float gB = (float)(global_batch > 0 ? global_batch : Bfull);
   CK(cudaMemsetAsync(h->loss, 0, sizeof(float) * 8, h->stream));
-  if (backward) CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
+  if (backward && !(flags & RUN_ACCUMULATE)) CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
   if ((r = decoder_prepare(h, backward))) return r;
   // piece schedule: host mode walks the batch in chunk-sized pieces, with a half-sized first piece so that less of the
   // first H2D copy is exposed before any kernel can start
@@ -1100,8 +1212,18 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
       slice_io(h, g0, hf->in, hf->nz, nullptr, &hs, &hn, nullptr);
       slice_io(h, g0, in, nz, nullptr, &ds, &dn, nullptr);
 #define H2D_(f, n) CK(cudaMemcpyAsync((void*)ds.f, hs.f, sizeof(float) * (size_t)(gn * (n)), cudaMemcpyHostToDevice, h->cs))
+      if (hf->cin) {      // packed bytes over the bus; the dense staging is filled by the expand kernels of the piece loop
+        const sndvae_inputs_compact* ci = hf->cin; const long long W = (N + 31) / 32;
+#define H2C_(dst, src, per, T) CK(cudaMemcpyAsync((void*)((dst) + g0 * (per)), (src) + g0 * (per), sizeof(T) * (size_t)(gn * (per)), cudaMemcpyHostToDevice, h->cs))
+        H2C_(h->hc_features, ci->features, (long long)N * h->F, float); H2C_(h->hc_rel, ci->rel, (long long)N * N, float);
+        H2C_(h->hc_adj_bits, ci->adj_bits, (long long)S * N * W, uint32_t); H2C_(h->hc_adjt_bits, ci->adj_truth_bits, (long long)N * W, uint32_t);
+#undef H2C_
+        CK(cudaMemcpyAsync((void*)ds.feature_truth, ci->feature_truth + g0 * N * h->F, sizeof(float) * (size_t)(gn * N * h->F), cudaMemcpyHostToDevice, h->cs));
+        CK(cudaMemcpyAsync((void*)ds.spatial_truth, ci->spatial_truth + g0 * N * h->D, sizeof(float) * (size_t)(gn * N * h->D), cudaMemcpyHostToDevice, h->cs));
+      } else {
       H2D_(features, (long long)S * N * h->F); H2D_(adj, (long long)S * N * N); H2D_(rel, (long long)S * N * N); H2D_(adj_truth, (long long)N * N);
       H2D_(feature_truth, (long long)N * h->F); H2D_(spatial_truth, (long long)N * h->D);
+      }
 #undef H2D_
       CK(cudaMemcpyAsync((void*)dn.eps_sg, hn.eps_sg, sizeof(float) * (size_t)(gn * S * c.sg_latent_size), cudaMemcpyHostToDevice, h->cs));
       if (h->dis) {
@@ -1116,6 +1238,13 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
     sndvae_inputs vin; sndvae_noise vnz; sndvae_outputs vout; memset(&vin, 0, sizeof vin); memset(&vnz, 0, sizeof vnz); memset(&vout, 0, sizeof vout);
     slice_io(h, g0, in, nz, out, &vin, &vnz, &vout);
     if (hf) CK(cudaStreamWaitEvent(h->stream, h->pev[2 * pi], 0));
+    if (hf && hf->cin) {    // unpack this piece's feeds into the dense staging the kernels read
+      const long long W = (N + 31) / 32;
+      LEW(expand_bits_k, gn * S * N * N, h->hc_adj_bits + g0 * S * N * W, (float*)vin.adj, gn * S * N, N, (int)W);
+      LEW(expand_bits_k, gn * N * N, h->hc_adjt_bits + g0 * N * W, (float*)vin.adj_truth, gn * N, N, (int)W);
+      LEW(repeat_rows_k, gn * S * N * N, h->hc_rel + g0 * N * N, (float*)vin.rel, gn, S, (long long)N * N);
+      LEW(repeat_rows_k, gn * S * N * h->F, h->hc_features + g0 * N * h->F, (float*)vin.features, gn, S, (long long)N * h->F);
+    }
     view_shift(h, g0); h->B = gn; h->BS = gn * S; h->Rn = gn * N;
     mark(h, "encoder");
     r = encoder_fwd(h, &vin);
@@ -1124,6 +1253,13 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
     if (!r) r = decoder_fwd(h, &vin, out ? &vout : nullptr, backward, gB);
     view_shift(h, -g0); h->B = Bfull; h->BS = Bfull * S; h->Rn = Bfull * N;
     if (r) return r;
+    if (hf && hf->gen_bits && out && out->generated_adj) {
+      const long long W = (N + 31) / 32;
+      LAUNCH(pack_adj_bits_k, cdiv(gn * N * W * 32, 256), 256, 0, (const long long*)out->generated_adj + g0 * N * N, h->hc_gen_bits + g0 * N * W, gn * N, N, (int)W);
+      CK(cudaEventRecord(h->pev[2 * pi + 1], h->stream));
+      CK(cudaStreamWaitEvent(h->ds, h->pev[2 * pi + 1], 0));
+      CK(cudaMemcpyAsync(hf->gen_bits + g0 * N * W, h->hc_gen_bits + g0 * N * W, sizeof(uint32_t) * (size_t)(gn * N * W), cudaMemcpyDeviceToHost, h->ds));
+    }
     if (hf && hf->gen_adj && out && out->generated_adj) {
       CK(cudaEventRecord(h->pev[2 * pi + 1], h->stream));
       CK(cudaStreamWaitEvent(h->ds, h->pev[2 * pi + 1], 0));
@@ -1134,9 +1270,12 @@ static int run(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, snd
   if (c.loss_variant == SNDVAE_LOSS_DIP && (r = dip_forward(h))) return r;      // needs every piece's posterior means
   if (c.loss_variant == SNDVAE_LOSS_TC && (r = tc_forward(h))) return r;        // ... and samples
   if (backward && (r = backward_rest(h, in, nz, gB))) return r;
-  mark(h, "end");
+  mark(h, "allreduce");
   CK(cudaGetLastError());
-  r = fetch_losses(h, losses_host);
+  const bool reduce = backward && (flags & RUN_ALLREDUCE) && h->comm && h->world > 1;
+  if (reduce && (r = allreduce_arena(h, true))) return r;
+  mark(h, "end");
+  r = fetch_losses(h, losses_host, reduce ? h->world : 1);
   report_stages(h);
   return r;
 }
@@ -1170,9 +1309,10 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
+  h->hf_ready = 0; h->hc_ready = 0; h->hc_features = nullptr; h->poisoned = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr; h->zz_planes = nullptr; h->zz_cap = 0;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
-  h->stt.used = 0; h->stt.on = getenv("SNDVAE_STAGE_TIMING") != nullptr;
+  h->stt.used = 0; h->stt.on = h->stt.print = getenv("SNDVAE_STAGE_TIMING") != nullptr; h->stt.steps = 0;
   sndvae_config& c = h->cfg;
   if (c.num_nodes < 2 || c.batch_size < 1 || c.num_feature < 1 || c.spatial_dim < 1 || c.node_h_size < 1)
     return fail(h, SNDVAE_E_ARG, "bad config: num_nodes=%d batch_size=%d", c.num_nodes, c.batch_size);
@@ -1193,6 +1333,13 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   h->Chv = h->dis ? 2 * h->H : h->H; h->C1 = c.e_d_hidden[0]; h->C2 = c.e_d_hidden[1];
   h->B = c.batch_size; h->BS = h->B * h->S; h->Rn = h->B * h->N;
   if (c.edge_capacity <= 0) c.edge_capacity = 4 * h->N;
+  { // widest per-node channel count any node-level layer reads or writes (conv1d inputs / outputs, concatenations)
+    int m = 64;
+    const int cand[] = {h->F, h->D, h->Chv, c.s_channel[0], c.s_channel[1], c.s_channel[2], c.g_conv_hidden[0] + h->F,
+                        c.g_conv_hidden[1] + h->F, c.n_d_channel[0], c.n_d_channel[1], c.s_d_channel[0], c.s_d_channel[1],
+                        c.s_d_channel[2], c.sg_conv_hidden[0][2], c.sg_conv_hidden[1][2]};
+    for (int v : cand) { if (v < 1) return fail(h, SNDVAE_E_ARG, "bad config: a layer width is %d", v); if (v > m) m = v; }
+    h->max_c = m; }
   if (c.use_tensor_cores && (h->C1 != TC_C1 || h->C2 != TC_C2))
     return fail(h, SNDVAE_E_ARG, "tensor-core e2e path requires e_d_hidden = (%d, %d)", TC_C1, TC_C2);
   if (c.chunk_graphs <= 0) {
@@ -1243,6 +1390,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
 int sndvae_destroy(sndvae_t* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
   if (h->spec) { spec_destroy(h->sp); ytc_destroy(h->ytc); }
   for (void* p : h->allocs) cudaFree(p);
@@ -1323,10 +1471,57 @@ int sndvae_apply_adam(sndvae_t* h) {
   CK(cudaGetLastError());
   return 0;
 }
+int sndvae_zero_grads(sndvae_t* h) {
+  if (!h) return SNDVAE_E_ARG;
+  CK(cudaMemsetAsync(h->G, 0, sizeof(float) * h->nparam, h->stream));
+  h->poisoned = 0;
+  return 0;
+}
+int sndvae_grads_accumulate(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host, int64_t gb) {
+  if (!h) return SNDVAE_E_ARG;
+  return run(h, in, nz, out, losses_host, true, gb, nullptr, RUN_ACCUMULATE);
+}
+int sndvae_allreduce_grads(sndvae_t* h) {
+  if (!h) return SNDVAE_E_ARG;
+  if (!h->comm) return fail(h, SNDVAE_E_STATE, "sndvae_allreduce_grads: no communicator (call sndvae_comm_init first)");
+  return allreduce_arena(h, false);
+}
 int sndvae_train_step(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host) {
   if (!h) return SNDVAE_E_ARG;
-  int r = run(h, in, nz, out, losses_host, true, 0); if (r) return r;
+  // with a communicator: local sums scaled by 1 / (world B), one all-reduce of the arena (+ the loss sums), then Adam
+  int r = run(h, in, nz, out, losses_host, true, (long long)h->world * h->B, nullptr, RUN_ALLREDUCE); if (r) return r;
   return sndvae_apply_adam(h);
+}
+int sndvae_set_beta(sndvae_t* h, float beta) {
+  if (!h) return SNDVAE_E_ARG;
+  if (!(beta >= 0.f)) return fail(h, SNDVAE_E_ARG, "beta must be >= 0");
+  h->cfg.beta = beta;
+  return 0;
+}
+
+int sndvae_comm_unique_id(uint8_t* id_host) {
+  if (!id_host) return SNDVAE_E_ARG;
+  if (nccl_load()) return SNDVAE_E_CUDA;
+  nccl_unique_id id;
+  if (g_nccl.GetUniqueId(&id) != 0) return SNDVAE_E_CUDA;
+  memcpy(id_host, id.internal, 128);
+  return 0;
+}
+int sndvae_comm_init(sndvae_t* h, const uint8_t* id_host, int32_t rank, int32_t world) {
+  if (!h || !id_host) return SNDVAE_E_ARG;
+  if (world < 1 || rank < 0 || rank >= world) return fail(h, SNDVAE_E_ARG, "sndvae_comm_init: rank %d of %d", rank, world);
+  if (h->comm) return fail(h, SNDVAE_E_STATE, "sndvae_comm_init: the handle already has a communicator");
+  if (const char* e = nccl_load()) return fail(h, SNDVAE_E_CUDA, "NCCL unavailable: %s", e);
+  nccl_unique_id id; memcpy(id.internal, id_host, 128);
+  CKN(g_nccl.CommInitRank(&h->comm, world, id, rank));
+  h->rank = rank; h->world = world;
+  return 0;
+}
+int sndvae_comm_info(const sndvae_t* h, int32_t* rank, int32_t* world) {
+  if (!h) return SNDVAE_E_ARG;
+  if (rank) *rank = h->rank;
+  if (world) *world = h->comm ? h->world : 1;
+  return 0;
 }
 
 int sndvae_generate(sndvae_t* h, const float* z_s, const float* z_sg, const float* z_g, sndvae_outputs* out) {
@@ -1345,15 +1540,31 @@ int sndvae_generate(sndvae_t* h, const float* z_s, const float* z_sg, const floa
   return 0;
 }
 
-int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, int64_t* gen_adj_host, float* losses_host) {
-  if (!h) return SNDVAE_E_ARG;
-  int r = check_inputs(h, in, nz); if (r) return r;
+// host feeds -> device staging -> forward + backward (pipelined pieces); optional accumulate / all-reduce; no update
+static int grads_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, int64_t* gen_adj_host, float* losses_host,
+                      long long global_batch, int flags, const sndvae_inputs_compact* cin = nullptr, uint32_t* gen_bits_host = nullptr) {
+  int r;
+  if (cin) {
+    if (!nz) return fail(h, SNDVAE_E_ARG, "noise struct is NULL");
+    if (!cin->features || !cin->adj_bits || !cin->rel || !cin->adj_truth_bits || !cin->feature_truth || !cin->spatial_truth)
+      return fail(h, SNDVAE_E_ARG, "a required compact feed (features, adj_bits, rel, adj_truth_bits, feature_truth, spatial_truth) is NULL");
+    if (!nz->eps_sg || (h->dis && (!nz->eps_s || !nz->eps_g))) return fail(h, SNDVAE_E_ARG, "a required noise tensor is NULL");
+  } else if ((r = check_inputs(h, in, nz))) return r;
   const sndvae_config& c = h->cfg; const int N = h->N; const long long B = h->B, BS = h->BS;
-  if (!h->hf_features) {
+  if (!h->hf_ready) {
+    if (h->hf_features) return fail(h, SNDVAE_E_STATE, "an earlier host-feed staging allocation failed; destroy the handle");
     DA(h->hf_features, BS * N * h->F); DA(h->hf_adj, BS * N * N); DA(h->hf_rel, BS * N * N); DA(h->hf_adj_truth, B * N * N);
     DA(h->hf_feature_truth, B * N * h->F); DA(h->hf_spatial_truth, B * N * h->D);
     DA(h->hf_eps_s, B * c.s_latent_size); DA(h->hf_eps_sg, BS * c.sg_latent_size); DA(h->hf_eps_g, B * c.g_latent_size);
     DA(h->hf_gen_adj, B * N * N);
+    h->hf_ready = 1;
+  }
+  if (cin && !h->hc_ready) {
+    if (h->hc_features) return fail(h, SNDVAE_E_STATE, "an earlier compact-feed staging allocation failed; destroy the handle");
+    const long long W = (N + 31) / 32;
+    DA(h->hc_features, B * N * h->F); DA(h->hc_rel, B * N * N); DA(h->hc_adj_bits, BS * N * W); DA(h->hc_adjt_bits, B * N * W);
+    DA(h->hc_gen_bits, B * N * W);
+    h->hc_ready = 1;
   }
   if (!h->cs) {
     CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->ds, cudaStreamNonBlocking));
@@ -1363,12 +1574,35 @@ int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_no
   din.features = h->hf_features; din.adj = h->hf_adj; din.rel = h->hf_rel; din.adj_truth = h->hf_adj_truth;
   din.feature_truth = h->hf_feature_truth; din.spatial_truth = h->hf_spatial_truth;
   sndvae_noise dnz; dnz.eps_s = h->hf_eps_s; dnz.eps_sg = h->hf_eps_sg; dnz.eps_g = h->hf_eps_g;
-  sndvae_outputs o; memset(&o, 0, sizeof o); o.generated_adj = gen_adj_host ? (int64_t*)h->hf_gen_adj : nullptr;
-  HostFeeds hfd; hfd.in = in; hfd.nz = nz; hfd.gen_adj = gen_adj_host;
-  r = run(h, &din, &dnz, &o, losses_host, true, 0, &hfd); if (r) return r;
-  r = sndvae_apply_adam(h); if (r) return r;
-  CK(cudaStreamSynchronize(h->ds));
-  CK(cudaStreamSynchronize(h->stream));
+  sndvae_outputs o; memset(&o, 0, sizeof o); o.generated_adj = (gen_adj_host || gen_bits_host) ? (int64_t*)h->hf_gen_adj : nullptr;
+  HostFeeds hfd; hfd.in = in; hfd.nz = nz; hfd.gen_adj = gen_adj_host; hfd.cin = cin; hfd.gen_bits = gen_bits_host;
+  return run(h, &din, &dnz, &o, losses_host, true, global_batch, &hfd, flags);
+}
+int sndvae_grads_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, int64_t* gen_adj_host, float* losses_host,
+                      int64_t global_batch, int32_t accumulate) {
+  if (!h) return SNDVAE_E_ARG;
+  int r = grads_host(h, in, nz, gen_adj_host, losses_host, global_batch, accumulate ? RUN_ACCUMULATE : 0); if (r) return r;
+  CK(cudaStreamSynchronize(h->ds));      // the caller's generated_adj buffer is complete on return
+  return 0;
+}
+int sndvae_train_step_host(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, int64_t* gen_adj_host, float* losses_host) {
+  if (!h) return SNDVAE_E_ARG;
+  int r = grads_host(h, in, nz, gen_adj_host, losses_host, (long long)h->world * h->B, RUN_ALLREDUCE); if (r) return r;
+  r = sndvae_apply_adam(h);
+  cudaError_t e1 = cudaStreamSynchronize(h->ds), e2 = cudaStreamSynchronize(h->stream);
+  if (r) return r;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "stream synchronize: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+  return 0;
+}
+
+int sndvae_train_step_host_compact(sndvae_t* h, const sndvae_inputs_compact* in, const sndvae_noise* nz, uint32_t* gen_bits_host,
+                                   float* losses_host) {
+  if (!h || !in) return SNDVAE_E_ARG;
+  int r = grads_host(h, nullptr, nz, nullptr, losses_host, (long long)h->world * h->B, RUN_ALLREDUCE, in, gen_bits_host); if (r) return r;
+  r = sndvae_apply_adam(h);
+  cudaError_t e1 = cudaStreamSynchronize(h->ds), e2 = cudaStreamSynchronize(h->stream);
+  if (r) return r;
+  if (e1 != cudaSuccess || e2 != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "stream synchronize: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
   return 0;
 }
 
@@ -1400,6 +1634,23 @@ int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms, int64_t* launch
   if (flops) *flops = fl;
   if (reset) h->ev_used = 0;
   return 0;
+}
+
+int sndvae_stage_times(sndvae_t* h, int32_t enable, char* names_host, double* ms_host, int32_t capacity, int64_t* steps_host) {
+  if (!h) return SNDVAE_E_ARG;
+  StageTimer& t = h->stt;
+  int n = 0;
+  if (names_host && ms_host) {
+    CK(cudaStreamSynchronize(h->stream));
+    for (auto& a : t.total) {
+      if (n >= capacity) break;
+      snprintf(names_host + (size_t)n * 32, 32, "%s", a.first.c_str()); ms_host[n] = a.second; ++n;
+    }
+  }
+  if (steps_host) *steps_host = t.steps;
+  t.total.clear(); t.steps = 0; t.used = 0;
+  t.on = enable ? 1 : t.print;
+  return n;
 }
 
 int sndvae_threshold_logits(sndvae_t* h, const float* logits, int64_t n, int64_t* out) {

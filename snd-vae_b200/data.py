@@ -53,3 +53,39 @@ def tile_pool(pool: Dict[str, np.ndarray], batch: int, pool_graphs: int, samplin
         per = sampling_num if k in ("adj", "features", "spatial", "rel") else 1
         out[k] = np.concatenate([v] * reps, axis=0)[: batch * per]
     return out
+
+
+# ---- compact feeds (include/sndvae.h sndvae_inputs_compact) ---------------------------------------------------------
+def pack_adj_bits(adj: np.ndarray) -> np.ndarray:
+    """0/1 adjacency [..., N, N] -> bit rows [..., N, W] uint32, W = ceil(N / 32); bit (j % 32) of word (j / 32) = adj[.., i, j] != 0."""
+    N = adj.shape[-1]
+    W = (N + 31) // 32
+    b = np.zeros(adj.shape[:-1] + (W * 32,), dtype=np.uint8)
+    b[..., :N] = adj != 0
+    return np.ascontiguousarray(np.packbits(b, axis=-1, bitorder="little")).view("<u4").reshape(adj.shape[:-1] + (W,))
+
+
+def unpack_adj_bits(bits: np.ndarray, num_nodes: int, dtype=np.int64) -> np.ndarray:
+    """Inverse of pack_adj_bits: [..., N, W] uint32 -> [..., N, N]."""
+    by = np.ascontiguousarray(bits.astype("<u4")).view(np.uint8)
+    return np.unpackbits(by, axis=-1, bitorder="little")[..., :num_nodes].astype(dtype)
+
+
+def pack_feeds(feeds: Dict[str, np.ndarray], sampling_num: int) -> Dict[str, np.ndarray]:
+    """The dense feed_dict arrays of main.py:253-264 -> the compact host feeds: per-graph `features` / `rel` once (the dense
+    rows b*S .. b*S+S-1 are copies, main.py:307-309), adjacencies as bit rows.  Raises if an adjacency is not 0/1 or the S
+    copies differ -- the compact format cannot carry those."""
+    S = sampling_num
+    for k in ("adj", "adj_truth"):
+        a = feeds[k]
+        if not np.array_equal(a, (a != 0).astype(a.dtype)):
+            raise ValueError(f"feed '{k}' is not a 0/1 adjacency: use the dense entry point")
+    rel = feeds["rel"].reshape(feeds["rel"].shape[:3])
+    for k, v in (("rel", rel), ("features", feeds["features"])):
+        g = v.reshape((-1, S) + v.shape[1:])
+        if not (g == g[:, :1]).all():
+            raise ValueError(f"feed '{k}' differs between the samples of a graph: use the dense entry point")
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    return {"features": f32(feeds["features"][::S]), "adj_bits": pack_adj_bits(feeds["adj"]), "rel": f32(rel[::S]),
+            "adj_truth_bits": pack_adj_bits(feeds["adj_truth"]), "feature_truth": f32(feeds["feature_truth"]),
+            "spatial_truth": f32(feeds["spatial_truth"])}

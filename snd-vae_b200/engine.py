@@ -225,6 +225,51 @@ class Engine:
     def apply_adam(self):
         self._check(self.lib.sndvae_apply_adam(self._h))
 
+    def zero_grads(self):
+        self._check(self.lib.sndvae_zero_grads(self._h))
+
+    def grads_accumulate(self, feeds, noise, fetch=("generated_adj",), global_batch=0):
+        """One micro-batch of a larger batch: adds its gradient (scaled 1 / global_batch) to the arena."""
+        inp, nz, keep = self._pack(feeds, noise)
+        out, res = self._outs(fetch)
+        losses = np.zeros(8, dtype=np.float32)
+        self._check(self.lib.sndvae_grads_accumulate(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data, global_batch))
+        res["overall_loss"] = losses[:self.n_losses].copy()
+        return res
+
+    def grads_accumulate_packed(self, inp, nz, out, losses, global_batch):
+        self._check(self.lib.sndvae_grads_accumulate(self._h, C.byref(inp), C.byref(nz), C.byref(out), losses.ctypes.data, global_batch))
+
+    def set_beta(self, beta: float):
+        """OptimizerVAE(..., beta=...) (optimizer.py:124): the KL / regulariser weight."""
+        self._check(self.lib.sndvae_set_beta(self._h, float(beta)))
+        self.cfg.beta = float(beta)
+
+    # -- data parallelism ---------------------------------------------------------------
+    def comm_init(self, rank: int, world: int, broadcast=None):
+        """Create the handle's NCCL communicator.  `broadcast(tensor_uint8[128])` must copy rank 0's tensor to every rank
+        (default: torch.distributed.broadcast on the default process group)."""
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            rc = self.lib.sndvae_comm_unique_id(buf)
+            if rc != 0:
+                raise SndvaeError("sndvae_comm_unique_id failed: NCCL is not available in this process")
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        if broadcast is None:
+            import torch.distributed as dist
+            dev_ident = ident.to(self.device) if dist.get_backend() == "nccl" else ident
+            dist.broadcast(dev_ident, src=0)
+            ident = dev_ident.cpu()
+        else:
+            ident = broadcast(ident)
+        raw = (C.c_uint8 * 128)(*[int(x) for x in ident.tolist()])
+        self._check(self.lib.sndvae_comm_init(self._h, raw, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def allreduce_grads(self):
+        self._check(self.lib.sndvae_allreduce_grads(self._h))
+
     def train_step(self, feeds, noise, fetch=("generated_adj",)):
         inp, nz, keep = self._pack(feeds, noise)
         out, res = self._outs(fetch)
@@ -254,6 +299,35 @@ class Engine:
                 setattr(nz, k, a.ctypes.data)
         self._check(self.lib.sndvae_train_step_host(self._h, C.byref(inp), C.byref(nz), gen_adj_np.ctypes.data,
                                                     losses_np.ctypes.data))
+
+    def grads_host(self, feeds_np, noise_np, gen_adj_np, losses_np, global_batch=0, accumulate=False):
+        """Host feeds in, gradient arena (+ generated_adj, losses) out; no all-reduce, no update."""
+        inp = _lib.Inputs()
+        for k in FEED_KEYS:
+            a = feeds_np.get(k)
+            if a is not None:
+                setattr(inp, k, a.ctypes.data)
+        nz = _lib.Noise()
+        for k in NOISE_KEYS:
+            a = noise_np.get(k)
+            if a is not None:
+                setattr(nz, k, a.ctypes.data)
+        self._check(self.lib.sndvae_grads_host(self._h, C.byref(inp), C.byref(nz), gen_adj_np.ctypes.data if gen_adj_np is not None else None,
+                                               losses_np.ctypes.data, int(global_batch), 1 if accumulate else 0))
+
+    def train_step_host_compact(self, compact_np, noise_np, gen_bits_np, losses_np):
+        """sndvae_train_step_host_compact: packed host feeds (preprocessing.pack_feeds) in, bit-packed adjacency out."""
+        inp = _lib.InputsCompact()
+        for k, _ in _lib.InputsCompact._fields_:
+            setattr(inp, k, compact_np[k].ctypes.data)
+        nz = _lib.Noise()
+        for k in NOISE_KEYS:
+            a = noise_np.get(k)
+            if a is not None:
+                setattr(nz, k, a.ctypes.data)
+        self._check(self.lib.sndvae_train_step_host_compact(self._h, C.byref(inp), C.byref(nz),
+                                                            gen_bits_np.ctypes.data if gen_bits_np is not None else None,
+                                                            losses_np.ctypes.data))
 
     def synth_inputs(self, seed: int) -> Dict[str, torch.Tensor]:
         """Device-side synthetic feeds (random-geometric graphs + spanning-forest samples) for this engine's batch:
@@ -304,6 +378,18 @@ class Engine:
         if got < 0:
             self._check(int(got))
         return buf[:got]
+
+    def stage_times(self, enable=True):
+        """Per-stage CUDA-event totals since the previous call: ({stage: ms}, steps); `enable` arms the timers for the next steps."""
+        cap = 64
+        names = C.create_string_buffer(32 * cap)
+        ms = (C.c_double * cap)()
+        steps = C.c_int64()
+        n = self.lib.sndvae_stage_times(self._h, 1 if enable else 0, names, ms, cap, C.byref(steps))
+        if n < 0:
+            self._check(int(n))
+        out = {names.raw[32 * i:32 * (i + 1)].split(b"\0", 1)[0].decode(): ms[i] for i in range(n)}
+        return out, int(steps.value)
 
     def launch_count(self) -> int:
         return int(self.lib.sndvae_launch_count(self._h))

@@ -103,14 +103,21 @@ class _ModelBase:
         return out
 
     # -- tf.train.Saver stand-in (main.py:299,351-352): .npz keyed by TF variable name ----
+    @staticmethod
+    def _ckpt_path(path):
+        path = str(path)
+        return path if path.endswith(".npz") else path + ".npz"      # saver.save(p) / saver.restore(p) take the same name
+
     def save(self, path):
         p = {k: v.numpy() for k, v in self.engine.get_params().items()}
         m, v, bp = self.engine.get_adam()
-        np.savez(path, **p, **{"adam_m/" + k: x.numpy() for k, x in m.items()},
-                 **{"adam_v/" + k: x.numpy() for k, x in v.items()}, adam_beta_pows=bp)
+        with open(self._ckpt_path(path), "wb") as f:
+            np.savez(f, **p, **{"adam_m/" + k: x.numpy() for k, x in m.items()},
+                     **{"adam_v/" + k: x.numpy() for k, x in v.items()}, adam_beta_pows=bp)
+        return self._ckpt_path(path)
 
     def restore(self, path):
-        z = np.load(path)
+        z = np.load(self._ckpt_path(path))
         names = [n for n, _, _ in self.engine.table]
         self.engine.set_params({k: torch.from_numpy(z[k]) for k in names})
         if "adam_beta_pows" in z:

@@ -15,9 +15,9 @@ class OptimizerVAE(object):
             raise ValueError(f"model_type '{FLAGS.model_type}' is not built (geoGCN, posGCN: SURVEY section 2 row 13)")
         self.model = model
         model.optimizer = self
-        model.engine.cfg.beta = float(beta)
-        if float(beta) != 1.0 and FLAGS.model_type in ("disentangled", "base", "beta-TCVAE"):
-            raise ValueError("beta is fixed at engine creation; construct the model with FLAGS beta=1 (main.py:515)")
+        # beta weights the KL terms ('disentangled', 'base', 'beta-TCVAE': optimizer.py:164,190) or the DIP regulariser
+        # ('NED-VAE-IP': optimizer.py:183); the reference hands it to this constructor (main.py:285-296,515)
+        model.engine.set_beta(float(beta))
         for name in ("opt_op", "cost", "adj_cost", "node_cost", "spatial_cost", "kl_sg", "kl_s", "kl_g"):
             setattr(self, name, Fetch(self, name))
         if model.engine.dis:
@@ -29,5 +29,11 @@ class OptimizerVAE(object):
     def grads_vars(self):
         """optimizer.compute_gradients(cost) (optimizer.py:198): (gradient, variable-name) pairs of
         the last backward pass, as views of the flat gradient arena."""
-        g = self.model.engine.get_grads()
-        return [(g[name], name) for name, _, _ in self.model.engine.table]
+        flat = self.model.engine.grads_tensor()          # zero-copy view of the device arena; entries are slices of it
+        out = []
+        for name, off, shape in self.model.engine.table:
+            n = 1
+            for d in shape:
+                n *= d
+            out.append((flat[off:off + n].view(shape), name))
+        return out

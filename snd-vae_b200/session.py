@@ -62,28 +62,40 @@ class Session:
         return False
 
     def run(self, fetches, feed_dict=None):
+        if fetches is None or isinstance(fetches, _NoOp):
+            return None                           # sess.run(tf.global_variables_initializer()) (main.py:302)
         single = not isinstance(fetches, (list, tuple))
         flist: List = [fetches] if single else list(fetches)
         flat = []
         for f in flist:
             flat.extend(f if isinstance(f, (list, tuple)) else [f])
+        if not any(isinstance(f, Fetch) for f in flat):
+            return None if single else [None for _ in flist]
         models = {id(f.owner.model if hasattr(f.owner, "model") else f.owner): (f.owner.model if hasattr(f.owner, "model") else f.owner)
                   for f in flat if isinstance(f, Fetch)}
         if len(models) != 1:
             raise SndvaeError("Session.run needs fetches of exactly one model")
         model = next(iter(models.values()))
-        values = model._run([f.name for f in flat], feed_dict or {})
+        values = model._run([f.name for f in flat if isinstance(f, Fetch)], feed_dict or {})
         it = iter(values)
+        nxt = lambda f: next(it) if isinstance(f, Fetch) else None     # no-op fetches (initialisers) come back as None
         out = []
         for f in flist:
             if isinstance(f, (list, tuple)):
-                out.append([next(it) for _ in f])
+                out.append([nxt(x) for x in f])
             else:
-                out.append(next(it))
+                out.append(nxt(f))
         return out[0] if single else out
+
+
+class _NoOp:
+    """A fetch that does nothing and returns None (TF: an Operation, e.g. the variable initialiser)."""
+
+    def __repr__(self):
+        return "<no-op>"
 
 
 def global_variables_initializer():
     """The reference calls sess.run(tf.global_variables_initializer()) (main.py:302); here the
     constructor already initialised the variables, so this is an accepted no-op fetch."""
-    return None
+    return _NoOp()

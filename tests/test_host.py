@@ -200,3 +200,10 @@ def test_make_config_refuses_the_3hop_branch():
         sv.make_config(8, 2, "disentangled", sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)))
     cfg = sv.make_config(8, 2, "disentangled", sg_conv_hidden=((4, 5, 6), (7, 8, 9)))
     assert [list(r) for r in cfg.sg_conv_hidden] == [[4, 5, 6], [7, 8, 9]]
+
+
+def test_session_initializer_fetch_is_a_noop():
+    """main.py:301-302: `sess.run(tf.global_variables_initializer())` right after tf.Session(); the shim returns None."""
+    with session.Session() as sess:
+        assert sess.run(session.global_variables_initializer()) is None
+        assert sess.run([session.global_variables_initializer()]) == [None]

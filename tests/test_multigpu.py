@@ -1,0 +1,86 @@
+"""Multi-GPU correctness on hardware; run with `gpurun --gpus 2 -- python -m pytest tests/test_multigpu.py -m gpu`.
+Two ranks, one process per GPU, NCCL: each rank takes half of a global batch through the library's own data-parallel step
+(sndvae_comm_init + sndvae_train_step: local sums scaled by 1 / global batch -> ncclAllReduce of the gradient arena and of the
+loss sums -> TF-Adam).  Rank 0's post-step parameters, losses and its half of generated_adj must equal the 1-GPU step on the
+concatenated batch.  Skipped (not failed) on a box with one GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sndvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _shard(inp, noise, r, b, S):
+    sl = slice(r * b, (r + 1) * b); sls = slice(r * b * S, (r + 1) * b * S)
+    si = {k: (v[sls] if k in ("adj", "features", "spatial", "rel") else v[sl]) for k, v in inp.items()}
+    sn = {"eps_s": noise["eps_s"][sl], "eps_g": noise["eps_g"][sl], "eps_sg": noise["eps_sg"][sls]}
+    return si, sn
+
+
+def _worker(rank, world, port, N, b, S, steps, host_feeds, outdir):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import sndvae_b200 as sv
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    cfg = O.Config(num_nodes=N, sampling_num=S)
+    P = O.init_params(cfg, 7, torch.float32)
+    inp = O.synthetic_inputs(cfg, world * b, 5, torch.float32); noise = O.synthetic_noise(cfg, world * b, 9, torch.float32)
+    si, sn = _shard(inp, noise, rank, b, S)
+    eng = sv.Engine(sv.make_config(N, b, "disentangled", sampling_num=S, chunk_graphs=2))
+    eng.set_params(P)
+    eng.comm_init(rank, world)
+    losses, gen = [], None
+    for _ in range(steps):
+        if host_feeds:
+            used = {k: np.ascontiguousarray(si[k].numpy()) for k in ("features", "adj", "rel", "adj_truth", "feature_truth", "spatial_truth")}
+            g = np.zeros((b, N, N), np.int64); ls = np.zeros(8, np.float32)
+            eng.train_step_host(used, {k: v.numpy() for k, v in sn.items()}, g, ls)
+            losses.append(ls[:7].copy()); gen = g
+        else:
+            r = eng.train_step(si, sn)
+            losses.append(r["overall_loss"]); gen = r["generated_adj"].cpu().numpy()
+    Pn = eng.get_params()
+    np.savez(os.path.join(outdir, f"rank{rank}.npz"), losses=np.asarray(losses), gen=gen, **{k: v.numpy() for k, v in Pn.items()})
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("host_feeds", [False, True])
+def test_two_gpu_step_equals_one_gpu_step(built, tmp_path, host_feeds):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    N, b, S, world, steps = 16, 3, 2, 2, 2
+    cfg = O.Config(num_nodes=N, sampling_num=S)
+    P = O.init_params(cfg, 7, torch.float32)
+    inp = O.synthetic_inputs(cfg, world * b, 5, torch.float32); noise = O.synthetic_noise(cfg, world * b, 9, torch.float32)
+    torch.cuda.set_device(0)
+    ref = built.Engine(built.make_config(N, world * b, "disentangled", sampling_num=S, chunk_graphs=2))
+    ref.set_params(P)
+    ref_losses, ref_gen = [], None
+    for _ in range(steps):
+        r = ref.train_step(inp, noise)
+        ref_losses.append(r["overall_loss"]); ref_gen = r["generated_adj"].cpu().numpy()
+    P1 = ref.get_params(); ref.close()
+    mp.spawn(_worker, args=(world, _free_port(), N, b, S, steps, host_feeds, str(tmp_path)), nprocs=world, join=True)
+    z0, z1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    np.testing.assert_allclose(z0["losses"], np.asarray(ref_losses), rtol=2e-5)       # global-batch means, identical on both ranks
+    np.testing.assert_allclose(z1["losses"], z0["losses"], rtol=1e-6)
+    assert np.array_equal(z0["gen"], ref_gen[:b]) and np.array_equal(z1["gen"], ref_gen[b:])
+    for k in P1:
+        np.testing.assert_allclose(z0[k], P1[k].numpy(), rtol=0, atol=2e-6, err_msg=k)
+        assert np.array_equal(z0[k], z1[k]), k                                         # replicas stay bit-identical

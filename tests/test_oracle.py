@@ -311,3 +311,22 @@ def test_golden_protein_fixture():
         for k in gr:
             d = z["gradsum/" + k]
             assert np.allclose([gr[k].sum().item(), gr[k].abs().sum().item()], d, rtol=1e-6, atol=1e-11), (mode, k)
+
+
+@pytest.mark.parametrize("model,N,B,S", [("disentangled", 8, 3, 2), ("disentangled", 25, 2, 3), ("base", 7, 2, 1)])
+def test_fft_form_equals_factored(model, N, B, S):
+    """Third form of the width-N correlations (torch.fft; what the N = 1024 GPU parity test uses as its checker) against the
+    block-Toeplitz form: losses, logits and every gradient to fp64 round-off."""
+    cfg = O.Config(num_nodes=N, model_type=model, sampling_num=S)
+    P = O.init_params(cfg, 7, torch.float64)
+    g = torch.Generator().manual_seed(1)
+    for k in P:
+        P[k] = P[k] + 0.05 * torch.randn(P[k].shape, generator=g, dtype=torch.float64)
+    inp = O.synthetic_inputs(cfg, B, 5, torch.float64)
+    nz = O.synthetic_noise(cfg, B, 9, torch.float64)
+    a = O.loss_and_grads(P, inp, nz, cfg, "factored")
+    b = O.loss_and_grads(P, inp, nz, cfg, "fft")
+    assert abs(float(a[3]["cost"]) - float(b[3]["cost"])) < 1e-12
+    assert (a[2]["generated_adj_prob"] - b[2]["generated_adj_prob"]).abs().max().item() < 1e-12
+    for k in a[4]:
+        assert (a[4][k] - b[4][k]).abs().max().item() < 1e-12, k
