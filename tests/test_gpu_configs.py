@@ -114,7 +114,7 @@ def test_checkpoint_roundtrip_identical_next_step(built, tmp_path):
     b = model_m.SGCNModelVAE(ph, F.num_feature, N, seed=99)  # different initial weights: everything must come from the file
     b.restore(path)
     rb = b.engine.train_step(inp, noise)
-    assert np.array_equal(ra["overall_loss"], rb["overall_loss"])
+    np.testing.assert_allclose(ra["overall_loss"], rb["overall_loss"], rtol=1e-6)     # loss sums go through atomics
     assert torch.equal(ra["generated_adj"].cpu(), rb["generated_adj"].cpu())
     Pa, Pb = a.engine.get_params(), b.engine.get_params()
     (ma, va, bpa), (mb, vb, bpb) = a.engine.get_adam(), b.engine.get_adam()
