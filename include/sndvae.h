@@ -272,6 +272,13 @@ int sndvae_stage_times(sndvae_t* h, int32_t enable, char* names_host, double* ms
  * with the e2e layers); offered as a standalone operator because layers.py defines it.  tcgen05 bf16x3. */
 int sndvae_inner_product_decode(sndvae_t* h, const float* z, int64_t batch, int32_t num_nodes, int32_t dim, float* logits);
 
+/* The node-level contraction kernel on its own (tsgemm.cuh: the GEMM under `linear`, layers.py:566-576, tf.layers.conv1d and the
+ * SpatialGraphConvolution coefficient products), exposed so that it can be checked against numpy at arbitrary shapes:
+ * row-major C[M,N] = alpha op(A) op(B) + beta C (+ bias[N], may be NULL); tA: A is stored [K,M]; tB: B is stored [N,K].
+ * Device pointers; synchronous. */
+int sndvae_debug_gemm(sndvae_t* h, int32_t tA, int32_t tB, int64_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                      const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias);
+
 /* argmax(softmax([l0,l1])) of model.py:208 on caller logits [n,2] -> int64 [n];
  * exposed so the thresholding rule can be checked bit-exactly on its own. */
 int sndvae_threshold_logits(sndvae_t* h, const float* logits, int64_t n, int64_t* out);

@@ -94,6 +94,7 @@ SYMBOLS = {
     "sndvae_launch_count": (I64, [C.c_void_p]),
     "sndvae_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(C.c_double)]),
     "sndvae_stage_times": (C.c_int, [C.c_void_p, I32, C.c_void_p, C.c_void_p, I32, C.POINTER(I64)]),
+    "sndvae_debug_gemm": (C.c_int, [C.c_void_p, I32, I32, I64, I32, I32, F32, C.c_void_p, I64, C.c_void_p, I64, F32, C.c_void_p, I64, C.c_void_p]),
     "sndvae_threshold_logits": (C.c_int, [C.c_void_p, C.c_void_p, I64, C.c_void_p]),
     "sndvae_inner_product_decode": (C.c_int, [C.c_void_p, C.c_void_p, I64, I32, I32, C.c_void_p]),
     "sndvae_debug_read": (I64, [C.c_void_p, C.c_char_p, C.c_void_p, I64]),

@@ -14,6 +14,7 @@
 #include "spectral.cuh"
 #include "synth.cuh"
 #include "zzt.cuh"
+#include "tsgemm.cuh"
 #include <cublas_v2.h>
 #include <string>
 #include <vector>
@@ -90,6 +91,7 @@ struct sndvae_handle {
   // them at once so that the forward functions can run on a contiguous piece of the batch (pipelined host step)
   struct Shift { char** p; long long bytes; };
   std::vector<Shift> shifts;
+  int use_cublas;                      // SNDVAE_CUBLAS=1: library sgemm instead of tsgemm (A/B switch while tsgemm is validated)
   int hf_ready;                        // every host-feed staging buffer is allocated
   int max_c;                           // widest node-level channel count of the config (sizes gA / gB / gC / colbuf)
   int poisoned;                        // a step failed half-way: arenas / losses are undefined until the next successful run
@@ -406,6 +408,10 @@ static int alloc_buffers(sndvae_t* h) {
 // row-major C[M,N] = alpha op(A) op(B) + beta C
 static cublasStatus_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
                               const float* B, int ldb, float beta, float* C, int ldc) {
+  if (!h->use_cublas) {     // tcgen05 split-bf16 kernel with in-loader fp32 -> bf16 hi / lo conversion (tsgemm.cuh)
+    cudaError_t e = tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, &h->launches);
+    return e == cudaSuccess ? CUBLAS_STATUS_SUCCESS : CUBLAS_STATUS_EXECUTION_FAILED;
+  }
   h->launches++;
   return cublasSgemm(h->blas, tB ? CUBLAS_OP_T : CUBLAS_OP_N, tA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda,
                      &beta, C, ldc);
@@ -1309,6 +1315,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
+  h->use_cublas = getenv("SNDVAE_CUBLAS") && atoi(getenv("SNDVAE_CUBLAS")) != 0;
   h->hf_ready = 0; h->hc_ready = 0; h->hc_features = nullptr; h->poisoned = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr; h->zz_planes = nullptr; h->zz_cap = 0;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
@@ -1651,6 +1658,15 @@ int sndvae_stage_times(sndvae_t* h, int32_t enable, char* names_host, double* ms
   t.total.clear(); t.steps = 0; t.used = 0;
   t.on = enable ? 1 : t.print;
   return n;
+}
+
+int sndvae_debug_gemm(sndvae_t* h, int32_t tA, int32_t tB, int64_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
+                      const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias) {
+  if (!h || !A || !B || !C) return SNDVAE_E_ARG;
+  cudaError_t e = tsgemm(h->stream, tA != 0, tB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &h->launches);
+  if (e != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "tsgemm: %s", cudaGetErrorString(e));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int sndvae_threshold_logits(sndvae_t* h, const float* logits, int64_t n, int64_t* out) {

@@ -372,6 +372,19 @@ class Engine:
         torch.cuda.synchronize(self.device)      # zz must outlive the kernels on the handle's stream
         return out
 
+    def debug_gemm(self, A: torch.Tensor, B: torch.Tensor, tA=False, tB=False, alpha=1.0, beta=0.0, C0=None, bias=None):
+        """C = alpha op(A) op(B) + beta C0 (+ bias) through the node-level contraction kernel (sndvae_debug_gemm)."""
+        A = A.to(self.device, torch.float32).contiguous(); B = B.to(self.device, torch.float32).contiguous()
+        K, M = (A.shape if tA else A.shape[::-1])
+        N = B.shape[0] if tB else B.shape[1]
+        Cm = (C0.to(self.device, torch.float32).clone().contiguous() if C0 is not None
+              else torch.full((M, N), float("nan"), device=self.device))
+        bt = bias.to(self.device, torch.float32).contiguous() if bias is not None else None
+        self._check(self.lib.sndvae_debug_gemm(self._h, int(tA), int(tB), M, N, K, float(alpha), A.data_ptr(), A.shape[1],
+                                               B.data_ptr(), B.shape[1], float(beta), Cm.data_ptr(), N,
+                                               bt.data_ptr() if bt is not None else None))
+        return Cm
+
     def debug_read(self, name: str, n: int) -> np.ndarray:
         buf = np.empty(n, dtype=np.float32)
         got = self.lib.sndvae_debug_read(self._h, name.encode(), buf.ctypes.data, n)
