@@ -134,6 +134,8 @@ struct SgcScratch {      // activations of one layer for a chunk of samples (row
   float* W2;             // [2C+2+h0, h1] [M2; b2]
   float* W3;             // [C+h1+1, h2]  [M3; b3]
   float* dWQ;            // gradient of WQ (scattered back into M1 / b1 after the step)
+  float* dW2;            // gradient of [M2; b2]  (coef2^T dm2s, accumulated over the chunks of a step)
+  float* dW3;            // gradient of [M3; b3]  (coef3^T dy)
   float* w46;            // [2, h0] gradient partial sums of w4, w6 (rows 3C and 3C+2 of M1)
 };
 
@@ -284,6 +286,20 @@ __global__ void sgc_pack_weights_k(const float* __restrict__ M1, const float* __
   } else if (idx < nQ + n2 + n3) {
     const int q = idx - nQ - n2; const int r = q / h2, h = q - r * h2;
     W3[q] = r < C + h1 ? M3[r * h2 + h] : b3[h];
+  }
+}
+// scatter the gradients of the packed blocks [M2; b2], [M3; b3] back into the arena (once per step and layer)
+__global__ void sgc_unpack_w23_k(const float* __restrict__ dW2, const float* __restrict__ dW3, float* __restrict__ gM2,
+                                 float* __restrict__ gb2, float* __restrict__ gM3, float* __restrict__ gb3, SgcDims D) {
+  const int C = D.C, h0 = D.h0, h1 = D.h1, h2 = D.h2;
+  const int K2 = 2 * C + 2 + h0, K3 = C + h1 + 1, n2 = K2 * h1, n3 = K3 * h2;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n2) {
+    const int r = idx / h1, h = idx - r * h1;
+    if (r < K2 - 1) gM2[idx] += dW2[idx]; else gb2[h] += dW2[idx];
+  } else if (idx < n2 + n3) {
+    const int q = idx - n2; const int r = q / h2, h = q - r * h2;
+    if (r < K3 - 1) gM3[q] += dW3[q]; else gb3[h] += dW3[q];
   }
 }
 // scatter the gradient of WQ and the w4 / w6 sums back into M1 / b1 (once per step and layer)

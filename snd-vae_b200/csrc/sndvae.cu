@@ -91,6 +91,7 @@ struct sndvae_handle {
   // them at once so that the forward functions can run on a contiguous piece of the batch (pipelined host step)
   struct Shift { char** p; long long bytes; };
   std::vector<Shift> shifts;
+  float* gemm_ws; size_t gemm_ws_floats;   // workspace of the deterministic split-K products (tsgemm.cuh)
   int use_cublas;                      // SNDVAE_CUBLAS=1: library sgemm instead of tsgemm (A/B switch while tsgemm is validated)
   int hf_ready;                        // every host-feed staging buffer is allocated
   int max_c;                           // widest node-level channel count of the config (sizes gA / gB / gC / colbuf)
@@ -289,6 +290,7 @@ static int alloc_scratch(sndvae_t* h, SgcScratch& s, int C, const int* hs, long 
   DA(s.dcoef3, rows * K3); DA(s.dm2s, rows * hs[1]); DA(s.dcoef2, rows * K2); DA(s.dP, rows * hs[0]); DA(s.dQc, rows * hs[0]);
   DA(s.dxphi, rows * C); DA(s.dcoefQ, rows * KQ); DA(s.dpx, rows * C);
   DA(s.WQ, KQ * hs[0]); DA(s.W2, K2 * hs[1]); DA(s.W3, K3 * hs[2]); DA(s.dWQ, KQ * hs[0]); DA(s.w46, 2 * hs[0]);
+  DA(s.dW2, K2 * hs[1]); DA(s.dW3, K3 * hs[2]);
   return 0;
 }
 // the scratch of layer l as seen by the chunk of samples starting at s0 (kernels index it with chunk-local sample numbers)
@@ -387,6 +389,7 @@ static int alloc_buffers(sndvae_t* h) {
     h->Yhi = h->Ylo = h->dOhi = h->dOlo = nullptr;
   }
   DA(h->loss, 8); DA(h->errflag, 1);
+  h->gemm_ws_floats = (size_t)16 << 20; DA(h->gemm_ws, h->gemm_ws_floats);      // 64 MB
   if (c.loss_variant == SNDVAE_LOSS_DIP) {
     const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
     int Lm = 0; for (int i = 0; i < 3; ++i) if (Ls[i] > Lm) Lm = Ls[i];
@@ -409,7 +412,7 @@ static int alloc_buffers(sndvae_t* h) {
 static cublasStatus_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
                               const float* B, int ldb, float beta, float* C, int ldc) {
   if (!h->use_cublas) {     // tcgen05 split-bf16 kernel with in-loader fp32 -> bf16 hi / lo conversion (tsgemm.cuh)
-    cudaError_t e = tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, &h->launches);
+    cudaError_t e = tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, &h->launches, h->gemm_ws, h->gemm_ws_floats);
     return e == cudaSuccess ? CUBLAS_STATUS_SUCCESS : CUBLAS_STATUS_EXECUTION_FAILED;
   }
   h->launches++;
@@ -460,10 +463,10 @@ static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* d
   }
   return 0;
 }
-// dM[K-1, hcols] += coef[:, :K-1]^T grad;  db[hcols] += coef[:, K-1]^T grad   (SGC parameter gradients)
-static int coef_grad(sndvae_t* h, const float* coef, int K, const float* grad, int hcols, long long rows, float* dM, float* db) {
-  CKB(gemm_rm(h, true, false, K - 1, hcols, (int)rows, 1.f, coef, K, grad, hcols, 1.f, dM, hcols));
-  CKB(gemm_rm(h, true, false, 1, hcols, (int)rows, 1.f, coef + (K - 1), K, grad, hcols, 1.f, db, hcols));
+// dW[K, hcols] += coef^T grad: the gradient of the packed block [M; b] (the last coefficient column multiplies the bias row);
+// scattered into the arena once per step by sgc_unpack_w23_k
+static int coef_grad(sndvae_t* h, const float* coef, int K, const float* grad, int hcols, long long rows, float* dW) {
+  CKB(gemm_rm(h, true, false, K, hcols, (int)rows, 1.f, coef, K, grad, hcols, 1.f, dW, hcols));
   return 0;
 }
 static SgcDims sgc_dims(sndvae_t* h, int l) {
@@ -509,8 +512,8 @@ static int sgc_layer_bwd(sndvae_t* h, int l, const float* x, const float* dy, fl
   CK(cudaMemsetAsync(S.dQc, 0, sizeof(float) * (size_t)rows * d.h0, h->stream));
   LAUNCH(sgc_edge_bwd_k, (unsigned)ns, 256, sizeof(float) * 2 * d.h0, h->E, d, S, M1 + (size_t)(3 * C) * d.h0, M1 + (size_t)(3 * C + 2) * d.h0, N, s0);
   // parameter gradients: coefficient rows (transposed) times the gradient rows
-  if ((r = coef_grad(h, S.coef3, K3, dy, d.h2, rows, h->G + p.sg_M3[l], h->G + p.sg_b3[l]))) return r;
-  if ((r = coef_grad(h, S.coef2, K2, S.dm2s, d.h1, rows, h->G + p.sg_M2[l], h->G + p.sg_b2[l]))) return r;
+  if ((r = coef_grad(h, S.coef3, K3, dy, d.h2, rows, S.dW3))) return r;
+  if ((r = coef_grad(h, S.coef2, K2, S.dm2s, d.h1, rows, S.dW2))) return r;
   CKB(gemm_rm(h, true, false, C, d.h0, rows, 1.f, S.xphi, C, S.dP, d.h0, 1.f, h->G + p.sg_M1[l], d.h0));       // dM1a
   CKB(gemm_rm(h, true, false, KQ, d.h0, rows, 1.f, S.coefQ, KQ, S.dQc, d.h0, 1.f, S.dWQ, d.h0));                // d[M1b; M1c; w5; b1]
   if (dx) {
@@ -997,6 +1000,8 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
       SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
       CK(cudaMemsetAsync(S.dWQ, 0, sizeof(float) * (2 * d.C + 2) * d.h0, h->stream));
       CK(cudaMemsetAsync(S.w46, 0, sizeof(float) * 2 * d.h0, h->stream));
+      CK(cudaMemsetAsync(S.dW2, 0, sizeof(float) * (2 * d.C + 2 + d.h0) * d.h1, h->stream));
+      CK(cudaMemsetAsync(S.dW3, 0, sizeof(float) * (d.C + d.h1 + 1) * d.h2, h->stream));
     }
     for (long long s0 = 0; s0 < BS; s0 += h->SC) {
       long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
@@ -1017,6 +1022,8 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     for (int l = 0; l < 2; ++l) {
       SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
       LEW(sgc_unpack_grads_k, (2 * d.C + 4) * d.h0, S.dWQ, S.w46, h->G + p.sg_M1[l], h->G + p.sg_b1[l], d);
+      LEW(sgc_unpack_w23_k, (2 * d.C + 2 + d.h0) * d.h1 + (d.C + d.h1 + 1) * d.h2, S.dW2, S.dW3, h->G + p.sg_M2[l], h->G + p.sg_b2[l],
+          h->G + p.sg_M3[l], h->G + p.sg_b3[l], d);
     }
   }
   return 0;
@@ -1663,7 +1670,7 @@ int sndvae_stage_times(sndvae_t* h, int32_t enable, char* names_host, double* ms
 int sndvae_debug_gemm(sndvae_t* h, int32_t tA, int32_t tB, int64_t M, int32_t N, int32_t K, float alpha, const float* A, int64_t lda,
                       const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias) {
   if (!h || !A || !B || !C) return SNDVAE_E_ARG;
-  cudaError_t e = tsgemm(h->stream, tA != 0, tB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &h->launches);
+  cudaError_t e = tsgemm(h->stream, tA != 0, tB != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &h->launches, h->gemm_ws, h->gemm_ws_floats);
   if (e != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "tsgemm: %s", cudaGetErrorString(e));
   CK(cudaStreamSynchronize(h->stream));
   return 0;

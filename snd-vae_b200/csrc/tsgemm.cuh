@@ -5,26 +5,36 @@
 // SpatialGraphConvolution (layers.py:171-196; sgc.cuh) and all of their input / weight gradients -- is one row-major fp32 GEMM
 //     C[M, N] = alpha * op(A)[M, K] * op(B)[K, N] + beta * C (+ bias[N])
 // with shapes that are tall and skinny (M = samples x nodes in the millions, K, N <= 256), or short with a huge reduction
-// (weight gradients: K = samples x nodes), or plain (latent heads: K = N * channels).  One kernel covers them:
+// (weight gradients: K = samples x nodes), or plain (latent heads: K = N * channels).
 //
-//  * operands stay fp32 in HBM; four producer warps read the tile with coalesced loads (along whichever index is contiguous
-//    in memory -- a transposed operand is transposed by the index math of the loader, not by a copy), split every value into
-//    bf16 hi + lo and write the K-major, un-swizzled canonical UMMA tiles (8 x 16-byte core matrices) by hand;
-//  * one thread issues the 3-pass split product  hi.hi + hi.lo + lo.hi  as tcgen05.mma kind::f16 (M = 128, N <= 256) with fp32
-//    accumulation in TMEM: fp32-grade results (~1e-6 relative) at tensor-core speed, so these GEMMs run at the speed their
-//    operands stream from HBM;
-//  * K loops longer than TG_GROUP chunks alternate between two TMEM slots while the epilogue warps drain the finished slot
-//    into round-to-nearest fp32 registers (tcgen05.mma accumulates with truncation: see e2e_tc.cuh);
-//  * weight gradients split the reduction over CTAs (grid.z) and add their partial tiles with red.global.add.f32.
+//  * Operands stay fp32 in HBM.  Producer warps read the tile with coalesced loads (along whichever index is contiguous in
+//    memory -- a transposed operand is transposed by the index math of the loader, not by a copy), split every value into
+//    three bf16 planes  x = hi + mid + lo  (24 mantissa bits: the split is exact up to fp32 rounding) and write the K-major,
+//    un-swizzled canonical UMMA tiles (8 x 16-byte core matrices) by hand.
+//  * One thread issues the six products of total order <= 2  (hi.hi, hi.mid, mid.hi, hi.lo, lo.hi, mid.mid)  as tcgen05.mma
+//    kind::f16, M = 128, N <= 128, fp32 accumulation in TMEM: the dropped terms are <= 2^-24 of |a||b|, i.e. the result is an
+//    fp32-grade product (weight gradients are cancelling sums over millions of rows -- a 3-pass bf16 split, 2^-17 per term,
+//    was measured to leave 8e-3 relative error on a bias gradient).  The tensor pipe has the room: these products are bound by
+//    the HBM stream of their operands.
+//  * tsgemm_tall_k (M in the millions, K <= 320): persistent CTAs, op(B) converted once and resident in shared memory, 16 producer
+//    warps software-pipelined one chunk ahead, two TMEM accumulator slots so that the epilogue of tile i (TMEM -> registers ->
+//    padded shared tile -> coalesced global stores) runs under the loads of tile i + 1.
+//  * tsgemm_k (everything else): one CTA per (M tile, N tile, K split); K loops longer than TG_GROUP chunks alternate between two
+//    TMEM slots while the epilogue warps drain the finished slot into round-to-nearest fp32 registers (tcgen05.mma accumulates
+//    with truncation, see e2e_tc.cuh); weight gradients split the reduction over grid.z and add their partial tiles with
+//    red.global.add.f32.
 #pragma once
 #include "e2e_tc.cuh"
 
-#define TG_BM 128        /* rows per CTA = MMA M */
+#define TG_BM 128        /* rows per tile = MMA M */
 #define TG_BK 32         /* K elements per pipeline stage (two MMA K steps of 16) */
-#define TG_STAGES 3
-#define TG_GROUP 16      /* K chunks per accumulation group: 96 tcgen05.mma accumulates */
-#define TG_PROD 128      /* producer threads (warps 0..3); warp 4 issues the MMAs; warps 5..8 are the epilogue */
-#define TG_THREADS (TG_PROD + 32 + 128)
+#define TG_NP 3          /* bf16 planes per operand */
+#define TG_GROUP 8       /* K chunks per accumulation group: 96 tcgen05.mma accumulates */
+#define TG_PROD 128      /* tsgemm_k: producer threads (warps 0..3); warp 4 issues the MMAs; warps 5..8 are the epilogue */
+#define TG_THREADS (TG_PROD + 32 + 128 + 32)    /* + warp 9: bulk-copy loader of the slab form */
+#define TG_RAW 4          /* raw fp32 slab ring of the slab form */
+#define TG_APLANE (TG_BM * TG_BK * 2)      /* one bf16 plane of an A chunk: 8 KB */
+#define TT_SMEM_MAX (225 * 1024)           /* dynamic shared memory limit (227 KB per CTA minus the static part) */
 
 struct TgArgs {
   const float* A; const float* B; float* C; const float* bias;
@@ -33,84 +43,143 @@ struct TgArgs {
   long long b_ns, b_ks;      // op(B)[k, n] = B[n * b_ns + k * b_ks]
   long long ldc;
   float alpha, beta;
-  int chunks_per_split;      // K chunks handled by one CTA along grid.z
-  int atomic;                // add the partial tile into C with atomics (split K; beta is taken as 1)
+  int chunks_per_split;      // tsgemm_k: K chunks handled by one CTA along grid.z
+  int atomic;                // tsgemm_k: add the partial tile into C with atomics (split K; beta is taken as 1)
+  int tiles_per_cta;         // tsgemm_tall_k: consecutive M tiles per CTA
+  long long split_stride;    // tsgemm_k, deterministic split K: split z writes its partial tile to C + z * split_stride (a workspace)
+  int lda, ldb;              // slab form: row lengths (floats) of the K-major slabs of A and B
 };
 
-// 8 consecutive K values -> 8 bf16 "hi" (round to nearest) + 8 bf16 "lo" (the rounded remainder), lowest K at the lowest address
-__device__ __forceinline__ void tg_split8(const float* v, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
+// 8 consecutive K values -> three packed bf16x8 planes, lowest K at the lowest address
+__device__ __forceinline__ void tg_split8(const float* v, uint4* pl) {
+  uint32_t w[TG_NP][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    float r0 = v[2 * i], r1 = v[2 * i + 1];
+#pragma unroll
+    for (int p = 0; p < TG_NP; ++p) {
+      const __nv_bfloat16 b0 = __float2bfloat16_rn(r0), b1 = __float2bfloat16_rn(r1);
+      r0 -= __bfloat162float(b0); r1 -= __bfloat162float(b1);
+      w[p][i] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+    }
   }
-  hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
+#pragma unroll
+  for (int p = 0; p < TG_NP; ++p) pl[p] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+}
+// byte offset of (row, 8-wide K group g) inside one plane of a chunk tile: core matrix (8 rows x 8 K) = 128 contiguous bytes,
+// the 4 core matrices of a row group along K 128 B apart (LBO), row groups 512 B apart (SBO)
+__device__ __forceinline__ int tg_tile_off(int row, int g) { return (row >> 3) * 512 + g * 128 + (row & 7) * 16; }
+
+// 8 K values of row r (global row index) starting at k of an operand with K contiguous in memory
+__device__ __forceinline__ void tg_load8_kmajor(const float* __restrict__ base, long long rs, long long r, long long rmax, int k, int kmax,
+                                                bool vec_ok, float* v) {
+  if (r < rmax && k < kmax) {
+    const float* p = base + r * rs + k;
+    if (vec_ok && k + 8 <= kmax) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (k + j < kmax) ? __ldg(p + j) : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+  }
 }
 
-// Stage one operand tile: R rows (r0 ...) x 32 K values (k0 ...) of the operand whose element (r, k) lives at base[r * rs + k * ks];
-// rows >= rmax and k >= kmax read as zero.  Canonical K-major tile without swizzle: core matrix (8 rows x 8 K) = 128 contiguous
-// bytes, the 4 core matrices of a row group along K 128 B apart (LBO), row groups 512 B apart (SBO).
+// 8 K values of item (row, g) of a chunk for either orientation of the operand (ks == 1: K contiguous; else rows contiguous)
+__device__ __forceinline__ void tg_load_item(const float* __restrict__ base, long long rs, long long ks, long long r, long long rmax,
+                                             int k, int kmax, bool vec_ok, float* v) {
+  if (ks == 1) tg_load8_kmajor(base, rs, r, rmax, k, kmax, vec_ok, v);
+  else {
+    const float* p8 = base + r * rs + (long long)k * ks;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (r < rmax && k + j < kmax) ? __ldg(p8 + (long long)j * ks) : 0.f;
+  }
+}
+__device__ __forceinline__ void tg_store_item(const float* v, uint8_t* st, int pstride, int row, int g) {
+  uint4 pl[TG_NP]; tg_split8(v, pl);
+  const int off = tg_tile_off(row, g);
+#pragma unroll
+  for (int p = 0; p < TG_NP; ++p) *reinterpret_cast<uint4*>(st + p * pstride + off) = pl[p];
+}
+
+// Stage one operand chunk: R rows (r0 ...) x 32 K values (k0 ...) of the operand whose element (r, k) lives at base[r * rs + k * ks];
+// rows >= rmax and k >= kmax read as zero.  `st` = plane 0, the other planes follow at `pstride` bytes.  nt threads, this one is t.
 __device__ __forceinline__ void tg_load_tile(const float* __restrict__ base, long long rs, long long ks, long long r0, long long rmax,
-                                             int k0, int kmax, int R, uint8_t* sh, uint8_t* sl, int t, bool vec_ok) {
+                                             int k0, int kmax, int R, uint8_t* st, int pstride, int t, int nt, bool vec_ok) {
   const int items = R * (TG_BK / 8);
   if (ks == 1) {                    // K contiguous in memory: 4 neighbouring threads read one row's 128 bytes
-#pragma unroll 4
-    for (int idx = t; idx < items; idx += TG_PROD) {
+#pragma unroll 2
+    for (int idx = t; idx < items; idx += nt) {
       const int row = idx >> 2, g = idx & 3;
-      const long long r = r0 + row; const int k = k0 + 8 * g;
       float v[8];
-      if (r < rmax && k < kmax) {
-        const float* p = base + r * rs + k;
-        if (vec_ok && k + 8 <= kmax) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+      tg_load8_kmajor(base, rs, r0 + row, rmax, k0 + 8 * g, kmax, vec_ok, v);
+      uint4 pl[TG_NP]; tg_split8(v, pl);
+      const int off = tg_tile_off(row, g);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (k + j < kmax) ? __ldg(p + j) : 0.f;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      }
-      uint4 hi, lo; tg_split8(v, hi, lo);
-      const int off = (row >> 3) * 512 + g * 128 + (row & 7) * 16;
-      *reinterpret_cast<uint4*>(sh + off) = hi; *reinterpret_cast<uint4*>(sl + off) = lo;
+      for (int p = 0; p < TG_NP; ++p) *reinterpret_cast<uint4*>(st + p * pstride + off) = pl[p];
     }
   } else {                          // rows contiguous in memory (a transposed operand): a warp reads 32 neighbouring rows per K value
 #pragma unroll 2
-    for (int idx = t; idx < items; idx += TG_PROD) {
+    for (int idx = t; idx < items; idx += nt) {
       const int g = idx / R, row = idx - g * R;
       const long long r = r0 + row; const int k = k0 + 8 * g;
       float v[8];
-      const float* p = base + r * rs + (long long)k * ks;
+      const float* p8 = base + r * rs + (long long)k * ks;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (r < rmax && k + j < kmax) ? __ldg(p + (long long)j * ks) : 0.f;
-      uint4 hi, lo; tg_split8(v, hi, lo);
-      const int off = (row >> 3) * 512 + g * 128 + (row & 7) * 16;
-      *reinterpret_cast<uint4*>(sh + off) = hi; *reinterpret_cast<uint4*>(sl + off) = lo;
+      for (int j = 0; j < 8; ++j) v[j] = (r < rmax && k + j < kmax) ? __ldg(p8 + (long long)j * ks) : 0.f;
+      uint4 pl[TG_NP]; tg_split8(v, pl);
+      const int off = tg_tile_off(row, g);
+#pragma unroll
+      for (int p = 0; p < TG_NP; ++p) *reinterpret_cast<uint4*>(st + p * pstride + off) = pl[p];
     }
   }
 }
 
-// BNMAX: widest N tile (TMEM columns per slot, accumulator registers of the grouped form); GROUPED: two-level accumulation
-template <int BNMAX, bool GROUPED>
-__global__ void __launch_bounds__(TG_THREADS, GROUPED ? 1 : (BNMAX <= 64 ? 3 : 2)) tsgemm_k(TgArgs P) {
-  constexpr int A_BYTES = TG_BM * TG_BK * 2;          // one bf16 plane of the A tile: 8 KB
-  constexpr int B_BYTES = BNMAX * TG_BK * 2;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+// the six split products of one 32-wide K chunk: A planes at sa + p * TG_APLANE, B planes at sb + p * bplane.  `dz` is the
+// descriptor of shared address 0 (LBO 128, SBO 512, no swizzle): the start-address field is the low 14 bits in 16-byte units
+// and every shared address is < 256 KB, so a tile's descriptor is dz + (address >> 4)
+__device__ __forceinline__ void tg_issue_chunk(uint32_t td, uint32_t sa, uint32_t sb, uint32_t bplane, uint32_t idesc, bool first, uint64_t dz) {
+#pragma unroll
+  for (int k = 0; k < TG_BK / 16; ++k) {          // one K step = two core matrices = 256 bytes further along the row group
+    uint64_t a[TG_NP], b[TG_NP];
+#pragma unroll
+    for (int p = 0; p < TG_NP; ++p) {
+      a[p] = dz + ((sa + p * TG_APLANE + k * 256) >> 4);
+      b[p] = dz + ((sb + p * bplane + k * 256) >> 4);
+    }
+    umma_bf16(td, a[0], b[0], idesc, (first && k == 0) ? 0u : 1u);
+    umma_bf16(td, a[0], b[1], idesc, 1u);
+    umma_bf16(td, a[1], b[0], idesc, 1u);
+    umma_bf16(td, a[0], b[2], idesc, 1u);
+    umma_bf16(td, a[2], b[0], idesc, 1u);
+    umma_bf16(td, a[1], b[1], idesc, 1u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// tsgemm_k: one CTA per (M tile, N tile, K split).  BNMAX: widest N tile; GROUPED: two-level accumulation for long K loops.
+// ---------------------------------------------------------------------------------------------------------------------------
+// SLAB (weight gradients: both operands stored [K, *] with short rows): a 32-row K chunk of A and of B is one contiguous slab
+// in memory, so warp 9 streams raw fp32 slabs into a ring with one cp.async.bulk each (TG_RAW chunks in flight, no registers
+// tied up) and the producer warps transpose / split from shared memory instead of from global.
+template <int BNMAX, bool GROUPED, bool SLAB>
+__global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) tsgemm_k(TgArgs P) {
+  constexpr int STAGES = SLAB ? 2 : ((BNMAX <= 64 || GROUPED) ? 3 : 2);
+  constexpr int B_PLANE = BNMAX * TG_BK * 2;
+  constexpr int STAGE_BYTES = TG_NP * (TG_APLANE + B_PLANE);
   constexpr uint32_t TMEM_COLS = GROUPED ? 2 * BNMAX : BNMAX;
-  static_assert(BNMAX == 64 || BNMAX == 128 || BNMAX == 256, "TMEM allocations are powers of two");
-  static_assert(TMEM_COLS <= 512, "TMEM");
+  static_assert(BNMAX == 64 || BNMAX == 128, "TMEM allocations are powers of two");
   extern __shared__ __align__(128) uint8_t tg_smem[];
-  __shared__ uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], raw_full[TG_RAW], raw_empty[TG_RAW];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m0 = (long long)blockIdx.x * TG_BM;
+  float* raw = reinterpret_cast<float*>(tg_smem + (size_t)STAGES * STAGE_BYTES);     // slab ring: [TG_RAW][32 lda + 32 ldb]
+  const int raw_floats = SLAB ? 32 * (P.lda + P.ldb) : 0;
   const int n0 = blockIdx.y * BNMAX;
   int bn = P.N - n0; if (bn > BNMAX) bn = BNMAX;
   const int bnc = (bn + 15) & ~15;                    // MMA N: a multiple of 16
@@ -120,8 +189,9 @@ __global__ void __launch_bounds__(TG_THREADS, GROUPED ? 1 : (BNMAX <= 64 ? 3 : 2
   const int ngroups = (nk + TG_GROUP - 1) / TG_GROUP;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&full_bar[s], TG_PROD); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TG_PROD / 32); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < TG_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TG_PROD / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) tmem_alloc(&tmem_base_s, TMEM_COLS);
@@ -130,42 +200,128 @@ __global__ void __launch_bounds__(TG_THREADS, GROUPED ? 1 : (BNMAX <= 64 ? 3 : 2
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  if (warp < 4) {
-    // ---- producers: global fp32 -> bf16 hi / lo canonical tiles ----
+  if (SLAB && warp == 9) {
+    if (lane == 0) {
+      int rc = 0;
+      for (int it = 0; it < nk; ++it) {
+        const long long k0 = (long long)(c_lo + it) * TG_BK;
+        if (k0 + TG_BK > P.K) continue;                      // ragged last chunk: the producers read it from global
+        const int rs = rc % TG_RAW;
+        mbar_wait(&raw_empty[rs], ((rc / TG_RAW) & 1) ^ 1);
+        float* dst = raw + (size_t)rs * raw_floats;
+        mbar_expect_tx(&raw_full[rs], 128u * (uint32_t)(P.lda + P.ldb));
+        bulk_load(dst, P.A + k0 * P.lda, 128u * (uint32_t)P.lda, &raw_full[rs]);
+        bulk_load(dst + 32 * P.lda, P.B + k0 * P.ldb, 128u * (uint32_t)P.ldb, &raw_full[rs]);
+        ++rc;
+      }
+    }
+  } else if (SLAB && warp < 4) {
+    const int t = threadIdx.x;
+    constexpr int NA = TG_BM * 4 / TG_PROD, NB = BNMAX * 4 / TG_PROD;
+    int rc = 0;
+    for (int it = 0; it < nk; ++it) {
+      const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+      const int k0 = (c_lo + it) * TG_BK;
+      const bool partial = k0 + TG_BK > P.K;
+      const int rs = rc % TG_RAW;
+      const float* rA = raw + (size_t)rs * raw_floats; const float* rB = rA + 32 * P.lda;
+      if (lane == 0) { if (!partial) mbar_wait(&raw_full[rs], (rc / TG_RAW) & 1); mbar_wait(&empty_bar[s], ph ^ 1); }
+      __syncwarp();
+      uint8_t* st = tg_smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int idx = t + q * TG_PROD, row = idx & (TG_BM - 1), g = idx >> 7;
+        float v[8];
+        if (partial) tg_load_item(P.A, 1, P.lda, m0 + row, P.M, k0 + 8 * g, P.K, false, v);
+        else {
+          const bool ok = m0 + row < P.M;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = ok ? rA[(8 * g + j) * P.lda + m0 + row] : 0.f;
+        }
+        tg_store_item(v, st, TG_APLANE, row, g);
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int idx = t + q * TG_PROD;
+        if (idx < bnc * 4) {
+          const int g = idx / bnc, row = idx - g * bnc;
+          float v[8];
+          if (partial) tg_load_item(P.B, 1, P.ldb, n0 + row, P.N, k0 + 8 * g, P.K, false, v);
+          else {
+            const bool ok = n0 + row < P.N;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ok ? rB[(8 * g + j) * P.ldb + n0 + row] : 0.f;
+          }
+          tg_store_item(v, st + TG_NP * TG_APLANE, B_PLANE, row, g);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&full_bar[s]); if (!partial) mbar_arrive(&raw_empty[rs]); }
+      if (!partial) ++rc;
+    }
+  } else if (warp < 4) {
+    // ---- producers: global fp32 -> bf16 planes in canonical tiles ----
     const int t = threadIdx.x;
     const bool a_vec = (P.a_ks == 1) && (P.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
     const bool b_vec = (P.b_ks == 1) && (P.b_ns % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.B) & 15) == 0);
+    // item (row, g) of thread t: K-contiguous operands give 4 neighbouring threads one row's 128 bytes; row-contiguous
+    // (transposed) operands give a warp 32 neighbouring rows per K value.  Every load of the chunk is issued before the first
+    // conversion (and before the wait for the stage), so that a thread has 48 - 64 values in flight.
+    constexpr int NA = TG_BM * 4 / TG_PROD, NB = BNMAX * 4 / TG_PROD;
     for (int it = 0; it < nk; ++it) {
-      const int s = it % TG_STAGES; const uint32_t ph = (it / TG_STAGES) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      uint8_t* st = tg_smem + (size_t)s * STAGE_BYTES;
+      const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
       const int k0 = (c_lo + it) * TG_BK;
-      tg_load_tile(P.A, P.a_rs, P.a_ks, m0, P.M, k0, P.K, TG_BM, st, st + A_BYTES, t, a_vec);
-      tg_load_tile(P.B, P.b_ns, P.b_ks, n0, P.N, k0, P.K, bnc, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, t, b_vec);
+      float va[NA][8], vb[NB][8];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int idx = t + q * TG_PROD;
+        const int row = P.a_ks == 1 ? idx >> 2 : idx & (TG_BM - 1), g = P.a_ks == 1 ? idx & 3 : idx >> 7;
+        tg_load_item(P.A, P.a_rs, P.a_ks, m0 + row, P.M, k0 + 8 * g, P.K, a_vec, va[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int idx = t + q * TG_PROD;
+        if (idx < bnc * 4) {
+          const int g = P.b_ks == 1 ? idx & 3 : idx / bnc, row = P.b_ks == 1 ? idx >> 2 : idx - g * bnc;
+          tg_load_item(P.B, P.b_ns, P.b_ks, n0 + row, P.N, k0 + 8 * g, P.K, b_vec, vb[q]);
+        }
+      }
+      if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1);      // one poller per warp; __syncwarp orders the others behind it
+      __syncwarp();
+      uint8_t* st = tg_smem + (size_t)s * STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < NA; ++q) {
+        const int idx = t + q * TG_PROD;
+        const int row = P.a_ks == 1 ? idx >> 2 : idx & (TG_BM - 1), g = P.a_ks == 1 ? idx & 3 : idx >> 7;
+        tg_store_item(va[q], st, TG_APLANE, row, g);
+      }
+#pragma unroll
+      for (int q = 0; q < NB; ++q) {
+        const int idx = t + q * TG_PROD;
+        if (idx < bnc * 4) {
+          const int g = P.b_ks == 1 ? idx & 3 : idx / bnc, row = P.b_ks == 1 ? idx >> 2 : idx - g * bnc;
+          tg_store_item(vb[q], st + TG_NP * TG_APLANE, B_PLANE, row, g);
+        }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
-      mbar_arrive(&full_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);                        // one arrival per producer warp
     }
+  } else if (warp == 9) {
+    // (idle in the plain form)
   } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(TG_BM, bnc, 0, 0);
+      const uint64_t dz = umma_desc(0u, 128, 512, 0ull);
       for (int it = 0; it < nk; ++it) {
         const int g = it / TG_GROUP, gi = it - g * TG_GROUP, slot = GROUPED ? (g & 1) : 0;
         if (GROUPED && gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
-        const int s = it % TG_STAGES; const uint32_t ph = (it / TG_STAGES) & 1;
+        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(tg_smem + (size_t)s * STAGE_BYTES);
-        const uint32_t td = tmem_d + slot * BNMAX;
-#pragma unroll
-        for (int k = 0; k < TG_BK / 16; ++k) {        // one K step = two core matrices = 256 bytes further along the row group
-          const uint64_t ah = umma_desc(sa + k * 256, 128, 512, 0ull);
-          const uint64_t al = umma_desc(sa + A_BYTES + k * 256, 128, 512, 0ull);
-          const uint64_t bh = umma_desc(sa + 2 * A_BYTES + k * 256, 128, 512, 0ull);
-          const uint64_t bl = umma_desc(sa + 2 * A_BYTES + B_BYTES + k * 256, 128, 512, 0ull);
-          umma_bf16(td, ah, bh, idesc, (gi | k) ? 1u : 0u);
-          umma_bf16(td, ah, bl, idesc, 1u);
-          umma_bf16(td, al, bh, idesc, 1u);
-        }
+        tg_issue_chunk(tmem_d + slot * BNMAX, sa, sa + TG_NP * TG_APLANE, B_PLANE, idesc, gi == 0, dz);
         umma_commit(&empty_bar[s]);
         if (gi == TG_GROUP - 1 || it == nk - 1) umma_commit(&acc_full[slot]);
       }
@@ -175,10 +331,9 @@ __global__ void __launch_bounds__(TG_THREADS, GROUPED ? 1 : (BNMAX <= 64 ? 3 : 2
     const int q = warp & 3;
     const long long row = m0 + q * 32 + lane;
     const bool rok = row < P.M;
-    float* crow = P.C + row * P.ldc + n0;
-    const bool c_vec = (P.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) && (n0 % 4 == 0);
+    float* crow = P.C + (long long)blockIdx.z * P.split_stride + row * P.ldc + n0;
+    const bool c_vec = (P.ldc % 4 == 0) && (P.split_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0) && (n0 % 4 == 0);
     if (nk == 0) {
-      // nothing to multiply in this split: only the first split owns beta * C + bias
       if (!P.atomic && rok) for (int c = 0; c < bn; ++c) crow[c] = (P.beta != 0.f ? P.beta * crow[c] : 0.f) + (P.bias ? P.bias[n0 + c] : 0.f);
     } else if (!GROUPED) {
       mbar_wait(&acc_full[0], 0);
@@ -252,55 +407,298 @@ __global__ void __launch_bounds__(TG_THREADS, GROUPED ? 1 : (BNMAX <= 64 ? 3 : 2
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_d, TMEM_COLS); }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// tsgemm_tall_k: persistent CTAs over consecutive M tiles, A with K contiguous (not transposed), op(B) resident.
+// 16 producer warps (one 8-value item per thread and chunk, loads issued one chunk ahead of the conversion), warp 16 issues the
+// MMAs, warps 17..20 are the epilogue.  Shared memory: B planes [chunk][plane][BNMAX x 32], A ring, padded output tile.
+// ---------------------------------------------------------------------------------------------------------------------------
+#define TT_PROD 512
+#define TT_THREADS (TT_PROD + 32 + 128)
+#define TT_STAGES 4
+#define TT_AHEAD 3        /* producer register prefetch distance (units of one 8-value item) */
+template <int BNMAX>
+__global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
+  constexpr int B_PLANE = BNMAX * TG_BK * 2;
+  constexpr int A_STAGE = TG_NP * TG_APLANE;
+  constexpr int SROW = BNMAX + 1;                      // padded row of the output staging tile (floats)
+  constexpr uint32_t TMEM_COLS = 2 * BNMAX;
+  extern __shared__ __align__(128) uint8_t tg_smem[];
+  __shared__ uint64_t full_bar[TT_STAGES], empty_bar[TT_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BNMAX;
+  int bn = P.N - n0; if (bn > BNMAX) bn = BNMAX;
+  const int bnc = (bn + 15) & ~15;
+  const int nkc = (P.K + TG_BK - 1) / TG_BK;
+  const long long mtiles = (P.M + TG_BM - 1) / TG_BM;
+  const long long t_lo = (long long)blockIdx.x * P.tiles_per_cta;
+  long long nt = mtiles - t_lo; if (nt > P.tiles_per_cta) nt = P.tiles_per_cta; if (nt < 0) nt = 0;
+  uint8_t* sB = tg_smem;
+  uint8_t* sA = tg_smem + (size_t)nkc * TG_NP * B_PLANE;
+  float* sC = reinterpret_cast<float*>(sA + (size_t)TT_STAGES * A_STAGE);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TT_STAGES; ++s) { mbar_init(&full_bar[s], TT_PROD / 32); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  {   // op(B): converted once per CTA by every thread
+    const bool b_vec = (P.b_ks == 1) && (P.b_ns % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.B) & 15) == 0);
+    for (int c = 0; c < nkc; ++c)
+      tg_load_tile(P.B, P.b_ns, P.b_ks, n0, P.N, c * TG_BK, P.K, bnc, sB + (size_t)c * TG_NP * B_PLANE, B_PLANE, threadIdx.x, TT_THREADS, b_vec);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  const long long units = nt * nkc;
+
+  if (warp < 16) {
+    const int t = threadIdx.x, row = t >> 2, g = t & 3;
+    const bool a_vec = (P.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
+    const int off = tg_tile_off(row, g);
+    // register ring: the loads of unit u + TT_AHEAD are issued before unit u is converted (TT_AHEAD x 32 bytes in flight per thread)
+    float buf[TT_AHEAD + 1][8];
+    long long lt = 0; int lc = 0;                                     // (tile, chunk) of the next unit to load
+#pragma unroll
+    for (int d = 0; d < TT_AHEAD; ++d) {
+      if (d < units) tg_load8_kmajor(P.A, P.a_rs, (t_lo + lt) * TG_BM + row, P.M, lc * TG_BK + 8 * g, P.K, a_vec, buf[d]);
+      if (++lc == nkc) { lc = 0; ++lt; }
+    }
+    for (long long u0 = 0; u0 < units; u0 += TT_AHEAD + 1) {
+#pragma unroll
+      for (int d = 0; d <= TT_AHEAD; ++d) {
+        const long long u = u0 + d;
+        if (u < units) {
+          if (u + TT_AHEAD < units)
+            tg_load8_kmajor(P.A, P.a_rs, (t_lo + lt) * TG_BM + row, P.M, lc * TG_BK + 8 * g, P.K, a_vec, buf[(d + TT_AHEAD) % (TT_AHEAD + 1)]);
+          if (++lc == nkc) { lc = 0; ++lt; }
+          const int s = (int)(u % TT_STAGES); const uint32_t ph = (uint32_t)((u / TT_STAGES) & 1);
+          uint4 pl[TG_NP]; tg_split8(buf[d], pl);
+          if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1);
+          __syncwarp();
+          uint8_t* st = sA + (size_t)s * A_STAGE + off;
+#pragma unroll
+          for (int p = 0; p < TG_NP; ++p) *reinterpret_cast<uint4*>(st + p * TG_APLANE) = pl[p];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 16) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(TG_BM, bnc, 0, 0);
+      const uint64_t dz = umma_desc(0u, 128, 512, 0ull);
+      const uint32_t sb0 = smem_u32(sB), sa0 = smem_u32(sA);
+      long long u = 0;
+      for (long long ti = 0; ti < nt; ++ti) {
+        const int slot = (int)(ti & 1);
+        mbar_wait(&acc_empty[slot], (uint32_t)(((ti >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int c = 0; c < nkc; ++c, ++u) {
+          const int s = (int)(u % TT_STAGES); const uint32_t ph = (uint32_t)((u / TT_STAGES) & 1);
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          tg_issue_chunk(tmem_d + slot * BNMAX, sa0 + s * A_STAGE, sb0 + c * TG_NP * B_PLANE, B_PLANE, idesc, c == 0, dz);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc_full[slot]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* srow = sC + (size_t)(q * 32) * SROW;         // this warp's 32 rows of the staging tile (only this warp touches them)
+    const bool flat = (P.ldc == bn) && (n0 == 0);         // the warp's 32 x bn block is contiguous in C
+    // contiguous block, nothing to read back: stage it in C's own layout and hand it to one bulk store per tile
+    const bool bulk = flat && P.beta == 0.f && ((reinterpret_cast<uintptr_t>(P.C) & 15) == 0);
+    const int sr = bulk ? bn : SROW;                      // staging row pitch (floats)
+    bool pending = false;
+    for (long long ti = 0; ti < nt; ++ti) {
+      const int slot = (int)(ti & 1);
+      mbar_wait(&acc_full[slot], (uint32_t)((ti >> 1) & 1));
+      tc_fence_after();
+      if (pending) { if (lane == 0) bulk_wait_read(); __syncwarp(); pending = false; }     // the previous store has left the staging rows
+      const uint32_t ta = tmem_d + slot * BNMAX + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < bnc; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(ta + c0, r);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < bn) srow[lane * sr + c0 + i] = P.alpha * __uint_as_float(r[i]) + (P.bias ? __ldg(P.bias + n0 + c0 + i) : 0.f);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[slot]);        // the accumulator slot is free for tile ti + 2
+      const long long r0 = (t_lo + ti) * TG_BM + q * 32;
+      long long nr = P.M - r0; if (nr > 32) nr = 32;
+      if (nr == 32 && bulk) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_store(P.C + r0 * P.ldc, srow, 32u * (uint32_t)bn * 4u);
+        pending = true;
+      } else if (nr > 0) {
+        if (flat) {
+          float* dst = P.C + r0 * P.ldc;
+          const int total = (int)nr * bn;
+          for (int e0 = 0; e0 < total; e0 += 128) {
+            float v[4]; int ee[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              ee[u] = e0 + u * 32 + lane;
+              const int rr = ee[u] / bn, cc = ee[u] - rr * bn;
+              v[u] = ee[u] < total ? srow[rr * sr + cc] : 0.f;
+            }
+            if (P.beta != 0.f) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) if (ee[u] < total) v[u] += P.beta * dst[ee[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (ee[u] < total) dst[ee[u]] = v[u];
+          }
+        } else {
+          for (int rr = 0; rr < (int)nr; rr += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (rr + u < (int)nr) {
+                float* dst = P.C + (r0 + rr + u) * P.ldc + n0;
+                for (int cc = lane; cc < bn; cc += 32) {
+                  float v = srow[(rr + u) * sr + cc];
+                  if (P.beta != 0.f) v += P.beta * dst[cc];
+                  dst[cc] = v;
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    if (pending && lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) { tc_fence_after(); tmem_dealloc(tmem_d, TMEM_COLS); }
+}
+
+// C[m, n] = beta C + bias[n] + sum_z ws[z][m][n]   (fixed summation order: the deterministic half of a split-K product)
+__global__ void tg_reduce_k(const float* __restrict__ ws, int nsplit, long long MN, int N, float* __restrict__ C, long long ldc,
+                            const float* __restrict__ bias, float beta) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= MN) return;
+  const long long m = idx / N; const int n = (int)(idx - m * N);
+  float acc = 0.f;
+  for (int z = 0; z < nsplit; ++z) acc += ws[(long long)z * MN + idx];
+  float* c = C + m * ldc + n;
+  *c = acc + (bias ? __ldg(bias + n) : 0.f) + (beta != 0.f ? beta * *c : 0.f);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
-template <int BNMAX, bool GROUPED>
+template <int BNMAX, bool GROUPED, bool SLAB>
 static cudaError_t tg_launch_t(const TgArgs& a, dim3 grid, cudaStream_t st) {
-  constexpr int smem = TG_STAGES * (2 * TG_BM * TG_BK * 2 + 2 * BNMAX * TG_BK * 2);
+  constexpr int STAGES = SLAB ? 2 : ((BNMAX <= 64 || GROUPED) ? 3 : 2);
+  const int smem = STAGES * TG_NP * (TG_APLANE + BNMAX * TG_BK * 2) + (SLAB ? TG_RAW * 128 * (a.lda + a.ldb) : 0);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tsgemm_k<BNMAX, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tsgemm_k<BNMAX, GROUPED, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_MAX);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  tsgemm_k<BNMAX, GROUPED><<<grid, TG_THREADS, smem, st>>>(a);
+  tsgemm_k<BNMAX, GROUPED, SLAB><<<grid, TG_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <int BNMAX>
+static cudaError_t tg_launch(const TgArgs& a, dim3 grid, cudaStream_t st, bool grouped, bool slab) {
+  if (slab) return grouped ? tg_launch_t<BNMAX, true, true>(a, grid, st) : tg_launch_t<BNMAX, false, true>(a, grid, st);
+  return grouped ? tg_launch_t<BNMAX, true, false>(a, grid, st) : tg_launch_t<BNMAX, false, false>(a, grid, st);
+}
+template <int BNMAX>
+static size_t tt_smem_bytes(int K) {
+  const int nkc = (K + TG_BK - 1) / TG_BK;
+  return (size_t)nkc * TG_NP * BNMAX * TG_BK * 2 + (size_t)TT_STAGES * TG_NP * TG_APLANE + (size_t)TG_BM * (BNMAX + 1) * 4;
+}
+template <int BNMAX>
+static cudaError_t tt_launch_t(const TgArgs& a, dim3 grid, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tsgemm_tall_k<BNMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_MAX);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  tsgemm_tall_k<BNMAX><<<grid, TT_THREADS, tt_smem_bytes<BNMAX>(a.K), st>>>(a);
   return cudaGetLastError();
 }
 
 // row-major  C[M, N] = alpha op(A) op(B) + beta C (+ bias);  op(A) = A^T when tA (A stored [K, M]), op(B) = B^T when tB (B stored [N, K]).
+// Results are deterministic except for weight-gradient shapes (tA with a long reduction), whose K splits are added with atomics.
 // `launches` is incremented by the number of kernels / memsets enqueued.
+// `ws` (ws_floats floats, may be NULL): workspace for the deterministic split of long-K products with few output tiles.
 static cudaError_t tsgemm(cudaStream_t st, bool tA, bool tB, long long M, int N, int K, float alpha, const float* A, long long lda,
-                          const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, long long* launches) {
+                          const float* B, long long ldb, float beta, float* C, long long ldc, const float* bias, long long* launches,
+                          float* ws = nullptr, size_t ws_floats = 0) {
   if (M <= 0 || N <= 0) return cudaSuccess;
   TgArgs a;
   a.A = A; a.B = B; a.C = C; a.bias = bias; a.M = M; a.N = N; a.K = K;
   a.a_rs = tA ? 1 : lda; a.a_ks = tA ? lda : 1;
   a.b_ns = tB ? ldb : 1; a.b_ks = tB ? 1 : ldb;
-  a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.atomic = 0;
+  a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.atomic = 0; a.tiles_per_cta = 1; a.chunks_per_split = 1; a.split_stride = 0;
   const int chunks = (K + TG_BK - 1) / TG_BK;
   const int bnmax = N <= 64 ? 64 : 128;
   const long long mt = (M + TG_BM - 1) / TG_BM; const int nt = (N + bnmax - 1) / bnmax;
+  if (mt > 0x7fffffffLL || nt > 65535) return cudaErrorInvalidValue;
+  // tall and skinny with op(B) small enough to stay in shared memory: the persistent kernel
+  const size_t tall_smem = bnmax == 64 ? tt_smem_bytes<64>(K) : tt_smem_bytes<128>(K);
+  if (!tA && K > 0 && mt >= 148 && tall_smem <= TT_SMEM_MAX) {
+    int device = 0, sms = 148; cudaGetDevice(&device); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    long long ctas = sms / nt; if (ctas < 1) ctas = 1; if (ctas > mt) ctas = mt;
+    a.tiles_per_cta = (int)((mt + ctas - 1) / ctas);
+    ctas = (mt + a.tiles_per_cta - 1) / a.tiles_per_cta;
+    dim3 grid((unsigned)ctas, (unsigned)nt, 1);
+    if (launches) ++*launches;
+    return bnmax == 64 ? tt_launch_t<64>(a, grid, st) : tt_launch_t<128>(a, grid, st);
+  }
   int ksplit = 1;
-  // a short output with a long reduction (weight gradients): split K over CTAs, partial tiles added with atomics
-  if (bias == nullptr && chunks > TG_GROUP && mt * nt < 2 * 148) {
-    long long want = (4 * 148 + mt * nt - 1) / (mt * nt);
-    const long long most = (chunks + 3) / 4;                         // at least 4 chunks per CTA
+  // a long reduction with few output tiles: split K over CTAs.  Weight gradients (tA: the reduction runs over rows) add their
+  // partial tiles with atomics; forward / input-gradient products (the latent heads at small batch) must stay deterministic, so
+  // their partial tiles go to the workspace and are summed in a fixed order by tg_reduce_k.
+  bool split_ws = false;
+  if (chunks >= 2 * TG_GROUP && mt * nt < 2 * 148) {
+    long long want = (2 * 148) / (mt * nt);                            // one wave of two CTAs per SM
+    if (want < 1) want = 1;
+    const long long most = chunks / TG_GROUP;                        // at least one accumulation group per CTA
     if (want > most) want = most;
-    const long long least = (chunks + TG_GROUP - 1) / TG_GROUP;      // at most one accumulation group per CTA
-    if (want < least) want = least;
-    ksplit = (int)want;
+    if (want > 65535) want = 65535;
+    if (!tA || bias != nullptr) {
+      const long long room = ws ? (long long)(ws_floats / (size_t)(M * N)) : 0;
+      if (want > room) want = room;
+      split_ws = want > 1;
+    }
+    if (want > 1) ksplit = (int)want;
   }
   a.chunks_per_split = (chunks + ksplit - 1) / ksplit;
   if (a.chunks_per_split < 1) a.chunks_per_split = 1;
   ksplit = chunks > 0 ? (chunks + a.chunks_per_split - 1) / a.chunks_per_split : 1;
-  if (ksplit > 1) {
+  if (ksplit > 1 && split_ws) {
+    a.C = ws; a.ldc = N; a.split_stride = M * N; a.bias = nullptr; a.beta = 0.f;
+  } else if (ksplit > 1) {
     a.atomic = 1;
     if (beta == 0.f) { cudaError_t e = cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st); if (e != cudaSuccess) return e; if (launches) ++*launches; }
     else if (beta != 1.f) return cudaErrorInvalidValue;              // not needed by any caller
   }
-  if (mt > 0x7fffffffLL || ksplit > 65535 || nt > 65535) return cudaErrorInvalidValue;
+  if (ksplit > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)mt, (unsigned)nt, (unsigned)ksplit);
   const bool grouped = a.chunks_per_split > TG_GROUP;
   if (launches) ++*launches;
-  if (bnmax == 64) return grouped ? tg_launch_t<64, true>(a, grid, st) : tg_launch_t<64, false>(a, grid, st);
-  return grouped ? tg_launch_t<128, true>(a, grid, st) : tg_launch_t<128, false>(a, grid, st);
+  // slab form: both operands K-major with rows short enough for a ring of raw slabs, 16-byte aligned bases
+  a.lda = (int)lda; a.ldb = (int)ldb;
+  const bool slab = tA && !tB && chunks >= 4 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0 &&
+                    2 * TG_NP * (TG_APLANE + bnmax * TG_BK * 2) + TG_RAW * 128 * (lda + ldb) <= TT_SMEM_MAX;
+  cudaError_t e = bnmax == 64 ? tg_launch<64>(a, grid, st, grouped, slab) : tg_launch<128>(a, grid, st, grouped, slab);
+  if (e != cudaSuccess || !(ksplit > 1 && split_ws)) return e;
+  tg_reduce_k<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(ws, ksplit, M * N, N, C, ldc, bias, beta);
+  if (launches) ++*launches;
+  return cudaGetLastError();
 }

@@ -216,6 +216,14 @@ GEMM_SHAPES = [  # tA, tB, M, N, K, beta, bias
     (1, 0, 1, 20, 30000, 1.0, False),      # bias-row gradient of the coefficient products (M = 1)
     (1, 0, 5000, 100, 4096, 1.0, False),   # head weight gradient [N * channels, hidden]
     (1, 0, 100, 100, 3000, 0.0, False),    # DIP covariance mu^T mu
+    # M >= 148 tiles: the persistent kernel with op(B) resident in shared memory
+    (0, 0, 20000, 50, 92, 0.0, False),     # SGC layer-1 coef2 . W2
+    (0, 0, 19001, 20, 23, 0.0, False),     # unaligned rows (scalar loads), ragged last tile
+    (0, 0, 25000, 50, 250, 1.0, True),     # conv1d rows x [5 Ci, Co], bias + beta, 8 resident chunks
+    (0, 1, 19500, 92, 50, 0.0, False),     # dcoef2 = dm2s . W2^T: 128-wide N tile
+    (0, 1, 20000, 250, 50, 0.0, False),    # conv1d input gradient rows x [Co, 5 Ci]^T: two N tiles
+    (0, 0, 19000, 20, 1, 0.0, False),      # K = 1
+    (0, 0, 40000, 71, 70, 1.0, False),     # odd widths both ways
 ]
 
 
@@ -223,7 +231,7 @@ GEMM_SHAPES = [  # tA, tB, M, N, K, beta, bias
 def test_node_level_gemm_kernel(built, tA, tB, M, N, K, beta, use_bias):
     """tsgemm.cuh (the tcgen05 split-bf16 GEMM under `linear`, conv1d and the SGC coefficient products) against numpy fp64 at
     every shape family the step uses, with ragged tiles, unaligned leading dimensions, K tails, transposed operands, bias,
-    beta and split-K accumulation.  Bound: 2e-5 of sum |a||b| per output (fp32 sgemm is ~1e-6 of that)."""
+    beta and split-K accumulation.  Bound: 4e-6 of sum |a||b| per output -- fp32-grade (a 3-pass bf16 split would sit at ~1e-5)."""
     eng = built.Engine(built.make_config(8, 2, "disentangled", sampling_num=2))
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A = torch.randn((K, M) if tA else (M, K), generator=g)
@@ -234,7 +242,7 @@ def test_node_level_gemm_kernel(built, tA, tB, M, N, K, beta, use_bias):
     out = eng.debug_gemm(A, B, tA=bool(tA), tB=bool(tB), alpha=alpha, beta=beta, C0=C0, bias=bias).cpu().double().numpy()
     a = (A.T if tA else A).double().numpy(); b = (B.T if tB else B).double().numpy()
     want = alpha * (a @ b) + (beta * C0.double().numpy() if C0 is not None else 0.0) + (bias.double().numpy() if bias is not None else 0.0)
-    bound = 2e-5 * (np.abs(a) @ np.abs(b)) + 1e-6 * np.abs(want) + 1e-6
+    bound = 4e-6 * (np.abs(a) @ np.abs(b)) + 1e-6 * np.abs(want) + 1e-6
     assert np.isfinite(out).all()
     assert (np.abs(out - want) <= bound).all(), float((np.abs(out - want) / bound).max())
     eng.close()
