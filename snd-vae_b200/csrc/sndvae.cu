@@ -408,25 +408,25 @@ static int alloc_buffers(sndvae_t* h) {
 // ------------------------------------------------------------------------------------------
 // small host helpers
 // ------------------------------------------------------------------------------------------
-// row-major C[M,N] = alpha op(A) op(B) + beta C
-static cublasStatus_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
-                              const float* B, int ldb, float beta, float* C, int ldc) {
-  if (!h->use_cublas) {     // tcgen05 split-bf16 kernel with in-loader fp32 -> bf16 hi / lo conversion (tsgemm.cuh)
-    cudaError_t e = tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, nullptr, &h->launches, h->gemm_ws, h->gemm_ws_floats);
-    return e == cudaSuccess ? CUBLAS_STATUS_SUCCESS : CUBLAS_STATUS_EXECUTION_FAILED;
-  }
-  h->launches++;
-  return cublasSgemm(h->blas, tB ? CUBLAS_OP_T : CUBLAS_OP_N, tA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda,
-                     &beta, C, ldc);
-}
 __global__ void bias_rows_k(float* __restrict__ C, const float* __restrict__ bias, long long rows, int cols) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < rows * cols) C[idx] = bias[idx % cols];
 }
+// row-major C[M,N] = alpha op(A) op(B) + beta C (+ bias[N] in the epilogue)
+static cublasStatus_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
+                              const float* B, int ldb, float beta, float* C, int ldc, const float* bias = nullptr) {
+  if (!h->use_cublas) {     // tcgen05 split-bf16 kernel with in-loader fp32 -> bf16 plane conversion (tsgemm.cuh)
+    cudaError_t e = tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &h->launches, h->gemm_ws, h->gemm_ws_floats);
+    return e == cudaSuccess ? CUBLAS_STATUS_SUCCESS : CUBLAS_STATUS_EXECUTION_FAILED;
+  }
+  if (bias) { LEW(bias_rows_k, (long long)M * N, C, bias, (long long)M, N); beta = 1.f; }
+  h->launches++;
+  return cublasSgemm(h->blas, tB ? CUBLAS_OP_T : CUBLAS_OP_N, tA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda,
+                     &beta, C, ldc);
+}
 // Y[rows, o] = X[rows, i] W[i, o] + bias   (layers.py:566-576 on flattened features)
 static int lin_fwd(sndvae_t* h, const float* X, const long* mb, float* Y, long long rows, int i, int o) {
-  LEW(bias_rows_k, rows * o, Y, h->P + mb[1], rows, o);
-  CKB(gemm_rm(h, false, false, (int)rows, o, i, 1.f, X, i, h->P + mb[0], o, 1.f, Y, o));
+  CKB(gemm_rm(h, false, false, (int)rows, o, i, 1.f, X, i, h->P + mb[0], o, 0.f, Y, o, h->P + mb[1]));
   return 0;
 }
 // dW += X^T dY; db += colsum(dY); dX = dY W^T (optional)
@@ -448,8 +448,7 @@ static void bn_bwd(sndvae_t* h, const float* dout, int ldd, const float* in, int
 static int conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, long long rows, int Ci, int Co) {
   if (rows * Ci < 4096) { LEW(conv1d_fwd_k, rows * Co, in, h->P + k, h->P + b, out, rows, h->N, Ci, Co, KS); return 0; }
   LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
-  LEW(bias_rows_k, rows * Co, out, h->P + b, rows, Co);
-  CKB(gemm_rm(h, false, false, (int)rows, Co, KS * Ci, 1.f, h->colbuf, KS * Ci, h->P + k, Co, 1.f, out, Co));
+  CKB(gemm_rm(h, false, false, (int)rows, Co, KS * Ci, 1.f, h->colbuf, KS * Ci, h->P + k, Co, 0.f, out, Co, h->P + b));
   return 0;
 }
 // weight/bias grads + optional input grad of a conv1d layer

@@ -46,11 +46,14 @@ struct TgArgs {
   int chunks_per_split;      // tsgemm_k: K chunks handled by one CTA along grid.z
   int atomic;                // tsgemm_k: add the partial tile into C with atomics (split K; beta is taken as 1)
   int tiles_per_cta;         // tsgemm_tall_k: consecutive M tiles per CTA
+  int bn_tile;               // tsgemm_tall_k: columns per N tile (a multiple of 16, <= TT_BN)
   long long split_stride;    // tsgemm_k, deterministic split K: split z writes its partial tile to C + z * split_stride (a workspace)
   int lda, ldb;              // slab form: row lengths (floats) of the K-major slabs of A and B
 };
 
-// 8 consecutive K values -> three packed bf16x8 planes, lowest K at the lowest address
+// 8 consecutive K values -> three packed bf16x8 planes, lowest K at the lowest address.  Pairs are converted with the packed
+// cvt.rn.bf16x2.f32 (one F2FP for two values; the scalar F2F runs on the 16-lane conversion pipe and was measured to bound the
+// producers) and the remainder is taken against the bf16 bits widened by a shift / mask.
 __device__ __forceinline__ void tg_split8(const float* v, uint4* pl) {
   uint32_t w[TG_NP][4];
 #pragma unroll
@@ -58,13 +61,48 @@ __device__ __forceinline__ void tg_split8(const float* v, uint4* pl) {
     float r0 = v[2 * i], r1 = v[2 * i + 1];
 #pragma unroll
     for (int p = 0; p < TG_NP; ++p) {
-      const __nv_bfloat16 b0 = __float2bfloat16_rn(r0), b1 = __float2bfloat16_rn(r1);
-      r0 -= __bfloat162float(b0); r1 -= __bfloat162float(b1);
-      w[p][i] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);          // .x = r0 (low half), .y = r1 (high half)
+      const uint32_t bits = *reinterpret_cast<const uint32_t*>(&b);
+      w[p][i] = bits;
+      if (p + 1 < TG_NP) { r0 -= __uint_as_float(bits << 16); r1 -= __uint_as_float(bits & 0xffff0000u); }
     }
   }
 #pragma unroll
   for (int p = 0; p < TG_NP; ++p) pl[p] = make_uint4(w[p][0], w[p][1], w[p][2], w[p][3]);
+}
+// 4 consecutive K values -> three packed bf16x4 planes (8 bytes each)
+__device__ __forceinline__ void tg_split4(const float* v, uint2* pl) {
+  uint32_t w[TG_NP][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float r0 = v[2 * i], r1 = v[2 * i + 1];
+#pragma unroll
+    for (int p = 0; p < TG_NP; ++p) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(r0, r1);
+      const uint32_t bits = *reinterpret_cast<const uint32_t*>(&b);
+      w[p][i] = bits;
+      if (p + 1 < TG_NP) { r0 -= __uint_as_float(bits << 16); r1 -= __uint_as_float(bits & 0xffff0000u); }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < TG_NP; ++p) pl[p] = make_uint2(w[p][0], w[p][1]);
+}
+// 4 K values of row r starting at k (K contiguous in memory)
+__device__ __forceinline__ void tg_load4_kmajor(const float* __restrict__ base, long long rs, long long r, long long rmax, int k, int kmax,
+                                                bool vec_ok, float* v) {
+  if (r < rmax && k < kmax) {
+    const float* p = base + r * rs + k;
+    if (vec_ok && k + 4 <= kmax) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (k + j < kmax) ? __ldg(p + j) : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = 0.f;
+  }
 }
 // byte offset of (row, 8-wide K group g) inside one plane of a chunk tile: core matrix (8 rows x 8 K) = 128 contiguous bytes,
 // the 4 core matrices of a row group along K 128 B apart (LBO), row groups 512 B apart (SBO)
@@ -231,12 +269,12 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
 #pragma unroll
       for (int q = 0; q < NA; ++q) {
         const int idx = t + q * TG_PROD, row = idx & (TG_BM - 1), g = idx >> 7;
+        if (m0 + row >= P.M) continue;           // rows past M only feed output rows that are never stored: left as they are
         float v[8];
         if (partial) tg_load_item(P.A, 1, P.lda, m0 + row, P.M, k0 + 8 * g, P.K, false, v);
         else {
-          const bool ok = m0 + row < P.M;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = ok ? rA[(8 * g + j) * P.lda + m0 + row] : 0.f;
+          for (int j = 0; j < 8; ++j) v[j] = rA[(8 * g + j) * P.lda + m0 + row];
         }
         tg_store_item(v, st, TG_APLANE, row, g);
       }
@@ -245,12 +283,12 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
         const int idx = t + q * TG_PROD;
         if (idx < bnc * 4) {
           const int g = idx / bnc, row = idx - g * bnc;
+          if (n0 + row >= P.N) continue;         // likewise: columns past N are never stored
           float v[8];
           if (partial) tg_load_item(P.B, 1, P.ldb, n0 + row, P.N, k0 + 8 * g, P.K, false, v);
           else {
-            const bool ok = n0 + row < P.N;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = ok ? rB[(8 * g + j) * P.ldb + n0 + row] : 0.f;
+            for (int j = 0; j < 8; ++j) v[j] = rB[(8 * g + j) * P.ldb + n0 + row];
           }
           tg_store_item(v, st + TG_NP * TG_APLANE, B_PLANE, row, g);
         }
@@ -414,28 +452,38 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
 // ---------------------------------------------------------------------------------------------------------------------------
 #define TT_PROD 512
 #define TT_THREADS (TT_PROD + 32 + 128)
-#define TT_STAGES 4
+#define TT_STAGES 3
+#define TT_BN 128         /* widest N tile of the persistent kernel: two B planes stacked along N make one MMA of N <= 256 */
 #define TT_AHEAD 3        /* producer register prefetch distance (units of one 8-value item) */
-template <int BNMAX>
+// MMA shape.  The three bf16 planes of op(B) lie back to back along N, so that products sharing their A plane are one
+// instruction over two stacked B planes; the six split products of a K step are four instructions into an accumulator of
+// 2 bnc columns, and the epilogue adds the two column blocks (which block a product lands in does not matter):
+//     A_hi  x [B_hi | B_mid]   (N = 2 bnc)      columns [0, bnc) += hi.hi,  [bnc, 2 bnc) += hi.mid
+//     A_mid x [B_hi | B_mid]   (N = 2 bnc)      columns [0, bnc) += mid.hi, [bnc, 2 bnc) += mid.mid
+//     A_lo  x [B_hi]           (N = bnc)        columns [0, bnc) += lo.hi
+//     A_hi  x [B_lo]           (N = bnc)        columns [bnc, 2 bnc) += hi.lo
+// (Measured: 6 -> 3 instructions per K step left the kernel's time unchanged -- it is not paced by the MMA count.)
 __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
-  constexpr int B_PLANE = BNMAX * TG_BK * 2;
+  constexpr int BNMAX = TT_BN;
   constexpr int A_STAGE = TG_NP * TG_APLANE;
-  constexpr int SROW = BNMAX + 1;                      // padded row of the output staging tile (floats)
-  constexpr uint32_t TMEM_COLS = 2 * BNMAX;
+  constexpr uint32_t SLOT_COLS = 256;                  // one accumulator slot: 2 bnc <= 256 columns
+  constexpr uint32_t TMEM_COLS = 2 * SLOT_COLS;
   extern __shared__ __align__(128) uint8_t tg_smem[];
   __shared__ uint64_t full_bar[TT_STAGES], empty_bar[TT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BNMAX;
-  int bn = P.N - n0; if (bn > BNMAX) bn = BNMAX;
+  const int n0 = blockIdx.y * P.bn_tile;
+  int bn = P.N - n0; if (bn > P.bn_tile) bn = P.bn_tile;
   const int bnc = (bn + 15) & ~15;
+  const int B_PLANE = bnc * TG_BK * 2;                  // planes back to back: rows p * bnc + n of the stacked operand
+  const int SROW = P.bn_tile + 1;                       // padded row of the output staging tile (floats)
   const int nkc = (P.K + TG_BK - 1) / TG_BK;
   const long long mtiles = (P.M + TG_BM - 1) / TG_BM;
   const long long t_lo = (long long)blockIdx.x * P.tiles_per_cta;
   long long nt = mtiles - t_lo; if (nt > P.tiles_per_cta) nt = P.tiles_per_cta; if (nt < 0) nt = 0;
   uint8_t* sB = tg_smem;
-  uint8_t* sA = tg_smem + (size_t)nkc * TG_NP * B_PLANE;
+  uint8_t* sA = tg_smem + (((size_t)nkc * TG_NP * B_PLANE + 1023) & ~(size_t)1023);
   float* sC = reinterpret_cast<float*>(sA + (size_t)TT_STAGES * A_STAGE);
 
   if (threadIdx.x == 0) {
@@ -459,13 +507,18 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
   if (warp < 16) {
     const int t = threadIdx.x, row = t >> 2, g = t & 3;
     const bool a_vec = (P.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
-    const int off = tg_tile_off(row, g);
-    // register ring: the loads of unit u + TT_AHEAD are issued before unit u is converted (TT_AHEAD x 32 bytes in flight per thread)
+    // Each thread owns row t / 4 and the K quads 4 g .. 4 g + 3 and 16 + 4 g .. 16 + 4 g + 3 of every chunk (g = t % 4): the four
+    // threads of a row read 64 contiguous bytes per load instruction, and a warp's 8-byte stores of a quad fill two whole core
+    // matrices (8 rows x 16 bytes each): conflict-free.  Register ring: the loads of unit u + TT_AHEAD are issued before unit u is
+    // converted (TT_AHEAD x 32 bytes in flight per thread).
+    const int off0 = tg_tile_off(row, g >> 1) + (g & 1) * 8, off1 = tg_tile_off(row, 2 + (g >> 1)) + (g & 1) * 8;
     float buf[TT_AHEAD + 1][8];
     long long lt = 0; int lc = 0;                                     // (tile, chunk) of the next unit to load
+#define TT_LOAD_(dst) do { const long long r_ = (t_lo + lt) * TG_BM + row; const int k_ = lc * TG_BK + 4 * g; \
+      tg_load4_kmajor(P.A, P.a_rs, r_, P.M, k_, P.K, a_vec, dst); tg_load4_kmajor(P.A, P.a_rs, r_, P.M, k_ + 16, P.K, a_vec, dst + 4); } while (0)
 #pragma unroll
     for (int d = 0; d < TT_AHEAD; ++d) {
-      if (d < units) tg_load8_kmajor(P.A, P.a_rs, (t_lo + lt) * TG_BM + row, P.M, lc * TG_BK + 8 * g, P.K, a_vec, buf[d]);
+      if (d < units) TT_LOAD_(buf[d]);
       if (++lc == nkc) { lc = 0; ++lt; }
     }
     for (long long u0 = 0; u0 < units; u0 += TT_AHEAD + 1) {
@@ -473,25 +526,28 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
       for (int d = 0; d <= TT_AHEAD; ++d) {
         const long long u = u0 + d;
         if (u < units) {
-          if (u + TT_AHEAD < units)
-            tg_load8_kmajor(P.A, P.a_rs, (t_lo + lt) * TG_BM + row, P.M, lc * TG_BK + 8 * g, P.K, a_vec, buf[(d + TT_AHEAD) % (TT_AHEAD + 1)]);
+          if (u + TT_AHEAD < units) TT_LOAD_(buf[(d + TT_AHEAD) % (TT_AHEAD + 1)]);
           if (++lc == nkc) { lc = 0; ++lt; }
           const int s = (int)(u % TT_STAGES); const uint32_t ph = (uint32_t)((u / TT_STAGES) & 1);
-          uint4 pl[TG_NP]; tg_split8(buf[d], pl);
+          uint2 p0[TG_NP], p1[TG_NP]; tg_split4(buf[d], p0); tg_split4(buf[d] + 4, p1);
           if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1);
           __syncwarp();
-          uint8_t* st = sA + (size_t)s * A_STAGE + off;
+          uint8_t* st = sA + (size_t)s * A_STAGE;
 #pragma unroll
-          for (int p = 0; p < TG_NP; ++p) *reinterpret_cast<uint4*>(st + p * TG_APLANE) = pl[p];
+          for (int p = 0; p < TG_NP; ++p) {
+            *reinterpret_cast<uint2*>(st + p * TG_APLANE + off0) = p0[p];
+            *reinterpret_cast<uint2*>(st + p * TG_APLANE + off1) = p1[p];
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[s]);
         }
       }
     }
+#undef TT_LOAD_
   } else if (warp == 16) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(TG_BM, bnc, 0, 0);
+      const uint32_t idesc2 = umma_idesc(TG_BM, 2 * bnc, 0, 0), idesc1 = umma_idesc(TG_BM, bnc, 0, 0);
       const uint64_t dz = umma_desc(0u, 128, 512, 0ull);
       const uint32_t sb0 = smem_u32(sB), sa0 = smem_u32(sA);
       long long u = 0;
@@ -503,7 +559,16 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
           const int s = (int)(u % TT_STAGES); const uint32_t ph = (uint32_t)((u / TT_STAGES) & 1);
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          tg_issue_chunk(tmem_d + slot * BNMAX, sa0 + s * A_STAGE, sb0 + c * TG_NP * B_PLANE, B_PLANE, idesc, c == 0, dz);
+          const uint32_t td = tmem_d + slot * SLOT_COLS, sa = sa0 + s * A_STAGE, sb = sb0 + c * TG_NP * B_PLANE;
+#pragma unroll
+          for (int k = 0; k < TG_BK / 16; ++k) {
+            const uint64_t b = dz + ((sb + k * 256) >> 4), bl = dz + ((sb + 2 * B_PLANE + k * 256) >> 4);
+            const uint64_t ah = dz + ((sa + k * 256) >> 4);
+            umma_bf16(td, ah, b, idesc2, (c == 0 && k == 0) ? 0u : 1u);
+            umma_bf16(td, dz + ((sa + TG_APLANE + k * 256) >> 4), b, idesc2, 1u);
+            umma_bf16(td, dz + ((sa + 2 * TG_APLANE + k * 256) >> 4), b, idesc1, 1u);
+            umma_bf16(td + bnc, ah, bl, idesc1, 1u);
+          }
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&acc_full[slot]);
@@ -522,13 +587,15 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
       mbar_wait(&acc_full[slot], (uint32_t)((ti >> 1) & 1));
       tc_fence_after();
       if (pending) { if (lane == 0) bulk_wait_read(); __syncwarp(); pending = false; }     // the previous store has left the staging rows
-      const uint32_t ta = tmem_d + slot * BNMAX + ((uint32_t)(q * 32) << 16);
+      const uint32_t ta = tmem_d + slot * SLOT_COLS + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < bnc; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(ta + c0, r);
+        uint32_t r0[16], r1[16];
+        tmem_ld16_nowait(ta + c0, r0); tmem_ld16_nowait(ta + bnc + c0, r1);
+        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (c0 + i < bn) srow[lane * sr + c0 + i] = P.alpha * __uint_as_float(r[i]) + (P.bias ? __ldg(P.bias + n0 + c0 + i) : 0.f);
+          if (c0 + i < bn)
+            srow[lane * sr + c0 + i] = P.alpha * (__uint_as_float(r1[i]) + __uint_as_float(r0[i])) + (P.bias ? __ldg(P.bias + n0 + c0 + i) : 0.f);
       }
       tc_fence_before();
       __syncwarp();
@@ -615,20 +682,18 @@ static cudaError_t tg_launch(const TgArgs& a, dim3 grid, cudaStream_t st, bool g
   if (slab) return grouped ? tg_launch_t<BNMAX, true, true>(a, grid, st) : tg_launch_t<BNMAX, false, true>(a, grid, st);
   return grouped ? tg_launch_t<BNMAX, true, false>(a, grid, st) : tg_launch_t<BNMAX, false, false>(a, grid, st);
 }
-template <int BNMAX>
-static size_t tt_smem_bytes(int K) {
+static size_t tt_smem_bytes(int K, int bnc) {
   const int nkc = (K + TG_BK - 1) / TG_BK;
-  return (size_t)nkc * TG_NP * BNMAX * TG_BK * 2 + (size_t)TT_STAGES * TG_NP * TG_APLANE + (size_t)TG_BM * (BNMAX + 1) * 4;
+  return (((size_t)nkc * TG_NP * bnc * TG_BK * 2 + 1023) & ~(size_t)1023) + (size_t)TT_STAGES * TG_NP * TG_APLANE + (size_t)TG_BM * (bnc + 1) * 4;
 }
-template <int BNMAX>
-static cudaError_t tt_launch_t(const TgArgs& a, dim3 grid, cudaStream_t st) {
+static cudaError_t tt_launch(const TgArgs& a, dim3 grid, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(tsgemm_tall_k<BNMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(tsgemm_tall_k, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_MAX);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  tsgemm_tall_k<BNMAX><<<grid, TT_THREADS, tt_smem_bytes<BNMAX>(a.K), st>>>(a);
+  tsgemm_tall_k<<<grid, TT_THREADS, tt_smem_bytes(a.K, a.bn_tile), st>>>(a);
   return cudaGetLastError();
 }
 
@@ -644,21 +709,24 @@ static cudaError_t tsgemm(cudaStream_t st, bool tA, bool tB, long long M, int N,
   a.A = A; a.B = B; a.C = C; a.bias = bias; a.M = M; a.N = N; a.K = K;
   a.a_rs = tA ? 1 : lda; a.a_ks = tA ? lda : 1;
   a.b_ns = tB ? ldb : 1; a.b_ks = tB ? 1 : ldb;
-  a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.atomic = 0; a.tiles_per_cta = 1; a.chunks_per_split = 1; a.split_stride = 0;
+  a.ldc = ldc; a.alpha = alpha; a.beta = beta; a.atomic = 0; a.tiles_per_cta = 1; a.chunks_per_split = 1; a.split_stride = 0; a.bn_tile = 0;
   const int chunks = (K + TG_BK - 1) / TG_BK;
   const int bnmax = N <= 64 ? 64 : 128;
   const long long mt = (M + TG_BM - 1) / TG_BM; const int nt = (N + bnmax - 1) / bnmax;
   if (mt > 0x7fffffffLL || nt > 65535) return cudaErrorInvalidValue;
-  // tall and skinny with op(B) small enough to stay in shared memory: the persistent kernel
-  const size_t tall_smem = bnmax == 64 ? tt_smem_bytes<64>(K) : tt_smem_bytes<128>(K);
-  if (!tA && K > 0 && mt >= 148 && tall_smem <= TT_SMEM_MAX) {
+  // tall and skinny with op(B) small enough to stay in shared memory: the persistent kernel, N tiles of equal width <= TT_BN
+  const int tnt = (N + TT_BN - 1) / TT_BN;
+  const int tbn = (((N + tnt - 1) / tnt) + 15) & ~15;
+  if (!tA && K > 0 && mt >= 148 && tbn <= TT_BN && tt_smem_bytes(K, tbn) <= TT_SMEM_MAX) {
     int device = 0, sms = 148; cudaGetDevice(&device); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    long long ctas = sms / nt; if (ctas < 1) ctas = 1; if (ctas > mt) ctas = mt;
+    const int tnt2 = (N + tbn - 1) / tbn;
+    long long ctas = sms / tnt2; if (ctas < 1) ctas = 1; if (ctas > mt) ctas = mt;
     a.tiles_per_cta = (int)((mt + ctas - 1) / ctas);
     ctas = (mt + a.tiles_per_cta - 1) / a.tiles_per_cta;
-    dim3 grid((unsigned)ctas, (unsigned)nt, 1);
+    a.bn_tile = tbn;
+    dim3 grid((unsigned)ctas, (unsigned)tnt2, 1);
     if (launches) ++*launches;
-    return bnmax == 64 ? tt_launch_t<64>(a, grid, st) : tt_launch_t<128>(a, grid, st);
+    return tt_launch(a, grid, st);
   }
   int ksplit = 1;
   // a long reduction with few output tiles: split K over CTAs.  Weight gradients (tA: the reduction runs over rows) add their
