@@ -28,7 +28,7 @@ extern "C" {
 
 #define SNDVAE_OK          0
 #define SNDVAE_E_ARG      -1   /* bad argument / shape (TF: InvalidArgumentError) */
-#define SNDVAE_E_CUDA     -2   /* CUDA / cuBLAS failure, or no usable device */
+#define SNDVAE_E_CUDA     -2   /* CUDA failure, or no usable device */
 #define SNDVAE_E_DENSE    -3   /* a sampled adjacency row set exceeded the edge capacity */
 #define SNDVAE_E_STATE    -4   /* call sequence error */
 

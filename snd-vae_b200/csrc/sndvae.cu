@@ -15,7 +15,6 @@
 #include "synth.cuh"
 #include "zzt.cuh"
 #include "tsgemm.cuh"
-#include <cublas_v2.h>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -41,7 +40,6 @@ struct StageTimer { std::vector<cudaEvent_t> ev; std::vector<const char*> name; 
 struct sndvae_handle {
   sndvae_config cfg;
   cudaStream_t stream;
-  cublasHandle_t blas;
   std::string err;
   std::vector<sndvae_param_info> table;
   PT pt;
@@ -92,7 +90,6 @@ struct sndvae_handle {
   struct Shift { char** p; long long bytes; };
   std::vector<Shift> shifts;
   float* gemm_ws; size_t gemm_ws_floats;   // workspace of the deterministic split-K products (tsgemm.cuh)
-  int use_cublas;                      // SNDVAE_CUBLAS=1: library sgemm instead of tsgemm (A/B switch while tsgemm is validated)
   int hf_ready;                        // every host-feed staging buffer is allocated
   int max_c;                           // widest node-level channel count of the config (sizes gA / gB / gC / colbuf)
   int poisoned;                        // a step failed half-way: arenas / losses are undefined until the next successful run
@@ -145,7 +142,7 @@ static int fail(sndvae_t* h, int code, const char* fmt, ...) {
   return code;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-#define CKB(call) do { cublasStatus_t s_ = (call); if (s_ != CUBLAS_STATUS_SUCCESS) return fail(h, SNDVAE_E_CUDA, "%s: cublas status %d (%s:%d)", #call, (int)s_, __FILE__, __LINE__); } while (0)
+#define CKB(call) do { cudaError_t s_ = (call); if (s_ != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(s_), __FILE__, __LINE__); } while (0)
 #define LAUNCH(k, grid, block, smem, ...) do { k<<<(grid), (block), (smem), h->stream>>>(__VA_ARGS__); h->launches++; } while (0)
 #define LEW(k, n, ...) LAUNCH(k, cdiv((n), 256), 256, 0, __VA_ARGS__)   /* elementwise launch */
 
@@ -412,17 +409,11 @@ __global__ void bias_rows_k(float* __restrict__ C, const float* __restrict__ bia
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < rows * cols) C[idx] = bias[idx % cols];
 }
-// row-major C[M,N] = alpha op(A) op(B) + beta C (+ bias[N] in the epilogue)
-static cublasStatus_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
-                              const float* B, int ldb, float beta, float* C, int ldc, const float* bias = nullptr) {
-  if (!h->use_cublas) {     // tcgen05 split-bf16 kernel with in-loader fp32 -> bf16 plane conversion (tsgemm.cuh)
-    cudaError_t e = tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &h->launches, h->gemm_ws, h->gemm_ws_floats);
-    return e == cudaSuccess ? CUBLAS_STATUS_SUCCESS : CUBLAS_STATUS_EXECUTION_FAILED;
-  }
-  if (bias) { LEW(bias_rows_k, (long long)M * N, C, bias, (long long)M, N); beta = 1.f; }
-  h->launches++;
-  return cublasSgemm(h->blas, tB ? CUBLAS_OP_T : CUBLAS_OP_N, tA ? CUBLAS_OP_T : CUBLAS_OP_N, N, M, K, &alpha, B, ldb, A, lda,
-                     &beta, C, ldc);
+// row-major C[M,N] = alpha op(A) op(B) + beta C (+ bias[N] in the epilogue): the hand-written tcgen05 kernels of tsgemm.cuh
+// (fp32 operands split into three bf16 planes by the loaders, six products, fp32 accumulation in TMEM)
+static cudaError_t gemm_rm(sndvae_t* h, bool tA, bool tB, int M, int N, int K, float alpha, const float* A, int lda,
+                           const float* B, int ldb, float beta, float* C, int ldc, const float* bias = nullptr) {
+  return tsgemm(h->stream, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, &h->launches, h->gemm_ws, h->gemm_ws_floats);
 }
 // Y[rows, o] = X[rows, i] W[i, o] + bias   (layers.py:566-576 on flattened features)
 static int lin_fwd(sndvae_t* h, const float* X, const long* mb, float* Y, long long rows, int i, int o) {
@@ -1320,8 +1311,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   *out = nullptr;
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
-  h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->blas = nullptr; h->pinned_loss = nullptr; h->ev_used = 0;
-  h->use_cublas = getenv("SNDVAE_CUBLAS") && atoi(getenv("SNDVAE_CUBLAS")) != 0;
+  h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->pinned_loss = nullptr; h->ev_used = 0;
   h->hf_ready = 0; h->hc_ready = 0; h->hc_features = nullptr; h->poisoned = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr; h->zz_planes = nullptr; h->zz_cap = 0;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
@@ -1377,11 +1367,6 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     return fail(h, SNDVAE_E_CUDA, "no CUDA device: the SND-VAE hot path has no CPU fallback");
   cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
   if (prop.major < 10) return fail(h, SNDVAE_E_CUDA, "device sm_%d%d is not sm_100: this library is built for B200 only", prop.major, prop.minor);
-  if (cublasCreate(&h->blas) != CUBLAS_STATUS_SUCCESS) return fail(h, SNDVAE_E_CUDA, "cublasCreate failed");
-  cublasSetStream(h->blas, h->stream);
-  // plain fp32 library GEMMs, no TF32.  (SNDVAE_CUBLAS_BF16X9=1 asks for cuBLAS's BF16x9 fp32 emulation instead; the cuBLAS 12.8
-  // that PyTorch loads into the process ignores it -- measured: no change in kernels or time.)
-  cublasSetMathMode(h->blas, getenv("SNDVAE_CUBLAS_BF16X9") ? CUBLAS_FP32_EMULATED_BF16X9_MATH : CUBLAS_PEDANTIC_MATH);
   int r = alloc_buffers(h); if (r) return r;
   if (cudaMallocHost((void**)&h->pinned_loss, 64) != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMallocHost failed");
   h->b1p = c.adam_beta1; h->b2p = c.adam_beta2;
@@ -1414,7 +1399,6 @@ int sndvae_destroy(sndvae_t* h) {
   if (h->cs) cudaStreamDestroy(h->cs);
   if (h->ds) cudaStreamDestroy(h->ds);
   if (h->pinned_loss) cudaFreeHost(h->pinned_loss);
-  if (h->blas) cublasDestroy(h->blas);
   delete h;
   return 0;
 }
