@@ -801,6 +801,46 @@ static int decoder_finish(sndvae_t* h, bool backward) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// data-parallel communicator: NCCL, resolved at run time (dlopen of the libnccl.so.2 already in the process -- PyTorch
+// loads it -- or on the loader path), so that libsndvae.so itself has no link-time dependency on it
+// ------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+typedef struct { char internal[128]; } nccl_unique_id;          // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
+struct NcclApi {
+  int (*GetUniqueId)(nccl_unique_id*);
+  int (*CommInitRank)(void**, int, nccl_unique_id, int);
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
+  int (*CommDestroy)(void*);
+  const char* (*GetErrorString)(int);
+  int ok;
+};
+static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+static const char* nccl_load() {
+  if (g_nccl.ok) return nullptr;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return "libnccl.so.2 is neither loaded in this process nor on the loader path";
+#define SYM_(f) do { *(void**)(&g_nccl.f) = dlsym(lib, "nccl" #f); if (!g_nccl.f) return "nccl" #f " not found in libnccl"; } while (0)
+  SYM_(GetUniqueId); SYM_(CommInitRank); SYM_(AllReduce); SYM_(AllGather); SYM_(CommDestroy); SYM_(GetErrorString);
+#undef SYM_
+  g_nccl.ok = 1;
+  return nullptr;
+}
+#define NCCL_FLOAT 7   /* ncclFloat32 */
+#define NCCL_SUM 0     /* ncclSum */
+#define CKN(call) do { int s_ = (call); if (s_ != 0) return fail(h, SNDVAE_E_CUDA, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(s_), __FILE__, __LINE__); } while (0)
+// sum of the gradient arena (and of the 8 loss sums) over the ranks of the communicator; no-op without one
+static int allreduce_arena(sndvae_t* h, bool with_losses) {
+  if (!h->comm || h->world <= 1) return 0;
+  CKN(g_nccl.AllReduce(h->G, h->G, (size_t)h->nparam, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
+  if (with_losses) CKN(g_nccl.AllReduce(h->loss, h->loss, 8, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
+  h->launches += with_losses ? 2 : 1;
+  return 0;
+}
+
 // ---- loss variants on the latents (optimizer.py:166-183) -------------------------------------------------------------
 static float capacity_C(const sndvae_t* h) {     // optimizer.py:172
   const sndvae_config& c = h->cfg;
@@ -808,25 +848,34 @@ static float capacity_C(const sndvae_t* h) {     // optimizer.py:172
   float C = c.C_max * c.C_step / c.C_stop_iter * (float)(h->global_iter / step);
   return C < 0.f ? 0.f : (C > c.C_max ? c.C_max : C);
 }
-// DIP forward for the three posterior means: batch covariance -> regulariser value (loss[6]) and d reg / d cov (kept for backward)
+// DIP forward for the three posterior means: batch covariance -> regulariser value (loss[6]) and d reg / d cov (kept for backward).
+// With a communicator the covariance is the GLOBAL batch's, as in the reference where one process sees the whole batch
+// (optimizer.py:7-21): the second-moment and mean sums are all-reduced (L^2 + L floats per latent) before dip_cov_k.
 static int dip_forward(sndvae_t* h) {
   const sndvae_config& c = h->cfg;
   const float* mus[3] = {h->mu_s, h->mu_g, h->mu_sg};
   const long long rows[3] = {h->B, h->B, h->BS};
   const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
+  const int world = (h->comm && h->world > 1) ? h->world : 1;
   for (int i = 0; i < 3; ++i) {
     const int L = Ls[i];
     CK(cudaMemsetAsync(h->dipv, 0, sizeof(float) * L, h->stream));
     LAUNCH(colsum_k, dim3(cdiv(rows[i], XTDY_SLAB), cdiv(L, 128)), 128, 0, mus[i], L, h->dipv, rows[i], L);
     CKB(gemm_rm(h, true, false, L, L, (int)rows[i], 1.f, mus[i], L, mus[i], L, 0.f, h->dipS, L));
-    LAUNCH(dip_cov_k, cdiv((long long)L * L, 256), 256, 0, h->dipS, h->dipv, h->dipG[i], h->dipm[i], h->loss + 6, L, 1.f / (float)rows[i],
+    if (world > 1) {
+      CKN(g_nccl.AllReduce(h->dipS, h->dipS, (size_t)L * L, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
+      CKN(g_nccl.AllReduce(h->dipv, h->dipv, (size_t)L, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
+      h->launches += 2;
+    }
+    LAUNCH(dip_cov_k, cdiv((long long)L * L, 256), 256, 0, h->dipS, h->dipv, h->dipG[i], h->dipm[i], h->loss + 6, L, 1.f / (float)(rows[i] * world),
            c.dip_lambda_od, c.dip_lambda_d);
   }
   return 0;
 }
-// dmu += beta (B / global batch) (2 / rows) (mu - m) G
+// dmu += beta (graphs under the statistic / global batch) (2 / rows of the statistic) (mu - m) G
 static int dip_backward(sndvae_t* h, int which, const float* mu, float* dmu, long long rows, int L, float gB) {
-  const float alpha = h->cfg.beta * 2.f / (float)rows * ((float)h->B / gB);
+  const int world = (h->comm && h->world > 1) ? h->world : 1;
+  const float alpha = h->cfg.beta * 2.f / (float)(rows * world) * ((float)(h->B * world) / gB);
   CKB(gemm_rm(h, false, false, (int)rows, L, L, alpha, mu, L, h->dipG[which], L, 1.f, dmu, L));
   CKB(gemm_rm(h, false, false, 1, L, L, 1.f, h->dipm[which], L, h->dipG[which], L, 0.f, h->dipv, L));
   LEW(sub_row_k, rows * L, dmu, h->dipv, rows, L, alpha);
@@ -1016,46 +1065,6 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
           h->G + p.sg_M3[l], h->G + p.sg_b3[l], d);
     }
   }
-  return 0;
-}
-
-// ------------------------------------------------------------------------------------------
-// data-parallel communicator: NCCL, resolved at run time (dlopen of the libnccl.so.2 already in the process -- PyTorch
-// loads it -- or on the loader path), so that libsndvae.so itself has no link-time dependency on it
-// ------------------------------------------------------------------------------------------
-#include <dlfcn.h>
-typedef struct { char internal[128]; } nccl_unique_id;          // ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES = 128)
-struct NcclApi {
-  int (*GetUniqueId)(nccl_unique_id*);
-  int (*CommInitRank)(void**, int, nccl_unique_id, int);
-  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t);
-  int (*CommDestroy)(void*);
-  const char* (*GetErrorString)(int);
-  int ok;
-};
-static NcclApi g_nccl = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-static const char* nccl_load() {
-  if (g_nccl.ok) return nullptr;
-  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) return "libnccl.so.2 is neither loaded in this process nor on the loader path";
-#define SYM_(f) do { *(void**)(&g_nccl.f) = dlsym(lib, "nccl" #f); if (!g_nccl.f) return "nccl" #f " not found in libnccl"; } while (0)
-  SYM_(GetUniqueId); SYM_(CommInitRank); SYM_(AllReduce); SYM_(AllGather); SYM_(CommDestroy); SYM_(GetErrorString);
-#undef SYM_
-  g_nccl.ok = 1;
-  return nullptr;
-}
-#define NCCL_FLOAT 7   /* ncclFloat32 */
-#define NCCL_SUM 0     /* ncclSum */
-#define CKN(call) do { int s_ = (call); if (s_ != 0) return fail(h, SNDVAE_E_CUDA, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString(s_), __FILE__, __LINE__); } while (0)
-// sum of the gradient arena (and of the 8 loss sums) over the ranks of the communicator; no-op without one
-static int allreduce_arena(sndvae_t* h, bool with_losses) {
-  if (!h->comm || h->world <= 1) return 0;
-  CKN(g_nccl.AllReduce(h->G, h->G, (size_t)h->nparam, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
-  if (with_losses) CKN(g_nccl.AllReduce(h->loss, h->loss, 8, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
-  h->launches += with_losses ? 2 : 1;
   return 0;
 }
 

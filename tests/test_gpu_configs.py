@@ -246,3 +246,55 @@ def test_node_level_gemm_kernel(built, tA, tB, M, N, K, beta, use_bias):
     assert np.isfinite(out).all()
     assert (np.abs(out - want) <= bound).all(), float((np.abs(out - want) / bound).max())
     eng.close()
+
+
+def test_drivers_train_reconstruct_generate(built, tmp_path):
+    """The three loops of main.py (train 299-356, test_reconstruct 374-426, test_generation 428-469) through the shims: batching
+    with the last partial batch dropped, accuracy / loss bookkeeping, checkpoint every `save_every` epochs, restore by path, the
+    z_*.npy dumps (main.py:411-416), and quirk Q11 (generation returns the encoder's posterior means)."""
+    flags = import_module("snd-vae_b200.flags"); model_m = import_module("snd-vae_b200.model"); opt_m = import_module("snd-vae_b200.optimizer")
+    sess_m = import_module("snd-vae_b200.session"); drv = import_module("snd-vae_b200.drivers"); data = import_module("snd-vae_b200.data")
+    F = flags.FLAGS; F.reset(); F.apply_dataset("synthetic2")
+    N, B, S, G = 12, 3, 2, 7                                   # 7 graphs -> two batches of 3, one graph dropped
+    F.batch_size = B; F.sampling_num = S; F.epochs = 2
+    d = data.synthetic_graphs(N, G, S, seed=3)
+    ph = sess_m.make_placeholders(B, S, N, F.num_feature, F.spatial_dim)
+
+    def build(kind):
+        F.type = kind
+        m = model_m.SGCNModelVAE(ph, F.num_feature, N)
+        o = opt_m.OptimizerVAE(preds_edge=m.generated_adj_prob, preds_node=m.generated_node_feat, preds_spatial=m.generated_spatial,
+                               labels_edge=ph["adj_truth"], labels_node=ph["feature_truth"], labels_spatial=ph["spatial_truth"],
+                               labels_rel=ph["rel_truth"], global_iter=ph["global_iter"], model=m, num_nodes=N, pos_weight=1.0, norm=1.0, beta=1)
+        return m, o
+    m, o = build("train")
+    log = drv.LossesLogger(str(tmp_path / "train_losses.csv"))
+    check, hist = drv.train(m, o, ph, d, ckpt_dir=str(tmp_path / "ckpt"), save_every=1, logger=log)
+    assert check.shape == (2, B, N, N) and len(hist) == 2 and set(hist[0]) >= {"loss", "adj_acc", "graph_kl", "spatial_kl", "sg_kl"}
+    assert all(np.isfinite(list(h.values())).all() for h in hist) and hist[1]["loss"] < hist[0]["loss"]
+    ck = str(tmp_path / "ckpt" / "model_dgt_global_1.ckpt")
+    assert os.path.exists(ck + ".npz") and len(log.rows) == 2 * len(hist[0])
+    Ptrained = {k: v.clone() for k, v in m.engine.get_params().items()}
+    mr, _ = build("test_reconstruct")
+    rec = drv.reconstruct(mr, ph, d, restore=ck, out_dir=str(tmp_path / "qual"), vae_type="disentangled")
+    for k, L in (("z_s", F.s_latent_size), ("z_sg", F.sg_latent_size), ("z_g", F.g_latent_size)):
+        z = np.load(tmp_path / "qual" / f"disentangled_{k}.npy")
+        assert z.shape == (2, B, L) and np.array_equal(z, rec[k])
+    assert rec["generated_adj"].shape == (2 * B, N, N) and rec["generated_spatial"].shape == (2 * B, N, 2)
+    # the restored model is the trained one: its posterior means are those of a direct forward pass on the first batch
+    eng = built.Engine(built.make_config(N, B, "disentangled", sampling_num=S))
+    eng.set_params(Ptrained)
+    first = {k: torch.from_numpy(np.ascontiguousarray(d[k][: B * S] if k in ("features", "spatial", "adj", "rel") else d[k][:B])) for k in d}
+    f = eng.forward(first, O.synthetic_noise(O.Config(num_nodes=N, sampling_num=S), B, 9, torch.float32), fetch=("z_mean_s", "z_mean_sg"))
+    np.testing.assert_allclose(rec["z_s"][0], f["z_mean_s"].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(rec["z_sg"][0], f["z_mean_sg"].cpu().numpy().reshape(B, S, -1).mean(1), rtol=1e-5, atol=1e-6)
+    eng.close()
+    mg, _ = build("test_generation")
+    gen = drv.generate(mg, ph, d, restore=ck)
+    np.testing.assert_allclose(gen["z_s"], rec["z_s"], rtol=1e-6, atol=1e-7)          # encoder means, whatever the decoder is fed (quirk Q11)
+    idx = np.arange(N)
+    assert gen["generated_adj"].shape == (2 * B, N, N) and (gen["generated_adj"][:, idx, idx] == 0).all()
+    assert not np.array_equal(gen["generated_spatial"], rec["generated_spatial"])     # prior draws, not posterior samples
+    with pytest.raises(ValueError):
+        drv.generate(mr, ph, d)
+    F.reset()

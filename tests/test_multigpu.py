@@ -29,7 +29,7 @@ def _shard(inp, noise, r, b, S):
     return si, sn
 
 
-def _worker(rank, world, port, N, b, S, steps, host_feeds, outdir):
+def _worker(rank, world, port, N, b, S, steps, host_feeds, outdir, variant="disentangled"):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     import sndvae_b200 as sv
@@ -40,7 +40,7 @@ def _worker(rank, world, port, N, b, S, steps, host_feeds, outdir):
     P = O.init_params(cfg, 7, torch.float32)
     inp = O.synthetic_inputs(cfg, world * b, 5, torch.float32); noise = O.synthetic_noise(cfg, world * b, 9, torch.float32)
     si, sn = _shard(inp, noise, rank, b, S)
-    eng = sv.Engine(sv.make_config(N, b, "disentangled", sampling_num=S, chunk_graphs=2))
+    eng = sv.Engine(sv.make_config(N, b, "disentangled", sampling_num=S, chunk_graphs=2, loss_variant=sv._lib.LOSS_VARIANTS[variant]))
     eng.set_params(P)
     eng.comm_init(rank, world)
     losses, gen = [], None
@@ -59,8 +59,10 @@ def _worker(rank, world, port, N, b, S, steps, host_feeds, outdir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("host_feeds", [False, True])
-def test_two_gpu_step_equals_one_gpu_step(built, tmp_path, host_feeds):
+@pytest.mark.parametrize("host_feeds,variant", [(False, "disentangled"), (True, "disentangled"), (False, "NED-VAE-IP")])
+def test_two_gpu_step_equals_one_gpu_step(built, tmp_path, host_feeds, variant):
+    """'NED-VAE-IP': the DIP regulariser couples every sample of the batch (optimizer.py:7-21); with a communicator its covariance is
+    the global batch's (second-moment sums all-reduced), so the 2-GPU step still equals the 1-GPU step on the concatenated batch."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -69,18 +71,18 @@ def test_two_gpu_step_equals_one_gpu_step(built, tmp_path, host_feeds):
     P = O.init_params(cfg, 7, torch.float32)
     inp = O.synthetic_inputs(cfg, world * b, 5, torch.float32); noise = O.synthetic_noise(cfg, world * b, 9, torch.float32)
     torch.cuda.set_device(0)
-    ref = built.Engine(built.make_config(N, world * b, "disentangled", sampling_num=S, chunk_graphs=2))
+    ref = built.Engine(built.make_config(N, world * b, "disentangled", sampling_num=S, chunk_graphs=2, loss_variant=built._lib.LOSS_VARIANTS[variant]))
     ref.set_params(P)
     ref_losses, ref_gen = [], None
     for _ in range(steps):
         r = ref.train_step(inp, noise)
         ref_losses.append(r["overall_loss"]); ref_gen = r["generated_adj"].cpu().numpy()
     P1 = ref.get_params(); ref.close()
-    mp.spawn(_worker, args=(world, _free_port(), N, b, S, steps, host_feeds, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), N, b, S, steps, host_feeds, str(tmp_path), variant), nprocs=world, join=True)
     z0, z1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
-    np.testing.assert_allclose(z0["losses"], np.asarray(ref_losses), rtol=2e-5)       # global-batch means, identical on both ranks
+    np.testing.assert_allclose(z0["losses"], np.asarray(ref_losses), rtol=2e-5, atol=1e-8)       # global-batch means, identical on both ranks
     np.testing.assert_allclose(z1["losses"], z0["losses"], rtol=1e-6)
     assert np.array_equal(z0["gen"], ref_gen[:b]) and np.array_equal(z1["gen"], ref_gen[b:])
     for k in P1:
-        np.testing.assert_allclose(z0[k], P1[k].numpy(), rtol=0, atol=2e-6, err_msg=k)
+        np.testing.assert_allclose(z0[k], P1[k].numpy(), rtol=0, atol=2e-6 if variant == "disentangled" else 2e-5, err_msg=k)
         assert np.array_equal(z0[k], z1[k]), k                                         # replicas stay bit-identical
