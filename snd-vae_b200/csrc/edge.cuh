@@ -195,6 +195,27 @@ __global__ void __launch_bounds__(YP_THREADS) y_producer_k(const float* __restri
   }
 }
 
+// The same product for any node_h_size (synthetic1: H = 50, main.py:164; protein: H = 5, main.py:230): one thread per output
+// (b, i, j, o), weights read through L1.  O(N^2 C1 Ch) per graph like the kernel above, without its register blocking -- the
+// configurations that need it have N = 25.
+__global__ void y_producer_generic_k(const float* __restrict__ a, const float* __restrict__ c, const float* __restrict__ WSa,
+                                     const float* __restrict__ WSc, const float* __restrict__ Rc, const float* __restrict__ Sa,
+                                     const float* __restrict__ b0, const float* __restrict__ gam1, const float* __restrict__ bet1,
+                                     YOut Y, int Bc, int N, int C1, int Ch) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long plane = (long long)Bc * N * N;
+  if (idx >= plane * C1) return;
+  const int o = (int)(idx % C1); const long long cell = idx / C1;
+  const int j = (int)(cell % N), i = (int)((cell / N) % N); const long long b = cell / ((long long)N * N);
+  const float* ai = a + (b * N + i) * Ch; const float* cj = c + (b * N + j) * Ch;
+  const float* wa = WSa + ((size_t)j * C1 + o) * Ch; const float* wc = WSc + ((size_t)i * C1 + o) * Ch;
+  float acc = 2.f * b0[o] + Rc[(b * N + j) * C1 + o] + Sa[(b * N + i) * C1 + o];
+  for (int ch = 0; ch < Ch; ++ch) acc = fmaf(ai[ch], __ldg(wa + ch), fmaf(cj[ch], __ldg(wc + ch), acc));
+  Y.E1[cell * C1 + o] = acc;
+  const float y = fmaxf(fmaf(acc, gam1[o] * BN_RS, bet1[o]), 0.f);
+  if (Y.Yf) { Y.Yf[cell * C1 + o] = y; Y.Yf[(plane + (b * N + j) * N + i) * C1 + o] = y; }
+}
+
 // backward counterpart of l0_combine_k for the tensor-core path: dE1 leaves as bf16 hi / lo planes in both
 // layouts (operands of the da / dc / dWS products), dSa[b,i,:] = sum_j dE1 is reduced here.
 __global__ void l0_combine_planes_k(const float* __restrict__ dY12, const float* __restrict__ E1, const float* __restrict__ gam1,

@@ -686,8 +686,10 @@ static int decoder_fwd(sndvae_t* h, const sndvae_inputs* in, sndvae_outputs* out
       dim3 yg(cdiv(N, YP_TJ), N);
       if (Chv == 40) LAUNCH(y_producer_k<40>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
                             h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
-      else LAUNCH(y_producer_k<20>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
+      else if (Chv == 20) LAUNCH(y_producer_k<20>, yg, YP_THREADS, 0, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
                   h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1);
+      else LEW(y_producer_generic_k, cells * C1, h->a + b0 * N * Chv, h->c + b0 * N * Chv, h->WSa, h->WSc, h->Rc + b0 * N * C1,
+               h->Sa + b0 * N * C1, h->P + p.e_b[0], h->P + p.e_bng[1], h->P + p.e_bnb[1], Y, bc, N, C1, Chv);
     }
     mark(h, "gemm_fwd");
     ev_begin(h, f1 * bc);
@@ -1335,11 +1337,17 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     return fail(h, SNDVAE_E_ARG, "loss_variant %d needs the disentangled model (optimizer.py:166-190)", c.loss_variant);
   if (c.loss_variant == SNDVAE_LOSS_TC && (c.s_latent_size > 32 * TCOR_LK || c.g_latent_size > 32 * TCOR_LK || c.sg_latent_size > 32 * TCOR_LK))
     return fail(h, SNDVAE_E_ARG, "the total-correlation kernels take latent sizes <= %d", 32 * TCOR_LK);
+  if (c.node_h_size != 20 && c.use_tensor_cores) {
+    // the tensor-core tiles of the edge decoder are built for node_h_size = 20 (synthetic2, main.py:209); other sizes
+    // (synthetic1: 50, main.py:164; protein: 5, main.py:230) run the e2e layers on the fp32 SIMT kernels
+    fprintf(stderr, "[sndvae] node_h_size = %d: edge decoder on the fp32 SIMT kernels (tensor-core tiles need node_h_size = 20)\n", c.node_h_size);
+    c.use_tensor_cores = 0;
+  }
   h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp); memset(&h->ytc, 0, sizeof h->ytc);
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
   if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);
-  if (c.node_h_size != 20 || c.e_d_hidden[0] > 52) return fail(h, SNDVAE_E_ARG, "this build supports node_h_size = 20 and e_d_hidden[0] <= 52 (synthetic2, main.py:209)");
+  if (c.e_d_hidden[0] > 52) return fail(h, SNDVAE_E_ARG, "this build supports e_d_hidden[0] <= 52 (main.py:209)");
   if (c.g_conv_hidden[0] > 32 || c.g_conv_hidden[1] > 32) return fail(h, SNDVAE_E_ARG, "g_conv_hidden must be <= 32");
   h->N = c.num_nodes; h->F = c.num_feature; h->D = c.spatial_dim; h->S = c.sampling_num; h->H = c.node_h_size;
   h->Chv = h->dis ? 2 * h->H : h->H; h->C1 = c.e_d_hidden[0]; h->C2 = c.e_d_hidden[1];

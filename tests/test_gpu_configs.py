@@ -298,3 +298,47 @@ def test_drivers_train_reconstruct_generate(built, tmp_path):
     with pytest.raises(ValueError):
         drv.generate(mr, ph, d)
     F.reset()
+
+
+@pytest.mark.parametrize("node_h,hid", [(50, 500), (5, 50)])
+def test_other_node_h_sizes_vs_oracle(built, node_h, hid):
+    """The reference's other flag blocks: synthetic1 (main.py:128-172: node_h_size = 50, sg hidden / latent 500) and the decoder
+    shape of `protein` (main.py:230: node_h_size = 5).  The tensor-core tiles are built for node_h_size = 20, so these run the
+    edge decoder on the fp32 SIMT kernels (selected by sndvae_create); losses, outputs and every gradient against the oracle."""
+    N, B, S = 25, 3, 2
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", node_h_size=node_h, sg_hidden_size=hid, sg_latent_size=hid)
+    enc, z, dec, L, grads = O.loss_and_grads(P, inp, noise, cfg, "factored")
+    eng = built.Engine(built.make_config(N, B, "disentangled", sampling_num=S, node_h_size=node_h, sg_hidden_size=hid, sg_latent_size=hid, chunk_graphs=2))
+    assert eng.cfg.use_tensor_cores == 2          # asked for the default; the handle itself switched to the SIMT edge decoder
+    eng.set_params(P)
+    res = eng.grads(inp, noise, fetch=("generated_adj_prob", "generated_spatial", "generated_node_feat"))
+    np.testing.assert_allclose(res["overall_loss"], [x.item() for x in L["overall_loss"]], rtol=1e-4)
+    for k in ("generated_adj_prob", "generated_spatial", "generated_node_feat"):
+        assert _relmax(res[k].cpu().numpy(), dec[k].detach().numpy()) < 1e-4, k
+    gg = eng.get_grads()
+    worst = max((_relmax(gg[k].numpy(), v.numpy()), k) for k, v in grads.items())
+    assert worst[0] < 1e-3, worst
+    eng.close()
+
+
+def test_synthetic1_flag_block_trains(built):
+    """flags.apply_dataset('synthetic1') (main.py:128-172) -> SGCNModelVAE / OptimizerVAE / Session.run: constructs and trains."""
+    flags = import_module("snd-vae_b200.flags"); model_m = import_module("snd-vae_b200.model"); opt_m = import_module("snd-vae_b200.optimizer")
+    sess_m = import_module("snd-vae_b200.session"); prep = import_module("snd-vae_b200.preprocessing"); data = import_module("snd-vae_b200.data")
+    F = flags.FLAGS; F.reset(); F.apply_dataset("synthetic1"); F.type = "train"; F.batch_size = 4; F.sampling_num = 3
+    N = 25
+    d = data.synthetic_graphs(N, F.batch_size, F.sampling_num, seed=11)
+    ph = sess_m.make_placeholders(F.batch_size, F.sampling_num, N, F.num_feature, F.spatial_dim)
+    m = model_m.SGCNModelVAE(ph, F.num_feature, N)
+    o = opt_m.OptimizerVAE(preds_edge=m.generated_adj_prob, preds_node=m.generated_node_feat, preds_spatial=m.generated_spatial,
+                           labels_edge=ph["adj_truth"], labels_node=ph["feature_truth"], labels_spatial=ph["spatial_truth"],
+                           labels_rel=ph["rel_truth"], global_iter=ph["global_iter"], model=m, num_nodes=N, pos_weight=1.0, norm=1.0, beta=1)
+    assert m.engine.cfg.node_h_size == 50 and m.engine.cfg.sg_latent_size == 500
+    fd = prep.construct_feed_dict_train(d["features"], d["spatial"], d["adj"], d["rel"], d["adj_truth"], d["feature_truth"], d["spatial_truth"], d["rel_truth"], ph)
+    costs = []
+    with sess_m.Session() as sess:
+        sess.run(sess_m.global_variables_initializer())
+        for _ in range(4):
+            costs.append(sess.run([o.opt_op, o.cost], feed_dict=fd)[1])
+    assert np.isfinite(costs).all() and costs[-1] < costs[0]
+    F.reset()
