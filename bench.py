@@ -517,7 +517,7 @@ def run_ours(args):
                    "parallelism": f"dp{world}", "collective": ("ncclAllReduce of the flat gradient arena inside libsndvae.so (sndvae_comm_init)" if world > 1 else "none"),
                    "chunk_graphs": int(eng.cfg.chunk_graphs), "tensor_cores": bool(args.tc), "e2e_layer1": {0: "fp32 SIMT", 1: "block-Toeplitz tcgen05 bf16x3", 2: "spectral: FFT + per-frequency tcgen05 bf16x3"}[args.tc],
                    "l2": "inputs larger than L2 (no flush needed)"},
-        "clocks": cs.summary(), "gpu_launches": int(launches), "final_loss": final_loss,
+        "clocks": cs.summary(), "gpu_launches": int(launches), "graph_replays": eng.graph_replays(), "final_loss": final_loss,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense, "stages": stages,
     }
     print(json.dumps(line), flush=True)

@@ -251,6 +251,11 @@ int sndvae_synth_inputs(sndvae_t* h, uint64_t seed, const sndvae_inputs* device_
 
 int64_t sndvae_launch_count(const sndvae_t* h);
 
+/* Small problems (batch_size * num_nodes^2 < 2^21 edge cells; SNDVAE_GRAPH=0/1 overrides) replay sndvae_train_step as one CUDA graph
+ * once the same feed / output buffers are seen a second time: the N = 25 step is ~260 launches of a few microseconds each
+ * (main.py's own configuration, BASELINE configs[0]).  Number of steps executed as a graph replay since create: */
+int64_t sndvae_graph_replays(const sndvae_t* h);
+
 /* The `global_iter` placeholder (main.py:262,329): only the 'disentangled_C' loss reads it (optimizer.py:172). */
 int sndvae_set_global_iter(sndvae_t* h, int64_t global_iter);
 

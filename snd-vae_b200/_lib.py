@@ -92,6 +92,7 @@ SYMBOLS = {
     "sndvae_set_global_iter": (C.c_int, [C.c_void_p, I64]),
     "sndvae_synth_inputs": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(Inputs)]),
     "sndvae_launch_count": (I64, [C.c_void_p]),
+    "sndvae_graph_replays": (I64, [C.c_void_p]),
     "sndvae_gemm_timing": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(I64), C.POINTER(C.c_double)]),
     "sndvae_stage_times": (C.c_int, [C.c_void_p, I32, C.c_void_p, C.c_void_p, I32, C.POINTER(I64)]),
     "sndvae_debug_gemm": (C.c_int, [C.c_void_p, I32, I32, I64, I32, I32, F32, C.c_void_p, I64, C.c_void_p, I64, F32, C.c_void_p, I64, C.c_void_p]),

@@ -8,7 +8,10 @@
 
 __global__ void __launch_bounds__(256) tf_adam_k(float4* __restrict__ p, const float4* __restrict__ g,
                                                  float4* __restrict__ m, float4* __restrict__ v, long long n4,
-                                                 float alpha, float omb1, float omb2, float eps) {
+                                                 const float* __restrict__ alpha_p, float omb1, float omb2, float eps) {
+  // alpha (the bias-corrected step size of this iteration) is read from device memory so that the launch arguments do not
+  // change from step to step: the whole step can then be replayed as one CUDA graph
+  const float alpha = __ldg(alpha_p);
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 P = p[i], G = g[i], M = m[i], V = v[i];

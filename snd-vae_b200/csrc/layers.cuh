@@ -77,10 +77,17 @@ __global__ void conv1d_bwd_in_k(const float* __restrict__ dout, const float* __r
 // slab of rows, each thread a strided set of (t, ci, co); one atomicAdd per
 // (block, parameter).
 #define XTDY_SLAB 512
+// grid of a row-slab reduction kernel: slabs of at most `max_slab` rows, but at least ~4 blocks per SM when the problem is small
+// (at N = 25, B = 32 a fixed 512-row slab left 2 blocks on 148 SMs)
+static inline unsigned slab_grid(long long rows, int max_slab) {
+  long long slab = rows / (148 * 4); if (slab < 8) slab = 8; if (slab > max_slab) slab = max_slab;
+  return (unsigned)((rows + slab - 1) / slab);
+}
 __global__ void xtdy_k(const float* __restrict__ X, int ldx, const float* __restrict__ dY, int ldy,
                        float* __restrict__ dW, long long rows, int N, int Ci, int Co, int ktaps) {
-  long long r0 = (long long)blockIdx.x * XTDY_SLAB;
-  long long r1 = r0 + XTDY_SLAB; if (r1 > rows) r1 = rows;
+  const long long slab = (rows + gridDim.x - 1) / gridDim.x;      // rows per block: the launch picks the grid (slab_grid)
+  long long r0 = (long long)blockIdx.x * slab;
+  long long r1 = r0 + slab; if (r1 > rows) r1 = rows;
   int pb = (ktaps - 1) / 2;
   int np = ktaps * Ci * Co;
   for (int p = threadIdx.x; p < np; p += blockDim.x) {
@@ -123,8 +130,9 @@ __global__ void col2im_k(const float* __restrict__ dcol, float* __restrict__ dX,
 
 // db[c] += sum_r dY[r, c];  grid = (row slabs, column tiles of blockDim.x)
 __global__ void colsum_k(const float* __restrict__ dY, int ldy, float* __restrict__ db, long long rows, int C) {
-  long long r0 = (long long)blockIdx.x * XTDY_SLAB;
-  long long r1 = r0 + XTDY_SLAB; if (r1 > rows) r1 = rows;
+  const long long slab = (rows + gridDim.x - 1) / gridDim.x;      // rows per block: the launch picks the grid (slab_grid)
+  long long r0 = (long long)blockIdx.x * slab;
+  long long r1 = r0 + slab; if (r1 > rows) r1 = rows;
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float acc = 0.f;
@@ -153,8 +161,9 @@ __global__ void bn_act_bwd_k(const float* __restrict__ dout, int ldd, const floa
                              const float* __restrict__ gamma, const float* __restrict__ beta,
                              float* din, int ldn, float* __restrict__ dgamma, float* __restrict__ dbeta,
                              long long rows, int C, int act, int order) {
-  long long r0 = (long long)blockIdx.x * BN_SLAB;
-  long long r1 = r0 + BN_SLAB; if (r1 > rows) r1 = rows;
+  const long long slab = (rows + gridDim.x - 1) / gridDim.x;
+  long long r0 = (long long)blockIdx.x * slab;
+  long long r1 = r0 + slab; if (r1 > rows) r1 = rows;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float g = gamma ? gamma[c] * BN_RS : 1.f, b = beta ? beta[c] : 0.f;
     float sg = 0.f, sb = 0.f;

@@ -89,6 +89,10 @@ struct sndvae_handle {
   // them at once so that the forward functions can run on a contiguous piece of the batch (pipelined host step)
   struct Shift { char** p; long long bytes; };
   std::vector<Shift> shifts;
+  float* adam_alpha;                   // device [1]: this iteration's Adam step size (see adam.cuh)
+  // small-problem path: the device-resident train step (memsets, ~300 kernels, Adam, loss read-back) captured once and replayed as
+  // a CUDA graph while the caller's buffers stay the same (SNDVAE_GRAPH=0 disables; default: problems of < 2^21 edge cells)
+  cudaGraphExec_t graph_exec; unsigned long long graph_key; int graph_mode; int capturing; long long graph_launches, graph_replays;
   float* gemm_ws; size_t gemm_ws_floats;   // workspace of the deterministic split-K products (tsgemm.cuh)
   int hf_ready;                        // every host-feed staging buffer is allocated
   int max_c;                           // widest node-level channel count of the config (sizes gA / gB / gC / colbuf)
@@ -385,7 +389,7 @@ static int alloc_buffers(sndvae_t* h) {
     DA(h->Yf, 2 * cells * C1); DA(h->dOf, 2 * cells * C2);
     h->Yhi = h->Ylo = h->dOhi = h->dOlo = nullptr;
   }
-  DA(h->loss, 8); DA(h->errflag, 1);
+  DA(h->loss, 8); DA(h->errflag, 1); DA(h->adam_alpha, 4);
   h->gemm_ws_floats = (size_t)16 << 20; DA(h->gemm_ws, h->gemm_ws_floats);      // 64 MB
   if (c.loss_variant == SNDVAE_LOSS_DIP) {
     const int Ls[3] = {c.s_latent_size, c.g_latent_size, c.sg_latent_size};
@@ -423,7 +427,7 @@ static int lin_fwd(sndvae_t* h, const float* X, const long* mb, float* Y, long l
 // dW += X^T dY; db += colsum(dY); dX = dY W^T (optional)
 static int lin_bwd(sndvae_t* h, const float* X, const long* mb, const float* dY, float* dX, long long rows, int i, int o) {
   CKB(gemm_rm(h, true, false, i, o, (int)rows, 1.f, X, i, dY, o, 1.f, h->G + mb[0], o));
-  LAUNCH(colsum_k, dim3(cdiv(rows, XTDY_SLAB), cdiv(o, 128)), 128, 0, dY, o, h->G + mb[1], rows, o);
+  LAUNCH(colsum_k, dim3(slab_grid(rows, XTDY_SLAB), cdiv(o, 128)), 128, 0, dY, o, h->G + mb[1], rows, o);
   if (dX) CKB(gemm_rm(h, false, true, (int)rows, i, o, 1.f, dY, o, h->P + mb[0], o, 0.f, dX, i));
   return 0;
 }
@@ -432,7 +436,7 @@ static void bn_fwd(sndvae_t* h, const float* in, int ldi, long g, long b, float*
 }
 static void bn_bwd(sndvae_t* h, const float* dout, int ldd, const float* in, int ldi, long g, long b, float* din, int ldn,
                    long long rows, int C, int act, int order) {
-  LAUNCH(bn_act_bwd_k, cdiv(rows, BN_SLAB), 64, 0, dout, ldd, in, ldi, g >= 0 ? h->P + g : nullptr, b >= 0 ? h->P + b : nullptr,
+  LAUNCH(bn_act_bwd_k, slab_grid(rows, BN_SLAB), 64, 0, dout, ldd, in, ldi, g >= 0 ? h->P + g : nullptr, b >= 0 ? h->P + b : nullptr,
          din, ldn, g >= 0 ? h->G + g : nullptr, b >= 0 ? h->G + b : nullptr, rows, C, act, order);
 }
 // conv1d k5 SAME over the node axis (model.py:122,191,216) as im2col + one tall library GEMM
@@ -446,7 +450,7 @@ static int conv_fwd(sndvae_t* h, const float* in, long k, long b, float* out, lo
 static int conv_bwd(sndvae_t* h, const float* in, long k, long b, const float* dout, float* din, long long rows, int Ci, int Co) {
   LEW(im2col_k, rows * KS * Ci, in, h->colbuf, rows, h->N, Ci, KS);
   CKB(gemm_rm(h, true, false, KS * Ci, Co, (int)rows, 1.f, h->colbuf, KS * Ci, dout, Co, 1.f, h->G + k, Co));
-  LAUNCH(colsum_k, dim3(cdiv(rows, XTDY_SLAB), cdiv(Co, 128)), 128, 0, dout, Co, h->G + b, rows, Co);
+  LAUNCH(colsum_k, dim3(slab_grid(rows, XTDY_SLAB), cdiv(Co, 128)), 128, 0, dout, Co, h->G + b, rows, Co);
   if (din) {      // dcol = dout . K^T (re-using the im2col buffer), then the transposed gather
     CKB(gemm_rm(h, false, true, (int)rows, KS * Ci, Co, 1.f, dout, Co, h->P + k, Co, 0.f, h->colbuf, KS * Ci));
     LEW(col2im_k, rows * Ci, h->colbuf, din, rows, h->N, Ci, KS);
@@ -514,9 +518,11 @@ static int sgc_layer_bwd(sndvae_t* h, int l, const float* x, const float* dy, fl
   return 0;
 }
 static void ev_begin(sndvae_t* h, double flops) {
+  if (h->capturing) return;
   if (h->ev_used < h->ev.size()) { h->ev[h->ev_used].flops = flops; cudaEventRecord(h->ev[h->ev_used].a, h->stream); }
 }
 static void ev_end(sndvae_t* h) {
+  if (h->capturing) return;
   if (h->ev_used < h->ev.size()) { cudaEventRecord(h->ev[h->ev_used].b, h->stream); h->ev_used++; }
 }
 
@@ -862,7 +868,7 @@ static int dip_forward(sndvae_t* h) {
   for (int i = 0; i < 3; ++i) {
     const int L = Ls[i];
     CK(cudaMemsetAsync(h->dipv, 0, sizeof(float) * L, h->stream));
-    LAUNCH(colsum_k, dim3(cdiv(rows[i], XTDY_SLAB), cdiv(L, 128)), 128, 0, mus[i], L, h->dipv, rows[i], L);
+    LAUNCH(colsum_k, dim3(slab_grid(rows[i], XTDY_SLAB), cdiv(L, 128)), 128, 0, mus[i], L, h->dipv, rows[i], L);
     CKB(gemm_rm(h, true, false, L, L, (int)rows[i], 1.f, mus[i], L, mus[i], L, 0.f, h->dipS, L));
     if (world > 1) {
       CKN(g_nccl.AllReduce(h->dipS, h->dipS, (size_t)L * L, NCCL_FLOAT, NCCL_SUM, h->comm, h->stream));
@@ -943,8 +949,8 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   LEW(add_inplace_k, Rn * Chv, h->dv, h->gA, Rn * Chv);
   // ---- node-feature decoder ----
   const int* nc = c.n_d_channel;
-  LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, h->q3, nc[1], h->dxpre, F, h->G + p.d_n_lin2[0], Rn, N, nc[1], F, 1);
-  LAUNCH(colsum_k, dim3(cdiv(Rn, XTDY_SLAB), cdiv(F, 128)), 128, 0, h->dxpre, F, h->G + p.d_n_lin2[1], Rn, F);
+  LAUNCH(xtdy_k, slab_grid(Rn, XTDY_SLAB), 64, 0, h->q3, nc[1], h->dxpre, F, h->G + p.d_n_lin2[0], Rn, N, nc[1], F, 1);
+  LAUNCH(colsum_k, dim3(slab_grid(Rn, XTDY_SLAB), cdiv(F, 128)), 128, 0, h->dxpre, F, h->G + p.d_n_lin2[1], Rn, F);
   LEW(rowlin_bwd_in_k, Rn * nc[1], h->dxpre, F, h->P + p.d_n_lin2[0], h->gA, nc[1], Rn, nc[1], F, 0);      // dq3
   if (h->dis) bn_bwd(h, h->gA, nc[1], h->q2, nc[1], p.decnode_g, p.decnode_b, h->gA, nc[1], Rn, nc[1], ACT_NONE, 0);  // dq2
   bn_bwd(h, h->gA, nc[1], h->q2p, nc[1], p.n_bng[1], p.n_bnb[1], h->gA, nc[1], Rn, nc[1], dact, 0);                   // dq2p
@@ -954,8 +960,8 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
   LEW(add_inplace_k, Rn * Chv, h->dv, h->gA, Rn * Chv);
   // ---- spatial decoder ----
   const int* sc = c.s_d_channel;
-  LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, h->s3, sc[2], h->dppre, D, h->G + p.d_s_lin2[0], Rn, N, sc[2], D, 1);
-  LAUNCH(colsum_k, dim3(cdiv(Rn, XTDY_SLAB), cdiv(D, 128)), 128, 0, h->dppre, D, h->G + p.d_s_lin2[1], Rn, D);
+  LAUNCH(xtdy_k, slab_grid(Rn, XTDY_SLAB), 64, 0, h->s3, sc[2], h->dppre, D, h->G + p.d_s_lin2[0], Rn, N, sc[2], D, 1);
+  LAUNCH(colsum_k, dim3(slab_grid(Rn, XTDY_SLAB), cdiv(D, 128)), 128, 0, h->dppre, D, h->G + p.d_s_lin2[1], Rn, D);
   LEW(rowlin_bwd_in_k, Rn * sc[2], h->dppre, D, h->P + p.d_s_lin2[0], h->gA, sc[2], Rn, sc[2], D, 0);      // ds3
   bn_bwd(h, h->gA, sc[2], h->s3p, sc[2], p.s_bng[2], p.s_bnb[2], h->gA, sc[2], Rn, sc[2], dact, 0);                   // ds3p
   if ((r = conv_bwd(h, h->s2, p.s_k[2], p.s_b[2], h->gA, h->gB, Rn, sc[1], sc[2]))) return r;                                            // ds2
@@ -997,12 +1003,12 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     bn_bwd(h, h->gA, g1c + F, h->c1, g1c, p.gg_bng[1], p.gg_bnb[1], h->gB, g1c, Rn, g1c, ACT_LRELU, 1);             // dc1
     CK(cudaMemsetAsync(h->gC, 0, sizeof(float) * Rn * g1c, h->stream));
     LAUNCH(graph_prop_bwd_k, cdiv(Rn * 32, 256), 256, 0, in->adj_truth, h->gB, h->gC, Rn, N, g1c);                  // dt1
-    LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 256, 0, h->g1, g0 + F, h->gC, g1c, h->G + p.gg_w[1], Rn, N, g0 + F, g1c, 1);
+    LAUNCH(xtdy_k, slab_grid(Rn, XTDY_SLAB), 256, 0, h->g1, g0 + F, h->gC, g1c, h->G + p.gg_w[1], Rn, N, g0 + F, g1c, 1);
     LEW(rowlin_bwd_in_k, Rn * (g0 + F), h->gC, g1c, h->P + p.gg_w[1], h->gA, g0 + F, Rn, g0 + F, g1c, 0);  // dg1
     bn_bwd(h, h->gA, g0 + F, h->c0, g0, p.gg_bng[0], p.gg_bnb[0], h->gB, g0, Rn, g0, ACT_LRELU, 1);                 // dc0
     CK(cudaMemsetAsync(h->gC, 0, sizeof(float) * Rn * g0, h->stream));
     LAUNCH(graph_prop_bwd_k, cdiv(Rn * 32, 256), 256, 0, in->adj_truth, h->gB, h->gC, Rn, N, g0);                   // dt0
-    LAUNCH(xtdy_k, cdiv(Rn, XTDY_SLAB), 64, 0, in->feature_truth, F, h->gC, g0, h->G + p.gg_w[0], Rn, N, F, g0, 1);
+    LAUNCH(xtdy_k, slab_grid(Rn, XTDY_SLAB), 64, 0, in->feature_truth, F, h->gC, g0, h->G + p.gg_w[0], Rn, N, F, g0, 1);
     // spatial head
     L = c.s_latent_size; Hh = c.s_hidden_size;
     const int* ec = c.s_channel;
@@ -1095,11 +1101,20 @@ static int copy_latents(sndvae_t* h, sndvae_outputs* out) {
 }
 
 // losses_host <- optimizer.overall_loss (optimizer.py:200-203)
-static int fetch_losses(sndvae_t* h, float* losses_host, int ranks_summed = 1) {
+// the read-back of the loss sums and of the error flag: enqueue (capturable) / wait and evaluate
+static int fetch_losses_enqueue(sndvae_t* h) {
   CK(cudaMemcpyAsync(h->pinned_loss, h->loss, sizeof(float) * 8, cudaMemcpyDeviceToHost, h->stream));
-  int ef = 0;
-  CK(cudaMemcpyAsync(&ef, h->errflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(h->pinned_loss + 8, h->errflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return 0;
+}
+static int fetch_losses_finish(sndvae_t* h, float* losses_host, int ranks_summed);
+static int fetch_losses(sndvae_t* h, float* losses_host, int ranks_summed = 1) {
+  int r = fetch_losses_enqueue(h); if (r) return r;
+  return fetch_losses_finish(h, losses_host, ranks_summed);
+}
+static int fetch_losses_finish(sndvae_t* h, float* losses_host, int ranks_summed) {
   CK(cudaStreamSynchronize(h->stream));
+  const int ef = *reinterpret_cast<const int*>(h->pinned_loss + 8);
   if (ef) { cudaMemsetAsync(h->errflag, 0, sizeof(int), h->stream);
             return fail(h, SNDVAE_E_DENSE, "a sampled adjacency has more than edge_capacity=%d non-zeros; the joint encoder expects spanning-forest samples (input_data.py:18-38)", h->cfg.edge_capacity); }
   if (!losses_host) return 0;
@@ -1176,7 +1191,7 @@ struct HostFeeds { const sndvae_inputs* in; const sndvae_noise* nz; int64_t* gen
 // The step.  Every graph's forward is independent of the rest of the batch (frozen-affine BN, SURVEY finding 3), so the
 // encoder + decoder + N^2 backward run piece by piece over contiguous graph ranges; with host feeds the H2D copy of piece k+1
 // and the D2H copy of piece k-1's generated_adj overlap piece k's kernels.  The node-level backward runs once at the end.
-enum { RUN_ACCUMULATE = 1, RUN_ALLREDUCE = 2 };
+enum { RUN_ACCUMULATE = 1, RUN_ALLREDUCE = 2, RUN_NOFETCH = 4 };
 static int run_body(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host,
                     bool backward, long long global_batch, const HostFeeds* hf, int flags);
 // a step that fails after work was enqueued leaves the gradient arena / loss sums half-written: drain the streams (the caller may
@@ -1289,6 +1304,7 @@ static int run_body(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz
   const bool reduce = backward && (flags & RUN_ALLREDUCE) && h->comm && h->world > 1;
   if (reduce && (r = allreduce_arena(h, true))) return r;
   mark(h, "end");
+  if (flags & RUN_NOFETCH) return fetch_losses_enqueue(h);      // graph capture: the caller waits and evaluates after the replay
   r = fetch_losses(h, losses_host, reduce ? h->world : 1);
   report_stages(h);
   return r;
@@ -1323,6 +1339,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->pinned_loss = nullptr; h->ev_used = 0;
+  h->graph_exec = nullptr; h->graph_key = 0; h->capturing = 0; h->graph_launches = 0; h->graph_replays = 0; h->graph_mode = 0;
   h->hf_ready = 0; h->hc_ready = 0; h->hc_features = nullptr; h->poisoned = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr; h->zz_planes = nullptr; h->zz_cap = 0;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
@@ -1378,6 +1395,8 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   { long long per_sample = (long long)h->N * 1200 * 4;     // SGC scratch: ~820 + ~210 floats per node for the two layers
     long long sc = (4LL << 30) / per_sample; if (sc < 1) sc = 1; if (sc > h->BS) sc = h->BS; h->SC = (int)sc; }
   if ((long long)2 * h->Bc * h->N * h->N * h->C1 > 2000000000LL) return fail(h, SNDVAE_E_ARG, "chunk too large for 32-bit GEMM dims");
+  { const char* g = getenv("SNDVAE_GRAPH");
+    h->graph_mode = g ? atoi(g) != 0 : ((long long)h->B * h->N * h->N < (1LL << 21)); }
   build_table(h);      // host-only: the table is valid even when no device is present (checked by the CPU tests)
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1385,7 +1404,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   cudaDeviceProp prop; int dev = 0; cudaGetDevice(&dev); cudaGetDeviceProperties(&prop, dev);
   if (prop.major < 10) return fail(h, SNDVAE_E_CUDA, "device sm_%d%d is not sm_100: this library is built for B200 only", prop.major, prop.minor);
   int r = alloc_buffers(h); if (r) return r;
-  if (cudaMallocHost((void**)&h->pinned_loss, 64) != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMallocHost failed");
+  if (cudaMallocHost((void**)&h->pinned_loss, 128) != cudaSuccess) return fail(h, SNDVAE_E_CUDA, "cudaMallocHost failed");
   h->b1p = c.adam_beta1; h->b2p = c.adam_beta2;
   h->ev.resize(4096);
   for (auto& e : h->ev) { cudaEventCreate(&e.a); cudaEventCreate(&e.b); e.flops = 0; }
@@ -1406,6 +1425,7 @@ int sndvae_destroy(sndvae_t* h) {
   if (!h) return 0;
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
   if (h->spec) { spec_destroy(h->sp); ytc_destroy(h->ytc); }
   for (void* p : h->allocs) cudaFree(p);
@@ -1472,18 +1492,30 @@ int sndvae_grads(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, s
   if (!h) return SNDVAE_E_ARG;
   return run(h, in, nz, out, losses_host, true, gb);
 }
+// this iteration's step size -> device scalar (outside any graph: it changes every step), then the running beta powers advance
+static int adam_set_alpha(sndvae_t* h) {
+  const sndvae_config& c = h->cfg;
+  // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) with fp32 running powers (TF ApplyAdam)
+  h->pinned_loss[12] = c.learning_rate * sqrtf(1.f - h->b2p) / (1.f - h->b1p);
+  CK(cudaMemcpyAsync(h->adam_alpha, h->pinned_loss + 12, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  h->b1p *= c.adam_beta1; h->b2p *= c.adam_beta2;
+  return 0;
+}
+static int adam_launch(sndvae_t* h) {
+  const sndvae_config& c = h->cfg;
+  long long n4 = h->nparam / 4;
+  unsigned grid = cdiv(n4, 256); if (grid > 148 * 8) grid = 148 * 8;
+  LAUNCH(tf_adam_k, grid, 256, 0, (float4*)h->P, (const float4*)h->G, (float4*)h->M, (float4*)h->V, n4, h->adam_alpha, 1.f - c.adam_beta1,
+         1.f - c.adam_beta2, c.adam_eps);
+  CK(cudaGetLastError());
+  return 0;
+}
 int sndvae_apply_adam(sndvae_t* h) {
   if (!h) return SNDVAE_E_ARG;
   const sndvae_config& c = h->cfg;
   // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) with fp32 running powers (TF ApplyAdam)
-  float alpha = c.learning_rate * sqrtf(1.f - h->b2p) / (1.f - h->b1p);
-  long long n4 = h->nparam / 4;
-  unsigned grid = cdiv(n4, 256); if (grid > 148 * 8) grid = 148 * 8;
-  LAUNCH(tf_adam_k, grid, 256, 0, (float4*)h->P, (const float4*)h->G, (float4*)h->M, (float4*)h->V, n4, alpha, 1.f - c.adam_beta1,
-         1.f - c.adam_beta2, c.adam_eps);
-  h->b1p *= c.adam_beta1; h->b2p *= c.adam_beta2;
-  CK(cudaGetLastError());
-  return 0;
+  int r = adam_set_alpha(h); if (r) return r;
+  return adam_launch(h);
 }
 int sndvae_zero_grads(sndvae_t* h) {
   if (!h) return SNDVAE_E_ARG;
@@ -1500,8 +1532,64 @@ int sndvae_allreduce_grads(sndvae_t* h) {
   if (!h->comm) return fail(h, SNDVAE_E_STATE, "sndvae_allreduce_grads: no communicator (call sndvae_comm_init first)");
   return allreduce_arena(h, false);
 }
+static unsigned long long graph_key_of(const sndvae_inputs* in, const sndvae_noise* nz, const sndvae_outputs* out) {
+  unsigned long long k = 1469598103934665603ull;
+  auto mix = [&k](const void* p) { k = (k ^ (unsigned long long)(uintptr_t)p) * 1099511628211ull; };
+  const void* const* a = reinterpret_cast<const void* const*>(in);
+  for (size_t i = 0; i < sizeof(*in) / sizeof(void*); ++i) mix(a[i]);
+  a = reinterpret_cast<const void* const*>(nz);
+  for (size_t i = 0; i < sizeof(*nz) / sizeof(void*); ++i) mix(a[i]);
+  if (out) { a = reinterpret_cast<const void* const*>(out); for (size_t i = 0; i < sizeof(*out) / sizeof(void*); ++i) mix(a[i]); }
+  return k | 1ull;
+}
+// The train step of a small problem is bound by launch latency (N = 25, B = 32: ~310 launches of a few microseconds each), so the
+// second call with the same buffers captures the whole step on the handle's stream and later calls replay the graph.
+static int train_step_graph(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host, bool* done) {
+  *done = false;
+  int r = check_inputs(h, in, nz); if (r) return r;
+  const unsigned long long key = graph_key_of(in, nz, out);
+  if (key != h->graph_key) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph_key == 0 || h->graph_key != (key ^ 2ull)) { h->graph_key = key ^ 2ull; return 0; }   // first sight of these buffers: run plainly (warms every lazy init)
+    cudaGraph_t g = nullptr;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->graph_mode = 0; return 0; }
+    h->capturing = 1;
+    r = run_body(h, in, nz, out, nullptr, true, h->B, nullptr, RUN_NOFETCH);
+    if (!r) r = adam_launch(h);
+    h->capturing = 0;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    if (r || e != cudaSuccess || !g || cudaGraphInstantiate(&h->graph_exec, g, 0) != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError(); h->graph_exec = nullptr; h->graph_mode = 0;       // something in the step cannot be captured: stay on plain launches
+      h->B = h->cfg.batch_size; h->BS = h->B * h->S; h->Rn = h->B * h->N;
+      return 0;
+    }
+    cudaGraphDestroy(g);
+    h->graph_key = key;
+  }
+  r = adam_set_alpha(h); if (r) return r;
+  CK(cudaGraphLaunch(h->graph_exec, h->stream));
+  h->launches += h->graph_launches; h->graph_replays++;
+  *done = true;
+  r = fetch_losses_finish(h, losses_host, 1);
+  h->poisoned = r ? 1 : 0;
+  return r;
+}
 int sndvae_train_step(sndvae_t* h, const sndvae_inputs* in, const sndvae_noise* nz, sndvae_outputs* out, float* losses_host) {
   if (!h) return SNDVAE_E_ARG;
+  if (h->graph_mode && !h->comm && !h->stt.on && h->cfg.loss_variant != SNDVAE_LOSS_CAPACITY && in && nz) {
+    bool done = false;
+    const long long l0 = h->launches;
+    int r = train_step_graph(h, in, nz, out, losses_host, &done);
+    if (r || done) return r;
+    if (h->graph_exec == nullptr && h->graph_mode) {
+      // plain run that the next call's capture will mirror: remember how many kernels one step launches
+      r = run(h, in, nz, out, losses_host, true, (long long)h->world * h->B, nullptr, RUN_ALLREDUCE); if (r) return r;
+      r = sndvae_apply_adam(h);
+      h->graph_launches = h->launches - l0;
+      return r;
+    }
+  }
   // with a communicator: local sums scaled by 1 / (world B), one all-reduce of the arena (+ the loss sums), then Adam
   int r = run(h, in, nz, out, losses_host, true, (long long)h->world * h->B, nullptr, RUN_ALLREDUCE); if (r) return r;
   return sndvae_apply_adam(h);
@@ -1636,6 +1724,7 @@ int sndvae_synth_inputs(sndvae_t* h, uint64_t seed, const sndvae_inputs* io) {
 }
 
 int64_t sndvae_launch_count(const sndvae_t* h) { return h ? h->launches : 0; }
+int64_t sndvae_graph_replays(const sndvae_t* h) { return h ? h->graph_replays : 0; }
 int sndvae_set_global_iter(sndvae_t* h, int64_t it) { if (!h) return SNDVAE_E_ARG; h->global_iter = it; return 0; }
 
 int sndvae_gemm_timing(sndvae_t* h, int reset, double* total_ms, int64_t* launches, double* flops) {

@@ -404,6 +404,9 @@ class Engine:
         out = {names.raw[32 * i:32 * (i + 1)].split(b"\0", 1)[0].decode(): ms[i] for i in range(n)}
         return out, int(steps.value)
 
+    def graph_replays(self) -> int:
+        return int(self.lib.sndvae_graph_replays(self._h))
+
     def launch_count(self) -> int:
         return int(self.lib.sndvae_launch_count(self._h))
 

@@ -342,3 +342,39 @@ def test_synthetic1_flag_block_trains(built):
             costs.append(sess.run([o.opt_op, o.cost], feed_dict=fd)[1])
     assert np.isfinite(costs).all() and costs[-1] < costs[0]
     F.reset()
+
+
+def test_cuda_graph_step_equals_plain_step(built):
+    """Small problems replay the device-resident train step as one CUDA graph (captured on the second call with the same
+    buffers).  Five steps with the graph against five plain steps: same losses, same adjacency, same parameters; new feed buffers
+    half-way force a re-capture."""
+    N, B, S = 25, 4, 3
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", dtype=torch.float32)
+    out = {}
+    for mode in ("1", "0"):
+        os.environ["SNDVAE_GRAPH"] = mode
+        try:
+            eng = built.Engine(built.make_config(N, B, "disentangled", sampling_num=S))
+        finally:
+            os.environ.pop("SNDVAE_GRAPH", None)
+        eng.set_params(P)
+        feeds = {k: v.to("cuda") for k, v in inp.items()}; nz = {k: v.to("cuda") for k, v in noise.items()}
+        ipk, npk, keep = eng._pack(feeds, nz)
+        o, res = eng._outs(("generated_adj",))
+        losses = np.zeros(8, np.float32)
+        hist, l0 = [], eng.launch_count()
+        for step in range(5):
+            if step == 3:      # other buffers with the same contents: the graph must be rebuilt, not replayed on stale pointers
+                feeds2 = {k: v.clone() for k, v in feeds.items()}
+                ipk, npk, keep2 = eng._pack(feeds2, nz)
+            eng.train_step_packed(ipk, npk, o, losses)
+            hist.append(losses[:7].copy())
+        assert eng.launch_count() - l0 > 5 * 100
+        # steps 0 (plain) 1 (capture + replay) 2 (replay) 3 (new buffers: plain) 4 (capture + replay)
+        assert eng.graph_replays() == (3 if mode == "1" else 0)
+        out[mode] = (np.array(hist), res["generated_adj"].cpu().numpy().copy(), eng.get_params())
+        eng.close()
+    np.testing.assert_allclose(out["1"][0], out["0"][0], rtol=2e-5, atol=1e-8)
+    assert np.array_equal(out["1"][1], out["0"][1])
+    for k in out["0"][2]:
+        np.testing.assert_allclose(out["1"][2][k].numpy(), out["0"][2][k].numpy(), rtol=0, atol=3e-6, err_msg=k)
