@@ -74,6 +74,12 @@ typedef struct sndvae_config {
   int32_t loss_variant;
   float   gamma, C_max, C_stop_iter, C_step;  /* main.py:95-98 */
   float   dip_lambda_od, dip_lambda_d;        /* 10, 100 (optimizer.py:183) */
+  /* Joint-encoder layer type.  2 (and 0): SpatialGraphConvolution (layers.py:143-198; FLAGS.dataset synthetic1/2/3,
+   * model.py:137-138) with sg_conv_hidden[l][0..2] on per-sample edge lists (spanning-forest samples).
+   * 3: SpatialGraphConvolution_3D (layers.py:200-277; FLAGS.dataset protein / mnist, model.py:139-140, main.py:225,241) with the
+   * four hidden sizes sg_conv_hidden3[l][0..3] on dense adjacencies (any real A). */
+  int32_t sg_hops;
+  int32_t sg_conv_hidden3[2][4];
 } sndvae_config;
 
 #define SNDVAE_LOSS_ELBO      0

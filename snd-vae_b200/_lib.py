@@ -28,6 +28,7 @@ class Config(C.Structure):
         ("learning_rate", F32), ("beta", F32), ("adam_beta1", F32), ("adam_beta2", F32), ("adam_eps", F32),
         ("loss_variant", I32), ("gamma", F32), ("C_max", F32), ("C_stop_iter", F32), ("C_step", F32),
         ("dip_lambda_od", F32), ("dip_lambda_d", F32),
+        ("sg_hops", I32), ("sg_conv_hidden3", (I32 * 4) * 2),
     ]
 
 

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "layers.cuh"
 #include "sgc.cuh"
+#include "sgc3.cuh"
 #include "edge.cuh"
 #include "adam.cuh"
 #include "e2e_tc.cuh"
@@ -26,6 +27,7 @@
 struct PT {   // parameter offsets (floats) into the flat arenas; -1 = absent
   long gg_w[2], gg_bng[2], gg_bnb[2], encg_g, encg_b, g_lin[3][2];
   long gs_k[3], gs_b[3], gs_bng[3], gs_bnb[3], encs_g, encs_b, s_lin[3][2];
+  long sg3_M[2][4], sg3_b[2][4];     // 3-hop layers: Matrix0..3 / bias0..3
   long sg_M1[2], sg_b1[2], sg_M2[2], sg_b2[2], sg_M3[2], sg_b3[2], sg_bng[2], sg_bnb[2], encsg_g, encsg_b, sg_lin[3][2];
   long d_sg_lin1[2], d_s_lin1[2], d_g_lin1[2];
   long n_k[2], n_b[2], n_bng[2], n_bnb[2], decnode_g, decnode_b, d_n_lin2[2];
@@ -57,6 +59,7 @@ struct sndvae_handle {
   float *fsg, *hsg, *mu_sg, *ls_sg, *dfsg;
   float *x1, *x2, *dxa, *dxb;          // SGC chunk activations / grads
   SgcEdges E; SgcScratch S0, S1;
+  int hops3; float *y3[2], *ws3; long long ws3_stride, SC3;   // SpatialGraphConvolution_3D: pre-BN layer outputs, per-sample workspace
   int sgc_keep;                        // forward activations of the joint encoder kept for every sample (no recompute in backward)
   float *z_s, *z_g, *z_sg, *zbar, *dz_s, *dz_g, *dzbar;
   float *dmu, *dls, *dh;               // head backward temporaries (sized for BS rows)
@@ -209,7 +212,17 @@ static void build_table(sndvae_t* h) {
     add_lin(h, "encoder/g_s3_lin", c.s_hidden_size, c.s_latent_size, p.s_lin[2]);
   }
   int ci = F;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 2 && h->hops3; ++i) {          // layers.py:210-225
+    const int* hs = c.sg_conv_hidden3[i];
+    const int rows[4] = {4 * ci + 5, 3 * ci + 3 + hs[0], 2 * ci + 1 + hs[1], ci + hs[2]};
+    for (int m = 0; m < 4; ++m) {
+      snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/Matrix%d", i, m); p.sg3_M[i][m] = add_param(h, nm, 2, rows[m], hs[m]);
+      snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/bias%d", i, m);   p.sg3_b[i][m] = add_param(h, nm, 1, hs[m]);
+    }
+    snprintf(nm, sizeof nm, "encoder/g_bn_sg%d", i); add_bn(h, nm, hs[3], &p.sg_bng[i], &p.sg_bnb[i]);
+    ci = hs[3];
+  }
+  for (int i = 0; i < 2 && !h->hops3; ++i) {
     const int* hs = c.sg_conv_hidden[i];
     snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/Matrix1", i); p.sg_M1[i] = add_param(h, nm, 2, 3 * ci + 3, hs[0]);
     snprintf(nm, sizeof nm, "encoder/g_sg%d_conv/bias1", i);   p.sg_b1[i] = add_param(h, nm, 1, hs[0]);
@@ -334,6 +347,21 @@ static int alloc_buffers(sndvae_t* h) {
   DG(E.ea, (long long)S * E.cap); DG(E.epr, (long long)S * E.cap); DG(E.eG, (long long)S * E.cap); DG(E.deg, S * N); DG(E.ssum, S * N); DG(E.nedges, S);
   const long long SC = h->SC;
   int r;
+  if (h->hops3) {
+    // SpatialGraphConvolution_3D: layer outputs before BN for every sample (per-graph views), one workspace slice per sample of a chunk
+    const int h30 = c.sg_conv_hidden3[0][3], h31 = c.sg_conv_hidden3[1][3];
+    Sgc3Dims d0 = {F, c.sg_conv_hidden3[0][0], c.sg_conv_hidden3[0][1], c.sg_conv_hidden3[0][2], h30};
+    Sgc3Dims d1 = {h30, c.sg_conv_hidden3[1][0], c.sg_conv_hidden3[1][1], c.sg_conv_hidden3[1][2], h31};
+    const long long w0 = sgc3_ws_floats(N, d0), w1 = sgc3_ws_floats(N, d1);
+    h->ws3_stride = (w0 > w1 ? w0 : w1);
+    long long sc3 = (2LL << 30) / (h->ws3_stride * 4); if (sc3 < 1) sc3 = 1; if (sc3 > h->BS) sc3 = h->BS; if (sc3 > 148 * 8) sc3 = 148 * 8;
+    h->SC3 = sc3;
+    DA(h->ws3, sc3 * h->ws3_stride);
+    DG(h->y3[0], (long long)S * N * h30); DG(h->y3[1], (long long)S * N * h31);
+    DG(h->x1, (long long)S * N * h30); DG(h->x2, (long long)S * N * h31);
+    DA(h->dxa, h->BS * N * (h31 > h30 ? h31 : h30)); DA(h->dxb, h->BS * N * (h31 > h30 ? h31 : h30));
+    h->sgc_keep = 1;
+  } else
   {
     // keep the joint encoder's forward activations for every sample when they fit (626 floats per node at the synthetic2 sizes:
     // 26 GB at N=256, B=4096, S=10) -- the backward pass then re-uses them instead of recomputing each chunk's forward
@@ -343,11 +371,13 @@ static int alloc_buffers(sndvae_t* h) {
     const long long bytes = h->BS * N * fl * 4;
     h->sgc_keep = (bytes <= (32LL << 30)) && !(getenv("SNDVAE_SGC_KEEP") && atoi(getenv("SNDVAE_SGC_KEEP")) == 0);
   }
-  const long long SF = h->sgc_keep ? h->BS : SC; const int pgs = h->sgc_keep ? S : 0;
-  if ((r = alloc_scratch(h, h->S0, F, c.sg_conv_hidden[0], SF, SC, N, pgs))) return r;
-  if ((r = alloc_scratch(h, h->S1, c.sg_conv_hidden[0][2], c.sg_conv_hidden[1], SF, SC, N, pgs))) return r;
-  DA(h->x1, SF * N * c.sg_conv_hidden[0][2]); DA(h->x2, SF * N * hl); DA(h->dxa, SC * N * hl); DA(h->dxb, SC * N * hl);
-  if (h->sgc_keep) { reg_shift(h, &h->x1, (long long)S * N * c.sg_conv_hidden[0][2]); reg_shift(h, &h->x2, (long long)S * N * hl); }
+  if (!h->hops3) {
+    const long long SF = h->sgc_keep ? h->BS : SC; const int pgs = h->sgc_keep ? S : 0;
+    if ((r = alloc_scratch(h, h->S0, F, c.sg_conv_hidden[0], SF, SC, N, pgs))) return r;
+    if ((r = alloc_scratch(h, h->S1, c.sg_conv_hidden[0][2], c.sg_conv_hidden[1], SF, SC, N, pgs))) return r;
+    DA(h->x1, SF * N * c.sg_conv_hidden[0][2]); DA(h->x2, SF * N * hl); DA(h->dxa, SC * N * hl); DA(h->dxb, SC * N * hl);
+    if (h->sgc_keep) { reg_shift(h, &h->x1, (long long)S * N * c.sg_conv_hidden[0][2]); reg_shift(h, &h->x2, (long long)S * N * hl); }
+  }
   DG(h->z_sg, S * c.sg_latent_size); DG(h->zbar, c.sg_latent_size); DG(h->dzbar, c.sg_latent_size);
   long long maxL = c.sg_latent_size > c.sg_hidden_size ? c.sg_latent_size : c.sg_hidden_size;
   if (h->dis) { int m2 = c.s_latent_size > c.g_latent_size ? c.s_latent_size : c.g_latent_size; if (m2 > maxL) maxL = m2;
@@ -545,6 +575,62 @@ static int sgc_chunk_fwd(sndvae_t* h, const sndvae_inputs* in, long long s0, lon
   return 0;
 }
 
+// ---- SpatialGraphConvolution_3D (sgc3.cuh) ---------------------------------------------------------------------------------
+static Sgc3Dims sgc3_dims(sndvae_t* h, int l) {
+  const sndvae_config& c = h->cfg; const int* hs = c.sg_conv_hidden3[l];
+  Sgc3Dims d = {l == 0 ? c.num_feature : c.sg_conv_hidden3[0][3], hs[0], hs[1], hs[2], hs[3]};
+  return d;
+}
+static Sgc3Params sgc3_params(sndvae_t* h, int l, float* arena) {
+  const PT& p = h->pt;
+  Sgc3Params w = {arena + p.sg3_M[l][0], arena + p.sg3_b[l][0], arena + p.sg3_M[l][1], arena + p.sg3_b[l][1],
+                  arena + p.sg3_M[l][2], arena + p.sg3_b[l][2], arena + p.sg3_M[l][3], arena + p.sg3_b[l][3]};
+  return w;
+}
+// layer l forward for every sample of the current view: x [BS, N, C] -> y3[l] (before BN), in chunks of SC3 samples
+static int sgc3_layer_fwd(sndvae_t* h, int l, const float* x, const sndvae_inputs* in) {
+  const Sgc3Dims d = sgc3_dims(h, l); const int N = h->N;
+  for (long long s0 = 0; s0 < h->BS; s0 += h->SC3) {
+    const long long ns = h->BS - s0 < h->SC3 ? h->BS - s0 : h->SC3;
+    LAUNCH(sgc3_k<false>, (unsigned)ns, 256, 0, x + s0 * N * d.C, in->adj + s0 * N * N, in->rel + s0 * N * N, sgc3_params(h, l, h->P),
+           sgc3_params(h, l, h->G), d, N, h->y3[l] + s0 * N * d.h3, (const float*)nullptr, (float*)nullptr, h->ws3, h->ws3_stride);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+static int sgc3_layer_bwd(sndvae_t* h, int l, const float* x, const float* dy, float* dx, const sndvae_inputs* in) {
+  const Sgc3Dims d = sgc3_dims(h, l); const int N = h->N;
+  for (long long s0 = 0; s0 < h->BS; s0 += h->SC3) {
+    const long long ns = h->BS - s0 < h->SC3 ? h->BS - s0 : h->SC3;
+    LAUNCH(sgc3_k<true>, (unsigned)ns, 256, 0, x + s0 * N * d.C, in->adj + s0 * N * N, in->rel + s0 * N * N, sgc3_params(h, l, h->P),
+           sgc3_params(h, l, h->G), d, N, (float*)nullptr, dy + s0 * N * d.h3, dx ? dx + s0 * N * d.C : nullptr, h->ws3, h->ws3_stride);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+static int sgc3_encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
+  const PT& p = h->pt; const int N = h->N; const long long BS = h->BS;
+  const int h30 = h->cfg.sg_conv_hidden3[0][3], h31 = h->cfg.sg_conv_hidden3[1][3];
+  int r;
+  if ((r = sgc3_layer_fwd(h, 0, in->features, in))) return r;
+  bn_fwd(h, h->y3[0], h30, p.sg_bng[0], p.sg_bnb[0], h->x1, h30, BS * N, h30, ACT_LRELU, 0);
+  if ((r = sgc3_layer_fwd(h, 1, h->x1, in))) return r;
+  bn_fwd(h, h->y3[1], h31, p.sg_bng[1], p.sg_bnb[1], h->x2, h31, BS * N, h31, ACT_LRELU, 0);
+  bn_fwd(h, h->x2, h31, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->fsg, h31, BS * N, h31, ACT_NONE, 0);
+  return 0;
+}
+// dfsg -> parameter gradients of both layers (the feeds need no gradient)
+static int sgc3_encoder_bwd(sndvae_t* h, const sndvae_inputs* in) {
+  const PT& p = h->pt; const int N = h->N; const long long BS = h->BS;
+  const int h30 = h->cfg.sg_conv_hidden3[0][3], h31 = h->cfg.sg_conv_hidden3[1][3];
+  int r;
+  bn_bwd(h, h->dfsg, h31, h->x2, h31, h->dis ? p.encsg_g : -1, h->dis ? p.encsg_b : -1, h->dxa, h31, BS * N, h31, ACT_NONE, 0);
+  bn_bwd(h, h->dxa, h31, h->y3[1], h31, p.sg_bng[1], p.sg_bnb[1], h->dxa, h31, BS * N, h31, ACT_LRELU, 0);      // dy1
+  if ((r = sgc3_layer_bwd(h, 1, h->x1, h->dxa, h->dxb, in))) return r;                                           // dx1
+  bn_bwd(h, h->dxb, h30, h->y3[0], h30, p.sg_bng[0], p.sg_bnb[0], h->dxb, h30, BS * N, h30, ACT_LRELU, 0);      // dy0
+  return sgc3_layer_bwd(h, 0, in->features, h->dxb, nullptr, in);
+}
+
 static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
   const sndvae_config& c = h->cfg; const PT& p = h->pt;
   const int N = h->N, F = h->F, D = h->D; const long long B = h->B, BS = h->BS, Rn = h->Rn;
@@ -577,6 +663,10 @@ static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
     if ((r = lin_fwd(h, h->hs, p.s_lin[1], h->mu_s, B, c.s_hidden_size, c.s_latent_size))) return r;
     if ((r = lin_fwd(h, h->hs, p.s_lin[2], h->ls_s, B, c.s_hidden_size, c.s_latent_size))) return r;
   }
+  if (h->hops3) {      // model.py:139-140: SpatialGraphConvolution_3D x2 on the dense sampled adjacencies
+    mark(h, "sgc_fwd");
+    int r3 = sgc3_encoder_fwd(h, in); if (r3) return r3;
+  } else {
   // joint encoder (model.py:134-151): edge lists once per step, SGC x2 in sample chunks
   mark(h, "sgc_edges");
   LAUNCH(sgc_build_edges_k, (unsigned)BS, 256, 0, in->adj, in->rel, h->E, N, h->errflag);
@@ -585,6 +675,7 @@ static int encoder_fwd(sndvae_t* h, const sndvae_inputs* in) {
   for (long long s0 = 0; s0 < BS; s0 += h->SC) {
     long long ns = BS - s0 < h->SC ? BS - s0 : h->SC;
     int r = sgc_chunk_fwd(h, in, s0, ns); if (r) return r;
+  }
   }
   mark(h, "enc_heads");
   const int h12 = c.sg_conv_hidden[1][2];
@@ -1043,6 +1134,7 @@ static int backward_rest(sndvae_t* h, const sndvae_inputs* in, const sndvae_nois
     if ((r = lin_bwd(h, h->hsg, p.sg_lin[2], h->dls, tmp, BS, Hh, L))) return r;
     LEW(add_inplace_k, BS * Hh, h->dh, tmp, BS * Hh);
     if ((r = lin_bwd(h, h->fsg, p.sg_lin[0], h->dh, h->dfsg, BS, N * h12, Hh))) return r;
+    if (h->hops3) return sgc3_encoder_bwd(h, in);
     for (int l = 0; l < 2; ++l) {
       SgcDims d = sgc_dims(h, l); SgcScratch& S = l == 0 ? h->S0 : h->S1;
       CK(cudaMemsetAsync(S.dWQ, 0, sizeof(float) * (2 * d.C + 2) * d.h0, h->stream));
@@ -1361,6 +1453,14 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
     c.use_tensor_cores = 0;
   }
   h->spec = c.use_tensor_cores == 2; memset(&h->sp, 0, sizeof h->sp); memset(&h->ytc, 0, sizeof h->ytc);
+  if (c.sg_hops != 0 && c.sg_hops != 2 && c.sg_hops != 3) return fail(h, SNDVAE_E_ARG, "sg_hops must be 2 (SpatialGraphConvolution) or 3 (SpatialGraphConvolution_3D)");
+  h->hops3 = c.sg_hops == 3; h->ws3 = nullptr; h->y3[0] = h->y3[1] = nullptr;
+  if (h->hops3) {
+    for (int l = 0; l < 2; ++l) {
+      for (int m = 0; m < 4; ++m) if (c.sg_conv_hidden3[l][m] < 1) return fail(h, SNDVAE_E_ARG, "sg_conv_hidden3[%d][%d] = %d", l, m, c.sg_conv_hidden3[l][m]);
+      c.sg_conv_hidden[l][2] = c.sg_conv_hidden3[l][3];      // the layer's output width, where the rest of the code reads it
+    }
+  }
   if (!h->dis) c.sampling_num = 1;     // model_joint.py is coherent only with one sample per graph
   if (c.sampling_num < 1) return fail(h, SNDVAE_E_ARG, "sampling_num must be >= 1");
   if (c.e_d_hidden[1] != EPI_C2) return fail(h, SNDVAE_E_ARG, "e_d_hidden[1] must be %d in this build", EPI_C2);

@@ -39,11 +39,16 @@ def make_config(num_nodes: int, batch_size: int, model_type: str = "disentangled
         cur = getattr(cfg, k)
         if hasattr(cur, "__len__"):
             if k == "sg_conv_hidden":
+                if len(v) == 2 and all(len(hs) == 4 for hs in v):
+                    # 4 sizes per layer = SpatialGraphConvolution_3D (layers.py:200-277; FLAGS.dataset protein / mnist)
+                    cfg.sg_hops = 3
+                    for i in range(2):
+                        for j in range(4):
+                            cfg.sg_conv_hidden3[i][j] = int(v[i][j])
+                    continue
                 if len(v) != 2 or any(len(hs) != 3 for hs in v):
-                    # 4 sizes per layer = SpatialGraphConvolution_3D (layers.py:200-277; FLAGS.dataset protein / mnist): the
-                    # CUDA engine does not build that branch -- refuse instead of truncating
-                    raise SndvaeError(f"sg_conv_hidden={v!r}: two layers of three hidden sizes required "
-                                      "(the 3-hop SpatialGraphConvolution_3D branch is not built)")
+                    raise SndvaeError(f"sg_conv_hidden={v!r}: two layers of three (SpatialGraphConvolution) or four "
+                                      "(SpatialGraphConvolution_3D) hidden sizes required")
                 for i in range(2):
                     for j in range(3):
                         cur[i][j] = int(v[i][j])

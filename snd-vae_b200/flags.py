@@ -49,6 +49,15 @@ class _Flags:
             self.__dict__.update(copy.deepcopy(base)); self.__dict__.update(_SYNTHETIC1)
         elif dataset == "synthetic2":
             self.__dict__.update(copy.deepcopy(base)); self.__dict__.update(_SYNTHETIC2)
+        elif dataset == "protein":         # main.py:218-236: 3-hop joint encoder (model.py:139-140), 3-D coordinates, small heads
+            self.__dict__.update(copy.deepcopy(base))
+            self.__dict__.update(spatial_dim=3, sg_conv_hidden=[[10, 10, 10, 10], [20, 20, 20, 20]], sg_hidden_size=50, sg_latent_size=50,
+                                 s_hidden_size=5, s_latent_size=5, g_hidden_size=5, g_latent_size=5, node_h_size=5,
+                                 s_channel=[10, 10, 20], s_kernel_size=[5, 5, 5], batch_size=50, decoder_batch_size=50,
+                                 sg_batch_size=50, sg_decoder_batch_size=50)
+        elif dataset == "mnist":           # main.py:237-241
+            self.__dict__.update(copy.deepcopy(base))
+            self.__dict__.update(spatial_dim=3, sg_conv_hidden=[[20, 20, 20, 20], [50, 50, 50, 50]])
         else:
             raise ValueError(f"dataset '{dataset}' is outside the hot path (SURVEY section 2, rows 11-13)")
 

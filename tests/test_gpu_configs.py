@@ -378,3 +378,85 @@ def test_cuda_graph_step_equals_plain_step(built):
     assert np.array_equal(out["1"][1], out["0"][1])
     for k in out["0"][2]:
         np.testing.assert_allclose(out["1"][2][k].numpy(), out["0"][2][k].numpy(), rtol=0, atol=3e-6, err_msg=k)
+
+
+PROTEIN = dict(spatial_dim=3, node_h_size=5, sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)), sg_hidden_size=50, sg_latent_size=50,
+               s_hidden_size=5, s_latent_size=5, g_hidden_size=5, g_latent_size=5)     # main.py:218-236
+
+
+def _protein_engine(built, N, B, S, **kw):
+    return built.Engine(built.make_config(N, B, "disentangled", sampling_num=S, spatial_dim=3, node_h_size=5,
+                                          sg_conv_hidden=PROTEIN["sg_conv_hidden"], sg_hidden_size=50, sg_latent_size=50, s_hidden_size=5,
+                                          s_latent_size=5, g_hidden_size=5, g_latent_size=5, **kw))
+
+
+def test_protein_golden_fixture(built):
+    """tests/golden/protein_n6.npz (the reference's protein flag block, main.py:218-236: SpatialGraphConvolution_3D joint encoder,
+    layers.py:200-277, D = 3, node_h_size = 5) against the CUDA path: losses, outputs, gradient sums, Adam trajectory."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "protein_n6.npz"))
+    N, B, S = int(z["N"]), int(z["B"]), int(z["S"])
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", **PROTEIN)
+    eng = _protein_engine(built, N, B, S)
+    assert [n for n, _, _ in eng.table] == [n for n, _, _ in O.param_table(cfg)]
+    eng.set_params(P)
+    res = eng.grads(inp, noise, fetch=("generated_adj_prob", "generated_spatial", "generated_node_feat", "z_sg"))
+    np.testing.assert_allclose(res["overall_loss"], z["overall_loss"], rtol=1e-4)
+    for k in ("generated_adj_prob", "generated_spatial", "generated_node_feat", "z_sg"):
+        assert _relmax(res[k].cpu().numpy(), z[k]) < 1e-4, k
+    gg = eng.get_grads()
+    for name_, _, _ in eng.table:
+        if "grad/" + name_ in z:
+            assert _relmax(gg[name_].numpy(), z["grad/" + name_]) < 1e-3, name_
+        s = z["gradsum/" + name_]
+        assert abs(gg[name_].double().sum().item() - s[0]) < 1e-3 * max(s[1], 1e-12), name_
+    costs = [eng.train_step(inp, noise)["overall_loss"][0] for _ in range(len(z["adam_costs"]))]
+    np.testing.assert_allclose(costs, z["adam_costs"], rtol=2e-4)
+    eng.close()
+
+
+@pytest.mark.parametrize("N,B,S,density", [(9, 3, 2, 0.45), (14, 2, 3, 0.25)])
+def test_three_hop_sgc_dense_adjacency_vs_oracle(built, N, B, S, density):
+    """SpatialGraphConvolution_3D on contact-map-like adjacencies (dense, symmetric 0/1 -- not forests) and on real-valued ones:
+    every output and gradient against the oracle's factored form (== the literal N^4 form to 1e-12, tests/test_oracle.py)."""
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", **PROTEIN)
+    g = torch.Generator().manual_seed(4)
+    A = (torch.rand((B * S, N, N), generator=g, dtype=torch.float64) < density).double()
+    A = torch.triu(A, 1); A = A + A.transpose(1, 2)
+    if density < 0.3:
+        A = A * torch.rand((B * S, N, N), generator=g, dtype=torch.float64)        # real-valued, asymmetric weights
+    inp = dict(inp); inp["adj"] = A
+    enc, z, dec, L, grads = O.loss_and_grads(P, inp, noise, cfg, "factored")
+    eng = _protein_engine(built, N, B, S, chunk_graphs=2)
+    eng.set_params(P)
+    res = eng.grads(inp, noise, fetch=("generated_adj_prob", "z_mean_sg", "z_std_sg"))
+    np.testing.assert_allclose(res["overall_loss"], [x.item() for x in L["overall_loss"]], rtol=1e-4)
+    for k in ("z_mean_sg", "z_std_sg"):
+        assert _relmax(res[k].cpu().numpy(), enc[k].detach().numpy()) < 1e-4, k
+    assert _relmax(res["generated_adj_prob"].cpu().numpy(), dec["generated_adj_prob"].detach().numpy()) < 1e-4
+    gg = eng.get_grads()
+    worst = max((_relmax(gg[k].numpy(), v.numpy()), k) for k, v in grads.items())
+    assert worst[0] < 1e-3, worst
+    eng.close()
+
+
+def test_protein_flag_block_trains(built):
+    """flags.apply_dataset('protein') (main.py:218-236) -> SGCNModelVAE / OptimizerVAE / Session.run: constructs and trains."""
+    flags = import_module("snd-vae_b200.flags"); model_m = import_module("snd-vae_b200.model"); opt_m = import_module("snd-vae_b200.optimizer")
+    sess_m = import_module("snd-vae_b200.session"); prep = import_module("snd-vae_b200.preprocessing"); data = import_module("snd-vae_b200.data")
+    F = flags.FLAGS; F.reset(); F.apply_dataset("protein"); F.type = "train"; F.batch_size = 4; F.sampling_num = 2
+    N = 16
+    d = data.synthetic_graphs(N, F.batch_size, F.sampling_num, spatial_dim=3, seed=12)
+    d["adj"] = np.repeat(d["adj_truth"], F.sampling_num, axis=0)          # the protein loader feeds the contact map itself
+    ph = sess_m.make_placeholders(F.batch_size, F.sampling_num, N, F.num_feature, F.spatial_dim)
+    m = model_m.SGCNModelVAE(ph, F.num_feature, N)
+    o = opt_m.OptimizerVAE(preds_edge=m.generated_adj_prob, preds_node=m.generated_node_feat, preds_spatial=m.generated_spatial,
+                           labels_edge=ph["adj_truth"], labels_node=ph["feature_truth"], labels_spatial=ph["spatial_truth"],
+                           labels_rel=ph["rel_truth"], global_iter=ph["global_iter"], model=m, num_nodes=N, pos_weight=1.0, norm=1.0, beta=1)
+    assert m.engine.cfg.sg_hops == 3 and "encoder/g_sg1_conv/Matrix0" in m.vars
+    fd = prep.construct_feed_dict_train(d["features"], d["spatial"], d["adj"], d["rel"], d["adj_truth"], d["feature_truth"], d["spatial_truth"], d["rel_truth"], ph)
+    costs = []
+    with sess_m.Session() as sess:
+        for _ in range(4):
+            costs.append(sess.run([o.opt_op, o.cost], feed_dict=fd)[1])
+    assert np.isfinite(costs).all() and costs[-1] < costs[0]
+    F.reset()

@@ -67,8 +67,10 @@ def test_flags_defaults_and_overrides():
     assert F.learning_rate == 0.0008 and F.num_edge_feature == 2
     F.apply_dataset("synthetic1")
     assert (F.sg_hidden_size, F.node_h_size, F.learning_rate) == (500, 50, 0.001)
+    F.apply_dataset("protein")                                                                                 # main.py:218-236
+    assert F.sg_conv_hidden == [[10, 10, 10, 10], [20, 20, 20, 20]] and (F.spatial_dim, F.node_h_size, F.batch_size) == (3, 5, 50)
     with pytest.raises(ValueError):
-        F.apply_dataset("protein")
+        F.apply_dataset("scene")
     F.reset()
 
 
@@ -192,15 +194,16 @@ def test_bench_compulsory_bytes_of_the_spectral_stage():
     assert bench.spectral_bytes(N) == fwd_y + gemm_f + inv_o + fwd_do + gemm_d + inv_dy + wgrad
 
 
-def test_make_config_refuses_the_3hop_branch():
-    """The reference's protein / mnist configuration (four hidden sizes per SGC layer) is not built on the device: the host
-    mirror raises instead of silently truncating the tuple."""
+def test_make_config_selects_the_3hop_branch():
+    """Four hidden sizes per SGC layer (the reference's protein / mnist configuration, main.py:225,241) select
+    SpatialGraphConvolution_3D (sg_hops = 3); mixed or malformed tuples raise instead of being truncated."""
     sv = import_module("snd-vae_b200")
-    with pytest.raises(Exception, match="SpatialGraphConvolution_3D"):
-        sv.make_config(8, 2, "disentangled", sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)))
+    cfg = sv.make_config(8, 2, "disentangled", sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20, 20)))
+    assert cfg.sg_hops == 3 and [list(r) for r in cfg.sg_conv_hidden3] == [[10, 10, 10, 10], [20, 20, 20, 20]]
+    with pytest.raises(Exception, match="SpatialGraphConvolution"):
+        sv.make_config(8, 2, "disentangled", sg_conv_hidden=((10, 10, 10, 10), (20, 20, 20)))
     cfg = sv.make_config(8, 2, "disentangled", sg_conv_hidden=((4, 5, 6), (7, 8, 9)))
-    assert [list(r) for r in cfg.sg_conv_hidden] == [[4, 5, 6], [7, 8, 9]]
-
+    assert cfg.sg_hops == 0 and [list(r) for r in cfg.sg_conv_hidden] == [[4, 5, 6], [7, 8, 9]]
 
 def test_session_initializer_fetch_is_a_noop():
     """main.py:301-302: `sess.run(tf.global_variables_initializer())` right after tf.Session(); the shim returns None."""
