@@ -104,9 +104,15 @@ __device__ __forceinline__ void tg_load4_kmajor(const float* __restrict__ base, 
     for (int j = 0; j < 4; ++j) v[j] = 0.f;
   }
 }
-// byte offset of (row, 8-wide K group g) inside one plane of a chunk tile: core matrix (8 rows x 8 K) = 128 contiguous bytes,
-// the 4 core matrices of a row group along K 128 B apart (LBO), row groups 512 B apart (SBO)
-__device__ __forceinline__ int tg_tile_off(int row, int g) { return (row >> 3) * 512 + g * 128 + (row & 7) * 16; }
+// byte offset of (row, 8-wide K group g) inside one plane of a chunk tile.  K-major rows of 32 bf16 = 64 bytes in the
+// SWIZZLE_64B layout of the UMMA descriptor: the 16-byte group g of row r sits at position g ^ ((r >> 1) & 3) of its row
+// (Swizzle<2,4,3> on the byte address; tiles are 512-byte aligned).  Whatever way the threads of a warp are spread over (row, g)
+// -- 4 groups of one row next to each other (K-contiguous operands) or 8 rows of one group (transposed operands) -- the 8 lanes
+// of a 16-byte store phase then hit 8 different bank groups.  (The first version used the un-swizzled interleaved layout:
+// 68 % of the kernel's shared-memory wavefronts were bank conflicts.)
+__device__ __forceinline__ int tg_tile_off(int row, int g) { return row * 64 + ((g ^ ((row >> 1) & 3)) << 4); }
+#define TG_DESC_ZERO umma_desc(0u, 16, 512, 4ull)     /* SWIZZLE_64B, 8-row groups 512 B apart; + (address >> 4) gives a tile's descriptor */
+#define TG_KSTEP_BYTES 32                             /* one MMA K step (16 bf16) further along the swizzled row */
 
 // 8 K values of row r (global row index) starting at k of an operand with K contiguous in memory
 __device__ __forceinline__ void tg_load8_kmajor(const float* __restrict__ base, long long rs, long long r, long long rmax, int k, int kmax,
@@ -177,16 +183,16 @@ __device__ __forceinline__ void tg_load_tile(const float* __restrict__ base, lon
 }
 
 // the six split products of one 32-wide K chunk: A planes at sa + p * TG_APLANE, B planes at sb + p * bplane.  `dz` is the
-// descriptor of shared address 0 (LBO 128, SBO 512, no swizzle): the start-address field is the low 14 bits in 16-byte units
+// descriptor of shared address 0 (TG_DESC_ZERO): the start-address field is the low 14 bits in 16-byte units
 // and every shared address is < 256 KB, so a tile's descriptor is dz + (address >> 4)
 __device__ __forceinline__ void tg_issue_chunk(uint32_t td, uint32_t sa, uint32_t sb, uint32_t bplane, uint32_t idesc, bool first, uint64_t dz) {
 #pragma unroll
-  for (int k = 0; k < TG_BK / 16; ++k) {          // one K step = two core matrices = 256 bytes further along the row group
+  for (int k = 0; k < TG_BK / 16; ++k) {          // one K step = 32 bytes further along the swizzled rows
     uint64_t a[TG_NP], b[TG_NP];
 #pragma unroll
     for (int p = 0; p < TG_NP; ++p) {
-      a[p] = dz + ((sa + p * TG_APLANE + k * 256) >> 4);
-      b[p] = dz + ((sb + p * bplane + k * 256) >> 4);
+      a[p] = dz + ((sa + p * TG_APLANE + k * TG_KSTEP_BYTES) >> 4);
+      b[p] = dz + ((sb + p * bplane + k * TG_KSTEP_BYTES) >> 4);
     }
     umma_bf16(td, a[0], b[0], idesc, (first && k == 0) ? 0u : 1u);
     umma_bf16(td, a[0], b[1], idesc, 1u);
@@ -210,7 +216,8 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
   constexpr int STAGE_BYTES = TG_NP * (TG_APLANE + B_PLANE);
   constexpr uint32_t TMEM_COLS = GROUPED ? 2 * BNMAX : BNMAX;
   static_assert(BNMAX == 64 || BNMAX == 128, "TMEM allocations are powers of two");
-  extern __shared__ __align__(128) uint8_t tg_smem[];
+  extern __shared__ __align__(128) uint8_t tg_smem_raw[];
+  uint8_t* tg_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 512-byte aligned tiles
   __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_full[2], acc_empty[2], raw_full[TG_RAW], raw_empty[TG_RAW];
   __shared__ uint32_t tmem_base_s;
 
@@ -351,7 +358,7 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
   } else if (warp == 4) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(TG_BM, bnc, 0, 0);
-      const uint64_t dz = umma_desc(0u, 128, 512, 0ull);
+      const uint64_t dz = TG_DESC_ZERO;
       for (int it = 0; it < nk; ++it) {
         const int g = it / TG_GROUP, gi = it - g * TG_GROUP, slot = GROUPED ? (g & 1) : 0;
         if (GROUPED && gi == 0) { mbar_wait(&acc_empty[slot], ((g >> 1) & 1) ^ 1); tc_fence_after(); }
@@ -468,7 +475,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
   constexpr int A_STAGE = TG_NP * TG_APLANE;
   constexpr uint32_t SLOT_COLS = 256;                  // one accumulator slot: 2 bnc <= 256 columns
   constexpr uint32_t TMEM_COLS = 2 * SLOT_COLS;
-  extern __shared__ __align__(128) uint8_t tg_smem[];
+  extern __shared__ __align__(128) uint8_t tg_smem_raw[];
+  uint8_t* tg_smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tg_smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[TT_STAGES], empty_bar[TT_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -507,11 +515,11 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
   if (warp < 16) {
     const int t = threadIdx.x, row = t >> 2, g = t & 3;
     const bool a_vec = (P.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
-    // Each thread owns row t / 4 and the K quads 4 g .. 4 g + 3 and 16 + 4 g .. 16 + 4 g + 3 of every chunk (g = t % 4): the four
-    // threads of a row read 64 contiguous bytes per load instruction, and a warp's 8-byte stores of a quad fill two whole core
-    // matrices (8 rows x 16 bytes each): conflict-free.  Register ring: the loads of unit u + TT_AHEAD are issued before unit u is
-    // converted (TT_AHEAD x 32 bytes in flight per thread).
-    const int off0 = tg_tile_off(row, g >> 1) + (g & 1) * 8, off1 = tg_tile_off(row, 2 + (g >> 1)) + (g & 1) * 8;
+    // Each thread loads the K quads 4 g .. 4 g + 3 and 16 + 4 g .. 16 + 4 g + 3 of row t / 4 (g = t % 4): the four threads of a row
+    // read 64 contiguous bytes per load instruction.  Neighbouring threads then swap one quad (shuffle) so that the even one holds
+    // the 8 consecutive K values of group g / 2 and the odd one those of group 2 + g / 2, and each stores three 16-byte plane pieces.
+    // Register ring: the loads of unit u + TT_AHEAD are issued before unit u is converted (TT_AHEAD x 32 bytes in flight per thread).
+    const int off = tg_tile_off(row, (g & 1) ? 2 + (g >> 1) : (g >> 1));
     float buf[TT_AHEAD + 1][8];
     long long lt = 0; int lc = 0;                                     // (tile, chunk) of the next unit to load
 #define TT_LOAD_(dst) do { const long long r_ = (t_lo + lt) * TG_BM + row; const int k_ = lc * TG_BK + 4 * g; \
@@ -525,19 +533,25 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
 #pragma unroll
       for (int d = 0; d <= TT_AHEAD; ++d) {
         const long long u = u0 + d;
-        if (u < units) {
+        if (u < units) {             // `units` is the same for every thread of the CTA: the shuffles below are warp-uniform
           if (u + TT_AHEAD < units) TT_LOAD_(buf[(d + TT_AHEAD) % (TT_AHEAD + 1)]);
           if (++lc == nkc) { lc = 0; ++lt; }
           const int s = (int)(u % TT_STAGES); const uint32_t ph = (uint32_t)((u / TT_STAGES) & 1);
-          uint2 p0[TG_NP], p1[TG_NP]; tg_split4(buf[d], p0); tg_split4(buf[d] + 4, p1);
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // even thread: keeps its first quad, receives the partner's first quad; odd thread: receives the partner's second, keeps its second
+            const float send = (g & 1) ? buf[d][j] : buf[d][4 + j];
+            const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+            v[j] = (g & 1) ? got : buf[d][j];
+            v[4 + j] = (g & 1) ? buf[d][4 + j] : got;
+          }
+          uint4 pl[TG_NP]; tg_split8(v, pl);
           if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1);
           __syncwarp();
-          uint8_t* st = sA + (size_t)s * A_STAGE;
+          uint8_t* st = sA + (size_t)s * A_STAGE + off;
 #pragma unroll
-          for (int p = 0; p < TG_NP; ++p) {
-            *reinterpret_cast<uint2*>(st + p * TG_APLANE + off0) = p0[p];
-            *reinterpret_cast<uint2*>(st + p * TG_APLANE + off1) = p1[p];
-          }
+          for (int p = 0; p < TG_NP; ++p) *reinterpret_cast<uint4*>(st + p * TG_APLANE) = pl[p];
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[s]);
@@ -548,7 +562,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
   } else if (warp == 16) {
     if (lane == 0) {
       const uint32_t idesc2 = umma_idesc(TG_BM, 2 * bnc, 0, 0), idesc1 = umma_idesc(TG_BM, bnc, 0, 0);
-      const uint64_t dz = umma_desc(0u, 128, 512, 0ull);
+      const uint64_t dz = TG_DESC_ZERO;
       const uint32_t sb0 = smem_u32(sB), sa0 = smem_u32(sA);
       long long u = 0;
       for (long long ti = 0; ti < nt; ++ti) {
@@ -562,11 +576,11 @@ __global__ void __launch_bounds__(TT_THREADS, 1) tsgemm_tall_k(TgArgs P) {
           const uint32_t td = tmem_d + slot * SLOT_COLS, sa = sa0 + s * A_STAGE, sb = sb0 + c * TG_NP * B_PLANE;
 #pragma unroll
           for (int k = 0; k < TG_BK / 16; ++k) {
-            const uint64_t b = dz + ((sb + k * 256) >> 4), bl = dz + ((sb + 2 * B_PLANE + k * 256) >> 4);
-            const uint64_t ah = dz + ((sa + k * 256) >> 4);
+            const uint64_t b = dz + ((sb + k * TG_KSTEP_BYTES) >> 4), bl = dz + ((sb + 2 * B_PLANE + k * TG_KSTEP_BYTES) >> 4);
+            const uint64_t ah = dz + ((sa + k * TG_KSTEP_BYTES) >> 4);
             umma_bf16(td, ah, b, idesc2, (c == 0 && k == 0) ? 0u : 1u);
-            umma_bf16(td, dz + ((sa + TG_APLANE + k * 256) >> 4), b, idesc2, 1u);
-            umma_bf16(td, dz + ((sa + 2 * TG_APLANE + k * 256) >> 4), b, idesc1, 1u);
+            umma_bf16(td, dz + ((sa + TG_APLANE + k * TG_KSTEP_BYTES) >> 4), b, idesc2, 1u);
+            umma_bf16(td, dz + ((sa + 2 * TG_APLANE + k * TG_KSTEP_BYTES) >> 4), b, idesc1, 1u);
             umma_bf16(td + bnc, ah, bl, idesc1, 1u);
           }
           umma_commit(&empty_bar[s]);
@@ -667,7 +681,7 @@ __global__ void tg_reduce_k(const float* __restrict__ ws, int nsplit, long long 
 template <int BNMAX, bool GROUPED, bool SLAB>
 static cudaError_t tg_launch_t(const TgArgs& a, dim3 grid, cudaStream_t st) {
   constexpr int STAGES = SLAB ? 2 : ((BNMAX <= 64 || GROUPED) ? 3 : 2);
-  const int smem = STAGES * TG_NP * (TG_APLANE + BNMAX * TG_BK * 2) + (SLAB ? TG_RAW * 128 * (a.lda + a.ldb) : 0);
+  const int smem = 1024 + STAGES * TG_NP * (TG_APLANE + BNMAX * TG_BK * 2) + (SLAB ? TG_RAW * 128 * (a.lda + a.ldb) : 0);
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(tsgemm_k<BNMAX, GROUPED, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_MAX);
@@ -684,7 +698,7 @@ static cudaError_t tg_launch(const TgArgs& a, dim3 grid, cudaStream_t st, bool g
 }
 static size_t tt_smem_bytes(int K, int bnc) {
   const int nkc = (K + TG_BK - 1) / TG_BK;
-  return (((size_t)nkc * TG_NP * bnc * TG_BK * 2 + 1023) & ~(size_t)1023) + (size_t)TT_STAGES * TG_NP * TG_APLANE + (size_t)TG_BM * (bnc + 1) * 4;
+  return 1024 + (((size_t)nkc * TG_NP * bnc * TG_BK * 2 + 1023) & ~(size_t)1023) + (size_t)TT_STAGES * TG_NP * TG_APLANE + (size_t)TG_BM * (bnc + 1) * 4;
 }
 static cudaError_t tt_launch(const TgArgs& a, dim3 grid, cudaStream_t st) {
   static bool attr_done = false;
@@ -763,7 +777,7 @@ static cudaError_t tsgemm(cudaStream_t st, bool tA, bool tB, long long M, int N,
   // slab form: both operands K-major with rows short enough for a ring of raw slabs, 16-byte aligned bases
   a.lda = (int)lda; a.ldb = (int)ldb;
   const bool slab = tA && !tB && chunks >= 4 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0 &&
-                    2 * TG_NP * (TG_APLANE + bnmax * TG_BK * 2) + TG_RAW * 128 * (lda + ldb) <= TT_SMEM_MAX;
+                    1024 + 2 * TG_NP * (TG_APLANE + bnmax * TG_BK * 2) + TG_RAW * 128 * (lda + ldb) <= TT_SMEM_MAX;
   cudaError_t e = bnmax == 64 ? tg_launch<64>(a, grid, st, grouped, slab) : tg_launch<128>(a, grid, st, grouped, slab);
   if (e != cudaSuccess || !(ksplit > 1 && split_ws)) return e;
   tg_reduce_k<<<(unsigned)((M * N + 255) / 256), 256, 0, st>>>(ws, ksplit, M * N, N, C, ldc, bias, beta);
