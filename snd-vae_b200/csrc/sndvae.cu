@@ -95,7 +95,7 @@ struct sndvae_handle {
   float* adam_alpha;                   // device [1]: this iteration's Adam step size (see adam.cuh)
   // small-problem path: the device-resident train step (memsets, ~300 kernels, Adam, loss read-back) captured once and replayed as
   // a CUDA graph while the caller's buffers stay the same (SNDVAE_GRAPH=0 disables; default: problems of < 2^21 edge cells)
-  cudaGraphExec_t graph_exec; unsigned long long graph_key; int graph_mode; int capturing; long long graph_launches, graph_replays;
+  cudaGraphExec_t graph_exec; cudaStream_t gs; unsigned long long graph_key; int graph_mode; int capturing; long long graph_launches, graph_replays;
   float* gemm_ws; size_t gemm_ws_floats;   // workspace of the deterministic split-K products (tsgemm.cuh)
   int hf_ready;                        // every host-feed staging buffer is allocated
   int max_c;                           // widest node-level channel count of the config (sizes gA / gB / gC / colbuf)
@@ -1431,7 +1431,7 @@ int sndvae_create(const sndvae_config* cfg, void* stream, sndvae_t** out) {
   sndvae_t* h = new sndvae_handle();
   *out = h;    // returned even on failure so that sndvae_last_error works; caller destroys
   h->cfg = *cfg; h->stream = (cudaStream_t)stream; h->launches = 0; h->pinned_loss = nullptr; h->ev_used = 0;
-  h->graph_exec = nullptr; h->graph_key = 0; h->capturing = 0; h->graph_launches = 0; h->graph_replays = 0; h->graph_mode = 0;
+  h->graph_exec = nullptr; h->gs = nullptr; h->graph_key = 0; h->capturing = 0; h->graph_launches = 0; h->graph_replays = 0; h->graph_mode = 0;
   h->hf_ready = 0; h->hc_ready = 0; h->hc_features = nullptr; h->poisoned = 0; h->comm = nullptr; h->rank = 0; h->world = 1;
   h->hf_features = nullptr; h->cs = nullptr; h->ds = nullptr; h->ev_start = nullptr; h->zz_planes = nullptr; h->zz_cap = 0;
   cudaFuncSetAttribute(edge_epilogue_k, cudaFuncAttributeMaxDynamicSharedMemorySize, EPI_SMEM_BYTES);
@@ -1526,6 +1526,7 @@ int sndvae_destroy(sndvae_t* h) {
   cudaStreamSynchronize(h->stream);
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->gs) cudaStreamDestroy(h->gs);
   tc_destroy(h->tc); if (h->cfg.use_tensor_cores) l0d_destroy(h->l0d);
   if (h->spec) { spec_destroy(h->sp); ytc_destroy(h->ytc); }
   for (void* p : h->allocs) cudaFree(p);
@@ -1652,13 +1653,28 @@ static int train_step_graph(sndvae_t* h, const sndvae_inputs* in, const sndvae_n
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->graph_key == 0 || h->graph_key != (key ^ 2ull)) { h->graph_key = key ^ 2ull; return 0; }   // first sight of these buffers: run plainly (warms every lazy init)
     cudaGraph_t g = nullptr;
-    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); h->graph_mode = 0; return 0; }
+    // the legacy default stream (what a caller without a stream of its own passes) cannot be captured: the step is then
+    // recorded on a stream of the handle's own -- nothing executes during capture -- and replayed on the caller's stream
+    const cudaStream_t user = h->stream;
+    if ((uintptr_t)user <= 2) {
+      if (!h->gs && cudaStreamCreateWithFlags(&h->gs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); h->graph_mode = 0; return 0; }
+      h->stream = h->gs;
+    }
+    const cudaError_t eb = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (eb != cudaSuccess) {
+      if (getenv("SNDVAE_GRAPH_DEBUG")) fprintf(stderr, "[sndvae graph] begin-capture: %s\n", cudaGetErrorString(eb));
+      cudaGetLastError(); h->graph_mode = 0; h->stream = user; return 0;
+    }
     h->capturing = 1;
     r = run_body(h, in, nz, out, nullptr, true, h->B, nullptr, RUN_NOFETCH);
     if (!r) r = adam_launch(h);
     h->capturing = 0;
     const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
-    if (r || e != cudaSuccess || !g || cudaGraphInstantiate(&h->graph_exec, g, 0) != cudaSuccess) {
+    h->stream = user;
+    cudaError_t ei = cudaSuccess;
+    if (r || e != cudaSuccess || !g || (ei = cudaGraphInstantiate(&h->graph_exec, g, 0)) != cudaSuccess) {
+      if (getenv("SNDVAE_GRAPH_DEBUG"))
+        fprintf(stderr, "[sndvae graph] capture dropped: step rc %d (%s), end-capture %s, instantiate %s\n", r, h->err.c_str(), cudaGetErrorString(e), cudaGetErrorString(ei));
       if (g) cudaGraphDestroy(g);
       cudaGetLastError(); h->graph_exec = nullptr; h->graph_mode = 0;       // something in the step cannot be captured: stay on plain launches
       h->B = h->cfg.batch_size; h->BS = h->B * h->S; h->Rn = h->B * h->N;

@@ -23,14 +23,28 @@
 // pair per thread, lines walked in an order chosen for DRAM sector merging and L2 reuse (LineWalk).
 #pragma once
 #include "e2e_tc.cuh"
+#include "fft2p.cuh"
 #include <vector>
 #include <cmath>
 
-#define SP_KA1 104     /* row stride (bf16) of the Y^ planes: [re c0..49 | im c0..49 | 4 pad] = 208 B (TMA: 16 B multiples) */
-#define SP_KA2 40      /* row stride (bf16) of the dO^ planes: [re q0..19 | im q0..19] = 80 B */
+#define SP_KA1 104     /* row stride (bf16) of the Y^ planes: 25 x [re c, re c+1, im c, im c+1] + 4 pad = 208 B (TMA: 16 B multiples) */
+#define SP_KA2 40      /* row stride (bf16) of the dO^ planes: 10 x [re q, re q+1, im q, im q+1] = 80 B */
 #define SP_NF 48       /* fwd GEMM N: 40 -> 48 (N % 16 == 0 at M = 128) */
 #define SP_ND 112      /* dgrad GEMM N: 100 -> 112 */
 #define SP_FFT_THREADS_MAX 512
+// Spectrum rows hold the channels in pairs, [re c, re c+1, im c, im c+1] for even c: the transforms pack two real channels
+// into one complex signal, so one thread owns exactly these four values of a row -- one 8-byte bf16 store per plane (forward) or
+// one 16-byte load (inverse) instead of two accesses half a row apart.  The GEMM operands (spec_stage_weights_k) and the
+// weight-gradient fold (spec_wgrad_finalize_k) index the rows through the same two functions.
+__host__ __device__ __forceinline__ int sp_kre(int c) { return ((c >> 1) << 2) | (c & 1); }
+__host__ __device__ __forceinline__ int sp_kim(int c) { return sp_kre(c) + 2; }
+__device__ __forceinline__ uint2 sp_pack_hi_lo(float x1r, float x2r, float x1i, float x2i, uint2& lo) {     // -> [re c, re c+1, im c, im c+1] hi, lo
+  const __nv_bfloat162 hr = __floats2bfloat162_rn(x1r, x2r), hi = __floats2bfloat162_rn(x1i, x2i);
+  const __nv_bfloat162 lr = __floats2bfloat162_rn(x1r - __low2float(hr), x2r - __high2float(hr));
+  const __nv_bfloat162 li = __floats2bfloat162_rn(x1i - __low2float(hi), x2i - __high2float(hi));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&lr), *reinterpret_cast<const uint32_t*>(&li));
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&hr), *reinterpret_cast<const uint32_t*>(&hi));
+}
 
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x)); }
 __device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -194,15 +208,10 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_fwd_k(FftFwdAr
         const float2 z1 = cur.p[f * g + cp], z2 = cur.p[(f == 0 ? 0 : L - f) * g + cp];
         const float x1r = 0.5f * (z1.x + z2.x), x1i = 0.5f * (z1.y - z2.y);
         const float x2r = 0.5f * (z1.y + z2.y), x2i = 0.5f * (z2.x - z1.x);
-        const long long o = ((long long)f * A.RA + line) * A.KA + 2 * (cp0 + cp);
-        __nv_bfloat162 h, l;
-        h.x = __float2bfloat16_rn(x1r); h.y = __float2bfloat16_rn(x2r);
-        l.x = __float2bfloat16_rn(x1r - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2r - __bfloat162float(h.y));
-        *reinterpret_cast<__nv_bfloat162*>(A.oh + o) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o) = l;
-        h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
-        l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
-        *reinterpret_cast<__nv_bfloat162*>(A.oh + o + A.C) = h; *reinterpret_cast<__nv_bfloat162*>(A.ol + o + A.C) = l;
-        if (cp0 + cp == CP - 1) for (int e = A.C + 2; e < A.KA - 2 * (CP - 1); e += 2) {   // the row's pad: no partly written sectors
+        const long long o = ((long long)f * A.RA + line) * A.KA + 4 * (cp0 + cp);
+        uint2 lo; const uint2 hi = sp_pack_hi_lo(x1r, x2r, x1i, x2i, lo);
+        *reinterpret_cast<uint2*>(A.oh + o) = hi; *reinterpret_cast<uint2*>(A.ol + o) = lo;
+        if (cp0 + cp == CP - 1) for (int e = 4; e < A.KA - 4 * (CP - 1); e += 2) {   // the row's pad: no partly written sectors
           *reinterpret_cast<uint32_t*>(A.oh + o + e) = 0u; *reinterpret_cast<uint32_t*>(A.ol + o + e) = 0u; }
       }
     }
@@ -234,9 +243,9 @@ __global__ void __launch_bounds__(SP_FFT_THREADS_MAX, 1) spec_fft_inv_k(FftInvAr
       // Z = X1 + i X2 over the full circle (X[L-f] = conj X[f]); inverse DFT = swap . forward DFT . swap
       for (int w = threadIdx.x; w < F * g; w += blockDim.x) {
         const int f = w / g, cp = w - f * g;
-        const float* row = A.in + ((long long)f * A.RA + line) * W + 2 * (cp0 + cp);
-        const float2 a = *reinterpret_cast<const float2*>(row);
-        float2 b = *reinterpret_cast<const float2*>(row + A.C);
+        const float4 ab = *reinterpret_cast<const float4*>(A.in + ((long long)f * A.RA + line) * W + 4 * (cp0 + cp));
+        const float2 a = make_float2(ab.x, ab.y);
+        float2 b = make_float2(ab.z, ab.w);
         const bool selfc = (f == 0) || (2 * f == L);
         if (selfc) b = make_float2(0.f, 0.f);
         buf0[f * g + cp] = make_float2(b.x + a.y, a.x - b.y);
@@ -428,8 +437,8 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
     const float2* res = bufB;
     if (R2) { fft_pass_ct<(R2 ? R2 : 2), R0 * R1, L, G, NT>(b, a, tw, jb, cp); __syncthreads(); res = bufA; }
     // spectra of the pair's two real channels, split into bf16 hi / lo rows of the GEMM operand: f = jb, jb + NT / G, ...
-    __nv_bfloat16* oh = A.oh + ((long long)jb * A.RA + line) * A.KA + 2 * cp;
-    __nv_bfloat16* ol = A.ol + ((long long)jb * A.RA + line) * A.KA + 2 * cp;
+    __nv_bfloat16* oh = A.oh + ((long long)jb * A.RA + line) * A.KA + 4 * cp;
+    __nv_bfloat16* ol = A.ol + ((long long)jb * A.RA + line) * A.KA + 4 * cp;
     const long long fstep = (long long)(NT / G) * A.RA * A.KA;
     const int padw = cp == G - 1 ? A.KA - 2 * C : 0;       // the last pair's thread also writes the row's pad (bf16 elements)
 #pragma unroll 4
@@ -437,17 +446,12 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_fwd_fast_k(FftFwdArgs A) {
       const float2 z1 = res[f * G + cp], z2 = res[(f == 0 ? 0 : L - f) * G + cp];
       const float x1r = 0.5f * (z1.x + z2.x), x1i = 0.5f * (z1.y - z2.y);
       const float x2r = 0.5f * (z1.y + z2.y), x2i = 0.5f * (z2.x - z1.x);
-      __nv_bfloat162 h, l;
-      h.x = __float2bfloat16_rn(x1r); h.y = __float2bfloat16_rn(x2r);
-      l.x = __float2bfloat16_rn(x1r - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2r - __bfloat162float(h.y));
-      *reinterpret_cast<__nv_bfloat162*>(oh) = h; *reinterpret_cast<__nv_bfloat162*>(ol) = l;
-      h.x = __float2bfloat16_rn(x1i); h.y = __float2bfloat16_rn(x2i);
-      l.x = __float2bfloat16_rn(x1i - __bfloat162float(h.x)); l.y = __float2bfloat16_rn(x2i - __bfloat162float(h.y));
-      *reinterpret_cast<__nv_bfloat162*>(oh + C) = h; *reinterpret_cast<__nv_bfloat162*>(ol + C) = l;
+      uint2 lo; const uint2 hi = sp_pack_hi_lo(x1r, x2r, x1i, x2i, lo);
+      *reinterpret_cast<uint2*>(oh) = hi; *reinterpret_cast<uint2*>(ol) = lo;
       // the row's pad (KA - 2C elements the tensor maps never read) is written too: a sector that leaves L2 partly written
       // costs a DRAM read-modify-write (measured: +1.7 GB of reads per 256 graphs, one sector per row and plane)
-      if (padw == 4) { *reinterpret_cast<uint2*>(oh + C + 2) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(ol + C + 2) = make_uint2(0u, 0u); }
-      else for (int e = 0; e < padw; e += 2) { *reinterpret_cast<uint32_t*>(oh + C + 2 + e) = 0u; *reinterpret_cast<uint32_t*>(ol + C + 2 + e) = 0u; }
+      if (padw == 4) { *reinterpret_cast<uint2*>(oh + 4) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(ol + 4) = make_uint2(0u, 0u); }
+      else for (int e = 0; e < padw; e += 2) { *reinterpret_cast<uint32_t*>(oh + 4 + e) = 0u; *reinterpret_cast<uint32_t*>(ol + 4 + e) = 0u; }
     }
     line = next;
   }
@@ -495,8 +499,9 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast_k(FftInvArgs A) {
     __syncthreads();
 #pragma unroll 4
     for (int f = jb; f < F; f += NT / G) {
-      const float2 a = *reinterpret_cast<const float2*>(stage + f * W + 2 * cp);
-      float2 b = *reinterpret_cast<const float2*>(stage + f * W + C + 2 * cp);
+      const float4 ab = *reinterpret_cast<const float4*>(stage + f * W + 4 * cp);
+      const float2 a = make_float2(ab.x, ab.y);
+      float2 b = make_float2(ab.z, ab.w);
       const bool selfc = (f == 0) || (2 * f == L);
       if (selfc) b = make_float2(0.f, 0.f);
       bufA[f * G + cp] = make_float2(b.x + a.y, a.x - b.y);
@@ -535,9 +540,9 @@ template <int L, int G> struct SpecHalfSrc {
   static constexpr int F = L / 2 + 1, FH = (F + 1) / 2, W = 4 * G, C = 2 * G;
   __device__ __forceinline__ float2 ld(int jb, int, int off) const {
     const int p = jb + off; const bool up = p >= F; const int f = up ? L - p : p;
-    const float* row = (f < FH ? h1 + f * W : h2 + (f - FH) * W) + 2 * cp;
-    const float2 a = *reinterpret_cast<const float2*>(row);
-    float2 b = *reinterpret_cast<const float2*>(row + C);
+    const float4 ab = *reinterpret_cast<const float4*>((f < FH ? h1 + f * W : h2 + (f - FH) * W) + 4 * cp);
+    const float2 a = make_float2(ab.x, ab.y);
+    float2 b = make_float2(ab.z, ab.w);
     if (f == 0 || 2 * f == L) b = make_float2(0.f, 0.f);
     return up ? make_float2(a.y - b.x, a.x + b.y) : make_float2(b.x + a.y, a.x - b.y);
   }
@@ -604,6 +609,155 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast2_k(FftInvArgs A) {
   cp_async_wait_all();
 }
 
+// ---- two-pass transforms (fft2p.cuh): L = 48 M as (3M) x 16 forward / 16 x (3M) inverse, 16 G threads ---------------------
+template <int M, int G> struct Fft2Cfg {
+  static constexpr int L = 48 * M, F = L / 2 + 1, NT = 16 * G;
+  static constexpr size_t BUF = (size_t)L * G * 8;
+  __host__ __device__ static size_t stage_fwd(int N) { return ((size_t)N * 2 * G * 4 + 127) & ~(size_t)127; }
+  static size_t smem_fwd(int N) { return (size_t)L * 8 + BUF + 2 * stage_fwd(N); }
+  static size_t smem_inv() { return (size_t)L * 8 + BUF + (size_t)F * 4 * G * 4; }
+};
+struct SpecEmitFwd {                   // X1 / X2 of a frequency -> bf16 hi / lo rows [re c.. | im c..] of the GEMM operand planes
+  __nv_bfloat16* oh; __nv_bfloat16* ol; long long fstride; int C, padw;
+  __device__ __forceinline__ void operator()(int f, float2 x1, float2 x2) const {
+    __nv_bfloat16* ph = oh + f * fstride; __nv_bfloat16* pl = ol + f * fstride;
+    uint2 lo; const uint2 hi = sp_pack_hi_lo(x1.x, x2.x, x1.y, x2.y, lo);
+    // the row's pad is written too (a partly written sector costs a DRAM read-modify-write, see spec_fft_fwd_fast_k)
+    if (padw == 4) { *reinterpret_cast<uint4*>(ph) = make_uint4(hi.x, hi.y, 0u, 0u); *reinterpret_cast<uint4*>(pl) = make_uint4(lo.x, lo.y, 0u, 0u); }
+    else {
+      *reinterpret_cast<uint2*>(ph) = hi; *reinterpret_cast<uint2*>(pl) = lo;
+      for (int e = 0; e < padw; e += 2) { *reinterpret_cast<uint32_t*>(ph + 4 + e) = 0u; *reinterpret_cast<uint32_t*>(pl + 4 + e) = 0u; }
+    }
+  }
+};
+template <int M, int G, int MINB, bool TABLE>
+__global__ void __launch_bounds__(16 * G, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
+  using Cfg = Fft2Cfg<M, G>;
+  constexpr int L = Cfg::L, C = 2 * G, NT = Cfg::NT, R0 = 3 * M;
+  extern __shared__ __align__(128) uint8_t fsm[];
+  __shared__ float s_g[C], s_b[C], s_raw[2][C];
+  __shared__ uint64_t stage_bar[2];          // completion of a contiguous line's bulk copy into staging tile 0 / 1
+  if (threadIdx.x == 0) { mbar_init(&stage_bar[0], 1); mbar_init(&stage_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  const int N = A.N;
+  float2* tw = reinterpret_cast<float2*>(fsm);
+  float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
+  float* stage0 = reinterpret_cast<float*>(fsm + (size_t)L * 8 + Cfg::BUF);
+  const size_t sstride = Cfg::stage_fwd(N) / 4;
+  for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  if (A.gam) for (int t = threadIdx.x; t < C; t += NT) { s_g[t] = A.gam[t] * BN_RS; s_b[t] = A.bet[t]; }
+  const bool shifter = A.gam && A.bias0 && threadIdx.x < C;       // see spec_fft_fwd_fast_k: the line's bias element arrives with the line
+  float sh_g = 0.f, sh_c = 0.f;
+  if (shifter) { sh_g = A.gam[threadIdx.x] * BN_RS; sh_c = fmaf(2.f * A.b0[threadIdx.x], sh_g, A.bet[threadIdx.x]); }
+  __syncthreads();
+  const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;
+  const bool vec16 = ((long long)N * C) % 4 == 0;
+  auto is_bulk = [&](long long line) { return A.bulk && vec16 && (line < A.lines0 || A.dir1_strided != 1); };
+  auto prefetch = [&](long long line, int slot) {
+    if (line >= A.lines) return;
+    float* stage = stage0 + slot * sstride;
+    if (shifter) cp_async4(&s_raw[slot][threadIdx.x], (line >= A.lines0 ? A.bias1 + (line - A.lines0) * C : A.bias0 + line * C) + threadIdx.x);
+    if (line < A.lines0 || A.dir1_strided != 1) {
+      const float* base = A.in + line * N * C;
+      if (A.dir1_strided == 2) {
+        const bool d1 = line >= A.lines0; const long long l1 = d1 ? line - A.lines0 : line; const long long b = l1 / N; const int x = (int)(l1 - b * N);
+        base = (d1 ? A.in1 : A.in) + (((b / 128) * N + x) * 128 + (b % 128)) * N * C;
+      }
+      if (A.bulk && vec16) { if (threadIdx.x == 0) { mbar_expect_tx(&stage_bar[slot], (uint32_t)(N * C * 4)); bulk_load(stage, base, (uint32_t)(N * C * 4), &stage_bar[slot]); } }
+      else if (vec16) { for (int t = threadIdx.x; t < N * C / 4; t += NT) cp_async16(stage + 4 * t, base + 4 * t); }
+      else { for (int t = threadIdx.x; t < N * G; t += NT) cp_async8(stage + 2 * t, base + 2 * t); }
+    } else {
+      const long long l1 = line - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
+      const float* base = A.in + (b * N * N + j) * C; const long long ps = (long long)N * C;
+      if constexpr (G % 2 == 0) {
+        constexpr int Q = G / 2;
+        for (int t = threadIdx.x; t < N * Q; t += NT) { const int pos = t / Q, k = t - pos * Q; cp_async16(stage + pos * C + 4 * k, base + pos * ps + 4 * k); }
+      } else {
+        for (int pos = jb; pos < N; pos += 16) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
+      }
+    }
+  };
+  LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = N; walk.order = A.order;
+  long long line = walk.at(0), line1 = walk.at(1);
+  prefetch(line, 0); cp_async_commit();
+  prefetch(line1, 1); cp_async_commit();
+  uint32_t phases = 0;
+  const int padw = cp == G - 1 ? A.KA - 2 * C : 0;
+  const long long fstride = A.RA * A.KA;
+  for (long long it = 0; line < A.lines; ++it) {
+    const int slot = (int)(it & 1);
+    const long long line2 = walk.at(it + 2);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");       // this line's per-thread copies have landed (the next line's may be in flight)
+    if (is_bulk(line)) { mbar_wait(&stage_bar[slot], (phases >> slot) & 1u); phases ^= 1u << slot; }
+    if (shifter) s_b[threadIdx.x] = fmaf(s_raw[slot][threadIdx.x], sh_g, sh_c);
+    __syncthreads();                       // staged line and shift visible; the previous line's pass 2 is done with bufA
+    FpBn bn; bn.on = A.gam != nullptr; bn.gx = bn.gy = 1.f; bn.bx = bn.by = 0.f;
+    if (bn.on) { bn.gx = s_g[2 * cp]; bn.gy = s_g[2 * cp + 1]; bn.bx = s_b[2 * cp]; bn.by = s_b[2 * cp + 1]; }
+    fp_fwd_pass1<M, G>(reinterpret_cast<const float2*>(stage0 + slot * sstride), bufA, jb, cp, N, bn);
+    __syncthreads();                       // bufA complete; this staging tile is free
+    prefetch(line2, slot); cp_async_commit();
+    if (jb <= R0 / 2) {
+      SpecEmitFwd em; em.oh = A.oh + line * A.KA + 4 * cp; em.ol = A.ol + line * A.KA + 4 * cp; em.fstride = fstride; em.C = C; em.padw = padw;
+      fp_fwd_pass2<M, G, TABLE>(bufA, tw, jb, cp, em);
+    }
+    line = line1; line1 = line2;
+  }
+  cp_async_wait_all();
+}
+struct SpecEmitInv {                   // inverse tail: (re, im) swapped back, scaled, first N positions only
+  float* base; int pstride; int N; float scale;
+  __device__ __forceinline__ void operator()(int pos, float2 v) const {
+    if (pos < N) *reinterpret_cast<float2*>(base + (size_t)(unsigned)(pos * pstride)) = make_float2(v.y * scale, v.x * scale);
+  }
+};
+template <int M, int G, int MINB, bool TABLE>
+__global__ void __launch_bounds__(16 * G, MINB) spec_fft_inv2_k(FftInvArgs A) {
+  using Cfg = Fft2Cfg<M, G>;
+  constexpr int L = Cfg::L, F = Cfg::F, C = 2 * G, W = 4 * G, NT = Cfg::NT, R1 = 3 * M;
+  extern __shared__ __align__(128) uint8_t fsm[];
+  float2* tw = reinterpret_cast<float2*>(fsm);
+  float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
+  float* stage = reinterpret_cast<float*>(fsm + (size_t)L * 8 + Cfg::BUF);
+  for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  __shared__ uint64_t stage_bar;
+  if (threadIdx.x == 0) { mbar_init(&stage_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  uint32_t stage_ph = 0;
+  const float scale = 1.f / (float)L;
+  const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;
+  auto prefetch = [&](long long line) {
+    if (line >= A.lines) return;
+    if (A.bulk) {                              // one bulk copy per spectrum row (W floats), all counted on one mbarrier phase
+      if (threadIdx.x == 0) mbar_expect_tx(&stage_bar, (uint32_t)(F * W * 4));
+      for (int f = threadIdx.x; f < F; f += NT) bulk_load(stage + f * W, A.in + ((long long)f * A.RA + line) * W, (uint32_t)(W * 4), &stage_bar);
+      return;
+    }
+    const float* src = A.in + ((long long)jb * A.RA + line) * W + 4 * cp;     // 16 bytes = two channel pairs' worth of one half row
+    const long long fstep = 16LL * A.RA * W;
+    for (int f = jb; f < F; f += 16, src += fstep) cp_async16(stage + f * W + 4 * cp, src);
+  };
+  LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = A.N; walk.order = A.order;
+  long long line = walk.at(0);
+  prefetch(line);
+  cp_async_commit();
+  for (long long it = 0; line < A.lines; ++it) {
+    const long long next = walk.at(it + 1);
+    cp_async_wait_all();
+    if (A.bulk) { mbar_wait(&stage_bar, stage_ph); stage_ph ^= 1; }
+    __syncthreads();                       // the line's rows have landed; the previous line's pass 2 is done with bufA
+    if (jb <= R1 / 2) fp_inv_pass1<M, G>(stage, bufA, jb, cp);
+    __syncthreads();                       // bufA complete; the staging area is free
+    prefetch(next); cp_async_commit();
+    SpecEmitInv dst; dst.base = A.out + line * A.N * C + 2 * cp; dst.pstride = C; dst.N = A.N; dst.scale = scale;
+    if (A.out1 && line >= A.lines0) {
+      const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
+      dst.base = A.out1 + (b * A.N * A.N + j) * C + 2 * cp; dst.pstride = A.N * C;
+    }
+    fp_inv_pass2<M, G, TABLE>(bufA, tw, jb, cp, dst);
+    line = next;
+  }
+  cp_async_wait_all();
+}
+
 // ---- per-step weight spectra and GEMM operand staging -----------------------------------------------------------
 // G^[f][c][q] = sum_t w1[t][c][q] exp(-2 pi i f (p - t) / L)   (double accumulation over the exact table)
 //   fwd   B (K-major, [f][n][k], k < 128): n = q: (k=c: Gr, k=C1+c: -Gi);  n = C2+q: (k=c: Gi, k=C1+c: Gr)
@@ -626,10 +780,11 @@ __global__ void spec_stage_weights_k(const float* __restrict__ w1, const double2
   auto put = [](__nv_bfloat16* hi, __nv_bfloat16* lo, size_t o, float v) {
     const __nv_bfloat16 h = __float2bfloat16_rn(v); hi[o] = h; lo[o] = __float2bfloat16_rn(v - __bfloat162float(h)); };
   const size_t bf = (size_t)f * SP_NF * 128, bd = (size_t)f * SP_ND * 64;
-  put(Bfh, Bfl, bf + (size_t)q * 128 + c, Gr);            put(Bfh, Bfl, bf + (size_t)q * 128 + C1 + c, -Gi);
-  put(Bfh, Bfl, bf + (size_t)(C2 + q) * 128 + c, Gi);     put(Bfh, Bfl, bf + (size_t)(C2 + q) * 128 + C1 + c, Gr);
-  put(Bdh, Bdl, bd + (size_t)c * 64 + q, Gr);             put(Bdh, Bdl, bd + (size_t)c * 64 + C2 + q, Gi);
-  put(Bdh, Bdl, bd + (size_t)(C1 + c) * 64 + q, -Gi);     put(Bdh, Bdl, bd + (size_t)(C1 + c) * 64 + C2 + q, Gr);
+  const int cr = sp_kre(c), ci = sp_kim(c), qr = sp_kre(q), qi = sp_kim(q);      // row positions of (re, im) of channel c / q
+  put(Bfh, Bfl, bf + (size_t)qr * 128 + cr, Gr);          put(Bfh, Bfl, bf + (size_t)qr * 128 + ci, -Gi);
+  put(Bfh, Bfl, bf + (size_t)qi * 128 + cr, Gi);          put(Bfh, Bfl, bf + (size_t)qi * 128 + ci, Gr);
+  put(Bdh, Bdl, bd + (size_t)cr * 64 + qr, Gr);           put(Bdh, Bdl, bd + (size_t)cr * 64 + qi, Gi);
+  put(Bdh, Bdl, bd + (size_t)ci * 64 + qr, -Gi);          put(Bdh, Bdl, bd + (size_t)ci * 64 + qi, Gr);
 }
 // dw1[t][c][q] += (1/L) sum_f kappa_f Re(dG^[f][c][q] e^{+2 pi i f (p - t) / L}),  dG^ = conj(Y^) dO^ from the 2x2 blocks of P:
 //   dGr = P[c][q] + P[C1+c][C2+q],  dGi = P[c][C2+q] - P[C1+c][q]      (P[f]: [128][SP_NF])
@@ -643,8 +798,9 @@ __global__ void spec_wgrad_finalize_k(const float* __restrict__ P, const double2
   double acc = 0.0;
   for (int f = 0; f < F; ++f) {
     const float* Pf = P + (size_t)f * 128 * SP_NF;
-    const double gr = (double)Pf[c * SP_NF + q] + (double)Pf[(C1 + c) * SP_NF + C2 + q];
-    const double gi = (double)Pf[c * SP_NF + C2 + q] - (double)Pf[(C1 + c) * SP_NF + q];
+    const int cr = sp_kre(c), ci = sp_kim(c), qr = sp_kre(q), qi = sp_kim(q);
+    const double gr = (double)Pf[cr * SP_NF + qr] + (double)Pf[ci * SP_NF + qi];
+    const double gi = (double)Pf[cr * SP_NF + qi] - (double)Pf[ci * SP_NF + qr];
     const double2 e = twd[(int)(((long long)f * m) % L)];        // e^{-i theta}: cos = e.x, sin(theta) = -e.y
     const double kap = (f == 0 || 2 * f == L) ? 1.0 : 2.0;
     acc += kap * (gr * e.x + gi * e.y);                           // Re((gr + i gi)(cos + i sin)) = gr cos - gi sin
@@ -973,7 +1129,7 @@ struct SpecState {
   __nv_bfloat16 *Bfh, *Bfl, *Bdh, *Bdl;  // staged weight spectra
   float* P;                              // wgrad accumulator [F][128][SP_NF]
   CUtensorMap mBfh, mBfl, mBdh, mBdl;
-  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv, fft_inv2, wgrad_stages, fft_bulk, fft_bulk_inv;
+  int fft_threads, fft_threads_generic, generic_only, grid_sms, fft_order, fft_order_inv, fft_inv2, wgrad_stages, fft_bulk, fft_bulk_inv, fft_2pass;
 };
 static size_t spec_fft_smem(int L, int G) { return (size_t)(L + 2 * (size_t)L * G) * sizeof(float2); }
 static constexpr int SPF_STAGES = 2, SPD_STAGES = 4;
@@ -1059,6 +1215,9 @@ static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st)
   s.generic_only = getenv("SNDVAE_FFT_GENERIC") ? 1 : 0;     // force the runtime-plan kernels (any N)
   s.fft_bulk = getenv("SNDVAE_FFT_BULK") ? atoi(getenv("SNDVAE_FFT_BULK")) : 1;      // measured: forward Y 5.67 -> 5.54 ms per 256 graphs
   s.fft_bulk_inv = getenv("SNDVAE_FFT_BULK_INV") ? atoi(getenv("SNDVAE_FFT_BULK_INV")) : 0;    // not measured yet (round 2)
+  // bit 0: forward, bit 1: inverse two-pass transforms (fft2p.cuh) where L = 384 / 192; measured per 256 graphs at N = 256 against the
+  // three-pass kernels: forward Y 5.20 -> 4.72 ms, inverse O 1.74 -> 1.34, forward dO 2.20 -> 2.25, inverse dY 4.53 -> 3.58
+  s.fft_2pass = getenv("SNDVAE_FFT_2PASS") ? atoi(getenv("SNDVAE_FFT_2PASS")) : 3;
   s.fft_inv2 = getenv("SNDVAE_FFT_INV2") ? atoi(getenv("SNDVAE_FFT_INV2")) : 1;
   s.wgrad_stages = getenv("SNDVAE_WGRAD_STAGES") ? atoi(getenv("SNDVAE_WGRAD_STAGES")) : SP_WSTAGES;
   if (s.wgrad_stages < 2 || s.wgrad_stages > SP_WSTAGES_MAX) s.wgrad_stages = SP_WSTAGES;
@@ -1109,6 +1268,28 @@ static int spec_launch_inv_fast2(SpecState& s, const FftInvArgs& a, cudaStream_t
   spec_fft_inv_fast2_k<R0, R1, R2, G, NT, MINB><<<(unsigned)(units < want ? units : want), NT, smem, st>>>(a);
   return 0;
 }
+template <int M, int G, int MINB, bool TABLE>
+static int spec_launch_fwd2(SpecState& s, const FftFwdArgs& a, cudaStream_t st) {
+  using Cfg = Fft2Cfg<M, G>;
+  const size_t smem = Cfg::smem_fwd(a.N);
+  if (smem > 226 * 1024 || a.N > 32 * M) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(spec_fft_fwd2_k<M, G, MINB, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
+  const long long want = (long long)s.grid_sms * MINB, units = a.order ? (a.lines + 1) / 2 : a.lines;
+  spec_fft_fwd2_k<M, G, MINB, TABLE><<<(unsigned)(units < want ? units : want), Cfg::NT, smem, st>>>(a);
+  return 0;
+}
+template <int M, int G, int MINB, bool TABLE>
+static int spec_launch_inv2(SpecState& s, const FftInvArgs& a, cudaStream_t st) {
+  using Cfg = Fft2Cfg<M, G>;
+  const size_t smem = Cfg::smem_inv();
+  if (smem > 226 * 1024 || a.N > 32 * M) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(spec_fft_inv2_k<M, G, MINB, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
+  const long long want = (long long)s.grid_sms * MINB, units = a.order ? (a.lines + 1) / 2 : a.lines;
+  spec_fft_inv2_k<M, G, MINB, TABLE><<<(unsigned)(units < want ? units : want), Cfg::NT, smem, st>>>(a);
+  return 0;
+}
 static bool spec_plan_is(const FftPlan& pl, int r0, int r1, int r2) {
   return pl.npass == (r2 ? 3 : 2) && pl.rad[0] == r0 && pl.rad[1] == r1 && (!r2 || pl.rad[2] == r2);
 }
@@ -1122,6 +1303,13 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
   if (a.order == 2 && (lines != 2 * lines0 || lines0 % s.N != 0)) a.order = 1;
   a.bulk = s.fft_bulk;
   int r = 1;
+  if (!s.generic_only && (s.fft_2pass & 1)) {      // twiddles from the table (measured: forward Y 5.32 -> 4.95 ms against the product chain)
+    if (s.pl.L == 384 && C == 50) r = spec_launch_fwd2<8, 25, 1, true>(s, a, st);
+    else if (s.pl.L == 384 && C == 20) r = spec_launch_fwd2<8, 10, 2, true>(s, a, st);      // (three CTAs per SM at 124 registers: 2.60 ms against 2.25)
+    else if (s.pl.L == 192 && C == 50) r = spec_launch_fwd2<4, 25, 1, true>(s, a, st);
+    else if (s.pl.L == 192 && C == 20) r = spec_launch_fwd2<4, 10, 2, true>(s, a, st);
+    if (r == 0) return tc_check_launch("spec_fft_fwd2_k");
+  }
   if (!s.generic_only) {
     if (spec_plan_is(s.pl, 6, 8, 8) && C == 50) r = s.fft_threads == 800 ? spec_launch_fwd_fast<6, 8, 8, 25, 800, 1>(s, a, st) : spec_launch_fwd_fast<6, 8, 8, 25, 400, 1>(s, a, st);
     else if (spec_plan_is(s.pl, 6, 8, 8) && C == 20) r = spec_launch_fwd_fast<6, 8, 8, 10, 320, 2>(s, a, st);
@@ -1141,6 +1329,13 @@ static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, 
   a.order = s.fft_order_inv >= 0 ? s.fft_order_inv : 0;      // measured: pairs do not help the inverse (its rows are read, not written)
   if (a.order == 2 && (lines != 2 * lines0 || lines0 % s.N != 0)) a.order = 1;
   int r = 1;
+  if (!s.generic_only && (s.fft_2pass & 2)) {      // twiddles by product chain (measured: inverse dY 3.70 ms against 3.77 with table reads)
+    if (s.pl.L == 384 && C == 50) r = spec_launch_inv2<8, 25, 1, false>(s, a, st);
+    else if (s.pl.L == 384 && C == 20) r = spec_launch_inv2<8, 10, 2, false>(s, a, st);
+    else if (s.pl.L == 192 && C == 50) r = spec_launch_inv2<4, 25, 1, false>(s, a, st);
+    else if (s.pl.L == 192 && C == 20) r = spec_launch_inv2<4, 10, 2, false>(s, a, st);
+    if (r == 0) return tc_check_launch("spec_fft_inv2_k");
+  }
   if (!s.generic_only && s.fft_inv2 && C == 50) {      // 3-pass plans at G = 25: split staging, extension fused into pass 1
     // (measured at N = 256: 4.88 -> 4.69 ms per 256 graphs; the G = 10 transforms, which have room for a separate staging
     // buffer anyway, lose 3 % with it and stay on the first form)

@@ -455,7 +455,7 @@ def test_fft_line_walk_orders_bit_identical(built, N, B, S, chunk):
         assert np.array_equal(out[name][0], out["default"][0]), name
         assert np.array_equal(out[name][1], out["default"][1]), name
         # the loss sums and the weight gradients go through atomics (order of addition is not fixed): tolerance, not bits
-        np.testing.assert_allclose(out[name][2], out["default"][2], rtol=1e-6)
+        np.testing.assert_allclose(out[name][2], out["default"][2], rtol=5e-6)
         for a, b in zip(out[name][3:], out["default"][3:]):
             assert _relmax(a, b) < 1e-5, name
 

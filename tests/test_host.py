@@ -210,3 +210,19 @@ def test_session_initializer_fetch_is_a_noop():
     with session.Session() as sess:
         assert sess.run(session.global_variables_initializer()) is None
         assert sess.run([session.global_variables_initializer()]) == [None]
+
+
+def test_fft2p_host(tmp_path):
+    """The two-pass transforms (snd-vae_b200/csrc/fft2p.cuh) are written as __host__ __device__ per-thread pieces; tests/fft2p_host.cu
+    runs the kernels' phases thread by thread on the CPU against a double-precision DFT: the register DFTs (16, pruned 24 / 12), the
+    paired radix-16 butterflies with the fused channel separation (every frequency <= L / 2 emitted), the Hermitian loads of the
+    inverse, at L = 384 and 192 with 25 and 10 channel pairs."""
+    import shutil, subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "fft2p_host")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-o", exe, os.path.join(root, "tests", "fft2p_host.cu")], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr

@@ -1,7 +1,8 @@
 """Turn the raw outputs of tools/final_profile.sh (gpurun_out/) into the tracked summaries under profiles/:
-   ncu_r1_final_b256.txt (ncu --set full, N^2-stage kernels), launches_r1_final_b256.txt (launch list of one step),
-   bench_r1_n256_b4096_1gpu_final.json (+ .stages.txt)."""
+   ncu_<tag>_final_b256.txt (ncu --set full, N^2-stage kernels), launches_<tag>_final_b256.txt (launch list of one step),
+   bench_<tag>_n256_b4096_1gpu_final.json (+ .stages.txt); <tag> = $PROFILE_TAG (default r2)."""
 import csv, os, re, shutil, subprocess, sys
+TAG = os.environ.get("PROFILE_TAG", "r2")          # round tag in the output file names
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 rows = list(csv.reader(open(os.path.join(G, "stage_full_raw.csv"))))
@@ -31,7 +32,7 @@ for r in rows[2:]:
         tt += t; tb += rd + wr
 out.append(f"# spectral e2e layer-1 stage (7 launches): {tt:.2f} ms, DRAM traffic {tb:.1f} GB = {tb / 256 * 1000:.0f} MB per graph "
            "(compulsory: 344.8 MB per graph, dO counted once)")
-open(os.path.join(P, "ncu_r1_final_b256.txt"), "w").write("\n".join(out) + "\n")
+open(os.path.join(P, f"ncu_{TAG}_final_b256.txt"), "w").write("\n".join(out) + "\n")
 print(out[-1])
 
 skip = int(sys.argv[1]) if len(sys.argv) > 1 else 310
@@ -42,7 +43,7 @@ st = sum(float(m.group(1)) for m in re.finditer(r"^(?:void )?spec_(?:fft|gemm_k|
 head = (f"# ncu --metrics gpu__time_duration.sum --clock-control none; second step (launches {skip}..) of: python bench.py --batch 256 --steps 1 "
         "--warmup 1 --no-cpu-baseline --no-e2e (N=256, one micro-batch of 256 graphs; per-launch times are cold-cache and serialised)\n")
 tail = f"# spectral e2e layer-1 stage (spec_fft_*, spec_gemm_*, spec_wgrad_k): {st:.3f} ms = {st / tot * 100:.1f}% of the launch-list time\n"
-open(os.path.join(P, "launches_r1_final_b256.txt"), "w").write(head + txt + tail)
+open(os.path.join(P, f"launches_{TAG}_final_b256.txt"), "w").write(head + txt + tail)
 print(tail.strip())
-shutil.copy(os.path.join(G, "bench_final.json"), os.path.join(P, "bench_r1_n256_b4096_1gpu_final.json"))
-shutil.copy(os.path.join(G, "bench_final.stages.txt"), os.path.join(P, "bench_r1_n256_b4096_1gpu_final.stages.txt"))
+shutil.copy(os.path.join(G, "bench_final.json"), os.path.join(P, f"bench_{TAG}_n256_b4096_1gpu_final.json"))
+shutil.copy(os.path.join(G, "bench_final.stages.txt"), os.path.join(P, f"bench_{TAG}_n256_b4096_1gpu_final.stages.txt"))
