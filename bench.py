@@ -478,9 +478,9 @@ def run_ours(args):
         except Exception:
             pass
         roofline = {
-            "bound": "hbm", "kernel": "e2e layer-1 spectral stage: spec_fft_fwd_fast_k, spec_gemm_k (fwd, dgrad), spec_fft_inv_fast_k, spec_wgrad_k",
+            "bound": "hbm", "kernel": "e2e layer-1 spectral stage: spec_fft_fwd2_k (Y, dO), spec_gemm_k (fwd, dgrad), spec_fft_inv2_k (O, dY), spec_wgrad_k",
             "achieved": ach_bw, "peak": peak_bw, "unit": "GB/s", "frac": (ach_bw / peak_bw) if ach_bw else None,
-            "traffic": (traffic["bytes_per_graph"] * B * K) if traffic else None,
+            "traffic": (traffic["bytes_per_graph"] * B * K) if traffic else None,      # per step, like gemm_ms_per_step
             "traffic_per_graph": traffic["bytes_per_graph"] if traffic else None,
             "traffic_source": traffic.get("source") if traffic else "no ncu capture kept for this N",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",

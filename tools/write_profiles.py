@@ -32,15 +32,26 @@ for r in rows[2:]:
         tt += t; tb += rd + wr
 out.append(f"# spectral e2e layer-1 stage (7 launches): {tt:.2f} ms, DRAM traffic {tb:.1f} GB = {tb / 256 * 1000:.0f} MB per graph "
            "(compulsory: 344.8 MB per graph, dO counted once)")
+import json
+tpath = os.path.join(P, "traffic.json")      # read by bench.py (roofline.traffic): measured DRAM bytes of the stage per graph, keyed by N
+try:
+    tj = json.load(open(tpath))
+except Exception:
+    tj = {}
+head_sha = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+tj["n256"] = {"bytes_per_graph": round(tb / 256 * 1e9), "stage_ms_per_256_graphs": round(tt, 3),
+              "source": f"profiles/ncu_{TAG}_final_b256.txt: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the stage's 7 launches "
+                        f"on a 256-graph micro-batch (tools/final_profile.sh at {head_sha})"}
+json.dump(tj, open(tpath, "w"), indent=1)
 open(os.path.join(P, f"ncu_{TAG}_final_b256.txt"), "w").write("\n".join(out) + "\n")
 print(out[-1])
 
-skip = int(sys.argv[1]) if len(sys.argv) > 1 else 310
+skip = int(sys.argv[1]) if len(sys.argv) > 1 else -1
 txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(G, "launches.csv"), str(skip), "45"],
                      capture_output=True, text=True).stdout
 tot = float(re.search(r"total ([\d.]+) ms", txt).group(1))
 st = sum(float(m.group(1)) for m in re.finditer(r"^(?:void )?spec_(?:fft|gemm_k|wgrad_k)[^\n]*ms=\s*([\d.]+)", txt, re.M))
-head = (f"# ncu --metrics gpu__time_duration.sum --clock-control none; second step (launches {skip}..) of: python bench.py --batch 256 --steps 1 "
+head = (f"# ncu --metrics gpu__time_duration.sum --clock-control none; second step (the launches between the first two tf_adam_k) of: python bench.py --batch 256 --steps 1 "
         "--warmup 1 --no-cpu-baseline --no-e2e (N=256, one micro-batch of 256 graphs; per-launch times are cold-cache and serialised)\n")
 tail = f"# spectral e2e layer-1 stage (spec_fft_*, spec_gemm_*, spec_wgrad_k): {st:.3f} ms = {st / tot * 100:.1f}% of the launch-list time\n"
 open(os.path.join(P, f"launches_{TAG}_final_b256.txt"), "w").write(head + txt + tail)
