@@ -622,12 +622,10 @@ struct SpecEmitFwd {                   // X1 / X2 of a frequency -> bf16 hi / lo
   __device__ __forceinline__ void operator()(int f, float2 x1, float2 x2) const {
     __nv_bfloat16* ph = oh + f * fstride; __nv_bfloat16* pl = ol + f * fstride;
     uint2 lo; const uint2 hi = sp_pack_hi_lo(x1.x, x2.x, x1.y, x2.y, lo);
+    *reinterpret_cast<uint2*>(ph) = hi; *reinterpret_cast<uint2*>(pl) = lo;
     // the row's pad is written too (a partly written sector costs a DRAM read-modify-write, see spec_fft_fwd_fast_k)
-    if (padw == 4) { *reinterpret_cast<uint4*>(ph) = make_uint4(hi.x, hi.y, 0u, 0u); *reinterpret_cast<uint4*>(pl) = make_uint4(lo.x, lo.y, 0u, 0u); }
-    else {
-      *reinterpret_cast<uint2*>(ph) = hi; *reinterpret_cast<uint2*>(pl) = lo;
-      for (int e = 0; e < padw; e += 2) { *reinterpret_cast<uint32_t*>(ph + 4 + e) = 0u; *reinterpret_cast<uint32_t*>(pl + 4 + e) = 0u; }
-    }
+    if (padw == 4) { *reinterpret_cast<uint2*>(ph + 4) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(pl + 4) = make_uint2(0u, 0u); }
+    else if (padw) for (int e = 0; e < padw; e += 2) { *reinterpret_cast<uint32_t*>(ph + 4 + e) = 0u; *reinterpret_cast<uint32_t*>(pl + 4 + e) = 0u; }
   }
 };
 template <int M, int G, int MINB, bool TABLE>
@@ -638,7 +636,7 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
   __shared__ float s_g[C], s_b[C], s_raw[2][C];
   __shared__ uint64_t stage_bar[2];          // completion of a contiguous line's bulk copy into staging tile 0 / 1
   if (threadIdx.x == 0) { mbar_init(&stage_bar[0], 1); mbar_init(&stage_bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  const int N = A.N;
+  const int N = A.N;                         // N C is a multiple of 4 (checked by the launcher): every line is whole 16-byte pieces
   float2* tw = reinterpret_cast<float2*>(fsm);
   float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
   float* stage0 = reinterpret_cast<float*>(fsm + (size_t)L * 8 + Cfg::BUF);
@@ -650,52 +648,53 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
   if (shifter) { sh_g = A.gam[threadIdx.x] * BN_RS; sh_c = fmaf(2.f * A.b0[threadIdx.x], sh_g, A.bet[threadIdx.x]); }
   __syncthreads();
   const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;
-  const bool vec16 = ((long long)N * C) % 4 == 0;
-  auto is_bulk = [&](long long line) { return A.bulk && vec16 && (line < A.lines0 || A.dir1_strided != 1); };
-  auto prefetch = [&](long long line, int slot) {
-    if (line >= A.lines) return;
-    float* stage = stage0 + slot * sstride;
-    if (shifter) cp_async4(&s_raw[slot][threadIdx.x], (line >= A.lines0 ? A.bias1 + (line - A.lines0) * C : A.bias0 + line * C) + threadIdx.x);
-    if (line < A.lines0 || A.dir1_strided != 1) {
-      const float* base = A.in + line * N * C;
-      if (A.dir1_strided == 2) {
-        const bool d1 = line >= A.lines0; const long long l1 = d1 ? line - A.lines0 : line; const long long b = l1 / N; const int x = (int)(l1 - b * N);
-        base = (d1 ? A.in1 : A.in) + (((b / 128) * N + x) * 128 + (b % 128)) * N * C;
-      }
-      if (A.bulk && vec16) { if (threadIdx.x == 0) { mbar_expect_tx(&stage_bar[slot], (uint32_t)(N * C * 4)); bulk_load(stage, base, (uint32_t)(N * C * 4), &stage_bar[slot]); } }
-      else if (vec16) { for (int t = threadIdx.x; t < N * C / 4; t += NT) cp_async16(stage + 4 * t, base + 4 * t); }
-      else { for (int t = threadIdx.x; t < N * G; t += NT) cp_async8(stage + 2 * t, base + 2 * t); }
-    } else {
-      const long long l1 = line - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
-      const float* base = A.in + (b * N * N + j) * C; const long long ps = (long long)N * C;
-      if constexpr (G % 2 == 0) {
-        constexpr int Q = G / 2;
-        for (int t = threadIdx.x; t < N * Q; t += NT) { const int pos = t / Q, k = t - pos * Q; cp_async16(stage + pos * C + 4 * k, base + pos * ps + 4 * k); }
-      } else {
-        for (int pos = jb; pos < N; pos += 16) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
-      }
-    }
-  };
   LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = N; walk.order = A.order;
-  long long line = walk.at(0), line1 = walk.at(1);
-  prefetch(line, 0); cp_async_commit();
-  prefetch(line1, 1); cp_async_commit();
   uint32_t phases = 0;
   const int padw = cp == G - 1 ? A.KA - 2 * C : 0;
   const long long fstride = A.RA * A.KA;
-  for (long long it = 0; line < A.lines; ++it) {
+  // One loop body for the pipeline's prologue and steady state (the code is long; a second copy of it costs instruction-cache
+  // misses): iteration `it` transforms line it (when it >= 0) and, between its two passes, starts the copy of line it + 2 into the
+  // staging tile that pass 1 has just freed.  Iterations -2 and -1 only start the copies of lines 0 and 1.
+  long long line = -1, line1 = -1;           // lines it and it + 1 (line = -1: nothing to transform yet)
+  for (long long it = -2;; ++it) {
     const int slot = (int)(it & 1);
     const long long line2 = walk.at(it + 2);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");       // this line's per-thread copies have landed (the next line's may be in flight)
-    if (is_bulk(line)) { mbar_wait(&stage_bar[slot], (phases >> slot) & 1u); phases ^= 1u << slot; }
-    if (shifter) s_b[threadIdx.x] = fmaf(s_raw[slot][threadIdx.x], sh_g, sh_c);
-    __syncthreads();                       // staged line and shift visible; the previous line's pass 2 is done with bufA
-    FpBn bn; bn.on = A.gam != nullptr; bn.gx = bn.gy = 1.f; bn.bx = bn.by = 0.f;
-    if (bn.on) { bn.gx = s_g[2 * cp]; bn.gy = s_g[2 * cp + 1]; bn.bx = s_b[2 * cp]; bn.by = s_b[2 * cp + 1]; }
-    fp_fwd_pass1<M, G>(reinterpret_cast<const float2*>(stage0 + slot * sstride), bufA, jb, cp, N, bn);
-    __syncthreads();                       // bufA complete; this staging tile is free
-    prefetch(line2, slot); cp_async_commit();
-    if (jb <= R0 / 2) {
+    if (it >= 0) {
+      if (line >= A.lines) break;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");       // this line's per-thread copies have landed (the next line's may be in flight)
+      if (A.bulk && (line < A.lines0 || A.dir1_strided != 1)) { mbar_wait(&stage_bar[slot], (phases >> slot) & 1u); phases ^= 1u << slot; }
+      if (shifter) s_b[threadIdx.x] = fmaf(s_raw[slot][threadIdx.x], sh_g, sh_c);
+      __syncthreads();                       // staged line and shift visible; the previous line's pass 2 is done with bufA
+      FpBn bn; bn.on = A.gam != nullptr; bn.gx = bn.gy = 1.f; bn.bx = bn.by = 0.f;
+      if (bn.on) { bn.gx = s_g[2 * cp]; bn.gy = s_g[2 * cp + 1]; bn.bx = s_b[2 * cp]; bn.by = s_b[2 * cp + 1]; }
+      fp_fwd_pass1<M, G>(reinterpret_cast<const float2*>(stage0 + slot * sstride), bufA, jb, cp, N, bn);
+      __syncthreads();                       // bufA complete; this staging tile is free
+    }
+    if (line2 < A.lines) {                   // prefetch line it + 2
+      float* stage = stage0 + slot * sstride;
+      if (shifter) cp_async4(&s_raw[slot][threadIdx.x], (line2 >= A.lines0 ? A.bias1 + (line2 - A.lines0) * C : A.bias0 + line2 * C) + threadIdx.x);
+      if (line2 < A.lines0 || A.dir1_strided != 1) {
+        const float* base = A.in + line2 * N * C;
+        if (A.dir1_strided == 2) {
+          const bool d1 = line2 >= A.lines0; const long long l1 = d1 ? line2 - A.lines0 : line2; const long long b = l1 / N; const int x = (int)(l1 - b * N);
+          base = (d1 ? A.in1 : A.in) + (((b / 128) * N + x) * 128 + (b % 128)) * N * C;
+        }
+        // a contiguous line is ONE bulk copy issued by one thread (no LDGSTS instructions); the others wait on the mbarrier's phase
+        if (A.bulk) { if (threadIdx.x == 0) { mbar_expect_tx(&stage_bar[slot], (uint32_t)(N * C * 4)); bulk_load(stage, base, (uint32_t)(N * C * 4), &stage_bar[slot]); } }
+        else { for (int t = threadIdx.x; t < N * C / 4; t += NT) cp_async16(stage + 4 * t, base + 4 * t); }
+      } else {                               // column line of a [b, N, N, C] tensor: one C-float piece per position
+        const long long l1 = line2 - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
+        const float* base = A.in + (b * N * N + j) * C; const long long ps = (long long)N * C;
+        if constexpr (G % 2 == 0) {
+          constexpr int Q = G / 2;
+          for (int t = threadIdx.x; t < N * Q; t += NT) { const int pos = t / Q, k = t - pos * Q; cp_async16(stage + pos * C + 4 * k, base + pos * ps + 4 * k); }
+        } else {
+          for (int pos = jb; pos < N; pos += 16) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
+        }
+      }
+    }
+    cp_async_commit();
+    if (it >= 0 && jb <= R0 / 2) {
       SpecEmitFwd em; em.oh = A.oh + line * A.KA + 4 * cp; em.ol = A.ol + line * A.KA + 4 * cp; em.fstride = fstride; em.C = C; em.padw = padw;
       fp_fwd_pass2<M, G, TABLE>(bufA, tw, jb, cp, em);
     }
@@ -1272,7 +1271,7 @@ template <int M, int G, int MINB, bool TABLE>
 static int spec_launch_fwd2(SpecState& s, const FftFwdArgs& a, cudaStream_t st) {
   using Cfg = Fft2Cfg<M, G>;
   const size_t smem = Cfg::smem_fwd(a.N);
-  if (smem > 226 * 1024 || a.N > 32 * M) return 1;
+  if (smem > 226 * 1024 || a.N > 32 * M || ((long long)a.N * 2 * G) % 4 != 0) return 1;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(spec_fft_fwd2_k<M, G, MINB, TABLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
   const long long want = (long long)s.grid_sms * MINB, units = a.order ? (a.lines + 1) / 2 : a.lines;
