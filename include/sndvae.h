@@ -69,8 +69,11 @@ typedef struct sndvae_config {
    *   SNDVAE_LOSS_DIP       'NED-VAE-IP':             mse + kl + beta sum_latents DIP(z_mean, lambda_od, lambda_d)  (optimizer.py:7-21,183)
    *   SNDVAE_LOSS_TC        'beta-TCVAE':             mse + beta kl + 10 sum_latents TC(z, z_mean, z_std): the minibatch
    *                          total-correlation estimate over all pairs of rows (optimizer.py:23-63,185-190); latent sizes <= 128
-   * DIP and TC are statistics of the batch the handle sees (per rank under data parallelism; their gradients are
-   * weighted batch_size / global_batch so that the all-reduced sum is the mean over ranks). */
+   * DIP: with a communicator (sndvae_comm_init) the second-moment sums of the posterior means are all-reduced, so the
+   * covariance is the GLOBAL batch's (optimizer.py:7-21 couples every sample of the batch) and the 2-GPU step equals the
+   * 1-GPU step on the concatenated batch (tests/test_multigpu.py).  TC is a statistic of the batch the handle sees (per rank
+   * under data parallelism; its gradient is weighted batch_size / global_batch so that the all-reduced sum is the mean
+   * over ranks). */
   int32_t loss_variant;
   float   gamma, C_max, C_stop_iter, C_step;  /* main.py:95-98 */
   float   dip_lambda_od, dip_lambda_d;        /* 10, 100 (optimizer.py:183) */

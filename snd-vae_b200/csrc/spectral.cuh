@@ -1210,7 +1210,9 @@ static int spec_init(SpecState& s, int N, long long rows_alloc, cudaStream_t st)
   cudaFuncSetAttribute(spec_gemm_k<SP_ND, 3, 1, 100, SPD_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spec_gemm_smem(SP_ND, 1, 100, SPD_STAGES));
   cudaFuncSetAttribute(spec_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_WGRAD_SMEM);
   s.fft_threads = getenv("SNDVAE_FFT_THREADS") ? atoi(getenv("SNDVAE_FFT_THREADS")) : 400;
-  s.fft_threads_generic = L == 384 ? 400 : 256;
+  s.fft_threads_generic = L == 384 ? 400 : (L >= 768 ? 512 : 256);      // measured at N = 1024 (L = 1536): 512 threads 186 graphs/s, 256 threads 167
+  if (getenv("SNDVAE_FFT_THREADS_GENERIC")) { const int t = atoi(getenv("SNDVAE_FFT_THREADS_GENERIC")); if (t >= 64 && t <= SP_FFT_THREADS_MAX) s.fft_threads_generic = t; }
+  if (getenv("SNDVAE_FFT_G")) { const int g = atoi(getenv("SNDVAE_FFT_G")); if (g >= 1 && g <= s.G1) s.G1 = g; if (g >= 1 && g <= s.G2) s.G2 = g; }
   s.generic_only = getenv("SNDVAE_FFT_GENERIC") ? 1 : 0;     // force the runtime-plan kernels (any N)
   s.fft_bulk = getenv("SNDVAE_FFT_BULK") ? atoi(getenv("SNDVAE_FFT_BULK")) : 1;      // measured: forward Y 5.67 -> 5.54 ms per 256 graphs
   s.fft_bulk_inv = getenv("SNDVAE_FFT_BULK_INV") ? atoi(getenv("SNDVAE_FFT_BULK_INV")) : 0;    // not measured yet (round 2)

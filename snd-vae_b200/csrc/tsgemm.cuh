@@ -10,7 +10,7 @@
 //  * Operands stay fp32 in HBM.  Producer warps read the tile with coalesced loads (along whichever index is contiguous in
 //    memory -- a transposed operand is transposed by the index math of the loader, not by a copy), split every value into
 //    three bf16 planes  x = hi + mid + lo  (24 mantissa bits: the split is exact up to fp32 rounding) and write the K-major,
-//    un-swizzled canonical UMMA tiles (8 x 16-byte core matrices) by hand.
+//    SWIZZLE_64B UMMA tiles (rows of 32 bf16, 16-byte groups XOR-ed with the row pair) by hand.
 //  * One thread issues the six products of total order <= 2  (hi.hi, hi.mid, mid.hi, hi.lo, lo.hi, mid.mid)  as tcgen05.mma
 //    kind::f16, M = 128, N <= 128, fp32 accumulation in TMEM: the dropped terms are <= 2^-24 of |a||b|, i.e. the result is an
 //    fp32-grade product (weight gradients are cancelling sums over millions of rows -- a 3-pass bf16 split, 2^-17 per term,
@@ -32,6 +32,8 @@
 #define TG_GROUP 8       /* K chunks per accumulation group: 96 tcgen05.mma accumulates */
 #define TG_PROD 128      /* tsgemm_k: producer threads (warps 0..3); warp 4 issues the MMAs; warps 5..8 are the epilogue */
 #define TG_THREADS (TG_PROD + 32 + 128 + 32)    /* + warp 9: bulk-copy loader of the slab form */
+#define TG_PROD_SLAB 256 /* slab form: eight producer warps */
+#define TG_THREADS_SLAB (TG_PROD_SLAB + 32 + 128 + 32)
 #define TG_RAW 4          /* raw fp32 slab ring of the slab form */
 #define TG_APLANE (TG_BM * TG_BK * 2)      /* one bf16 plane of an A chunk: 8 KB */
 #define TT_SMEM_MAX (225 * 1024)           /* dynamic shared memory limit (227 KB per CTA minus the static part) */
@@ -210,7 +212,11 @@ __device__ __forceinline__ void tg_issue_chunk(uint32_t td, uint32_t sa, uint32_
 // in memory, so warp 9 streams raw fp32 slabs into a ring with one cp.async.bulk each (TG_RAW chunks in flight, no registers
 // tied up) and the producer warps transpose / split from shared memory instead of from global.
 template <int BNMAX, bool GROUPED, bool SLAB>
-__global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) tsgemm_k(TgArgs P) {
+__global__ void __launch_bounds__(SLAB ? TG_THREADS_SLAB : TG_THREADS, (SLAB || (GROUPED && BNMAX > 64)) ? 1 : 2) tsgemm_k(TgArgs P) {
+  // warp roles: [0, PW) producers, PW issues the MMAs, PW + 1 .. PW + 4 epilogue (PW is a multiple of 4, so warp & 3 is still the
+  // TMEM lane quarter), PW + 5 the slab loader.  The slab form is one CTA per SM (its raw ring fills the shared memory), so it
+  // carries twice the producer warps: with four, the fp32 -> three-plane conversion of a chunk bounded it at ~1.2 TB/s.
+  constexpr int PROD = SLAB ? TG_PROD_SLAB : TG_PROD, PW = PROD / 32;
   constexpr int STAGES = SLAB ? 2 : ((BNMAX <= 64 || GROUPED) ? 3 : 2);
   constexpr int B_PLANE = BNMAX * TG_BK * 2;
   constexpr int STAGE_BYTES = TG_NP * (TG_APLANE + B_PLANE);
@@ -234,18 +240,18 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
   const int ngroups = (nk + TG_GROUP - 1) / TG_GROUP;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], TG_PROD / 32); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], PW); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-    for (int s = 0; s < TG_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], TG_PROD / 32); }
+    for (int s = 0; s < TG_RAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], PW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(&tmem_base_s, TMEM_COLS);
+  if (warp == PW) tmem_alloc(&tmem_base_s, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_s;
 
-  if (SLAB && warp == 9) {
+  if (SLAB && warp == PW + 5) {
     if (lane == 0) {
       int rc = 0;
       for (int it = 0; it < nk; ++it) {
@@ -260,9 +266,9 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
         ++rc;
       }
     }
-  } else if (SLAB && warp < 4) {
+  } else if (SLAB && warp < PW) {
     const int t = threadIdx.x;
-    constexpr int NA = TG_BM * 4 / TG_PROD, NB = BNMAX * 4 / TG_PROD;
+    constexpr int NA = TG_BM * 4 / PROD, NB = (BNMAX * 4 + PROD - 1) / PROD;
     int rc = 0;
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
       uint8_t* st = tg_smem + (size_t)s * STAGE_BYTES;
 #pragma unroll
       for (int q = 0; q < NA; ++q) {
-        const int idx = t + q * TG_PROD, row = idx & (TG_BM - 1), g = idx >> 7;
+        const int idx = t + q * PROD, row = idx & (TG_BM - 1), g = idx >> 7;
         if (m0 + row >= P.M) continue;           // rows past M only feed output rows that are never stored: left as they are
         float v[8];
         if (partial) tg_load_item(P.A, 1, P.lda, m0 + row, P.M, k0 + 8 * g, P.K, false, v);
@@ -287,7 +293,7 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
       }
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        const int idx = t + q * TG_PROD;
+        const int idx = t + q * PROD;
         if (idx < bnc * 4) {
           const int g = idx / bnc, row = idx - g * bnc;
           if (n0 + row >= P.N) continue;         // likewise: columns past N are never stored
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
       if (lane == 0) { mbar_arrive(&full_bar[s]); if (!partial) mbar_arrive(&raw_empty[rs]); }
       if (!partial) ++rc;
     }
-  } else if (warp < 4) {
+  } else if (warp < PW) {
     // ---- producers: global fp32 -> bf16 planes in canonical tiles ----
     const int t = threadIdx.x;
     const bool a_vec = (P.a_ks == 1) && (P.a_rs % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.A) & 15) == 0);
@@ -313,20 +319,20 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
     // item (row, g) of thread t: K-contiguous operands give 4 neighbouring threads one row's 128 bytes; row-contiguous
     // (transposed) operands give a warp 32 neighbouring rows per K value.  Every load of the chunk is issued before the first
     // conversion (and before the wait for the stage), so that a thread has 48 - 64 values in flight.
-    constexpr int NA = TG_BM * 4 / TG_PROD, NB = BNMAX * 4 / TG_PROD;
+    constexpr int NA = TG_BM * 4 / PROD, NB = (BNMAX * 4 + PROD - 1) / PROD;
     for (int it = 0; it < nk; ++it) {
       const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
       const int k0 = (c_lo + it) * TG_BK;
       float va[NA][8], vb[NB][8];
 #pragma unroll
       for (int q = 0; q < NA; ++q) {
-        const int idx = t + q * TG_PROD;
+        const int idx = t + q * PROD;
         const int row = P.a_ks == 1 ? idx >> 2 : idx & (TG_BM - 1), g = P.a_ks == 1 ? idx & 3 : idx >> 7;
         tg_load_item(P.A, P.a_rs, P.a_ks, m0 + row, P.M, k0 + 8 * g, P.K, a_vec, va[q]);
       }
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        const int idx = t + q * TG_PROD;
+        const int idx = t + q * PROD;
         if (idx < bnc * 4) {
           const int g = P.b_ks == 1 ? idx & 3 : idx / bnc, row = P.b_ks == 1 ? idx >> 2 : idx - g * bnc;
           tg_load_item(P.B, P.b_ns, P.b_ks, n0 + row, P.N, k0 + 8 * g, P.K, b_vec, vb[q]);
@@ -337,13 +343,13 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
       uint8_t* st = tg_smem + (size_t)s * STAGE_BYTES;
 #pragma unroll
       for (int q = 0; q < NA; ++q) {
-        const int idx = t + q * TG_PROD;
+        const int idx = t + q * PROD;
         const int row = P.a_ks == 1 ? idx >> 2 : idx & (TG_BM - 1), g = P.a_ks == 1 ? idx & 3 : idx >> 7;
         tg_store_item(va[q], st, TG_APLANE, row, g);
       }
 #pragma unroll
       for (int q = 0; q < NB; ++q) {
-        const int idx = t + q * TG_PROD;
+        const int idx = t + q * PROD;
         if (idx < bnc * 4) {
           const int g = P.b_ks == 1 ? idx & 3 : idx / bnc, row = P.b_ks == 1 ? idx >> 2 : idx - g * bnc;
           tg_store_item(vb[q], st + TG_NP * TG_APLANE, B_PLANE, row, g);
@@ -353,9 +359,9 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);                        // one arrival per producer warp
     }
-  } else if (warp == 9) {
+  } else if (warp == PW + 5) {
     // (idle in the plain form)
-  } else if (warp == 4) {
+  } else if (warp == PW) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(TG_BM, bnc, 0, 0);
       const uint64_t dz = TG_DESC_ZERO;
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(TG_THREADS, (GROUPED && BNMAX > 64) ? 1 : 2) t
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_d, TMEM_COLS); }
+  if (warp == PW) { tc_fence_after(); tmem_dealloc(tmem_d, TMEM_COLS); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -688,7 +694,7 @@ static cudaError_t tg_launch_t(const TgArgs& a, dim3 grid, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  tsgemm_k<BNMAX, GROUPED, SLAB><<<grid, TG_THREADS, smem, st>>>(a);
+  tsgemm_k<BNMAX, GROUPED, SLAB><<<grid, SLAB ? TG_THREADS_SLAB : TG_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <int BNMAX>
