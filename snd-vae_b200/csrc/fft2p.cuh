@@ -149,15 +149,16 @@ template <int R, bool TABLE> FP_HD void fp_twiddle(float2* v, const float2* tw, 
 // ======================================================================================================================
 struct FpBn { bool on; float gx, gy, bx, by; };          // x <- relu(x * g + b) for the thread's two channels
 
-// pass 1: butterfly jb of the radix-3M pass (Ns = 1): inputs at positions jb + 16 r (r < 2M), outputs at 3M jb + r (r < 3M)
-template <int M, int G> FP_HD void fp_fwd_pass1(const float2* stage, float2* bufA, int jb, int cp, int N, const FpBn& bn) {
+// pass 1: butterfly jb (< T0) of the radix-3M pass (Ns = 1): inputs at positions jb + T0 r (r < 2M), outputs at 3M jb + r (r < 3M).
+// T0 = L / (3M): 16 in the two-pass plans, 64 in the three-pass plan of L = 1536.
+template <int M, int G, int T0> FP_HD void fp_fwd_pass1_t(const float2* stage, float2* bufA, int jb, int cp, int N, const FpBn& bn) {
   float2 v[3 * M];
   const float2* s = stage + jb * G + cp;
 #pragma unroll
   for (int r = 0; r < 2 * M; ++r) {
     float2 x = fp_mk(0.f, 0.f);
-    if (jb + 16 * r < N) {
-      x = s[16 * r * G];
+    if (jb + T0 * r < N) {
+      x = s[T0 * r * G];
       if (bn.on) { x.x = fmaxf(fmaf(x.x, bn.gx, bn.bx), 0.f); x.y = fmaxf(fmaf(x.y, bn.gy, bn.by), 0.f); }
     }
     v[r] = x;
@@ -167,42 +168,64 @@ template <int M, int G> FP_HD void fp_fwd_pass1(const float2* stage, float2* buf
 #pragma unroll
   for (int r = 0; r < 3 * M; ++r) o[r * G] = v[r];
 }
-// one radix-16 butterfly k (< 3M) of pass 2 (Ns = 3M): inputs bufA[k + 3M r] * tw[r k], outputs (left in v) are the
-// spectrum points f = k + 3M r
-template <int M, int G, bool TABLE> FP_HD void fp_fwd_bfly16(const float2* bufA, const float2* tw, int k, int cp, float2* v) {
-  const float2* s = bufA + k * G + cp;
-#pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = s[3 * M * r * G];
-  fp_twiddle<16, TABLE>(v, tw, k);
-  fp_dft16(v);
+template <int M, int G> FP_HD void fp_fwd_pass1(const float2* stage, float2* bufA, int jb, int cp, int N, const FpBn& bn) {
+  fp_fwd_pass1_t<M, G, 16>(stage, bufA, jb, cp, N, bn);
 }
-// pass 2 of unit u (u <= 3M / 2): butterflies kA = u and kB = 3M - u, channel separation of the pairs (f, L - f), and
+template <int R> FP_HD void fp_dftR(float2* v) { if (R == 16) fp_dft16(v); else fp_dft8(v); }
+// one radix-R butterfly k (< NS) of the last pass (Ns = NS, L = R NS): inputs buf[k + NS r] * tw[r k], outputs (left in v) are
+// the spectrum points f = k + NS r
+template <int R, int NS, int G, bool TABLE> FP_HD void fp_fwd_bfly_t(const float2* buf, const float2* tw, int k, int cp, float2* v) {
+  const float2* s = buf + k * G + cp;
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = s[NS * r * G];
+  fp_twiddle<R, TABLE>(v, tw, k);
+  fp_dftR<R>(v);
+}
+// last pass of unit u (u <= NS / 2): butterflies kA = u and kB = NS - u, channel separation of the pairs (f, L - f), and
 // emit(f, X1, X2) for each of the unit's frequencies f <= L / 2, where X1 / X2 are the spectra of the pair's two real channels
 //   X1 = (Z[f] + conj Z[L - f]) / 2,   X2 = (Z[f] - conj Z[L - f]) / (2 i)
-template <int M, int G, bool TABLE, class Emit> FP_HD void fp_fwd_pass2(const float2* bufA, const float2* tw, int u, int cp, Emit& emit) {
-  constexpr int R0 = 3 * M;
-  const bool pair = (u != 0) && (2 * u != R0);
-  float2 a[16], b[16];
-  fp_fwd_bfly16<M, G, TABLE>(bufA, tw, u, cp, a);
-  if (pair) fp_fwd_bfly16<M, G, TABLE>(bufA, tw, R0 - u, cp, b);
+// (R = 16, NS = 3M in the two-pass plans; R = 8, NS = 192 in the three-pass plan of L = 1536)
+template <int R, int NS, int G, bool TABLE, class Emit> FP_HD void fp_fwd_last_t(const float2* buf, const float2* tw, int u, int cp, Emit& emit) {
+  const bool pair = (u != 0) && (2 * u != NS);
+  float2 a[R], b[R];
+  fp_fwd_bfly_t<R, NS, G, TABLE>(buf, tw, u, cp, a);
+  if (pair) fp_fwd_bfly_t<R, NS, G, TABLE>(buf, tw, NS - u, cp, b);
   else {
-    // self-paired butterflies: u = 3M / 2 mirrors onto itself (b = a); u = 0 onto itself shifted by one output (L - 3M r = 3M (16 - r))
+    // self-paired butterflies: u = NS / 2 mirrors onto itself (b = a); u = 0 onto itself shifted by one output (L - NS r = NS (R - r))
 #pragma unroll
-    for (int r = 0; r < 16; ++r) b[r] = (u == 0) ? a[(r + 1) & 15] : a[r];
+    for (int r = 0; r < R; ++r) b[r] = (u == 0) ? a[(r + 1) & (R - 1)] : a[r];
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {                       // f = u + 3M r  <->  L - f = (3M - u) + 3M (15 - r)
-    const float2 z1 = a[r], z2 = b[15 - r];
-    emit(u + R0 * r, fp_mk(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y)), fp_mk(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x)));
+  for (int r = 0; r < R / 2; ++r) {                   // f = u + NS r  <->  L - f = (NS - u) + NS (R - 1 - r)
+    const float2 z1 = a[r], z2 = b[R - 1 - r];
+    emit(u + NS * r, fp_mk(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y)), fp_mk(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x)));
   }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {                       // f = (3M - u) + 3M r  <->  L - f = u + 3M (15 - r)
-    // self-paired units would repeat the frequencies above, except f = L / 2 (u = 0, r = 7)
-    if (pair || (u == 0 && r == 7)) {
-      const float2 z1 = b[r], z2 = a[15 - r];
-      emit(R0 - u + R0 * r, fp_mk(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y)), fp_mk(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x)));
+  for (int r = 0; r < R / 2; ++r) {                   // f = (NS - u) + NS r  <->  L - f = u + NS (R - 1 - r)
+    // self-paired units would repeat the frequencies above, except f = L / 2 (u = 0, r = R / 2 - 1)
+    if (pair || (u == 0 && r == R / 2 - 1)) {
+      const float2 z1 = b[r], z2 = a[R - 1 - r];
+      emit(NS - u + NS * r, fp_mk(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y)), fp_mk(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x)));
     }
   }
+}
+template <int M, int G, bool TABLE, class Emit> FP_HD void fp_fwd_pass2(const float2* bufA, const float2* tw, int u, int cp, Emit& emit) {
+  fp_fwd_last_t<16, 3 * M, G, TABLE>(bufA, tw, u, cp, emit);
+}
+// middle pass of the three-pass plans: radix-8 butterfly j (< T = L / 8) of a pass with Ns = NS; TS = L / (8 NS)
+//   v[r] = in[j + T r] * tw[r k TS],  k = j mod NS;  out[(j - k) 8 + k + NS r] = DFT_8(v)[r]
+template <int G, int NS, int T, int TS> FP_HD void fp_mid8(const float2* in, float2* out, const float2* tw, int j, int cp) {
+  const int k = j % NS;
+  float2 v[8];
+  const float2* s = in + j * G + cp;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) v[r] = s[T * r * G];
+#pragma unroll
+  for (int r = 1; r < 8; ++r) v[r] = fp_mul(v[r], tw[r * k * TS]);
+  fp_dft8(v);
+  float2* o = out + ((j - k) * 8 + k) * G + cp;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) o[NS * r * G] = v[r];
 }
 
 // ======================================================================================================================
@@ -211,46 +234,49 @@ template <int M, int G, bool TABLE, class Emit> FP_HD void fp_fwd_pass2(const fl
 // below run on the swapped values and the final store swaps back (and scales by 1 / L).
 // ======================================================================================================================
 // swapped Z[f] and swapped Z[L - f] from row f of the staged spectrum (pair cp: one 16-byte read): a = (re X1, re X2), b = (im X1, im X2)
-template <int M, int G> FP_HD void fp_inv_load(const float* stage, int f, int cp, float2& direct, float2& mirror) {
+template <int LH, int G> FP_HD void fp_inv_load(const float* stage, int f, int cp, float2& direct, float2& mirror) {
   const float4 ab = *reinterpret_cast<const float4*>(stage + f * (4 * G) + 4 * cp);
   const float2 a = fp_mk(ab.x, ab.y);
   float2 b = fp_mk(ab.z, ab.w);
-  if (f == 0 || f == 24 * M) b = fp_mk(0.f, 0.f);        // the imaginary parts of the self-conjugate frequencies do not enter
+  if (f == 0 || f == LH) b = fp_mk(0.f, 0.f);            // the imaginary parts of the self-conjugate frequencies (0, L / 2) do not enter
   direct = fp_mk(b.x + a.y, a.x - b.y);
   mirror = fp_mk(a.y - b.x, a.x + b.y);
 }
-// pass 1 of unit u (u <= 3M / 2): radix-16 butterflies jA = u and jB = 3M - u (Ns = 1, no twiddles).  Butterfly j reads the
-// positions j + 3M r; L - (u + 3M r) = (3M - u) + 3M (15 - r), so the rows f = u + 3M r and f = (3M - u) + 3M r (r < 8, all
-// <= L / 2) give every input of both.  Outputs at 16 j + r.
-template <int M, int G> FP_HD void fp_inv_pass1(const float* stage, float2* bufA, int u, int cp) {
-  constexpr int R1 = 3 * M;
-  const bool pair = (u != 0) && (2 * u != R1);
-  float2 a[16], b[16];
+// first pass of unit u (u <= T / 2): radix-R butterflies jA = u and jB = T - u (Ns = 1, no twiddles; L = R T).  Butterfly j reads
+// the positions j + T r; L - (u + T r) = (T - u) + T (R - 1 - r), so the rows f = u + T r and f = (T - u) + T r (r < R / 2, all
+// <= L / 2) give every input of both.  Outputs at R j + r.  (R = 16, T = 3M two-pass; R = 8, T = 192 three-pass L = 1536)
+template <int R, int T, int G> FP_HD void fp_inv_first_t(const float* stage, float2* bufA, int u, int cp) {
+  const bool pair = (u != 0) && (2 * u != T);
+  float2 a[R], b[R];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) fp_inv_load<M, G>(stage, u + R1 * r, cp, a[r], b[15 - r]);
+  for (int r = 0; r < R / 2; ++r) fp_inv_load<R * T / 2, G>(stage, u + T * r, cp, a[r], b[R - 1 - r]);
 #pragma unroll
-  for (int r = 0; r < 8; ++r) fp_inv_load<M, G>(stage, R1 - u + R1 * r, cp, b[r], a[15 - r]);
-  // (u = 3M / 2: both loops read the same rows and b = a; u = 0: the second loop reads the rows 3M (r + 1), b is a shifted by one)
-  fp_dft16(a);
-  float2* o = bufA + (16 * u) * G + cp;
+  for (int r = 0; r < R / 2; ++r) fp_inv_load<R * T / 2, G>(stage, T - u + T * r, cp, b[r], a[R - 1 - r]);
+  // (u = T / 2: both loops read the same rows and b = a; u = 0: the second loop reads the rows T (r + 1), b is a shifted by one)
+  fp_dftR<R>(a);
+  float2* o = bufA + (R * u) * G + cp;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) o[r * G] = a[r];
+  for (int r = 0; r < R; ++r) o[r * G] = a[r];
   if (pair) {
-    fp_dft16(b);
-    float2* o2 = bufA + (16 * (R1 - u)) * G + cp;
+    fp_dftR<R>(b);
+    float2* o2 = bufA + (R * (T - u)) * G + cp;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) o2[r * G] = b[r];
+    for (int r = 0; r < R; ++r) o2[r * G] = b[r];
   }
 }
-// pass 2: butterfly k (< 16) of the radix-3M pass (Ns = 16): inputs bufA[k + 16 r] * tw[r k] (r < 3M), outputs at the
-// positions k + 16 r (r < 2M; the others are >= 32 M >= N): emit(pos, value) with the value still swapped and unscaled
-template <int M, int G, bool TABLE, class Emit> FP_HD void fp_inv_pass2(const float2* bufA, const float2* tw, int k, int cp, Emit& emit) {
+template <int M, int G> FP_HD void fp_inv_pass1(const float* stage, float2* bufA, int u, int cp) { fp_inv_first_t<16, 3 * M, G>(stage, bufA, u, cp); }
+// last pass: butterfly k (< T1) of the radix-3M pass (Ns = T1 = L / (3M)): inputs buf[k + T1 r] * tw[r k] (r < 3M), outputs at the
+// positions k + T1 r (r < 2M; the others are >= 2M T1 >= N): emit(pos, value) with the value still swapped and unscaled
+template <int M, int G, int T1, bool TABLE, class Emit> FP_HD void fp_inv_last_t(const float2* buf, const float2* tw, int k, int cp, Emit& emit) {
   float2 v[3 * M];
-  const float2* s = bufA + k * G + cp;
+  const float2* s = buf + k * G + cp;
 #pragma unroll
-  for (int r = 0; r < 3 * M; ++r) v[r] = s[16 * r * G];
+  for (int r = 0; r < 3 * M; ++r) v[r] = s[T1 * r * G];
   fp_twiddle<3 * M, TABLE>(v, tw, k);
   fp_dft3M_out2M<M>(v);
 #pragma unroll
-  for (int r = 0; r < 2 * M; ++r) emit(k + 16 * r, v[r]);
+  for (int r = 0; r < 2 * M; ++r) emit(k + T1 * r, v[r]);
+}
+template <int M, int G, bool TABLE, class Emit> FP_HD void fp_inv_pass2(const float2* bufA, const float2* tw, int k, int cp, Emit& emit) {
+  fp_inv_last_t<M, G, 16, TABLE>(bufA, tw, k, cp, emit);
 }

@@ -757,6 +757,139 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_inv2_k(FftInvArgs A) {
   cp_async_wait_all();
 }
 
+// ---- three-pass transforms for L = 1536 (N = 769..1024): 24 (pruned) x 8 x 8 (paired) forward, 8 (paired) x 8 x 24 (pruned) inverse.
+// A line is 12 KB of shared memory per channel pair, so a CTA works on (line, group of G = 5 channel pairs) items: 64 G threads,
+// ping-pong buffers, the group's 40-byte (forward) / 80-byte (inverse) pieces of the line staged by cp.async one / two items ahead.
+template <int G> struct Fft3Cfg {
+  static constexpr int L = 1536, F = L / 2 + 1, NT = 64 * G;
+  static constexpr size_t BUF = (size_t)L * G * 8;
+  __host__ __device__ static size_t stage_fwd(int N) { return ((size_t)N * 2 * G * 4 + 127) & ~(size_t)127; }
+  static size_t smem_fwd(int N) { return (size_t)L * 8 + 2 * BUF + 2 * stage_fwd(N); }
+  static size_t smem_inv() { return (size_t)L * 8 + 2 * BUF + (size_t)F * 4 * G * 4; }
+};
+template <int G>
+__global__ void __launch_bounds__(64 * G, 1) spec_fft_fwd3_k(FftFwdArgs A) {
+  using Cfg = Fft3Cfg<G>;
+  constexpr int L = Cfg::L, NT = Cfg::NT;
+  extern __shared__ __align__(128) uint8_t fsm[];
+  __shared__ float s_g[64], s_c[64], s_b[2 * G], s_raw[2][2 * G];
+  const int N = A.N, C = A.C, NG = C / (2 * G);          // C is a multiple of 2G (checked by the launcher)
+  float2* tw = reinterpret_cast<float2*>(fsm);
+  float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
+  float2* bufB = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
+  float* stage0 = reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
+  const size_t sstride = Cfg::stage_fwd(N) / 4;
+  for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  const bool bn = A.gam != nullptr, shift = bn && A.bias0 != nullptr;
+  if (bn) for (int t = threadIdx.x; t < C; t += NT) {        // x <- relu(x s_g + s_c (+ line bias * s_g))
+    s_g[t] = A.gam[t] * BN_RS;
+    s_c[t] = shift ? fmaf(2.f * A.b0[t], A.gam[t] * BN_RS, A.bet[t]) : A.bet[t];
+  }
+  __syncthreads();
+  const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;
+  LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = N; walk.order = A.order;
+  const long long fstride = A.RA * A.KA;
+  // items it = (line index it / NG, group it % NG); iteration `it` transforms item it and, after its first pass, starts the copies of
+  // item it + 2 into the staging tile that pass has just freed (iterations -2, -1 only start the copies of items 0, 1)
+  for (long long it = -2;; ++it) {
+    const int slot = (int)(it & 1);
+    const long long it2 = it + 2, line2 = walk.at(it2 / NG), line = it >= 0 ? walk.at(it / NG) : -1;
+    const int grp = it >= 0 ? (int)(it % NG) : 0, grp2 = (int)(it2 % NG);
+    if (it >= 0) {
+      if (line >= A.lines) break;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      if (shift && threadIdx.x < 2 * G) s_b[threadIdx.x] = fmaf(s_raw[slot][threadIdx.x], s_g[2 * G * grp + threadIdx.x], s_c[2 * G * grp + threadIdx.x]);
+      __syncthreads();                       // staged piece and shift visible; the previous item's last pass is done with bufB
+      FpBn p; p.on = bn; p.gx = p.gy = 1.f; p.bx = p.by = 0.f;
+      if (bn) {
+        const int c = 2 * (G * grp + cp);
+        p.gx = s_g[c]; p.gy = s_g[c + 1];
+        p.bx = shift ? s_b[2 * cp] : s_c[c]; p.by = shift ? s_b[2 * cp + 1] : s_c[c + 1];
+      }
+      fp_fwd_pass1_t<8, G, 64>(reinterpret_cast<const float2*>(stage0 + slot * sstride), bufA, jb, cp, N, p);
+      __syncthreads();                       // bufA complete; this staging tile is free
+    }
+    if (line2 < A.lines) {                   // prefetch item it + 2: the group's 2G floats of every position
+      float* stage = stage0 + slot * sstride;
+      const float* base; long long ps = C;
+      if (line2 < A.lines0 || A.dir1_strided != 1) {
+        base = A.in + line2 * N * C;
+        if (A.dir1_strided == 2) {
+          const bool d1 = line2 >= A.lines0; const long long l1 = d1 ? line2 - A.lines0 : line2; const long long b = l1 / N; const int x = (int)(l1 - b * N);
+          base = (d1 ? A.in1 : A.in) + (((b / 128) * N + x) * 128 + (b % 128)) * N * C;
+        }
+      } else {
+        const long long l1 = line2 - A.lines0; const long long b = l1 / N; const int j = (int)(l1 - b * N);
+        base = A.in + (b * N * N + j) * C; ps = (long long)N * C;
+      }
+      base += 2 * G * grp2;
+      if (shift && threadIdx.x < 2 * G)
+        cp_async4(&s_raw[slot][threadIdx.x], (line2 >= A.lines0 ? A.bias1 + (line2 - A.lines0) * C : A.bias0 + line2 * C) + 2 * G * grp2 + threadIdx.x);
+      for (int pos = jb; pos < N; pos += 64) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
+    }
+    cp_async_commit();
+    if (it >= 0) {
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) fp_mid8<G, 24, 192, 8>(bufA, bufB, tw, jb + 64 * i, cp);
+      __syncthreads();                       // bufB complete
+      const int cg = G * grp + cp;           // channel pair of the whole line
+      SpecEmitFwd em; em.oh = A.oh + line * A.KA + 4 * cg; em.ol = A.ol + line * A.KA + 4 * cg; em.fstride = fstride; em.C = C;
+      em.padw = 2 * cg + 2 == C ? A.KA - 2 * C : 0;
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) { const int u = jb + 64 * i; if (u <= 96) fp_fwd_last_t<8, 192, G, true>(bufB, tw, u, cp, em); }
+    }
+  }
+  cp_async_wait_all();
+}
+template <int G>
+__global__ void __launch_bounds__(64 * G, 1) spec_fft_inv3_k(FftInvArgs A) {
+  using Cfg = Fft3Cfg<G>;
+  constexpr int L = Cfg::L, F = Cfg::F, NT = Cfg::NT;
+  extern __shared__ __align__(128) uint8_t fsm[];
+  float2* tw = reinterpret_cast<float2*>(fsm);
+  float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
+  float2* bufB = reinterpret_cast<float2*>(fsm + (size_t)L * 8 + Cfg::BUF);
+  float* stage = reinterpret_cast<float*>(fsm + (size_t)L * 8 + 2 * Cfg::BUF);
+  for (int t = threadIdx.x; t < L; t += NT) tw[t] = A.tw[t];
+  __syncthreads();
+  const int C = A.C, W = 2 * C, NG = C / (2 * G);
+  const float scale = 1.f / (float)L;
+  const int jb = threadIdx.x / G, cp = threadIdx.x - jb * G;
+  LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = A.N; walk.order = A.order;
+  // iteration `it` transforms item it = (line index it / NG, group it % NG); the rows of item it + 1 load under its passes 2 and 3
+  for (long long it = -1;; ++it) {
+    const long long line = it >= 0 ? walk.at(it / NG) : -1, next = walk.at((it + 1) / NG);
+    const int grp = it >= 0 ? (int)(it % NG) : 0, grpn = (int)((it + 1) % NG);
+    if (it >= 0) {
+      if (line >= A.lines) break;
+      cp_async_wait_all();
+      __syncthreads();                       // the item's rows have landed; the previous item's last pass is done with bufB
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) { const int u = jb + 64 * i; if (u <= 96) fp_inv_first_t<8, 192, G>(stage, bufA, u, cp); }
+      __syncthreads();                       // bufA complete; the staging area is free
+    }
+    if (next < A.lines) {                    // 16 bytes = one channel pair's [re, re, im, im] of one row
+      const float* src = A.in + ((long long)jb * A.RA + next) * W + 4 * (G * grpn + cp);
+      const long long fstep = 64LL * A.RA * W;
+      for (int f = jb; f < F; f += 64, src += fstep) cp_async16(stage + (f * G + cp) * 4, src);
+    }
+    cp_async_commit();
+    if (it >= 0) {
+#pragma unroll 1
+      for (int i = 0; i < 3; ++i) fp_mid8<G, 8, 192, 24>(bufA, bufB, tw, jb + 64 * i, cp);
+      __syncthreads();                       // bufB complete
+      const int cg = G * grp + cp;
+      SpecEmitInv dst; dst.base = A.out + line * A.N * C + 2 * cg; dst.pstride = C; dst.N = A.N; dst.scale = scale;
+      if (A.out1 && line >= A.lines0) {
+        const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
+        dst.base = A.out1 + (b * A.N * A.N + j) * C + 2 * cg; dst.pstride = A.N * C;
+      }
+      fp_inv_last_t<8, G, 64, false>(bufB, tw, jb, cp, dst);
+    }
+  }
+  cp_async_wait_all();
+}
+
 // ---- per-step weight spectra and GEMM operand staging -----------------------------------------------------------
 // G^[f][c][q] = sum_t w1[t][c][q] exp(-2 pi i f (p - t) / L)   (double accumulation over the exact table)
 //   fwd   B (K-major, [f][n][k], k < 128): n = q: (k=c: Gr, k=C1+c: -Gi);  n = C2+q: (k=c: Gi, k=C1+c: Gr)
@@ -1291,6 +1424,28 @@ static int spec_launch_inv2(SpecState& s, const FftInvArgs& a, cudaStream_t st) 
   spec_fft_inv2_k<M, G, MINB, TABLE><<<(unsigned)(units < want ? units : want), Cfg::NT, smem, st>>>(a);
   return 0;
 }
+template <int G>
+static int spec_launch_fwd3(SpecState& s, const FftFwdArgs& a, cudaStream_t st) {
+  using Cfg = Fft3Cfg<G>;
+  const size_t smem = Cfg::smem_fwd(a.N);
+  if (smem > 226 * 1024 || a.N > 1024 || a.C % (2 * G) != 0 || a.C > 64) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(spec_fft_fwd3_k<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
+  const long long want = s.grid_sms, units = a.order ? (a.lines + 1) / 2 : a.lines;
+  spec_fft_fwd3_k<G><<<(unsigned)(units < want ? units : want), Cfg::NT, smem, st>>>(a);
+  return 0;
+}
+template <int G>
+static int spec_launch_inv3(SpecState& s, const FftInvArgs& a, cudaStream_t st) {
+  using Cfg = Fft3Cfg<G>;
+  const size_t smem = Cfg::smem_inv();
+  if (smem > 226 * 1024 || a.N > 1024 || a.C % (2 * G) != 0) return 1;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(spec_fft_inv3_k<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); attr = true; }
+  const long long want = s.grid_sms, units = a.order ? (a.lines + 1) / 2 : a.lines;
+  spec_fft_inv3_k<G><<<(unsigned)(units < want ? units : want), Cfg::NT, smem, st>>>(a);
+  return 0;
+}
 static bool spec_plan_is(const FftPlan& pl, int r0, int r1, int r2) {
   return pl.npass == (r2 ? 3 : 2) && pl.rad[0] == r0 && pl.rad[1] == r1 && (!r2 || pl.rad[2] == r2);
 }
@@ -1309,6 +1464,7 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
     else if (s.pl.L == 384 && C == 20) r = spec_launch_fwd2<8, 10, 2, true>(s, a, st);      // (three CTAs per SM at 124 registers: 2.60 ms against 2.25)
     else if (s.pl.L == 192 && C == 50) r = spec_launch_fwd2<4, 25, 1, true>(s, a, st);
     else if (s.pl.L == 192 && C == 20) r = spec_launch_fwd2<4, 10, 2, true>(s, a, st);
+    else if (s.pl.L == 1536) r = spec_launch_fwd3<5>(s, a, st);                              // N = 769..1024
     if (r == 0) return tc_check_launch("spec_fft_fwd2_k");
   }
   if (!s.generic_only) {
@@ -1335,6 +1491,7 @@ static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, 
     else if (s.pl.L == 384 && C == 20) r = spec_launch_inv2<8, 10, 2, false>(s, a, st);
     else if (s.pl.L == 192 && C == 50) r = spec_launch_inv2<4, 25, 1, false>(s, a, st);
     else if (s.pl.L == 192 && C == 20) r = spec_launch_inv2<4, 10, 2, false>(s, a, st);
+    else if (s.pl.L == 1536) r = spec_launch_inv3<5>(s, a, st);
     if (r == 0) return tc_check_launch("spec_fft_inv2_k");
   }
   if (!s.generic_only && s.fft_inv2 && C == 50) {      // 3-pass plans at G = 25: split staging, extension fused into pass 1
