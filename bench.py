@@ -226,6 +226,13 @@ def stage_bytes(name, N, S, C1=50, C2=20):
         "epilogue": cells * (2 * 4 * C2 + 4 + 8 + 4 * C2),            # O12 + adj_truth read, int64 adjacency + dO written
         "gemm_dgrad": 4 * cells * C2 + lines * (2 * 8 * F * C2 + 2 * 8 * F * C1 + 4 * N * C1) + lines * 8 * F * (C1 + C2),  # fft(dO) + mix + ifft(dY) + wgrad
         "combine": cells * (2 * 4 * C1 + 4 * C1 + 2 * 4 * C1),        # dY12 + E1 read, dE1 hi/lo planes in both layouts written
+        # layer-0 dense backward: each of its four large GEMMs (da, dc, dWSa, dWSc) reads the hi + lo planes of one dE1 layout once
+        "l0_gemms": 4 * cells * 4 * C1,
+        # joint encoder (two SGC layers): 626 floats of forward activations per (sample, node) at the synthetic2 sizes,
+        # written by the forward pass and read by the products that consume them; the backward pass reads them again and moves
+        # gradient rows of the same shapes (approximate: intermediates of this factorization, not boundary I/O)
+        "sgc_fwd": 2 * 4 * 626 * S * N,
+        "sgc_bwd_act": 3 * 4 * 626 * S * N,
     }
     return t.get(name)
 
