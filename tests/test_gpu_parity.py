@@ -494,6 +494,28 @@ def test_fft_staging_variants_agree(built, N, B, S):
         assert _relmax(out[name][0], out["three_pass"][0]) < 5e-6, name
 
 
+def test_fft_three_pass_l1536_matches_runtime_plan(built):
+    """N = 1024 (L = 1536): the compile-time three-pass transforms (24 x 8 x 8 on (line, 5-channel-pair group) items, spec_fft_fwd3_k /
+    spec_fft_inv3_k) against the runtime-plan kernels they replace (SNDVAE_FFT_2PASS=0): logits, losses and dw1 agree to the rounding
+    of two FFT factorizations.  (Against the oracle: tests/test_gpu_configs.py::test_n1024_all_gradients_vs_oracle.)"""
+    N, B, S = 1024, 1, 2
+    cfg, P, inp, noise = _setup(N, B, S, "disentangled", dtype=torch.float32)
+    out = {}
+    for name, env in (("three_pass", {}), ("runtime_plan", {"SNDVAE_FFT_2PASS": "0"})):
+        os.environ.update(env)
+        try:
+            eng = _engine(built, N, B, S, "disentangled", 2, chunk=1)
+        finally:
+            for k in env: os.environ.pop(k, None)
+        eng.set_params(P)
+        r = eng.grads(inp, noise, fetch=("generated_adj_prob",))
+        out[name] = (r["generated_adj_prob"].cpu().numpy(), np.asarray(r["overall_loss"]), eng.get_grads()["decoder/e1_deconv/w1"].numpy())
+        eng.close()
+    assert _relmax(out["three_pass"][0], out["runtime_plan"][0]) < 2e-5
+    np.testing.assert_allclose(out["three_pass"][1], out["runtime_plan"][1], rtol=2e-5)
+    assert _relmax(out["three_pass"][2], out["runtime_plan"][2]) < 1e-4
+
+
 @pytest.mark.parametrize("B,N,hd", [(3, 9, 5), (2, 100, 20), (2, 256, 40), (1, 300, 100), (2, 131, 72)])
 def test_inner_product_decoder(built, B, N, hd):
     """InnerProductDecoder (layers.py:400-410; standalone operator, not used by the reference's models): z z^T per graph on
