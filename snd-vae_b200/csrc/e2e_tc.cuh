@@ -90,6 +90,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// The same two instructions for a warp that runs its issue loop CONVERGED (all 32 lanes, warp-uniform operands): the election sits
+// inside the asm statement, so the compiler keeps descriptors, TMEM addresses and barrier addresses in uniform registers and emits one
+// predicated UTCHMMA -- under `if (lane == 0)` it has to move every operand into uniform registers (R2UR) and wrap each instruction in an
+// ELECT / BRA.U.ANY loop.  Measured (tools/mma_probe.cu): 73 instead of 83 cycles per back-to-back MMA with nothing else in the loop; the
+// scalar work between the MMAs is what the short-N products of this library are bound by (~180 cycles per MMA before).
+__device__ __forceinline__ void umma_bf16_conv(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_conv(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "elect.sync _|q, 0xffffffff;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -1169,18 +1169,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {     // the whole warp runs the issue loop converged (umma_bf16_conv elects the issuing lane); ring slot and phase by counters
       constexpr uint32_t idesc = umma_idesc(128, SP_NF, 1, 1);
-      int it = 0, gcount = 0;
+      int s = 0, gcount = 0; uint32_t ph = 0;
       for (long long u = u0; u < u1; ++u) {
         const int ks = (int)(u % P.KS);
         const long long c_lo = (long long)ks * cper; long long c_hi = c_lo + cper; if (c_hi > kchunks) c_hi = kchunks;
         const int nk = c_hi > c_lo ? (int)(c_hi - c_lo) : 0;
-        for (int i = 0; i < nk; ++i, ++it) {
+        for (int i = 0; i < nk; ++i) {
           const int gi = i % SP_WGROUP;
           const int slot = gcount & 1;
           if (gi == 0) { mbar_wait(&acc_empty[slot], ((gcount >> 1) & 1) ^ 1); tc_fence_after(); }
-          const int s = it % P.stages; const uint32_t ph = (it / P.stages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
@@ -1192,12 +1191,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_wgrad_k(const __grid_const
             const uint64_t bh = umma_desc_sw128(sa + 2 * A_PLANE + k * 2048, BLK, 1024);
             const uint64_t bl = umma_desc_sw128(sa + 2 * A_PLANE + B_PLANE + k * 2048, BLK, 1024);
             const uint32_t td = td0 + (k & 1) * 64;      // two independent chains: no back-to-back accumulates into one tile
-            umma_bf16(td, ah, bh, idesc, (gi | (k >> 1)) ? 1u : 0u);
-            umma_bf16(td, ah, bl, idesc, 1u);
-            umma_bf16(td, al, bh, idesc, 1u);
+            umma_bf16_conv(td, ah, bh, idesc, (gi | (k >> 1)) ? 1u : 0u);
+            umma_bf16_conv(td, ah, bl, idesc, 1u);
+            umma_bf16_conv(td, al, bh, idesc, 1u);
           }
-          umma_commit(&empty_bar[s]);
-          if (gi == SP_WGROUP - 1 || i == nk - 1) { umma_commit(&acc_full[slot]); ++gcount; }
+          umma_commit_conv(&empty_bar[s]);
+          if (gi == SP_WGROUP - 1 || i == nk - 1) { umma_commit_conv(&acc_full[slot]); ++gcount; }
+          if (++s == P.stages) { s = 0; ph ^= 1; }
         }
       }
     }
