@@ -611,7 +611,9 @@ __global__ void __launch_bounds__(NT, MINB) spec_fft_inv_fast2_k(FftInvArgs A) {
 
 // ---- two-pass transforms (fft2p.cuh): L = 48 M as (3M) x 16 forward / 16 x (3M) inverse, 16 G threads ---------------------
 template <int M, int G> struct Fft2Cfg {
-  static constexpr int L = 48 * M, F = L / 2 + 1, NT = 16 * G;
+  // JB = butterfly slots per channel pair.  L = 384: 16 (pass 1 has 16 butterflies, the paired pass 13 units).  L = 192: the paired pass
+  // has only 7 units, so 8 slots (the 16 butterflies of the other pass take two rounds) and twice the CTAs per SM instead of 9 idle slots.
+  static constexpr int L = 48 * M, F = L / 2 + 1, JB = M == 4 ? 8 : 16, NT = JB * G;
   static constexpr size_t BUF = (size_t)L * G * 8;
   __host__ __device__ static size_t stage_fwd(int N) { return ((size_t)N * 2 * G * 4 + 127) & ~(size_t)127; }
   static size_t smem_fwd(int N) { return (size_t)L * 8 + BUF + 2 * stage_fwd(N); }
@@ -629,9 +631,9 @@ struct SpecEmitFwd {                   // X1 / X2 of a frequency -> bf16 hi / lo
   }
 };
 template <int M, int G, int MINB, bool TABLE>
-__global__ void __launch_bounds__(16 * G, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
+__global__ void __launch_bounds__(Fft2Cfg<M, G>::NT, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
   using Cfg = Fft2Cfg<M, G>;
-  constexpr int L = Cfg::L, C = 2 * G, NT = Cfg::NT, R0 = 3 * M;
+  constexpr int L = Cfg::L, C = 2 * G, NT = Cfg::NT, R0 = 3 * M, JB = Cfg::JB;
   extern __shared__ __align__(128) uint8_t fsm[];
   __shared__ float s_g[C], s_b[C], s_raw[2][C];
   __shared__ uint64_t stage_bar[2];          // completion of a contiguous line's bulk copy into staging tile 0 / 1
@@ -667,7 +669,8 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
       __syncthreads();                       // staged line and shift visible; the previous line's pass 2 is done with bufA
       FpBn bn; bn.on = A.gam != nullptr; bn.gx = bn.gy = 1.f; bn.bx = bn.by = 0.f;
       if (bn.on) { bn.gx = s_g[2 * cp]; bn.gy = s_g[2 * cp + 1]; bn.bx = s_b[2 * cp]; bn.by = s_b[2 * cp + 1]; }
-      fp_fwd_pass1<M, G>(reinterpret_cast<const float2*>(stage0 + slot * sstride), bufA, jb, cp, N, bn);
+#pragma unroll 1
+      for (int j = jb; j < 16; j += JB) fp_fwd_pass1<M, G>(reinterpret_cast<const float2*>(stage0 + slot * sstride), bufA, j, cp, N, bn);
       __syncthreads();                       // bufA complete; this staging tile is free
     }
     if (line2 < A.lines) {                   // prefetch line it + 2
@@ -689,7 +692,7 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_fwd2_k(FftFwdArgs A) {
           constexpr int Q = G / 2;
           for (int t = threadIdx.x; t < N * Q; t += NT) { const int pos = t / Q, k = t - pos * Q; cp_async16(stage + pos * C + 4 * k, base + pos * ps + 4 * k); }
         } else {
-          for (int pos = jb; pos < N; pos += 16) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
+          for (int pos = jb; pos < N; pos += JB) cp_async8(stage + 2 * (pos * G + cp), base + pos * ps + 2 * cp);
         }
       }
     }
@@ -709,9 +712,9 @@ struct SpecEmitInv {                   // inverse tail: (re, im) swapped back, s
   }
 };
 template <int M, int G, int MINB, bool TABLE>
-__global__ void __launch_bounds__(16 * G, MINB) spec_fft_inv2_k(FftInvArgs A) {
+__global__ void __launch_bounds__(Fft2Cfg<M, G>::NT, MINB) spec_fft_inv2_k(FftInvArgs A) {
   using Cfg = Fft2Cfg<M, G>;
-  constexpr int L = Cfg::L, F = Cfg::F, C = 2 * G, W = 4 * G, NT = Cfg::NT, R1 = 3 * M;
+  constexpr int L = Cfg::L, F = Cfg::F, C = 2 * G, W = 4 * G, NT = Cfg::NT, R1 = 3 * M, JB = Cfg::JB;
   extern __shared__ __align__(128) uint8_t fsm[];
   float2* tw = reinterpret_cast<float2*>(fsm);
   float2* bufA = reinterpret_cast<float2*>(fsm + (size_t)L * 8);
@@ -731,8 +734,8 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_inv2_k(FftInvArgs A) {
       return;
     }
     const float* src = A.in + ((long long)jb * A.RA + line) * W + 4 * cp;     // 16 bytes = two channel pairs' worth of one half row
-    const long long fstep = 16LL * A.RA * W;
-    for (int f = jb; f < F; f += 16, src += fstep) cp_async16(stage + f * W + 4 * cp, src);
+    const long long fstep = (long long)JB * A.RA * W;
+    for (int f = jb; f < F; f += JB, src += fstep) cp_async16(stage + f * W + 4 * cp, src);
   };
   LineWalk walk; walk.lines = A.lines; walk.lines0 = A.lines0; walk.N = A.N; walk.order = A.order;
   long long line = walk.at(0);
@@ -751,7 +754,8 @@ __global__ void __launch_bounds__(16 * G, MINB) spec_fft_inv2_k(FftInvArgs A) {
       const long long l1 = line - A.lines0; const long long b = l1 / A.N; const int j = (int)(l1 - b * A.N);
       dst.base = A.out1 + (b * A.N * A.N + j) * C + 2 * cp; dst.pstride = A.N * C;
     }
-    fp_inv_pass2<M, G, TABLE>(bufA, tw, jb, cp, dst);
+#pragma unroll 1
+    for (int k = jb; k < 16; k += JB) fp_inv_pass2<M, G, TABLE>(bufA, tw, k, cp, dst);
     line = next;
   }
   cp_async_wait_all();
@@ -1462,8 +1466,8 @@ static int spec_fft_fwd(SpecState& s, const float* in, const float* in1, long lo
   if (!s.generic_only && (s.fft_2pass & 1)) {      // twiddles from the table (measured: forward Y 5.32 -> 4.95 ms against the product chain)
     if (s.pl.L == 384 && C == 50) r = spec_launch_fwd2<8, 25, 1, true>(s, a, st);
     else if (s.pl.L == 384 && C == 20) r = spec_launch_fwd2<8, 10, 2, true>(s, a, st);      // (three CTAs per SM at 124 registers: 2.60 ms against 2.25)
-    else if (s.pl.L == 192 && C == 50) r = spec_launch_fwd2<4, 25, 1, true>(s, a, st);
-    else if (s.pl.L == 192 && C == 20) r = spec_launch_fwd2<4, 10, 2, true>(s, a, st);
+    else if (s.pl.L == 192 && C == 50) r = spec_launch_fwd2<4, 25, 2, true>(s, a, st);
+    else if (s.pl.L == 192 && C == 20) r = spec_launch_fwd2<4, 10, 4, true>(s, a, st);
     else if (s.pl.L == 1536) r = spec_launch_fwd3<5>(s, a, st);                              // N = 769..1024
     if (r == 0) return tc_check_launch("spec_fft_fwd2_k");
   }
@@ -1489,8 +1493,8 @@ static int spec_fft_inv(SpecState& s, const float* in, float* out, float* out1, 
   if (!s.generic_only && (s.fft_2pass & 2)) {      // twiddles by product chain (measured: inverse dY 3.70 ms against 3.77 with table reads)
     if (s.pl.L == 384 && C == 50) r = spec_launch_inv2<8, 25, 1, false>(s, a, st);
     else if (s.pl.L == 384 && C == 20) r = spec_launch_inv2<8, 10, 2, false>(s, a, st);
-    else if (s.pl.L == 192 && C == 50) r = spec_launch_inv2<4, 25, 1, false>(s, a, st);
-    else if (s.pl.L == 192 && C == 20) r = spec_launch_inv2<4, 10, 2, false>(s, a, st);
+    else if (s.pl.L == 192 && C == 50) r = spec_launch_inv2<4, 25, 2, false>(s, a, st);
+    else if (s.pl.L == 192 && C == 20) r = spec_launch_inv2<4, 10, 4, false>(s, a, st);
     else if (s.pl.L == 1536) r = spec_launch_inv3<5>(s, a, st);
     if (r == 0) return tc_check_launch("spec_fft_inv2_k");
   }
