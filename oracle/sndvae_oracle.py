@@ -15,7 +15,7 @@ internal: (1) a *literal* restatement that materialises what TF materialises,
 (2) an independent *factored* restatement, (1)==(2) to 1e-12 in fp64 (and a third form, mode "fft": the width-N
 correlations through torch.fft, == (2) to 1e-12, which is what scales to N = 1024 on a CPU),
 (3) autograd == central finite differences, (4) seeded golden vectors under
-tests/golden/ made by oracle/make_golden.py.
+tests/golden/ made by tests/golden/make_golden.py.
 
 Reference lines followed (file:line into /root/reference):
   lrelu                         layers.py:112-113
